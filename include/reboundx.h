@@ -1,0 +1,173 @@
+/*
+ * reboundx.h -- public C API of the B200-native drop-in for REBOUNDx's force path.
+ *
+ * This header re-declares, from scratch, the part of REBOUNDx 5.1.0's C API that the
+ * `rebx_additional_forces` hot path and its set-up calls need.  Struct layouts and enum
+ * values are ABI: the reference's ctypes wrapper mirrors them field for field
+ * (reference reboundx/extras.py:251-258,319-333,376-381; reboundx/tools.py:4), so user C
+ * code and the unmodified Python wrapper bind to this library exactly as they bind to the
+ * reference's libreboundx.  Each declaration cites the reference declaration it replaces.
+ *
+ * Out of scope: operators, splitting integrators, binary I/O,
+ * interpolation and the other built-in forces.  Their declarations are intentionally
+ * absent; a custom force (user function pointer) still runs on the host through the same
+ * dispatcher.
+ */
+#ifndef REBOUNDX_B200_REBOUNDX_H
+#define REBOUNDX_B200_REBOUNDX_H
+
+#include <stdint.h>
+#include "rebound.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* reference src/reboundx.h:49 */
+#define AP_PTR(p) ((struct rebx_node**)&(p).ap)
+
+/* reference src/reboundx.h:50-52 / src/core.c:41-43 (read by reboundx/__init__.py:19-26) */
+extern const char* rebx_build_str;
+extern const char* rebx_version_str;
+extern const char* rebx_githash_str;
+
+/* reference src/reboundx.h:61-72 */
+enum rebx_param_type {
+    REBX_TYPE_NONE    = 0,
+    REBX_TYPE_DOUBLE  = 1,
+    REBX_TYPE_INT     = 2,
+    REBX_TYPE_POINTER = 3,
+    REBX_TYPE_FORCE   = 4,
+    REBX_TYPE_UINT32  = 5,
+    REBX_TYPE_ORBIT   = 6,
+    REBX_TYPE_ODE     = 7,
+    REBX_TYPE_VEC3D   = 8,
+    REBX_TYPE_STRING  = 9
+};
+
+/* reference src/reboundx.h:77-81 */
+enum REBX_COORDINATES {
+    REBX_COORDINATES_JACOBI      = 0,
+    REBX_COORDINATES_BARYCENTRIC = 1,
+    REBX_COORDINATES_PARTICLE    = 2
+};
+
+/* reference src/reboundx.h:94-98 */
+enum rebx_force_type {
+    REBX_FORCE_NONE = 0,
+    REBX_FORCE_POS  = 1,   /* derivable from a position-only potential */
+    REBX_FORCE_VEL  = 2    /* depends on velocities */
+};
+
+/* reference src/reboundx.h:194-197 */
+struct rebx_node {
+    void* object;
+    struct rebx_node* next;
+};
+
+/* reference src/reboundx.h:203-207 */
+struct rebx_param {
+    char* name;
+    enum rebx_param_type type;
+    void* value;
+};
+
+/* reference src/reboundx.h:213-223.  Exactly seven pointers: Python allocates this struct
+ * itself (extras.py:39-45,327-333), so no field may be added -- all device state lives in
+ * a side table keyed by the address of this struct. */
+struct rebx_extras {
+    struct reb_simulation* sim;
+    struct rebx_node* additional_forces;
+    struct rebx_node* pre_timestep_modifications;
+    struct rebx_node* post_timestep_modifications;
+    struct rebx_node* registered_params;
+    struct rebx_node* allocated_forces;
+    struct rebx_node* allocated_operators;
+};
+
+/* reference src/reboundx.h:228-236 */
+struct rebx_force {
+    char* name;
+    struct rebx_node* ap;
+    struct reb_simulation* sim;
+    enum rebx_force_type force_type;
+    void (*update_accelerations)(struct reb_simulation* const sim, struct rebx_force* const force,
+                                 struct reb_particle* const particles, const int N);
+    void (*free_memory)(struct rebx_extras* rebx, struct rebx_force* const force);
+};
+
+/* ---- attach / free: reference src/reboundx.h:294-304, src/core.h:37-38 ---------------- */
+struct rebx_extras* rebx_attach(struct reb_simulation* sim);
+void rebx_initialize(struct reb_simulation* sim, struct rebx_extras* rebx);
+void rebx_register_default_params(struct rebx_extras* rebx);
+void rebx_detach(struct rebx_extras* rebx);
+void rebx_extras_cleanup(struct reb_simulation* sim);
+void rebx_free(struct rebx_extras* rebx);
+void rebx_free_pointers(struct rebx_extras* rebx);
+
+/* ---- forces: reference src/reboundx.h:306,355-359,385 --------------------------------- */
+struct rebx_force* rebx_create_force(struct rebx_extras* const rebx, const char* name);
+struct rebx_force* rebx_load_force(struct rebx_extras* const rebx, const char* name);
+int rebx_add_force(struct rebx_extras* rebx, struct rebx_force* force);
+int rebx_remove_force(struct rebx_extras* rebx, struct rebx_force* force);
+struct rebx_force* rebx_get_force(struct rebx_extras* const rebx, const char* const name);
+
+/* ---- parameters: reference src/reboundx.h:427-435,631, src/core.h:100-106 -------------- */
+void  rebx_register_param(struct rebx_extras* const rebx, const char* name, enum rebx_param_type type);
+enum rebx_param_type rebx_get_type(struct rebx_extras* rebx, const char* name);
+void* rebx_get_param(struct rebx_extras* const rebx, struct rebx_node* ap, const char* const param_name);
+struct rebx_param* rebx_get_param_struct(struct rebx_extras* const rebx, struct rebx_node* ap, const char* const param_name);
+struct rebx_param* rebx_get_or_add_param(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name);
+void rebx_set_param_pointer(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name, void* val);
+void rebx_set_param_double(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name, double val);
+void rebx_set_param_int(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name, int val);
+void rebx_set_param_uint32(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name, uint32_t val);
+void rebx_set_param_vec3d(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name, struct reb_vec3d val);
+void rebx_set_param_string(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name, const char* const val);
+struct rebx_param* rebx_create_param(struct rebx_extras* rebx, const char* name, enum rebx_param_type type);
+int  rebx_add_param(struct rebx_extras* const rebx, struct rebx_node** apptr, struct rebx_param* param);
+struct rebx_node* rebx_create_node(struct rebx_extras* rebx);
+
+/* ---- lists and memory: reference src/linkedlist.h:34-57, src/core.h:90-98 --------------- */
+void rebx_add_node(struct rebx_node** head, struct rebx_node* node);
+int  rebx_remove_node(struct rebx_node** head, void* object);
+int  rebx_len(struct rebx_node* head);
+void* rebx_malloc(struct rebx_extras* const rebx, size_t memsize);
+void rebx_free_ap(struct rebx_node** ap);
+void rebx_free_particle_ap(struct reb_particle* p);
+void rebx_free_force(struct rebx_extras* rebx, struct rebx_force* force);
+void rebx_free_param(struct rebx_param* param);
+void rebx_error(struct rebx_extras* rebx, const char* const msg);
+void rebx_reset_accelerations(struct reb_particle* const ps, const int N);
+
+/* ---- the hot path --------------------------------------------------------------------- */
+/* Dispatcher installed as sim->additional_forces: reference src/core.c:1026-1041. */
+void rebx_additional_forces(struct reb_simulation* sim);
+
+/* Plug-in entry points with the reference's force signature (src/reboundx.h:234); each one
+ * replaces the host loop of the same name (prototypes: reference src/core.h:59-75). */
+void rebx_radiation_forces(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);        /* src/radiation_forces.c:100 */
+void rebx_gravitational_harmonics(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N); /* src/gravitational_harmonics.c:136 */
+void rebx_gr_potential(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);            /* src/gr_potential.c:80 */
+void rebx_yarkovsky_effect(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);        /* src/yarkovsky_effect.c:218 */
+void rebx_modify_orbits_forces(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);    /* src/modify_orbits_forces.c:130 */
+void rebx_gas_damping_timescale(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);   /* src/gas_damping_timescale.c:132 */
+void rebx_modify_orbits_with_type_I_migration(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N); /* src/type_I_migration.c:205 */
+
+/* Host scalar helpers: reference src/reboundx.h:497,510; src/inner_disk_edge.c:61 */
+double rebx_rad_calc_beta(const double G, const double c, const double source_mass, const double source_luminosity, const double radius, const double density, const double Q_pr);
+double rebx_rad_calc_particle_radius(const double G, const double c, const double source_mass, const double source_luminosity, const double beta, const double density, const double Q_pr);
+double rebx_calculate_planet_trap(const double r, const double dedge, const double hedge);
+
+/* ---- additions of this build (all keep the rebx_ prefix, reference .github/workflows/c.yml:34) */
+/* Tell the SoA parameter tables that a value was changed through a raw pointer obtained
+ * from rebx_get_param (the API setters mark the tables dirty themselves). */
+void rebx_mark_params_dirty(struct rebx_extras* rebx);
+/* Bulk ingest: sets `param_name` on particles[index[k]] (index==NULL => k) for k<n. */
+void rebx_set_param_double_array(struct rebx_extras* const rebx, const char* const param_name, const int64_t* index, const double* val, size_t n);
+void rebx_set_param_int_array(struct rebx_extras* const rebx, const char* const param_name, const int64_t* index, const int* val, size_t n);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REBOUNDX_B200_REBOUNDX_H */

@@ -1,0 +1,139 @@
+/*
+ * rebx_b200.h -- thin C-ABI device layer under the REBOUNDx force dispatcher.
+ *
+ * Plain pointers and sizes only: every `const double*` below is a DEVICE pointer into HBM
+ * unless it says "host".  The layer is what the host dispatcher in
+ * reboundx_b200/csrc/dispatch.cpp calls per force evaluation, and what a resident-state
+ * caller (bench.py, a device integrator) calls directly with its own buffers and stream.
+ *
+ * One "pass" streams the particle state of one shard once and applies up to
+ * REBX_B200_MAX_EFFECTS stacked effects in list order, i.e. it replaces that many
+ * consecutive iterations of the reference's dispatch loop (src/core.c:1031-1040) and the
+ * per-particle rebx_get_param walks inside each effect (src/core.c:725-746) by SoA
+ * parameter tables.
+ */
+#ifndef REBX_B200_H
+#define REBX_B200_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REBX_B200_MAX_EFFECTS   4
+#define REBX_B200_BODY_DOUBLES  24
+#define REBX_B200_MAX_TABLES    9
+#define REBX_B200_MAX_SCALARS   8
+
+/* "parameter absent on this particle" marker inside a double table: a quiet NaN with a
+ * private payload, compared bit-wise (a NaN produced by arithmetic never has it). */
+#define REBX_B200_ABSENT_BITS   0x7ff8b200dead0001ULL
+
+/* Effect kinds; the comment names the reference loop each one replaces. */
+enum rebx_b200_kind {
+    REBX_B200_NONE            = 0,
+    REBX_B200_RADIATION       = 1,  /* src/radiation_forces.c:69-98   */
+    REBX_B200_HARMONICS       = 2,  /* src/gravitational_harmonics.c:184-224 (one oblate body per entry) */
+    REBX_B200_GR_POTENTIAL    = 3,  /* src/gr_potential.c:60-78       */
+    REBX_B200_YARKOVSKY       = 4,  /* src/yarkovsky_effect.c:76-216  */
+    REBX_B200_MODIFY_ORBITS   = 5,  /* src/modify_orbits_forces.c:77-128 under src/rebxtools.c:66-147 */
+    REBX_B200_GAS_DAMPING     = 6,  /* src/gas_damping_timescale.c:67-130 under rebx_com_force */
+    REBX_B200_TYPE_I          = 7,  /* src/type_I_migration.c:115-203 under rebx_com_force */
+    REBX_B200_KIND_COUNT      = 8
+};
+
+/* Body record (REBX_B200_BODY_DOUBLES doubles, device memory): the source / primary /
+ * oblate body an effect entry refers to.  Slots:
+ *   0      global particle index of the body (stored as a double), or -1 for a pure
+ *          reference frame that is no particle (barycentre)
+ *   1..3   x y z     4..6  vx vy vz     7  m
+ *   HARMONICS only: 8 J2, 9 J4 (0 when unset), 10 R_eq, 11..13 u-hat, 14..16 v-hat, 17..19 w-hat
+ */
+enum { REBX_B200_BODY_INDEX = 0, REBX_B200_BODY_X = 1, REBX_B200_BODY_VX = 4, REBX_B200_BODY_M = 7,
+       REBX_B200_BODY_J2 = 8, REBX_B200_BODY_J4 = 9, REBX_B200_BODY_REQ = 10,
+       REBX_B200_BODY_U = 11, REBX_B200_BODY_V = 14, REBX_B200_BODY_W = 17 };
+
+/* effect.flags bits */
+#define REBX_B200_FLAG_TRAP        1   /* MODIFY_ORBITS: ide_position and ide_width both set */
+#define REBX_B200_FLAG_BARYCENTRIC 2   /* damping trio: body = barycentre, mass ratio m/M */
+
+/* SoA view of one shard of particle state resident in HBM. */
+typedef struct rebx_b200_state {
+    int64_t n;                 /* particles in the shard */
+    int64_t index_base;        /* global particle index of element 0 */
+    const double *x, *y, *z;
+    const double *vx, *vy, *vz;   /* may be NULL when no effect in the pass reads velocities */
+    const double *m;              /* may be NULL likewise */
+    const double *r;              /* particle radius (yarkovsky only) */
+    double *ax, *ay, *az;         /* read-modify-write: a += force */
+} rebx_b200_state;
+
+/* One stacked effect.  Per-kind meaning of tab[] / scal[]:
+ *   RADIATION     tab0 beta                                   scal0 G, scal1 c
+ *   HARMONICS     -                                           scal0 G
+ *   GR_POTENTIAL  -                                           scal0 G, scal1 c*c
+ *   YARKOVSKY     tab0 ye_body_density tab1 ye_rotation_period tab2 ye_thermal_inertia
+ *                 tab3 ye_albedo tab4 ye_emissivity tab5 ye_k tab6..8 ye_spin_axis_x/y/z
+ *                 itab: ye_flag code (-1,0,1 valid; 2 = skip)  scal0 G, scal1 ye_lstar,
+ *                 scal2 ye_c, scal3 ye_stef_boltz
+ *   MODIFY_ORBITS tab0 tau_a tab1 tau_e tab2 tau_inc            scal0 G, scal1 ide_position, scal2 ide_width
+ *   GAS_DAMPING   tab0 d_factor                                 scal0 G, scal1 cs_coeff, scal2 tau_coeff
+ *   TYPE_I        -                                             scal0 G, scal1 tIm_flaring_index, scal2 tIm_scale_height_1,
+ *                                                               scal3 tIm_surface_density_1, scal4 tIm_surface_density_exponent,
+ *                                                               scal5 ide_position, scal6 ide_width
+ * Tables are indexed like the state arrays (element k <-> global index index_base+k);
+ * an unset double parameter holds REBX_B200_ABSENT_BITS. */
+typedef struct rebx_b200_effect {
+    int32_t kind;
+    int32_t flags;
+    const double* body;                       /* REBX_B200_BODY_DOUBLES doubles */
+    const double* tab[REBX_B200_MAX_TABLES];
+    const int32_t* itab;
+    double scal[REBX_B200_MAX_SCALARS];
+    double* backreaction;   /* 3 doubles: signed sum of the back-reaction terms this shard puts on
+                               `body` (add it to the body's acceleration), or NULL to discard */
+} rebx_b200_effect;
+
+typedef struct rebx_b200_pass {
+    rebx_b200_state st;
+    int32_t n_effects;
+    int32_t reserved;
+    rebx_b200_effect fx[REBX_B200_MAX_EFFECTS];   /* applied in array order */
+} rebx_b200_pass;
+
+/* Layout of the host AoS particle record (taken from whichever rebound.h was compiled in). */
+typedef struct rebx_b200_aos_layout {
+    int32_t stride;                                   /* sizeof(struct reb_particle) */
+    int32_t off_x, off_v, off_a, off_m, off_r;        /* byte offsets of x, vx, ax, m, r */
+} rebx_b200_aos_layout;
+
+/* ---- device management --------------------------------------------------------------- */
+int  rebx_b200_device_count(void);                       /* 0 when no usable CUDA device */
+const char* rebx_b200_error_string(int code);            /* text for a non-zero return code */
+size_t rebx_b200_workspace_bytes(void);                  /* scratch a pass launch needs */
+int  rebx_b200_sm_count(int device);
+
+/* ---- kernels (all asynchronous on `stream`, a cudaStream_t passed as void*) ------------ */
+/* Streams the shard once and applies pass->fx[0..n_effects) in order.  `workspace` is
+ * device scratch of rebx_b200_workspace_bytes().  Returns 0 or a cudaError_t value.
+ * `launches` (host, may be NULL) is incremented by the number of kernels launched. */
+int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* stream, int* launches);
+
+/* a[index - index_base] += backreaction for each effect whose body lies inside the shard. */
+int rebx_b200_apply_backreaction(const rebx_b200_pass* pass, void* stream, int* launches);
+
+/* Barycentric second sweep: a[k] += delta[0..2] for every particle in the shard. */
+int rebx_b200_add_uniform(const rebx_b200_state* st, const double* delta, void* stream, int* launches);
+
+/* AoS <-> SoA staging for the host-facing path (device-side transposes of one chunk). */
+int rebx_b200_unpack_aos(const void* aos, const rebx_b200_aos_layout* layout, const rebx_b200_state* st_out_as_mutable,
+                         void* stream, int* launches);
+int rebx_b200_pack_acc_aos(void* aos, const rebx_b200_aos_layout* layout, const rebx_b200_state* st,
+                           void* stream, int* launches);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REBX_B200_H */

@@ -1,0 +1,704 @@
+// dispatch.cpp -- the force dispatcher and its host<->device staging.
+//
+// Replaces, behind the unchanged plug-in signature (reference src/reboundx.h:234), the
+// reference's per-evaluation work:
+//   * rebx_additional_forces (src/core.c:1026-1041): walk the LIFO force list, warn, call
+//     each force.  Here maximal runs of device-backed forces become ONE fused sweep.
+//   * the per-particle rebx_get_param list walks inside every effect (src/core.c:725-746):
+//     replaced by SoA parameter tables in HBM, rebuilt only when the owning extras'
+//     generation counter says a parameter may have changed.
+//   * the per-particle arithmetic: CUDA kernels behind include/rebx_b200.h.
+// There is NO host arithmetic fallback: without a CUDA device every built-in force raises
+// a REBOUND error and leaves the accelerations untouched.
+#include <cuda_runtime.h>
+
+#include <algorithm>
+#include <climits>
+#include <cmath>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <thread>
+
+#include "internal.h"
+
+namespace rebxh {
+
+// ---- small RAII helpers ------------------------------------------------------------------
+struct DevBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFree(p); p = nullptr; cap = 0; }
+        const size_t want = (bytes + 255) & ~size_t(255);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want; else p = nullptr;
+        return e;
+    }
+    ~DevBuf() { if (p) cudaFree(p); }
+    DevBuf() = default;
+    DevBuf(const DevBuf&) = delete;
+    DevBuf& operator=(const DevBuf&) = delete;
+};
+
+struct PinnedBuf {
+    void* p = nullptr;
+    size_t cap = 0;
+    cudaError_t ensure(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) { cudaFreeHost(p); p = nullptr; cap = 0; }
+        cudaError_t e = cudaMallocHost(&p, bytes);
+        if (e == cudaSuccess) cap = bytes; else p = nullptr;
+        return e;
+    }
+    ~PinnedBuf() { if (p) cudaFreeHost(p); }
+    PinnedBuf() = default;
+    PinnedBuf(const PinnedBuf&) = delete;
+    PinnedBuf& operator=(const PinnedBuf&) = delete;
+};
+
+static inline bool is_absent(double v) {
+    unsigned long long bits;
+    std::memcpy(&bits, &v, sizeof bits);
+    return bits == REBX_B200_ABSENT_BITS;
+}
+
+static double absent_value() {
+    const unsigned long long bits = REBX_B200_ABSENT_BITS;
+    double d;
+    std::memcpy(&d, &bits, sizeof d);
+    return d;
+}
+
+// ---- SoA parameter tables of one force ------------------------------------------------------
+struct Oblate { double J2, J4, Req, u[3], v[3], w[3]; };
+
+struct ForceTables {
+    int kind = 0;
+    std::uint64_t gen = 0, epoch = 0;
+    size_t N = 0;
+    bool valid = false, uploaded = false;
+    std::vector<double> h[REBX_B200_MAX_TABLES];
+    std::vector<int32_t> hi;
+    DevBuf d[REBX_B200_MAX_TABLES];
+    DevBuf di;
+    std::vector<int64_t> bodies;     // RADIATION: sources; HARMONICS: oblate bodies; damping trio: first "primary"
+    std::vector<Oblate> oblate;
+    int64_t n_incomplete = 0;        // particles whose parameter set the reference would report as incomplete
+};
+
+struct Stats {
+    std::uint64_t calls = 0, launches = 0, h2d_bytes = 0, d2h_bytes = 0, table_builds = 0;
+};
+
+struct DeviceContext {
+    int device = 0;
+    bool ready = false;
+    cudaStream_t stream[2] = {nullptr, nullptr};
+    cudaEvent_t bodies_ready = nullptr;
+    DevBuf aos[2], soa[2], work[2], bodies, br;
+    PinnedBuf bodies_h, br_h;
+    std::unordered_map<struct rebx_force*, std::unique_ptr<ForceTables>> tables;
+    void* registered_ptr = nullptr;
+    size_t registered_bytes = 0;
+    Stats stats;
+    size_t chunk = size_t(1) << 20;
+    bool paranoid = false;
+
+    void unregister_host() {
+        if (registered_ptr) { cudaHostUnregister(registered_ptr); cudaGetLastError(); }
+        registered_ptr = nullptr; registered_bytes = 0;
+    }
+    ~DeviceContext() {
+        if (ready) {
+            cudaSetDevice(device);
+            for (auto& s : stream) if (s) { cudaStreamSynchronize(s); }
+        }
+        unregister_host();
+        tables.clear();
+        if (bodies_ready) cudaEventDestroy(bodies_ready);
+        for (auto& s : stream) if (s) cudaStreamDestroy(s);
+    }
+};
+
+static void delete_ctx(DeviceContext* c) { delete c; }
+
+// ---- kinds ------------------------------------------------------------------------------------
+static int kind_of(const struct rebx_force* f) {
+    auto fn = f->update_accelerations;
+    if (fn == rebx_radiation_forces) return REBX_B200_RADIATION;
+    if (fn == rebx_gravitational_harmonics) return REBX_B200_HARMONICS;
+    if (fn == rebx_gr_potential) return REBX_B200_GR_POTENTIAL;
+    if (fn == rebx_yarkovsky_effect) return REBX_B200_YARKOVSKY;
+    if (fn == rebx_modify_orbits_forces) return REBX_B200_MODIFY_ORBITS;
+    if (fn == rebx_gas_damping_timescale) return REBX_B200_GAS_DAMPING;
+    if (fn == rebx_modify_orbits_with_type_I_migration) return REBX_B200_TYPE_I;
+    return REBX_B200_NONE;
+}
+
+// ---- table builder (host) ----------------------------------------------------------------------
+struct Want {
+    const char* name;        // interned
+    double* dst = nullptr;   // double table, or
+    int32_t* idst = nullptr; // int table (value), with ipresent marking presence
+    uint8_t* present = nullptr;
+};
+
+static inline bool same_name(const char* a, const char* b) {
+    return a == b || (a[0] == b[0] && std::strcmp(a, b) == 0);
+}
+
+template <typename Fn>
+static void parallel_ranges(size_t N, Fn fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    size_t T = std::min<size_t>(std::min<size_t>(hw, 32), N/32768 + 1);
+    if (T <= 1) { fn(0, size_t(0), N); return; }
+    std::vector<std::thread> th;
+    const size_t per = (N + T - 1)/T;
+    for (size_t t = 0; t < T; t++) {
+        const size_t lo = std::min(N, t*per), hi = std::min(N, lo + per);
+        th.emplace_back([=] { fn((int)t, lo, hi); });
+    }
+    for (auto& x : th) x.join();
+}
+
+// uvw(): reference src/gravitational_harmonics.c:104-134 (body-fixed frame from the spin vector)
+static void spin_frame(const struct reb_vec3d Omega, Oblate& o) {
+    const double omega2 = Omega.x*Omega.x + Omega.y*Omega.y + Omega.z*Omega.z;
+    const double omega = std::sqrt(omega2);
+    const double sx = Omega.x/omega, sy = Omega.y/omega, sz = Omega.z/omega;
+    o.w[0] = sx; o.w[1] = sy; o.w[2] = sz;
+    const double fac = std::sqrt(sx*sx + sy*sy);
+    if (fac != 0.0) { o.u[0] = -sy/fac; o.u[1] = sx/fac; o.u[2] = 0.0; }
+    else            { o.u[0] = 1.0;     o.u[1] = 0.0;    o.u[2] = 0.0; }
+    o.v[0] = -(o.u[1]*o.w[2] - o.u[2]*o.w[1]);
+    o.v[1] = -(o.u[2]*o.w[0] - o.u[0]*o.w[2]);
+    o.v[2] = -(o.u[0]*o.w[1] - o.u[1]*o.w[0]);
+}
+
+static void build_tables(ForceTables& T, int kind, struct rebx_force* force, const struct reb_particle* particles, size_t N) {
+    T.kind = kind;
+    T.N = N;
+    T.bodies.clear();
+    T.oblate.clear();
+    T.n_incomplete = 0;
+    T.uploaded = false;
+    const double ABSENT = absent_value();
+
+    std::vector<const char*> dnames;     // double tables in tab[] order
+    const char* flag_name = nullptr;     // presence-only int parameter collected into T.bodies
+    const char* ival_name = nullptr;     // int parameter whose value is tabulated
+    switch (kind) {
+        case REBX_B200_RADIATION:     dnames = {"beta"}; flag_name = "radiation_source"; break;
+        case REBX_B200_YARKOVSKY:     dnames = {"ye_body_density", "ye_rotation_period", "ye_thermal_inertia", "ye_albedo",
+                                                "ye_emissivity", "ye_k", "ye_spin_axis_x", "ye_spin_axis_y", "ye_spin_axis_z"};
+                                      ival_name = "ye_flag"; break;
+        case REBX_B200_MODIFY_ORBITS: dnames = {"tau_a", "tau_e", "tau_inc"}; flag_name = "primary"; break;
+        case REBX_B200_GAS_DAMPING:   dnames = {"d_factor"}; flag_name = "primary"; break;
+        case REBX_B200_TYPE_I:        flag_name = "primary"; break;
+        default: break;
+    }
+    for (auto& n : dnames) n = intern_name(n);
+    if (flag_name) flag_name = intern_name(flag_name);
+    if (ival_name) ival_name = intern_name(ival_name);
+    const char* nJ2 = intern_name("J2"); const char* nJ4 = intern_name("J4");
+    const char* nReq = intern_name("R_eq"); const char* nOmega = intern_name("Omega");
+
+    const size_t nd = dnames.size();
+    for (size_t j = 0; j < REBX_B200_MAX_TABLES; j++) { if (j < nd) T.h[j].assign(N, ABSENT); else { T.h[j].clear(); T.h[j].shrink_to_fit(); } }
+    std::vector<uint8_t> ipresent;
+    if (ival_name) { T.hi.assign(N, 2); ipresent.assign(N, 0); } else { T.hi.clear(); }
+
+    unsigned hw = std::thread::hardware_concurrency();
+    std::vector<std::vector<int64_t>> flagged(std::max(1u, std::min(hw ? hw : 1u, 32u)) + 1);
+    std::vector<std::vector<std::pair<int64_t, Oblate>>> obl(flagged.size());
+
+    parallel_ranges(N, [&](int t, size_t lo, size_t hi) {
+        for (size_t i = lo; i < hi; i++) {
+            const struct rebx_node* node = static_cast<const struct rebx_node*>(particles[i].ap);
+            if (!node) continue;
+            unsigned found = 0;            // bit j: double table j ; bit 30: flag ; bit 29: ival
+            const double* J2 = nullptr; const double* J4 = nullptr; const double* Req = nullptr; const struct reb_vec3d* Om = nullptr;
+            for (; node; node = node->next) {
+                const struct rebx_param* p = static_cast<const struct rebx_param*>(node->object);
+                const char* nm = p->name;
+                bool matched = false;
+                for (size_t j = 0; j < nd && !matched; j++) {
+                    if (same_name(nm, dnames[j])) {
+                        matched = true;
+                        if (!(found & (1u << j)) && p->value) { T.h[j][i] = *static_cast<const double*>(p->value); }
+                        found |= 1u << j;            // newest entry wins, like the reference's first-match walk
+                    }
+                }
+                if (matched) continue;
+                if (flag_name && same_name(nm, flag_name)) {
+                    if (!(found & (1u << 30)) && p->value) flagged[t].push_back((int64_t)i);
+                    found |= 1u << 30;
+                } else if (ival_name && same_name(nm, ival_name)) {
+                    if (!(found & (1u << 29)) && p->value) { T.hi[i] = *static_cast<const int*>(p->value); ipresent[i] = 1; }
+                    found |= 1u << 29;
+                } else if (kind == REBX_B200_HARMONICS) {
+                    if (!J2 && same_name(nm, nJ2)) J2 = static_cast<const double*>(p->value);
+                    else if (!J4 && same_name(nm, nJ4)) J4 = static_cast<const double*>(p->value);
+                    else if (!Req && same_name(nm, nReq)) Req = static_cast<const double*>(p->value);
+                    else if (!Om && same_name(nm, nOmega)) Om = static_cast<const struct reb_vec3d*>(p->value);
+                }
+            }
+            if (kind == REBX_B200_HARMONICS && J2 && *J2 != 0.0 && Req) {
+                // src/gravitational_harmonics.c:141-159: J2 set and non-zero, R_eq set; J4 and Omega optional
+                Oblate o;
+                o.J2 = *J2; o.J4 = J4 ? *J4 : 0.0; o.Req = *Req;
+                struct reb_vec3d Omega = {0.0, 0.0, 1.0};
+                if (Om) Omega = *Om;
+                spin_frame(Omega, o);
+                obl[t].push_back({(int64_t)i, o});
+            }
+        }
+    });
+    for (auto& v : flagged) T.bodies.insert(T.bodies.end(), v.begin(), v.end());
+    if (kind == REBX_B200_HARMONICS) {
+        for (auto& v : obl) for (auto& pr : v) { T.bodies.push_back(pr.first); T.oblate.push_back(pr.second); }
+    }
+
+    if (kind == REBX_B200_YARKOVSKY) {
+        // src/yarkovsky_effect.c:244 (eligibility) and :127-130 (full version needs every parameter)
+        const bool have_sb = find_value(force->ap, "ye_stef_boltz") != nullptr;
+        int64_t incomplete = 0;
+        for (size_t i = 0; i < N; i++) {
+            int code = 2;
+            const bool eligible = ipresent[i] && !is_absent(T.h[0][i]) && !is_absent(T.h[3][i]);
+            if (eligible) {
+                const int f = T.hi[i];
+                if (f == 1 || f == -1) code = f;
+                else if (f == 0) {
+                    bool all = have_sb;
+                    for (int j : {1, 2, 4, 5, 6, 7, 8}) if (is_absent(T.h[j][i])) all = false;
+                    if (all) code = 0;
+                    else if (particles[i].r != 0 && i > 0) incomplete++;
+                }
+                // any other flag value is undefined behaviour in the reference (uninitialised
+                // magnitude, yarkovsky_effect.c:104-124): treated as "skip" here.
+            }
+            T.hi[i] = code;
+        }
+        T.n_incomplete = incomplete;
+    }
+    if (kind == REBX_B200_GAS_DAMPING) {
+        int64_t missing = 0;
+        for (size_t i = 0; i < N; i++) if (is_absent(T.h[0][i])) missing++;
+        T.n_incomplete = missing;      // refined at dispatch (the reference body itself is exempt)
+    }
+    T.valid = true;
+}
+
+static cudaError_t upload_tables(ForceTables& T, Stats& st) {
+    if (T.uploaded) return cudaSuccess;
+    for (size_t j = 0; j < REBX_B200_MAX_TABLES; j++) {
+        if (T.h[j].empty()) continue;
+        cudaError_t e = T.d[j].ensure(T.h[j].size()*sizeof(double));
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpy(T.d[j].p, T.h[j].data(), T.h[j].size()*sizeof(double), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+        st.h2d_bytes += T.h[j].size()*sizeof(double);
+    }
+    if (!T.hi.empty()) {
+        cudaError_t e = T.di.ensure(T.hi.size()*sizeof(int32_t));
+        if (e != cudaSuccess) return e;
+        e = cudaMemcpy(T.di.p, T.hi.data(), T.hi.size()*sizeof(int32_t), cudaMemcpyHostToDevice);
+        if (e != cudaSuccess) return e;
+        st.h2d_bytes += T.hi.size()*sizeof(int32_t);
+    }
+    T.uploaded = true;
+    return cudaSuccess;
+}
+
+// Host-only table cache for callers without a device (tests of the builder).
+static ForceTables& tables_for(Side* side, DeviceContext* ctx, struct rebx_force* force, int kind,
+                               const struct reb_particle* particles, size_t N, std::unordered_map<struct rebx_force*, std::unique_ptr<ForceTables>>& store) {
+    auto& slot = store[force];
+    if (!slot) slot = std::make_unique<ForceTables>();
+    ForceTables& T = *slot;
+    const bool stale = !T.valid || T.kind != kind || T.N != N || T.gen != side->generation || T.epoch != global_epoch() || (ctx && ctx->paranoid);
+    if (stale) {
+        build_tables(T, kind, force, particles, N);
+        T.gen = side->generation;
+        T.epoch = global_epoch();
+        if (ctx) ctx->stats.table_builds++;
+    }
+    return T;
+}
+
+// ---- device context -------------------------------------------------------------------------------
+static DeviceContext* ensure_ctx(Side* side, std::string& why) {
+    if (side->dev && side->dev->ready) { cudaSetDevice(side->dev->device); return side->dev.get(); }
+    int count = 0;
+    cudaError_t e = cudaGetDeviceCount(&count);
+    if (e != cudaSuccess || count == 0) {
+        cudaGetLastError();
+        why = std::string("no usable CUDA device (") + (e != cudaSuccess ? cudaGetErrorString(e) : "device count is 0") + ")";
+        return nullptr;
+    }
+    std::unique_ptr<DeviceContext, void (*)(DeviceContext*)> ctx(new DeviceContext(), delete_ctx);
+    const char* env = std::getenv("REBX_B200_DEVICE");
+    ctx->device = env ? std::atoi(env) : 0;
+    if (ctx->device < 0 || ctx->device >= count) ctx->device = 0;
+    if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
+    for (auto& s : ctx->stream) if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
+    if ((e = cudaEventCreateWithFlags(&ctx->bodies_ready, cudaEventDisableTiming)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
+    if (const char* c = std::getenv("REBX_B200_CHUNK")) { long v = std::atol(c); if (v >= 1024) ctx->chunk = (size_t)v & ~size_t(1); }
+    if (const char* p = std::getenv("REBX_B200_PARANOID")) ctx->paranoid = std::atoi(p) != 0;
+    ctx->ready = true;
+    side->dev = std::move(ctx);
+    return side->dev.get();
+}
+
+// ---- one fused segment ----------------------------------------------------------------------------
+struct Entry {
+    int kind = 0, flags = 0;
+    double scal[REBX_B200_MAX_SCALARS] = {0};
+    int64_t body_index = -1;
+    ForceTables* T = nullptr;
+    const Oblate* ob = nullptr;
+    bool reduces = false;
+};
+
+static const double* get_d(struct rebx_force* f, const char* name) { return static_cast<const double*>(find_value(f->ap, name)); }
+
+// Builds the effect entries of one force; returns false (after reporting) when the force does nothing.
+static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceContext* ctx, struct rebx_force* force, int kind,
+                              const struct reb_particle* particles, size_t N, std::vector<Entry>& out,
+                              std::unordered_map<struct rebx_force*, std::unique_ptr<ForceTables>>& store) {
+    Entry e;
+    e.kind = kind;
+    e.scal[0] = sim->G;
+    switch (kind) {
+    case REBX_B200_RADIATION: {
+        const double* c = get_d(force, "c");
+        if (!c) { reb_simulation_error(sim, "Need to set speed of light in radiation_forces effect.  See examples in documentation.\n"); return false; }
+        e.scal[1] = *c;
+        ForceTables& T = tables_for(side, ctx, force, kind, particles, N, store);
+        e.T = &T;
+        if (T.bodies.empty()) { e.body_index = 0; out.push_back(e); }          // default source: index 0 (radiation_forces.c:115-117)
+        else for (int64_t s : T.bodies) { e.body_index = s; out.push_back(e); }  // one sweep per flagged source, ascending
+        return true;
+    }
+    case REBX_B200_HARMONICS: {
+        ForceTables& T = tables_for(side, ctx, force, kind, particles, N, store);
+        e.T = &T; e.reduces = true;
+        for (size_t b = 0; b < T.bodies.size(); b++) { e.body_index = T.bodies[b]; e.ob = &T.oblate[b]; out.push_back(e); }
+        return !T.bodies.empty();
+    }
+    case REBX_B200_GR_POTENTIAL: {
+        const double* c = get_d(force, "c");
+        if (!c) { reb_simulation_error(sim, "REBOUNDx Error: Need to set speed of light in gr effect.  See examples in documentation.\n"); return false; }
+        if (N < 2) return false;
+        e.scal[1] = (*c)*(*c);
+        e.body_index = 0; e.reduces = true;
+        out.push_back(e);
+        return true;
+    }
+    case REBX_B200_YARKOVSKY: {
+        const double* lstar = get_d(force, "ye_lstar");
+        const double* c = get_d(force, "ye_c");
+        if (!lstar || !c || N < 2) return false;                               // yarkovsky_effect.c:244: silently inactive
+        const double* sb = get_d(force, "ye_stef_boltz");
+        e.scal[1] = *lstar; e.scal[2] = *c; e.scal[3] = sb ? *sb : 0.0;
+        ForceTables& T = tables_for(side, ctx, force, kind, particles, N, store);
+        e.T = &T; e.body_index = 0;
+        if (T.n_incomplete > 0)
+            reb_simulation_error(sim, "REBOUNDx Error: One or more parameters missing for this version of the Yarkovsky effect in Rebx. Please make sure you've given values to all variables for this version before running simulations. If you'd rather use the simplified version of this effect (requires fewer parameters), then please set 'ye_flag' to -1 or 1.\n\n");
+        out.push_back(e);
+        return true;
+    }
+    case REBX_B200_MODIFY_ORBITS:
+    case REBX_B200_GAS_DAMPING:
+    case REBX_B200_TYPE_I: {
+        const int* cptr = static_cast<const int*>(find_value(force->ap, "coordinates"));
+        const int coordinates = cptr ? *cptr : REBX_COORDINATES_JACOBI;
+        ForceTables& T = tables_for(side, ctx, force, kind, particles, N, store);
+        e.T = &T; e.reduces = true;
+        if (coordinates == REBX_COORDINATES_PARTICLE) {
+            if (T.bodies.empty()) {
+                reb_simulation_error(sim, "Coordinates set to REBX_COORDINATES_PARTICLE, but primary param was not found in any particle.  Need to set parameter.\n");
+                return false;   // the reference goes on to index particles[-1] here (rebxtools.c:139); we stop
+            }
+            e.body_index = T.bodies.front();
+        } else {
+            reb_simulation_error(sim, "REBOUNDx-B200 Error: Jacobi and barycentric coordinates are not available on the device path in this build; set the force's 'coordinates' parameter to REBX_COORDINATES_PARTICLE.\n");
+            return false;
+        }
+        if (kind == REBX_B200_MODIFY_ORBITS) {
+            const double* dedge = get_d(force, "ide_position");
+            const double* hedge = get_d(force, "ide_width");
+            if (dedge && hedge) { e.flags |= REBX_B200_FLAG_TRAP; e.scal[1] = *dedge; e.scal[2] = *hedge; }
+        } else if (kind == REBX_B200_GAS_DAMPING) {
+            const double* cs = get_d(force, "cs_coeff");
+            const double* tc = get_d(force, "tau_coeff");
+            int64_t missing = T.n_incomplete;
+            // the reference body is never evaluated, so its own missing d_factor is no error
+            if (is_absent(T.h[0][(size_t)e.body_index])) missing--;
+            if (!cs || !tc || missing > 0)
+                rebx_error(static_cast<struct rebx_extras*>(sim->extras), "Need to set d_factor, cs_coeff, tau_coeff parameters.  See examples in documentation.\n");
+            if (!cs || !tc) return false;                                      // every particle returns a zero force
+            e.scal[1] = *cs; e.scal[2] = *tc;
+        } else {
+            const double* beta = get_d(force, "tIm_flaring_index");
+            const double* h0 = get_d(force, "tIm_scale_height_1");
+            const double* sd0 = get_d(force, "tIm_surface_density_1");
+            const double* s = get_d(force, "tIm_surface_density_exponent");
+            const double* dedge = get_d(force, "ide_position");
+            const double* hedge = get_d(force, "ide_width");
+            e.scal[1] = beta ? *beta : 0.0;  e.scal[2] = h0 ? *h0 : 0.01;      // defaults: type_I_migration.c:121-126
+            e.scal[3] = sd0 ? *sd0 : 0.0;    e.scal[4] = s ? *s : 0.0;
+            e.scal[5] = dedge ? *dedge : 0.0; e.scal[6] = hedge ? *hedge : 0.0;
+        }
+        out.push_back(e);
+        return true;
+    }
+    default: return false;
+    }
+}
+
+static void fill_body(double* rec, const Entry& e, const struct reb_particle* particles) {
+    for (int j = 0; j < REBX_B200_BODY_DOUBLES; j++) rec[j] = 0.0;
+    const struct reb_particle& b = particles[e.body_index];
+    rec[REBX_B200_BODY_INDEX] = (double)e.body_index;
+    rec[REBX_B200_BODY_X+0] = b.x;  rec[REBX_B200_BODY_X+1] = b.y;  rec[REBX_B200_BODY_X+2] = b.z;
+    rec[REBX_B200_BODY_VX+0] = b.vx; rec[REBX_B200_BODY_VX+1] = b.vy; rec[REBX_B200_BODY_VX+2] = b.vz;
+    rec[REBX_B200_BODY_M] = b.m;
+    if (e.ob) {
+        rec[REBX_B200_BODY_J2] = e.ob->J2; rec[REBX_B200_BODY_J4] = e.ob->J4; rec[REBX_B200_BODY_REQ] = e.ob->Req;
+        for (int j = 0; j < 3; j++) { rec[REBX_B200_BODY_U+j] = e.ob->u[j]; rec[REBX_B200_BODY_V+j] = e.ob->v[j]; rec[REBX_B200_BODY_W+j] = e.ob->w[j]; }
+    }
+}
+
+#define REBXB_CUDA(call, what) do { cudaError_t err__ = (call); if (err__ != cudaSuccess) { fail = what; fail_code = err__; goto failed; } } while (0)
+
+static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, int nf, struct reb_particle* particles, const int Nint) {
+    struct rebx_extras* rebx = static_cast<struct rebx_extras*>(sim->extras);
+    if (rebx == nullptr || Nint <= 0) return;
+    const size_t N = (size_t)Nint;
+    Side* side = side_of(rebx);
+    std::string why;
+    DeviceContext* ctx = ensure_ctx(side, why);
+    if (!ctx) {
+        std::string msg = "REBOUNDx-B200 Error: " + why + ". The built-in forces of this library run on the GPU only; accelerations were NOT updated.\n";
+        reb_simulation_error(sim, msg.c_str());
+        return;
+    }
+    ctx->stats.calls++;
+
+    std::vector<Entry> entries;
+    for (int f = 0; f < nf; f++) entries_for_force(sim, side, ctx, forces[f], kind_of(forces[f]), particles, N, entries, ctx->tables);
+    if (entries.empty()) return;
+
+    const char* fail = nullptr;
+    cudaError_t fail_code = cudaSuccess;
+    const size_t ne = entries.size();
+    const size_t CH = ctx->chunk;
+    const size_t nchunks = (N + CH - 1)/CH;
+    const size_t chunk_cap = std::min(N, CH);
+    bool need_vel = false, need_m = false, need_r = false;
+    for (const Entry& e : entries) {
+        switch (e.kind) {
+            case REBX_B200_RADIATION: need_vel = true; break;
+            case REBX_B200_HARMONICS: case REBX_B200_GR_POTENTIAL: need_m = true; break;
+            case REBX_B200_YARKOVSKY: need_vel = need_m = need_r = true; break;
+            default: need_vel = need_m = true; break;
+        }
+    }
+    const rebx_b200_aos_layout L = {(int32_t)sizeof(struct reb_particle), (int32_t)offsetof(struct reb_particle, x),
+                                    (int32_t)offsetof(struct reb_particle, vx), (int32_t)offsetof(struct reb_particle, ax),
+                                    (int32_t)offsetof(struct reb_particle, m), (int32_t)offsetof(struct reb_particle, r)};
+    const size_t soa_stride = (chunk_cap + 1) & ~size_t(1);      // keep every array 16-byte aligned
+    int launches = 0;
+    double* bodies_h = nullptr;
+    double* br_h = nullptr;
+
+    // tables to HBM (no-op unless rebuilt)
+    for (Entry& e : entries) if (e.T) REBXB_CUDA(upload_tables(*e.T, ctx->stats), "uploading parameter tables");
+
+    REBXB_CUDA(ctx->bodies_h.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating pinned body records");
+    REBXB_CUDA(ctx->bodies.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating body records");
+    REBXB_CUDA(ctx->br_h.ensure(nchunks*ne*3*sizeof(double)), "allocating pinned back-reaction sums");
+    REBXB_CUDA(ctx->br.ensure(nchunks*ne*3*sizeof(double)), "allocating back-reaction sums");
+    for (int b = 0; b < 2 && (size_t)b < nchunks; b++) {
+        REBXB_CUDA(ctx->aos[b].ensure(chunk_cap*sizeof(struct reb_particle)), "allocating AoS staging");
+        REBXB_CUDA(ctx->soa[b].ensure(11*soa_stride*sizeof(double)), "allocating SoA state");
+        REBXB_CUDA(ctx->work[b].ensure(rebx_b200_workspace_bytes()), "allocating reduction scratch");
+    }
+    // Pin the caller's particle array once so the DMA engines can stream it (only worth it for
+    // the simulation's own long-lived array, not for an integrator's scratch copy).
+    if (particles == sim->particles && N*sizeof(struct reb_particle) >= (size_t(8) << 20)) {
+        if (ctx->registered_ptr != particles || ctx->registered_bytes != N*sizeof(struct reb_particle)) {
+            ctx->unregister_host();
+            if (cudaHostRegister(particles, N*sizeof(struct reb_particle), cudaHostRegisterDefault) == cudaSuccess) {
+                ctx->registered_ptr = particles; ctx->registered_bytes = N*sizeof(struct reb_particle);
+            } else {
+                cudaGetLastError();     // pageable copies still work, just slower
+            }
+        }
+    }
+
+    bodies_h = static_cast<double*>(ctx->bodies_h.p);
+    for (size_t e = 0; e < ne; e++) fill_body(bodies_h + e*REBX_B200_BODY_DOUBLES, entries[e], particles);
+    REBXB_CUDA(cudaMemcpyAsync(ctx->bodies.p, bodies_h, ne*REBX_B200_BODY_DOUBLES*sizeof(double), cudaMemcpyHostToDevice, ctx->stream[0]), "copying body records");
+    REBXB_CUDA(cudaMemsetAsync(ctx->br.p, 0, nchunks*ne*3*sizeof(double), ctx->stream[0]), "clearing back-reaction sums");
+    REBXB_CUDA(cudaEventRecord(ctx->bodies_ready, ctx->stream[0]), "recording event");
+    REBXB_CUDA(cudaStreamWaitEvent(ctx->stream[1], ctx->bodies_ready, 0), "waiting on event");
+    ctx->stats.h2d_bytes += ne*REBX_B200_BODY_DOUBLES*sizeof(double);
+
+    for (size_t c = 0; c < nchunks; c++) {
+        const int b = (int)(c & 1);
+        cudaStream_t s = ctx->stream[b];
+        const size_t c0 = c*CH, n = std::min(CH, N - c0);
+        const size_t bytes = n*sizeof(struct reb_particle);
+        REBXB_CUDA(cudaMemcpyAsync(ctx->aos[b].p, particles + c0, bytes, cudaMemcpyHostToDevice, s), "copying particles to the device");
+        ctx->stats.h2d_bytes += bytes;
+        double* base = static_cast<double*>(ctx->soa[b].p);
+        rebx_b200_state st;
+        st.n = (int64_t)n; st.index_base = (int64_t)c0;
+        st.x = base + 0*soa_stride; st.y = base + 1*soa_stride; st.z = base + 2*soa_stride;
+        st.vx = need_vel ? base + 3*soa_stride : nullptr; st.vy = need_vel ? base + 4*soa_stride : nullptr; st.vz = need_vel ? base + 5*soa_stride : nullptr;
+        st.m = need_m ? base + 6*soa_stride : nullptr;
+        st.r = need_r ? base + 7*soa_stride : nullptr;
+        st.ax = base + 8*soa_stride; st.ay = base + 9*soa_stride; st.az = base + 10*soa_stride;
+        REBXB_CUDA((cudaError_t)rebx_b200_unpack_aos(ctx->aos[b].p, &L, &st, s, &launches), "unpacking particles");
+        for (size_t e0 = 0; e0 < ne; e0 += REBX_B200_MAX_EFFECTS) {
+            rebx_b200_pass P;
+            std::memset(&P, 0, sizeof P);
+            P.st = st;
+            P.n_effects = (int32_t)std::min<size_t>(REBX_B200_MAX_EFFECTS, ne - e0);
+            for (int j = 0; j < P.n_effects; j++) {
+                const Entry& en = entries[e0 + j];
+                rebx_b200_effect& fx = P.fx[j];
+                fx.kind = en.kind; fx.flags = en.flags;
+                fx.body = static_cast<const double*>(ctx->bodies.p) + (e0 + j)*REBX_B200_BODY_DOUBLES;
+                for (int k = 0; k < REBX_B200_MAX_SCALARS; k++) fx.scal[k] = en.scal[k];
+                if (en.T) {
+                    for (int k = 0; k < REBX_B200_MAX_TABLES; k++) fx.tab[k] = en.T->d[k].p ? static_cast<const double*>(en.T->d[k].p) + c0 : nullptr;
+                    fx.itab = en.T->di.p ? static_cast<const int32_t*>(en.T->di.p) + c0 : nullptr;
+                }
+                fx.backreaction = en.reduces ? static_cast<double*>(ctx->br.p) + (c*ne + e0 + j)*3 : nullptr;
+            }
+            REBXB_CUDA((cudaError_t)rebx_b200_launch_pass(&P, ctx->work[b].p, s, &launches), "launching the force sweep");
+        }
+        REBXB_CUDA((cudaError_t)rebx_b200_pack_acc_aos(ctx->aos[b].p, &L, &st, s, &launches), "packing accelerations");
+        REBXB_CUDA(cudaMemcpyAsync(particles + c0, ctx->aos[b].p, bytes, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
+        ctx->stats.d2h_bytes += bytes;
+    }
+    REBXB_CUDA(cudaStreamSynchronize(ctx->stream[1]), "waiting for the device");
+    br_h = static_cast<double*>(ctx->br_h.p);
+    REBXB_CUDA(cudaMemcpyAsync(br_h, ctx->br.p, nchunks*ne*3*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream[0]), "copying back-reaction sums");
+    REBXB_CUDA(cudaStreamSynchronize(ctx->stream[0]), "waiting for the device");
+    ctx->stats.d2h_bytes += nchunks*ne*3*sizeof(double);
+    ctx->stats.launches += (std::uint64_t)launches;
+
+    // Back-reaction onto the source / primary / oblate bodies (gr_potential.c:74-76,
+    // gravitational_harmonics.c:221-223, rebxtools.c:139-141): chunk sums added in chunk order.
+    for (size_t e = 0; e < ne; e++) {
+        if (!entries[e].reduces) continue;
+        double sx = 0.0, sy = 0.0, sz = 0.0;
+        for (size_t c = 0; c < nchunks; c++) { sx += br_h[(c*ne + e)*3 + 0]; sy += br_h[(c*ne + e)*3 + 1]; sz += br_h[(c*ne + e)*3 + 2]; }
+        struct reb_particle& b = particles[entries[e].body_index];
+        b.ax += sx; b.ay += sy; b.az += sz;
+    }
+    return;
+
+failed:
+    {
+        cudaGetLastError();
+        char buf[400];
+        snprintf(buf, sizeof buf, "REBOUNDx-B200 Error: CUDA failure while %s: %s. Accelerations are NOT valid for this call.\n", fail, cudaGetErrorString(fail_code));
+        reb_simulation_error(sim, buf);
+        cudaStreamSynchronize(ctx->stream[0]); cudaStreamSynchronize(ctx->stream[1]); cudaGetLastError();
+    }
+}
+
+}  // namespace rebxh
+
+using namespace rebxh;
+
+extern "C" {
+
+// ---- plug-in entry points: the reference's force signature, one fused sweep each ---------------
+#define REBXB_ENTRY(fn) \
+    void fn(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N) { \
+        struct rebx_force* one = force; run_segment(sim, &one, 1, particles, N); }
+REBXB_ENTRY(rebx_radiation_forces)
+REBXB_ENTRY(rebx_gravitational_harmonics)
+REBXB_ENTRY(rebx_gr_potential)
+REBXB_ENTRY(rebx_yarkovsky_effect)
+REBXB_ENTRY(rebx_modify_orbits_forces)
+REBXB_ENTRY(rebx_gas_damping_timescale)
+REBXB_ENTRY(rebx_modify_orbits_with_type_I_migration)
+
+// The dispatcher installed as sim->additional_forces (reference src/core.c:1026-1041).
+void rebx_additional_forces(struct reb_simulation* sim) {
+    if (sim->N_var != 0) {
+        reb_simulation_warning(sim, "REBOUNDx: Variational particles have been added to the simulation but are not implemented in REBOUNDx and will not be evolved self-consistently.");
+    }
+    struct rebx_extras* rebx = static_cast<struct rebx_extras*>(sim->extras);
+    if (!rebx) return;
+    std::vector<struct rebx_force*> order;
+    for (struct rebx_node* n = rebx->additional_forces; n; n = n->next) order.push_back(static_cast<struct rebx_force*>(n->object));
+    const bool whfast_vel = sim->force_is_velocity_dependent && sim->integrator.name && std::strcmp(sim->integrator.name, "whfast") == 0;
+    const double Nd = (double)sim->N;          // the reference stores N in a double before narrowing it (core.c:1037)
+    const int N = (int)Nd;
+    size_t i = 0;
+    while (i < order.size()) {
+        size_t j = i;
+        while (j < order.size() && kind_of(order[j]) != REBX_B200_NONE) j++;
+        if (j > i) {
+            if (whfast_vel) for (size_t k = i; k < j; k++)
+                reb_simulation_warning(sim, "REBOUNDx: Passing a velocity-dependent force to WHFAST, will accumulate errors proportional to the force. If forces get big, consider using IAS15 or applying force as an operator.");
+            run_segment(sim, order.data() + i, (int)(j - i), sim->particles, N);
+            i = j;
+        } else {
+            if (whfast_vel)
+                reb_simulation_warning(sim, "REBOUNDx: Passing a velocity-dependent force to WHFAST, will accumulate errors proportional to the force. If forces get big, consider using IAS15 or applying force as an operator.");
+            order[i]->update_accelerations(sim, order[i], sim->particles, N);   // custom / foreign force: host callback
+            i++;
+        }
+    }
+}
+
+// ---- introspection used by tests and bench (host side only) -------------------------------------
+// Builds (without touching the device) the SoA table `index` of `force` and copies it to `out`.
+// Returns the number of elements, or -1.  index -1 selects the int table; index -2 copies the
+// body index list (as doubles).
+int64_t rebx_b200_host_table(struct rebx_extras* rebx, struct rebx_force* force, int index, double* out, int64_t cap) {
+    if (!rebx || !rebx->sim || !force) return -1;
+    const int kind = kind_of(force);
+    if (kind == REBX_B200_NONE) return -1;
+    static std::unordered_map<struct rebx_force*, std::unique_ptr<ForceTables>> scratch;
+    scratch.erase(force);
+    ForceTables& T = tables_for(side_of(rebx), nullptr, force, kind, rebx->sim->particles, rebx->sim->N, scratch);
+    int64_t n = -1;
+    if (index >= 0 && index < REBX_B200_MAX_TABLES) {
+        n = (int64_t)T.h[index].size();
+        for (int64_t k = 0; k < n && k < cap; k++) out[k] = T.h[index][(size_t)k];
+    } else if (index == -1) {
+        n = (int64_t)T.hi.size();
+        for (int64_t k = 0; k < n && k < cap; k++) out[k] = (double)T.hi[(size_t)k];
+    } else if (index == -2) {
+        n = (int64_t)T.bodies.size();
+        for (int64_t k = 0; k < n && k < cap; k++) out[k] = (double)T.bodies[(size_t)k];
+    }
+    scratch.erase(force);
+    return n;
+}
+
+// Counters of the host-facing path: {calls, kernel launches, H2D bytes, D2H bytes, table builds}.
+int rebx_b200_get_stats(struct rebx_extras* rebx, uint64_t out[5]) {
+    if (!rebx) return -1;
+    Side* side = side_of(rebx);
+    if (!side->dev) { for (int k = 0; k < 5; k++) out[k] = 0; return 0; }
+    const Stats& s = side->dev->stats;
+    out[0] = s.calls; out[1] = s.launches; out[2] = s.h2d_bytes; out[3] = s.d2h_bytes; out[4] = s.table_builds;
+    return 0;
+}
+
+}  // extern "C"

@@ -1,0 +1,398 @@
+// forces_math.cuh -- per-particle FP64 arithmetic of the REBOUNDx force effects, for sm_100a.
+//
+// Every function here evaluates ONE particle against ONE body record and is written in the
+// association order of the reference's C expressions, so that with
+// -fmad=false the +,-,*,/ and sqrt results are bit-identical to the reference built without
+// FMA contraction.  libdevice pow/atan/sin/cos/acos differ from glibc by <= 1-2 ulp.
+//
+// Compiled only into kernels.cu.  No host fallbacks exist: these are __device__ only.
+#pragma once
+#include <cstdint>
+#include <cmath>
+#include "rebx_b200.h"
+
+namespace rebxb {
+
+constexpr double kPi     = 3.14159265358979323846;
+constexpr double kTwoPi  = 2*kPi;
+constexpr double kPi5    = kPi*kPi*kPi*kPi*kPi;          // M_PI*M_PI*M_PI*M_PI*M_PI, left-assoc (yarkovsky_effect.c:156)
+constexpr double kTiny   = 1.E-308;
+
+struct Particle { double x, y, z, vx, vy, vz, m, r; };
+struct Vec3     { double x, y, z; };
+
+__device__ __forceinline__ bool is_absent(double v) {
+    return (unsigned long long)__double_as_longlong(v) == REBX_B200_ABSENT_BITS;
+}
+
+// ---------------------------------------------------------------------------------------
+// Two-body elements relative to `body` -- restates REBOUND's reb_orbit_from_particle_err
+// (third-party, not under /root/reference; same restatement as rebound_shim.c).
+// Only the members the force path reads: a, e, inc, P.
+// ---------------------------------------------------------------------------------------
+struct Orbit { double a, e, inc, P; };
+
+template <bool WANT_E, bool WANT_INC, bool WANT_P>
+__device__ __forceinline__ Orbit orbit_from_particle(double G, const Particle& p, const double* __restrict__ body) {
+    Orbit o;
+    const double nan = __longlong_as_double(0x7ff8000000000000LL);
+    o.a = nan; o.e = nan; o.inc = nan; o.P = nan;
+    const double bm = body[REBX_B200_BODY_M];
+    if (bm <= kTiny) return o;                          // primary has no mass
+    const double mu = G*(p.m + bm);
+    const double dx = p.x - body[REBX_B200_BODY_X+0];
+    const double dy = p.y - body[REBX_B200_BODY_X+1];
+    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
+    const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
+    const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    const double d = sqrt(dx*dx + dy*dy + dz*dz);
+    const double vsquared = dvx*dvx + dvy*dvy + dvz*dvz;
+    const double vcircsquared = mu/d;
+    const double a = -mu/(vsquared - 2.*vcircsquared);
+    if (d <= kTiny) return o;                           // particle on top of primary
+    o.a = a;
+    if (WANT_E) {
+        const double vdiffsquared = vsquared - vcircsquared;
+        const double vr = (dx*dvx + dy*dvy + dz*dvz)/d;
+        const double rvr = d*vr;
+        const double muinv = 1./mu;
+        const double ex = muinv*(vdiffsquared*dx - rvr*dvx);
+        const double ey = muinv*(vdiffsquared*dy - rvr*dvy);
+        const double ez = muinv*(vdiffsquared*dz - rvr*dvz);
+        o.e = sqrt(ex*ex + ey*ey + ez*ez);
+    }
+    if (WANT_P) {
+        const double n = a/fabs(a)*sqrt(fabs(mu/(a*a*a)));
+        o.P = kTwoPi/n;
+    }
+    if (WANT_INC) {
+        const double hx = (dy*dvz - dz*dvy);
+        const double hy = (dz*dvx - dx*dvz);
+        const double hz = (dx*dvy - dy*dvx);
+        const double h = sqrt(hx*hx + hy*hy + hz*hz);
+        const double cosine = hz/h;
+        double val;
+        if (cosine > -1. && cosine < 1.) val = acos(cosine);
+        else                             val = (cosine <= -1.) ? kPi : 0.;
+        o.inc = val;
+    }
+    return o;
+}
+
+// src/inner_disk_edge.c:61-77
+__device__ __forceinline__ double planet_trap(double r, double dedge, double hedge) {
+    if (r > dedge*(1.0 + hedge)) return 1.0;
+    if (dedge*(1.0 - hedge) < r) return 5.5*cos(((dedge*(1.0 + hedge) - r)*2*kPi)/(4*hedge*dedge)) - 4.5;
+    return -10.0;
+}
+
+// ---------------------------------------------------------------------------------------
+// Effects.  Each returns through `a` (running acceleration of the particle, already
+// holding gravity + earlier effects) and `red` (signed back-reaction sum onto the body).
+// `gi` is the particle's global index, `k` its index inside the shard's tables.
+// ---------------------------------------------------------------------------------------
+
+// src/radiation_forces.c:69-98
+__device__ __forceinline__ void radiation(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                          const Particle& p, double beta, Vec3& a) {
+    if (is_absent(beta)) return;
+    const double c  = fx.scal[1];
+    const double mu = fx.scal[0]*body[REBX_B200_BODY_M];
+    const double dx = p.x - body[REBX_B200_BODY_X+0];
+    const double dy = p.y - body[REBX_B200_BODY_X+1];
+    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double dr = sqrt(dx*dx + dy*dy + dz*dz);
+    const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
+    const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
+    const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    const double rdot = (dx*dvx + dy*dvy + dz*dvz)/dr;
+    const double a_rad = beta*mu/(dr*dr);
+    const double k1 = 1. - rdot/c;
+    a.x += a_rad*(k1*dx/dr - dvx/c);
+    a.y += a_rad*(k1*dy/dr - dvy/c);
+    a.z += a_rad*(k1*dz/dr - dvz/c);
+}
+
+// src/gravitational_harmonics.c:184-224 with j2_func :72-86 and j4_func :88-102
+__device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                          const Particle& p, Vec3& a, Vec3& red) {
+    const double G   = fx.scal[0];
+    const double bm  = body[REBX_B200_BODY_M];
+    const double J2  = body[REBX_B200_BODY_J2];
+    const double J4  = body[REBX_B200_BODY_J4];
+    const double Req = body[REBX_B200_BODY_REQ];
+    const double ux = body[REBX_B200_BODY_U+0], uy = body[REBX_B200_BODY_U+1], uz = body[REBX_B200_BODY_U+2];
+    const double vx = body[REBX_B200_BODY_V+0], vy = body[REBX_B200_BODY_V+1], vz = body[REBX_B200_BODY_V+2];
+    const double wx = body[REBX_B200_BODY_W+0], wy = body[REBX_B200_BODY_W+1], wz = body[REBX_B200_BODY_W+2];
+
+    const double dx = p.x - body[REBX_B200_BODY_X+0];
+    const double dy = p.y - body[REBX_B200_BODY_X+1];
+    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double r2 = dx*dx + dy*dy + dz*dz;
+    const double r  = sqrt(r2);
+    const double du = ux*dx + uy*dy + uz*dz;
+    const double dv = vx*dx + vy*dy + vz*dz;
+    const double dw = wx*dx + wy*dy + wz*dz;
+    const double costheta  = dw/r;
+    const double costheta2 = costheta*costheta;
+
+    double au = 0.0, av = 0.0, aw = 0.0;
+    {   // J2 != 0 is guaranteed by the table builder (body skipped otherwise)
+        const double f1 = 1.5*G*bm*J2*Req*Req/r2/r2/r;
+        const double f2 = 5.0*costheta2 - 1.0;
+        const double f3 = f2 - 2.0;
+        au += f1*f2*du;
+        av += f1*f2*dv;
+        aw += f1*f3*dw;
+    }
+    if (J4 != 0.0) {
+        const double f1 = 0.625*G*bm*J4*Req*Req*Req*Req/r2/r2/r2/r;
+        const double f2 = 63.0*costheta2*costheta2 - 42.0*costheta2 + 3.0;
+        const double f3 = f2 - 28.0*costheta2 + 12.0;
+        au += f1*f2*du;
+        av += f1*f2*dv;
+        aw += f1*f3*dw;
+    }
+    const double ax = ux*au + vx*av + wx*aw;
+    const double ay = uy*au + vy*av + wy*aw;
+    const double az = uz*au + vz*av + wz*aw;
+    a.x += ax;  a.y += ay;  a.z += az;
+    const double fac = p.m/bm;
+    red.x -= fac*ax;  red.y -= fac*ay;  red.z -= fac*az;
+}
+
+// src/gr_potential.c:60-78
+__device__ __forceinline__ void gr_potential(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                             const Particle& p, Vec3& a, Vec3& red) {
+    const double Gm = fx.scal[0]*body[REBX_B200_BODY_M];
+    const double prefac1 = 6.*Gm*Gm/fx.scal[1];
+    const double dx = p.x - body[REBX_B200_BODY_X+0];
+    const double dy = p.y - body[REBX_B200_BODY_X+1];
+    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double r2 = dx*dx + dy*dy + dz*dz;
+    const double prefac = prefac1/(r2*r2);
+    a.x -= prefac*dx;  a.y -= prefac*dy;  a.z -= prefac*dz;
+    const double mr = p.m/body[REBX_B200_BODY_M];
+    red.x += mr*prefac*dx;  red.y += mr*prefac*dy;  red.z += mr*prefac*dz;
+}
+
+// src/yarkovsky_effect.c:76-216.  `code` is the table builder's ye_flag code:
+// -1 / 0 / +1 as in the reference, 2 = particle not eligible (a required parameter is
+// missing, or a flag value the reference leaves undefined).
+struct YarkParams { double density, rot_period, Gamma, albedo, emissivity, k, sx, sy, sz; };
+
+__device__ __forceinline__ void yarkovsky(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                          const Particle& p, const YarkParams& yp, int code, Vec3& a) {
+    if (code == 2 || p.r == 0) return;
+    const double G = fx.scal[0], lstar = fx.scal[1], c = fx.scal[2], stef_boltz = fx.scal[3];
+    const double radius = p.r;
+    const double q_yar = 1.0 - yp.albedo;
+    const double dx = p.x - body[REBX_B200_BODY_X+0];
+    const double dy = p.y - body[REBX_B200_BODY_X+1];
+    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
+    const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
+    const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    const double distance = sqrt((dx*dx) + (dy*dy) + (dz*dz));
+    const double rdotv = ((dx*dvx) + (dy*dvy) + (dz*dvz))/(c*distance);
+    const double i0 = ((1 - rdotv)*(dx/distance)) - (dvx/c);
+    const double i1 = ((1 - rdotv)*(dy/distance)) - (dvy/c);
+    const double i2 = ((1 - rdotv)*(dz/distance)) - (dvz/c);
+
+    double mag;
+    double Y[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};
+    if (code != 0) {
+        mag = (3*q_yar*lstar)/(64*kPi*radius*yp.density*c*distance*distance);
+        if (code == 1) Y[1][0] = 1.0; else Y[0][1] = 1.0;
+    } else {
+        const Orbit o = orbit_from_particle<false, false, true>(G, p, body);
+        mag = (3*yp.k*q_yar*lstar)/(16*kPi*radius*yp.density*c*distance*distance);
+        const double sx = yp.sx, sy = yp.sy, sz = yp.sz;
+        const double Smag = sqrt((sx*sx) + sy*sy + sz*sz);
+        const double hx = (dy*dvz) - (dz*dvy);
+        const double hy = (dz*dvx) - (dx*dvz);
+        const double hz = (dx*dvy) - (dy*dvx);
+        const double Hmag = sqrt((hx*hx) + (hy*hy) + (hz*hz));
+        const double inv_smag = 1.0/Smag;
+        const double inv_mag_sqrd = 1.0/(Smag*Smag);
+        const double inv_hmag = 1.0/Hmag;
+        const double inv_hmag_sqrd = 1.0/(Hmag*Hmag);
+        const double R1s[3][3] = {{0.0, -sz*inv_smag, sy*inv_smag}, {sz*inv_smag, 0.0, -sx*inv_smag}, {-sy*inv_smag, sx*inv_smag, 0.0}};
+        const double R2s[3][3] = {{sx*sx*inv_mag_sqrd, sx*sy*inv_mag_sqrd, sx*sz*inv_mag_sqrd},
+                                  {sx*sy*inv_mag_sqrd, sy*sy*inv_mag_sqrd, sy*sz*inv_mag_sqrd},
+                                  {sx*sz*inv_mag_sqrd, sy*sz*inv_mag_sqrd, sz*sz*inv_mag_sqrd}};
+        const double R1h[3][3] = {{0.0, -hz*inv_hmag, hy*inv_hmag}, {hz*inv_hmag, 0.0, -hx*inv_hmag}, {-hy*inv_hmag, hx*inv_hmag, 0.0}};
+        const double R2h[3][3] = {{hx*hx*inv_hmag_sqrd, hx*hy*inv_hmag_sqrd, hx*hz*inv_hmag_sqrd},
+                                  {hx*hy*inv_hmag_sqrd, hy*hy*inv_hmag_sqrd, hy*hz*inv_hmag_sqrd},
+                                  {hx*hz*inv_hmag_sqrd, hy*hz*inv_hmag_sqrd, hz*hz*inv_hmag_sqrd}};
+        const double pre  = .5*pow((stef_boltz*yp.emissivity)/kPi5, .25);
+        const double flux = pow((lstar*q_yar)/(distance*distance), .75);
+        const double tanPhi     = 1.0/(1.0 + pre*sqrt(yp.rot_period/(yp.Gamma*yp.Gamma))*flux);
+        const double tanEpsilon = 1.0/(1.0 + pre*sqrt(o.P/(yp.Gamma*yp.Gamma))*flux);
+        const double Phi = atan(tanPhi);
+        const double Epsilon = atan(tanEpsilon);
+        const double cos_phi = cos(Phi), sin_phi = sin(Phi);
+        const double cos_epsilon = cos(Epsilon), sin_epsilon = sin(Epsilon);
+        double Rys[3][3], Ryh[3][3];
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                const double unit = (i == j) ? 1.0 : 0.0;
+                Rys[i][j] = (cos_phi*unit) + (sin_phi*R1s[i][j]) + ((1.0 - cos_phi)*R2s[i][j]);
+                Ryh[i][j] = (cos_epsilon*unit) - (sin_epsilon*R1h[i][j]) + ((1 - cos_epsilon)*R2h[i][j]);
+            }
+        }
+#pragma unroll
+        for (int i = 0; i < 3; i++) {
+#pragma unroll
+            for (int j = 0; j < 3; j++) {
+                Y[i][j] = (Rys[i][0]*Ryh[0][j]) + (Rys[i][1]*Ryh[1][j]) + (Rys[i][2]*Ryh[2][j]);
+            }
+        }
+    }
+    const double d0 = (Y[0][0]*i0) + (Y[0][1]*i1) + (Y[0][2]*i2);
+    const double d1 = (Y[1][0]*i0) + (Y[1][1]*i1) + (Y[1][2]*i2);
+    const double d2 = (Y[2][0]*i0) + (Y[2][1]*i1) + (Y[2][2]*i2);
+    a.x += mag*d0;  a.y += mag*d1;  a.z += mag*d2;
+}
+
+// Shared tail of rebx_com_force for one particle (src/rebxtools.c:101-141):
+// PARTICLE coordinates  : p.a += f ; p.a -= mr f ; body.a -= mr f   with mr = m/(M+m)
+// BARYCENTRIC           : p.a += f ;                all.a  -= mr f   with mr = m/M  (second sweep)
+__device__ __forceinline__ void com_force_tail(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                               const Particle& p, const Vec3& f, Vec3& a, Vec3& red) {
+    a.x += f.x;  a.y += f.y;  a.z += f.z;
+    const double M = body[REBX_B200_BODY_M];
+    if (fx.flags & REBX_B200_FLAG_BARYCENTRIC) {
+        const double mr = p.m/M;
+        red.x -= mr*f.x;  red.y -= mr*f.y;  red.z -= mr*f.z;
+    } else {
+        const double mr = p.m/(M + p.m);
+        a.x -= mr*f.x;  a.y -= mr*f.y;  a.z -= mr*f.z;
+        red.x -= mr*f.x;  red.y -= mr*f.y;  red.z -= mr*f.z;
+    }
+}
+
+struct Rel { double dx, dy, dz, dvx, dvy, dvz, r2; };
+__device__ __forceinline__ Rel relative(const Particle& p, const double* __restrict__ body) {
+    Rel q;
+    q.dvx = p.vx - body[REBX_B200_BODY_VX+0];
+    q.dvy = p.vy - body[REBX_B200_BODY_VX+1];
+    q.dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    q.dx = p.x - body[REBX_B200_BODY_X+0];
+    q.dy = p.y - body[REBX_B200_BODY_X+1];
+    q.dz = p.z - body[REBX_B200_BODY_X+2];
+    q.r2 = q.dx*q.dx + q.dy*q.dy + q.dz*q.dz;
+    return q;
+}
+
+// src/modify_orbits_forces.c:77-128
+__device__ __forceinline__ Vec3 modify_orbits(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                              const Particle& p, double tau_a_tab, double tau_e_tab, double tau_inc_tab) {
+    double invtau_a = 0.0;
+    double tau_e = INFINITY, tau_inc = INFINITY;
+    const Rel q = relative(p, body);
+    if (!is_absent(tau_a_tab)) {
+        invtau_a = 1.0/tau_a_tab;
+        if (fx.flags & REBX_B200_FLAG_TRAP) {
+            const Orbit o = orbit_from_particle<false, false, false>(fx.scal[0], p, body);
+            invtau_a *= planet_trap(o.a, fx.scal[1], fx.scal[2]);
+        }
+    }
+    if (!is_absent(tau_e_tab))   tau_e = tau_e_tab;
+    if (!is_absent(tau_inc_tab)) tau_inc = tau_inc_tab;
+    Vec3 f;
+    f.x = q.dvx*invtau_a/(2.);
+    f.y = q.dvy*invtau_a/(2.);
+    f.z = q.dvz*invtau_a/(2.);
+    if (tau_e < INFINITY || tau_inc < INFINITY) {
+        const double vdotr = q.dx*q.dvx + q.dy*q.dvy + q.dz*q.dvz;
+        const double prefac = 2*vdotr/q.r2/tau_e;
+        f.x += prefac*q.dx;
+        f.y += prefac*q.dy;
+        f.z += prefac*q.dz + 2.*q.dvz/tau_inc;
+    }
+    return f;
+}
+
+// src/gas_damping_timescale.c:67-130.  d_factor absent => zero force (the host raises the error).
+__device__ __forceinline__ Vec3 gas_damping(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                            const Particle& p, double d_factor) {
+    Vec3 f = {0.0, 0.0, 0.0};
+    if (is_absent(d_factor)) return f;
+    const double G = fx.scal[0], cs_coeff = fx.scal[1], tau_coeff = fx.scal[2];
+    const Orbit o = orbit_from_particle<true, true, false>(G, p, body);
+    const Rel q = relative(p, body);
+    const double a0 = o.a, e0 = o.e, inc0 = o.inc;
+    const double starMass = body[REBX_B200_BODY_M];
+    const double planetMass = p.m;
+    double coeff;
+    const double vk = sqrt(G*starMass/a0);
+    const double v = sqrt(e0*e0 + inc0*inc0)*vk;
+    const double cs = cs_coeff/sqrt(sqrt(a0));
+    const double v_over_cs = v/cs;
+    if (v <= cs) {
+        coeff = 1.;
+    } else if (inc0 < cs/vk) {
+        coeff = v_over_cs*v_over_cs*v_over_cs;
+    } else {
+        coeff = v_over_cs*v_over_cs*v_over_cs*v_over_cs;
+    }
+    const double tau_e = -tau_coeff*d_factor*a0*a0*(starMass/planetMass)*coeff;
+    const double tau_inc = 2.*tau_e;
+    if (tau_e < INFINITY || tau_inc < INFINITY) {
+        const double vdotr = q.dx*q.dvx + q.dy*q.dvy + q.dz*q.dvz;
+        const double prefac = 2*vdotr/q.r2/tau_e;
+        f.x += prefac*q.dx;
+        f.y += prefac*q.dy;
+        f.z += prefac*q.dz + 2.*q.dvz/tau_inc;
+    }
+    return f;
+}
+
+// src/type_I_migration.c:69-113 (time-scale fits) and :115-203
+__device__ __forceinline__ Vec3 type_I_migration(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                                 const Particle& p) {
+    const double G = fx.scal[0], beta = fx.scal[1], h0 = fx.scal[2], sd0 = fx.scal[3], s = fx.scal[4];
+    const double dedge = fx.scal[5], hedge = fx.scal[6];
+    const Orbit o = orbit_from_particle<true, true, false>(G, p, body);
+    const double a0 = o.a, e0 = o.e, inc0 = o.inc;
+    const double mp = p.m, ms = body[REBX_B200_BODY_M];
+    const Rel q = relative(p, body);
+
+    const double h  = h0*pow(q.r2, beta/2);
+    const double h2 = h*h;
+    const double eh = e0/h;
+    const double ih = inc0/h;
+
+    const double sd   = sd0*pow(sqrt(q.r2), -s);
+    const double wave = (sqrt(ms*ms*ms)*h2*h2)/(mp*sd*sqrt(a0*G));
+
+    const double term  = (eh/2.25);
+    const double term2 = (eh/2.84)*(eh/2.84);
+    const double term3 = (eh/2.02)*(eh/2.02);
+    const double Pe = (1. + pow(term, 1.2) + term2*term2*term2)/(1. - term3*term3);
+    const double t_mig = ((2.*wave)/(2.7 + 1.1*s))*(1/h2)*(Pe + (Pe/fabs(Pe))*((0.070*ih) + (0.085*ih*ih*ih*ih) - (0.080*eh*ih*ih)));
+    const double invtau_mig = planet_trap(a0, dedge, hedge)/t_mig;
+    const double tau_e   = (wave/0.780)*(1. - (0.14*eh*eh) + (0.06*eh*eh*eh) + (0.18*eh*ih*ih));
+    const double tau_inc = (wave/0.544)*(1 - (0.30*ih*ih) + (0.24*ih*ih*ih) + (0.14*eh*eh*ih));
+
+    Vec3 f = {0.0, 0.0, 0.0};
+    if (invtau_mig != 0.0) {
+        f.x = -q.dvx*invtau_mig;
+        f.y = -q.dvy*invtau_mig;
+        f.z = -q.dvz*invtau_mig;
+    }
+    if (tau_e < INFINITY || tau_inc < INFINITY) {
+        const double vdotr = q.dx*q.dvx + q.dy*q.dvy + q.dz*q.dvz;
+        const double prefac = -2*vdotr/q.r2/tau_e;
+        f.x += prefac*q.dx;
+        f.y += prefac*q.dy;
+        f.z += prefac*q.dz - 2*q.dvz/tau_inc;
+    }
+    return f;
+}
+
+}  // namespace rebxb
