@@ -1,0 +1,291 @@
+#!/usr/bin/env python
+"""bench.py -- particle-force evaluations per second of the rebx_additional_forces hot path.
+
+Default workload (BASELINE.json configs[1]): synthetic debris disk, 10^7 test particles per
+GPU, radiation_forces with Poynting-Robertson drag, beta per particle.  One "step" is one
+force evaluation (one dispatch) over the whole ensemble.
+
+  python bench.py --gpus 1 --steps K --warmup W                  # this build
+  torchrun ... bench.py --gpus N ...                             # one rank per GPU, weak scaling
+  python bench.py --impl reference ...                           # the reference's CPU loop
+
+JSON keys (one line, rank 0): value = evals/s with state resident in HBM (CUDA events, max over
+ranks); e2e = evals/s through the REBOUND-facing call sim->additional_forces(sim) on HOST
+particle arrays, host<->device copies inside the timed region; roofline = the sweep kernel's
+algorithmic HBM bytes / its event-timed duration vs the measured copy bandwidth;
+cpu_baseline = the reference's own C loop (oracle/_ref) on one host core, bounded sample.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "particle-force evals/sec"
+WORKLOADS = {
+    # name: (builder, forces in ADD order, default particles per GPU)
+    "debris_disk": ("debris_disk", ["radiation_forces"], 10_000_000),
+    "circumplanetary_ring": ("circumplanetary_ring", ["gravitational_harmonics", "gr_potential"], 10_000_000),
+    "asteroid_ensemble": ("asteroid_ensemble", ["yarkovsky_effect", "gr_potential"], 1_000_000),
+    "planetesimal_disk": ("planetesimal_disk", ["modify_orbits_forces", "gas_damping_timescale", "type_I_migration"], 1_000_000),
+}
+
+
+def parse():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=20)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="ours", choices=["ours", "reference"])
+    ap.add_argument("--workload", default="debris_disk", choices=sorted(WORKLOADS))
+    ap.add_argument("--n", type=int, default=0, help="test particles per GPU (0 = the config's size)")
+    ap.add_argument("--e2e-steps", type=int, default=0, help="steps of the host-facing leg (0 = min(steps, 10))")
+    ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    return ap.parse_args()
+
+
+def peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return float(json.load(f)["hbm_gbs"]), "measured (MEASURED_PEAKS.json hbm_gbs)"
+    return 6650.0, "fallback (B200_PROFILING.md, 6.65 TB/s)"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+
+    def __init__(self, index):
+        self.index, self.proc, self.lines = index, None, []
+
+    def __enter__(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+                                         stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except OSError:
+            self.proc = None
+        return self
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def __exit__(self, *exc):
+        if self.proc:
+            time.sleep(0.15)
+            self.proc.terminate()
+            try:
+                self.proc.wait(timeout=5)
+            except subprocess.TimeoutExpired:
+                self.proc.kill()
+
+    def summary(self):
+        sm, mx, reasons = [], [], set()
+        names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
+        for line in self.lines:
+            parts = [p.strip() for p in line.split(",")]
+            if len(parts) < 7:
+                continue
+            try:
+                sm.append(float(parts[0])); mx.append(float(parts[1]))
+            except ValueError:
+                continue
+            for name, val in zip(names, parts[3:7]):
+                if val.lower().startswith("active"):
+                    reasons.add(name)
+        if not sm:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+
+
+def cpu_reference_leg(workload, add_order, sample_n, reps):
+    """The reference's own C implementation (oracle/_ref, kind "reference") or, if that library
+    was never built, the C restatement (kind "port"), one host thread, bounded sample."""
+    from reboundx_b200 import workloads
+    from oracle import oracle
+    w = getattr(workloads, workload)(sample_n)
+    n = w["x"].shape[0]
+    nf = len(add_order)
+    if oracle.have_ref():
+        _, t = oracle.ref_apply(w, add_order, None, "PARTICLE", reps=reps)
+        kind = "reference"
+    else:
+        best = float("inf")
+        for _ in range(reps + 1):
+            t0 = time.perf_counter()
+            oracle.port_apply(w, add_order[::-1], None, "PARTICLE")
+            best = min(best, time.perf_counter() - t0)
+        t, kind = best, "port"
+    return {"value": (n - 1)*nf/t, "unit": METRIC, "cores": 1, "kind": kind,
+            "sample": f"{workload}: {n - 1} particles x {nf} force(s), best of {reps} dispatches of rebx_additional_forces, 1 thread (the reference dispatch is single-threaded)",
+            "ms_per_dispatch": t*1e3}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return
+    builder, add_order, n_default = WORKLOADS[args.workload]
+    sample = min(args.cpu_sample, args.n or n_default)
+    steps = max(1, args.steps)
+    base = cpu_reference_leg(builder, add_order, sample, steps)
+    line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "evals/s", "n_gpus": args.gpus,
+            "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_dispatch"], "higher_is_better": True,
+            "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
+            "config": {"workload": f"{args.workload}: {'+'.join(add_order)}, bounded sample of {sample} test particles on host cores"},
+            "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
+            "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
+    line["cpu_baseline"]["unit"] = "evals/s"
+    print(json.dumps(line), flush=True)
+
+
+def run_ours(args):
+    import torch
+    import torch.distributed as dist
+    from reboundx_b200 import device, scenarios, workloads
+
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    if not torch.cuda.is_available():
+        raise SystemExit("bench.py: no CUDA device; the force path has no CPU fallback")
+    torch.cuda.set_device(local)
+    os.environ["REBX_B200_DEVICE"] = str(local)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+    dev = f"cuda:{local}"
+    builder, add_order, n_default = WORKLOADS[args.workload]
+    n = args.n or n_default
+    exec_order = add_order[::-1]
+    nf = len(add_order)
+
+    # Weak scaling: every rank owns n test particles of one global ensemble of world*n; the
+    # central body (global index 0) is replicated and broadcast from rank 0 every evaluation.
+    w = getattr(workloads, builder)(n, seed=3 + rank)
+    lo = 0 if rank == 0 else 1
+    shard = device.Shard(w, exec_order, dev, lo=lo, index_base=(0 if rank == 0 else 1 + rank*n))
+    n_local = shard.n - (1 if rank == 0 else 0)          # the body itself is not an evaluation
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    group = None
+    for _ in range(max(3, args.warmup)):
+        shard.evaluate(group)
+    barrier()
+
+    # ---- resident leg: K evaluations, CUDA events on the launching stream, max over ranks -------
+    launches0 = shard.launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    with ClockSampler(local) as clocks:
+        barrier()
+        e0.record()
+        for _ in range(args.steps):
+            shard.evaluate(group)
+        e1.record()
+        barrier()
+    ms_total = e0.elapsed_time(e1)
+    gpu_launches = shard.launches - launches0
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_step = float(t.item())/args.steps
+    value = world*n*nf/(ms_step*1e-3)
+
+    # ---- roofline of the dominant kernel (the fused sweep), timed alone per launch ---------------
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(args.steps):
+        shard.launch()
+    k1.record()
+    torch.cuda.synchronize()
+    kernel_ms = k0.elapsed_time(k1)/args.steps
+    peak, peak_src = peaks()
+    achieved = shard.algorithmic_bytes/(kernel_ms*1e-3)/1e9
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
+                "traffic": None, "kernel": "pass_kernel<V=2>(%s)" % ",".join(exec_order),
+                "algorithmic_bytes_per_particle": device.algorithmic_bytes_per_particle(shard.kinds),
+                "kernel_ms": kernel_ms, "peak_source": peak_src}
+    prof = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(prof):
+        with open(prof) as f:
+            roofline["traffic"] = json.load(f).get(args.workload)
+
+    # ---- end-to-end leg: the REBOUND-facing call on host particle arrays ---------------------------
+    e2e = None
+    if not args.no_e2e:
+        del shard
+        torch.cuda.empty_cache()
+        sim, rebx, _ = scenarios.build(w, add_order)
+        for _ in range(2):
+            sim.additional_forces()
+        sim.process_messages()
+        s0 = rebx.stats()
+        steps = args.e2e_steps or min(args.steps, 10)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(steps):
+            sim.additional_forces()            # synchronous: accelerations are valid on return
+        dt = time.perf_counter() - t0
+        s1 = rebx.stats()
+        sim.process_messages()
+        tt = torch.tensor([dt], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        dt = float(tt.item())
+        e2e = {"value": world*n*nf*steps/dt, "unit": "evals/s",
+               "h2d_bytes_per_step": (s1["h2d_bytes"] - s0["h2d_bytes"])//steps,
+               "d2h_bytes_per_step": (s1["d2h_bytes"] - s0["d2h_bytes"])//steps,
+               "ms_per_step": dt/steps*1e3, "steps": steps,
+               "launches_per_step": (s1["launches"] - s0["launches"])//steps,
+               "call": "sim->additional_forces(sim) == rebx_additional_forces, host AoS particles (cudaHostRegister-pinned)"}
+        rebx.detach()
+        sim.free()
+
+    cpu = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        cpu = cpu_reference_leg(builder, add_order, min(args.cpu_sample, n), 5)
+        cpu["unit"] = "evals/s"
+        cpu.pop("ms_per_dispatch")
+
+    if rank == 0:
+        line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
+                "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+                "data": "synthetic",
+                "config": {"workload": f"{args.workload}: {n} test particles per GPU, {'+'.join(add_order)}",
+                           "particles_per_gpu": n, "forces": add_order,
+                           "l2": f"inputs larger than L2 ({shard_bytes(n, exec_order)/1e6:.0f} MB streamed per step)",
+                           "sharding": "index ranges; body state broadcast per step (NCCL) when n_gpus > 1"},
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+                "clocks": clocks.summary()}
+        print(json.dumps(line), flush=True)
+    if world > 1:
+        dist.destroy_process_group()
+
+
+def shard_bytes(n, exec_order):
+    from reboundx_b200 import device
+    return device.algorithmic_bytes_per_particle([device.KIND[k] for k in exec_order])*n
+
+
+if __name__ == "__main__":
+    a = parse()
+    if a.impl == "reference":
+        run_reference(a)
+    else:
+        run_ours(a)

@@ -100,7 +100,8 @@ def _full(w, name, n):
 
 def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE"):
     """Runs the C restatement on workload `w`; `exec_order` is the EXECUTION order of forces.
-    Returns ((ax, ay, az), {force: long-double back-reaction sum})."""
+    Returns ((ax, ay, az), {force: [sum_x, sum_y, sum_z, abs_x, abs_y, abs_z]}): the back-reaction
+    terms onto the body summed in long double, and the sum of their absolute values."""
     lib = _port()
     n = w["x"].shape[0]
     S = {k: np.ascontiguousarray(w[k], dtype=np.float64) for k in ("x", "y", "z", "vx", "vy", "vz", "m", "r")}
@@ -108,7 +109,7 @@ def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE"):
     br = {}
     keep = []
     for name in exec_order:
-        out = (c_longdouble*3)()
+        out = (c_longdouble*6)()
         if name == "radiation_forces":
             beta, mask = _full(w, "beta", n)
             keep += [beta, mask]

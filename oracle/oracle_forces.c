@@ -96,7 +96,9 @@ void oracle_radiation_forces(int64_t n, const double* x, const double* y, const 
 
 /* reference src/gravitational_harmonics.c:136-226 for ONE oblate body `bi`
  * (J2 != 0 and R_eq set are the caller's responsibility; J4 == 0 means unset).
- * br[3] (may be NULL) receives the back-reaction sum accumulated in long double. */
+ * br[6] (may be NULL) receives the back-reaction sum accumulated in long double (br[0..2])
+ * and the sum of the terms' absolute values (br[3..5], the scale a reduction's rounding
+ * error is measured against). */
 void oracle_gravitational_harmonics(int64_t n, const double* x, const double* y, const double* z, const double* m,
                                     int64_t bi, double J2, double J4, double R_eq, const double Omega[3], double G,
                                     double* ax, double* ay, double* az, long double* br) {
@@ -108,7 +110,7 @@ void oracle_gravitational_harmonics(int64_t n, const double* x, const double* y,
     const double wx = sx, wy = sy, wz = sz;
     const double vx_ = -(uy*wz - uz*wy), vy_ = -(uz*wx - ux*wz), vz_ = -(ux*wy - uy*wx);
     const double bx = x[bi], by = y[bi], bz = z[bi], bm = m[bi];
-    long double bsx = 0, bsy = 0, bsz = 0;
+    long double bsx = 0, bsy = 0, bsz = 0, bax = 0, bay = 0, baz = 0;
     for (int64_t j = 0; j < n; j++) {
         if (j == bi) continue;
         const double dx = x[j] - bx, dy = y[j] - by, dz = z[j] - bz;
@@ -139,8 +141,9 @@ void oracle_gravitational_harmonics(int64_t n, const double* x, const double* y,
         const double fac = m[j]/bm;
         ax[bi] -= fac*fx; ay[bi] -= fac*fy; az[bi] -= fac*fz;
         bsx -= (long double)(fac*fx); bsy -= (long double)(fac*fy); bsz -= (long double)(fac*fz);
+        bax += fabsl((long double)(fac*fx)); bay += fabsl((long double)(fac*fy)); baz += fabsl((long double)(fac*fz));
     }
-    if (br) { br[0] = bsx; br[1] = bsy; br[2] = bsz; }
+    if (br) { br[0] = bsx; br[1] = bsy; br[2] = bsz; br[3] = bax; br[4] = bay; br[5] = baz; }
 }
 
 /* reference src/gr_potential.c:60-89 */
@@ -149,7 +152,7 @@ void oracle_gr_potential(int64_t n, const double* x, const double* y, const doub
     const double C2 = c*c;
     const double sx = x[0], sy = y[0], sz = z[0], sm = m[0];
     const double prefac1 = 6.*(G*sm)*(G*sm)/C2;
-    long double bsx = 0, bsy = 0, bsz = 0;
+    long double bsx = 0, bsy = 0, bsz = 0, bax = 0, bay = 0, baz = 0;
     for (int64_t i = 1; i < n; i++) {
         const double dx = x[i] - sx, dy = y[i] - sy, dz = z[i] - sz;
         const double r2 = dx*dx + dy*dy + dz*dz;
@@ -158,8 +161,9 @@ void oracle_gr_potential(int64_t n, const double* x, const double* y, const doub
         const double tx = m[i]/sm*prefac*dx, ty = m[i]/sm*prefac*dy, tz = m[i]/sm*prefac*dz;
         ax[0] += tx; ay[0] += ty; az[0] += tz;
         bsx += (long double)tx; bsy += (long double)ty; bsz += (long double)tz;
+        bax += fabsl((long double)tx); bay += fabsl((long double)ty); baz += fabsl((long double)tz);
     }
-    if (br) { br[0] = bsx; br[1] = bsy; br[2] = bsz; }
+    if (br) { br[0] = bsx; br[1] = bsy; br[2] = bsz; br[3] = bax; br[4] = bay; br[5] = baz; }
 }
 
 /* reference src/yarkovsky_effect.c:76-248.  flag values outside {-1,0,1} and particles whose
@@ -325,8 +329,8 @@ static body_t com_all(int64_t n, const double* x, const double* y, const double*
 
 /* Returns 0, or 1 when PARTICLE coordinates are requested and `primary` < 0 (the reference
  * reports an error there).  Sequential, i = n-1 .. 0, O(n^2) in Jacobi/barycentric mode exactly
- * like the reference.  br[3] (may be NULL): long-double sum of the terms put on the primary
- * (PARTICLE mode only). */
+ * like the reference.  br[6] (may be NULL): long-double sum of the terms put on the primary and
+ * the sum of their absolute values (PARTICLE mode only). */
 int oracle_com_force(int kind, int coordinates, int64_t primary, const oracle_damping_params* P, double G,
                      int64_t n, const double* x, const double* y, const double* z,
                      const double* vx, const double* vy, const double* vz, const double* m,
@@ -340,7 +344,7 @@ int oracle_com_force(int kind, int coordinates, int64_t primary, const oracle_da
         com.x = x[primary]; com.y = y[primary]; com.z = z[primary];
         com.vx = vx[primary]; com.vy = vy[primary]; com.vz = vz[primary]; com.m = m[primary];
     }
-    long double bsx = 0, bsy = 0, bsz = 0;
+    long double bsx = 0, bsy = 0, bsz = 0, bax = 0, bay = 0, baz = 0;
     for (int64_t i = n - 1; i >= 0; i--) {
         if (i == refindex) continue;
         if (coordinates == ORACLE_JACOBI) {         /* rebx_get_com_without_particle, rebxtools.c:6-30 */
@@ -364,8 +368,9 @@ int oracle_com_force(int kind, int coordinates, int64_t primary, const oracle_da
             ax[i] -= massratio*f[0]; ay[i] -= massratio*f[1]; az[i] -= massratio*f[2];
             ax[refindex] -= massratio*f[0]; ay[refindex] -= massratio*f[1]; az[refindex] -= massratio*f[2];
             bsx -= (long double)(massratio*f[0]); bsy -= (long double)(massratio*f[1]); bsz -= (long double)(massratio*f[2]);
+            bax += fabsl((long double)(massratio*f[0])); bay += fabsl((long double)(massratio*f[1])); baz += fabsl((long double)(massratio*f[2]));
         }
     }
-    if (br) { br[0] = bsx; br[1] = bsy; br[2] = bsz; }
+    if (br) { br[0] = bsx; br[1] = bsy; br[2] = bsz; br[3] = bax; br[4] = bay; br[5] = baz; }
     return 0;
 }

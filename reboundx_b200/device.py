@@ -1,0 +1,221 @@
+"""Resident-state front end of the device layer (include/rebx_b200.h).
+
+A ``Shard`` keeps one contiguous index range of an ensemble as SoA tensors in HBM together
+with the SoA parameter tables of the attached effects, and applies them with one call of
+``rebx_b200_launch_pass`` per force evaluation.  torch is used for device memory, streams
+and (in ``sync_bodies`` / ``reduce_backreaction``) torch.distributed plumbing only; every
+kernel is this package's own CUDA code reached through the C-ABI with raw pointers.
+
+Sharding: particles are split by index range across ranks; the O(1)
+source / primary bodies are replicated in a small ``bodies`` tensor that rank 0 broadcasts
+each evaluation; back-reaction sums (3 doubles per effect) are all-reduced and applied by
+the rank that owns the body.
+"""
+import ctypes
+from ctypes import POINTER, Structure, c_double, c_int, c_int32, c_int64, c_void_p
+
+import numpy as np
+
+from . import _lib
+
+MAX_EFFECTS, BODY_DOUBLES, MAX_TABLES, MAX_SCALARS = 4, 24, 9, 8
+ABSENT_BITS = 0x7ff8b200dead0001
+ABSENT = np.frombuffer(np.uint64(ABSENT_BITS).tobytes(), dtype=np.float64)[0]
+
+KIND = {"radiation_forces": 1, "gravitational_harmonics": 2, "gr_potential": 3, "yarkovsky_effect": 4,
+        "modify_orbits_forces": 5, "gas_damping_timescale": 6, "type_I_migration": 7}
+FLAG_TRAP, FLAG_BARYCENTRIC = 1, 2
+# algorithmic HBM bytes per particle of ONE fused pass: state read once,
+# acceleration read + written, parameter tables read once
+STATE_BYTES = {"pos": 24, "vel": 24, "m": 8, "r": 8, "acc_rw": 48}
+NEEDS = {1: ("vel",), 2: ("m",), 3: ("m",), 4: ("vel", "m", "r"), 5: ("vel", "m"), 6: ("vel", "m"), 7: ("vel", "m")}
+TABLE_BYTES = {1: 8, 2: 0, 3: 0, 4: 9*8 + 4, 5: 24, 6: 8, 7: 0}
+
+
+class CState(Structure):
+    _fields_ = [("n", c_int64), ("index_base", c_int64)] + [(k, c_void_p) for k in
+                ("x", "y", "z", "vx", "vy", "vz", "m", "r", "ax", "ay", "az")]
+
+
+class CEffect(Structure):
+    _fields_ = [("kind", c_int32), ("flags", c_int32), ("body", c_void_p), ("tab", c_void_p*MAX_TABLES),
+                ("itab", c_void_p), ("scal", c_double*MAX_SCALARS), ("backreaction", c_void_p)]
+
+
+class CPass(Structure):
+    _fields_ = [("st", CState), ("n_effects", c_int32), ("reserved", c_int32), ("fx", CEffect*MAX_EFFECTS)]
+
+
+def algorithmic_bytes_per_particle(kinds):
+    needs = {"pos", "acc_rw"}
+    for k in kinds:
+        needs.update(NEEDS[k])
+    return sum(STATE_BYTES[s] for s in needs) + sum(TABLE_BYTES[k] for k in kinds)
+
+
+def spin_frame(Omega):
+    """Body-fixed frame of an oblate body (reference src/gravitational_harmonics.c:104-134)."""
+    ox, oy, oz = (float(v) for v in Omega)
+    omega = np.sqrt(ox*ox + oy*oy + oz*oz)
+    sx, sy, sz = ox/omega, oy/omega, oz/omega
+    fac = np.sqrt(sx*sx + sy*sy)
+    u = (-sy/fac, sx/fac, 0.0) if fac != 0.0 else (1.0, 0.0, 0.0)
+    w = (sx, sy, sz)
+    v = (-(u[1]*w[2] - u[2]*w[1]), -(u[2]*w[0] - u[0]*w[2]), -(u[0]*w[1] - u[1]*w[0]))
+    return u, v, w
+
+
+class Shard:
+    """Particles [lo, hi) of a workload, resident on `device`, with `exec_order` effects."""
+
+    def __init__(self, w, exec_order, device, lo=0, hi=None, coordinates="PARTICLE", acc0=None, index_base=None):
+        import torch
+        self.torch = torch
+        self.lib = lib = _lib.load()
+        lib.rebx_b200_launch_pass.restype = c_int
+        lib.rebx_b200_apply_backreaction.restype = c_int
+        lib.rebx_b200_workspace_bytes.restype = ctypes.c_size_t
+        lib.rebx_b200_error_string.restype = ctypes.c_char_p
+        if not torch.cuda.is_available() or lib.rebx_b200_device_count() < 1:
+            raise RuntimeError("reboundx_b200.device needs a CUDA device: the force path has no CPU fallback")
+        self.device = torch.device(device)
+        n_total = w["x"].shape[0]
+        hi = n_total if hi is None else hi
+        self.lo, self.hi, self.n = lo, hi, hi - lo
+        # global index of element `lo` (differs from `lo` when `w` is itself one rank's slice of a
+        # larger ensemble that replicates the central body at local index 0)
+        self.index_base = lo if index_base is None else index_base
+        self.exec_order = list(exec_order)
+        if not 1 <= len(self.exec_order) <= MAX_EFFECTS:
+            raise ValueError("1..4 stacked effects per pass")
+        self.kinds = [KIND[name] for name in self.exec_order]
+
+        def dev(a, dtype=torch.float64):
+            return torch.from_numpy(np.ascontiguousarray(a)).to(self.device, dtype=dtype)
+
+        self.state = {k: dev(w[k][lo:hi]) for k in ("x", "y", "z", "vx", "vy", "vz", "m", "r")}
+        for i, k in enumerate(("ax", "ay", "az")):
+            self.state[k] = dev(acc0[i][lo:hi]) if acc0 is not None else torch.zeros(self.n, dtype=torch.float64, device=self.device)
+
+        def table(name):
+            full = np.full(n_total, ABSENT)
+            full[1:] = w[name]
+            return dev(full[lo:hi])
+
+        # body records (host master copy, refreshed from the global state by the owner rank)
+        self.bodies_host = np.zeros((len(self.kinds), BODY_DOUBLES))
+        self.tables, self.itables, self.scalars, self.flags = [], [], [], []
+        for e, (name, kind) in enumerate(zip(self.exec_order, self.kinds)):
+            tabs, itab, scal, flags = [], None, [w["G"]] + [0.0]*(MAX_SCALARS - 1), 0
+            self.bodies_host[e, 0] = 0.0
+            self.bodies_host[e, 1:8] = [w[k][0] for k in ("x", "y", "z", "vx", "vy", "vz", "m")]
+            if kind == 1:
+                tabs = [table("beta")]
+                scal[1] = w["c"]
+            elif kind == 2:
+                u, v, ww = spin_frame(w.get("Omega") or (0.0, 0.0, 1.0))
+                self.bodies_host[e, 8:11] = [w["J2"], w.get("J4") or 0.0, w["R_eq"]]
+                self.bodies_host[e, 11:14], self.bodies_host[e, 14:17], self.bodies_host[e, 17:20] = u, v, ww
+            elif kind == 3:
+                scal[1] = w["c"]*w["c"]
+            elif kind == 4:
+                names = ["ye_body_density", "ye_rotation_period", "ye_thermal_inertia", "ye_albedo", "ye_emissivity",
+                         "ye_k", "ye_spin_axis_x", "ye_spin_axis_y", "ye_spin_axis_z"]
+                tabs = [table(p) for p in names]
+                code = np.full(n_total, 2, dtype=np.int32)
+                code[1:] = w["ye_flag"]
+                itab = dev(code[lo:hi], dtype=torch.int32)
+                scal[1:4] = [w["ye_lstar"], w["ye_c"], w["ye_stef_boltz"]]
+            elif kind == 5:
+                tabs = [table(p) for p in ("tau_a", "tau_e", "tau_inc")]
+                if w.get("ide_position") is not None and w.get("ide_width") is not None:
+                    flags |= FLAG_TRAP
+                    scal[1:3] = [w["ide_position"], w["ide_width"]]
+            elif kind == 6:
+                tabs = [table("d_factor")]
+                scal[1:3] = [w["cs_coeff"], w["tau_coeff"]]
+            elif kind == 7:
+                scal[1:7] = [w.get("tIm_flaring_index") or 0.0,
+                             0.01 if w.get("tIm_scale_height_1") is None else w["tIm_scale_height_1"],
+                             w.get("tIm_surface_density_1") or 0.0, w.get("tIm_surface_density_exponent") or 0.0,
+                             w.get("ide_position") or 0.0, w.get("ide_width") or 0.0]
+            if kind in (5, 6, 7) and coordinates != "PARTICLE":
+                raise NotImplementedError("resident shards support PARTICLE coordinates")
+            self.tables.append(tabs)
+            self.itables.append(itab)
+            self.scalars.append(scal)
+            self.flags.append(flags)
+        self.bodies = dev(self.bodies_host)
+        self.backreaction = torch.zeros((len(self.kinds), 3), dtype=torch.float64, device=self.device)
+        self.workspace = torch.empty(lib.rebx_b200_workspace_bytes(), dtype=torch.uint8, device=self.device)
+        self.launches = 0
+        self._pass = self._make_pass()
+
+    # ------------------------------------------------------------------------------------------
+    def _make_pass(self):
+        P = CPass()
+        P.st.n, P.st.index_base = self.n, self.index_base
+        for k in ("x", "y", "z", "vx", "vy", "vz", "m", "r", "ax", "ay", "az"):
+            setattr(P.st, k, self.state[k].data_ptr())
+        P.n_effects = len(self.kinds)
+        for e, kind in enumerate(self.kinds):
+            fx = P.fx[e]
+            fx.kind, fx.flags = kind, self.flags[e]
+            fx.body = self.bodies.data_ptr() + e*BODY_DOUBLES*8
+            for j, t in enumerate(self.tables[e]):
+                fx.tab[j] = t.data_ptr()
+            fx.itab = self.itables[e].data_ptr() if self.itables[e] is not None else None
+            for j, v in enumerate(self.scalars[e]):
+                fx.scal[j] = float(v)
+            fx.backreaction = self.backreaction.data_ptr() + e*3*8
+        return P
+
+    @property
+    def algorithmic_bytes(self):
+        """HBM bytes one pass must move for this shard (the roofline numerator)."""
+        return algorithmic_bytes_per_particle(self.kinds)*self.n
+
+    def _check(self, rc, what):
+        if rc != 0:
+            raise RuntimeError(f"{what} failed: {self.lib.rebx_b200_error_string(c_int(rc)).decode()}")
+
+    def sync_bodies(self, group=None, src=0):
+        """Active-body state broadcast (NCCL over NVLink when a process group is up)."""
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.broadcast(self.bodies, src=src, group=group)
+
+    def launch(self, stream=None):
+        """One force evaluation of the shard: a += sum of the stacked effects (asynchronous)."""
+        s = self.torch.cuda.current_stream(self.device) if stream is None else stream
+        n = c_int(0)
+        rc = self.lib.rebx_b200_launch_pass(ctypes.byref(self._pass), c_void_p(self.workspace.data_ptr()),
+                                            c_void_p(s.cuda_stream), ctypes.byref(n))
+        self._check(rc, "rebx_b200_launch_pass")
+        self.launches += n.value
+        return n.value
+
+    def reduce_backreaction(self, group=None):
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
+            dist.all_reduce(self.backreaction, group=group)
+
+    def apply_backreaction(self, stream=None):
+        s = self.torch.cuda.current_stream(self.device) if stream is None else stream
+        n = c_int(0)
+        rc = self.lib.rebx_b200_apply_backreaction(ctypes.byref(self._pass), c_void_p(s.cuda_stream), ctypes.byref(n))
+        self._check(rc, "rebx_b200_apply_backreaction")
+        self.launches += n.value
+        return n.value
+
+    def evaluate(self, group=None):
+        """Full evaluation incl. the multi-GPU exchange steps; returns kernels launched."""
+        self.sync_bodies(group)
+        k = self.launch()
+        if any(kind != 1 and kind != 4 for kind in self.kinds):
+            self.reduce_backreaction(group)
+            k += self.apply_backreaction()
+        return k
+
+    def acc(self):
+        return [self.state[k].cpu().numpy() for k in ("ax", "ay", "az")]

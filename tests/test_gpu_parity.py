@@ -1,0 +1,234 @@
+"""GPU parity tests proper: the CUDA path, called through the drop-in C-ABI exactly as REBOUND
+would call it (sim->additional_forces on host AoS particles), against the oracle on the same
+seeded inputs.  Oracle = the reference's own sources compiled in place (oracle/_ref) when
+present, else the C restatement (bit-identical to it, tests/test_oracle.py)."""
+import numpy as np
+import pytest
+
+from parity import TOL, errors
+
+pytestmark = pytest.mark.gpu
+
+TRIO = ["modify_orbits_forces", "gas_damping_timescale", "type_I_migration"]
+
+
+def oracle_acc(w, add_order, acc0, coordinates="PARTICLE"):
+    from oracle import oracle
+    want, br = oracle.port_apply(w, add_order[::-1], acc0, coordinates)
+    if oracle.have_ref():
+        ref = oracle.ref_apply(w, add_order, acc0, coordinates)
+        for k in range(3):          # the restatement IS the reference, bit for bit
+            assert np.array_equal(np.array(ref[k]), want[k])
+    return want, br
+
+
+def device_acc(w, add_order, acc0, coordinates="PARTICLE"):
+    from reboundx_b200 import scenarios
+    sim, rebx, handles = scenarios.build(w, add_order, coordinates=coordinates, acc=acc0)
+    sim.additional_forces()
+    sim.process_messages()
+    out = sim.acc()
+    stats = rebx.stats()
+    rebx.detach()
+    sim.free()
+    assert stats["launches"] >= 1, "no CUDA kernel was launched"
+    return out, stats
+
+
+def acc_variants(w, seed):
+    from reboundx_b200 import workloads
+    return {"zero": None, "gravity": workloads.gravity_like_acc(w, np.random.default_rng(seed))}
+
+
+@pytest.mark.parametrize("n", [1, 2, 1000, 40001])
+@pytest.mark.parametrize("base", ["zero", "gravity"])
+def test_radiation_forces_bit_exact(built, n, base):
+    """Config 1/2 shape: star + dust, beta per particle (reference src/radiation_forces.c)."""
+    from reboundx_b200 import workloads
+    w = workloads.debris_disk(n)
+    acc0 = acc_variants(w, 1)[base]
+    want, _ = oracle_acc(w, ["radiation_forces"], acc0)
+    got, _ = device_acc(w, ["radiation_forces"], acc0)
+    e = errors(got, want)
+    assert e["bit_identical"], e
+
+
+@pytest.mark.parametrize("order", [["gravitational_harmonics", "gr_potential"], ["gr_potential", "gravitational_harmonics"]])
+@pytest.mark.parametrize("tilted", [False, True])
+def test_harmonics_gr_potential_test_particles(built, order, tilted):
+    """Config 3: oblate planet + massless ring, J2/J4 fused with gr_potential, both LIFO orders."""
+    from reboundx_b200 import workloads
+    w = workloads.circumplanetary_ring(30001, tilted=tilted)
+    for base, acc0 in acc_variants(w, 2).items():
+        want, _ = oracle_acc(w, order, acc0)
+        got, stats = device_acc(w, order, acc0)
+        e = errors(got, want)
+        assert e["bit_identical"], (base, e)
+
+
+def test_harmonics_gr_potential_massive_ring_backreaction(built):
+    """Massive ring particles: per-particle results stay bit-exact; the back-reaction summed onto
+    the planet is a parallel reduction and is compared with the exactly (long double) summed
+    terms, tolerance relative to the sum of |terms|."""
+    from reboundx_b200 import workloads
+    order = ["gravitational_harmonics", "gr_potential"]
+    w = workloads.circumplanetary_ring(30001, tilted=True, massive=True)
+    acc0 = acc_variants(w, 3)["gravity"]
+    want, br = oracle_acc(w, order, acc0)
+    got, _ = device_acc(w, order, acc0)
+    e = errors(got, want, skip=(0,))
+    assert e["bit_identical"], e
+    exact = np.array([acc0[k][0] for k in range(3)]) + br["gravitational_harmonics"][:3] + br["gr_potential"][:3]
+    scale = br["gravitational_harmonics"][3:] + br["gr_potential"][3:] + np.abs([acc0[k][0] for k in range(3)])
+    for k in range(3):
+        assert abs(got[k][0] - exact[k]) <= TOL*scale[k], (k, got[k][0], exact[k], scale[k])
+        assert abs(want[k][0] - exact[k]) <= 1e-11*scale[k]      # the reference's own sequential sum
+
+
+@pytest.mark.parametrize("base", ["zero", "gravity"])
+def test_yarkovsky_gr_potential(built, base):
+    """Config 4: all three ye_flag modes, per-particle parameters, fused with gr_potential."""
+    from reboundx_b200 import workloads
+    order = ["yarkovsky_effect", "gr_potential"]
+    w = workloads.asteroid_ensemble(30001)
+    acc0 = acc_variants(w, 4)[base]
+    want, _ = oracle_acc(w, order, acc0)
+    got, _ = device_acc(w, order, acc0)
+    e = errors(got, want, skip=(0,))
+    # libdevice pow/atan/sin/cos vs glibc: not bit-identical; norm-wise within tolerance always
+    assert e["max_normwise"] <= TOL, e
+    assert e["frac_component_above_tol"] <= 1e-4, e
+    simple = np.concatenate([[False], w["ye_flag"] != 0])
+    es = errors([g[simple] for g in got], [x[simple] for x in want])
+    assert es["bit_identical"], es          # simple versions use + - * / sqrt only
+
+
+@pytest.mark.parametrize("add_order", [TRIO, TRIO[::-1], ["modify_orbits_forces"], ["type_I_migration", "gas_damping_timescale"]])
+def test_damping_trio_particle_coordinates(built, add_order):
+    """Config 5 in REBX_COORDINATES_PARTICLE (the O(N) mode of the reference)."""
+    from reboundx_b200 import workloads
+    w = workloads.planetesimal_disk(30001)
+    acc0 = acc_variants(w, 5)["gravity"]
+    want, br = oracle_acc(w, add_order, acc0)
+    got, _ = device_acc(w, add_order, acc0)
+    e = errors(got, want, skip=(0,))
+    assert e["max_normwise"] <= TOL, e
+    assert e["frac_component_above_tol"] <= 5e-3, e
+    exact = np.array([acc0[k][0] for k in range(3)]) + sum(br[f][:3] for f in add_order)
+    scale = sum(br[f][3:] for f in add_order) + np.abs([acc0[k][0] for k in range(3)])
+    for k in range(3):
+        assert abs(got[k][0] - exact[k]) <= 1e-12*scale[k], (k, got[k][0], exact[k], scale[k])
+
+
+def test_modify_orbits_without_trap_bit_exact(built):
+    """modify_orbits_forces without the planet trap uses + - * / only: bit-identical."""
+    from reboundx_b200 import workloads
+    w = workloads.planetesimal_disk(20001)
+    w["ide_position"] = None
+    w["ide_width"] = None
+    acc0 = acc_variants(w, 6)["gravity"]
+    want, _ = oracle_acc(w, ["modify_orbits_forces"], acc0)
+    got, _ = device_acc(w, ["modify_orbits_forces"], acc0)
+    assert errors(got, want, skip=(0,))["bit_identical"]
+
+
+def test_resident_shards_match_host_path(built):
+    """The resident SoA entry (reboundx_b200.device.Shard) over two index-range shards gives the
+    same accelerations as the host-facing call over the whole ensemble."""
+    import torch
+    from reboundx_b200 import device, workloads
+    w = workloads.debris_disk(50001)
+    acc0 = acc_variants(w, 7)["gravity"]
+    want, _ = oracle_acc(w, ["radiation_forces"], acc0)
+    n = w["x"].shape[0]
+    cut = 20000
+    parts = []
+    for lo, hi in ((0, cut), (cut, n)):
+        sh = device.Shard(w, ["radiation_forces"], "cuda:0", lo=lo, hi=hi, acc0=acc0)
+        sh.evaluate()
+        torch.cuda.synchronize()
+        parts.append(sh.acc())
+    got = [np.concatenate([p[k] for p in parts]) for k in range(3)]
+    assert errors(got, want)["bit_identical"]
+
+
+def test_resident_backreaction_two_shards(built):
+    """Back-reaction across shards: per-shard sums added, applied by the shard owning the body."""
+    import torch
+    from reboundx_b200 import device, workloads
+    order = ["gravitational_harmonics", "gr_potential"]
+    w = workloads.circumplanetary_ring(30001, massive=True)
+    acc0 = acc_variants(w, 8)["gravity"]
+    want, br = oracle_acc(w, order, acc0)
+    n = w["x"].shape[0]
+    shards = [device.Shard(w, order[::-1], "cuda:0", lo=lo, hi=hi, acc0=acc0) for lo, hi in ((0, 15000), (15000, n))]
+    for sh in shards:
+        sh.launch()
+    total = shards[0].backreaction + shards[1].backreaction       # what the NCCL all-reduce computes
+    for sh in shards:
+        sh.backreaction.copy_(total)
+        sh.apply_backreaction()
+    torch.cuda.synchronize()
+    got = [np.concatenate([sh.acc()[k] for sh in shards]) for k in range(3)]
+    assert errors(got, want, skip=(0,))["bit_identical"]
+    exact = np.array([acc0[k][0] for k in range(3)]) + sum(br[f][:3] for f in order)
+    scale = sum(br[f][3:] for f in order) + np.abs([acc0[k][0] for k in range(3)])
+    for k in range(3):
+        assert abs(got[k][0] - exact[k]) <= TOL*scale[k]
+
+
+def test_dirty_tracking_and_custom_host_force(built):
+    """Tables are rebuilt when (and only when) a parameter changes; a custom host force keeps
+    running through the same dispatcher between device sweeps."""
+    from reboundx_b200 import scenarios, workloads
+    from reboundx_b200.host import RebParticle
+    w = workloads.debris_disk(5000)
+    sim, rebx, handles = scenarios.build(w, ["radiation_forces"])
+    calls = []
+
+    def kick(simp, forcep, particles, N):
+        calls.append(N)
+        particles[1].ax += 1.0
+
+    custom = rebx.create_force("kick")
+    custom.force_type = "pos"
+    custom.update_accelerations = kick
+    rebx.add_force(custom)
+    sim.additional_forces(); sim.process_messages()
+    s1 = rebx.stats()
+    a1 = sim.acc()
+    sim.set_acc()
+    sim.additional_forces(); sim.process_messages()
+    s2 = rebx.stats()
+    a2 = sim.acc()
+    assert calls == [sim.N, sim.N]
+    assert s2["table_builds"] == s1["table_builds"], "tables rebuilt although nothing changed"
+    assert np.array_equal(a1[0], a2[0])
+    rebx.particle_params(7)["beta"] = 0.9
+    sim.set_acc()
+    sim.additional_forces(); sim.process_messages()
+    s3 = rebx.stats()
+    a3 = sim.acc()
+    assert s3["table_builds"] == s2["table_builds"] + 1
+    assert a3[0][7] != a2[0][7] and np.array_equal(np.delete(a3[0], 7), np.delete(a2[0], 7))
+    w2 = dict(w); w2["beta"] = w["beta"].copy(); w2["beta"][6] = 0.9
+    want, _ = oracle_acc(w2, ["radiation_forces"], None)
+    want[0][1] += 1.0
+    assert errors(a3, want)["bit_identical"]
+
+
+def test_multi_chunk_pipeline(built, monkeypatch):
+    """Small chunk size forces the double-buffered H2D/kernel/D2H pipeline through many chunks
+    (odd sizes, ragged tail) and must not change a single bit."""
+    from reboundx_b200 import workloads
+    monkeypatch.setenv("REBX_B200_CHUNK", "4096")
+    order = ["gravitational_harmonics", "gr_potential"]
+    w = workloads.circumplanetary_ring(33333, massive=True)
+    acc0 = acc_variants(w, 9)["gravity"]
+    want, br = oracle_acc(w, order, acc0)
+    got, stats = device_acc(w, order, acc0)
+    assert errors(got, want, skip=(0,))["bit_identical"]
+    exact = np.array([acc0[k][0] for k in range(3)]) + sum(br[f][:3] for f in order)
+    scale = sum(br[f][3:] for f in order) + np.abs([acc0[k][0] for k in range(3)])
+    for k in range(3):
+        assert abs(got[k][0] - exact[k]) <= TOL*scale[k]
