@@ -173,3 +173,98 @@ def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE"):
         else:
             raise ValueError(name)
     return acc, br
+
+
+# ---- general cases (reboundx_b200.scenarios.build_case format) -------------------------------------
+def _pp(case, name, n, dtype=np.float64):
+    """(values[n], present[n]) of a per-particle parameter, or (None, zeros) when nobody has it."""
+    ent = case.get("particle_params", {}).get(name)
+    vals = np.zeros(n, dtype=dtype)
+    mask = np.zeros(n, dtype=np.uint8)
+    if ent is not None and len(ent[0]):
+        idx = np.asarray(ent[0], dtype=np.int64)
+        vals[idx] = np.asarray(ent[1], dtype=dtype)
+        mask[idx] = 1
+    return vals, mask
+
+
+def port_case(case):
+    """Runs the C restatement on a general case; returns (ax, ay, az).  Forces execute in
+    reverse ADD order like the reference's push-front list."""
+    lib = _port()
+    lib.oracle_com_force.restype = c_int
+    st = case["state"]
+    n = st["x"].shape[0]
+    S = {k: np.ascontiguousarray(st[k], dtype=np.float64) for k in ("x", "y", "z", "vx", "vy", "vz", "m", "r")}
+    acc = [np.zeros(n) if case.get("acc0") is None else np.array(a, dtype=np.float64) for a in (case.get("acc0") or (None,)*3)]
+    G = case["G"]
+    ub = lambda a: a.ctypes.data_as(POINTER(c_ubyte))
+    for f in case["forces"][::-1]:
+        name, fp = f["name"], f.get("params", {})
+        if name == "radiation_forces":
+            if "c" not in fp:
+                continue
+            beta, mask = _pp(case, "beta", n)
+            _, smask = _pp(case, "radiation_source", n, np.int32)
+            src = np.nonzero(smask)[0].astype(np.int64)
+            lib.oracle_radiation_forces(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]),
+                                        _d(S["m"]), _d(beta), ub(mask), c_double(G), c_double(fp["c"]),
+                                        src.ctypes.data_as(POINTER(c_int64)) if len(src) else None, c_int64(len(src)),
+                                        _d(acc[0]), _d(acc[1]), _d(acc[2]))
+        elif name == "gravitational_harmonics":
+            J2, hJ2 = _pp(case, "J2", n)
+            J4, hJ4 = _pp(case, "J4", n)
+            Rq, hRq = _pp(case, "R_eq", n)
+            om = case.get("particle_vec3", {}).get("Omega", ([], []))
+            omega = {int(i): v for i, v in zip(om[0], om[1])}
+            for i in range(n):
+                if not hJ2[i] or J2[i] == 0.0 or not hRq[i]:
+                    continue
+                Om = (c_double*3)(*[float(c) for c in omega.get(i, (0.0, 0.0, 1.0))])
+                lib.oracle_gravitational_harmonics(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["m"]), c_int64(i),
+                                                   c_double(J2[i]), c_double(J4[i] if hJ4[i] else 0.0), c_double(Rq[i]), Om,
+                                                   c_double(G), _d(acc[0]), _d(acc[1]), _d(acc[2]), None)
+        elif name == "gr_potential":
+            if "c" not in fp:
+                continue
+            lib.oracle_gr_potential(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["m"]), c_double(G), c_double(fp["c"]),
+                                    _d(acc[0]), _d(acc[1]), _d(acc[2]), None)
+        elif name == "yarkovsky_effect":
+            if "ye_lstar" not in fp or "ye_c" not in fp:
+                continue
+            pars, masks = zip(*[_pp(case, p, n) for p in YARK_PARAMS])
+            flag, fmask = _pp(case, "ye_flag", n, np.int32)
+            P = (POINTER(c_double)*9)(*[_d(a) for a in pars])
+            M = (POINTER(c_ubyte)*9)(*[ub(a) for a in masks])
+            sb = fp.get("ye_stef_boltz")
+            lib.oracle_yarkovsky_effect(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]),
+                                        _d(S["m"]), _d(S["r"]), P, M, flag.ctypes.data_as(POINTER(c_int)), ub(fmask),
+                                        c_double(G), c_double(fp["ye_lstar"]), c_double(fp["ye_c"]), c_double(sb or 0.0),
+                                        c_int(0 if sb is None else 1), _d(acc[0]), _d(acc[1]), _d(acc[2]))
+        elif name in KIND:
+            dp = _DampingParams()
+            keep = []
+            for p in ("tau_a", "tau_e", "tau_inc", "d_factor"):
+                vals, mask = _pp(case, p, n)
+                keep += [vals, mask]
+                setattr(dp, p, _d(vals))
+                setattr(dp, "has_" + p, ub(mask))
+            coords = fp.get("coordinates", 0)
+            _, pmask = _pp(case, "primary", n, np.int32)
+            prim = np.nonzero(pmask)[0]
+            primary = int(prim[0]) if len(prim) else -1
+            if name == "modify_orbits_forces":
+                dp.trap = int("ide_position" in fp and "ide_width" in fp)
+                dp.dedge, dp.hedge = fp.get("ide_position", 0.0), fp.get("ide_width", 0.0)
+            if name == "gas_damping_timescale" and ("cs_coeff" not in fp or "tau_coeff" not in fp):
+                continue
+            dp.cs_coeff, dp.tau_coeff = fp.get("cs_coeff", 0.0), fp.get("tau_coeff", 0.0)
+            dp.tIm_beta, dp.tIm_h0 = fp.get("tIm_flaring_index", 0.0), fp.get("tIm_scale_height_1", 0.01)
+            dp.tIm_sd0, dp.tIm_s = fp.get("tIm_surface_density_1", 0.0), fp.get("tIm_surface_density_exponent", 0.0)
+            dp.tIm_dedge, dp.tIm_hedge = fp.get("ide_position", 0.0), fp.get("ide_width", 0.0)
+            lib.oracle_com_force(c_int(KIND[name]), c_int(coords), c_int64(primary), ctypes.byref(dp), c_double(G),
+                                 c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]), _d(S["m"]),
+                                 _d(acc[0]), _d(acc[1]), _d(acc[2]), None)
+        else:
+            raise ValueError(name)
+    return acc

@@ -16,7 +16,7 @@ from ctypes import POINTER, Structure, c_double, c_int, c_int32, c_int64, c_void
 
 import numpy as np
 
-from . import _lib
+from . import _lib, sharding
 
 MAX_EFFECTS, BODY_DOUBLES, MAX_TABLES, MAX_SCALARS = 4, 24, 9, 8
 ABSENT_BITS = 0x7ff8b200dead0001
@@ -181,9 +181,7 @@ class Shard:
 
     def sync_bodies(self, group=None, src=0):
         """Active-body state broadcast (NCCL over NVLink when a process group is up)."""
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.broadcast(self.bodies, src=src, group=group)
+        sharding.broadcast_bodies(self.bodies, src=src, group=group)
 
     def launch(self, stream=None):
         """One force evaluation of the shard: a += sum of the stacked effects (asynchronous)."""
@@ -196,9 +194,7 @@ class Shard:
         return n.value
 
     def reduce_backreaction(self, group=None):
-        import torch.distributed as dist
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
-            dist.all_reduce(self.backreaction, group=group)
+        sharding.allreduce_backreaction(self.backreaction, group=group)
 
     def apply_backreaction(self, stream=None):
         s = self.torch.cuda.current_stream(self.device) if stream is None else stream

@@ -69,3 +69,42 @@ def build(w, forces, lib=None, coordinates="PARTICLE", integrator="ias15", acc=N
             done.add("J2")
         rebx.add_force(f)
     return sim, rebx, handles
+
+
+# ---- general cases (arbitrary presence patterns), used by the golden fixtures ----------------------
+def build_case(case, lib=None):
+    """case = {"G", "integrator"?, "state": {x..r}, "acc0": (ax, ay, az) | None,
+               "forces": [{"name", "params": {p: value}}, ...]   (ADD order),
+               "particle_params": {p: (index array, value array)},   double or int by registry
+               "particle_vec3": {p: (index array, [k,3] array)}}"""
+    st = case["state"]
+    sim = Simulation(G=case["G"], integrator=case.get("integrator", "ias15"))
+    sim.set_particles(st["x"], st["y"], st["z"], st["vx"], st["vy"], st["vz"], st["m"], st["r"])
+    if case.get("acc0") is not None:
+        sim.set_acc(*case["acc0"])
+    rebx = Extras(sim, lib=lib)
+    for p, (idx, val) in case.get("particle_params", {}).items():
+        if len(idx):
+            rebx.set_particle_params(p, val, idx)
+    for p, (idx, val) in case.get("particle_vec3", {}).items():
+        for i, v in zip(idx, val):
+            rebx.particle_params(int(i))[p] = tuple(float(c) for c in v)
+    handles = []
+    for f in case["forces"]:
+        h = rebx.load_force(f["name"])
+        for p, v in f.get("params", {}).items():
+            h.params[p] = v
+        rebx.add_force(h)
+        handles.append(h)
+    return sim, rebx, handles
+
+
+def run_case(case, lib=None):
+    """One dispatch; returns ((ax, ay, az), [(kind, message), ...])."""
+    sim, rebx, _ = build_case(case, lib)
+    sim.additional_forces()
+    msgs = sim.messages()
+    out = sim.acc()
+    rebx.detach()
+    sim.free()
+    return out, msgs

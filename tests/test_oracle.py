@@ -1,0 +1,111 @@
+"""Pins the oracle (CPU, no GPU needed).
+
+* the C restatement (oracle/oracle_forces.c, kind "port") against the committed golden vectors,
+  which were produced by the reference's own C sources (tests/golden/make_golden.py);
+* when oracle/_ref is present, the reference-compiled library against the same vectors and
+  against the restatement on larger seeded ensembles.
+The reference itself ships no acceleration-level known answers; the
+fixtures cover its two radiation examples (config 1) and the edge cases of its presence logic.
+"""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+import golden_io  # noqa: E402
+
+# effects whose arithmetic is + - * / sqrt only are bit-reproducible on any IEEE host
+EXACT = {"rad_debris_disk_example", "rad_circumplanetary_example", "rad_presence_and_two_sources",
+         "harmonics_presence_edges", "gr_potential_massive", "stacked_rad_gr_harmonics",
+         "modify_orbits_partial_params", "single_particle"}
+
+
+def test_fixture_inventory():
+    assert set(golden_io.names()) >= EXACT | {"yarkovsky_all_modes", "trio_particle", "trio_jacobi", "trio_barycentric"}
+
+
+@pytest.mark.parametrize("name", golden_io.names())
+def test_port_matches_golden(built, name):
+    from oracle import oracle
+    case, want, _ = golden_io.load(name)
+    got = np.array(oracle.port_case(case))
+    if name in EXACT:
+        assert np.array_equal(got, want)
+    else:       # libm transcendentals may differ between hosts by an ulp
+        scale = np.maximum(np.max(np.abs(want), axis=0), 1e-300)
+        assert np.max(np.abs(got - want)/scale) <= 1e-14
+
+
+@pytest.mark.parametrize("name", golden_io.names())
+def test_reference_build_matches_golden(built, name):
+    from oracle import oracle
+    from reboundx_b200 import scenarios
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built (no reference tree on this machine)")
+    case, want, msgs = golden_io.load(name)
+    got, got_msgs = scenarios.run_case(case, oracle.ref_lib())
+    got = np.array(got)
+    if name in EXACT:
+        assert np.array_equal(got, want)
+    else:
+        scale = np.maximum(np.max(np.abs(want), axis=0), 1e-300)
+        assert np.max(np.abs(got - want)/scale) <= 1e-14
+    assert sorted(set(got_msgs)) == sorted(msgs)
+
+
+@pytest.mark.parametrize("which", ["debris_disk", "ring", "ring_massive_tilted", "asteroids", "planetesimals"])
+def test_port_equals_reference_on_seeded_ensembles(built, which):
+    from oracle import oracle
+    from reboundx_b200 import workloads as W
+    if not oracle.have_ref():
+        pytest.skip("oracle/_ref not built")
+    w, add = {"debris_disk": (W.debris_disk(5000), ["radiation_forces"]),
+              "ring": (W.circumplanetary_ring(5000), ["gravitational_harmonics", "gr_potential"]),
+              "ring_massive_tilted": (W.circumplanetary_ring(5000, tilted=True, massive=True), ["gr_potential", "gravitational_harmonics"]),
+              "asteroids": (W.asteroid_ensemble(5000), ["yarkovsky_effect", "gr_potential"]),
+              "planetesimals": (W.planetesimal_disk(5000), ["modify_orbits_forces", "gas_damping_timescale", "type_I_migration"])}[which]
+    acc0 = W.gravity_like_acc(w, np.random.default_rng(0))
+    ref = oracle.ref_apply(w, add, acc0)
+    port, _ = oracle.port_apply(w, add[::-1], acc0)
+    for k in range(3):
+        assert np.array_equal(np.array(ref[k]), port[k])
+
+
+def test_planet_trap_branches(built):
+    """reference src/inner_disk_edge.c:61-77"""
+    import ctypes
+    from oracle import oracle
+    lib = ctypes.CDLL(oracle.PORT_PATH)
+    lib.oracle_planet_trap.restype = ctypes.c_double
+    f = lambda r: lib.oracle_planet_trap(ctypes.c_double(r), ctypes.c_double(0.3), ctypes.c_double(0.02))
+    assert f(0.5) == 1.0 and f(0.2) == -10.0
+    mid = f(0.303)
+    assert -4.5 < mid < 1.0
+    assert abs(mid - (5.5*np.cos(((0.3*1.02 - 0.303)*2*np.pi)/(4*0.02*0.3)) - 4.5)) < 1e-14
+
+
+def test_restated_orbit_elements_roundtrip(built):
+    """The REBOUND restatement (rebound_shim.c) inverts the element->Cartesian map of workloads.py
+    (independent implementation), pinning a, e, inc and P at the 1e-12 level."""
+    import ctypes
+    from reboundx_b200 import _lib, workloads as W
+    from reboundx_b200.host import RebParticle
+    shim = _lib.load_shim()
+
+    class Orbit(ctypes.Structure):
+        _fields_ = [(k, ctypes.c_double) for k in ("d", "v", "h", "P", "n", "a", "e", "inc", "Omega", "omega", "pomega", "f", "M", "l",
+                                                   "theta", "T", "rhill", "pal_h", "pal_k", "pal_ix", "pal_iy", "hx", "hy", "hz", "ex", "ey", "ez")]
+    shim.reb_orbit_from_particle.restype = Orbit
+    shim.reb_orbit_from_particle.argtypes = [ctypes.c_double, RebParticle, RebParticle]
+    rng = np.random.default_rng(5)
+    G, M = 4*np.pi**2, 1.0
+    for _ in range(50):
+        a, e, inc = rng.uniform(0.5, 5), rng.uniform(0, 0.6), rng.uniform(0.01, 1.5)
+        x, y, z, vx, vy, vz = W.kepler_to_cartesian(G*M, np.array([a]), np.array([e]), np.array([inc]),
+                                                    *(rng.uniform(0, 2*np.pi, (3, 1))))
+        p = RebParticle(x=x[0], y=y[0], z=z[0], vx=vx[0], vy=vy[0], vz=vz[0], m=0.0)
+        o = shim.reb_orbit_from_particle(G, p, RebParticle(m=M))
+        assert abs(o.a - a) < 1e-11*a and abs(o.e - e) < 1e-11 and abs(o.inc - inc) < 1e-11
+        assert abs(o.P - 2*np.pi*np.sqrt(a**3/(G*M))) < 1e-11*o.P
