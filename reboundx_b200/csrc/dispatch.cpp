@@ -95,15 +95,16 @@ struct Stats {
 struct DeviceContext {
     int device = 0;
     bool ready = false;
-    cudaStream_t stream[2] = {nullptr, nullptr};
+    static constexpr int kBuffers = 3;      // chunks in flight: H2D of c+1 and D2H of c-1 overlap the sweep of c
+    cudaStream_t stream[kBuffers] = {nullptr, nullptr, nullptr};
     cudaEvent_t bodies_ready = nullptr;
-    DevBuf aos[2], soa[2], work[2], bodies, br;
+    DevBuf aos[kBuffers], soa[kBuffers], work[kBuffers], bodies, br;
     PinnedBuf bodies_h, br_h;
     std::unordered_map<struct rebx_force*, std::unique_ptr<ForceTables>> tables;
     void* registered_ptr = nullptr;
     size_t registered_bytes = 0;
     Stats stats;
-    size_t chunk = size_t(1) << 20;
+    size_t chunk = size_t(1) << 19;         // 64 MB of AoS records per pipeline stage
     bool paranoid = false;
 
     void unregister_host() {
@@ -524,7 +525,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     REBXB_CUDA(ctx->bodies.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating body records");
     REBXB_CUDA(ctx->br_h.ensure(nchunks*ne*3*sizeof(double)), "allocating pinned back-reaction sums");
     REBXB_CUDA(ctx->br.ensure(nchunks*ne*3*sizeof(double)), "allocating back-reaction sums");
-    for (int b = 0; b < 2 && (size_t)b < nchunks; b++) {
+    for (int b = 0; b < DeviceContext::kBuffers && (size_t)b < nchunks; b++) {
         REBXB_CUDA(ctx->aos[b].ensure(chunk_cap*sizeof(struct reb_particle)), "allocating AoS staging");
         REBXB_CUDA(ctx->soa[b].ensure(11*soa_stride*sizeof(double)), "allocating SoA state");
         REBXB_CUDA(ctx->work[b].ensure(rebx_b200_workspace_bytes()), "allocating reduction scratch");
@@ -547,11 +548,11 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     REBXB_CUDA(cudaMemcpyAsync(ctx->bodies.p, bodies_h, ne*REBX_B200_BODY_DOUBLES*sizeof(double), cudaMemcpyHostToDevice, ctx->stream[0]), "copying body records");
     REBXB_CUDA(cudaMemsetAsync(ctx->br.p, 0, nchunks*ne*3*sizeof(double), ctx->stream[0]), "clearing back-reaction sums");
     REBXB_CUDA(cudaEventRecord(ctx->bodies_ready, ctx->stream[0]), "recording event");
-    REBXB_CUDA(cudaStreamWaitEvent(ctx->stream[1], ctx->bodies_ready, 0), "waiting on event");
+    for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamWaitEvent(ctx->stream[b], ctx->bodies_ready, 0), "waiting on event");
     ctx->stats.h2d_bytes += ne*REBX_B200_BODY_DOUBLES*sizeof(double);
 
     for (size_t c = 0; c < nchunks; c++) {
-        const int b = (int)(c & 1);
+        const int b = (int)(c % DeviceContext::kBuffers);
         cudaStream_t s = ctx->stream[b];
         const size_t c0 = c*CH, n = std::min(CH, N - c0);
         const size_t bytes = n*sizeof(struct reb_particle);
@@ -589,7 +590,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         REBXB_CUDA(cudaMemcpyAsync(particles + c0, ctx->aos[b].p, bytes, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
         ctx->stats.d2h_bytes += bytes;
     }
-    REBXB_CUDA(cudaStreamSynchronize(ctx->stream[1]), "waiting for the device");
+    for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamSynchronize(ctx->stream[b]), "waiting for the device");
     br_h = static_cast<double*>(ctx->br_h.p);
     REBXB_CUDA(cudaMemcpyAsync(br_h, ctx->br.p, nchunks*ne*3*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream[0]), "copying back-reaction sums");
     REBXB_CUDA(cudaStreamSynchronize(ctx->stream[0]), "waiting for the device");
@@ -613,7 +614,8 @@ failed:
         char buf[400];
         snprintf(buf, sizeof buf, "REBOUNDx-B200 Error: CUDA failure while %s: %s. Accelerations are NOT valid for this call.\n", fail, cudaGetErrorString(fail_code));
         reb_simulation_error(sim, buf);
-        cudaStreamSynchronize(ctx->stream[0]); cudaStreamSynchronize(ctx->stream[1]); cudaGetLastError();
+        for (auto& st : ctx->stream) cudaStreamSynchronize(st);
+        cudaGetLastError();
     }
 }
 

@@ -21,6 +21,7 @@
 #include <cuda_runtime.h>
 #include <cstdint>
 #include <cstdio>
+#include <cstdlib>
 #include "rebx_b200.h"
 #include "forces_math.cuh"
 
@@ -113,7 +114,7 @@ __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const double* 
     }
 }
 
-template <int K>
+template <int K, int NWARPS = kWarps>
 __device__ __forceinline__ void reduce_effect(Vec3 red, int e, double (*s_red)[3], double* __restrict__ partials) {
     if constexpr (Traits<K>::red) {
 #pragma unroll
@@ -129,14 +130,26 @@ __device__ __forceinline__ void reduce_effect(Vec3 red, int e, double (*s_red)[3
         if (threadIdx.x < 3) {
             double s = 0.0;
 #pragma unroll
-            for (int w = 0; w < kWarps; w++) s += s_red[w][threadIdx.x];
+            for (int w = 0; w < NWARPS; w++) s += s_red[w][threadIdx.x];
             partials[((size_t)blockIdx.x*REBX_B200_MAX_EFFECTS + e)*3 + threadIdx.x] = s;
         }
     }
 }
 
+// Resident CTAs per SM the register allocator is asked to make room for.  The light,
+// HBM-bound sweeps (radiation, gr_potential) are latency-bound at 2 CTAs (round-1 ncu: 102
+// registers, 16 warps/SM, 0.49 eligible warps/cycle, 80 % of HBM); capping them at 64
+// registers (4 CTAs, 32 warps/SM) costs a few spilled doubles but lifts the radiation sweep
+// to 93 % of the measured copy bandwidth.  The FP64-heavy sweeps keep their registers.
+template <int K0, int K1, int K2, int K3>
+constexpr int min_blocks() {
+    constexpr bool light = (K0 == REBX_B200_RADIATION || K0 == REBX_B200_GR_POTENTIAL) &&
+                           (K1 == 0 || K1 == REBX_B200_RADIATION || K1 == REBX_B200_GR_POTENTIAL) && K2 == 0 && K3 == 0;
+    return light ? 4 : 2;
+}
+
 template <int V, int K0, int K1, int K2, int K3>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, min_blocks<K0, K1, K2, K3>())
 pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ partials) {
     constexpr bool VEL  = Traits<K0>::vel  || Traits<K1>::vel  || Traits<K2>::vel  || Traits<K3>::vel;
     constexpr bool MASS = Traits<K0>::mass || Traits<K1>::mass || Traits<K2>::mass || Traits<K3>::mass;
@@ -195,6 +208,195 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
     reduce_effect<K1>(red1, 1, s_red, partials);
     reduce_effect<K2>(red2, 2, s_red, partials);
     reduce_effect<K3>(red3, 3, s_red, partials);
+}
+
+// ---------------------------------------------------------------------------------------------
+// pass_kernel_tma<K0..K3>: same sweep, but the particle state and parameter tables are moved
+// HBM -> shared memory by the TMA engine (cp.async.bulk, 1-D bulk copies completing on an
+// mbarrier) through a STAGES-deep ring per CTA.  One producer warp issues the copies; kTile
+// compute threads (one particle each per stage) pull their operands out of shared memory.
+// The copies need no registers and no resident warps while in flight, so memory-level
+// parallelism no longer depends on occupancy of the register-heavy FP64 division code
+// (round-1 ncu: 102 regs -> 16 warps/SM, issue-active 38 %, eligible warps 0.49/cycle).
+// Requires 16-byte aligned arrays; the ragged tail (n % kTile) is handled with plain loads.
+// ---------------------------------------------------------------------------------------------
+constexpr int kTile       = 256;
+constexpr int kTmaThreads = kTile + 32;
+constexpr int kTmaWarps   = kTmaThreads/32;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" :: "r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" :: "r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" :: "r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    asm volatile(
+        "{\n"
+        ".reg .pred P1;\n"
+        "LAB_WAIT:\n"
+        "mbarrier.try_wait.parity.shared::cta.b64 P1, [%0], %1;\n"
+        "@P1 bra DONE;\n"
+        "bra LAB_WAIT;\n"
+        "DONE:\n"
+        "}\n" :: "r"(smem_u32(bar)), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void bulk_g2s(void* dst, const void* src, uint32_t bytes, uint64_t* bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 :: "r"(smem_u32(dst)), "l"(src), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+template <int K0, int K1, int K2, int K3>
+struct TmaCfg {
+    static constexpr bool VEL  = Traits<K0>::vel  || Traits<K1>::vel  || Traits<K2>::vel  || Traits<K3>::vel;
+    static constexpr bool MASS = Traits<K0>::mass || Traits<K1>::mass || Traits<K2>::mass || Traits<K3>::mass;
+    static constexpr bool RAD  = Traits<K0>::rad  || Traits<K1>::rad  || Traits<K2>::rad  || Traits<K3>::rad;
+    static constexpr int oV = 3, oM = oV + (VEL ? 3 : 0), oR = oM + (MASS ? 1 : 0), oA = oR + (RAD ? 1 : 0);
+    static constexpr int oT0 = oA + 3, oT1 = oT0 + Traits<K0>::ntab, oT2 = oT1 + Traits<K1>::ntab, oT3 = oT2 + Traits<K2>::ntab;
+    static constexpr int ND = oT3 + Traits<K3>::ntab;                     // double arrays per stage
+    static constexpr int oI0 = 0, oI1 = oI0 + (Traits<K0>::itab ? 1 : 0), oI2 = oI1 + (Traits<K1>::itab ? 1 : 0),
+                         oI3 = oI2 + (Traits<K2>::itab ? 1 : 0);
+    static constexpr int NI = oI3 + (Traits<K3>::itab ? 1 : 0);           // int arrays per stage
+    static constexpr int stage_bytes = ND*kTile*8 + NI*kTile*4;
+    static constexpr int budget = 72*1024;                                // ~3 CTAs per SM
+    static constexpr int STAGES = (budget/stage_bytes) >= 4 ? 4 : ((budget/stage_bytes) >= 2 ? (budget/stage_bytes) : 2);
+    static constexpr int smem_bytes = STAGES*stage_bytes + 2*STAGES*8 + 16;
+};
+
+template <int K, int OT, int OI>
+__device__ __forceinline__ void smem_params(const unsigned char* stage, int nd, int tid, Params<K, 1>& q) {
+#pragma unroll
+    for (int j = 0; j < Traits<K>::ntab; j++) q.t[j][0] = reinterpret_cast<const double*>(stage)[(OT + j)*kTile + tid];
+    if constexpr (Traits<K>::itab) q.it[0] = reinterpret_cast<const int32_t*>(stage + (size_t)nd*kTile*8)[OI*kTile + tid];
+}
+
+template <int K0, int K1, int K2, int K3>
+__global__ void __launch_bounds__(kTmaThreads)
+pass_kernel_tma(const __grid_constant__ rebx_b200_pass P, double* __restrict__ partials) {
+    using C = TmaCfg<K0, K1, K2, K3>;
+    constexpr int STAGES = C::STAGES;
+    extern __shared__ __align__(128) unsigned char smem[];
+    __shared__ double s_body[REBX_B200_MAX_EFFECTS][REBX_B200_BODY_DOUBLES];
+    __shared__ double s_red[kTmaWarps][3];
+    uint64_t* full_bar  = reinterpret_cast<uint64_t*>(smem + (size_t)STAGES*C::stage_bytes);
+    uint64_t* empty_bar = full_bar + STAGES;
+
+    const int tid = threadIdx.x;
+    for (int idx = tid; idx < P.n_effects*REBX_B200_BODY_DOUBLES; idx += kTmaThreads) {
+        const int e = idx/REBX_B200_BODY_DOUBLES, j = idx - e*REBX_B200_BODY_DOUBLES;
+        s_body[e][j] = P.fx[e].body[j];
+    }
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], kTile/32); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads();
+
+    const int64_t n = P.st.n;
+    const int64_t nfull = n/kTile;                      // full tiles go through the TMA ring
+    Vec3 red0 = {0., 0., 0.}, red1 = {0., 0., 0.}, red2 = {0., 0., 0.}, red3 = {0., 0., 0.};
+
+    if (tid >= kTile) {
+        // ---------------- producer warp: one elected lane feeds the ring --------------------
+        if (tid == kTile) {
+            const void* dsrc[C::ND];
+            dsrc[0] = P.st.x; dsrc[1] = P.st.y; dsrc[2] = P.st.z;
+            if constexpr (C::VEL)  { dsrc[C::oV] = P.st.vx; dsrc[C::oV + 1] = P.st.vy; dsrc[C::oV + 2] = P.st.vz; }
+            if constexpr (C::MASS) { dsrc[C::oM] = P.st.m; }
+            if constexpr (C::RAD)  { dsrc[C::oR] = P.st.r; }
+            dsrc[C::oA] = P.st.ax; dsrc[C::oA + 1] = P.st.ay; dsrc[C::oA + 2] = P.st.az;
+#pragma unroll
+            for (int j = 0; j < Traits<K0>::ntab; j++) dsrc[C::oT0 + j] = P.fx[0].tab[j];
+#pragma unroll
+            for (int j = 0; j < Traits<K1>::ntab; j++) dsrc[C::oT1 + j] = P.fx[1].tab[j];
+#pragma unroll
+            for (int j = 0; j < Traits<K2>::ntab; j++) dsrc[C::oT2 + j] = P.fx[2].tab[j];
+#pragma unroll
+            for (int j = 0; j < Traits<K3>::ntab; j++) dsrc[C::oT3 + j] = P.fx[3].tab[j];
+            const void* isrc[C::NI > 0 ? C::NI : 1];
+            if constexpr (Traits<K0>::itab) isrc[C::oI0] = P.fx[0].itab;
+            if constexpr (Traits<K1>::itab) isrc[C::oI1] = P.fx[1].itab;
+            if constexpr (Traits<K2>::itab) isrc[C::oI2] = P.fx[2].itab;
+            if constexpr (Traits<K3>::itab) isrc[C::oI3] = P.fx[3].itab;
+            int it = 0;
+            for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x, it++) {
+                const int s = it % STAGES;
+                if (it >= STAGES) mbar_wait(&empty_bar[s], ((it/STAGES) - 1) & 1);
+                unsigned char* stage = smem + (size_t)s*C::stage_bytes;
+                mbar_expect_tx(&full_bar[s], C::stage_bytes);
+                const int64_t k0 = tile*kTile;
+#pragma unroll
+                for (int j = 0; j < C::ND; j++)
+                    bulk_g2s(stage + (size_t)j*kTile*8, static_cast<const double*>(dsrc[j]) + k0, kTile*8, &full_bar[s]);
+#pragma unroll
+                for (int j = 0; j < C::NI; j++)
+                    bulk_g2s(stage + (size_t)C::ND*kTile*8 + (size_t)j*kTile*4, static_cast<const int32_t*>(isrc[j]) + k0, kTile*4, &full_bar[s]);
+            }
+        }
+    } else {
+        // ---------------- compute threads: one particle per thread per stage -------------------
+        const long long b0 = (long long)s_body[0][0];
+        const long long b1 = (K1 != 0) ? (long long)s_body[1][0] : -1;
+        const long long b2 = (K2 != 0) ? (long long)s_body[2][0] : -1;
+        const long long b3 = (K3 != 0) ? (long long)s_body[3][0] : -1;
+        auto one = [&](const Particle& p, Vec3& a, long long gi, const Params<K0, 1>& q0, const Params<K1, 1>& q1,
+                       const Params<K2, 1>& q2, const Params<K3, 1>& q3) {
+            if (gi != b0) apply<K0, 1>(P.fx[0], s_body[0], p, q0, 0, a, red0);
+            if constexpr (K1 != 0) { if (gi != b1) apply<K1, 1>(P.fx[1], s_body[1], p, q1, 0, a, red1); }
+            if constexpr (K2 != 0) { if (gi != b2) apply<K2, 1>(P.fx[2], s_body[2], p, q2, 0, a, red2); }
+            if constexpr (K3 != 0) { if (gi != b3) apply<K3, 1>(P.fx[3], s_body[3], p, q3, 0, a, red3); }
+        };
+        int it = 0;
+        for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x, it++) {
+            const int s = it % STAGES;
+            mbar_wait(&full_bar[s], (it/STAGES) & 1);
+            const unsigned char* stage = smem + (size_t)s*C::stage_bytes;
+            const double* sd = reinterpret_cast<const double*>(stage);
+            Particle p;
+            p.x = sd[0*kTile + tid]; p.y = sd[1*kTile + tid]; p.z = sd[2*kTile + tid];
+            if constexpr (C::VEL)  { p.vx = sd[(C::oV + 0)*kTile + tid]; p.vy = sd[(C::oV + 1)*kTile + tid]; p.vz = sd[(C::oV + 2)*kTile + tid]; }
+            else { p.vx = p.vy = p.vz = 0.0; }
+            if constexpr (C::MASS) { p.m = sd[C::oM*kTile + tid]; } else { p.m = 0.0; }
+            if constexpr (C::RAD)  { p.r = sd[C::oR*kTile + tid]; } else { p.r = 0.0; }
+            Vec3 a = {sd[(C::oA + 0)*kTile + tid], sd[(C::oA + 1)*kTile + tid], sd[(C::oA + 2)*kTile + tid]};
+            Params<K0, 1> q0; Params<K1, 1> q1; Params<K2, 1> q2; Params<K3, 1> q3;
+            smem_params<K0, C::oT0, C::oI0>(stage, C::ND, tid, q0);
+            if constexpr (K1 != 0) smem_params<K1, C::oT1, C::oI1>(stage, C::ND, tid, q1);
+            if constexpr (K2 != 0) smem_params<K2, C::oT2, C::oI2>(stage, C::ND, tid, q2);
+            if constexpr (K3 != 0) smem_params<K3, C::oT3, C::oI3>(stage, C::ND, tid, q3);
+            __syncwarp();
+            if ((tid & 31) == 0) mbar_arrive(&empty_bar[s]);       // operands are in registers: release the stage
+            const int64_t k = tile*kTile + tid;
+            one(p, a, P.st.index_base + k, q0, q1, q2, q3);
+            __stcs(P.st.ax + k, a.x); __stcs(P.st.ay + k, a.y); __stcs(P.st.az + k, a.z);
+        }
+        // ragged tail: plain loads, spread over the CTAs
+        const int64_t rem0 = nfull*kTile;
+        for (int64_t k = rem0 + (int64_t)blockIdx.x*kTile + tid; k < n; k += (int64_t)gridDim.x*kTile) {
+            Particle p;
+            p.x = __ldcs(P.st.x + k); p.y = __ldcs(P.st.y + k); p.z = __ldcs(P.st.z + k);
+            if constexpr (C::VEL)  { p.vx = __ldcs(P.st.vx + k); p.vy = __ldcs(P.st.vy + k); p.vz = __ldcs(P.st.vz + k); }
+            else { p.vx = p.vy = p.vz = 0.0; }
+            if constexpr (C::MASS) { p.m = __ldcs(P.st.m + k); } else { p.m = 0.0; }
+            if constexpr (C::RAD)  { p.r = __ldcs(P.st.r + k); } else { p.r = 0.0; }
+            Vec3 a = {__ldcs(P.st.ax + k), __ldcs(P.st.ay + k), __ldcs(P.st.az + k)};
+            Params<K0, 1> q0; Params<K1, 1> q1; Params<K2, 1> q2; Params<K3, 1> q3;
+            load_params<K0, 1>(P.fx[0], k, true, q0);
+            if constexpr (K1 != 0) load_params<K1, 1>(P.fx[1], k, true, q1);
+            if constexpr (K2 != 0) load_params<K2, 1>(P.fx[2], k, true, q2);
+            if constexpr (K3 != 0) load_params<K3, 1>(P.fx[3], k, true, q3);
+            one(p, a, P.st.index_base + k, q0, q1, q2, q3);
+            __stcs(P.st.ax + k, a.x); __stcs(P.st.ay + k, a.y); __stcs(P.st.az + k, a.z);
+        }
+    }
+    reduce_effect<K0, kTmaWarps>(red0, 0, s_red, partials);
+    reduce_effect<K1, kTmaWarps>(red1, 1, s_red, partials);
+    reduce_effect<K2, kTmaWarps>(red2, 2, s_red, partials);
+    reduce_effect<K3, kTmaWarps>(red3, 3, s_red, partials);
 }
 
 // Sums the per-CTA partials in a fixed order and writes fx.backreaction (3 doubles each).
@@ -275,11 +477,12 @@ pack_acc_aos_kernel(unsigned char* __restrict__ aos, rebx_b200_aos_layout L,
 
 // ---- launch plumbing ----------------------------------------------------------------------
 typedef void (*pass_fn)(const rebx_b200_pass, double*);
-struct Combo { int k[4]; pass_fn fn[2]; bool red[4]; };   // fn[0]: V=1, fn[1]: V=2
+struct Combo { int k[4]; pass_fn fn[2]; bool red[4]; pass_fn tma; int tma_smem; };   // fn[0]: V=1, fn[1]: V=2
 
 #define REBXB_COMBO(a, b, c, d) { {a, b, c, d}, { pass_kernel<1, a, b, c, d>, pass_kernel<2, a, b, c, d> }, \
-                                  { Traits<a>::red, Traits<b>::red, Traits<c>::red, Traits<d>::red } },
-static const Combo kCombos[] = {
+                                  { Traits<a>::red, Traits<b>::red, Traits<c>::red, Traits<d>::red }, \
+                                  pass_kernel_tma<a, b, c, d>, TmaCfg<a, b, c, d>::smem_bytes },
+static Combo kCombos[] = {
     // singles
     REBXB_COMBO(1,0,0,0) REBXB_COMBO(2,0,0,0) REBXB_COMBO(3,0,0,0) REBXB_COMBO(4,0,0,0)
     REBXB_COMBO(5,0,0,0) REBXB_COMBO(6,0,0,0) REBXB_COMBO(7,0,0,0)
@@ -324,16 +527,23 @@ static DevInfo device_info() {
     return info;
 }
 
-static int grid_for(const void* fn, int64_t work_items) {
+static int grid_for(const void* fn, int64_t work_items, int threads = kThreads, int smem = 0, int items_per_block = kThreads) {
     const DevInfo di = device_info();
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, kThreads, 0) != cudaSuccess || per_sm < 1) per_sm = 1;
-    int64_t blocks = (work_items + kThreads - 1)/kThreads;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    int64_t blocks = (work_items + items_per_block - 1)/items_per_block;
     int64_t cap = (int64_t)(di.ok ? di.sms : 148)*per_sm;
     if (cap > kMaxBlocks) cap = kMaxBlocks - (kMaxBlocks % (di.ok ? di.sms : 148));
     if (blocks > cap) blocks = cap;
     if (blocks < 1) blocks = 1;
     return (int)blocks;
+}
+
+static bool use_tma() {
+    // opt-in (REBX_B200_KERNEL=tma): measured slower than the occupancy-tuned plain sweep on B200
+    // (radiation 10^7: 0.179 ms vs 0.171 ms; FP64-heavy sweeps 5-30 % slower), see DESIGN.md
+    static const int mode = [] { const char* e = getenv("REBX_B200_KERNEL"); return (e && e[0] == 't') ? 1 : 0; }();
+    return mode != 0;
 }
 
 static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
@@ -429,12 +639,23 @@ int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* str
             if (j < take) sub.fx[j] = pass->fx[done + j];
             else { sub.fx[j] = rebx_b200_effect(); sub.fx[j].kind = 0; }
         }
-        const int V = vsel ? 2 : 1;
-        pass_fn fn = combo->fn[vsel];
-        const int64_t tiles = (sub.st.n + V - 1)/V;
-        const int grid = grid_for(reinterpret_cast<const void*>(fn), tiles);
-        fn<<<grid, kThreads, 0, s>>>(sub, static_cast<double*>(workspace));
-        cudaError_t err = cudaGetLastError();
+        int grid;
+        cudaError_t err;
+        if (vsel && use_tma() && sub.st.n >= 4*kTile) {
+            // TMA-fed ring (needs 16-byte aligned arrays, which `vsel` established)
+            pass_fn fn = combo->tma;
+            err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, combo->tma_smem);
+            if (err != cudaSuccess) return err;
+            grid = grid_for(reinterpret_cast<const void*>(fn), sub.st.n, kTmaThreads, combo->tma_smem, kTile);
+            fn<<<grid, kTmaThreads, combo->tma_smem, s>>>(sub, static_cast<double*>(workspace));
+        } else {
+            const int V = vsel ? 2 : 1;
+            pass_fn fn = combo->fn[vsel];
+            const int64_t tiles = (sub.st.n + V - 1)/V;
+            grid = grid_for(reinterpret_cast<const void*>(fn), tiles);
+            fn<<<grid, kThreads, 0, s>>>(sub, static_cast<double*>(workspace));
+        }
+        err = cudaGetLastError();
         if (err != cudaSuccess) return err;
         if (launches) (*launches)++;
         unsigned red_mask = 0;
