@@ -124,6 +124,19 @@ int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* str
 /* a[index - index_base] += backreaction for each effect whose body lies inside the shard. */
 int rebx_b200_apply_backreaction(const rebx_b200_pass* pass, void* stream, int* launches);
 
+/* ---- centre-of-mass reference frames of rebx_com_force (reference src/rebxtools.c:66-147) ------
+ * scratch: device memory of rebx_b200_scan_scratch_bytes(n), reusable between calls. */
+size_t rebx_b200_scan_scratch_bytes(int64_t n);
+/* totals7 (device) = { sum m, sum m x, sum m y, sum m z, sum m vx, sum m vy, sum m vz } of the shard.
+ * A sharded caller all-reduces totals7 before the next call. */
+int rebx_b200_mass_moments(const rebx_b200_state* st, double* totals7, void* scratch, void* stream, int* launches);
+/* Writes `nbodies` consecutive body records (device) describing the barycentre (index -1). */
+int rebx_b200_com_bodies(const double* totals7, double* bodies, int nbodies, void* stream, int* launches);
+/* REBX_COORDINATES_JACOBI for 1..3 stacked damping effects (kinds 5,6,7) over the WHOLE ensemble
+ * (index_base must be 0): prefix scan of the mass moments, sweep, suffix scan of the
+ * back-reaction, all on the device in O(n).  fx[].body and fx[].backreaction are ignored. */
+int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* stream, int* launches);
+
 /* Barycentric second sweep: a[k] += delta[0..2] for every particle in the shard. */
 int rebx_b200_add_uniform(const rebx_b200_state* st, const double* delta, void* stream, int* launches);
 

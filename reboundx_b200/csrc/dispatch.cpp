@@ -98,7 +98,7 @@ struct DeviceContext {
     static constexpr int kBuffers = 3;      // chunks in flight: H2D of c+1 and D2H of c-1 overlap the sweep of c
     cudaStream_t stream[kBuffers] = {nullptr, nullptr, nullptr};
     cudaEvent_t bodies_ready = nullptr;
-    DevBuf aos[kBuffers], soa[kBuffers], work[kBuffers], bodies, br;
+    DevBuf aos[kBuffers], soa[kBuffers], work[kBuffers], bodies, br, scan, totals;
     PinnedBuf bodies_h, br_h;
     std::unordered_map<struct rebx_force*, std::unique_ptr<ForceTables>> tables;
     void* registered_ptr = nullptr;
@@ -363,6 +363,7 @@ struct Entry {
     ForceTables* T = nullptr;
     const Oblate* ob = nullptr;
     bool reduces = false;
+    int frame = 0;          // 0: body is a particle; 1: barycentre (second uniform sweep); 2: Jacobi (scan path)
 };
 
 static const double* get_d(struct rebx_force* f, const char* name) { return static_cast<const double*>(find_value(f->ap, name)); }
@@ -426,8 +427,13 @@ static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceCont
                 return false;   // the reference goes on to index particles[-1] here (rebxtools.c:139); we stop
             }
             e.body_index = T.bodies.front();
+        } else if (coordinates == REBX_COORDINATES_BARYCENTRIC) {
+            e.frame = 1; e.flags |= REBX_B200_FLAG_BARYCENTRIC; e.body_index = -1;
+        } else if (coordinates == REBX_COORDINATES_JACOBI) {
+            e.frame = 2; e.body_index = 0;           // particle 0 has no Jacobi coordinate (rebxtools.c:71-73)
+            if (N < 2) return false;
         } else {
-            reb_simulation_error(sim, "REBOUNDx-B200 Error: Jacobi and barycentric coordinates are not available on the device path in this build; set the force's 'coordinates' parameter to REBX_COORDINATES_PARTICLE.\n");
+            reb_simulation_error(sim, "Coordinates not supported in REBOUNDx.\n");
             return false;
         }
         if (kind == REBX_B200_MODIFY_ORBITS) {
@@ -439,7 +445,7 @@ static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceCont
             const double* tc = get_d(force, "tau_coeff");
             int64_t missing = T.n_incomplete;
             // the reference body is never evaluated, so its own missing d_factor is no error
-            if (is_absent(T.h[0][(size_t)e.body_index])) missing--;
+            if (e.body_index >= 0 && is_absent(T.h[0][(size_t)e.body_index])) missing--;
             if (!cs || !tc || missing > 0)
                 rebx_error(static_cast<struct rebx_extras*>(sim->extras), "Need to set d_factor, cs_coeff, tau_coeff parameters.  See examples in documentation.\n");
             if (!cs || !tc) return false;                                      // every particle returns a zero force
@@ -464,6 +470,8 @@ static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceCont
 
 static void fill_body(double* rec, const Entry& e, const struct reb_particle* particles) {
     for (int j = 0; j < REBX_B200_BODY_DOUBLES; j++) rec[j] = 0.0;
+    rec[REBX_B200_BODY_INDEX] = -1.0;
+    if (e.body_index < 0) return;                   // barycentre: the record is computed on the device
     const struct reb_particle& b = particles[e.body_index];
     rec[REBX_B200_BODY_INDEX] = (double)e.body_index;
     rec[REBX_B200_BODY_X+0] = b.x;  rec[REBX_B200_BODY_X+1] = b.y;  rec[REBX_B200_BODY_X+2] = b.z;
@@ -498,7 +506,11 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     const char* fail = nullptr;
     cudaError_t fail_code = cudaSuccess;
     const size_t ne = entries.size();
-    const size_t CH = ctx->chunk;
+    // Centre-of-mass frames need the whole ensemble on the device (a reduction or a scan over
+    // all particles precedes the sweep), so such a segment runs as one resident chunk.
+    bool whole = false;
+    for (const Entry& e : entries) if (e.frame != 0) whole = true;
+    const size_t CH = whole ? ((N + 1) & ~size_t(1)) : ctx->chunk;
     const size_t nchunks = (N + CH - 1)/CH;
     const size_t chunk_cap = std::min(N, CH);
     bool need_vel = false, need_m = false, need_r = false;
@@ -529,6 +541,10 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         REBXB_CUDA(ctx->aos[b].ensure(chunk_cap*sizeof(struct reb_particle)), "allocating AoS staging");
         REBXB_CUDA(ctx->soa[b].ensure(11*soa_stride*sizeof(double)), "allocating SoA state");
         REBXB_CUDA(ctx->work[b].ensure(rebx_b200_workspace_bytes()), "allocating reduction scratch");
+    }
+    if (whole) {
+        REBXB_CUDA(ctx->scan.ensure(rebx_b200_scan_scratch_bytes((int64_t)N)), "allocating scan scratch");
+        REBXB_CUDA(ctx->totals.ensure(16*sizeof(double)), "allocating mass moments");
     }
     // Pin the caller's particle array once so the DMA engines can stream it (only worth it for
     // the simulation's own long-lived array, not for an integrator's scratch copy).
@@ -567,11 +583,16 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         st.r = need_r ? base + 7*soa_stride : nullptr;
         st.ax = base + 8*soa_stride; st.ay = base + 9*soa_stride; st.az = base + 10*soa_stride;
         REBXB_CUDA((cudaError_t)rebx_b200_unpack_aos(ctx->aos[b].p, &L, &st, s, &launches), "unpacking particles");
-        for (size_t e0 = 0; e0 < ne; e0 += REBX_B200_MAX_EFFECTS) {
+        for (size_t e0 = 0; e0 < ne;) {
+            // consecutive entries sharing a reference-frame class form one launch group
+            const int frame = entries[e0].frame;
+            const size_t cap = frame == 2 ? 3 : REBX_B200_MAX_EFFECTS;
+            size_t e1 = e0;
+            while (e1 < ne && e1 - e0 < cap && entries[e1].frame == frame) e1++;
             rebx_b200_pass P;
             std::memset(&P, 0, sizeof P);
             P.st = st;
-            P.n_effects = (int32_t)std::min<size_t>(REBX_B200_MAX_EFFECTS, ne - e0);
+            P.n_effects = (int32_t)(e1 - e0);
             for (int j = 0; j < P.n_effects; j++) {
                 const Entry& en = entries[e0 + j];
                 rebx_b200_effect& fx = P.fx[j];
@@ -584,7 +605,20 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 }
                 fx.backreaction = en.reduces ? static_cast<double*>(ctx->br.p) + (c*ne + e0 + j)*3 : nullptr;
             }
-            REBXB_CUDA((cudaError_t)rebx_b200_launch_pass(&P, ctx->work[b].p, s, &launches), "launching the force sweep");
+            if (frame == 2) {
+                REBXB_CUDA((cudaError_t)rebx_b200_launch_jacobi(&P, ctx->scan.p, s, &launches), "launching the Jacobi-frame sweep");
+            } else {
+                if (frame == 1) {   // barycentre record computed on the device from the resident state
+                    REBXB_CUDA((cudaError_t)rebx_b200_mass_moments(&st, static_cast<double*>(ctx->totals.p), ctx->scan.p, s, &launches), "reducing mass moments");
+                    REBXB_CUDA((cudaError_t)rebx_b200_com_bodies(static_cast<const double*>(ctx->totals.p),
+                                                                 static_cast<double*>(ctx->bodies.p) + e0*REBX_B200_BODY_DOUBLES, P.n_effects, s, &launches), "building the barycentre record");
+                }
+                REBXB_CUDA((cudaError_t)rebx_b200_launch_pass(&P, ctx->work[b].p, s, &launches), "launching the force sweep");
+                if (frame == 1)     // every particle loses sum_i (m_i/M) f_i  (rebxtools.c:108-115)
+                    for (int j = 0; j < P.n_effects; j++)
+                        REBXB_CUDA((cudaError_t)rebx_b200_add_uniform(&st, P.fx[j].backreaction, s, &launches), "applying the barycentric back-reaction");
+            }
+            e0 = e1;
         }
         REBXB_CUDA((cudaError_t)rebx_b200_pack_acc_aos(ctx->aos[b].p, &L, &st, s, &launches), "packing accelerations");
         REBXB_CUDA(cudaMemcpyAsync(particles + c0, ctx->aos[b].p, bytes, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
@@ -600,7 +634,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     // Back-reaction onto the source / primary / oblate bodies (gr_potential.c:74-76,
     // gravitational_harmonics.c:221-223, rebxtools.c:139-141): chunk sums added in chunk order.
     for (size_t e = 0; e < ne; e++) {
-        if (!entries[e].reduces) continue;
+        if (!entries[e].reduces || entries[e].frame != 0) continue;    // COM frames were applied on the device
         double sx = 0.0, sy = 0.0, sz = 0.0;
         for (size_t c = 0; c < nchunks; c++) { sx += br_h[(c*ne + e)*3 + 0]; sy += br_h[(c*ne + e)*3 + 1]; sz += br_h[(c*ne + e)*3 + 2]; }
         struct reb_particle& b = particles[entries[e].body_index];

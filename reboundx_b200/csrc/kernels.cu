@@ -475,6 +475,10 @@ pack_acc_aos_kernel(unsigned char* __restrict__ aos, rebx_b200_aos_layout L,
     }
 }
 
+}  // namespace rebxb
+#include "kernels_jacobi.cuh"
+namespace rebxb {
+
 // ---- launch plumbing ----------------------------------------------------------------------
 typedef void (*pass_fn)(const rebx_b200_pass, double*);
 struct Combo { int k[4]; pass_fn fn[2]; bool red[4]; pass_fn tma; int tma_smem; };   // fn[0]: V=1, fn[1]: V=2
@@ -680,6 +684,61 @@ int rebx_b200_apply_backreaction(const rebx_b200_pass* pass, void* stream, int* 
     apply_backreaction_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(*pass);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+size_t rebx_b200_scan_scratch_bytes(int64_t n) {
+    const int64_t ntiles = (n + kScanThreads - 1)/kScanThreads + 1;
+    return (size_t)(ntiles*10 + 16 + 3*(n + 2))*sizeof(double);
+}
+
+int rebx_b200_mass_moments(const rebx_b200_state* st, double* totals7, void* scratch, void* stream, int* launches) {
+    if (!st || !totals7 || !scratch || !st->m || !st->vx) return cudaErrorInvalidValue;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (st->n == 0) return cudaMemsetAsync(totals7, 0, 7*sizeof(double), s);
+    const int64_t ntiles = (st->n + kScanThreads - 1)/kScanThreads;
+    double* rows = static_cast<double*>(scratch);
+    moments_tile_kernel<<<(unsigned)ntiles, kScanThreads, 0, s>>>(*st, rows);
+    scan_tiles_kernel<7, false><<<1, 512, 0, s>>>(rows, ntiles, totals7);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) *launches += 2;
+    return err;
+}
+
+int rebx_b200_com_bodies(const double* totals7, double* bodies, int nbodies, void* stream, int* launches) {
+    if (!totals7 || !bodies || nbodies < 1) return cudaErrorInvalidValue;
+    com_body_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(totals7, bodies, nbodies);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* stream, int* launches) {
+    if (!pass || !scratch) return cudaErrorInvalidValue;
+    const rebx_b200_pass& P = *pass;
+    if (P.n_effects < 1 || P.n_effects > 3 || P.st.index_base != 0) return cudaErrorInvalidValue;
+    if (!P.st.x || !P.st.vx || !P.st.m || !P.st.ax) return cudaErrorInvalidValue;
+    if (P.st.n == 0) return 0;
+    const JacobiCombo* combo = nullptr;
+    for (const JacobiCombo& c : kJacobiCombos) {
+        bool ok = true;
+        for (int j = 0; j < 3; j++) if (c.k[j] != (j < P.n_effects ? P.fx[j].kind : 0)) ok = false;
+        if (ok) { combo = &c; break; }
+    }
+    if (!combo) return cudaErrorInvalidValue;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    const int64_t n = P.st.n, ntiles = (n + kScanThreads - 1)/kScanThreads;
+    double* rows7 = static_cast<double*>(scratch);
+    double* rows3 = rows7 + (size_t)(ntiles + 1)*7;
+    double* totals = rows3 + (size_t)(ntiles + 1)*3;
+    double* tvec = totals + 16;
+    moments_tile_kernel<<<(unsigned)ntiles, kScanThreads, 0, s>>>(P.st, rows7);
+    scan_tiles_kernel<7, false><<<1, 512, 0, s>>>(rows7, ntiles, totals);
+    combo->fn<<<(unsigned)ntiles, kScanThreads, 0, s>>>(P, rows7, tvec, rows3);
+    scan_tiles_kernel<3, true><<<1, 512, 0, s>>>(rows3, ntiles, totals + 8);
+    jacobi_apply_kernel<<<(unsigned)ntiles, kScanThreads, 0, s>>>(P.st, tvec, rows3);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) *launches += 5;
     return err;
 }
 

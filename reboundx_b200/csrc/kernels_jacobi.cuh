@@ -1,0 +1,224 @@
+// kernels_jacobi.cuh -- centre-of-mass reference frames of rebx_com_force on the device
+// (reference src/rebxtools.c:66-147), included by kernels.cu.
+//
+// BARYCENTRIC: every particle is evaluated against the total centre of mass; the reference
+// then subtracts (m_i/M) f_i from EVERY particle, one i at a time -- O(N^2).  Here: one
+// reduction for the mass moments, the ordinary sweep (FLAG_BARYCENTRIC) that also reduces
+// sum_i (m_i/M) f_i, and one uniform add.  O(N).
+//
+// JACOBI: particle i is evaluated against the centre of mass of particles 0..i-1, which the
+// reference obtains by peeling particles off the total COM backwards (rebxtools.c:6-30,97-99),
+// and (m_i/(M_i+m_i)) f_i is subtracted from every j <= i -- O(N^2) again.  Here the recurrence
+// is two scans:  exclusive PREFIX sums of (m, m r, m v) give COM_i, and an inclusive SUFFIX
+// sum of t_i = (m_i/(M_i+m_i)) sum_e f_i^e gives what particle j must lose.  O(N), five
+// kernels: tile sums -> scan of tile sums -> sweep (in-tile scan + forces) -> reverse scan of
+// tile sums -> apply (in-tile reverse scan).
+#pragma once
+
+namespace rebxb {
+
+constexpr int kScanThreads = 256;
+
+// Exclusive scan of NC doubles per thread across a CTA of kScanThreads; returns the CTA total
+// in `total` (valid in every thread).  Fixed evaluation order => deterministic.
+template <int NC>
+__device__ __forceinline__ void block_exclusive_scan(double (&v)[NC], double (&total)[NC], double (*s_warp)[NC]) {
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+    double incl[NC], excl[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        double x = v[c];
+#pragma unroll
+        for (int off = 1; off < 32; off <<= 1) {
+            const double y = __shfl_up_sync(0xffffffffu, x, off);
+            if (lane >= off) x += y;
+        }
+        incl[c] = x;
+        const double up = __shfl_up_sync(0xffffffffu, x, 1);
+        excl[c] = lane ? up : 0.0;
+    }
+    __syncthreads();
+    if (lane == 31) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) s_warp[warp][c] = incl[c];
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NC; c++) {
+        double before = 0.0, all = 0.0;
+#pragma unroll
+        for (int w = 0; w < kScanThreads/32; w++) {
+            const double s = s_warp[w][c];
+            if (w < warp) before += s;
+            all += s;
+        }
+        total[c] = all;
+        v[c] = before + excl[c];
+    }
+}
+
+// ---- mass moments: sum m, sum m r, sum m v ------------------------------------------------------
+// tile_sums[tile][7]; one tile = kScanThreads consecutive particles.
+__global__ void __launch_bounds__(kScanThreads)
+moments_tile_kernel(rebx_b200_state st, double* __restrict__ tile_sums) {
+    __shared__ double s_warp[kScanThreads/32][7];
+    const int64_t k = (int64_t)blockIdx.x*kScanThreads + threadIdx.x;
+    double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    if (k < st.n) {
+        const double m = st.m[k];
+        v[0] = m; v[1] = st.x[k]*m; v[2] = st.y[k]*m; v[3] = st.z[k]*m;
+        v[4] = st.vx[k]*m; v[5] = st.vy[k]*m; v[6] = st.vz[k]*m;
+    }
+    double total[7];
+    block_exclusive_scan<7>(v, total, s_warp);
+    if (threadIdx.x < 7) tile_sums[(size_t)blockIdx.x*7 + threadIdx.x] = total[threadIdx.x];
+}
+
+// In-place exclusive scan over `ntiles` rows of NC doubles (forward, or backward when REV),
+// single CTA of 512 threads each owning a contiguous span.  totals[NC] gets the grand total.
+template <int NC, bool REV>
+__global__ void __launch_bounds__(512)
+scan_tiles_kernel(double* __restrict__ rows, int64_t ntiles, double* __restrict__ totals) {
+    __shared__ double s_part[512][NC];
+    const int t = threadIdx.x;
+    const int64_t span = (ntiles + 511)/512;
+    const int64_t lo = (int64_t)t*span, hi = (lo + span < ntiles) ? lo + span : ntiles;
+    auto row = [&](int64_t i) { return REV ? (ntiles - 1 - i) : i; };
+    double acc[NC];
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = 0.0;
+    for (int64_t i = lo; i < hi; i++)
+#pragma unroll
+        for (int c = 0; c < NC; c++) acc[c] += rows[(size_t)row(i)*NC + c];
+#pragma unroll
+    for (int c = 0; c < NC; c++) s_part[t][c] = acc[c];
+    __syncthreads();
+    if (t < NC) {                         // serial scan of the 512 partials, one component per thread
+        double run = 0.0;
+        for (int i = 0; i < 512; i++) { const double x = s_part[i][t]; s_part[i][t] = run; run += x; }
+        if (totals) totals[t] = run;
+    }
+    __syncthreads();
+#pragma unroll
+    for (int c = 0; c < NC; c++) acc[c] = s_part[t][c];
+    for (int64_t i = lo; i < hi; i++) {
+#pragma unroll
+        for (int c = 0; c < NC; c++) {
+            const size_t idx = (size_t)row(i)*NC + c;
+            const double x = rows[idx];
+            rows[idx] = acc[c];
+            acc[c] += x;
+        }
+    }
+}
+
+// Body record of the barycentre from the grand totals (reb_simulation_com restated as a
+// reduction: x = sum(m x)/sum(m); index -1 = "no particle").
+__global__ void com_body_kernel(const double* __restrict__ totals, double* __restrict__ body, int nbodies) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const double M = totals[0];
+    for (int b = 0; b < nbodies; b++) {
+        double* rec = body + (size_t)b*REBX_B200_BODY_DOUBLES;
+        for (int j = 0; j < REBX_B200_BODY_DOUBLES; j++) rec[j] = 0.0;
+        rec[REBX_B200_BODY_INDEX] = -1.0;
+        for (int j = 0; j < 6; j++) rec[REBX_B200_BODY_X + j] = (M > 0.) ? totals[1 + j]/M : totals[1 + j];
+        rec[REBX_B200_BODY_M] = M;
+    }
+}
+
+// ---- Jacobi sweep --------------------------------------------------------------------------------
+template <int K>
+__device__ __forceinline__ Vec3 damping_force(const rebx_b200_effect& fx, const double* __restrict__ body, const Particle& p, int64_t k) {
+    if constexpr (K == REBX_B200_MODIFY_ORBITS) {
+        return modify_orbits(fx, body, p, __ldcs(fx.tab[0] + k), __ldcs(fx.tab[1] + k), __ldcs(fx.tab[2] + k));
+    } else if constexpr (K == REBX_B200_GAS_DAMPING) {
+        return gas_damping(fx, body, p, __ldcs(fx.tab[0] + k));
+    } else if constexpr (K == REBX_B200_TYPE_I) {
+        return type_I_migration(fx, body, p);
+    } else {
+        return Vec3{0.0, 0.0, 0.0};
+    }
+}
+
+// tile_prefix[tile][7]: exclusive prefix of the mass moments at the tile's first particle.
+// Writes a += f (particle's own force), tvec[3][n] = t_i, tile_tsums[tile][3] = sum of t in the tile.
+template <int K0, int K1, int K2>
+__global__ void __launch_bounds__(kScanThreads)
+jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __restrict__ tile_prefix,
+                    double* __restrict__ tvec, double* __restrict__ tile_tsums) {
+    __shared__ double s_warp[kScanThreads/32][7];
+    const rebx_b200_state& st = P.st;
+    const int64_t k = (int64_t)blockIdx.x*kScanThreads + threadIdx.x;
+    const bool live = k < st.n;
+    Particle p = {0, 0, 0, 0, 0, 0, 0, 0};
+    if (live) {
+        p.x = st.x[k]; p.y = st.y[k]; p.z = st.z[k]; p.vx = st.vx[k]; p.vy = st.vy[k]; p.vz = st.vz[k]; p.m = st.m[k];
+    }
+    double v[7] = {p.m, p.x*p.m, p.y*p.m, p.z*p.m, p.vx*p.m, p.vy*p.m, p.vz*p.m};
+    double total[7];
+    block_exclusive_scan<7>(v, total, s_warp);
+    double body[REBX_B200_BODY_DOUBLES];
+    const double M = tile_prefix[(size_t)blockIdx.x*7] + v[0];          // mass interior to particle k
+#pragma unroll
+    for (int j = 0; j < 6; j++) {
+        const double S = tile_prefix[(size_t)blockIdx.x*7 + 1 + j] + v[1 + j];
+        body[REBX_B200_BODY_X + j] = (M > 0.) ? S/M : S;
+    }
+    body[REBX_B200_BODY_INDEX] = -1.0;
+    body[REBX_B200_BODY_M] = M;
+
+    double t[3] = {0.0, 0.0, 0.0};
+    const long long gi = st.index_base + k;
+    if (live && gi != 0) {                                              // particle 0 has no Jacobi coordinate (rebxtools.c:71-73)
+        Vec3 a = {st.ax[k], st.ay[k], st.az[k]};
+        const double mr = p.m/(M + p.m);
+        Vec3 f;
+        f = damping_force<K0>(P.fx[0], body, p, k);
+        a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
+        if constexpr (K1 != 0) {
+            f = damping_force<K1>(P.fx[1], body, p, k);
+            a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
+        }
+        if constexpr (K2 != 0) {
+            f = damping_force<K2>(P.fx[2], body, p, k);
+            a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
+        }
+        st.ax[k] = a.x; st.ay[k] = a.y; st.az[k] = a.z;
+    }
+    if (live) { tvec[k] = t[0]; tvec[st.n + k] = t[1]; tvec[2*st.n + k] = t[2]; }
+    // tile total of t (any order is fine; reuse the scan)
+    double tt[3], tot3[3];
+    tt[0] = t[0]; tt[1] = t[1]; tt[2] = t[2];
+    block_exclusive_scan<3>(tt, tot3, reinterpret_cast<double (*)[3]>(&s_warp[0][0]));
+    if (threadIdx.x < 3) tile_tsums[(size_t)blockIdx.x*3 + threadIdx.x] = tot3[threadIdx.x];
+}
+
+// a_j -= sum_{i >= j} t_i : in-tile reverse inclusive scan + exclusive suffix of the tiles behind.
+__global__ void __launch_bounds__(kScanThreads)
+jacobi_apply_kernel(rebx_b200_state st, const double* __restrict__ tvec, const double* __restrict__ tile_suffix) {
+    __shared__ double s_warp[kScanThreads/32][3];
+    const int64_t tile_lo = (int64_t)blockIdx.x*kScanThreads;
+    const int64_t tile_hi = (tile_lo + kScanThreads < st.n) ? tile_lo + kScanThreads : st.n;
+    const int64_t k = tile_hi - 1 - threadIdx.x;                        // reversed order inside the tile
+    const bool live = k >= tile_lo;
+    double t[3] = {0.0, 0.0, 0.0};
+    if (live) { t[0] = tvec[k]; t[1] = tvec[st.n + k]; t[2] = tvec[2*st.n + k]; }
+    double own[3] = {t[0], t[1], t[2]}, tot[3];
+    block_exclusive_scan<3>(t, tot, s_warp);
+    if (live) {
+        st.ax[k] -= tile_suffix[(size_t)blockIdx.x*3 + 0] + (t[0] + own[0]);
+        st.ay[k] -= tile_suffix[(size_t)blockIdx.x*3 + 1] + (t[1] + own[1]);
+        st.az[k] -= tile_suffix[(size_t)blockIdx.x*3 + 2] + (t[2] + own[2]);
+    }
+}
+
+typedef void (*jacobi_fn)(const rebx_b200_pass, const double*, double*, double*);
+struct JacobiCombo { int k[3]; jacobi_fn fn; };
+#define REBXB_JCOMBO(a, b, c) { {a, b, c}, jacobi_sweep_kernel<a, b, c> },
+static const JacobiCombo kJacobiCombos[] = {
+    REBXB_JCOMBO(5,0,0) REBXB_JCOMBO(6,0,0) REBXB_JCOMBO(7,0,0)
+    REBXB_JCOMBO(5,6,0) REBXB_JCOMBO(6,5,0) REBXB_JCOMBO(5,7,0) REBXB_JCOMBO(7,5,0) REBXB_JCOMBO(6,7,0) REBXB_JCOMBO(7,6,0)
+    REBXB_JCOMBO(5,6,7) REBXB_JCOMBO(5,7,6) REBXB_JCOMBO(6,5,7) REBXB_JCOMBO(6,7,5) REBXB_JCOMBO(7,5,6) REBXB_JCOMBO(7,6,5)
+};
+
+}  // namespace rebxb

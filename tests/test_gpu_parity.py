@@ -232,3 +232,54 @@ def test_multi_chunk_pipeline(built, monkeypatch):
     scale = sum(br[f][3:] for f in order) + np.abs([acc0[k][0] for k in range(3)])
     for k in range(3):
         assert abs(got[k][0] - exact[k]) <= TOL*scale[k]
+
+
+@pytest.mark.parametrize("coordinates", ["JACOBI", "BARYCENTRIC"])
+@pytest.mark.parametrize("add_order", [TRIO, ["gas_damping_timescale", "modify_orbits_forces"], ["type_I_migration"]])
+def test_damping_trio_centre_of_mass_frames(built, coordinates, add_order):
+    """REBX_COORDINATES_JACOBI (the reference's default) and _BARYCENTRIC: O(N^2) sequential loops in
+    the reference (src/rebxtools.c:92-128), scans / reductions on the device.  The evaluation order
+    of the sums differs, so the bar is the north-star tolerance, not bit identity."""
+    from reboundx_b200 import workloads
+    w = workloads.planetesimal_disk(3000)
+    if coordinates == "BARYCENTRIC":
+        w["d_factor"] = np.full(3000, 5.0)
+    acc0 = acc_variants(w, 10)["gravity"]
+    want, _ = oracle_acc(w, add_order, acc0, coordinates)
+    from reboundx_b200 import scenarios
+    sim, rebx, _ = scenarios.build(w, add_order, coordinates=coordinates, acc=acc0)
+    sim.additional_forces()
+    msgs = sim.messages()
+    got = sim.acc()
+    assert rebx.stats()["launches"] >= 3
+    rebx.detach(); sim.free()
+    errs = [m for k, m in msgs if k == "error"]
+    if coordinates == "BARYCENTRIC" and "gas_damping_timescale" in add_order:
+        assert errs and all("d_factor" in m for m in errs)       # the star has no d_factor: same error as the reference
+    else:
+        assert not errs, errs
+    if coordinates == "BARYCENTRIC":
+        # The star itself is evaluated against the barycentre it sits 3.5e-8 AU away from: its
+        # relative position is the difference of two AU-scale numbers, so ANY change in the order
+        # the centre of mass is summed in (sequential fold in REBOUND, tree reduction here) moves
+        # it by ~eps*|x|/|x0 - com|.  That one body gets a conditioning-aware bound; all others
+        # must meet the tolerance.
+        e = errors(got, want, skip=(0,))
+        M = w["m"].sum()
+        off = np.sqrt(sum((w[k][0] - (w[k]*w["m"]).sum()/M)**2 for k in ("x", "y", "z")))
+        cond = np.max(np.abs(w["x"]))/off
+        star = errors([g[:1] for g in got], [x[:1] for x in want])
+        assert star["max_normwise"] <= 16*np.finfo(float).eps*cond, (star, cond)
+    else:
+        e = errors(got, want)
+    assert e["max_normwise"] <= TOL, e
+    assert e["frac_component_above_tol"] <= 5e-3, e
+
+
+def test_jacobi_is_the_default_frame(built):
+    """No 'coordinates' parameter => REBX_COORDINATES_JACOBI (reference src/modify_orbits_forces.c:131-135)."""
+    from reboundx_b200 import workloads
+    w = workloads.planetesimal_disk(1500)
+    want, _ = oracle_acc(w, ["modify_orbits_forces"], None, "JACOBI")
+    got, _ = device_acc(w, ["modify_orbits_forces"], None, coordinates=None)
+    assert errors(got, want)["max_normwise"] <= TOL
