@@ -198,6 +198,11 @@ class Simulation:
     def time_additional_forces(self, reps=1):
         return float(self._shim.reb_shim_time_additional_forces(self._p, c_int(reps)))
 
+    def integrate(self, nsteps, scheme="leapfrog"):
+        """Host integrator harness of the stand-in (NOT REBOUND's WHFast/IAS15): `nsteps` fixed steps of
+        `dt` with Newtonian gravity from the first N_active bodies + additional_forces."""
+        self._shim.reb_shim_integrate(self._p, c_int(nsteps), c_int({"leapfrog": 0, "rk4": 1}[scheme]))
+
     def free(self):
         if self._p is not None:
             self._shim.reb_simulation_free(self._p)

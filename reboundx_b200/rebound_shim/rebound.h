@@ -144,6 +144,14 @@ void reb_shim_bulk_set_int(struct reb_simulation* r, reb_shim_set_int_fn setter,
 void** reb_shim_particle_ap(struct reb_simulation* r, size_t i);
 /* Calls r->additional_forces(r) if installed; returns 1 if it was called. */
 int reb_shim_call_additional_forces(struct reb_simulation* r);
+/* Host integrator harness (NOT REBOUND's integrators, which are not available here): advances the
+ * simulation `nsteps` fixed steps of r->dt.  Accelerations = Newtonian gravity of the first N_active
+ * bodies (all, when unset) on every particle + r->additional_forces(r).
+ *   scheme 0: drift-kick-drift leapfrog, one force evaluation per step  (stands in for WHFast)
+ *   scheme 1: classical RK4, four force evaluations per step           (stands in for IAS15's
+ *             multi-evaluation high-order stepping)
+ * Used to compare trajectories between two force implementations with everything else equal. */
+void reb_shim_integrate(struct reb_simulation* r, int nsteps, int scheme);
 /* Wall-clock seconds for `reps` calls of r->additional_forces(r) (best single call). */
 double reb_shim_time_additional_forces(struct reb_simulation* r, int reps);
 

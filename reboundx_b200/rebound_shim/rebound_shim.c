@@ -413,3 +413,79 @@ double reb_shim_time_additional_forces(struct reb_simulation* r, int reps){
     }
     return best;
 }
+
+/* ------------------------------------------------------------------ integrator harness */
+
+static void shim_accelerations(struct reb_simulation* r){
+    const size_t N = r->N;
+    const size_t Nact = (r->N_active == SIZE_MAX || r->N_active > N) ? N : r->N_active;
+    struct reb_particle* p = r->particles;
+    const double soft2 = r->softening*r->softening;
+    for (size_t i = 0; i < N; i++){ p[i].ax = 0.; p[i].ay = 0.; p[i].az = 0.; }
+    for (size_t j = 0; j < Nact; j++){
+        const double mj = p[j].m;
+        if (mj == 0.) continue;
+        for (size_t i = 0; i < N; i++){
+            if (i == j) continue;
+            const double dx = p[i].x - p[j].x, dy = p[i].y - p[j].y, dz = p[i].z - p[j].z;
+            const double r2 = dx*dx + dy*dy + dz*dz + soft2;
+            const double pref = -r->G*mj/(r2*sqrt(r2));
+            p[i].ax += pref*dx; p[i].ay += pref*dy; p[i].az += pref*dz;
+        }
+    }
+    if (r->additional_forces) r->additional_forces(r);
+}
+
+void reb_shim_integrate(struct reb_simulation* r, int nsteps, int scheme){
+    const size_t N = r->N;
+    struct reb_particle* p = r->particles;
+    const double dt = r->dt;
+    if (scheme == 0){
+        for (int s = 0; s < nsteps; s++){
+            for (size_t i = 0; i < N; i++){ p[i].x += 0.5*dt*p[i].vx; p[i].y += 0.5*dt*p[i].vy; p[i].z += 0.5*dt*p[i].vz; }
+            r->t += 0.5*dt;
+            shim_accelerations(r);
+            for (size_t i = 0; i < N; i++){ p[i].vx += dt*p[i].ax; p[i].vy += dt*p[i].ay; p[i].vz += dt*p[i].az; }
+            for (size_t i = 0; i < N; i++){ p[i].x += 0.5*dt*p[i].vx; p[i].y += 0.5*dt*p[i].vy; p[i].z += 0.5*dt*p[i].vz; }
+            r->t += 0.5*dt;
+            r->dt_last_done = dt;
+        }
+        return;
+    }
+    /* RK4 on (x, v) */
+    double* y0 = malloc(6*N*sizeof(double));
+    double* k = malloc(4*6*N*sizeof(double));
+    for (int s = 0; s < nsteps; s++){
+        const double t0 = r->t;
+        for (size_t i = 0; i < N; i++){
+            y0[6*i+0] = p[i].x; y0[6*i+1] = p[i].y; y0[6*i+2] = p[i].z;
+            y0[6*i+3] = p[i].vx; y0[6*i+4] = p[i].vy; y0[6*i+5] = p[i].vz;
+        }
+        const double c[4] = {0., 0.5, 0.5, 1.};
+        for (int st = 0; st < 4; st++){
+            if (st > 0){
+                const double* kp = k + (size_t)(st-1)*6*N;
+                for (size_t i = 0; i < N; i++){
+                    p[i].x = y0[6*i+0] + c[st]*dt*kp[6*i+0]; p[i].y = y0[6*i+1] + c[st]*dt*kp[6*i+1]; p[i].z = y0[6*i+2] + c[st]*dt*kp[6*i+2];
+                    p[i].vx = y0[6*i+3] + c[st]*dt*kp[6*i+3]; p[i].vy = y0[6*i+4] + c[st]*dt*kp[6*i+4]; p[i].vz = y0[6*i+5] + c[st]*dt*kp[6*i+5];
+                }
+            }
+            r->t = t0 + c[st]*dt;
+            shim_accelerations(r);
+            double* kc = k + (size_t)st*6*N;
+            for (size_t i = 0; i < N; i++){
+                kc[6*i+0] = p[i].vx; kc[6*i+1] = p[i].vy; kc[6*i+2] = p[i].vz;
+                kc[6*i+3] = p[i].ax; kc[6*i+4] = p[i].ay; kc[6*i+5] = p[i].az;
+            }
+        }
+        for (size_t i = 0; i < N; i++){
+            double y[6];
+            for (int q = 0; q < 6; q++)
+                y[q] = y0[6*i+q] + dt/6.*(k[6*i+q] + 2.*k[6*N+6*i+q] + 2.*k[12*N+6*i+q] + k[18*N+6*i+q]);
+            p[i].x = y[0]; p[i].y = y[1]; p[i].z = y[2]; p[i].vx = y[3]; p[i].vy = y[4]; p[i].vz = y[5];
+        }
+        r->t = t0 + dt;
+        r->dt_last_done = dt;
+    }
+    free(y0); free(k);
+}

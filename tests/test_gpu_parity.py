@@ -283,3 +283,67 @@ def test_jacobi_is_the_default_frame(built):
     want, _ = oracle_acc(w, ["modify_orbits_forces"], None, "JACOBI")
     got, _ = device_acc(w, ["modify_orbits_forces"], None, coordinates=None)
     assert errors(got, want)["max_normwise"] <= TOL
+
+
+# ---- criterion (ii): trajectories after 10^3 steps --------------------------------------------------
+def _trajectory(case_or_w, lib, nsteps, scheme, dt, n_active, add_order=None, coordinates="PARTICLE"):
+    from reboundx_b200 import scenarios
+    if add_order is None:
+        sim, rebx, _ = scenarios.build_case(case_or_w, lib)
+    else:
+        sim, rebx, _ = scenarios.build(case_or_w, add_order, lib=lib, coordinates=coordinates)
+    sim.dt = dt
+    sim.N_active = n_active
+    sim.integrate(nsteps, scheme)
+    errs = [m for k, m in sim.messages() if k == "error"]
+    assert not errs, errs[:2]
+    out = np.array(sim.posvel())
+    rebx.detach(); sim.free()
+    return out
+
+
+def _assert_trajectories_agree(a, b, tol=1e-10):
+    pos_scale = np.sqrt((b[:3]**2).sum(axis=0))
+    vel_scale = np.sqrt((b[3:]**2).sum(axis=0))
+    dpos = np.sqrt(((a[:3] - b[:3])**2).sum(axis=0))
+    dvel = np.sqrt(((a[3:] - b[3:])**2).sum(axis=0))
+    live = pos_scale > 0
+    assert np.max(dpos[live]/pos_scale[live]) <= tol, np.max(dpos[live]/pos_scale[live])
+    live = vel_scale > 0
+    assert np.max(dvel[live]/vel_scale[live]) <= tol, np.max(dvel[live]/vel_scale[live])
+
+
+@pytest.mark.parametrize("scheme", ["leapfrog", "rk4"])
+def test_trajectory_debris_disk_1000_steps(built, scheme):
+    """Config 1a shape (Sun + 1000 dust grains, beta = 0.1, dt = 1e8 s): 10^3 steps with the CUDA force
+    vs the reference-compiled force, everything else identical (host harness, not REBOUND)."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import golden_io
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    case, _, _ = golden_io.load("rad_debris_disk_example")
+    ours = _trajectory(case, None, 1000, scheme, 1e8, 1)
+    ref = _trajectory(case, oracle.ref_lib(), 1000, scheme, 1e8, 1)
+    _assert_trajectories_agree(ours, ref)
+    assert np.array_equal(ours, ref)          # bit-exact forces => bit-exact trajectories
+
+
+@pytest.mark.parametrize("which", ["ring", "asteroids", "planetesimals_particle", "planetesimals_jacobi"])
+def test_trajectories_other_configs_1000_steps(built, which):
+    from oracle import oracle
+    from reboundx_b200 import workloads as W
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    if which == "ring":
+        w, add, coords, dt = W.circumplanetary_ring(400, massive=True), ["gravitational_harmonics", "gr_potential"], "PARTICLE", 50.0
+    elif which == "asteroids":
+        w, add, coords, dt = W.asteroid_ensemble(400), ["yarkovsky_effect", "gr_potential"], "PARTICLE", 0.01
+    elif which == "planetesimals_particle":
+        w, add, coords, dt = W.planetesimal_disk(400), TRIO, "PARTICLE", 0.002
+    else:
+        w, add, coords, dt = W.planetesimal_disk(400), TRIO, "JACOBI", 0.002
+    ours = _trajectory(w, None, 1000, "rk4", dt, 1, add, coords)
+    ref = _trajectory(w, oracle.ref_lib(), 1000, "rk4", dt, 1, add, coords)
+    _assert_trajectories_agree(ours, ref)
