@@ -27,6 +27,9 @@
 
 namespace rebxb {
 
+#ifndef REBXB_HEAVY_MINBLOCKS
+#define REBXB_HEAVY_MINBLOCKS 2
+#endif
 constexpr int kThreads   = 256;
 constexpr int kMaxBlocks = 4096;
 constexpr int kWarps     = kThreads/32;
@@ -145,7 +148,7 @@ template <int K0, int K1, int K2, int K3>
 constexpr int min_blocks() {
     constexpr bool light = (K0 == REBX_B200_RADIATION || K0 == REBX_B200_GR_POTENTIAL) &&
                            (K1 == 0 || K1 == REBX_B200_RADIATION || K1 == REBX_B200_GR_POTENTIAL) && K2 == 0 && K3 == 0;
-    return light ? 4 : 2;
+    return light ? 4 : REBXB_HEAVY_MINBLOCKS;
 }
 
 template <int V, int K0, int K1, int K2, int K3>
