@@ -218,11 +218,11 @@ def run_ours(args):
     peak, peak_src = peaks()
     achieved = shard.algorithmic_bytes/(kernel_ms*1e-3)/1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
-                "traffic": None, "kernel": "pass_kernel<V=2>(%s)" % ",".join(exec_order),
+                "traffic": None, "kernel": "pass_kernel(%s)" % ",".join(exec_order),
                 "algorithmic_bytes_per_particle": device.algorithmic_bytes_per_particle(shard.kinds),
                 "kernel_ms": kernel_ms, "peak_source": peak_src}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof):
+    if os.path.exists(prof) and n == n_default:       # ncu dram__bytes_read+write per launch, captured at the config's size
         with open(prof) as f:
             roofline["traffic"] = json.load(f).get(args.workload)
 

@@ -26,6 +26,94 @@ __device__ __forceinline__ bool is_absent(double v) {
 }
 
 // ---------------------------------------------------------------------------------------
+// Correctly rounded division with a SHARED reciprocal.
+//
+// An IEEE FP64 division costs ~16 DFMA issue slots on B200 (profiles/r01_fp64_probe.txt) and
+// the force expressions divide several numerators by the same divisor (|r|, r^2, c).  With
+// y = RN(1/b) obtained from ONE true division, each further quotient is
+//     q0 = RN(a y);  r0 = a - b q0 (exact, FMA);  q1 = RN(q0 + r0 y)      -> faithful
+//     r1 = a - b q1 (exact, FMA);                 q  = RN(q1 + r1 y)      -> RN(a/b)
+// The last step is Markstein's theorem (Markstein 1990; Muller et al., Handbook of
+// Floating-Point Arithmetic, "division with an FMA"): with y the correctly rounded reciprocal
+// and q1 faithful, the corrected quotient is the correctly rounded a/b, except when b's
+// significand is all ones -- that case, zeros, subnormals, infinities/NaNs and any exponent
+// outside +-400 (so nothing over/underflows on the way) take the ordinary division.  The
+// result is therefore bit-identical to `a/b`; 5 slots per quotient instead of ~16.
+//
+// MEASURED (B200, round 1): compiling with -DREBXB_SHARED_RECIP=1 halves the FP64 instruction
+// count of the J2/J4+gr_potential sweep (769 -> 395 static FP64 SASS instructions) and keeps every
+// bit-exactness test green, but does NOT shorten the sweep (0.2865 vs 0.2857 ms at 10^7): ncu shows
+// the FP64-heavy sweeps stall on the fixed latency of DEPENDENT operations (stall_wait dominates),
+// and the corrected quotient is as long a dependent chain as the hardware division sequence.  On
+// the radiation sweep the extra live values spill at the 64-register cap (0.207 vs 0.174 ms).
+// Hence off by default; kept as a compile-time option.
+// ---------------------------------------------------------------------------------------
+#ifndef REBXB_SHARED_RECIP
+#define REBXB_SHARED_RECIP 0
+#endif
+struct Recip { double b, y; bool ok; };
+
+__device__ __forceinline__ bool mid_exponent(double v) {
+    const int e = (__double2hiint(v) >> 20) & 0x7ff;
+    return e > 1023 - 400 && e < 1023 + 400;
+}
+
+__device__ __forceinline__ Recip make_recip(double b) {
+    Recip R;
+    R.b = b;
+    if (!REBXB_SHARED_RECIP) { R.y = 0.0; R.ok = false; return R; }
+    R.y = 1.0/b;
+    const unsigned long long mant = (unsigned long long)__double_as_longlong(b) & 0x000fffffffffffffULL;
+    R.ok = mid_exponent(b) && mant != 0x000fffffffffffffULL;
+    return R;
+}
+
+__device__ __noinline__ double div_slow(double a, double b) { return a/b; }
+
+__device__ __forceinline__ double div_by(double a, const Recip& R) {
+    if (!REBXB_SHARED_RECIP) return a/R.b;
+    if (R.ok && mid_exponent(a)) {
+        double q = a*R.y;
+        double r = fma(-R.b, q, a);
+        q = fma(r, R.y, q);
+        r = fma(-R.b, q, a);
+        return fma(r, R.y, q);
+    }
+    return div_slow(a, R.b);
+}
+
+// Per-thread constants of one effect entry, computed once before the sweep loop (all of
+// them particle-independent sub-expressions of the reference formulas, same association).
+struct Pre { Recip rc; double k0, k1; };
+
+template <int K>
+__device__ __forceinline__ Pre prepare(const rebx_b200_effect& fx, const double* __restrict__ body) {
+    Pre pre;
+    pre.rc.b = 1.0; pre.rc.y = 1.0; pre.rc.ok = false; pre.k0 = 0.0; pre.k1 = 0.0;
+    const double bm = body[REBX_B200_BODY_M];
+    if constexpr (K == REBX_B200_RADIATION) {
+        pre.rc = make_recip(fx.scal[1]);                 // 1/c
+        pre.k0 = fx.scal[0]*bm;                          // mu = G*m_source           (radiation_forces.c:71)
+    } else if constexpr (K == REBX_B200_HARMONICS) {
+        const double G = fx.scal[0], J2 = body[REBX_B200_BODY_J2], J4 = body[REBX_B200_BODY_J4], Req = body[REBX_B200_BODY_REQ];
+        pre.k0 = 1.5*G*bm*J2*Req*Req;                    // numerator of f1 in j2_func (gravitational_harmonics.c:77)
+        pre.k1 = 0.625*G*bm*J4*Req*Req*Req*Req;          // numerator of f1 in j4_func (:93)
+    } else if constexpr (K == REBX_B200_GR_POTENTIAL) {
+        const double Gm = fx.scal[0]*bm;
+        pre.k0 = 6.*Gm*Gm/fx.scal[1];                    // prefac1                    (gr_potential.c:62)
+    } else if constexpr (K == REBX_B200_YARKOVSKY) {
+        pre.rc = make_recip(fx.scal[2]);                 // 1/ye_c
+    }
+    return pre;
+}
+
+// m_particle / m_body.  For a massless test particle and a body of positive mass the quotient is
+// exactly +0, which is what the division would return.
+__device__ __forceinline__ double mass_ratio(double m, double bm) {
+    return (m == 0.0 && bm > 0.0) ? 0.0 : m/bm;
+}
+
+// ---------------------------------------------------------------------------------------
 // Two-body elements relative to `body` -- restates REBOUND's reb_orbit_from_particle_err
 // (third-party, not under /root/reference; same restatement as rebound_shim.c).
 // Only the members the force path reads: a, e, inc, P.
@@ -94,34 +182,31 @@ __device__ __forceinline__ double planet_trap(double r, double dedge, double hed
 // ---------------------------------------------------------------------------------------
 
 // src/radiation_forces.c:69-98
-__device__ __forceinline__ void radiation(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ void radiation(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
                                           const Particle& p, double beta, Vec3& a) {
     if (is_absent(beta)) return;
-    const double c  = fx.scal[1];
-    const double mu = fx.scal[0]*body[REBX_B200_BODY_M];
+    const double mu = pre.k0;
     const double dx = p.x - body[REBX_B200_BODY_X+0];
     const double dy = p.y - body[REBX_B200_BODY_X+1];
     const double dz = p.z - body[REBX_B200_BODY_X+2];
     const double dr = sqrt(dx*dx + dy*dy + dz*dz);
+    const Recip rdr = make_recip(dr);
     const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
     const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
     const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
-    const double rdot = (dx*dvx + dy*dvy + dz*dvz)/dr;
+    const double rdot = div_by(dx*dvx + dy*dvy + dz*dvz, rdr);
     const double a_rad = beta*mu/(dr*dr);
-    const double k1 = 1. - rdot/c;
-    a.x += a_rad*(k1*dx/dr - dvx/c);
-    a.y += a_rad*(k1*dy/dr - dvy/c);
-    a.z += a_rad*(k1*dz/dr - dvz/c);
+    const double k1 = 1. - div_by(rdot, pre.rc);
+    a.x += a_rad*(div_by(k1*dx, rdr) - div_by(dvx, pre.rc));
+    a.y += a_rad*(div_by(k1*dy, rdr) - div_by(dvy, pre.rc));
+    a.z += a_rad*(div_by(k1*dz, rdr) - div_by(dvz, pre.rc));
 }
 
 // src/gravitational_harmonics.c:184-224 with j2_func :72-86 and j4_func :88-102
-__device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
                                           const Particle& p, Vec3& a, Vec3& red) {
-    const double G   = fx.scal[0];
     const double bm  = body[REBX_B200_BODY_M];
-    const double J2  = body[REBX_B200_BODY_J2];
     const double J4  = body[REBX_B200_BODY_J4];
-    const double Req = body[REBX_B200_BODY_REQ];
     const double ux = body[REBX_B200_BODY_U+0], uy = body[REBX_B200_BODY_U+1], uz = body[REBX_B200_BODY_U+2];
     const double vx = body[REBX_B200_BODY_V+0], vy = body[REBX_B200_BODY_V+1], vz = body[REBX_B200_BODY_V+2];
     const double wx = body[REBX_B200_BODY_W+0], wy = body[REBX_B200_BODY_W+1], wz = body[REBX_B200_BODY_W+2];
@@ -131,15 +216,16 @@ __device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const doub
     const double dz = p.z - body[REBX_B200_BODY_X+2];
     const double r2 = dx*dx + dy*dy + dz*dz;
     const double r  = sqrt(r2);
+    const Recip rr2 = make_recip(r2), rr = make_recip(r);
     const double du = ux*dx + uy*dy + uz*dz;
     const double dv = vx*dx + vy*dy + vz*dz;
     const double dw = wx*dx + wy*dy + wz*dz;
-    const double costheta  = dw/r;
+    const double costheta  = div_by(dw, rr);
     const double costheta2 = costheta*costheta;
 
     double au = 0.0, av = 0.0, aw = 0.0;
     {   // J2 != 0 is guaranteed by the table builder (body skipped otherwise)
-        const double f1 = 1.5*G*bm*J2*Req*Req/r2/r2/r;
+        const double f1 = div_by(div_by(div_by(pre.k0, rr2), rr2), rr);      // 3/2 G m J2 R^2 /r2/r2/r
         const double f2 = 5.0*costheta2 - 1.0;
         const double f3 = f2 - 2.0;
         au += f1*f2*du;
@@ -147,7 +233,7 @@ __device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const doub
         aw += f1*f3*dw;
     }
     if (J4 != 0.0) {
-        const double f1 = 0.625*G*bm*J4*Req*Req*Req*Req/r2/r2/r2/r;
+        const double f1 = div_by(div_by(div_by(div_by(pre.k1, rr2), rr2), rr2), rr);   // 5/8 G m J4 R^4 /r2/r2/r2/r
         const double f2 = 63.0*costheta2*costheta2 - 42.0*costheta2 + 3.0;
         const double f3 = f2 - 28.0*costheta2 + 12.0;
         au += f1*f2*du;
@@ -158,22 +244,21 @@ __device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const doub
     const double ay = uy*au + vy*av + wy*aw;
     const double az = uz*au + vz*av + wz*aw;
     a.x += ax;  a.y += ay;  a.z += az;
-    const double fac = p.m/bm;
+    const double fac = mass_ratio(p.m, bm);
     red.x -= fac*ax;  red.y -= fac*ay;  red.z -= fac*az;
 }
 
 // src/gr_potential.c:60-78
-__device__ __forceinline__ void gr_potential(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ void gr_potential(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
                                              const Particle& p, Vec3& a, Vec3& red) {
-    const double Gm = fx.scal[0]*body[REBX_B200_BODY_M];
-    const double prefac1 = 6.*Gm*Gm/fx.scal[1];
+    const double prefac1 = pre.k0;
     const double dx = p.x - body[REBX_B200_BODY_X+0];
     const double dy = p.y - body[REBX_B200_BODY_X+1];
     const double dz = p.z - body[REBX_B200_BODY_X+2];
     const double r2 = dx*dx + dy*dy + dz*dz;
     const double prefac = prefac1/(r2*r2);
     a.x -= prefac*dx;  a.y -= prefac*dy;  a.z -= prefac*dz;
-    const double mr = p.m/body[REBX_B200_BODY_M];
+    const double mr = mass_ratio(p.m, body[REBX_B200_BODY_M]);
     red.x += mr*prefac*dx;  red.y += mr*prefac*dy;  red.z += mr*prefac*dz;
 }
 
@@ -182,7 +267,7 @@ __device__ __forceinline__ void gr_potential(const rebx_b200_effect& fx, const d
 // missing, or a flag value the reference leaves undefined).
 struct YarkParams { double density, rot_period, Gamma, albedo, emissivity, k, sx, sy, sz; };
 
-__device__ __forceinline__ void yarkovsky(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ void yarkovsky(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
                                           const Particle& p, const YarkParams& yp, int code, Vec3& a) {
     if (code == 2 || p.r == 0) return;
     const double G = fx.scal[0], lstar = fx.scal[1], c = fx.scal[2], stef_boltz = fx.scal[3];
@@ -195,10 +280,11 @@ __device__ __forceinline__ void yarkovsky(const rebx_b200_effect& fx, const doub
     const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
     const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
     const double distance = sqrt((dx*dx) + (dy*dy) + (dz*dz));
+    const Recip rd = make_recip(distance);
     const double rdotv = ((dx*dvx) + (dy*dvy) + (dz*dvz))/(c*distance);
-    const double i0 = ((1 - rdotv)*(dx/distance)) - (dvx/c);
-    const double i1 = ((1 - rdotv)*(dy/distance)) - (dvy/c);
-    const double i2 = ((1 - rdotv)*(dz/distance)) - (dvz/c);
+    const double i0 = ((1 - rdotv)*div_by(dx, rd)) - div_by(dvx, pre.rc);
+    const double i1 = ((1 - rdotv)*div_by(dy, rd)) - div_by(dvy, pre.rc);
+    const double i2 = ((1 - rdotv)*div_by(dz, rd)) - div_by(dvz, pre.rc);
 
     double mag;
     double Y[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};

@@ -94,17 +94,17 @@ __device__ __forceinline__ void load_params(const rebx_b200_effect& fx, int64_t 
 }
 
 template <int K, int V>
-__device__ __forceinline__ void apply(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ void apply(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
                                       const Particle& p, const Params<K, V>& q, int v, Vec3& a, Vec3& red) {
     if constexpr (K == REBX_B200_RADIATION) {
-        radiation(fx, body, p, q.t[0][v], a);
+        radiation(fx, body, pre, p, q.t[0][v], a);
     } else if constexpr (K == REBX_B200_HARMONICS) {
-        harmonics(fx, body, p, a, red);
+        harmonics(fx, body, pre, p, a, red);
     } else if constexpr (K == REBX_B200_GR_POTENTIAL) {
-        gr_potential(fx, body, p, a, red);
+        gr_potential(fx, body, pre, p, a, red);
     } else if constexpr (K == REBX_B200_YARKOVSKY) {
         YarkParams yp{q.t[0][v], q.t[1][v], q.t[2][v], q.t[3][v], q.t[4][v], q.t[5][v], q.t[6][v], q.t[7][v], q.t[8][v]};
-        yarkovsky(fx, body, p, yp, q.it[v], a);
+        yarkovsky(fx, body, pre, p, yp, q.it[v], a);
     } else if constexpr (K == REBX_B200_MODIFY_ORBITS) {
         const Vec3 f = modify_orbits(fx, body, p, q.t[0][v], q.t[1][v], q.t[2][v]);
         com_force_tail(fx, body, p, f, a, red);
@@ -170,6 +170,10 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
     const long long b2 = (K2 != 0) ? (long long)s_body[2][0] : -1;
     const long long b3 = (K3 != 0) ? (long long)s_body[3][0] : -1;
 
+    const Pre pre0 = prepare<K0>(P.fx[0], s_body[0]);
+    const Pre pre1 = prepare<K1>(P.fx[1], s_body[1]);
+    const Pre pre2 = prepare<K2>(P.fx[2], s_body[2]);
+    const Pre pre3 = prepare<K3>(P.fx[3], s_body[3]);
     Vec3 red0 = {0., 0., 0.}, red1 = {0., 0., 0.}, red2 = {0., 0., 0.}, red3 = {0., 0., 0.};
 
     const int64_t n = P.st.n;
@@ -199,10 +203,10 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
             if constexpr (RAD)  { p.r = r[v]; } else { p.r = 0.0; }
             Vec3 a = {ax[v], ay[v], az[v]};
             const long long gi = P.st.index_base + k + v;
-            if (gi != b0) apply<K0, V>(P.fx[0], s_body[0], p, q0, v, a, red0);
-            if constexpr (K1 != 0) { if (gi != b1) apply<K1, V>(P.fx[1], s_body[1], p, q1, v, a, red1); }
-            if constexpr (K2 != 0) { if (gi != b2) apply<K2, V>(P.fx[2], s_body[2], p, q2, v, a, red2); }
-            if constexpr (K3 != 0) { if (gi != b3) apply<K3, V>(P.fx[3], s_body[3], p, q3, v, a, red3); }
+            if (gi != b0) apply<K0, V>(P.fx[0], s_body[0], pre0, p, q0, v, a, red0);
+            if constexpr (K1 != 0) { if (gi != b1) apply<K1, V>(P.fx[1], s_body[1], pre1, p, q1, v, a, red1); }
+            if constexpr (K2 != 0) { if (gi != b2) apply<K2, V>(P.fx[2], s_body[2], pre2, p, q2, v, a, red2); }
+            if constexpr (K3 != 0) { if (gi != b3) apply<K3, V>(P.fx[3], s_body[3], pre3, p, q3, v, a, red3); }
             ax[v] = a.x; ay[v] = a.y; az[v] = a.z;
         }
         st<V>(P.st.ax, k, full, ax); st<V>(P.st.ay, k, full, ay); st<V>(P.st.az, k, full, az);
@@ -346,12 +350,16 @@ pass_kernel_tma(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
         const long long b1 = (K1 != 0) ? (long long)s_body[1][0] : -1;
         const long long b2 = (K2 != 0) ? (long long)s_body[2][0] : -1;
         const long long b3 = (K3 != 0) ? (long long)s_body[3][0] : -1;
+        const Pre pre0 = prepare<K0>(P.fx[0], s_body[0]);
+        const Pre pre1 = prepare<K1>(P.fx[1], s_body[1]);
+        const Pre pre2 = prepare<K2>(P.fx[2], s_body[2]);
+        const Pre pre3 = prepare<K3>(P.fx[3], s_body[3]);
         auto one = [&](const Particle& p, Vec3& a, long long gi, const Params<K0, 1>& q0, const Params<K1, 1>& q1,
                        const Params<K2, 1>& q2, const Params<K3, 1>& q3) {
-            if (gi != b0) apply<K0, 1>(P.fx[0], s_body[0], p, q0, 0, a, red0);
-            if constexpr (K1 != 0) { if (gi != b1) apply<K1, 1>(P.fx[1], s_body[1], p, q1, 0, a, red1); }
-            if constexpr (K2 != 0) { if (gi != b2) apply<K2, 1>(P.fx[2], s_body[2], p, q2, 0, a, red2); }
-            if constexpr (K3 != 0) { if (gi != b3) apply<K3, 1>(P.fx[3], s_body[3], p, q3, 0, a, red3); }
+            if (gi != b0) apply<K0, 1>(P.fx[0], s_body[0], pre0, p, q0, 0, a, red0);
+            if constexpr (K1 != 0) { if (gi != b1) apply<K1, 1>(P.fx[1], s_body[1], pre1, p, q1, 0, a, red1); }
+            if constexpr (K2 != 0) { if (gi != b2) apply<K2, 1>(P.fx[2], s_body[2], pre2, p, q2, 0, a, red2); }
+            if constexpr (K3 != 0) { if (gi != b3) apply<K3, 1>(P.fx[3], s_body[3], pre3, p, q3, 0, a, red3); }
         };
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x, it++) {
@@ -628,7 +636,7 @@ int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* str
         return 0;
     }
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int vsel = pass_is_vectorizable(*pass) ? 1 : 0;
+    const bool aligned = pass_is_vectorizable(*pass);
     int done = 0;
     while (done < pass->n_effects) {
         int take = pass->n_effects - done;
@@ -648,8 +656,14 @@ int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* str
         }
         int grid;
         cudaError_t err;
-        if (vsel && use_tma() && sub.st.n >= 4*kTile) {
-            // TMA-fed ring (needs 16-byte aligned arrays, which `vsel` established)
+        // Two particles per thread (double2 access) pay off for the light and the J2/J4 sweeps; the
+        // register-heavy ones (yarkovsky, damping trio) run 5-20 % faster with one particle per
+        // thread (measured: asteroid 0.098 vs 0.104 ms, planetesimal 0.135 vs 0.171 ms).
+        bool heavy = false;
+        for (int j = 0; j < take; j++) if (sub.fx[j].kind >= REBX_B200_YARKOVSKY) heavy = true;
+        const int vsel = (aligned && !heavy) ? 1 : 0;
+        if (aligned && use_tma() && sub.st.n >= 4*kTile) {
+            // TMA-fed ring (needs 16-byte aligned arrays)
             pass_fn fn = combo->tma;
             err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, combo->tma_smem);
             if (err != cudaSuccess) return err;
