@@ -149,6 +149,7 @@ void rebx_additional_forces(struct reb_simulation* sim);
 void rebx_radiation_forces(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);        /* src/radiation_forces.c:100 */
 void rebx_gravitational_harmonics(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N); /* src/gravitational_harmonics.c:136 */
 void rebx_gr_potential(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);            /* src/gr_potential.c:80 */
+void rebx_gr(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);                      /* src/gr.c:166 */
 void rebx_yarkovsky_effect(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);        /* src/yarkovsky_effect.c:218 */
 void rebx_modify_orbits_forces(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);    /* src/modify_orbits_forces.c:130 */
 void rebx_gas_damping_timescale(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);   /* src/gas_damping_timescale.c:132 */

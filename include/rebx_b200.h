@@ -137,6 +137,25 @@ int rebx_b200_com_bodies(const double* totals7, double* bodies, int nbodies, voi
  * back-reaction, all on the device in O(n).  fx[].body and fx[].backreaction are ignored. */
 int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* stream, int* launches);
 
+/* ---- 1PN `gr` effect (reference src/gr.c:65-164) for N_active <= REBX_B200_GR_MAX_ACTIVE ---------
+ * Passed BY VALUE from host memory.  active[i] = {x, y, z, m} of active body i; com[] = the Jacobi
+ * origin of a test particle: position, velocity and Newtonian acceleration of the actives' centre of
+ * mass; mu = G*m_0.  Particles with global index < n_active are skipped by both kernels (the
+ * O(n_active^2) part is the caller's). */
+#define REBX_B200_GR_MAX_ACTIVE 8
+typedef struct rebx_b200_gr_args {
+    int32_t n_active;
+    int32_t max_iterations;
+    double G, C2, mu;
+    double com[9];
+    double active[REBX_B200_GR_MAX_ACTIVE][4];
+} rebx_b200_gr_args;
+/* pull[i*3+c] (device) = sum over the shard's test particles j of G m_j (x_i - x_j)_c / r^3. */
+int rebx_b200_gr_pull(const rebx_b200_state* st, const rebx_b200_gr_args* args, double* pull, void* workspace, void* stream, int* launches);
+/* a += 1PN acceleration for every test particle; *not_converged (device int) is set to 1 when a
+ * fixed-point iteration ran 10 times without converging (the reference's warning, gr.c:130-133). */
+int rebx_b200_gr_sweep(const rebx_b200_state* st, const rebx_b200_gr_args* args, int* not_converged, void* stream, int* launches);
+
 /* Barycentric second sweep: a[k] += delta[0..2] for every particle in the shard. */
 int rebx_b200_add_uniform(const rebx_b200_state* st, const double* delta, void* stream, int* launches);
 

@@ -39,11 +39,13 @@ def ref_lib():
     return _lib.load(REF_PATH)
 
 
-def ref_apply(w, forces, acc0=None, coordinates="PARTICLE", reps=0, messages=None):
+def ref_apply(w, forces, acc0=None, coordinates="PARTICLE", reps=0, messages=None, n_active=None):
     """Runs the compiled reference on workload `w`; `forces` in ADD order (they execute reversed).
     Returns (ax, ay, az) or, with reps > 0, ((ax, ay, az), best seconds per dispatch)."""
     from reboundx_b200 import scenarios
     sim, rebx, _ = scenarios.build(w, forces, lib=ref_lib(), coordinates=coordinates, acc=acc0)
+    if n_active is not None:
+        sim.N_active = n_active
     if reps > 0:
         sim.additional_forces()                       # warm-up
         if acc0 is not None:
@@ -98,7 +100,7 @@ def _full(w, name, n):
     return full, mask
 
 
-def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE"):
+def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE", n_active=-1):
     """Runs the C restatement on workload `w`; `exec_order` is the EXECUTION order of forces.
     Returns ((ax, ay, az), {force: [sum_x, sum_y, sum_z, abs_x, abs_y, abs_z]}): the back-reaction
     terms onto the body summed in long double, and the sum of their absolute values."""
@@ -126,6 +128,10 @@ def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE"):
             lib.oracle_gr_potential(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["m"]), c_double(w["G"]), c_double(w["c"]),
                                     _d(acc[0]), _d(acc[1]), _d(acc[2]), out)
             br[name] = np.array([float(v) for v in out])
+        elif name == "gr":
+            lib.oracle_gr(c_int64(n), c_int64(n_active), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]),
+                          _d(S["m"]), c_double(w["G"]), c_double(w["c"]), c_int(w.get("max_iterations") or 10),
+                          _d(acc[0]), _d(acc[1]), _d(acc[2]))
         elif name == "yarkovsky_effect":
             pars, masks = [], []
             for p in YARK_PARAMS:

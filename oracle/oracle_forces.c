@@ -374,3 +374,92 @@ int oracle_com_force(int kind, int coordinates, int64_t primary, const oracle_da
     if (br) { br[0] = bsx; br[1] = bsy; br[2] = bsz; br[3] = bax; br[4] = bay; br[5] = baz; }
     return 0;
 }
+
+/* ---- gr (reference src/gr.c:65-181) ----------------------------------------------------------
+ * n_active < 0 means "unset" (all particles active).  The Jacobi transforms restate REBOUND's
+ * reb_transformations_inertial_to_jacobi_posvelacc / _jacobi_to_inertial_acc (third-party, same
+ * restatement as reboundx_b200/rebound_shim/rebound_shim.c: parity UNPINNED at that boundary).
+ * Returns 1 if some fixed-point iteration hit 10 iterations (the reference's warning). */
+#include <stdlib.h>
+int oracle_gr(int64_t n, int64_t n_active, const double* x, const double* y, const double* z,
+              const double* vx, const double* vy, const double* vz, const double* m,
+              double G, double c, int max_iterations, double* ax, double* ay, double* az) {
+    const int64_t A = (n_active < 0 || n_active > n) ? n : n_active;
+    const double C2 = c*c;
+    double* na = calloc(3*(size_t)n, sizeof(double));          /* Newtonian accelerations */
+    double* J = malloc(9*(size_t)n*sizeof(double));             /* Jacobi pos, vel, acc */
+    int warned = 0;
+    for (int64_t i = 0; i < A; i++) {
+        for (int64_t j = i + 1; j < n; j++) {
+            const double dx = x[i] - x[j], dy = y[i] - y[j], dz = z[i] - z[j];
+            const double r2 = dx*dx + dy*dy + dz*dz;
+            const double r = sqrt(r2);
+            const double prefac = G/(r2*r);
+            na[3*i] -= prefac*m[j]*dx; na[3*i+1] -= prefac*m[j]*dy; na[3*i+2] -= prefac*m[j]*dz;
+            na[3*j] += prefac*m[i]*dx; na[3*j+1] += prefac*m[i]*dy; na[3*j+2] += prefac*m[i]*dz;
+        }
+    }
+    const double mu = G*m[0];
+    /* inertial -> Jacobi (pos, vel, acc) */
+    double eta = m[0];
+    double s[9] = {eta*x[0], eta*y[0], eta*z[0], eta*vx[0], eta*vy[0], eta*vz[0], eta*na[0], eta*na[1], eta*na[2]};
+    for (int64_t i = 1; i < A; i++) {
+        const double ei = 1./eta;
+        const double pi[9] = {x[i], y[i], z[i], vx[i], vy[i], vz[i], na[3*i], na[3*i+1], na[3*i+2]};
+        eta += m[i];
+        const double pme = eta*ei;
+        for (int q = 0; q < 9; q++) { J[9*i+q] = pi[q] - s[q]*ei; }
+        for (int q = 0; q < 9; q++) { s[q] = s[q]*pme + m[i]*J[9*i+q]; }
+    }
+    const double Mtotal = eta, Mtotali = 1./Mtotal;
+    for (int64_t i = A; i < n; i++) {
+        const double pi[9] = {x[i], y[i], z[i], vx[i], vy[i], vz[i], na[3*i], na[3*i+1], na[3*i+2]};
+        for (int q = 0; q < 9; q++) J[9*i+q] = pi[q] - s[q]*Mtotali;
+    }
+    for (int q = 0; q < 9; q++) J[q] = s[q]*Mtotali;
+    /* 1PN term in Jacobi coordinates */
+    for (int64_t i = 1; i < n; i++) {
+        const double px = J[9*i], py = J[9*i+1], pz = J[9*i+2], pvx = J[9*i+3], pvy = J[9*i+4], pvz = J[9*i+5];
+        const double pax = J[9*i+6], pay = J[9*i+7], paz = J[9*i+8];
+        double vix = pvx, viy = pvy, viz = pvz;
+        double vi2 = vix*vix + viy*viy + viz*viz;
+        const double ri = sqrt(px*px + py*py + pz*pz);
+        int q = 0;
+        double Aa = (0.5*vi2 + 3.*mu/ri)/C2;
+        for (q = 0; q < max_iterations; q++) {
+            const double ox = vix, oy = viy, oz = viz;
+            vix = pvx/(1. - Aa); viy = pvy/(1. - Aa); viz = pvz/(1. - Aa);
+            vi2 = vix*vix + viy*viy + viz*viz;
+            Aa = (0.5*vi2 + 3.*mu/ri)/C2;
+            const double dvx = vix - ox, dvy = viy - oy, dvz = viz - oz;
+            if ((dvx*dvx + dvy*dvy + dvz*dvz)/vi2 < 2.220446049250313e-16*2.220446049250313e-16) break;
+        }
+        if (q == 10) warned = 1;
+        const double B = (mu/ri - 1.5*vi2)*mu/(ri*ri*ri)/C2;
+        const double rdotrdot = px*pvx + py*pvy + pz*pvz;
+        const double vdx = pax + B*px, vdy = pay + B*py, vdz = paz + B*pz;
+        const double vdotvdot = vix*vdx + viy*vdy + viz*vdz;
+        const double D = (vdotvdot - 3.*mu/(ri*ri*ri)*rdotrdot)/C2;
+        J[9*i+6] = B*(1. - Aa)*px - Aa*pax - D*vix;
+        J[9*i+7] = B*(1. - Aa)*py - Aa*pay - D*viy;
+        J[9*i+8] = B*(1. - Aa)*pz - Aa*paz - D*viz;
+    }
+    J[6] = J[7] = J[8] = 0.;
+    /* Jacobi -> inertial (acc) */
+    eta = Mtotal;
+    double sa[3] = {J[6]*eta, J[7]*eta, J[8]*eta};
+    {
+        const double ei = 1./eta;
+        for (int64_t i = A; i < n; i++) for (int q = 0; q < 3; q++) na[3*i+q] = J[9*i+6+q] + sa[q]*ei;
+    }
+    for (int64_t i = A - 1; i > 0; i--) {
+        const double ei = 1./eta;
+        for (int q = 0; q < 3; q++) { sa[q] = (sa[q] - m[i]*J[9*i+6+q])*ei; na[3*i+q] = J[9*i+6+q] + sa[q]; }
+        eta -= m[i];
+        for (int q = 0; q < 3; q++) sa[q] *= eta;
+    }
+    { const double mi = 1./eta; for (int q = 0; q < 3; q++) na[q] = sa[q]*mi; }
+    for (int64_t i = 0; i < n; i++) { ax[i] += na[3*i]; ay[i] += na[3*i+1]; az[i] += na[3*i+2]; }
+    free(na); free(J);
+    return warned;
+}

@@ -366,6 +366,7 @@ struct rebx_force* rebx_load_force(struct rebx_extras* const rebx, const char* n
         {"radiation_forces",        REBX_FORCE_VEL, rebx_radiation_forces},
         {"gravitational_harmonics", REBX_FORCE_POS, rebx_gravitational_harmonics},
         {"gr_potential",            REBX_FORCE_POS, rebx_gr_potential},
+        {"gr",                      REBX_FORCE_VEL, rebx_gr},
         {"yarkovsky_effect",        REBX_FORCE_VEL, rebx_yarkovsky_effect},
         {"modify_orbits_forces",    REBX_FORCE_VEL, rebx_modify_orbits_forces},
         {"gas_damping_timescale",   REBX_FORCE_VEL, rebx_gas_damping_timescale},

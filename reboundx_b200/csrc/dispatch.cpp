@@ -21,8 +21,11 @@
 #include <thread>
 
 #include "internal.h"
+#include "transformations.h"     // REBOUND's Jacobi transforms, as the reference's src/gr.c:61 includes them
 
 namespace rebxh {
+
+constexpr int KIND_GR = 100;     // host-orchestrated effect, not a rebx_b200_launch_pass kind
 
 // ---- small RAII helpers ------------------------------------------------------------------
 struct DevBuf {
@@ -98,8 +101,8 @@ struct DeviceContext {
     static constexpr int kBuffers = 3;      // chunks in flight: H2D of c+1 and D2H of c-1 overlap the sweep of c
     cudaStream_t stream[kBuffers] = {nullptr, nullptr, nullptr};
     cudaEvent_t bodies_ready = nullptr;
-    DevBuf aos[kBuffers], soa[kBuffers], work[kBuffers], bodies, br, scan, totals;
-    PinnedBuf bodies_h, br_h;
+    DevBuf aos[kBuffers], soa[kBuffers], work[kBuffers], bodies, br, scan, totals, grbuf;
+    PinnedBuf bodies_h, br_h, gr_h;
     std::unordered_map<struct rebx_force*, std::unique_ptr<ForceTables>> tables;
     void* registered_ptr = nullptr;
     size_t registered_bytes = 0;
@@ -135,6 +138,7 @@ static int kind_of(const struct rebx_force* f) {
     if (fn == rebx_modify_orbits_forces) return REBX_B200_MODIFY_ORBITS;
     if (fn == rebx_gas_damping_timescale) return REBX_B200_GAS_DAMPING;
     if (fn == rebx_modify_orbits_with_type_I_migration) return REBX_B200_TYPE_I;
+    if (fn == rebx_gr) return KIND_GR;
     return REBX_B200_NONE;
 }
 
@@ -363,7 +367,9 @@ struct Entry {
     ForceTables* T = nullptr;
     const Oblate* ob = nullptr;
     bool reduces = false;
-    int frame = 0;          // 0: body is a particle; 1: barycentre (second uniform sweep); 2: Jacobi (scan path)
+    int frame = 0;          // 0: body is a particle; 1: barycentre (second uniform sweep); 2: Jacobi (scan path); 3: gr
+    int n_active = 0;       // gr only
+    std::vector<struct reb_particle> gr_active;     // gr only: host result for the active bodies
 };
 
 static const double* get_d(struct rebx_force* f, const char* name) { return static_cast<const double*>(find_value(f->ap, name)); }
@@ -464,8 +470,80 @@ static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceCont
         out.push_back(e);
         return true;
     }
+    case KIND_GR: {
+        const double* c = get_d(force, "c");
+        if (!c) { reb_simulation_error(sim, "REBOUNDx Error: Need to set speed of light in gr effect.  See examples in documentation.\n"); return false; }
+        const size_t A = (sim->N_active == SIZE_MAX || sim->N_active > N) ? N : sim->N_active;
+        if (A < 1 || N < 2) return false;
+        if (A > REBX_B200_GR_MAX_ACTIVE) {
+            reb_simulation_error(sim, "REBOUNDx-B200 Error: the device implementation of 'gr' handles up to 8 active (massive) bodies plus any number of test particles; set sim->N_active. (With N_active unset the reference recomputes O(N^2) Newtonian gravity.)\n");
+            return false;
+        }
+        const int* it = static_cast<const int*>(find_value(force->ap, "max_iterations"));
+        e.scal[1] = (*c)*(*c);
+        e.scal[2] = it ? (double)*it : 10.0;
+        e.frame = 3; e.n_active = (int)A; e.body_index = 0;
+        out.push_back(e);
+        return true;
+    }
     default: return false;
     }
+}
+
+// Host part of `gr` for the active bodies (reference src/gr.c:79-160 restricted to i < N_active):
+// Newtonian accelerations among the actives minus the pull of the test particles (reduced on the
+// device), Jacobi transform, fixed-point + 1PN term for actives 1..A-1, transform back.  Fills
+// args.com (Jacobi origin of the test particles) and `act[i].a*` (what to add to the actives).
+static void gr_host_actives(const struct reb_particle* particles, int A, double G, double C2, int max_iterations,
+                            const double* pull, rebx_b200_gr_args& args, std::vector<struct reb_particle>& act, bool& not_converged) {
+    act.assign(particles, particles + A);
+    std::vector<struct reb_particle> pj(A);
+    for (int i = 0; i < A; i++) { act[i].ax = 0.; act[i].ay = 0.; act[i].az = 0.; }
+    for (int i = 0; i < A; i++) {
+        const struct reb_particle pi = act[i];
+        for (int j = i + 1; j < A; j++) {
+            const struct reb_particle pq = act[j];
+            const double dx = pi.x - pq.x, dy = pi.y - pq.y, dz = pi.z - pq.z;
+            const double r2 = dx*dx + dy*dy + dz*dz;
+            const double r = std::sqrt(r2);
+            const double prefac = G/(r2*r);
+            act[i].ax -= prefac*pq.m*dx; act[i].ay -= prefac*pq.m*dy; act[i].az -= prefac*pq.m*dz;
+            act[j].ax += prefac*pi.m*dx; act[j].ay += prefac*pi.m*dy; act[j].az += prefac*pi.m*dz;
+        }
+        act[i].ax -= pull[3*i + 0]; act[i].ay -= pull[3*i + 1]; act[i].az -= pull[3*i + 2];
+    }
+    const double mu = G*act[0].m;
+    reb_transformations_inertial_to_jacobi_posvelacc(act.data(), pj.data(), act.data(), A, A);
+    args.com[0] = pj[0].x;  args.com[1] = pj[0].y;  args.com[2] = pj[0].z;
+    args.com[3] = pj[0].vx; args.com[4] = pj[0].vy; args.com[5] = pj[0].vz;
+    args.com[6] = pj[0].ax; args.com[7] = pj[0].ay; args.com[8] = pj[0].az;
+    for (int i = 1; i < A; i++) {
+        const struct reb_particle p = pj[i];
+        double vix = p.vx, viy = p.vy, viz = p.vz;
+        double vi2 = vix*vix + viy*viy + viz*viz;
+        const double ri = std::sqrt(p.x*p.x + p.y*p.y + p.z*p.z);
+        int q = 0;
+        double Aa = (0.5*vi2 + 3.*mu/ri)/C2;
+        for (q = 0; q < max_iterations; q++) {
+            const double ox = vix, oy = viy, oz = viz;
+            vix = p.vx/(1. - Aa); viy = p.vy/(1. - Aa); viz = p.vz/(1. - Aa);
+            vi2 = vix*vix + viy*viy + viz*viz;
+            Aa = (0.5*vi2 + 3.*mu/ri)/C2;
+            const double dvx = vix - ox, dvy = viy - oy, dvz = viz - oz;
+            if ((dvx*dvx + dvy*dvy + dvz*dvz)/vi2 < 2.220446049250313e-16*2.220446049250313e-16) break;
+        }
+        if (q == 10) not_converged = true;
+        const double B = (mu/ri - 1.5*vi2)*mu/(ri*ri*ri)/C2;
+        const double rdotrdot = p.x*p.vx + p.y*p.vy + p.z*p.vz;
+        const double vdx = p.ax + B*p.x, vdy = p.ay + B*p.y, vdz = p.az + B*p.z;
+        const double vdotvdot = vix*vdx + viy*vdy + viz*vdz;
+        const double D = (vdotvdot - 3.*mu/(ri*ri*ri)*rdotrdot)/C2;
+        pj[i].ax = B*(1. - Aa)*p.x - Aa*p.ax - D*vix;
+        pj[i].ay = B*(1. - Aa)*p.y - Aa*p.ay - D*viy;
+        pj[i].az = B*(1. - Aa)*p.z - Aa*p.az - D*viz;
+    }
+    pj[0].ax = 0.; pj[0].ay = 0.; pj[0].az = 0.;
+    reb_transformations_jacobi_to_inertial_acc(act.data(), pj.data(), act.data(), A, A);
 }
 
 static void fill_body(double* rec, const Entry& e, const struct reb_particle* particles) {
@@ -519,7 +597,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
             case REBX_B200_RADIATION: need_vel = true; break;
             case REBX_B200_HARMONICS: case REBX_B200_GR_POTENTIAL: need_m = true; break;
             case REBX_B200_YARKOVSKY: need_vel = need_m = need_r = true; break;
-            default: need_vel = need_m = true; break;
+            default: need_vel = need_m = true; break;     // damping trio and gr
         }
     }
     const rebx_b200_aos_layout L = {(int32_t)sizeof(struct reb_particle), (int32_t)offsetof(struct reb_particle, x),
@@ -586,9 +664,34 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         for (size_t e0 = 0; e0 < ne;) {
             // consecutive entries sharing a reference-frame class form one launch group
             const int frame = entries[e0].frame;
-            const size_t cap = frame == 2 ? 3 : REBX_B200_MAX_EFFECTS;
+            const size_t cap = frame == 3 ? 1 : (frame == 2 ? 3 : REBX_B200_MAX_EFFECTS);
             size_t e1 = e0;
             while (e1 < ne && e1 - e0 < cap && entries[e1].frame == frame) e1++;
+            if (frame == 3) {
+                // `gr`: device reduction -> host part for the active bodies -> device sweep (see kernels_gr.cuh)
+                Entry& en = entries[e0];
+                rebx_b200_gr_args ga;
+                std::memset(&ga, 0, sizeof ga);
+                ga.n_active = en.n_active; ga.max_iterations = (int)en.scal[2];
+                ga.G = sim->G; ga.C2 = en.scal[1]; ga.mu = sim->G*particles[0].m;
+                for (int i = 0; i < en.n_active; i++) { ga.active[i][0] = particles[i].x; ga.active[i][1] = particles[i].y; ga.active[i][2] = particles[i].z; ga.active[i][3] = particles[i].m; }
+                REBXB_CUDA(ctx->grbuf.ensure(64*sizeof(double)), "allocating gr scratch");
+                REBXB_CUDA(ctx->gr_h.ensure(64*sizeof(double)), "allocating pinned gr scratch");
+                double* pull_d = static_cast<double*>(ctx->grbuf.p);
+                int* flag_d = reinterpret_cast<int*>(pull_d + 32);
+                double* pull_h = static_cast<double*>(ctx->gr_h.p);
+                REBXB_CUDA(cudaMemsetAsync(flag_d, 0, sizeof(int), s), "clearing the convergence flag");
+                REBXB_CUDA((cudaError_t)rebx_b200_gr_pull(&st, &ga, pull_d, ctx->work[b].p, s, &launches), "reducing the test particles' pull");
+                REBXB_CUDA(cudaMemcpyAsync(pull_h, pull_d, (size_t)en.n_active*3*sizeof(double), cudaMemcpyDeviceToHost, s), "copying the pull");
+                REBXB_CUDA(cudaStreamSynchronize(s), "waiting for the device");
+                bool host_nc = false;
+                gr_host_actives(particles, en.n_active, sim->G, ga.C2, ga.max_iterations, pull_h, ga, en.gr_active, host_nc);
+                REBXB_CUDA((cudaError_t)rebx_b200_gr_sweep(&st, &ga, flag_d, s, &launches), "launching the gr sweep");
+                REBXB_CUDA(cudaMemcpyAsync(pull_h + 32, flag_d, sizeof(int), cudaMemcpyDeviceToHost, s), "copying the convergence flag");
+                if (host_nc) *reinterpret_cast<int*>(pull_h + 40) = 1; else *reinterpret_cast<int*>(pull_h + 40) = 0;
+                e0 = e1;
+                continue;
+            }
             rebx_b200_pass P;
             std::memset(&P, 0, sizeof P);
             P.st = st;
@@ -634,6 +737,17 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     // Back-reaction onto the source / primary / oblate bodies (gr_potential.c:74-76,
     // gravitational_harmonics.c:221-223, rebxtools.c:139-141): chunk sums added in chunk order.
     for (size_t e = 0; e < ne; e++) {
+        if (entries[e].frame == 3) {                // gr: the active bodies were finished on the host
+            for (int i = 0; i < entries[e].n_active; i++) {
+                particles[i].ax += entries[e].gr_active[(size_t)i].ax;
+                particles[i].ay += entries[e].gr_active[(size_t)i].ay;
+                particles[i].az += entries[e].gr_active[(size_t)i].az;
+            }
+            const double* gh = static_cast<const double*>(ctx->gr_h.p);
+            if (*reinterpret_cast<const int*>(gh + 32) || *reinterpret_cast<const int*>(gh + 40))
+                reb_simulation_warning(sim, "REBOUNDx Warning: 10 iterations in gr.c failed to converge. This is typically because the perturbation is too strong for the current implementation.");
+            continue;
+        }
         if (!entries[e].reduces || entries[e].frame != 0) continue;    // COM frames were applied on the device
         double sx = 0.0, sy = 0.0, sz = 0.0;
         for (size_t c = 0; c < nchunks; c++) { sx += br_h[(c*ne + e)*3 + 0]; sy += br_h[(c*ne + e)*3 + 1]; sz += br_h[(c*ne + e)*3 + 2]; }
@@ -666,6 +780,7 @@ extern "C" {
 REBXB_ENTRY(rebx_radiation_forces)
 REBXB_ENTRY(rebx_gravitational_harmonics)
 REBXB_ENTRY(rebx_gr_potential)
+REBXB_ENTRY(rebx_gr)
 REBXB_ENTRY(rebx_yarkovsky_effect)
 REBXB_ENTRY(rebx_modify_orbits_forces)
 REBXB_ENTRY(rebx_gas_damping_timescale)

@@ -488,6 +488,7 @@ pack_acc_aos_kernel(unsigned char* __restrict__ aos, rebx_b200_aos_layout L,
 
 }  // namespace rebxb
 #include "kernels_jacobi.cuh"
+#include "kernels_gr.cuh"
 namespace rebxb {
 
 // ---- launch plumbing ----------------------------------------------------------------------
@@ -756,6 +757,32 @@ int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* str
     jacobi_apply_kernel<<<(unsigned)ntiles, kScanThreads, 0, s>>>(P.st, tvec, rows3);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) *launches += 5;
+    return err;
+}
+
+int rebx_b200_gr_pull(const rebx_b200_state* st, const rebx_b200_gr_args* args, double* pull, void* workspace, void* stream, int* launches) {
+    if (!st || !args || !pull || !workspace || !st->m) return cudaErrorInvalidValue;
+    if (args->n_active < 1 || args->n_active > REBX_B200_GR_MAX_ACTIVE) return cudaErrorInvalidValue;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (st->n == 0) return cudaMemsetAsync(pull, 0, (size_t)args->n_active*3*sizeof(double), s);
+    int grid = grid_for(reinterpret_cast<const void*>(gr_pull_kernel), st->n);
+    const int cap = kMaxBlocks*REBX_B200_MAX_EFFECTS/REBX_B200_GR_MAX_ACTIVE;      // workspace rows available
+    if (grid > cap) grid = cap;
+    gr_pull_kernel<<<grid, kThreads, 0, s>>>(*st, *args, static_cast<double*>(workspace));
+    gr_pull_finalize_kernel<<<1, kThreads, 0, s>>>(static_cast<const double*>(workspace), grid, args->n_active, pull);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) *launches += 2;
+    return err;
+}
+
+int rebx_b200_gr_sweep(const rebx_b200_state* st, const rebx_b200_gr_args* args, int* not_converged, void* stream, int* launches) {
+    if (!st || !args || !not_converged || !st->vx || !st->ax) return cudaErrorInvalidValue;
+    if (args->n_active < 1 || args->n_active > REBX_B200_GR_MAX_ACTIVE) return cudaErrorInvalidValue;
+    if (st->n == 0) return 0;
+    const int grid = grid_for(reinterpret_cast<const void*>(gr_sweep_kernel), st->n);
+    gr_sweep_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(*st, *args, not_converged);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) (*launches)++;
     return err;
 }
 

@@ -1,0 +1,130 @@
+// kernels_gr.cuh -- device part of the 1PN `gr` effect (reference src/gr.c:65-164), included by
+// kernels.cu.  The reference recomputes Newtonian accelerations from the N_active massive bodies,
+// moves to Jacobi coordinates, solves a per-particle fixed point for the Jacobi velocity
+// (:114-129), evaluates the post-Newtonian acceleration (:135-148) and transforms back.
+//
+// Split used here (N_active <= REBX_B200_GR_MAX_ACTIVE, the regime of a test-particle ensemble):
+//   gr_pull_kernel   sum over test particles j of G m_j (x_i - x_j)/r^3 for each active body i --
+//                    what the test particles contribute to the actives' Newtonian acceleration
+//                    (gr.c:79-96 with j >= N_active); exact zeros for massless test particles.
+//   host             the O(N_active^2) part for the active bodies, in the reference's order, and
+//                    the Jacobi origin (centre of mass of the actives: position, velocity,
+//                    Newtonian acceleration) for the test particles.
+//   gr_sweep_kernel  per test particle: Newtonian pull of the actives (ascending i like the
+//                    reference), Jacobi coordinates, fixed-point iteration, 1PN acceleration; a += .
+#pragma once
+
+namespace rebxb {
+
+__global__ void __launch_bounds__(kThreads)
+gr_pull_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_gr_args A, double* __restrict__ partials) {
+    __shared__ double s_red[kWarps][3];
+    double acc[REBX_B200_GR_MAX_ACTIVE][3];
+#pragma unroll
+    for (int i = 0; i < REBX_B200_GR_MAX_ACTIVE; i++) acc[i][0] = acc[i][1] = acc[i][2] = 0.0;
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < st.n; k += stride) {
+        if (st.index_base + k < A.n_active) continue;
+        const double mj = st.m[k];
+        if (mj == 0.0) continue;                    // contributes exact zeros
+        const double xj = st.x[k], yj = st.y[k], zj = st.z[k];
+#pragma unroll
+        for (int i = 0; i < REBX_B200_GR_MAX_ACTIVE; i++) {
+            if (i < A.n_active) {
+                const double dx = A.active[i][0] - xj, dy = A.active[i][1] - yj, dz = A.active[i][2] - zj;
+                const double r2 = dx*dx + dy*dy + dz*dz;
+                const double r = sqrt(r2);
+                const double prefac = A.G/(r2*r);
+                acc[i][0] += prefac*mj*dx; acc[i][1] += prefac*mj*dy; acc[i][2] += prefac*mj*dz;
+            }
+        }
+    }
+    for (int i = 0; i < A.n_active; i++) {
+        double v[3] = {acc[i][0], acc[i][1], acc[i][2]};
+#pragma unroll
+        for (int c = 0; c < 3; c++)
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) v[c] += __shfl_down_sync(0xffffffffu, v[c], off);
+        __syncthreads();
+        if ((threadIdx.x & 31) == 0) { s_red[threadIdx.x >> 5][0] = v[0]; s_red[threadIdx.x >> 5][1] = v[1]; s_red[threadIdx.x >> 5][2] = v[2]; }
+        __syncthreads();
+        if (threadIdx.x < 3) {
+            double s = 0.0;
+#pragma unroll
+            for (int w = 0; w < kWarps; w++) s += s_red[w][threadIdx.x];
+            partials[((size_t)blockIdx.x*REBX_B200_GR_MAX_ACTIVE + i)*3 + threadIdx.x] = s;
+        }
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+gr_pull_finalize_kernel(const double* __restrict__ partials, int nblocks, int n_active, double* __restrict__ pull) {
+    __shared__ double s[kThreads];
+    for (int q = 0; q < n_active*3; q++) {
+        double acc = 0.0;
+        for (int b = threadIdx.x; b < nblocks; b += kThreads) acc += partials[(size_t)b*REBX_B200_GR_MAX_ACTIVE*3 + q];
+        s[threadIdx.x] = acc;
+        __syncthreads();
+        for (int w = kThreads/2; w > 0; w >>= 1) {
+            if (threadIdx.x < w) s[threadIdx.x] += s[threadIdx.x + w];
+            __syncthreads();
+        }
+        if (threadIdx.x == 0) pull[q] = s[0];
+        __syncthreads();
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+gr_sweep_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_gr_args A, int* __restrict__ not_converged) {
+    const double C2 = A.C2, mu = A.mu;
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < st.n; k += stride) {
+        if (st.index_base + k < A.n_active) continue;           // actives are finished on the host
+        const double x = st.x[k], y = st.y[k], z = st.z[k];
+        // Newtonian acceleration from the active bodies (gr.c:79-96, role "j")
+        double nx = 0.0, ny = 0.0, nz = 0.0;
+        for (int i = 0; i < A.n_active; i++) {
+            const double dx = A.active[i][0] - x, dy = A.active[i][1] - y, dz = A.active[i][2] - z;
+            const double r2 = dx*dx + dy*dy + dz*dz;
+            const double r = sqrt(r2);
+            const double prefac = A.G/(r2*r);
+            nx += prefac*A.active[i][3]*dx; ny += prefac*A.active[i][3]*dy; nz += prefac*A.active[i][3]*dz;
+        }
+        // Jacobi coordinates of a test particle: relative to the centre of mass of the actives
+        const double px = x - A.com[0], py = y - A.com[1], pz = z - A.com[2];
+        const double pvx = st.vx[k] - A.com[3], pvy = st.vy[k] - A.com[4], pvz = st.vz[k] - A.com[5];
+        const double pax = nx - A.com[6], pay = ny - A.com[7], paz = nz - A.com[8];
+        // fixed point for the Jacobi velocity (gr.c:105-129)
+        double vix = pvx, viy = pvy, viz = pvz;
+        double vi2 = vix*vix + viy*viy + viz*viz;
+        const double ri = sqrt(px*px + py*py + pz*pz);
+        int q = 0;
+        double Aa = (0.5*vi2 + 3.*mu/ri)/C2;
+        for (q = 0; q < A.max_iterations; q++) {
+            const double ox = vix, oy = viy, oz = viz;
+            vix = pvx/(1. - Aa);
+            viy = pvy/(1. - Aa);
+            viz = pvz/(1. - Aa);
+            vi2 = vix*vix + viy*viy + viz*viz;
+            Aa = (0.5*vi2 + 3.*mu/ri)/C2;
+            const double dvx = vix - ox, dvy = viy - oy, dvz = viz - oz;
+            if ((dvx*dvx + dvy*dvy + dvz*dvz)/vi2 < 2.220446049250313e-16*2.220446049250313e-16) break;
+        }
+        if (q == 10) *not_converged = 1;                        // the reference compares with 10, not max_iterations (gr.c:130-133)
+        const double B = (mu/ri - 1.5*vi2)*mu/(ri*ri*ri)/C2;
+        const double rdotrdot = px*pvx + py*pvy + pz*pvz;
+        const double vdx = pax + B*px, vdy = pay + B*py, vdz = paz + B*pz;
+        const double vdotvdot = vix*vdx + viy*vdy + viz*vdz;
+        const double D = (vdotvdot - 3.*mu/(ri*ri*ri)*rdotrdot)/C2;
+        const double gx = B*(1. - Aa)*px - Aa*pax - D*vix;
+        const double gy = B*(1. - Aa)*py - Aa*pay - D*viy;
+        const double gz = B*(1. - Aa)*pz - Aa*paz - D*viz;
+        // back to inertial: a test particle's acceleration is its Jacobi acceleration plus s_a/eta with
+        // s_a = 0 (the Jacobi acceleration of the centre of mass is zeroed, gr.c:151-155)
+        st.ax[k] += gx + 0.0;
+        st.ay[k] += gy + 0.0;
+        st.az[k] += gz + 0.0;
+    }
+}
+
+}  // namespace rebxb

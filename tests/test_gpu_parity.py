@@ -347,3 +347,48 @@ def test_trajectories_other_configs_1000_steps(built, which):
     ours = _trajectory(w, None, 1000, "rk4", dt, 1, add, coords)
     ref = _trajectory(w, oracle.ref_lib(), 1000, "rk4", dt, 1, add, coords)
     _assert_trajectories_agree(ours, ref)
+
+
+@pytest.mark.parametrize("case", ["one_active_massive_asteroids", "three_active_massless", "stacked_with_yarkovsky"])
+def test_gr_1pn(built, case):
+    """`gr` (reference src/gr.c): device reduction + host part for the <= 8 active bodies + device sweep.
+    Massless test particles: bit-identical.  Massive ones change the order in which their pull on the
+    active bodies is summed, so the bar is the tolerance."""
+    from oracle import oracle
+    from reboundx_b200 import scenarios, workloads
+    w = workloads.asteroid_ensemble(20001)
+    forces, n_active = ["gr"], 1
+    if case == "three_active_massless":
+        w["m"][1], w["m"][2] = 1e-3, 3e-4
+        w["m"][3:] = 0.0
+        n_active = 3
+    elif case == "stacked_with_yarkovsky":
+        forces = ["yarkovsky_effect", "gr"]
+    acc0 = acc_variants(w, 11)["gravity"]
+    want, _ = oracle.port_apply(w, forces[::-1], acc0, n_active=n_active)
+    if oracle.have_ref():
+        ref = oracle.ref_apply(w, forces, acc0, n_active=n_active)
+        for k in range(3):
+            assert np.array_equal(np.array(ref[k]), want[k])
+    sim, rebx, _ = scenarios.build(w, forces, acc=acc0)
+    sim.N_active = n_active
+    sim.additional_forces()
+    sim.process_messages()
+    got = sim.acc()
+    rebx.detach(); sim.free()
+    e = errors(got, want)
+    if case == "three_active_massless":
+        assert e["bit_identical"], e
+    else:
+        assert e["max_normwise"] <= TOL, e
+        assert e["frac_component_above_tol"] <= 1e-4, e
+
+
+def test_gr_needs_n_active_for_large_ensembles(built):
+    from reboundx_b200 import scenarios, workloads
+    w = workloads.asteroid_ensemble(100)
+    sim, rebx, _ = scenarios.build(w, ["gr"])
+    sim.additional_forces()
+    with pytest.raises(RuntimeError, match="N_active"):
+        sim.process_messages()
+    rebx.detach(); sim.free()
