@@ -226,6 +226,28 @@ def run_ours(args):
         with open(prof) as f:
             roofline["traffic"] = json.load(f).get(args.workload)
 
+    # ---- resident stepping leg: full drift-kick-drift steps, no PCIe --------------
+    resident = None
+    if not args.no_e2e:
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        dt_step = 1e-3*2*np.pi*np.sqrt(float(np.hypot(w["x"][1], w["y"][1]))**3/(w["G"]*w["m"][0]))
+        for _ in range(3):
+            shard.leapfrog_step(dt_step, w["G"], group)
+        barrier()
+        l0 = shard.launches
+        s0.record()
+        for _ in range(args.steps):
+            shard.leapfrog_step(dt_step, w["G"], group)
+        s1.record()
+        barrier()
+        tr = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        ms_r = float(tr.item())/args.steps
+        resident = {"value": world*n*nf/(ms_r*1e-3), "unit": "evals/s", "ms_per_step": ms_r,
+                    "launches_per_step": (shard.launches - l0)//args.steps,
+                    "what": "device-resident drift-kick-drift step (drift, body refresh, central gravity, force sweep, kick, drift); state never leaves HBM"}
+
     # ---- end-to-end leg: the REBOUND-facing call on host particle arrays ---------------------------
     e2e = None
     if not args.no_e2e:
@@ -271,7 +293,7 @@ def run_ours(args):
                            "particles_per_gpu": n, "forces": add_order,
                            "l2": f"inputs larger than L2 ({shard_bytes(n, exec_order)/1e6:.0f} MB streamed per step)",
                            "sharding": "index ranges; body state broadcast per step (NCCL) when n_gpus > 1"},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "gpu_launches": gpu_launches,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "resident_step": resident, "gpu_launches": gpu_launches,
                 "clocks": clocks.summary()}
         print(json.dumps(line), flush=True)
     if world > 1:

@@ -159,6 +159,19 @@ int rebx_b200_gr_sweep(const rebx_b200_state* st, const rebx_b200_gr_args* args,
 /* Barycentric second sweep: a[k] += delta[0..2] for every particle in the shard. */
 int rebx_b200_add_uniform(const rebx_b200_state* st, const double* delta, void* stream, int* launches);
 
+/* ---- resident stepping around the path ----------------------------
+ * The callers either side of the force path, kept on the device so that a test-particle ensemble
+ * never crosses PCIe between force evaluations.  (The state struct's const pointers are written.) */
+/* x += dt v : reference rebx_drift_step, src/steppers.c:109-118 */
+int rebx_b200_drift(const rebx_b200_state* st, double dt, void* stream, int* launches);
+/* v += dt a : the update loop of reference rebx_kick_step, src/steppers.c:120-130 */
+int rebx_b200_kick(const rebx_b200_state* st, double dt, void* stream, int* launches);
+/* a = sum over `nbodies` body records (device) of -G m_b (r - r_b)/|r - r_b|^3 (overwrites a; the body
+ * whose index equals the particle's is skipped): what REBOUND's gravity gives a test particle. */
+int rebx_b200_point_mass_gravity(const rebx_b200_state* st, const double* bodies, int nbodies, double G, double softening, void* stream, int* launches);
+/* Refreshes pos/vel/mass of every body record whose particle index lies inside the shard. */
+int rebx_b200_gather_bodies(const rebx_b200_state* st, double* bodies, int nbodies, void* stream, int* launches);
+
 /* AoS <-> SoA staging for the host-facing path (device-side transposes of one chunk). */
 int rebx_b200_unpack_aos(const void* aos, const rebx_b200_aos_layout* layout, const rebx_b200_state* st_out_as_mutable,
                          void* stream, int* launches);

@@ -455,6 +455,50 @@ add_uniform_kernel(double* __restrict__ ax, double* __restrict__ ay, double* __r
     }
 }
 
+// ---- resident stepping (callers either side of the force path) ------------------------------------
+__global__ void __launch_bounds__(kThreads)
+drift_kernel(double* __restrict__ x, double* __restrict__ y, double* __restrict__ z,
+             const double* __restrict__ vx, const double* __restrict__ vy, const double* __restrict__ vz, int64_t n, double dt) {
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < n; k += stride) {
+        x[k] += dt*vx[k]; y[k] += dt*vy[k]; z[k] += dt*vz[k];
+    }
+}
+
+__global__ void __launch_bounds__(kThreads)
+gravity_kernel(rebx_b200_state st, const double* __restrict__ bodies, int nbodies, double G, double soft2) {
+    __shared__ double s_b[8][REBX_B200_BODY_DOUBLES];
+    for (int idx = threadIdx.x; idx < nbodies*REBX_B200_BODY_DOUBLES; idx += kThreads)
+        s_b[idx/REBX_B200_BODY_DOUBLES][idx % REBX_B200_BODY_DOUBLES] = bodies[idx];
+    __syncthreads();
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < st.n; k += stride) {
+        const double x = st.x[k], y = st.y[k], z = st.z[k];
+        double ax = 0.0, ay = 0.0, az = 0.0;
+        const long long gi = st.index_base + k;
+        for (int b = 0; b < nbodies; b++) {
+            const double mb = s_b[b][REBX_B200_BODY_M];
+            if ((long long)s_b[b][REBX_B200_BODY_INDEX] == gi || mb == 0.0) continue;
+            const double dx = x - s_b[b][REBX_B200_BODY_X+0], dy = y - s_b[b][REBX_B200_BODY_X+1], dz = z - s_b[b][REBX_B200_BODY_X+2];
+            const double r2 = dx*dx + dy*dy + dz*dz + soft2;
+            const double pref = -G*mb/(r2*sqrt(r2));
+            ax += pref*dx; ay += pref*dy; az += pref*dz;
+        }
+        st.ax[k] = ax; st.ay[k] = ay; st.az[k] = az;
+    }
+}
+
+__global__ void gather_bodies_kernel(rebx_b200_state st, double* __restrict__ bodies, int nbodies) {
+    const int b = threadIdx.x;
+    if (b >= nbodies) return;
+    double* rec = bodies + (size_t)b*REBX_B200_BODY_DOUBLES;
+    const long long k = (long long)rec[REBX_B200_BODY_INDEX] - st.index_base;
+    if (k < 0 || k >= st.n) return;
+    rec[REBX_B200_BODY_X+0] = st.x[k]; rec[REBX_B200_BODY_X+1] = st.y[k]; rec[REBX_B200_BODY_X+2] = st.z[k];
+    if (st.vx) { rec[REBX_B200_BODY_VX+0] = st.vx[k]; rec[REBX_B200_BODY_VX+1] = st.vy[k]; rec[REBX_B200_BODY_VX+2] = st.vz[k]; }
+    if (st.m) rec[REBX_B200_BODY_M] = st.m[k];
+}
+
 // ---- AoS <-> SoA staging (host-facing path; sits behind PCIe, so kept simple) ----------------
 __global__ void __launch_bounds__(kThreads)
 unpack_aos_kernel(const unsigned char* __restrict__ aos, rebx_b200_aos_layout L,
@@ -791,6 +835,46 @@ int rebx_b200_add_uniform(const rebx_b200_state* st, const double* delta, void* 
     if (st->n == 0) return 0;
     const int grid = grid_for(reinterpret_cast<const void*>(add_uniform_kernel), st->n);
     add_uniform_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(st->ax, st->ay, st->az, st->n, delta);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+int rebx_b200_drift(const rebx_b200_state* st, double dt, void* stream, int* launches) {
+    if (!st || !st->vx) return cudaErrorInvalidValue;
+    if (st->n == 0) return 0;
+    const int grid = grid_for(reinterpret_cast<const void*>(drift_kernel), st->n);
+    drift_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(
+        const_cast<double*>(st->x), const_cast<double*>(st->y), const_cast<double*>(st->z), st->vx, st->vy, st->vz, st->n, dt);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+int rebx_b200_kick(const rebx_b200_state* st, double dt, void* stream, int* launches) {
+    if (!st || !st->vx || !st->ax) return cudaErrorInvalidValue;
+    if (st->n == 0) return 0;
+    const int grid = grid_for(reinterpret_cast<const void*>(drift_kernel), st->n);
+    drift_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(          // same update, other arrays
+        const_cast<double*>(st->vx), const_cast<double*>(st->vy), const_cast<double*>(st->vz), st->ax, st->ay, st->az, st->n, dt);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+int rebx_b200_point_mass_gravity(const rebx_b200_state* st, const double* bodies, int nbodies, double G, double softening, void* stream, int* launches) {
+    if (!st || !bodies || nbodies < 0 || nbodies > 8 || !st->ax) return cudaErrorInvalidValue;
+    if (st->n == 0) return 0;
+    const int grid = grid_for(reinterpret_cast<const void*>(gravity_kernel), st->n);
+    gravity_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(*st, bodies, nbodies, G, softening*softening);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+int rebx_b200_gather_bodies(const rebx_b200_state* st, double* bodies, int nbodies, void* stream, int* launches) {
+    if (!st || !bodies || nbodies < 1 || nbodies > 32) return cudaErrorInvalidValue;
+    gather_bodies_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(*st, bodies, nbodies);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) (*launches)++;
     return err;

@@ -213,5 +213,54 @@ class Shard:
             k += self.apply_backreaction()
         return k
 
+    # ---- resident stepping around the path -------------------------------
+    def _stream(self, stream):
+        return self.torch.cuda.current_stream(self.device) if stream is None else stream
+
+    def _call(self, name, *args, stream=None):
+        n = c_int(0)
+        fn = getattr(self.lib, name)
+        fn.restype = c_int
+        rc = fn(ctypes.byref(self._pass.st), *args, c_void_p(self._stream(stream).cuda_stream), ctypes.byref(n))
+        self._check(rc, name)
+        self.launches += n.value
+        return n.value
+
+    def drift(self, dt, stream=None):
+        """x += dt v (reference rebx_drift_step, src/steppers.c:109-118)."""
+        return self._call("rebx_b200_drift", c_double(dt), stream=stream)
+
+    def kick(self, dt, stream=None):
+        """v += dt a (reference rebx_kick_step's update loop, src/steppers.c:120-130)."""
+        return self._call("rebx_b200_kick", c_double(dt), stream=stream)
+
+    def gravity(self, G, n_active=1, softening=0.0, stream=None):
+        """a = Newtonian pull of the first `n_active` body records (overwrites a)."""
+        return self._call("rebx_b200_point_mass_gravity", c_void_p(self.bodies.data_ptr()), c_int(n_active), c_double(G),
+                          c_double(softening), stream=stream)
+
+    def refresh_bodies(self, group=None, stream=None):
+        """Re-read the body records from the (moved) particles this shard owns, then broadcast."""
+        k = self._call("rebx_b200_gather_bodies", c_void_p(self.bodies.data_ptr()), c_int(len(self.kinds)), stream=stream)
+        self.sync_bodies(group)
+        return k
+
+    def leapfrog_step(self, dt, G, group=None):
+        """One drift-kick-drift step entirely on the device: the same scheme as the host harness
+        (rebound_shim.c: reb_shim_integrate scheme 0) with N_active = 1."""
+        k = self.drift(0.5*dt)
+        k += self.refresh_bodies(group)
+        k += self.gravity(G, 1)
+        k += self.launch()
+        if any(kind != 1 and kind != 4 for kind in self.kinds):
+            self.reduce_backreaction(group)
+            k += self.apply_backreaction()
+        k += self.kick(dt)
+        k += self.drift(0.5*dt)
+        return k
+
+    def posvel(self):
+        return [self.state[k].cpu().numpy() for k in ("x", "y", "z", "vx", "vy", "vz")]
+
     def acc(self):
         return [self.state[k].cpu().numpy() for k in ("ax", "ay", "az")]

@@ -392,3 +392,29 @@ def test_gr_needs_n_active_for_large_ensembles(built):
     with pytest.raises(RuntimeError, match="N_active"):
         sim.process_messages()
     rebx.detach(); sim.free()
+
+
+def test_resident_leapfrog_matches_host_harness_bitwise(built):
+    """drift/kick/gravity kept on the device around the force sweep.  1000
+    drift-kick-drift steps of a resident shard (no PCIe traffic) reproduce, bit for bit, the host
+    harness stepping the reference-compiled radiation force through sim->additional_forces."""
+    import os, sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import golden_io
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    w = workloads.debris_disk(1000, seed=3)
+    w["beta"] = np.full(1000, 0.1)
+    case = {"G": w["G"], "integrator": "whfast", "state": {k: w[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m", "r")}, "acc0": None,
+            "forces": [{"name": "radiation_forces", "params": {"c": w["c"]}}],
+            "particle_params": {"beta": (np.arange(1, 1001, dtype=np.int64), w["beta"])}}
+    ref = _trajectory(case, oracle.ref_lib(), 1000, "leapfrog", 1e8, 1)
+    sh = device.Shard(w, ["radiation_forces"], "cuda:0")
+    for _ in range(1000):
+        sh.leapfrog_step(1e8, w["G"])
+    torch.cuda.synchronize()
+    got = np.array(sh.posvel())
+    assert np.array_equal(got, ref)
