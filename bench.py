@@ -70,7 +70,7 @@ class ClockSampler:
 
     def __enter__(self):
         try:
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "100"],
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.index}", f"--query-gpu={self.Q}", "--format=csv,noheader,nounits", "-lms", "20"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             self.thread = threading.Thread(target=self._read, daemon=True)
             self.thread.start()
@@ -198,22 +198,21 @@ def run_ours(args):
             shard.evaluate(group)
         e1.record()
         barrier()
+        # ---- roofline of the dominant kernel (the fused sweep), timed alone per launch -----------
+        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        torch.cuda.synchronize()
+        k0.record()
+        for _ in range(args.steps):
+            shard.launch()
+        k1.record()
+        torch.cuda.synchronize()
     ms_total = e0.elapsed_time(e1)
-    gpu_launches = shard.launches - launches0
+    gpu_launches = shard.launches - launches0 - args.steps      # launches of the timed `value` region only
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_step = float(t.item())/args.steps
     value = world*n*nf/(ms_step*1e-3)
-
-    # ---- roofline of the dominant kernel (the fused sweep), timed alone per launch ---------------
-    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    torch.cuda.synchronize()
-    k0.record()
-    for _ in range(args.steps):
-        shard.launch()
-    k1.record()
-    torch.cuda.synchronize()
     kernel_ms = k0.elapsed_time(k1)/args.steps
     peak, peak_src = peaks()
     achieved = shard.algorithmic_bytes/(kernel_ms*1e-3)/1e9
