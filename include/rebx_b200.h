@@ -172,6 +172,15 @@ int rebx_b200_point_mass_gravity(const rebx_b200_state* st, const double* bodies
 /* Refreshes pos/vel/mass of every body record whose particle index lies inside the shard. */
 int rebx_b200_gather_bodies(const rebx_b200_state* st, double* bodies, int nbodies, void* stream, int* launches);
 
+/* One whole drift-kick-drift step (x += dt/2 v; a = pull of the stack's central body + stacked effects;
+ * v += dt a; x += dt/2 v) in ONE sweep: accelerations stay in registers, 96 B/particle + tables.
+ * All effects of the pass must refer to the same central body, whose record(s) and state the call
+ * also advances (single shard: the back-reaction sums are used as they come out of this shard).
+ * Same per-particle arithmetic as drift + gather_bodies + point_mass_gravity + launch_pass +
+ * apply_backreaction + kick + drift.  Returns cudaErrorNotSupported for a stack without a fused
+ * instantiation. */
+int rebx_b200_leapfrog_step(const rebx_b200_pass* pass, double dt, double G, double softening, void* workspace, void* stream, int* launches);
+
 /* AoS <-> SoA staging for the host-facing path (device-side transposes of one chunk). */
 int rebx_b200_unpack_aos(const void* aos, const rebx_b200_aos_layout* layout, const rebx_b200_state* st_out_as_mutable,
                          void* stream, int* launches);

@@ -218,6 +218,122 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
 }
 
 // ---------------------------------------------------------------------------------------------
+// step_kernel<V, K0..K3>: one whole drift-kick-drift step in ONE sweep.
+// Per particle:  x += dt/2 v;  a = pull of the central body + stacked effects;  v += dt a;
+// x += dt/2 v.  The acceleration lives in registers only, so a step moves 96 B/particle (+ tables)
+// instead of the ~370 B of the five separate sweeps (drift, gravity, force, kick, drift), with the
+// identical per-particle arithmetic (bit-identical trajectories, tests/test_gpu_parity.py).
+// Requires every effect of the stack to refer to the same central body; that body itself is skipped
+// here and advanced by step_body_kernel once the back-reaction sums are final.
+// ---------------------------------------------------------------------------------------------
+struct StepArgs { double dt, hdt, G, soft2; };
+
+template <int V, int K0, int K1, int K2, int K3>
+__global__ void __launch_bounds__(kThreads, min_blocks<K0, K1, K2, K3>())
+step_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ partials, const StepArgs S) {
+    constexpr bool MASS = Traits<K0>::mass || Traits<K1>::mass || Traits<K2>::mass || Traits<K3>::mass;
+    constexpr bool RAD  = Traits<K0>::rad  || Traits<K1>::rad  || Traits<K2>::rad  || Traits<K3>::rad;
+
+    __shared__ double s_body[REBX_B200_MAX_EFFECTS][REBX_B200_BODY_DOUBLES];
+    __shared__ double s_red[kWarps][3];
+    for (int idx = threadIdx.x; idx < P.n_effects*REBX_B200_BODY_DOUBLES; idx += kThreads) {
+        const int e = idx/REBX_B200_BODY_DOUBLES, j = idx - e*REBX_B200_BODY_DOUBLES;
+        s_body[e][j] = P.fx[e].body[j];
+    }
+    __syncthreads();
+    if (threadIdx.x < P.n_effects*3) {          // the body's own first half drift, same arithmetic as a particle's
+        const int e = threadIdx.x/3, c = threadIdx.x - e*3;
+        s_body[e][REBX_B200_BODY_X + c] += S.hdt*s_body[e][REBX_B200_BODY_VX + c];
+    }
+    __syncthreads();
+    const long long b0 = (long long)s_body[0][0];
+    const Pre pre0 = prepare<K0>(P.fx[0], s_body[0]);
+    const Pre pre1 = prepare<K1>(P.fx[1], s_body[1]);
+    const Pre pre2 = prepare<K2>(P.fx[2], s_body[2]);
+    const Pre pre3 = prepare<K3>(P.fx[3], s_body[3]);
+    Vec3 red0 = {0., 0., 0.}, red1 = {0., 0., 0.}, red2 = {0., 0., 0.}, red3 = {0., 0., 0.};
+    const double bmass = s_body[0][REBX_B200_BODY_M];
+
+    double* const X = const_cast<double*>(P.st.x);  double* const Y = const_cast<double*>(P.st.y);  double* const Z = const_cast<double*>(P.st.z);
+    double* const VX = const_cast<double*>(P.st.vx); double* const VY = const_cast<double*>(P.st.vy); double* const VZ = const_cast<double*>(P.st.vz);
+    const int64_t n = P.st.n;
+    const int64_t ntiles = (n + V - 1)/V;
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t t = (int64_t)blockIdx.x*kThreads + threadIdx.x; t < ntiles; t += stride) {
+        const int64_t k = t*V;
+        const bool full = (k + V <= n);
+        double x[V], y[V], z[V], vx[V], vy[V], vz[V], m[V], r[V];
+        ld<V>(P.st.x, k, full, x); ld<V>(P.st.y, k, full, y); ld<V>(P.st.z, k, full, z);
+        ld<V>(P.st.vx, k, full, vx); ld<V>(P.st.vy, k, full, vy); ld<V>(P.st.vz, k, full, vz);
+        if constexpr (MASS) { ld<V>(P.st.m, k, full, m); }
+        if constexpr (RAD)  { ld<V>(P.st.r, k, full, r); }
+        Params<K0, V> q0; Params<K1, V> q1; Params<K2, V> q2; Params<K3, V> q3;
+        load_params<K0, V>(P.fx[0], k, full, q0);
+        if constexpr (K1 != 0) load_params<K1, V>(P.fx[1], k, full, q1);
+        if constexpr (K2 != 0) load_params<K2, V>(P.fx[2], k, full, q2);
+        if constexpr (K3 != 0) load_params<K3, V>(P.fx[3], k, full, q3);
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            if (v > 0 && !full) break;
+            const long long gi = P.st.index_base + k + v;
+            if (gi == b0) continue;                                 // the central body: step_body_kernel
+            Particle p;
+            p.x = x[v] + S.hdt*vx[v]; p.y = y[v] + S.hdt*vy[v]; p.z = z[v] + S.hdt*vz[v];
+            p.vx = vx[v]; p.vy = vy[v]; p.vz = vz[v];
+            if constexpr (MASS) { p.m = m[v]; } else { p.m = 0.0; }
+            if constexpr (RAD)  { p.r = r[v]; } else { p.r = 0.0; }
+            Vec3 a = {0.0, 0.0, 0.0};
+            if (bmass != 0.0) {                                     // central gravity (gravity_kernel's arithmetic)
+                const double dx = p.x - s_body[0][REBX_B200_BODY_X+0], dy = p.y - s_body[0][REBX_B200_BODY_X+1], dz = p.z - s_body[0][REBX_B200_BODY_X+2];
+                const double r2 = dx*dx + dy*dy + dz*dz + S.soft2;
+                const double pref = -S.G*bmass/(r2*sqrt(r2));
+                a.x += pref*dx; a.y += pref*dy; a.z += pref*dz;
+            }
+            apply<K0, V>(P.fx[0], s_body[0], pre0, p, q0, v, a, red0);
+            if constexpr (K1 != 0) apply<K1, V>(P.fx[1], s_body[1], pre1, p, q1, v, a, red1);
+            if constexpr (K2 != 0) apply<K2, V>(P.fx[2], s_body[2], pre2, p, q2, v, a, red2);
+            if constexpr (K3 != 0) apply<K3, V>(P.fx[3], s_body[3], pre3, p, q3, v, a, red3);
+            vx[v] = p.vx + S.dt*a.x; vy[v] = p.vy + S.dt*a.y; vz[v] = p.vz + S.dt*a.z;
+            x[v] = p.x + S.hdt*vx[v]; y[v] = p.y + S.hdt*vy[v]; z[v] = p.z + S.hdt*vz[v];
+        }
+        st<V>(X, k, full, x); st<V>(Y, k, full, y); st<V>(Z, k, full, z);
+        st<V>(VX, k, full, vx); st<V>(VY, k, full, vy); st<V>(VZ, k, full, vz);
+    }
+    reduce_effect<K0>(red0, 0, s_red, partials);
+    reduce_effect<K1>(red1, 1, s_red, partials);
+    reduce_effect<K2>(red2, 2, s_red, partials);
+    reduce_effect<K3>(red3, 3, s_red, partials);
+}
+
+// The central body's own step (one thread): half drift, kick by the back-reaction sums of the stack
+// (in stack order, like apply_backreaction), half drift; then every body record is refreshed.
+__global__ void step_body_kernel(const __grid_constant__ rebx_b200_pass P, const StepArgs S, unsigned red_mask) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    double* rec0 = const_cast<double*>(P.fx[0].body);
+    const long long bi = (long long)rec0[REBX_B200_BODY_INDEX];
+    const long long k = bi - P.st.index_base;
+    double pos[3] = {rec0[REBX_B200_BODY_X+0], rec0[REBX_B200_BODY_X+1], rec0[REBX_B200_BODY_X+2]};
+    double vel[3] = {rec0[REBX_B200_BODY_VX+0], rec0[REBX_B200_BODY_VX+1], rec0[REBX_B200_BODY_VX+2]};
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int e = 0; e < P.n_effects; e++)
+        if (((red_mask >> e) & 1u) && P.fx[e].backreaction)
+            for (int c = 0; c < 3; c++) a[c] += P.fx[e].backreaction[c];
+    for (int c = 0; c < 3; c++) {
+        pos[c] += S.hdt*vel[c];
+        vel[c] += S.dt*a[c];
+        pos[c] += S.hdt*vel[c];
+    }
+    for (int e = 0; e < P.n_effects; e++) {
+        double* rec = const_cast<double*>(P.fx[e].body);
+        for (int c = 0; c < 3; c++) { rec[REBX_B200_BODY_X + c] = pos[c]; rec[REBX_B200_BODY_VX + c] = vel[c]; }
+    }
+    if (k >= 0 && k < P.st.n) {
+        const_cast<double*>(P.st.x)[k] = pos[0]; const_cast<double*>(P.st.y)[k] = pos[1]; const_cast<double*>(P.st.z)[k] = pos[2];
+        const_cast<double*>(P.st.vx)[k] = vel[0]; const_cast<double*>(P.st.vy)[k] = vel[1]; const_cast<double*>(P.st.vz)[k] = vel[2];
+    }
+}
+
+// ---------------------------------------------------------------------------------------------
 // pass_kernel_tma<K0..K3>: same sweep, but the particle state and parameter tables are moved
 // HBM -> shared memory by the TMA engine (cp.async.bulk, 1-D bulk copies completing on an
 // mbarrier) through a STAGES-deep ring per CTA.  One producer warp issues the copies; kTile
@@ -537,11 +653,13 @@ namespace rebxb {
 
 // ---- launch plumbing ----------------------------------------------------------------------
 typedef void (*pass_fn)(const rebx_b200_pass, double*);
-struct Combo { int k[4]; pass_fn fn[2]; bool red[4]; pass_fn tma; int tma_smem; };   // fn[0]: V=1, fn[1]: V=2
+typedef void (*step_fn)(const rebx_b200_pass, double*, const StepArgs);
+struct Combo { int k[4]; pass_fn fn[2]; bool red[4]; pass_fn tma; int tma_smem; step_fn step[2]; };   // fn[0]: V=1, fn[1]: V=2
 
 #define REBXB_COMBO(a, b, c, d) { {a, b, c, d}, { pass_kernel<1, a, b, c, d>, pass_kernel<2, a, b, c, d> }, \
                                   { Traits<a>::red, Traits<b>::red, Traits<c>::red, Traits<d>::red }, \
-                                  pass_kernel_tma<a, b, c, d>, TmaCfg<a, b, c, d>::smem_bytes },
+                                  pass_kernel_tma<a, b, c, d>, TmaCfg<a, b, c, d>::smem_bytes, \
+                                  { step_kernel<1, a, b, c, d>, step_kernel<2, a, b, c, d> } },
 static Combo kCombos[] = {
     // singles
     REBXB_COMBO(1,0,0,0) REBXB_COMBO(2,0,0,0) REBXB_COMBO(3,0,0,0) REBXB_COMBO(4,0,0,0)
@@ -837,6 +955,37 @@ int rebx_b200_add_uniform(const rebx_b200_state* st, const double* delta, void* 
     add_uniform_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(st->ax, st->ay, st->az, st->n, delta);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+int rebx_b200_leapfrog_step(const rebx_b200_pass* pass, double dt, double G, double softening, void* workspace, void* stream, int* launches) {
+    if (!pass || !workspace) return cudaErrorInvalidValue;
+    const int bad = check_pass(*pass);
+    if (bad) return bad;
+    const rebx_b200_pass& P = *pass;
+    if (!P.st.vx || !P.st.vy || !P.st.vz) return cudaErrorInvalidValue;
+    if (P.st.n == 0) return 0;
+    const Combo* combo = find_combo(P.fx, P.n_effects);
+    if (!combo) return cudaErrorNotSupported;            // stack not instantiated: use the separate sweeps
+    for (int e = 1; e < P.n_effects; e++) if (P.fx[e].body == nullptr) return cudaErrorInvalidValue;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    bool heavy = false;
+    for (int j = 0; j < P.n_effects; j++) if (P.fx[j].kind >= REBX_B200_YARKOVSKY) heavy = true;
+    const int vsel = (pass_is_vectorizable(P) && !heavy) ? 1 : 0;
+    const int V = vsel ? 2 : 1;
+    const StepArgs S = {dt, 0.5*dt, G, softening*softening};
+    step_fn fn = combo->step[vsel];
+    const int grid = grid_for(reinterpret_cast<const void*>(fn), (P.st.n + V - 1)/V);
+    fn<<<grid, kThreads, 0, s>>>(P, static_cast<double*>(workspace), S);
+    int nl = 1;
+    unsigned red_mask = 0;
+    bool any = false;
+    for (int j = 0; j < P.n_effects; j++) if (combo->red[j]) { red_mask |= 1u << j; if (P.fx[j].backreaction) any = true; }
+    if (any) { finalize_kernel<<<1, kThreads, 0, s>>>(P, static_cast<const double*>(workspace), grid, red_mask); nl++; }
+    step_body_kernel<<<1, 32, 0, s>>>(P, S, any ? red_mask : 0u);
+    nl++;
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) *launches += nl;
     return err;
 }
 

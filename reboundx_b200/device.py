@@ -259,6 +259,17 @@ class Shard:
         k += self.drift(0.5*dt)
         return k
 
+    def fused_leapfrog_step(self, dt, G, softening=0.0, stream=None):
+        """The same step as `leapfrog_step` in one sweep (rebx_b200_leapfrog_step): the acceleration
+        never touches HBM.  Single shard only."""
+        n = c_int(0)
+        self.lib.rebx_b200_leapfrog_step.restype = c_int
+        rc = self.lib.rebx_b200_leapfrog_step(ctypes.byref(self._pass), c_double(dt), c_double(G), c_double(softening),
+                                              c_void_p(self.workspace.data_ptr()), c_void_p(self._stream(stream).cuda_stream), ctypes.byref(n))
+        self._check(rc, "rebx_b200_leapfrog_step")
+        self.launches += n.value
+        return n.value
+
     def posvel(self):
         return [self.state[k].cpu().numpy() for k in ("x", "y", "z", "vx", "vy", "vz")]
 
