@@ -449,3 +449,89 @@ def test_fused_leapfrog_step_equals_separate_sweeps(built, which):
         # follow the grid, and the two kernels run different grids -> last-bit differences in the
         # body's kick.  Everything else is the same arithmetic.
         _assert_trajectories_agree(pa, pb, tol=1e-11)
+
+
+# ---- BASELINE.json full sizes: size-independent properties ---------------------------------------------
+def _subsample(w, idx, per_particle):
+    """Workload restricted to the central body + the particles `idx` (global indices >= 1)."""
+    sub = {}
+    for k, v in w.items():
+        if isinstance(v, np.ndarray) and v.shape[0] == w["x"].shape[0]:
+            sub[k] = np.concatenate([v[:1], v[idx]])
+        elif isinstance(v, np.ndarray) and k in per_particle:
+            sub[k] = v[idx - 1]
+        else:
+            sub[k] = v
+    return sub
+
+
+FULL = {
+    "debris_disk": (10_000_000, ["radiation_forces"], ["beta"]),
+    "circumplanetary_ring": (10_000_000, ["gravitational_harmonics", "gr_potential"], []),
+    "asteroid_ensemble": (1_000_000, ["yarkovsky_effect", "gr_potential"],
+                          ["ye_body_density", "ye_rotation_period", "ye_thermal_inertia", "ye_albedo", "ye_emissivity", "ye_k",
+                           "ye_spin_axis_x", "ye_spin_axis_y", "ye_spin_axis_z", "ye_flag"]),
+    "planetesimal_disk": (1_000_000, TRIO, ["tau_a", "tau_e", "tau_inc", "d_factor"]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL))
+def test_full_size_against_oracle_on_a_random_subsample(built, name):
+    """At the configuration's full size the oracle cannot be run on everything in seconds, but every
+    particle's force depends only on itself and the central body: the oracle evaluated on
+    (body + 50 000 random particles) must reproduce the full device result at those indices --
+    bit for bit where the arithmetic is + - * / sqrt, to the tolerance otherwise.  Massless
+    ensembles only (a massive ensemble couples through the back-reaction sum, tested at small N)."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    n, add, per_particle = FULL[name]
+    w = getattr(workloads, name)(n)
+    w["m"][1:] = 0.0 if name in ("debris_disk", "circumplanetary_ring") else w["m"][1:]
+    rng = np.random.default_rng(99)
+    acc0 = workloads.gravity_like_acc(w, rng)
+    sh = device.Shard(w, add[::-1], "cuda:0", acc0=acc0)
+    sh.launch()
+    torch.cuda.synchronize()
+    got = sh.acc()
+    idx = np.sort(rng.choice(np.arange(1, n + 1), size=50_000, replace=False))
+    sub = _subsample(w, idx, per_particle)
+    sub_acc0 = [np.concatenate([a[:1], a[idx]]) for a in acc0]
+    want, _ = oracle.port_apply(sub, add[::-1], sub_acc0)
+    g = [a[idx] for a in got]
+    ww = [a[1:] for a in want]
+    e = errors(g, ww)
+    if name in ("debris_disk", "circumplanetary_ring"):
+        assert e["bit_identical"], e
+    else:
+        assert e["max_normwise"] <= TOL, e
+        assert e["frac_component_above_tol"] <= 5e-3, e
+    assert all(np.isfinite(a).all() for a in got)
+
+
+def test_full_size_radiation_is_linear_in_beta_and_shard_independent(built):
+    """Config 2 at 10^7: doubling every beta doubles every force exactly (a power-of-two scaling
+    commutes with each rounding), and cutting the ensemble into three ragged shards changes no bit."""
+    import torch
+    from reboundx_b200 import device, workloads
+    n = 10_000_000
+    w = workloads.debris_disk(n)
+    one = device.Shard(w, ["radiation_forces"], "cuda:0")
+    one.launch()
+    w2 = dict(w); w2["beta"] = 2.0*w["beta"]
+    two = device.Shard(w2, ["radiation_forces"], "cuda:0")
+    two.launch()
+    torch.cuda.synchronize()
+    for k in ("ax", "ay", "az"):
+        assert torch.equal(two.state[k], 2.0*one.state[k])
+        assert bool(torch.any(one.state[k] != 0))
+    del two
+    cuts = [0, 3_333_333, 6_000_001, n + 1]
+    parts = []
+    for lo, hi in zip(cuts, cuts[1:]):
+        sh = device.Shard(w, ["radiation_forces"], "cuda:0", lo=lo, hi=hi)
+        sh.launch()
+        parts.append(sh)
+    torch.cuda.synchronize()
+    for k in ("ax", "ay", "az"):
+        assert torch.equal(torch.cat([p.state[k] for p in parts]), one.state[k])
