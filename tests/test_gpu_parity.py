@@ -535,3 +535,26 @@ def test_full_size_radiation_is_linear_in_beta_and_shard_independent(built):
     torch.cuda.synchronize()
     for k in ("ax", "ay", "az"):
         assert torch.equal(torch.cat([p.state[k] for p in parts]), one.state[k])
+
+
+def test_full_size_host_facing_call(built):
+    """The exact call bench.py's e2e leg times -- sim->additional_forces(sim) on 10^7 host AoS particles,
+    chunked three-buffer pipeline -- checked against the oracle on a random subsample, bit for bit."""
+    from oracle import oracle
+    from reboundx_b200 import scenarios, workloads
+    n = 10_000_000
+    w = workloads.debris_disk(n)
+    rng = np.random.default_rng(5)
+    acc0 = workloads.gravity_like_acc(w, rng)
+    sim, rebx, _ = scenarios.build(w, ["radiation_forces"], acc=acc0)
+    sim.additional_forces()
+    sim.process_messages()
+    got = sim.acc()
+    stats = rebx.stats()
+    rebx.detach(); sim.free()
+    assert stats["h2d_bytes"] >= n*128 and stats["d2h_bytes"] >= n*128 and stats["launches"] >= 3*(n >> 19)
+    idx = np.sort(rng.choice(np.arange(1, n + 1), size=50_000, replace=False))
+    sub = _subsample(w, idx, ["beta"])
+    want, _ = oracle.port_apply(sub, ["radiation_forces"], [np.concatenate([a[:1], a[idx]]) for a in acc0])
+    assert errors([a[idx] for a in got], [a[1:] for a in want])["bit_identical"]
+    assert all(got[k][0] == acc0[k][0] for k in range(3))          # the source itself feels nothing
