@@ -558,3 +558,52 @@ def test_full_size_host_facing_call(built):
     want, _ = oracle.port_apply(sub, ["radiation_forces"], [np.concatenate([a[:1], a[idx]]) for a in acc0])
     assert errors([a[idx] for a in got], [a[1:] for a in want])["bit_identical"]
     assert all(got[k][0] == acc0[k][0] for k in range(3))          # the source itself feels nothing
+
+
+def test_raw_pointer_writes_need_mark_dirty(built):
+    """A value changed through a pointer obtained from rebx_get_param and KEPT across evaluations is
+    invisible to the API's dirty tracking: rebx_mark_params_dirty (or REBX_B200_PARANOID=1) makes it
+    visible.  Obtaining the pointer again through the API marks the tables dirty by itself."""
+    import ctypes
+    from reboundx_b200 import scenarios, workloads
+    w = workloads.debris_disk(3000)
+    sim, rebx, _ = scenarios.build(w, ["radiation_forces"])
+    lib = rebx._lib
+    lib.rebx_get_param.restype = ctypes.POINTER(ctypes.c_double)
+    lib.rebx_get_param.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p]
+    ptr = lib.rebx_get_param(rebx._ptr, sim.particle(9).ap, b"beta")
+    sim.additional_forces(); sim.process_messages()
+    a1 = sim.acc()[0][9]
+    ptr[0] = 2.0*ptr[0]                      # raw write, no API call
+    sim.set_acc(); sim.additional_forces(); sim.process_messages()
+    assert sim.acc()[0][9] == a1             # stale table: documented behaviour
+    rebx.mark_params_dirty()
+    sim.set_acc(); sim.additional_forces(); sim.process_messages()
+    assert sim.acc()[0][9] == 2.0*a1
+    rebx.detach(); sim.free()
+
+
+def test_missing_parameters_report_like_the_reference(built):
+    """Error paths of the effects (reference tests/test_gr.py:17-21 and the effects' own checks)."""
+    from reboundx_b200 import scenarios, workloads
+    from reboundx_b200.host import Extras, Simulation
+    w = workloads.debris_disk(100)
+    for name, pattern in (("radiation_forces", "speed of light"), ("gr_potential", "speed of light"), ("gr", "speed of light")):
+        sim = Simulation(G=w["G"])
+        sim.set_particles(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["m"], w["r"])
+        sim.N_active = 1
+        rebx = Extras(sim)
+        rebx.add_force(rebx.load_force(name))
+        before = sim.acc()
+        sim.additional_forces()
+        with pytest.raises(RuntimeError, match=pattern):
+            sim.process_messages()
+        assert all(np.array_equal(a, b) for a, b in zip(before, sim.acc()))
+        rebx.detach(); sim.free()
+    w5 = workloads.planetesimal_disk(100)
+    sim, rebx, _ = scenarios.build(w5, ["modify_orbits_forces"], coordinates=None)
+    rebx.get_force("modify_orbits_forces").params["coordinates"] = 2          # PARTICLE, but nobody is 'primary'
+    sim.additional_forces()
+    with pytest.raises(RuntimeError, match="primary param was not found"):
+        sim.process_messages()
+    rebx.detach(); sim.free()
