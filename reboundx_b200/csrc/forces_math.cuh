@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cmath>
 #include "rebx_b200.h"
+#include "exact_math.cuh"
 
 namespace rebxb {
 
@@ -26,73 +27,40 @@ __device__ __forceinline__ bool is_absent(double v) {
 }
 
 // ---------------------------------------------------------------------------------------
-// Correctly rounded division with a SHARED reciprocal.
-//
-// An IEEE FP64 division costs ~16 DFMA issue slots on B200 (profiles/r01_fp64_probe.txt) and
-// the force expressions divide several numerators by the same divisor (|r|, r^2, c).  With
-// y = RN(1/b) obtained from ONE true division, each further quotient is
-//     q0 = RN(a y);  r0 = a - b q0 (exact, FMA);  q1 = RN(q0 + r0 y)      -> faithful
-//     r1 = a - b q1 (exact, FMA);                 q  = RN(q1 + r1 y)      -> RN(a/b)
-// The last step is Markstein's theorem (Markstein 1990; Muller et al., Handbook of
-// Floating-Point Arithmetic, "division with an FMA"): with y the correctly rounded reciprocal
-// and q1 faithful, the corrected quotient is the correctly rounded a/b, except when b's
-// significand is all ones -- that case, zeros, subnormals, infinities/NaNs and any exponent
-// outside +-400 (so nothing over/underflows on the way) take the ordinary division.  The
-// result is therefore bit-identical to `a/b`; 5 slots per quotient instead of ~16.
-//
-// MEASURED (B200, round 1): compiling with -DREBXB_SHARED_RECIP=1 halves the FP64 instruction
-// count of the J2/J4+gr_potential sweep (769 -> 395 static FP64 SASS instructions) and keeps every
-// bit-exactness test green, but does NOT shorten the sweep (0.2865 vs 0.2857 ms at 10^7): ncu shows
-// the FP64-heavy sweeps stall on the fixed latency of DEPENDENT operations (stall_wait dominates),
-// and the corrected quotient is as long a dependent chain as the hardware division sequence.  On
-// the radiation sweep the extra live values spill at the 64-register cap (0.207 vs 0.174 ms).
-// Hence off by default; kept as a compile-time option.
+// Arithmetic policies.  The light effects (radiation, J2/J4, gr_potential) are written once against
+// a policy M that supplies reciprocal / division / square root:
+//   IeeeMath  the hardware operators (each ends in a conditional slow-path call);
+//   FastMath  the straight-line, correctly rounded sequences of exact_math.cuh, which flag operands
+//             outside their domain in `bad` instead of branching.  Bit-identical results; the caller
+//             redoes a flagged particle with IeeeMath.
 // ---------------------------------------------------------------------------------------
-#ifndef REBXB_SHARED_RECIP
-#define REBXB_SHARED_RECIP 0
-#endif
-struct Recip { double b, y; bool ok; };
-
-__device__ __forceinline__ bool mid_exponent(double v) {
-    const int e = (__double2hiint(v) >> 20) & 0x7ff;
-    return e > 1023 - 400 && e < 1023 + 400;
-}
-
-__device__ __forceinline__ Recip make_recip(double b) {
-    Recip R;
-    R.b = b;
-    if (!REBXB_SHARED_RECIP) { R.y = 0.0; R.ok = false; return R; }
-    R.y = 1.0/b;
-    const unsigned long long mant = (unsigned long long)__double_as_longlong(b) & 0x000fffffffffffffULL;
-    R.ok = mid_exponent(b) && mant != 0x000fffffffffffffULL;
-    return R;
-}
-
-__device__ __noinline__ double div_slow(double a, double b) { return a/b; }
-
-__device__ __forceinline__ double div_by(double a, const Recip& R) {
-    if (!REBXB_SHARED_RECIP) return a/R.b;
-    if (R.ok && mid_exponent(a)) {
-        double q = a*R.y;
-        double r = fma(-R.b, q, a);
-        q = fma(r, R.y, q);
-        r = fma(-R.b, q, a);
-        return fma(r, R.y, q);
-    }
-    return div_slow(a, R.b);
-}
+struct IeeeMath {
+    static constexpr bool straight_line = false;
+    struct R { double b; };
+    static __device__ __forceinline__ R rcp(double b, unsigned&) { return R{b}; }
+    static __device__ __forceinline__ double div(double a, const R& r, unsigned&) { return a/r.b; }
+    static __device__ __forceinline__ double sqrt_(double x, unsigned&) { return sqrt(x); }
+};
+struct FastMath {
+    static constexpr bool straight_line = true;
+    using R = ExactRecip;
+    static __device__ __forceinline__ R rcp(double b, unsigned& bad) { return exact_rcp(b, bad); }
+    static __device__ __forceinline__ double div(double a, const R& r, unsigned& bad) { return exact_div(a, r, bad); }
+    static __device__ __forceinline__ double sqrt_(double x, unsigned& bad) { return exact_sqrt(x, bad); }
+};
 
 // Per-thread constants of one effect entry, computed once before the sweep loop (all of
 // them particle-independent sub-expressions of the reference formulas, same association).
-struct Pre { Recip rc; double k0, k1; };
+struct Pre { ExactRecip rc; unsigned rc_bad; double c, k0, k1; };
 
 template <int K>
 __device__ __forceinline__ Pre prepare(const rebx_b200_effect& fx, const double* __restrict__ body) {
     Pre pre;
-    pre.rc.b = 1.0; pre.rc.y = 1.0; pre.rc.ok = false; pre.k0 = 0.0; pre.k1 = 0.0;
+    pre.rc.b = 1.0; pre.rc.y = 1.0; pre.rc_bad = 0u; pre.c = 1.0; pre.k0 = 0.0; pre.k1 = 0.0;
     const double bm = body[REBX_B200_BODY_M];
     if constexpr (K == REBX_B200_RADIATION) {
-        pre.rc = make_recip(fx.scal[1]);                 // 1/c
+        pre.c = fx.scal[1];
+        pre.rc = exact_rcp(pre.c, pre.rc_bad);           // RN(1/c), shared by the four divisions by c
         pre.k0 = fx.scal[0]*bm;                          // mu = G*m_source           (radiation_forces.c:71)
     } else if constexpr (K == REBX_B200_HARMONICS) {
         const double G = fx.scal[0], J2 = body[REBX_B200_BODY_J2], J4 = body[REBX_B200_BODY_J4], Req = body[REBX_B200_BODY_REQ];
@@ -102,7 +70,7 @@ __device__ __forceinline__ Pre prepare(const rebx_b200_effect& fx, const double*
         const double Gm = fx.scal[0]*bm;
         pre.k0 = 6.*Gm*Gm/fx.scal[1];                    // prefac1                    (gr_potential.c:62)
     } else if constexpr (K == REBX_B200_YARKOVSKY) {
-        pre.rc = make_recip(fx.scal[2]);                 // 1/ye_c
+        pre.c = fx.scal[2];
     }
     return pre;
 }
@@ -181,30 +149,46 @@ __device__ __forceinline__ double planet_trap(double r, double dedge, double hed
 // `gi` is the particle's global index, `k` its index inside the shard's tables.
 // ---------------------------------------------------------------------------------------
 
+// Division by the speed of light: FastMath reuses the per-thread reciprocal of c.
+template <class M> __device__ __forceinline__ double div_c(double a, const Pre& pre, unsigned& bad);
+template <> __device__ __forceinline__ double div_c<IeeeMath>(double a, const Pre& pre, unsigned&) { return a/pre.c; }
+template <> __device__ __forceinline__ double div_c<FastMath>(double a, const Pre& pre, unsigned& bad) { bad |= pre.rc_bad; return exact_div(a, pre.rc, bad); }
+
 // src/radiation_forces.c:69-98
+template <class M>
 __device__ __forceinline__ void radiation(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
-                                          const Particle& p, double beta, Vec3& a) {
-    if (is_absent(beta)) return;
+                                          const Particle& p, double beta, Vec3& a, unsigned& bad) {
+    const bool absent = is_absent(beta);
+    if constexpr (M::straight_line) beta = absent ? 0.0 : beta;     // keep the marker NaN out of the arithmetic; result discarded below
+    else if (absent) return;                                        // a particle without beta feels nothing (radiation_forces.c:78)
     const double mu = pre.k0;
     const double dx = p.x - body[REBX_B200_BODY_X+0];
     const double dy = p.y - body[REBX_B200_BODY_X+1];
     const double dz = p.z - body[REBX_B200_BODY_X+2];
-    const double dr = sqrt(dx*dx + dy*dy + dz*dz);
-    const Recip rdr = make_recip(dr);
+    const double dr = M::sqrt_(dx*dx + dy*dy + dz*dz, bad);
+    const typename M::R rdr = M::rcp(dr, bad);
     const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
     const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
     const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
-    const double rdot = div_by(dx*dvx + dy*dvy + dz*dvz, rdr);
-    const double a_rad = beta*mu/(dr*dr);
-    const double k1 = 1. - div_by(rdot, pre.rc);
-    a.x += a_rad*(div_by(k1*dx, rdr) - div_by(dvx, pre.rc));
-    a.y += a_rad*(div_by(k1*dy, rdr) - div_by(dvy, pre.rc));
-    a.z += a_rad*(div_by(k1*dz, rdr) - div_by(dvz, pre.rc));
+    const double rdot = M::div(dx*dvx + dy*dvy + dz*dvz, rdr, bad);
+    const double a_rad = M::div(beta*mu, M::rcp(dr*dr, bad), bad);
+    const double k1 = 1. - div_c<M>(rdot, pre, bad);
+    const double fx_ = a_rad*(M::div(k1*dx, rdr, bad) - div_c<M>(dvx, pre, bad));
+    const double fy_ = a_rad*(M::div(k1*dy, rdr, bad) - div_c<M>(dvy, pre, bad));
+    const double fz_ = a_rad*(M::div(k1*dz, rdr, bad) - div_c<M>(dvz, pre, bad));
+    if constexpr (M::straight_line) {       // select instead of branching
+        a.x = absent ? a.x : a.x + fx_;
+        a.y = absent ? a.y : a.y + fy_;
+        a.z = absent ? a.z : a.z + fz_;
+    } else {
+        a.x += fx_;  a.y += fy_;  a.z += fz_;
+    }
 }
 
 // src/gravitational_harmonics.c:184-224 with j2_func :72-86 and j4_func :88-102
+template <class M>
 __device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
-                                          const Particle& p, Vec3& a, Vec3& red) {
+                                          const Particle& p, Vec3& a, Vec3& red, unsigned& bad) {
     const double bm  = body[REBX_B200_BODY_M];
     const double J4  = body[REBX_B200_BODY_J4];
     const double ux = body[REBX_B200_BODY_U+0], uy = body[REBX_B200_BODY_U+1], uz = body[REBX_B200_BODY_U+2];
@@ -215,25 +199,25 @@ __device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const doub
     const double dy = p.y - body[REBX_B200_BODY_X+1];
     const double dz = p.z - body[REBX_B200_BODY_X+2];
     const double r2 = dx*dx + dy*dy + dz*dz;
-    const double r  = sqrt(r2);
-    const Recip rr2 = make_recip(r2), rr = make_recip(r);
+    const double r  = M::sqrt_(r2, bad);
+    const typename M::R rr2 = M::rcp(r2, bad), rr = M::rcp(r, bad);
     const double du = ux*dx + uy*dy + uz*dz;
     const double dv = vx*dx + vy*dy + vz*dz;
     const double dw = wx*dx + wy*dy + wz*dz;
-    const double costheta  = div_by(dw, rr);
+    const double costheta  = M::div(dw, rr, bad);
     const double costheta2 = costheta*costheta;
 
     double au = 0.0, av = 0.0, aw = 0.0;
     {   // J2 != 0 is guaranteed by the table builder (body skipped otherwise)
-        const double f1 = div_by(div_by(div_by(pre.k0, rr2), rr2), rr);      // 3/2 G m J2 R^2 /r2/r2/r
+        const double f1 = M::div(M::div(M::div(pre.k0, rr2, bad), rr2, bad), rr, bad);      // 3/2 G m J2 R^2 /r2/r2/r
         const double f2 = 5.0*costheta2 - 1.0;
         const double f3 = f2 - 2.0;
         au += f1*f2*du;
         av += f1*f2*dv;
         aw += f1*f3*dw;
     }
-    if (J4 != 0.0) {
-        const double f1 = div_by(div_by(div_by(div_by(pre.k1, rr2), rr2), rr2), rr);   // 5/8 G m J4 R^4 /r2/r2/r2/r
+    if (J4 != 0.0) {    // same for every thread of the launch (a property of the oblate body)
+        const double f1 = M::div(M::div(M::div(M::div(pre.k1, rr2, bad), rr2, bad), rr2, bad), rr, bad);   // 5/8 G m J4 R^4 /r2/r2/r2/r
         const double f2 = 63.0*costheta2*costheta2 - 42.0*costheta2 + 3.0;
         const double f3 = f2 - 28.0*costheta2 + 12.0;
         au += f1*f2*du;
@@ -249,14 +233,15 @@ __device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const doub
 }
 
 // src/gr_potential.c:60-78
+template <class M>
 __device__ __forceinline__ void gr_potential(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
-                                             const Particle& p, Vec3& a, Vec3& red) {
+                                             const Particle& p, Vec3& a, Vec3& red, unsigned& bad) {
     const double prefac1 = pre.k0;
     const double dx = p.x - body[REBX_B200_BODY_X+0];
     const double dy = p.y - body[REBX_B200_BODY_X+1];
     const double dz = p.z - body[REBX_B200_BODY_X+2];
     const double r2 = dx*dx + dy*dy + dz*dz;
-    const double prefac = prefac1/(r2*r2);
+    const double prefac = M::div(prefac1, M::rcp(r2*r2, bad), bad);
     a.x -= prefac*dx;  a.y -= prefac*dy;  a.z -= prefac*dz;
     const double mr = mass_ratio(p.m, body[REBX_B200_BODY_M]);
     red.x += mr*prefac*dx;  red.y += mr*prefac*dy;  red.z += mr*prefac*dz;
@@ -280,11 +265,10 @@ __device__ __forceinline__ void yarkovsky(const rebx_b200_effect& fx, const doub
     const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
     const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
     const double distance = sqrt((dx*dx) + (dy*dy) + (dz*dz));
-    const Recip rd = make_recip(distance);
     const double rdotv = ((dx*dvx) + (dy*dvy) + (dz*dvz))/(c*distance);
-    const double i0 = ((1 - rdotv)*div_by(dx, rd)) - div_by(dvx, pre.rc);
-    const double i1 = ((1 - rdotv)*div_by(dy, rd)) - div_by(dvy, pre.rc);
-    const double i2 = ((1 - rdotv)*div_by(dz, rd)) - div_by(dvz, pre.rc);
+    const double i0 = ((1 - rdotv)*(dx/distance)) - (dvx/c);
+    const double i1 = ((1 - rdotv)*(dy/distance)) - (dvy/c);
+    const double i2 = ((1 - rdotv)*(dz/distance)) - (dvz/c);
 
     double mag;
     double Y[3][3] = {{0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}, {0.0, 0.0, 0.0}};

@@ -27,6 +27,9 @@
 
 namespace rebxb {
 
+#ifndef REBXB_FASTMATH
+#define REBXB_FASTMATH 0
+#endif
 #ifndef REBXB_HEAVY_MINBLOCKS
 #define REBXB_HEAVY_MINBLOCKS 2
 #endif
@@ -93,15 +96,15 @@ __device__ __forceinline__ void load_params(const rebx_b200_effect& fx, int64_t 
     if constexpr (Traits<K>::itab) ldi<V>(fx.itab, k, full, q.it);
 }
 
-template <int K, int V>
+template <int K, int V, class M = IeeeMath>
 __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
-                                      const Particle& p, const Params<K, V>& q, int v, Vec3& a, Vec3& red) {
+                                      const Particle& p, const Params<K, V>& q, int v, Vec3& a, Vec3& red, unsigned& bad) {
     if constexpr (K == REBX_B200_RADIATION) {
-        radiation(fx, body, pre, p, q.t[0][v], a);
+        radiation<M>(fx, body, pre, p, q.t[0][v], a, bad);
     } else if constexpr (K == REBX_B200_HARMONICS) {
-        harmonics(fx, body, pre, p, a, red);
+        harmonics<M>(fx, body, pre, p, a, red, bad);
     } else if constexpr (K == REBX_B200_GR_POTENTIAL) {
-        gr_potential(fx, body, pre, p, a, red);
+        gr_potential<M>(fx, body, pre, p, a, red, bad);
     } else if constexpr (K == REBX_B200_YARKOVSKY) {
         YarkParams yp{q.t[0][v], q.t[1][v], q.t[2][v], q.t[3][v], q.t[4][v], q.t[5][v], q.t[6][v], q.t[7][v], q.t[8][v]};
         yarkovsky(fx, body, pre, p, yp, q.it[v], a);
@@ -193,21 +196,63 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
         if constexpr (K1 != 0) load_params<K1, V>(P.fx[1], k, full, q1);
         if constexpr (K2 != 0) load_params<K2, V>(P.fx[2], k, full, q2);
         if constexpr (K3 != 0) load_params<K3, V>(P.fx[3], k, full, q3);
-#pragma unroll
-        for (int v = 0; v < V; v++) {
-            if (v > 0 && !full) break;
+        auto particle = [&](int v) {
             Particle p;
             p.x = x[v]; p.y = y[v]; p.z = z[v];
             if constexpr (VEL)  { p.vx = vx[v]; p.vy = vy[v]; p.vz = vz[v]; } else { p.vx = p.vy = p.vz = 0.0; }
             if constexpr (MASS) { p.m = m[v]; } else { p.m = 0.0; }
             if constexpr (RAD)  { p.r = r[v]; } else { p.r = 0.0; }
+            return p;
+        };
+        // reference semantics with the hardware operators: branches around the body itself
+        auto exact_one = [&](int v) {
+            const Particle p = particle(v);
             Vec3 a = {ax[v], ay[v], az[v]};
+            unsigned unused = 0;
             const long long gi = P.st.index_base + k + v;
-            if (gi != b0) apply<K0, V>(P.fx[0], s_body[0], pre0, p, q0, v, a, red0);
-            if constexpr (K1 != 0) { if (gi != b1) apply<K1, V>(P.fx[1], s_body[1], pre1, p, q1, v, a, red1); }
-            if constexpr (K2 != 0) { if (gi != b2) apply<K2, V>(P.fx[2], s_body[2], pre2, p, q2, v, a, red2); }
-            if constexpr (K3 != 0) { if (gi != b3) apply<K3, V>(P.fx[3], s_body[3], pre3, p, q3, v, a, red3); }
+            if (gi != b0) apply<K0, V>(P.fx[0], s_body[0], pre0, p, q0, v, a, red0, unused);
+            if constexpr (K1 != 0) { if (gi != b1) apply<K1, V>(P.fx[1], s_body[1], pre1, p, q1, v, a, red1, unused); }
+            if constexpr (K2 != 0) { if (gi != b2) apply<K2, V>(P.fx[2], s_body[2], pre2, p, q2, v, a, red2, unused); }
+            if constexpr (K3 != 0) { if (gi != b3) apply<K3, V>(P.fx[3], s_body[3], pre3, p, q3, v, a, red3, unused); }
             ax[v] = a.x; ay[v] = a.y; az[v] = a.z;
+        };
+        // MEASURED (B200, round 1): the straight-line FastMath pass keeps every bit-exactness test green
+        // but does not pay: J2/J4+gr_potential 0.2875 ms (hardware operators: 0.2857 ms), radiation
+        // 0.197 ms vs 0.172 ms (the extra live values spill at the 64-register cap).  The FP64-heavy
+        // sweeps are bound by registers -> warps x ILP, not by basic-block boundaries.  Compile with
+        // -DREBXB_FASTMATH=1 to enable it; off by default.
+        constexpr bool FAST = REBXB_FASTMATH && K0 <= REBX_B200_GR_POTENTIAL && K1 <= REBX_B200_GR_POTENTIAL &&
+                              K2 <= REBX_B200_GR_POTENTIAL && K3 <= REBX_B200_GR_POTENTIAL;
+        if constexpr (FAST) {
+            // Straight-line pass over the thread's V particles (one basic block, so their dependent
+            // FP64 chains interleave); operands outside FastMath's domain, the body itself and a
+            // ragged tail are flagged and redone below with the hardware operators.
+            unsigned bad = full ? 0u : 1u;
+            const Vec3 s0 = red0, s1 = red1, s2 = red2, s3 = red3;
+            Vec3 an[V];
+#pragma unroll
+            for (int v = 0; v < V; v++) {
+                const Particle p = particle(v);
+                Vec3 a = {ax[v], ay[v], az[v]};
+                const long long gi = P.st.index_base + k + v;
+                bad |= (gi == b0 || gi == b1 || gi == b2 || gi == b3) ? 1u : 0u;
+                apply<K0, V, FastMath>(P.fx[0], s_body[0], pre0, p, q0, v, a, red0, bad);
+                if constexpr (K1 != 0) apply<K1, V, FastMath>(P.fx[1], s_body[1], pre1, p, q1, v, a, red1, bad);
+                if constexpr (K2 != 0) apply<K2, V, FastMath>(P.fx[2], s_body[2], pre2, p, q2, v, a, red2, bad);
+                if constexpr (K3 != 0) apply<K3, V, FastMath>(P.fx[3], s_body[3], pre3, p, q3, v, a, red3, bad);
+                an[v] = a;
+            }
+            if (bad) {
+                red0 = s0; red1 = s1; red2 = s2; red3 = s3;
+#pragma unroll
+                for (int v = 0; v < V; v++) { if (v > 0 && !full) break; exact_one(v); }
+            } else {
+#pragma unroll
+                for (int v = 0; v < V; v++) { ax[v] = an[v].x; ay[v] = an[v].y; az[v] = an[v].z; }
+            }
+        } else {
+#pragma unroll
+            for (int v = 0; v < V; v++) { if (v > 0 && !full) break; exact_one(v); }
         }
         st<V>(P.st.ax, k, full, ax); st<V>(P.st.ay, k, full, ay); st<V>(P.st.az, k, full, az);
     }
@@ -289,10 +334,11 @@ step_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
                 const double pref = -S.G*bmass/(r2*sqrt(r2));
                 a.x += pref*dx; a.y += pref*dy; a.z += pref*dz;
             }
-            apply<K0, V>(P.fx[0], s_body[0], pre0, p, q0, v, a, red0);
-            if constexpr (K1 != 0) apply<K1, V>(P.fx[1], s_body[1], pre1, p, q1, v, a, red1);
-            if constexpr (K2 != 0) apply<K2, V>(P.fx[2], s_body[2], pre2, p, q2, v, a, red2);
-            if constexpr (K3 != 0) apply<K3, V>(P.fx[3], s_body[3], pre3, p, q3, v, a, red3);
+            unsigned unused = 0;
+            apply<K0, V>(P.fx[0], s_body[0], pre0, p, q0, v, a, red0, unused);
+            if constexpr (K1 != 0) apply<K1, V>(P.fx[1], s_body[1], pre1, p, q1, v, a, red1, unused);
+            if constexpr (K2 != 0) apply<K2, V>(P.fx[2], s_body[2], pre2, p, q2, v, a, red2, unused);
+            if constexpr (K3 != 0) apply<K3, V>(P.fx[3], s_body[3], pre3, p, q3, v, a, red3, unused);
             vx[v] = p.vx + S.dt*a.x; vy[v] = p.vy + S.dt*a.y; vz[v] = p.vz + S.dt*a.z;
             x[v] = p.x + S.hdt*vx[v]; y[v] = p.y + S.hdt*vy[v]; z[v] = p.z + S.hdt*vz[v];
         }
@@ -472,10 +518,11 @@ pass_kernel_tma(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
         const Pre pre3 = prepare<K3>(P.fx[3], s_body[3]);
         auto one = [&](const Particle& p, Vec3& a, long long gi, const Params<K0, 1>& q0, const Params<K1, 1>& q1,
                        const Params<K2, 1>& q2, const Params<K3, 1>& q3) {
-            if (gi != b0) apply<K0, 1>(P.fx[0], s_body[0], pre0, p, q0, 0, a, red0);
-            if constexpr (K1 != 0) { if (gi != b1) apply<K1, 1>(P.fx[1], s_body[1], pre1, p, q1, 0, a, red1); }
-            if constexpr (K2 != 0) { if (gi != b2) apply<K2, 1>(P.fx[2], s_body[2], pre2, p, q2, 0, a, red2); }
-            if constexpr (K3 != 0) { if (gi != b3) apply<K3, 1>(P.fx[3], s_body[3], pre3, p, q3, 0, a, red3); }
+            unsigned unused = 0;
+            if (gi != b0) apply<K0, 1>(P.fx[0], s_body[0], pre0, p, q0, 0, a, red0, unused);
+            if constexpr (K1 != 0) { if (gi != b1) apply<K1, 1>(P.fx[1], s_body[1], pre1, p, q1, 0, a, red1, unused); }
+            if constexpr (K2 != 0) { if (gi != b2) apply<K2, 1>(P.fx[2], s_body[2], pre2, p, q2, 0, a, red2, unused); }
+            if constexpr (K3 != 0) { if (gi != b3) apply<K3, 1>(P.fx[3], s_body[3], pre3, p, q3, 0, a, red3, unused); }
         };
         int it = 0;
         for (int64_t tile = blockIdx.x; tile < nfull; tile += gridDim.x, it++) {
