@@ -607,3 +607,62 @@ def test_missing_parameters_report_like_the_reference(built):
     with pytest.raises(RuntimeError, match="primary param was not found"):
         sim.process_messages()
     rebx.detach(); sim.free()
+
+
+@pytest.mark.parametrize("effect", ["gr_potential", "gravitational_harmonics"])
+def test_force_is_minus_gradient_of_the_reference_potential(built, effect):
+    """The reference's conservation tests (reboundx/tests/test_conservation.py:44-56,73-87) pin these two
+    effects through their potentials.  Independent of the force oracle: m_i a_i computed on the device
+    must equal -dU/dx_i, with U the REFERENCE's own potential function (compiled in oracle/_ref)
+    differentiated by 4th-order central differences.  Same 3-body set-up as the reference's test."""
+    import ctypes
+    from oracle import oracle
+    from reboundx_b200 import workloads as W
+    from reboundx_b200.host import Extras, Simulation
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    G = 1.0
+    x1, y1, z1, vx1, vy1, vz1 = (float(v[0]) for v in W.kepler_to_cartesian(G*1.0001, np.array([1.0]), np.array([0.1]), np.array([0.0]), np.array([0.3]), np.array([0.7]), np.array([1.1])))
+    x2, y2, z2, vx2, vy2, vz2 = (float(v[0]) for v in W.kepler_to_cartesian(G*1.0002, np.array([2.0]), np.array([0.1]), np.array([0.2]), np.array([1.3]), np.array([0.2]), np.array([2.5])))
+    state = {"x": np.array([0.0, x1, x2]), "y": np.array([0.0, y1, y2]), "z": np.array([0.0, z1, z2]),
+             "vx": np.array([0.0, vx1, vx2]), "vy": np.array([0.0, vy1, vy2]), "vz": np.array([0.0, vz1, vz2]),
+             "m": np.array([1.0, 1e-4, 1e-4])}
+
+    def build(lib, pos):
+        sim = Simulation(G=G)
+        sim.set_particles(pos["x"], pos["y"], pos["z"], state["vx"], state["vy"], state["vz"], state["m"])
+        rebx = Extras(sim, lib=lib)
+        f = rebx.load_force(effect)
+        if effect == "gr_potential":
+            f.params["c"] = 1.0e2
+        else:
+            p0 = rebx.particle_params(0)
+            p0["J2"] = 1e-3; p0["J4"] = 1e-3; p0["R_eq"] = 1e-1; p0["Omega"] = (0.2, -0.1, 1.0)
+        rebx.add_force(f)
+        return sim, rebx, f
+
+    ref = oracle.ref_lib()
+    ref.rebx_gr_potential_potential.restype = ctypes.c_double
+    ref.rebx_gravitational_harmonics_potential.restype = ctypes.c_double
+
+    def potential(pos):
+        sim, rebx, f = build(ref, pos)
+        U = ref.rebx_gr_potential_potential(rebx._ptr, f._ptr) if effect == "gr_potential" else ref.rebx_gravitational_harmonics_potential(rebx._ptr)
+        rebx.detach(); sim.free()
+        return U
+
+    sim, rebx, _ = build(None, state)
+    sim.additional_forces(); sim.process_messages()
+    acc = sim.acc()
+    rebx.detach(); sim.free()
+    h = 1e-4
+    for i in range(3):
+        for c, key in enumerate(("x", "y", "z")):
+            def U(delta):
+                pos = {k: state[k].copy() for k in ("x", "y", "z")}
+                pos[key][i] += delta
+                return potential(pos)
+            dU = (-U(2*h) + 8*U(h) - 8*U(-h) + U(-2*h))/(12*h)
+            force = state["m"][i]*acc[c][i]
+            scale = max(abs(state["m"][i]*a[i]) for a in acc)
+            assert abs(force + dU) <= 2e-7*scale + 1e-18, (i, key, force, -dU)
