@@ -708,20 +708,17 @@ struct Combo { int k[4]; pass_fn fn[2]; bool red[4]; pass_fn tma; int tma_smem; 
                                   pass_kernel_tma<a, b, c, d>, TmaCfg<a, b, c, d>::smem_bytes, \
                                   { step_kernel<1, a, b, c, d>, step_kernel<2, a, b, c, d> } },
 static Combo kCombos[] = {
-    // singles
+    // every effect alone (any other stack falls back to consecutive single sweeps, still in list order)
     REBXB_COMBO(1,0,0,0) REBXB_COMBO(2,0,0,0) REBXB_COMBO(3,0,0,0) REBXB_COMBO(4,0,0,0)
     REBXB_COMBO(5,0,0,0) REBXB_COMBO(6,0,0,0) REBXB_COMBO(7,0,0,0)
-    // config 3: J2/J4 (+) gr_potential, either order; two oblate bodies
-    REBXB_COMBO(2,3,0,0) REBXB_COMBO(3,2,0,0) REBXB_COMBO(2,2,0,0)
+    // config 3: J2/J4 (+) gr_potential, either LIFO order
+    REBXB_COMBO(2,3,0,0) REBXB_COMBO(3,2,0,0)
     // config 4: yarkovsky (+) gr_potential
     REBXB_COMBO(4,3,0,0) REBXB_COMBO(3,4,0,0)
-    // radiation stacks
-    REBXB_COMBO(1,3,0,0) REBXB_COMBO(3,1,0,0) REBXB_COMBO(1,1,0,0)
-    REBXB_COMBO(1,3,2,0) REBXB_COMBO(2,3,1,0)
-    // config 5: damping trio in the two natural LIFO orders, and its pairs
+    // radiation (+) gr_potential
+    REBXB_COMBO(1,3,0,0) REBXB_COMBO(3,1,0,0)
+    // config 5: damping trio in the two natural LIFO orders
     REBXB_COMBO(7,6,5,0) REBXB_COMBO(5,6,7,0)
-    REBXB_COMBO(5,6,0,0) REBXB_COMBO(6,5,0,0) REBXB_COMBO(6,7,0,0) REBXB_COMBO(7,6,0,0)
-    REBXB_COMBO(5,7,0,0) REBXB_COMBO(7,5,0,0)
 };
 constexpr int kNumCombos = sizeof(kCombos)/sizeof(kCombos[0]);
 
