@@ -181,6 +181,18 @@ int rebx_b200_gather_bodies(const rebx_b200_state* st, double* bodies, int nbodi
  * instantiation. */
 int rebx_b200_leapfrog_step(const rebx_b200_pass* pass, double dt, double G, double softening, void* workspace, void* stream, int* launches);
 
+/* Integrates the velocities across `dt` under the stacked effects of `pass` alone, positions fixed --
+ * the device form of the reference's integrate_force operator and its schemes
+ * (src/integrate_force.c:34-78; src/integrator_euler.c:33-41, _rk2.c:38-66, _rk4.c:40-90,
+ * _implicit_midpoint.c:87-124).  `scheme` uses the reference's enum rebx_integrator values
+ * (0 implicit midpoint, 1 RK4, 2 Euler, 3 RK2).  `scratch`: 12*n doubles of device memory.  Every
+ * stage evaluates the sweep on scratch velocity/acceleration arrays, like the reference evaluates
+ * update_accelerations on scratch particle copies.  *iterations (host, may be NULL) returns the
+ * implicit-midpoint iteration count (10 = not converged, the reference warns).  Synchronises the
+ * stream for the implicit-midpoint convergence test only. */
+int rebx_b200_integrate_force(const rebx_b200_pass* pass, double dt, int scheme, void* scratch, void* workspace,
+                              void* stream, int* launches, int* iterations);
+
 /* AoS <-> SoA staging for the host-facing path (device-side transposes of one chunk). */
 int rebx_b200_unpack_aos(const void* aos, const rebx_b200_aos_layout* layout, const rebx_b200_state* st_out_as_mutable,
                          void* stream, int* launches);

@@ -274,3 +274,29 @@ def port_case(case):
         else:
             raise ValueError(name)
     return acc
+
+
+# ---- the reference's integrate_force operator (src/integrate_force.c + src/integrator_*.c) ----------
+INTEGRATORS = {"implicit_midpoint": 0, "rk4": 1, "euler": 2, "rk2": 3}       # reference reboundx.h enum rebx_integrator
+
+
+def ref_integrate_force(w, force_name, dt, scheme, nsteps=1):
+    """Velocities after `nsteps` applications of the reference's rebx_integrate_force(sim, operator, dt)
+    with the reference's own force loop, all compiled in oracle/_ref.  Returns (vx, vy, vz)."""
+    from ctypes import c_char_p
+    from reboundx_b200 import scenarios
+    from reboundx_b200.host import RebxForce
+    lib = ref_lib()
+    sim, rebx, handles = scenarios.build(w, [force_name], lib=lib)
+    lib.rebx_load_operator.restype = POINTER(RebxForce)          # rebx_operator has the same leading layout
+    op = lib.rebx_load_operator(rebx._ptr, c_char_p(b"integrate_force"))
+    ap = ctypes.cast(ctypes.addressof(op.contents) + RebxForce.ap.offset, c_void_p)
+    lib.rebx_set_param_pointer(rebx._ptr, ap, c_char_p(b"force"), handles[force_name]._ptr)
+    lib.rebx_set_param_int(rebx._ptr, ap, c_char_p(b"integrator"), c_int(INTEGRATORS[scheme]))
+    for _ in range(nsteps):
+        lib.rebx_integrate_force(sim.ptr, op, c_double(dt))
+    msgs = sim.messages()
+    out = sim.posvel()[3:]
+    rebx.detach()
+    sim.free()
+    return out, msgs

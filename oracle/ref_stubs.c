@@ -10,5 +10,5 @@ STUB(rebx_central_force) STUB(rebx_exponential_migration) STUB(rebx_gas_dynamica
 STUB(rebx_gr_full) STUB(rebx_lense_thirring) STUB(rebx_stochastic_forces)
 STUB(rebx_tides_constant_time_lag) STUB(rebx_tides_dynamical) STUB(rebx_tides_spin)
 STUB(rebx_modify_mass) STUB(rebx_modify_orbits_direct) STUB(rebx_track_min_distance)
-STUB(rebx_integrate_force) STUB(rebx_ias15_step) STUB(rebx_kepler_step) STUB(rebx_jump_step)
+STUB(rebx_ias15_step) STUB(rebx_kepler_step) STUB(rebx_jump_step)
 STUB(rebx_interaction_step) STUB(rebx_drift_step) STUB(rebx_kick_step)

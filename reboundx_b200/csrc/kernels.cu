@@ -662,6 +662,69 @@ __global__ void gather_bodies_kernel(rebx_b200_state st, double* __restrict__ bo
     if (st.m) rec[REBX_B200_BODY_M] = st.m[k];
 }
 
+// ---- integrate_force schemes: element-wise stage updates --------------------------------------------
+struct V3 { double *x, *y, *z; };
+struct CV3 { const double *x, *y, *z; };
+
+// out = v + s*a
+__global__ void __launch_bounds__(kThreads) stage_axpy_kernel(V3 out, CV3 v, CV3 a, double s, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < n; k += stride) {
+        out.x[k] = v.x[k] + s*a.x[k]; out.y[k] = v.y[k] + s*a.y[k]; out.z[k] = v.z[k] + s*a.z[k];
+    }
+}
+// RK4 stage 4 set-up (integrator_rk4.c:73-80): v2 = v + dt*a3 ; a3 += a2 ; a2 = 0
+__global__ void __launch_bounds__(kThreads) rk4_stage4_kernel(V3 v2, V3 a2, V3 a3, CV3 v, double dt, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < n; k += stride) {
+        v2.x[k] = v.x[k] + dt*a3.x[k]; v2.y[k] = v.y[k] + dt*a3.y[k]; v2.z[k] = v.z[k] + dt*a3.z[k];
+        a3.x[k] += a2.x[k]; a3.y[k] += a2.y[k]; a3.z[k] += a2.z[k];
+        a2.x[k] = 0.; a2.y[k] = 0.; a2.z[k] = 0.;
+    }
+}
+// v += w*(a1 + a4 + 2.*a23)   (integrator_rk4.c:84-89)
+__global__ void __launch_bounds__(kThreads) rk4_final_kernel(V3 v, CV3 a1, CV3 a4, CV3 a23, double w, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < n; k += stride) {
+        v.x[k] += w*(a1.x[k] + a4.x[k] + 2.*a23.x[k]);
+        v.y[k] += w*(a1.y[k] + a4.y[k] + 2.*a23.y[k]);
+        v.z[k] += w*(a1.z[k] + a4.z[k] + 2.*a23.z[k]);
+    }
+}
+// v += b1*a1 + b2*a2   (integrator_rk2.c:60-65)
+__global__ void __launch_bounds__(kThreads) rk2_final_kernel(V3 v, CV3 a1, CV3 a2, double b1, double b2, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < n; k += stride) {
+        v.x[k] += b1*a1.x[k] + b2*a2.x[k]; v.y[k] += b1*a1.y[k] + b2*a2.y[k]; v.z[k] += b1*a1.z[k] + b2*a2.z[k];
+    }
+}
+// implicit midpoint: v_avg = 0.5*(v_orig + v_final), a_avg = 0  (integrator_implicit_midpoint.c:33-49)
+__global__ void __launch_bounds__(kThreads) im_average_kernel(V3 vavg, V3 aavg, CV3 vorig, CV3 vfinal, int64_t n) {
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < n; k += stride) {
+        vavg.x[k] = 0.5*(vorig.x[k] + vfinal.x[k]); vavg.y[k] = 0.5*(vorig.y[k] + vfinal.y[k]); vavg.z[k] = 0.5*(vorig.z[k] + vfinal.z[k]);
+        aavg.x[k] = 0.; aavg.y[k] = 0.; aavg.z[k] = 0.;
+    }
+}
+// convergence sums of compare() (integrator_implicit_midpoint.c:51-66): sum |v1-v2|^2 and sum |v1|^2
+__global__ void __launch_bounds__(kThreads) im_compare_kernel(CV3 v1, CV3 v2, int64_t n, double* __restrict__ sums) {
+    __shared__ double s_a[kThreads], s_b[kThreads];
+    double d2 = 0.0, t2 = 0.0;
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < n; k += stride) {
+        const double dx = v1.x[k] - v2.x[k], dy = v1.y[k] - v2.y[k], dz = v1.z[k] - v2.z[k];
+        d2 += dx*dx + dy*dy + dz*dz;
+        t2 += v1.x[k]*v1.x[k] + v1.y[k]*v1.y[k] + v1.z[k]*v1.z[k];
+    }
+    s_a[threadIdx.x] = d2; s_b[threadIdx.x] = t2;
+    __syncthreads();
+    for (int w = kThreads/2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) { s_a[threadIdx.x] += s_a[threadIdx.x + w]; s_b[threadIdx.x] += s_b[threadIdx.x + w]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { atomicAdd(&sums[0], s_a[0]); atomicAdd(&sums[1], s_b[0]); }
+}
+
 // ---- AoS <-> SoA staging (host-facing path; sits behind PCIe, so kept simple) ----------------
 __global__ void __launch_bounds__(kThreads)
 unpack_aos_kernel(const unsigned char* __restrict__ aos, rebx_b200_aos_layout L,
@@ -820,7 +883,7 @@ const char* rebx_b200_error_string(int code) {
 }
 
 size_t rebx_b200_workspace_bytes(void) {
-    return (size_t)kMaxBlocks*REBX_B200_MAX_EFFECTS*3*sizeof(double);
+    return ((size_t)kMaxBlocks*REBX_B200_MAX_EFFECTS*3 + 8)*sizeof(double);     // CTA partials + a few scalars
 }
 
 int rebx_b200_sm_count(int device) {
@@ -1029,6 +1092,110 @@ int rebx_b200_leapfrog_step(const rebx_b200_pass* pass, double dt, double G, dou
     step_body_kernel<<<1, 32, 0, s>>>(P, S, any ? red_mask : 0u);
     nl++;
     cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) *launches += nl;
+    return err;
+}
+
+// One force evaluation of the stack on stage arrays (v, a): what the reference's schemes do with
+// force->update_accelerations(sim, force, scratch_copy, N).  The body record follows the stage's
+// velocity of the body, as `particles[source]` does there.
+static int stage_eval(const rebx_b200_pass& base, CV3 v, V3 a, void* workspace, cudaStream_t s, int* launches) {
+    rebx_b200_pass P = base;
+    P.st.vx = v.x; P.st.vy = v.y; P.st.vz = v.z;
+    P.st.ax = a.x; P.st.ay = a.y; P.st.az = a.z;
+    int rc = rebx_b200_gather_bodies(&P.st, const_cast<double*>(P.fx[0].body), P.n_effects, s, launches);
+    if (rc) return rc;
+    rc = rebx_b200_launch_pass(&P, workspace, s, launches);
+    if (rc) return rc;
+    return rebx_b200_apply_backreaction(&P, s, launches);
+}
+
+int rebx_b200_integrate_force(const rebx_b200_pass* pass, double dt, int scheme, void* scratch, void* workspace,
+                              void* stream, int* launches, int* iterations) {
+    if (!pass || !scratch || !workspace) return cudaErrorInvalidValue;
+    const int bad = check_pass(*pass);
+    if (bad) return bad;
+    const rebx_b200_pass& P = *pass;
+    if (!P.st.vx) return cudaErrorInvalidValue;
+    // the body records of a stack must be contiguous (as device.Shard and the dispatcher lay them out)
+    for (int e = 1; e < P.n_effects; e++) if (P.fx[e].body != P.fx[0].body + (size_t)e*REBX_B200_BODY_DOUBLES) return cudaErrorInvalidValue;
+    const int64_t n = P.st.n;
+    if (n == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    double* w = static_cast<double*>(scratch);
+    auto slot = [&](int i) { return V3{w + (size_t)(3*i)*n, w + (size_t)(3*i + 1)*n, w + (size_t)(3*i + 2)*n}; };
+    auto c = [](V3 q) { return CV3{q.x, q.y, q.z}; };
+    const V3 v = {const_cast<double*>(P.st.vx), const_cast<double*>(P.st.vy), const_cast<double*>(P.st.vz)};
+    const V3 a1 = {P.st.ax, P.st.ay, P.st.az};
+    const int grid = grid_for(reinterpret_cast<const void*>(stage_axpy_kernel), n);
+    int nl = 0, rc = 0;
+    cudaError_t err;
+    auto zero = [&](V3 q) {
+        cudaMemsetAsync(q.x, 0, n*sizeof(double), s); cudaMemsetAsync(q.y, 0, n*sizeof(double), s); cudaMemsetAsync(q.z, 0, n*sizeof(double), s);
+    };
+    zero(a1);                                        // rebx_reset_accelerations (integrate_force.c:46)
+    if (scheme == 2) {                               // Euler
+        if ((rc = stage_eval(P, c(v), a1, workspace, s, &nl))) return rc;
+        stage_axpy_kernel<<<grid, kThreads, 0, s>>>(v, c(v), c(a1), dt, n); nl++;
+    } else if (scheme == 3) {                        // RK2
+        const V3 v2 = slot(0), a2 = slot(1);
+        zero(a2);
+        if ((rc = stage_eval(P, c(v), a1, workspace, s, &nl))) return rc;
+        stage_axpy_kernel<<<grid, kThreads, 0, s>>>(v2, c(v), c(a1), 2.*dt/3., n); nl++;
+        if ((rc = stage_eval(P, c(v2), a2, workspace, s, &nl))) return rc;
+        rk2_final_kernel<<<grid, kThreads, 0, s>>>(v, c(a1), c(a2), dt/4., 3.*dt/4., n); nl++;
+    } else if (scheme == 1) {                        // RK4
+        const V3 v2 = slot(0), a2 = slot(1), v3 = slot(2), a3 = slot(3);
+        const double dt2 = dt/2.;
+        zero(a2); zero(a3);
+        if ((rc = stage_eval(P, c(v), a1, workspace, s, &nl))) return rc;
+        stage_axpy_kernel<<<grid, kThreads, 0, s>>>(v2, c(v), c(a1), dt2, n); nl++;
+        if ((rc = stage_eval(P, c(v2), a2, workspace, s, &nl))) return rc;
+        stage_axpy_kernel<<<grid, kThreads, 0, s>>>(v3, c(v), c(a2), dt2, n); nl++;
+        if ((rc = stage_eval(P, c(v3), a3, workspace, s, &nl))) return rc;
+        rk4_stage4_kernel<<<grid, kThreads, 0, s>>>(v2, a2, a3, c(v), dt, n); nl++;
+        if ((rc = stage_eval(P, c(v2), a2, workspace, s, &nl))) return rc;
+        rk4_final_kernel<<<grid, kThreads, 0, s>>>(v, c(a1), c(a2), c(a3), dt/6., n); nl++;
+    } else if (scheme == 0) {                        // implicit midpoint
+        const V3 vfinal = slot(0), vprev = slot(1), vavg = slot(2), aavg = slot(3);
+        double* sums = static_cast<double*>(workspace) + (size_t)kMaxBlocks*REBX_B200_MAX_EFFECTS*3;        // scalar tail of the workspace
+        for (int q = 0; q < 3; q++) {
+            double* src[3] = {v.x, v.y, v.z};
+            double* d1[3] = {vfinal.x, vfinal.y, vfinal.z};
+            double* d2[3] = {vavg.x, vavg.y, vavg.z};
+            cudaMemcpyAsync(d1[q], src[q], n*sizeof(double), cudaMemcpyDeviceToDevice, s);
+            cudaMemcpyAsync(d2[q], src[q], n*sizeof(double), cudaMemcpyDeviceToDevice, s);
+        }
+        zero(aavg);
+        int it = 0;
+        for (it = 0; it < 10; it++) {
+            for (int q = 0; q < 3; q++) {
+                double* from[3] = {vfinal.x, vfinal.y, vfinal.z};
+                double* to[3] = {vprev.x, vprev.y, vprev.z};
+                cudaMemcpyAsync(to[q], from[q], n*sizeof(double), cudaMemcpyDeviceToDevice, s);
+            }
+            if ((rc = stage_eval(P, c(vavg), aavg, workspace, s, &nl))) return rc;
+            stage_axpy_kernel<<<grid, kThreads, 0, s>>>(vfinal, c(v), c(aavg), dt, n); nl++;
+            cudaMemsetAsync(sums, 0, 2*sizeof(double), s);
+            im_compare_kernel<<<grid, kThreads, 0, s>>>(c(vfinal), c(vprev), n, sums); nl++;
+            double h[2];
+            if ((err = cudaMemcpyAsync(h, sums, sizeof h, cudaMemcpyDeviceToHost, s)) != cudaSuccess) return err;
+            if ((err = cudaStreamSynchronize(s)) != cudaSuccess) return err;
+            if (h[0]/h[1] < 2.220446049250313e-16*2.220446049250313e-16) break;
+            im_average_kernel<<<grid, kThreads, 0, s>>>(vavg, aavg, c(v), c(vfinal), n); nl++;
+        }
+        if (iterations) *iterations = it;
+        for (int q = 0; q < 3; q++) {
+            double* from[3] = {vfinal.x, vfinal.y, vfinal.z};
+            double* to[3] = {v.x, v.y, v.z};
+            cudaMemcpyAsync(to[q], from[q], n*sizeof(double), cudaMemcpyDeviceToDevice, s);
+        }
+    } else {
+        return cudaErrorInvalidValue;
+    }
+    // leave the body records consistent with the updated velocities
+    if ((rc = rebx_b200_gather_bodies(&P.st, const_cast<double*>(P.fx[0].body), P.n_effects, s, &nl))) return rc;
+    err = cudaGetLastError();
     if (err == cudaSuccess && launches) *launches += nl;
     return err;
 }

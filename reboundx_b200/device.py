@@ -270,6 +270,22 @@ class Shard:
         self.launches += n.value
         return n.value
 
+    def integrate_force(self, dt, scheme="rk4", stream=None):
+        """Velocities across `dt` under this shard's stacked effects alone (positions fixed): the
+        reference's integrate_force operator (src/integrate_force.c) with its euler / rk2 / rk4 /
+        implicit_midpoint schemes, on the device."""
+        code = {"implicit_midpoint": 0, "rk4": 1, "euler": 2, "rk2": 3}[scheme]
+        if getattr(self, "_scratch", None) is None:
+            self._scratch = self.torch.empty(12*self.n, dtype=self.torch.float64, device=self.device)
+        n, it = c_int(0), c_int(-1)
+        self.lib.rebx_b200_integrate_force.restype = c_int
+        rc = self.lib.rebx_b200_integrate_force(ctypes.byref(self._pass), c_double(dt), c_int(code), c_void_p(self._scratch.data_ptr()),
+                                                c_void_p(self.workspace.data_ptr()), c_void_p(self._stream(stream).cuda_stream),
+                                                ctypes.byref(n), ctypes.byref(it))
+        self._check(rc, "rebx_b200_integrate_force")
+        self.launches += n.value
+        return it.value
+
     def posvel(self):
         return [self.state[k].cpu().numpy() for k in ("x", "y", "z", "vx", "vy", "vz")]
 

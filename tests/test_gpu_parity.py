@@ -666,3 +666,34 @@ def test_force_is_minus_gradient_of_the_reference_potential(built, effect):
             force = state["m"][i]*acc[c][i]
             scale = max(abs(state["m"][i]*a[i]) for a in acc)
             assert abs(force + dU) <= 2e-7*scale + 1e-18, (i, key, force, -dU)
+
+
+@pytest.mark.parametrize("scheme", ["euler", "rk2", "rk4", "implicit_midpoint"])
+def test_device_integrate_force_against_the_reference_operator(built, scheme):
+    """the reference's integrate_force operator and its four schemes
+    (src/integrate_force.c, src/integrator_*.c, compiled unmodified into oracle/_ref together with the
+    reference's radiation loop) against rebx_b200_integrate_force on a resident shard."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    w = workloads.debris_disk(20001)
+    w["beta"] = w["beta"]*50.0                  # a strong force, so every stage matters
+    dt = 3.0e8
+    (vx, vy, vz), msgs = oracle.ref_integrate_force(w, "radiation_forces", dt, scheme, nsteps=3)
+    assert not [m for k, m in msgs if k == "error"]
+    sh = device.Shard(w, ["radiation_forces"], "cuda:0")
+    for _ in range(3):
+        sh.integrate_force(dt, scheme)
+    torch.cuda.synchronize()
+    got = sh.posvel()
+    assert np.array_equal(np.array(got[:3]), np.array([w["x"], w["y"], w["z"]]))       # positions untouched
+    want = np.array([vx, vy, vz])
+    if scheme == "implicit_midpoint":
+        # the convergence test sums over all particles; the device sums in another order, so the
+        # iteration may stop one step apart in the last bit
+        assert np.max(np.abs(np.array(got[3:]) - want)/np.max(np.abs(want))) <= 1e-15
+    else:
+        assert np.array_equal(np.array(got[3:]), want)
+    assert np.any(want != np.array([w["vx"], w["vy"], w["vz"]]))
