@@ -127,6 +127,7 @@ void rebx_set_param_string(struct rebx_extras* const rebx, struct rebx_node** ap
 struct rebx_param* rebx_create_param(struct rebx_extras* rebx, const char* name, enum rebx_param_type type);
 int  rebx_add_param(struct rebx_extras* const rebx, struct rebx_node** apptr, struct rebx_param* param);
 struct rebx_node* rebx_create_node(struct rebx_extras* rebx);
+size_t rebx_sizeof(struct rebx_extras* rebx, enum rebx_param_type type);   /* reference src/core.h:52 */
 
 /* ---- lists and memory: reference src/linkedlist.h:34-57, src/core.h:90-98 --------------- */
 void rebx_add_node(struct rebx_node** head, struct rebx_node* node);

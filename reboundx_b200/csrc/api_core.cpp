@@ -493,6 +493,21 @@ void rebx_set_param_string(struct rebx_extras* const rebx, struct rebx_node** ap
     if (param->value) *static_cast<const char**>(param->value) = reb_simulation_register_name(rebx->sim, val);
 }
 
+// reference src/core.c:1141-1177 (used by the binary writer, src/output.c)
+size_t rebx_sizeof(struct rebx_extras* rebx, enum rebx_param_type type) {
+    switch (type) {
+        case REBX_TYPE_DOUBLE:  return sizeof(double);
+        case REBX_TYPE_INT:     return sizeof(int);
+        case REBX_TYPE_UINT32:  return sizeof(uint32_t);
+        case REBX_TYPE_FORCE:   return sizeof(struct rebx_force);
+        case REBX_TYPE_VEC3D:   return sizeof(struct reb_vec3d);
+        case REBX_TYPE_POINTER: case REBX_TYPE_STRING: case REBX_TYPE_ORBIT: case REBX_TYPE_ODE: return 0;
+        default:
+            rebx_error(rebx, "REBOUNDx Error: Parameter type passed to rebx_sizeof is not registered.\n");
+            return 0;
+    }
+}
+
 void rebx_mark_params_dirty(struct rebx_extras* rebx) { mark_dirty(rebx); }
 
 // Bulk ingest (extension): same list structure as N calls of rebx_set_param_*, but the type

@@ -321,6 +321,22 @@ class Extras:
         sim._extras_ref = self
         self.process_messages()
 
+    @classmethod
+    def from_pointer(cls, sim, ptr, lib=None):
+        """Wraps a `struct rebx_extras*` created elsewhere (e.g. by rebx_create_extras_from_binary)."""
+        self = cls.__new__(cls)
+        self._lib = lib or _lib.load()
+        self._sim = sim
+        self._lib.rebx_get_param_struct.restype = POINTER(RebxParam)
+        self._lib.rebx_get_param_struct.argtypes = [c_void_p, POINTER(RebxNode), c_char_p]
+        self._lib.rebx_get_type.restype = c_int
+        self._lib.rebx_get_type.argtypes = [c_void_p, c_char_p]
+        self._lib.rebx_get_force.restype = POINTER(RebxForce)
+        self._lib.rebx_len.restype = c_int
+        self._ptr = ctypes.cast(ptr, POINTER(RebxExtras))
+        sim._extras_ref = self
+        return self
+
     @property
     def struct(self):
         return self._ptr.contents
