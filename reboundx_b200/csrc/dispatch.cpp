@@ -108,6 +108,7 @@ struct DeviceContext {
     size_t registered_bytes = 0;
     Stats stats;
     size_t chunk = size_t(1) << 19;         // 64 MB of AoS records per pipeline stage
+    bool chunk_from_env = false;
     bool paranoid = false;
 
     void unregister_host() {
@@ -352,7 +353,7 @@ static DeviceContext* ensure_ctx(Side* side, std::string& why) {
     if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
     for (auto& s : ctx->stream) if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
     if ((e = cudaEventCreateWithFlags(&ctx->bodies_ready, cudaEventDisableTiming)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
-    if (const char* c = std::getenv("REBX_B200_CHUNK")) { long v = std::atol(c); if (v >= 1024) ctx->chunk = (size_t)v & ~size_t(1); }
+    if (const char* c = std::getenv("REBX_B200_CHUNK")) { long v = std::atol(c); if (v >= 1024) { ctx->chunk = (size_t)v & ~size_t(1); ctx->chunk_from_env = true; } }
     if (const char* p = std::getenv("REBX_B200_PARANOID")) ctx->paranoid = std::atoi(p) != 0;
     ctx->ready = true;
     side->dev = std::move(ctx);
@@ -588,10 +589,15 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     // all particles precedes the sweep), so such a segment runs as one resident chunk.
     bool whole = false;
     for (const Entry& e : entries) if (e.frame != 0) whole = true;
-    const size_t CH = whole ? ((N + 1) & ~size_t(1)) : ctx->chunk;
+    // Pipeline granularity: the configured chunk for large ensembles; mid-size ones are cut into ~6
+    // pieces (>= 32768 particles) so that H2D, sweep and D2H of different pieces overlap.
+    size_t CH = ctx->chunk;
+    if (!ctx->chunk_from_env && N < 6*ctx->chunk) CH = std::max<size_t>(32768, ((N/6) + 1) & ~size_t(1));
+    if (whole) CH = (N + 1) & ~size_t(1);
     const size_t nchunks = (N + CH - 1)/CH;
     const size_t chunk_cap = std::min(N, CH);
-    bool need_vel = false, need_m = false, need_r = false;
+    bool need_vel = false, need_m = false, need_r = false, any_reduces = false;
+    for (const Entry& e : entries) if (e.reduces) any_reduces = true;
     for (const Entry& e : entries) {
         switch (e.kind) {
             case REBX_B200_RADIATION: need_vel = true; break;
@@ -626,7 +632,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     }
     // Pin the caller's particle array once so the DMA engines can stream it (only worth it for
     // the simulation's own long-lived array, not for an integrator's scratch copy).
-    if (particles == sim->particles && N*sizeof(struct reb_particle) >= (size_t(8) << 20)) {
+    if (particles == sim->particles && N*sizeof(struct reb_particle) >= (size_t(256) << 10)) {
         if (ctx->registered_ptr != particles || ctx->registered_bytes != N*sizeof(struct reb_particle)) {
             ctx->unregister_host();
             if (cudaHostRegister(particles, N*sizeof(struct reb_particle), cudaHostRegisterDefault) == cudaSuccess) {
@@ -640,9 +646,11 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     bodies_h = static_cast<double*>(ctx->bodies_h.p);
     for (size_t e = 0; e < ne; e++) fill_body(bodies_h + e*REBX_B200_BODY_DOUBLES, entries[e], particles);
     REBXB_CUDA(cudaMemcpyAsync(ctx->bodies.p, bodies_h, ne*REBX_B200_BODY_DOUBLES*sizeof(double), cudaMemcpyHostToDevice, ctx->stream[0]), "copying body records");
-    REBXB_CUDA(cudaMemsetAsync(ctx->br.p, 0, nchunks*ne*3*sizeof(double), ctx->stream[0]), "clearing back-reaction sums");
-    REBXB_CUDA(cudaEventRecord(ctx->bodies_ready, ctx->stream[0]), "recording event");
-    for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamWaitEvent(ctx->stream[b], ctx->bodies_ready, 0), "waiting on event");
+    if (any_reduces) REBXB_CUDA(cudaMemsetAsync(ctx->br.p, 0, nchunks*ne*3*sizeof(double), ctx->stream[0]), "clearing back-reaction sums");
+    if (nchunks > 1) {      // the other pipeline streams must see the body records
+        REBXB_CUDA(cudaEventRecord(ctx->bodies_ready, ctx->stream[0]), "recording event");
+        for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamWaitEvent(ctx->stream[b], ctx->bodies_ready, 0), "waiting on event");
+    }
     ctx->stats.h2d_bytes += ne*REBX_B200_BODY_DOUBLES*sizeof(double);
 
     for (size_t c = 0; c < nchunks; c++) {
@@ -727,11 +735,13 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         REBXB_CUDA(cudaMemcpyAsync(particles + c0, ctx->aos[b].p, bytes, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
         ctx->stats.d2h_bytes += bytes;
     }
-    for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamSynchronize(ctx->stream[b]), "waiting for the device");
+    if (nchunks > 1) for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamSynchronize(ctx->stream[b]), "waiting for the device");
     br_h = static_cast<double*>(ctx->br_h.p);
-    REBXB_CUDA(cudaMemcpyAsync(br_h, ctx->br.p, nchunks*ne*3*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream[0]), "copying back-reaction sums");
+    if (any_reduces) {
+        REBXB_CUDA(cudaMemcpyAsync(br_h, ctx->br.p, nchunks*ne*3*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream[0]), "copying back-reaction sums");
+        ctx->stats.d2h_bytes += nchunks*ne*3*sizeof(double);
+    }
     REBXB_CUDA(cudaStreamSynchronize(ctx->stream[0]), "waiting for the device");
-    ctx->stats.d2h_bytes += nchunks*ne*3*sizeof(double);
     ctx->stats.launches += (std::uint64_t)launches;
 
     // Back-reaction onto the source / primary / oblate bodies (gr_potential.c:74-76,
