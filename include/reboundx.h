@@ -156,6 +156,10 @@ void rebx_modify_orbits_forces(struct reb_simulation* const sim, struct rebx_for
 void rebx_gas_damping_timescale(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);   /* src/gas_damping_timescale.c:132 */
 void rebx_modify_orbits_with_type_I_migration(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N); /* src/type_I_migration.c:205 */
 
+/* Widened per SURVEY.md section 8f rank 3 (same-shape neighbouring forces): */
+void rebx_central_force(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);         /* src/central_force.c:87 */
+void rebx_exponential_migration(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N); /* src/exponential_migration.c:103 */
+
 /* Host scalar helpers: reference src/reboundx.h:497,510; src/inner_disk_edge.c:61 */
 double rebx_rad_calc_beta(const double G, const double c, const double source_mass, const double source_luminosity, const double radius, const double density, const double Q_pr);
 double rebx_rad_calc_particle_radius(const double G, const double c, const double source_mass, const double source_luminosity, const double beta, const double density, const double Q_pr);

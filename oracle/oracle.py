@@ -26,7 +26,7 @@ PORT_PATH = os.path.join(_HERE, "liboracle_forces.so")
 
 YARK_PARAMS = ["ye_body_density", "ye_rotation_period", "ye_thermal_inertia", "ye_albedo", "ye_emissivity",
                "ye_k", "ye_spin_axis_x", "ye_spin_axis_y", "ye_spin_axis_z"]
-KIND = {"modify_orbits_forces": 5, "gas_damping_timescale": 6, "type_I_migration": 7}
+KIND = {"modify_orbits_forces": 5, "gas_damping_timescale": 6, "type_I_migration": 7, "exponential_migration": 9}
 COORD = {"JACOBI": 0, "BARYCENTRIC": 1, "PARTICLE": 2}
 
 
@@ -76,7 +76,10 @@ class _DampingParams(ctypes.Structure):
                 ("d_factor", POINTER(c_double)), ("has_d_factor", POINTER(c_ubyte)),
                 ("cs_coeff", c_double), ("tau_coeff", c_double),
                 ("tIm_beta", c_double), ("tIm_h0", c_double), ("tIm_sd0", c_double), ("tIm_s", c_double),
-                ("tIm_dedge", c_double), ("tIm_hedge", c_double)]
+                ("tIm_dedge", c_double), ("tIm_hedge", c_double),
+                ("em_tau_a", POINTER(c_double)), ("em_aini", POINTER(c_double)), ("em_afin", POINTER(c_double)),
+                ("has_em_tau_a", POINTER(c_ubyte)), ("has_em_aini", POINTER(c_ubyte)), ("has_em_afin", POINTER(c_ubyte)),
+                ("t", c_double)]
 
 
 def _port():
@@ -128,6 +131,10 @@ def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE", n_active=-1):
             lib.oracle_gr_potential(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["m"]), c_double(w["G"]), c_double(w["c"]),
                                     _d(acc[0]), _d(acc[1]), _d(acc[2]), out)
             br[name] = np.array([float(v) for v in out])
+        elif name == "central_force":
+            lib.oracle_central_force(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["m"]), c_int64(0),
+                                     c_double(w["Acentral"]), c_double(w["gammacentral"]), _d(acc[0]), _d(acc[1]), _d(acc[2]), out)
+            br[name] = np.array([float(v) for v in out])
         elif name == "gr":
             lib.oracle_gr(c_int64(n), c_int64(n_active), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]),
                           _d(S["m"]), c_double(w["G"]), c_double(w["c"]), c_int(w.get("max_iterations") or 10),
@@ -155,12 +162,13 @@ def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE", n_active=-1):
                                         _d(acc[0]), _d(acc[1]), _d(acc[2]))
         elif name in KIND:
             dp = _DampingParams()
-            for p in ("tau_a", "tau_e", "tau_inc", "d_factor"):
+            for p in ("tau_a", "tau_e", "tau_inc", "d_factor", "em_tau_a", "em_aini", "em_afin"):
                 full, mask = _full(w, p, n)
                 if full is not None:
                     keep += [full, mask]
                     setattr(dp, p, _d(full))
                     setattr(dp, "has_" + p, mask.ctypes.data_as(POINTER(c_ubyte)))
+            dp.t = w.get("t") or 0.0
             if name == "modify_orbits_forces":
                 dp.trap = int(w.get("ide_position") is not None and w.get("ide_width") is not None)
                 dp.dedge, dp.hedge = w.get("ide_position") or 0.0, w.get("ide_width") or 0.0
@@ -250,7 +258,8 @@ def port_case(case):
         elif name in KIND:
             dp = _DampingParams()
             keep = []
-            for p in ("tau_a", "tau_e", "tau_inc", "d_factor"):
+            dp.t = case.get("t", 0.0)
+            for p in ("tau_a", "tau_e", "tau_inc", "d_factor", "em_tau_a", "em_aini", "em_afin"):
                 vals, mask = _pp(case, p, n)
                 keep += [vals, mask]
                 setattr(dp, p, _d(vals))

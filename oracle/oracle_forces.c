@@ -232,8 +232,27 @@ void oracle_yarkovsky_effect(int64_t n, const double* x, const double* y, const 
     }
 }
 
+/* reference src/central_force.c:63-96 for ONE central body `bi` with (Acentral, gammacentral) */
+void oracle_central_force(int64_t n, const double* x, const double* y, const double* z, const double* m,
+                          int64_t bi, double A, double gamma, double* ax, double* ay, double* az, long double* br) {
+    const double sx = x[bi], sy = y[bi], sz = z[bi], sm = m[bi];
+    long double bsx = 0, bsy = 0, bsz = 0, bax = 0, bay = 0, baz = 0;
+    for (int64_t i = 0; i < n; i++) {
+        if (i == bi) continue;
+        const double dx = x[i] - sx, dy = y[i] - sy, dz = z[i] - sz;
+        const double r2 = dx*dx + dy*dy + dz*dz;
+        const double prefac = A*pow(r2, (gamma - 1.)/2.);
+        ax[i] += prefac*dx; ay[i] += prefac*dy; az[i] += prefac*dz;
+        const double tx = m[i]/sm*prefac*dx, ty = m[i]/sm*prefac*dy, tz = m[i]/sm*prefac*dz;
+        ax[bi] -= tx; ay[bi] -= ty; az[bi] -= tz;
+        bsx -= (long double)tx; bsy -= (long double)ty; bsz -= (long double)tz;
+        bax += fabsl((long double)tx); bay += fabsl((long double)ty); baz += fabsl((long double)tz);
+    }
+    if (br) { br[0] = bsx; br[1] = bsy; br[2] = bsz; br[3] = bax; br[4] = bay; br[5] = baz; }
+}
+
 /* ---- damping trio under rebx_com_force (reference src/rebxtools.c:66-147) ------------------ */
-enum { ORACLE_MODIFY_ORBITS = 5, ORACLE_GAS_DAMPING = 6, ORACLE_TYPE_I = 7 };
+enum { ORACLE_MODIFY_ORBITS = 5, ORACLE_GAS_DAMPING = 6, ORACLE_TYPE_I = 7, ORACLE_EXP_MIGRATION = 9 };
 enum { ORACLE_JACOBI = 0, ORACLE_BARYCENTRIC = 1, ORACLE_PARTICLE = 2 };
 
 typedef struct {
@@ -245,6 +264,10 @@ typedef struct {
     const double* d_factor; const unsigned char* has_d_factor; double cs_coeff, tau_coeff;
     /* type_I_migration */
     double tIm_beta, tIm_h0, tIm_sd0, tIm_s, tIm_dedge, tIm_hedge;
+    /* exponential_migration */
+    const double *em_tau_a, *em_aini, *em_afin;
+    const unsigned char *has_em_tau_a, *has_em_aini, *has_em_afin;
+    double t;
 } oracle_damping_params;
 
 static void damping_calc(int kind, const oracle_damping_params* P, double G, int64_t i,
@@ -291,6 +314,15 @@ static void damping_calc(int kind, const oracle_damping_params* P, double G, int
             const double prefac = 2*vdotr/r2/tau_e;
             f[0] += prefac*dx; f[1] += prefac*dy; f[2] += prefac*dz + 2.*dvz/tau_inc;
         }
+    } else if (kind == ORACLE_EXP_MIGRATION) {     /* src/exponential_migration.c:61-100 */
+        const orbit_t o = orbit_of(G, px, py, pz, pvx, pvy, pvz, pm, src);
+        double em_tau_a = INFINITY, em_aini = 24., em_afin = 30.;
+        if (P->em_tau_a && has(P->has_em_tau_a, i)) em_tau_a = P->em_tau_a[i];
+        if (P->em_aini && has(P->has_em_aini, i)) em_aini = P->em_aini[i];
+        if (P->em_afin && has(P->has_em_afin, i)) em_afin = P->em_afin[i];
+        f[0] = (dvx/(2.*em_tau_a))*((em_afin - em_aini)/(o.a))*exp(-(P->t)/em_tau_a);
+        f[1] = (dvy/(2.*em_tau_a))*((em_afin - em_aini)/(o.a))*exp(-(P->t)/em_tau_a);
+        f[2] = (dvz/(2.*em_tau_a))*((em_afin - em_aini)/(o.a))*exp(-(P->t)/em_tau_a);
     } else {                                       /* src/type_I_migration.c:69-203 */
         const orbit_t o = orbit_of(G, px, py, pz, pvx, pvy, pvz, pm, src);
         const double a0 = o.a, e0 = o.e, inc0 = o.inc, mp = pm, ms = src->m;

@@ -140,6 +140,8 @@ static int kind_of(const struct rebx_force* f) {
     if (fn == rebx_gas_damping_timescale) return REBX_B200_GAS_DAMPING;
     if (fn == rebx_modify_orbits_with_type_I_migration) return REBX_B200_TYPE_I;
     if (fn == rebx_gr) return KIND_GR;
+    if (fn == rebx_central_force) return REBX_B200_CENTRAL_FORCE;
+    if (fn == rebx_exponential_migration) return REBX_B200_EXP_MIGRATION;
     return REBX_B200_NONE;
 }
 
@@ -204,6 +206,7 @@ static void build_tables(ForceTables& T, int kind, struct rebx_force* force, con
         case REBX_B200_MODIFY_ORBITS: dnames = {"tau_a", "tau_e", "tau_inc"}; flag_name = "primary"; break;
         case REBX_B200_GAS_DAMPING:   dnames = {"d_factor"}; flag_name = "primary"; break;
         case REBX_B200_TYPE_I:        flag_name = "primary"; break;
+        case REBX_B200_EXP_MIGRATION: dnames = {"em_tau_a", "em_aini", "em_afin"}; flag_name = "primary"; break;
         default: break;
     }
     for (auto& n : dnames) n = intern_name(n);
@@ -211,6 +214,7 @@ static void build_tables(ForceTables& T, int kind, struct rebx_force* force, con
     if (ival_name) ival_name = intern_name(ival_name);
     const char* nJ2 = intern_name("J2"); const char* nJ4 = intern_name("J4");
     const char* nReq = intern_name("R_eq"); const char* nOmega = intern_name("Omega");
+    const char* nAc = intern_name("Acentral"); const char* nGc = intern_name("gammacentral");
 
     const size_t nd = dnames.size();
     for (size_t j = 0; j < REBX_B200_MAX_TABLES; j++) { if (j < nd) T.h[j].assign(N, ABSENT); else { T.h[j].clear(); T.h[j].shrink_to_fit(); } }
@@ -245,12 +249,23 @@ static void build_tables(ForceTables& T, int kind, struct rebx_force* force, con
                 } else if (ival_name && same_name(nm, ival_name)) {
                     if (!(found & (1u << 29)) && p->value) { T.hi[i] = *static_cast<const int*>(p->value); ipresent[i] = 1; }
                     found |= 1u << 29;
+                } else if (kind == REBX_B200_CENTRAL_FORCE) {
+                    // Acentral / gammacentral ride in the J2 / J4 slots of the collected record
+                    if (!J2 && same_name(nm, nAc)) J2 = static_cast<const double*>(p->value);
+                    else if (!J4 && same_name(nm, nGc)) J4 = static_cast<const double*>(p->value);
                 } else if (kind == REBX_B200_HARMONICS) {
                     if (!J2 && same_name(nm, nJ2)) J2 = static_cast<const double*>(p->value);
                     else if (!J4 && same_name(nm, nJ4)) J4 = static_cast<const double*>(p->value);
                     else if (!Req && same_name(nm, nReq)) Req = static_cast<const double*>(p->value);
                     else if (!Om && same_name(nm, nOmega)) Om = static_cast<const struct reb_vec3d*>(p->value);
                 }
+            }
+            if (kind == REBX_B200_CENTRAL_FORCE && J2 && J4) {
+                // src/central_force.c:88-95: a central body has BOTH Acentral and gammacentral
+                Oblate o;
+                std::memset(&o, 0, sizeof o);
+                o.J2 = *J2; o.J4 = *J4;
+                obl[t].push_back({(int64_t)i, o});
             }
             if (kind == REBX_B200_HARMONICS && J2 && *J2 != 0.0 && Req) {
                 // src/gravitational_harmonics.c:141-159: J2 set and non-zero, R_eq set; J4 and Omega optional
@@ -264,7 +279,7 @@ static void build_tables(ForceTables& T, int kind, struct rebx_force* force, con
         }
     });
     for (auto& v : flagged) T.bodies.insert(T.bodies.end(), v.begin(), v.end());
-    if (kind == REBX_B200_HARMONICS) {
+    if (kind == REBX_B200_HARMONICS || kind == REBX_B200_CENTRAL_FORCE) {
         for (auto& v : obl) for (auto& pr : v) { T.bodies.push_back(pr.first); T.oblate.push_back(pr.second); }
     }
 
@@ -393,6 +408,7 @@ static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceCont
         else for (int64_t s : T.bodies) { e.body_index = s; out.push_back(e); }  // one sweep per flagged source, ascending
         return true;
     }
+    case REBX_B200_CENTRAL_FORCE:
     case REBX_B200_HARMONICS: {
         ForceTables& T = tables_for(side, ctx, force, kind, particles, N, store);
         e.T = &T; e.reduces = true;
@@ -423,6 +439,7 @@ static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceCont
     }
     case REBX_B200_MODIFY_ORBITS:
     case REBX_B200_GAS_DAMPING:
+    case REBX_B200_EXP_MIGRATION:
     case REBX_B200_TYPE_I: {
         const int* cptr = static_cast<const int*>(find_value(force->ap, "coordinates"));
         const int coordinates = cptr ? *cptr : REBX_COORDINATES_JACOBI;
@@ -457,6 +474,8 @@ static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceCont
                 rebx_error(static_cast<struct rebx_extras*>(sim->extras), "Need to set d_factor, cs_coeff, tau_coeff parameters.  See examples in documentation.\n");
             if (!cs || !tc) return false;                                      // every particle returns a zero force
             e.scal[1] = *cs; e.scal[2] = *tc;
+        } else if (kind == REBX_B200_EXP_MIGRATION) {
+            e.scal[1] = sim->t;                                                 // exp(-t/tau), exponential_migration.c:96
         } else {
             const double* beta = get_d(force, "tIm_flaring_index");
             const double* h0 = get_d(force, "tIm_scale_height_1");
@@ -601,7 +620,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     for (const Entry& e : entries) {
         switch (e.kind) {
             case REBX_B200_RADIATION: need_vel = true; break;
-            case REBX_B200_HARMONICS: case REBX_B200_GR_POTENTIAL: need_m = true; break;
+            case REBX_B200_HARMONICS: case REBX_B200_GR_POTENTIAL: case REBX_B200_CENTRAL_FORCE: need_m = true; break;
             case REBX_B200_YARKOVSKY: need_vel = need_m = need_r = true; break;
             default: need_vel = need_m = true; break;     // damping trio and gr
         }
@@ -791,6 +810,8 @@ REBXB_ENTRY(rebx_radiation_forces)
 REBXB_ENTRY(rebx_gravitational_harmonics)
 REBXB_ENTRY(rebx_gr_potential)
 REBXB_ENTRY(rebx_gr)
+REBXB_ENTRY(rebx_central_force)
+REBXB_ENTRY(rebx_exponential_migration)
 REBXB_ENTRY(rebx_yarkovsky_effect)
 REBXB_ENTRY(rebx_modify_orbits_forces)
 REBXB_ENTRY(rebx_gas_damping_timescale)

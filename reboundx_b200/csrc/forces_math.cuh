@@ -465,4 +465,36 @@ __device__ __forceinline__ Vec3 type_I_migration(const rebx_b200_effect& fx, con
     return f;
 }
 
+// src/central_force.c:63-85: a += A r^(gamma-1) d ; the central body recoils by m/m_source of it
+__device__ __forceinline__ void central_force(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                              const Particle& p, Vec3& a, Vec3& red) {
+    const double A = body[REBX_B200_BODY_J2], gamma = body[REBX_B200_BODY_J4];     // slots 8, 9 of the record
+    const double dx = p.x - body[REBX_B200_BODY_X+0];
+    const double dy = p.y - body[REBX_B200_BODY_X+1];
+    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double r2 = dx*dx + dy*dy + dz*dz;
+    const double prefac = A*pow(r2, (gamma - 1.)/2.);
+    a.x += prefac*dx;  a.y += prefac*dy;  a.z += prefac*dz;
+    const double mr = p.m/body[REBX_B200_BODY_M];
+    red.x -= mr*prefac*dx;  red.y -= mr*prefac*dy;  red.z -= mr*prefac*dz;
+}
+
+// src/exponential_migration.c:61-100 (absent parameters: tau = inf, a_ini = 24, a_fin = 30, :65-67)
+__device__ __forceinline__ Vec3 exponential_migration(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                                      const Particle& p, double tau_tab, double aini_tab, double afin_tab) {
+    const Orbit o = orbit_from_particle<false, false, false>(fx.scal[0], p, body);
+    const double em_tau_a = is_absent(tau_tab) ? INFINITY : tau_tab;
+    const double em_aini = is_absent(aini_tab) ? 24. : aini_tab;
+    const double em_afin = is_absent(afin_tab) ? 30. : afin_tab;
+    const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
+    const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
+    const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    const double t = fx.scal[1];
+    Vec3 f;
+    f.x = (dvx/(2.*em_tau_a))*((em_afin - em_aini)/(o.a))*exp(-(t)/em_tau_a);
+    f.y = (dvy/(2.*em_tau_a))*((em_afin - em_aini)/(o.a))*exp(-(t)/em_tau_a);
+    f.z = (dvz/(2.*em_tau_a))*((em_afin - em_aini)/(o.a))*exp(-(t)/em_tau_a);
+    return f;
+}
+
 }  // namespace rebxb

@@ -135,6 +135,8 @@ __device__ __forceinline__ Vec3 damping_force(const rebx_b200_effect& fx, const 
         return gas_damping(fx, body, p, __ldcs(fx.tab[0] + k));
     } else if constexpr (K == REBX_B200_TYPE_I) {
         return type_I_migration(fx, body, p);
+    } else if constexpr (K == REBX_B200_EXP_MIGRATION) {
+        return exponential_migration(fx, body, p, __ldcs(fx.tab[0] + k), __ldcs(fx.tab[1] + k), __ldcs(fx.tab[2] + k));
     } else {
         return Vec3{0.0, 0.0, 0.0};
     }
@@ -216,7 +218,7 @@ typedef void (*jacobi_fn)(const rebx_b200_pass, const double*, double*, double*)
 struct JacobiCombo { int k[3]; jacobi_fn fn; };
 #define REBXB_JCOMBO(a, b, c) { {a, b, c}, jacobi_sweep_kernel<a, b, c> },
 static const JacobiCombo kJacobiCombos[] = {
-    REBXB_JCOMBO(5,0,0) REBXB_JCOMBO(6,0,0) REBXB_JCOMBO(7,0,0)
+    REBXB_JCOMBO(5,0,0) REBXB_JCOMBO(6,0,0) REBXB_JCOMBO(7,0,0) REBXB_JCOMBO(9,0,0)
     REBXB_JCOMBO(5,6,0) REBXB_JCOMBO(6,5,0) REBXB_JCOMBO(5,7,0) REBXB_JCOMBO(7,5,0) REBXB_JCOMBO(6,7,0) REBXB_JCOMBO(7,6,0)
     REBXB_JCOMBO(5,6,7) REBXB_JCOMBO(5,7,6) REBXB_JCOMBO(6,5,7) REBXB_JCOMBO(6,7,5) REBXB_JCOMBO(7,5,6) REBXB_JCOMBO(7,6,5)
 };

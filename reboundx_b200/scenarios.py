@@ -13,6 +13,7 @@ _PARTICLE_DOUBLES = {
                          "ye_emissivity", "ye_k", "ye_spin_axis_x", "ye_spin_axis_y", "ye_spin_axis_z"],
     "modify_orbits_forces": ["tau_a", "tau_e", "tau_inc"],
     "gas_damping_timescale": ["d_factor"],
+    "exponential_migration": ["em_tau_a", "em_aini", "em_afin"],
 }
 _FORCE_DOUBLES = {
     "radiation_forces": ["c"],
@@ -24,7 +25,7 @@ _FORCE_DOUBLES = {
     "type_I_migration": ["ide_position", "ide_width", "tIm_flaring_index", "tIm_surface_density_exponent",
                          "tIm_surface_density_1", "tIm_scale_height_1"],
 }
-_COM_FORCES = ("modify_orbits_forces", "gas_damping_timescale", "type_I_migration")
+_COM_FORCES = ("modify_orbits_forces", "gas_damping_timescale", "type_I_migration", "exponential_migration")
 
 
 def build(w, forces, lib=None, coordinates="PARTICLE", integrator="ias15", acc=None):
@@ -67,7 +68,14 @@ def build(w, forces, lib=None, coordinates="PARTICLE", integrator="ias15", acc=N
             if w.get("Omega") is not None:
                 p0["Omega"] = w["Omega"]
             done.add("J2")
+        if name == "central_force" and "Acentral" not in done:
+            p0 = rebx.particle_params(0)
+            p0["Acentral"] = w["Acentral"]
+            p0["gammacentral"] = w["gammacentral"]
+            done.add("Acentral")
         rebx.add_force(f)
+    if w.get("t") is not None:
+        sim.t = w["t"]
     return sim, rebx, handles
 
 

@@ -697,3 +697,39 @@ def test_device_integrate_force_against_the_reference_operator(built, scheme):
     else:
         assert np.array_equal(np.array(got[3:]), want)
     assert np.any(want != np.array([w["vx"], w["vy"], w["vz"]]))
+
+
+# ---- same-shape neighbouring forces --------------------------------------------
+@pytest.mark.parametrize("gamma", [-1.0, -1.7, 2.0])
+def test_central_force(built, gamma):
+    """reference src/central_force.c: a = A r^(gamma-1) d from a body carrying Acentral and gammacentral,
+    with recoil of that body.  pow() is not bit-reproducible between libdevice and glibc."""
+    from reboundx_b200 import workloads
+    w = workloads.circumplanetary_ring(30001, massive=True)
+    w["Acentral"], w["gammacentral"] = 3.0e-9*(1e8)**(-1.7 - gamma), gamma
+    acc0 = acc_variants(w, 12)["gravity"]
+    want, br = oracle_acc(w, ["central_force"], acc0)
+    got, _ = device_acc(w, ["central_force"], acc0)
+    e = errors(got, want, skip=(0,))
+    assert e["max_normwise"] <= TOL, e
+    assert e["frac_component_above_tol"] <= 1e-3, e
+    exact = np.array([acc0[k][0] for k in range(3)]) + br["central_force"][:3]
+    scale = br["central_force"][3:] + np.abs([acc0[k][0] for k in range(3)])
+    for k in range(3):
+        assert abs(got[k][0] - exact[k]) <= 1e-12*scale[k]
+
+
+@pytest.mark.parametrize("coordinates", ["PARTICLE", "JACOBI", "BARYCENTRIC"])
+def test_exponential_migration(built, coordinates):
+    """reference src/exponential_migration.c under rebx_com_force, all three coordinate systems;
+    the force depends on sim->t."""
+    from reboundx_b200 import workloads
+    n = 3000
+    w = workloads.planetesimal_disk(n)
+    w.update(em_tau_a=np.full(n, 2.0e4), em_aini=np.full(n, 1.0), em_afin=np.full(n, 1.5), t=321.5)
+    acc0 = acc_variants(w, 13)["gravity"]
+    want, _ = oracle_acc(w, ["exponential_migration"], acc0, coordinates)
+    got, _ = device_acc(w, ["exponential_migration"], acc0, coordinates)
+    e = errors(got, want, skip=(0,) if coordinates == "BARYCENTRIC" else ())
+    assert e["max_normwise"] <= TOL, e
+    assert np.max(np.abs(np.array(got) - np.array(acc0))) > 0
