@@ -43,7 +43,8 @@ enum rebx_b200_kind {
     REBX_B200_TYPE_I          = 7,  /* src/type_I_migration.c:115-203 under rebx_com_force */
     REBX_B200_CENTRAL_FORCE   = 8,  /* src/central_force.c:63-85 (one central body per entry)  [SURVEY 8f rank 3] */
     REBX_B200_EXP_MIGRATION   = 9,  /* src/exponential_migration.c:61-100 under rebx_com_force     [SURVEY 8f rank 3] */
-    REBX_B200_KIND_COUNT      = 10
+    REBX_B200_LENSE_THIRRING  = 10, /* src/lense_thirring.c:65-100                                 [SURVEY 8f rank 3] */
+    REBX_B200_KIND_COUNT      = 11
 };
 
 /* Body record (REBX_B200_BODY_DOUBLES doubles, device memory): the source / primary /
@@ -53,6 +54,7 @@ enum rebx_b200_kind {
  *   1..3   x y z     4..6  vx vy vz     7  m
  *   HARMONICS only: 8 J2, 9 J4 (0 when unset), 10 R_eq, 11..13 u-hat, 14..16 v-hat, 17..19 w-hat
  *   CENTRAL_FORCE only: 8 Acentral, 9 gammacentral
+ *   LENSE_THIRRING only: 8..10 spin angular momentum J = I*Omega of the source
  */
 enum { REBX_B200_BODY_INDEX = 0, REBX_B200_BODY_X = 1, REBX_B200_BODY_VX = 4, REBX_B200_BODY_M = 7,
        REBX_B200_BODY_J2 = 8, REBX_B200_BODY_J4 = 9, REBX_B200_BODY_REQ = 10,
@@ -87,6 +89,7 @@ typedef struct rebx_b200_state {
  *                                                               scal3 tIm_surface_density_1, scal4 tIm_surface_density_exponent,
  *                                                               scal5 ide_position, scal6 ide_width
  *   CENTRAL_FORCE -                                             (Acentral, gammacentral live in the body record)
+ *   LENSE_THIRRING -                                            scal0 G, scal1 lt_c*lt_c
  *   EXP_MIGRATION tab0 em_tau_a tab1 em_aini tab2 em_afin        scal0 G, scal1 sim->t
  * Tables are indexed like the state arrays (element k <-> global index index_base+k);
  * an unset double parameter holds REBX_B200_ABSENT_BITS. */

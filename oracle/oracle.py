@@ -135,6 +135,11 @@ def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE", n_active=-1):
             lib.oracle_central_force(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["m"]), c_int64(0),
                                      c_double(w["Acentral"]), c_double(w["gammacentral"]), _d(acc[0]), _d(acc[1]), _d(acc[2]), out)
             br[name] = np.array([float(v) for v in out])
+        elif name == "lense_thirring":
+            Om = (c_double*3)(*w["Omega"])
+            lib.oracle_lense_thirring(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]), _d(S["m"]),
+                                      c_double(w["G"]), c_double(w["lt_c"]), c_double(w["I"]), Om, _d(acc[0]), _d(acc[1]), _d(acc[2]), out)
+            br[name] = np.array([float(v) for v in out])
         elif name == "gr":
             lib.oracle_gr(c_int64(n), c_int64(n_active), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]),
                           _d(S["m"]), c_double(w["G"]), c_double(w["c"]), c_int(w.get("max_iterations") or 10),

@@ -251,6 +251,37 @@ void oracle_central_force(int64_t n, const double* x, const double* y, const dou
     if (br) { br[0] = bsx; br[1] = bsy; br[2] = bsz; br[3] = bax; br[4] = bay; br[5] = baz; }
 }
 
+/* reference src/lense_thirring.c:65-100 (source = particle 0 with spin angular momentum J = I*Omega) */
+void oracle_lense_thirring(int64_t n, const double* x, const double* y, const double* z,
+                           const double* vx, const double* vy, const double* vz, const double* m,
+                           double G, double c, double I, const double Omega[3], double* ax, double* ay, double* az, long double* br) {
+    const double C2 = c*c;
+    const double gamma = 1.000021;
+    const double sx = x[0], sy = y[0], sz = z[0], svx = vx[0], svy = vy[0], svz = vz[0], ms = m[0];
+    long double bs[3] = {0, 0, 0}, ba[3] = {0, 0, 0};
+    for (int64_t i = 1; i < n; i++) {
+        const double dx = x[i] - sx, dy = y[i] - sy, dz = z[i] - sz;
+        const double r2 = dx*dx + dy*dy + dz*dz;
+        const double r = sqrt(r2);
+        const double r3 = r2*r;
+        const double dvx = vx[i] - svx, dvy = vy[i] - svy, dvz = vz[i] - svz;
+        const double Jx = I*Omega[0], Jy = I*Omega[1], Jz = I*Omega[2];
+        const double mt = m[i];
+        const double mtot = ms + mt;
+        const double mratio = mt/ms;
+        const double Omega_fac = ms/mtot*(1. + gamma)*G/2/C2/r3;
+        const double Jdotr = Jx*dx + Jy*dy + Jz*dz;
+        const double Ox = Omega_fac*(-Jx + 3.*Jdotr*dx/r2);
+        const double Oy = Omega_fac*(-Jy + 3.*Jdotr*dy/r2);
+        const double Oz = Omega_fac*(-Jz + 3.*Jdotr*dz/r2);
+        ax[i] += 2.*(Oy*dvz - Oz*dvy); ay[i] += 2.*(Oz*dvx - Ox*dvz); az[i] += 2.*(Ox*dvy - Oy*dvx);
+        const double t[3] = {mratio*2.*(Oy*dvz - Oz*dvy), mratio*2.*(Oz*dvx - Ox*dvz), mratio*2.*(Ox*dvy - Oy*dvx)};
+        ax[0] -= t[0]; ay[0] -= t[1]; az[0] -= t[2];
+        for (int q = 0; q < 3; q++) { bs[q] -= (long double)t[q]; ba[q] += fabsl((long double)t[q]); }
+    }
+    if (br) { for (int q = 0; q < 3; q++) { br[q] = bs[q]; br[3 + q] = ba[q]; } }
+}
+
 /* ---- damping trio under rebx_com_force (reference src/rebxtools.c:66-147) ------------------ */
 enum { ORACLE_MODIFY_ORBITS = 5, ORACLE_GAS_DAMPING = 6, ORACLE_TYPE_I = 7, ORACLE_EXP_MIGRATION = 9 };
 enum { ORACLE_JACOBI = 0, ORACLE_BARYCENTRIC = 1, ORACLE_PARTICLE = 2 };

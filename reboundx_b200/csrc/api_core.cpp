@@ -372,6 +372,7 @@ struct rebx_force* rebx_load_force(struct rebx_extras* const rebx, const char* n
         {"gas_damping_timescale",   REBX_FORCE_VEL, rebx_gas_damping_timescale},
         {"type_I_migration",        REBX_FORCE_VEL, rebx_modify_orbits_with_type_I_migration},
         {"central_force",           REBX_FORCE_POS, rebx_central_force},
+        {"lense_thirring",          REBX_FORCE_VEL, rebx_lense_thirring},
         {"exponential_migration",   REBX_FORCE_VEL, rebx_exponential_migration},
     };
     struct rebx_force* force = rebx_create_force(rebx, name);

@@ -142,6 +142,7 @@ static int kind_of(const struct rebx_force* f) {
     if (fn == rebx_gr) return KIND_GR;
     if (fn == rebx_central_force) return REBX_B200_CENTRAL_FORCE;
     if (fn == rebx_exponential_migration) return REBX_B200_EXP_MIGRATION;
+    if (fn == rebx_lense_thirring) return REBX_B200_LENSE_THIRRING;
     return REBX_B200_NONE;
 }
 
@@ -384,6 +385,8 @@ struct Entry {
     const Oblate* ob = nullptr;
     bool reduces = false;
     int frame = 0;          // 0: body is a particle; 1: barycentre (second uniform sweep); 2: Jacobi (scan path); 3: gr
+    double extra[3] = {0, 0, 0};    // lense_thirring: spin angular momentum of the source (body record slots 8..10)
+    bool has_extra = false;
     int n_active = 0;       // gr only
     std::vector<struct reb_particle> gr_active;     // gr only: host result for the active bodies
 };
@@ -490,6 +493,21 @@ static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceCont
         out.push_back(e);
         return true;
     }
+    case REBX_B200_LENSE_THIRRING: {
+        const double* c = get_d(force, "lt_c");
+        if (!c) { reb_simulation_error(sim, "REBOUNDx Error: Need to set speed of light in LT effect.  See examples in documentation.\n"); return false; }
+        if (N < 2) return false;
+        // the source is particles[0]; it needs both its moment of inertia I and its spin vector Omega (lense_thirring.c:109-115)
+        const double* I = static_cast<const double*>(find_value(static_cast<struct rebx_node*>(particles[0].ap), "I"));
+        const struct reb_vec3d* Om = static_cast<const struct reb_vec3d*>(find_value(static_cast<struct rebx_node*>(particles[0].ap), "Omega"));
+        if (!I || !Om) return false;
+        e.scal[1] = (*c)*(*c);
+        e.body_index = 0; e.reduces = true;
+        e.extra[0] = (*I)*Om->x; e.extra[1] = (*I)*Om->y; e.extra[2] = (*I)*Om->z;
+        e.has_extra = true;
+        out.push_back(e);
+        return true;
+    }
     case KIND_GR: {
         const double* c = get_d(force, "c");
         if (!c) { reb_simulation_error(sim, "REBOUNDx Error: Need to set speed of light in gr effect.  See examples in documentation.\n"); return false; }
@@ -575,6 +593,7 @@ static void fill_body(double* rec, const Entry& e, const struct reb_particle* pa
     rec[REBX_B200_BODY_X+0] = b.x;  rec[REBX_B200_BODY_X+1] = b.y;  rec[REBX_B200_BODY_X+2] = b.z;
     rec[REBX_B200_BODY_VX+0] = b.vx; rec[REBX_B200_BODY_VX+1] = b.vy; rec[REBX_B200_BODY_VX+2] = b.vz;
     rec[REBX_B200_BODY_M] = b.m;
+    if (e.has_extra) { rec[8] = e.extra[0]; rec[9] = e.extra[1]; rec[10] = e.extra[2]; }
     if (e.ob) {
         rec[REBX_B200_BODY_J2] = e.ob->J2; rec[REBX_B200_BODY_J4] = e.ob->J4; rec[REBX_B200_BODY_REQ] = e.ob->Req;
         for (int j = 0; j < 3; j++) { rec[REBX_B200_BODY_U+j] = e.ob->u[j]; rec[REBX_B200_BODY_V+j] = e.ob->v[j]; rec[REBX_B200_BODY_W+j] = e.ob->w[j]; }
@@ -622,7 +641,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
             case REBX_B200_RADIATION: need_vel = true; break;
             case REBX_B200_HARMONICS: case REBX_B200_GR_POTENTIAL: case REBX_B200_CENTRAL_FORCE: need_m = true; break;
             case REBX_B200_YARKOVSKY: need_vel = need_m = need_r = true; break;
-            default: need_vel = need_m = true; break;     // damping trio and gr
+            default: need_vel = need_m = true; break;     // damping trio, gr, lense_thirring
         }
     }
     const rebx_b200_aos_layout L = {(int32_t)sizeof(struct reb_particle), (int32_t)offsetof(struct reb_particle, x),
@@ -812,6 +831,7 @@ REBXB_ENTRY(rebx_gr_potential)
 REBXB_ENTRY(rebx_gr)
 REBXB_ENTRY(rebx_central_force)
 REBXB_ENTRY(rebx_exponential_migration)
+REBXB_ENTRY(rebx_lense_thirring)
 REBXB_ENTRY(rebx_yarkovsky_effect)
 REBXB_ENTRY(rebx_modify_orbits_forces)
 REBXB_ENTRY(rebx_gas_damping_timescale)

@@ -479,6 +479,38 @@ __device__ __forceinline__ void central_force(const rebx_b200_effect& fx, const 
     red.x -= mr*prefac*dx;  red.y -= mr*prefac*dy;  red.z -= mr*prefac*dz;
 }
 
+// src/lense_thirring.c:65-100: gravitomagnetic acceleration 2 Omega_LT x v from the spin of particle 0
+__device__ __forceinline__ void lense_thirring(const rebx_b200_effect& fx, const double* __restrict__ body,
+                                               const Particle& p, Vec3& a, Vec3& red) {
+    const double G = fx.scal[0], C2 = fx.scal[1];
+    const double gamma = 1.000021;                               // Eddington-Robertson-Schiff parameter, hard-coded in the reference
+    const double dx = p.x - body[REBX_B200_BODY_X+0];
+    const double dy = p.y - body[REBX_B200_BODY_X+1];
+    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double r2 = dx*dx + dy*dy + dz*dz;
+    const double r = sqrt(r2);
+    const double r3 = r2*r;
+    const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
+    const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
+    const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    const double Jx = body[8], Jy = body[9], Jz = body[10];
+    const double ms = body[REBX_B200_BODY_M];
+    const double mt = p.m;
+    const double mtot = ms + mt;
+    const double mratio = mt/ms;
+    const double Omega_fac = ms/mtot*(1. + gamma)*G/2/C2/r3;
+    const double Jdotr = Jx*dx + Jy*dy + Jz*dz;
+    const double Omega_x = Omega_fac*(-Jx + 3.*Jdotr*dx/r2);
+    const double Omega_y = Omega_fac*(-Jy + 3.*Jdotr*dy/r2);
+    const double Omega_z = Omega_fac*(-Jz + 3.*Jdotr*dz/r2);
+    a.x += 2.*(Omega_y*dvz - Omega_z*dvy);
+    a.y += 2.*(Omega_z*dvx - Omega_x*dvz);
+    a.z += 2.*(Omega_x*dvy - Omega_y*dvx);
+    red.x -= mratio*2.*(Omega_y*dvz - Omega_z*dvy);
+    red.y -= mratio*2.*(Omega_z*dvx - Omega_x*dvz);
+    red.z -= mratio*2.*(Omega_x*dvy - Omega_y*dvx);
+}
+
 // src/exponential_migration.c:61-100 (absent parameters: tau = inf, a_ini = 24, a_fin = 30, :65-67)
 __device__ __forceinline__ Vec3 exponential_migration(const rebx_b200_effect& fx, const double* __restrict__ body,
                                                       const Particle& p, double tau_tab, double aini_tab, double afin_tab) {

@@ -19,6 +19,7 @@ _FORCE_DOUBLES = {
     "radiation_forces": ["c"],
     "gr_potential": ["c"],
     "gr": ["c"],
+    "lense_thirring": ["lt_c"],
     "yarkovsky_effect": ["ye_lstar", "ye_c", "ye_stef_boltz"],
     "modify_orbits_forces": ["ide_position", "ide_width"],
     "gas_damping_timescale": ["cs_coeff", "tau_coeff"],
@@ -68,6 +69,11 @@ def build(w, forces, lib=None, coordinates="PARTICLE", integrator="ias15", acc=N
             if w.get("Omega") is not None:
                 p0["Omega"] = w["Omega"]
             done.add("J2")
+        if name == "lense_thirring" and "I" not in done:
+            p0 = rebx.particle_params(0)
+            p0["I"] = w["I"]
+            p0["Omega"] = w["Omega"]
+            done.add("I")
         if name == "central_force" and "Acentral" not in done:
             p0 = rebx.particle_params(0)
             p0["Acentral"] = w["Acentral"]

@@ -733,3 +733,19 @@ def test_exponential_migration(built, coordinates):
     e = errors(got, want, skip=(0,) if coordinates == "BARYCENTRIC" else ())
     assert e["max_normwise"] <= TOL, e
     assert np.max(np.abs(np.array(got) - np.array(acc0))) > 0
+
+
+def test_lense_thirring_bit_exact(built):
+    """reference src/lense_thirring.c: + - * / sqrt only, so per-particle results are bit-identical."""
+    from reboundx_b200 import workloads
+    w = workloads.asteroid_ensemble(30001)
+    w.update(lt_c=w["c"], I=0.07*1.0*(4.65e-3)**2, Omega=(0.3, -0.4, 90.0))
+    acc0 = acc_variants(w, 14)["gravity"]
+    want, br = oracle_acc(w, ["lense_thirring"], acc0)
+    got, _ = device_acc(w, ["lense_thirring"], acc0)
+    assert errors(got, want, skip=(0,))["bit_identical"]
+    exact = np.array([acc0[k][0] for k in range(3)]) + br["lense_thirring"][:3]
+    scale = br["lense_thirring"][3:] + np.abs([acc0[k][0] for k in range(3)])
+    for k in range(3):
+        assert abs(got[k][0] - exact[k]) <= 1e-12*scale[k]
+    assert np.any(np.array(got)[:, 1:] != np.array(acc0)[:, 1:])
