@@ -104,10 +104,15 @@ typedef struct rebx_b200_effect {
                                `body` (add it to the body's acceleration), or NULL to discard */
 } rebx_b200_effect;
 
+/* pass.reserved bit: every effect of the pass refers to the SAME central body (identical position,
+ * velocity and mass in all body records).  Lets the fused sweep share the relative coordinates and the
+ * orbit elements between stacked effects; results are unchanged. */
+#define REBX_B200_PASS_SHARED_BODY 1
+
 typedef struct rebx_b200_pass {
     rebx_b200_state st;
     int32_t n_effects;
-    int32_t reserved;
+    int32_t reserved;                             /* REBX_B200_PASS_* bits */
     rebx_b200_effect fx[REBX_B200_MAX_EFFECTS];   /* applied in array order */
 } rebx_b200_pass;
 

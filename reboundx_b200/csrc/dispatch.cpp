@@ -742,6 +742,11 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
             std::memset(&P, 0, sizeof P);
             P.st = st;
             P.n_effects = (int32_t)(e1 - e0);
+            {   // one central body for the whole group => the sweep may share its relative coordinates
+                bool same = true;
+                for (size_t j = e0 + 1; j < e1; j++) if (entries[j].body_index != entries[e0].body_index) same = false;
+                if (same) P.reserved |= REBX_B200_PASS_SHARED_BODY;
+            }
             for (int j = 0; j < P.n_effects; j++) {
                 const Entry& en = entries[e0 + j];
                 rebx_b200_effect& fx = P.fx[j];

@@ -20,6 +20,14 @@ constexpr double kPi5    = kPi*kPi*kPi*kPi*kPi;          // M_PI*M_PI*M_PI*M_PI*
 constexpr double kTiny   = 1.E-308;
 
 struct Particle { double x, y, z, vx, vy, vz, m, r; };
+// Position, velocity and mass of the body an effect refers to, held in REGISTERS: stacked effects that
+// share one central body then share one Origin, and the compiler can merge their common sub-expressions
+// (values re-read from shared memory after every libdevice / division slow-path call could not be).
+struct Origin { double x, y, z, vx, vy, vz, m; };
+__device__ __forceinline__ Origin load_origin(const double* __restrict__ rec) {
+    return Origin{rec[REBX_B200_BODY_X+0], rec[REBX_B200_BODY_X+1], rec[REBX_B200_BODY_X+2],
+                  rec[REBX_B200_BODY_VX+0], rec[REBX_B200_BODY_VX+1], rec[REBX_B200_BODY_VX+2], rec[REBX_B200_BODY_M]};
+}
 struct Vec3     { double x, y, z; };
 
 __device__ __forceinline__ bool is_absent(double v) {
@@ -54,10 +62,10 @@ struct FastMath {
 struct Pre { ExactRecip rc; unsigned rc_bad; double c, k0, k1; };
 
 template <int K>
-__device__ __forceinline__ Pre prepare(const rebx_b200_effect& fx, const double* __restrict__ body) {
+__device__ __forceinline__ Pre prepare(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body) {
     Pre pre;
     pre.rc.b = 1.0; pre.rc.y = 1.0; pre.rc_bad = 0u; pre.c = 1.0; pre.k0 = 0.0; pre.k1 = 0.0;
-    const double bm = body[REBX_B200_BODY_M];
+    const double bm = org.m;
     if constexpr (K == REBX_B200_RADIATION) {
         pre.c = fx.scal[1];
         pre.rc = exact_rcp(pre.c, pre.rc_bad);           // RN(1/c), shared by the four divisions by c
@@ -89,19 +97,19 @@ __device__ __forceinline__ double mass_ratio(double m, double bm) {
 struct Orbit { double a, e, inc, P; };
 
 template <bool WANT_E, bool WANT_INC, bool WANT_P>
-__device__ __forceinline__ Orbit orbit_from_particle(double G, const Particle& p, const double* __restrict__ body) {
+__device__ __forceinline__ Orbit orbit_from_particle(double G, const Particle& p, const Origin& org, const double* __restrict__ body) {
     Orbit o;
     const double nan = __longlong_as_double(0x7ff8000000000000LL);
     o.a = nan; o.e = nan; o.inc = nan; o.P = nan;
-    const double bm = body[REBX_B200_BODY_M];
+    const double bm = org.m;
     if (bm <= kTiny) return o;                          // primary has no mass
     const double mu = G*(p.m + bm);
-    const double dx = p.x - body[REBX_B200_BODY_X+0];
-    const double dy = p.y - body[REBX_B200_BODY_X+1];
-    const double dz = p.z - body[REBX_B200_BODY_X+2];
-    const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
-    const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
-    const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    const double dx = p.x - org.x;
+    const double dy = p.y - org.y;
+    const double dz = p.z - org.z;
+    const double dvx = p.vx - org.vx;
+    const double dvy = p.vy - org.vy;
+    const double dvz = p.vz - org.vz;
     const double d = sqrt(dx*dx + dy*dy + dz*dz);
     const double vsquared = dvx*dvx + dvy*dvy + dvz*dvz;
     const double vcircsquared = mu/d;
@@ -156,20 +164,20 @@ template <> __device__ __forceinline__ double div_c<FastMath>(double a, const Pr
 
 // src/radiation_forces.c:69-98
 template <class M>
-__device__ __forceinline__ void radiation(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
+__device__ __forceinline__ void radiation(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body, const Pre& pre,
                                           const Particle& p, double beta, Vec3& a, unsigned& bad) {
     const bool absent = is_absent(beta);
     if constexpr (M::straight_line) beta = absent ? 0.0 : beta;     // keep the marker NaN out of the arithmetic; result discarded below
     else if (absent) return;                                        // a particle without beta feels nothing (radiation_forces.c:78)
     const double mu = pre.k0;
-    const double dx = p.x - body[REBX_B200_BODY_X+0];
-    const double dy = p.y - body[REBX_B200_BODY_X+1];
-    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double dx = p.x - org.x;
+    const double dy = p.y - org.y;
+    const double dz = p.z - org.z;
     const double dr = M::sqrt_(dx*dx + dy*dy + dz*dz, bad);
     const typename M::R rdr = M::rcp(dr, bad);
-    const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
-    const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
-    const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    const double dvx = p.vx - org.vx;
+    const double dvy = p.vy - org.vy;
+    const double dvz = p.vz - org.vz;
     const double rdot = M::div(dx*dvx + dy*dvy + dz*dvz, rdr, bad);
     const double a_rad = M::div(beta*mu, M::rcp(dr*dr, bad), bad);
     const double k1 = 1. - div_c<M>(rdot, pre, bad);
@@ -187,17 +195,17 @@ __device__ __forceinline__ void radiation(const rebx_b200_effect& fx, const doub
 
 // src/gravitational_harmonics.c:184-224 with j2_func :72-86 and j4_func :88-102
 template <class M>
-__device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
+__device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body, const Pre& pre,
                                           const Particle& p, Vec3& a, Vec3& red, unsigned& bad) {
-    const double bm  = body[REBX_B200_BODY_M];
+    const double bm  = org.m;
     const double J4  = body[REBX_B200_BODY_J4];
     const double ux = body[REBX_B200_BODY_U+0], uy = body[REBX_B200_BODY_U+1], uz = body[REBX_B200_BODY_U+2];
     const double vx = body[REBX_B200_BODY_V+0], vy = body[REBX_B200_BODY_V+1], vz = body[REBX_B200_BODY_V+2];
     const double wx = body[REBX_B200_BODY_W+0], wy = body[REBX_B200_BODY_W+1], wz = body[REBX_B200_BODY_W+2];
 
-    const double dx = p.x - body[REBX_B200_BODY_X+0];
-    const double dy = p.y - body[REBX_B200_BODY_X+1];
-    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double dx = p.x - org.x;
+    const double dy = p.y - org.y;
+    const double dz = p.z - org.z;
     const double r2 = dx*dx + dy*dy + dz*dz;
     const double r  = M::sqrt_(r2, bad);
     const typename M::R rr2 = M::rcp(r2, bad), rr = M::rcp(r, bad);
@@ -234,16 +242,16 @@ __device__ __forceinline__ void harmonics(const rebx_b200_effect& fx, const doub
 
 // src/gr_potential.c:60-78
 template <class M>
-__device__ __forceinline__ void gr_potential(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
+__device__ __forceinline__ void gr_potential(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body, const Pre& pre,
                                              const Particle& p, Vec3& a, Vec3& red, unsigned& bad) {
     const double prefac1 = pre.k0;
-    const double dx = p.x - body[REBX_B200_BODY_X+0];
-    const double dy = p.y - body[REBX_B200_BODY_X+1];
-    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double dx = p.x - org.x;
+    const double dy = p.y - org.y;
+    const double dz = p.z - org.z;
     const double r2 = dx*dx + dy*dy + dz*dz;
     const double prefac = M::div(prefac1, M::rcp(r2*r2, bad), bad);
     a.x -= prefac*dx;  a.y -= prefac*dy;  a.z -= prefac*dz;
-    const double mr = mass_ratio(p.m, body[REBX_B200_BODY_M]);
+    const double mr = mass_ratio(p.m, org.m);
     red.x += mr*prefac*dx;  red.y += mr*prefac*dy;  red.z += mr*prefac*dz;
 }
 
@@ -252,18 +260,18 @@ __device__ __forceinline__ void gr_potential(const rebx_b200_effect& fx, const d
 // missing, or a flag value the reference leaves undefined).
 struct YarkParams { double density, rot_period, Gamma, albedo, emissivity, k, sx, sy, sz; };
 
-__device__ __forceinline__ void yarkovsky(const rebx_b200_effect& fx, const double* __restrict__ body, const Pre& pre,
+__device__ __forceinline__ void yarkovsky(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body, const Pre& pre,
                                           const Particle& p, const YarkParams& yp, int code, Vec3& a) {
     if (code == 2 || p.r == 0) return;
     const double G = fx.scal[0], lstar = fx.scal[1], c = fx.scal[2], stef_boltz = fx.scal[3];
     const double radius = p.r;
     const double q_yar = 1.0 - yp.albedo;
-    const double dx = p.x - body[REBX_B200_BODY_X+0];
-    const double dy = p.y - body[REBX_B200_BODY_X+1];
-    const double dz = p.z - body[REBX_B200_BODY_X+2];
-    const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
-    const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
-    const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    const double dx = p.x - org.x;
+    const double dy = p.y - org.y;
+    const double dz = p.z - org.z;
+    const double dvx = p.vx - org.vx;
+    const double dvy = p.vy - org.vy;
+    const double dvz = p.vz - org.vz;
     const double distance = sqrt((dx*dx) + (dy*dy) + (dz*dz));
     const double rdotv = ((dx*dvx) + (dy*dvy) + (dz*dvz))/(c*distance);
     const double i0 = ((1 - rdotv)*(dx/distance)) - (dvx/c);
@@ -276,7 +284,7 @@ __device__ __forceinline__ void yarkovsky(const rebx_b200_effect& fx, const doub
         mag = (3*q_yar*lstar)/(64*kPi*radius*yp.density*c*distance*distance);
         if (code == 1) Y[1][0] = 1.0; else Y[0][1] = 1.0;
     } else {
-        const Orbit o = orbit_from_particle<false, false, true>(G, p, body);
+        const Orbit o = orbit_from_particle<false, false, true>(G, p, org, body);
         mag = (3*yp.k*q_yar*lstar)/(16*kPi*radius*yp.density*c*distance*distance);
         const double sx = yp.sx, sy = yp.sy, sz = yp.sz;
         const double Smag = sqrt((sx*sx) + sy*sy + sz*sz);
@@ -331,10 +339,10 @@ __device__ __forceinline__ void yarkovsky(const rebx_b200_effect& fx, const doub
 // Shared tail of rebx_com_force for one particle (src/rebxtools.c:101-141):
 // PARTICLE coordinates  : p.a += f ; p.a -= mr f ; body.a -= mr f   with mr = m/(M+m)
 // BARYCENTRIC           : p.a += f ;                all.a  -= mr f   with mr = m/M  (second sweep)
-__device__ __forceinline__ void com_force_tail(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ void com_force_tail(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
                                                const Particle& p, const Vec3& f, Vec3& a, Vec3& red) {
     a.x += f.x;  a.y += f.y;  a.z += f.z;
-    const double M = body[REBX_B200_BODY_M];
+    const double M = org.m;
     if (fx.flags & REBX_B200_FLAG_BARYCENTRIC) {
         const double mr = p.m/M;
         red.x -= mr*f.x;  red.y -= mr*f.y;  red.z -= mr*f.z;
@@ -346,28 +354,28 @@ __device__ __forceinline__ void com_force_tail(const rebx_b200_effect& fx, const
 }
 
 struct Rel { double dx, dy, dz, dvx, dvy, dvz, r2; };
-__device__ __forceinline__ Rel relative(const Particle& p, const double* __restrict__ body) {
+__device__ __forceinline__ Rel relative(const Particle& p, const Origin& org, const double* __restrict__ body) {
     Rel q;
-    q.dvx = p.vx - body[REBX_B200_BODY_VX+0];
-    q.dvy = p.vy - body[REBX_B200_BODY_VX+1];
-    q.dvz = p.vz - body[REBX_B200_BODY_VX+2];
-    q.dx = p.x - body[REBX_B200_BODY_X+0];
-    q.dy = p.y - body[REBX_B200_BODY_X+1];
-    q.dz = p.z - body[REBX_B200_BODY_X+2];
+    q.dvx = p.vx - org.vx;
+    q.dvy = p.vy - org.vy;
+    q.dvz = p.vz - org.vz;
+    q.dx = p.x - org.x;
+    q.dy = p.y - org.y;
+    q.dz = p.z - org.z;
     q.r2 = q.dx*q.dx + q.dy*q.dy + q.dz*q.dz;
     return q;
 }
 
 // src/modify_orbits_forces.c:77-128
-__device__ __forceinline__ Vec3 modify_orbits(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ Vec3 modify_orbits(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
                                               const Particle& p, double tau_a_tab, double tau_e_tab, double tau_inc_tab) {
     double invtau_a = 0.0;
     double tau_e = INFINITY, tau_inc = INFINITY;
-    const Rel q = relative(p, body);
+    const Rel q = relative(p, org, body);
     if (!is_absent(tau_a_tab)) {
         invtau_a = 1.0/tau_a_tab;
         if (fx.flags & REBX_B200_FLAG_TRAP) {
-            const Orbit o = orbit_from_particle<false, false, false>(fx.scal[0], p, body);
+            const Orbit o = orbit_from_particle<false, false, false>(fx.scal[0], p, org, body);
             invtau_a *= planet_trap(o.a, fx.scal[1], fx.scal[2]);
         }
     }
@@ -388,15 +396,15 @@ __device__ __forceinline__ Vec3 modify_orbits(const rebx_b200_effect& fx, const 
 }
 
 // src/gas_damping_timescale.c:67-130.  d_factor absent => zero force (the host raises the error).
-__device__ __forceinline__ Vec3 gas_damping(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ Vec3 gas_damping(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
                                             const Particle& p, double d_factor) {
     Vec3 f = {0.0, 0.0, 0.0};
     if (is_absent(d_factor)) return f;
     const double G = fx.scal[0], cs_coeff = fx.scal[1], tau_coeff = fx.scal[2];
-    const Orbit o = orbit_from_particle<true, true, false>(G, p, body);
-    const Rel q = relative(p, body);
+    const Orbit o = orbit_from_particle<true, true, false>(G, p, org, body);
+    const Rel q = relative(p, org, body);
     const double a0 = o.a, e0 = o.e, inc0 = o.inc;
-    const double starMass = body[REBX_B200_BODY_M];
+    const double starMass = org.m;
     const double planetMass = p.m;
     double coeff;
     const double vk = sqrt(G*starMass/a0);
@@ -423,14 +431,14 @@ __device__ __forceinline__ Vec3 gas_damping(const rebx_b200_effect& fx, const do
 }
 
 // src/type_I_migration.c:69-113 (time-scale fits) and :115-203
-__device__ __forceinline__ Vec3 type_I_migration(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ Vec3 type_I_migration(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
                                                  const Particle& p) {
     const double G = fx.scal[0], beta = fx.scal[1], h0 = fx.scal[2], sd0 = fx.scal[3], s = fx.scal[4];
     const double dedge = fx.scal[5], hedge = fx.scal[6];
-    const Orbit o = orbit_from_particle<true, true, false>(G, p, body);
+    const Orbit o = orbit_from_particle<true, true, false>(G, p, org, body);
     const double a0 = o.a, e0 = o.e, inc0 = o.inc;
-    const double mp = p.m, ms = body[REBX_B200_BODY_M];
-    const Rel q = relative(p, body);
+    const double mp = p.m, ms = org.m;
+    const Rel q = relative(p, org, body);
 
     const double h  = h0*pow(q.r2, beta/2);
     const double h2 = h*h;
@@ -466,35 +474,35 @@ __device__ __forceinline__ Vec3 type_I_migration(const rebx_b200_effect& fx, con
 }
 
 // src/central_force.c:63-85: a += A r^(gamma-1) d ; the central body recoils by m/m_source of it
-__device__ __forceinline__ void central_force(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ void central_force(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
                                               const Particle& p, Vec3& a, Vec3& red) {
     const double A = body[REBX_B200_BODY_J2], gamma = body[REBX_B200_BODY_J4];     // slots 8, 9 of the record
-    const double dx = p.x - body[REBX_B200_BODY_X+0];
-    const double dy = p.y - body[REBX_B200_BODY_X+1];
-    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double dx = p.x - org.x;
+    const double dy = p.y - org.y;
+    const double dz = p.z - org.z;
     const double r2 = dx*dx + dy*dy + dz*dz;
     const double prefac = A*pow(r2, (gamma - 1.)/2.);
     a.x += prefac*dx;  a.y += prefac*dy;  a.z += prefac*dz;
-    const double mr = p.m/body[REBX_B200_BODY_M];
+    const double mr = p.m/org.m;
     red.x -= mr*prefac*dx;  red.y -= mr*prefac*dy;  red.z -= mr*prefac*dz;
 }
 
 // src/lense_thirring.c:65-100: gravitomagnetic acceleration 2 Omega_LT x v from the spin of particle 0
-__device__ __forceinline__ void lense_thirring(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ void lense_thirring(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
                                                const Particle& p, Vec3& a, Vec3& red) {
     const double G = fx.scal[0], C2 = fx.scal[1];
     const double gamma = 1.000021;                               // Eddington-Robertson-Schiff parameter, hard-coded in the reference
-    const double dx = p.x - body[REBX_B200_BODY_X+0];
-    const double dy = p.y - body[REBX_B200_BODY_X+1];
-    const double dz = p.z - body[REBX_B200_BODY_X+2];
+    const double dx = p.x - org.x;
+    const double dy = p.y - org.y;
+    const double dz = p.z - org.z;
     const double r2 = dx*dx + dy*dy + dz*dz;
     const double r = sqrt(r2);
     const double r3 = r2*r;
-    const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
-    const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
-    const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    const double dvx = p.vx - org.vx;
+    const double dvy = p.vy - org.vy;
+    const double dvz = p.vz - org.vz;
     const double Jx = body[8], Jy = body[9], Jz = body[10];
-    const double ms = body[REBX_B200_BODY_M];
+    const double ms = org.m;
     const double mt = p.m;
     const double mtot = ms + mt;
     const double mratio = mt/ms;
@@ -512,15 +520,15 @@ __device__ __forceinline__ void lense_thirring(const rebx_b200_effect& fx, const
 }
 
 // src/exponential_migration.c:61-100 (absent parameters: tau = inf, a_ini = 24, a_fin = 30, :65-67)
-__device__ __forceinline__ Vec3 exponential_migration(const rebx_b200_effect& fx, const double* __restrict__ body,
+__device__ __forceinline__ Vec3 exponential_migration(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
                                                       const Particle& p, double tau_tab, double aini_tab, double afin_tab) {
-    const Orbit o = orbit_from_particle<false, false, false>(fx.scal[0], p, body);
+    const Orbit o = orbit_from_particle<false, false, false>(fx.scal[0], p, org, body);
     const double em_tau_a = is_absent(tau_tab) ? INFINITY : tau_tab;
     const double em_aini = is_absent(aini_tab) ? 24. : aini_tab;
     const double em_afin = is_absent(afin_tab) ? 30. : afin_tab;
-    const double dvx = p.vx - body[REBX_B200_BODY_VX+0];
-    const double dvy = p.vy - body[REBX_B200_BODY_VX+1];
-    const double dvz = p.vz - body[REBX_B200_BODY_VX+2];
+    const double dvx = p.vx - org.vx;
+    const double dvy = p.vy - org.vy;
+    const double dvz = p.vz - org.vz;
     const double t = fx.scal[1];
     Vec3 f;
     f.x = (dvx/(2.*em_tau_a))*((em_afin - em_aini)/(o.a))*exp(-(t)/em_tau_a);

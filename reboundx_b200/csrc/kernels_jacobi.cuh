@@ -128,15 +128,15 @@ __global__ void com_body_kernel(const double* __restrict__ totals, double* __res
 
 // ---- Jacobi sweep --------------------------------------------------------------------------------
 template <int K>
-__device__ __forceinline__ Vec3 damping_force(const rebx_b200_effect& fx, const double* __restrict__ body, const Particle& p, int64_t k) {
+__device__ __forceinline__ Vec3 damping_force(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body, const Particle& p, int64_t k) {
     if constexpr (K == REBX_B200_MODIFY_ORBITS) {
-        return modify_orbits(fx, body, p, __ldcs(fx.tab[0] + k), __ldcs(fx.tab[1] + k), __ldcs(fx.tab[2] + k));
+        return modify_orbits(fx, org, body, p, __ldcs(fx.tab[0] + k), __ldcs(fx.tab[1] + k), __ldcs(fx.tab[2] + k));
     } else if constexpr (K == REBX_B200_GAS_DAMPING) {
-        return gas_damping(fx, body, p, __ldcs(fx.tab[0] + k));
+        return gas_damping(fx, org, body, p, __ldcs(fx.tab[0] + k));
     } else if constexpr (K == REBX_B200_TYPE_I) {
-        return type_I_migration(fx, body, p);
+        return type_I_migration(fx, org, body, p);
     } else if constexpr (K == REBX_B200_EXP_MIGRATION) {
-        return exponential_migration(fx, body, p, __ldcs(fx.tab[0] + k), __ldcs(fx.tab[1] + k), __ldcs(fx.tab[2] + k));
+        return exponential_migration(fx, org, body, p, __ldcs(fx.tab[0] + k), __ldcs(fx.tab[1] + k), __ldcs(fx.tab[2] + k));
     } else {
         return Vec3{0.0, 0.0, 0.0};
     }
@@ -175,14 +175,15 @@ jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __re
         Vec3 a = {st.ax[k], st.ay[k], st.az[k]};
         const double mr = p.m/(M + p.m);
         Vec3 f;
-        f = damping_force<K0>(P.fx[0], body, p, k);
+        const Origin org = load_origin(body);
+        f = damping_force<K0>(P.fx[0], org, body, p, k);
         a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
         if constexpr (K1 != 0) {
-            f = damping_force<K1>(P.fx[1], body, p, k);
+            f = damping_force<K1>(P.fx[1], org, body, p, k);
             a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
         }
         if constexpr (K2 != 0) {
-            f = damping_force<K2>(P.fx[2], body, p, k);
+            f = damping_force<K2>(P.fx[2], org, body, p, k);
             a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
         }
         st.ax[k] = a.x; st.ay[k] = a.y; st.az[k] = a.z;

@@ -158,6 +158,7 @@ class Shard:
         for k in ("x", "y", "z", "vx", "vy", "vz", "m", "r", "ax", "ay", "az"):
             setattr(P.st, k, self.state[k].data_ptr())
         P.n_effects = len(self.kinds)
+        P.reserved = 1          # REBX_B200_PASS_SHARED_BODY: every effect of a Shard refers to the central body (index 0)
         for e, kind in enumerate(self.kinds):
             fx = P.fx[e]
             fx.kind, fx.flags = kind, self.flags[e]
