@@ -161,6 +161,12 @@ void rebx_central_force(struct reb_simulation* const sim, struct rebx_force* con
 void rebx_lense_thirring(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);        /* src/lense_thirring.c:102 */
 void rebx_exponential_migration(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N); /* src/exponential_migration.c:103 */
 
+/* Diagnostic potentials of the device-backed effects: reference
+ * src/reboundx.h:553,575,582; reduced on the device. */
+double rebx_gr_potential_potential(struct rebx_extras* const rebx, const struct rebx_force* const gr_potential);
+double rebx_gravitational_harmonics_potential(struct rebx_extras* const rebx);
+double rebx_central_force_potential(struct rebx_extras* const rebx);
+
 /* Host scalar helpers: reference src/reboundx.h:497,510; src/inner_disk_edge.c:61 */
 double rebx_rad_calc_beta(const double G, const double c, const double source_mass, const double source_luminosity, const double radius, const double density, const double Q_pr);
 double rebx_rad_calc_particle_radius(const double G, const double c, const double source_mass, const double source_luminosity, const double beta, const double density, const double Q_pr);

@@ -169,6 +169,15 @@ int rebx_b200_gr_pull(const rebx_b200_state* st, const rebx_b200_gr_args* args, 
  * fixed-point iteration ran 10 times without converging (the reference's warning, gr.c:130-133). */
 int rebx_b200_gr_sweep(const rebx_b200_state* st, const rebx_b200_gr_args* args, int* not_converged, void* stream, int* launches);
 
+/* ---- diagnostic potentials -------------------------------------------
+ * *potential (device double) = this shard's part of the interaction potential of ONE effect entry
+ * (`fx->kind` in GR_POTENTIAL, HARMONICS, CENTRAL_FORCE; fields as for the force sweep):
+ *   GR_POTENTIAL   -sum_i 3 (G m_0)^2/c^2 m_i / r_i^2                 reference src/gr_potential.c:91-120
+ *   HARMONICS      sum_j J2 and J4 terms of body `fx->body`            reference src/gravitational_harmonics.c:228-316
+ *   CENTRAL_FORCE  -sum_i m_i A r^(gamma+1)/(gamma+1)  (log for -1)    reference src/central_force.c:98-121
+ * A sharded caller all-reduces the result. */
+int rebx_b200_potential(const rebx_b200_state* st, const rebx_b200_effect* fx, double* potential, void* workspace, void* stream, int* launches);
+
 /* Barycentric second sweep: a[k] += delta[0..2] for every particle in the shard. */
 int rebx_b200_add_uniform(const rebx_b200_state* st, const double* delta, void* stream, int* launches);
 

@@ -820,11 +820,107 @@ failed:
     }
 }
 
+// Diagnostic potentials (reference src/gr_potential.c:91-120, src/gravitational_harmonics.c:254-316,
+// src/central_force.c:98-135): the whole ensemble goes to the device once, one reduction per body.
+static double run_potential(struct rebx_extras* rebx, int kind, const struct rebx_force* force) {
+    if (rebx == nullptr || rebx->sim == nullptr) { rebx_error(rebx, ""); return 0; }
+    struct reb_simulation* sim = rebx->sim;
+    const size_t N = sim->N;
+    struct reb_particle* particles = sim->particles;
+    if (N < 2) return 0;
+    Side* side = side_of(rebx);
+    std::string why;
+    DeviceContext* ctx = ensure_ctx(side, why);
+    if (!ctx) {
+        std::string msg = "REBOUNDx-B200 Error: " + why + ". The potentials of this library are reduced on the GPU only.\n";
+        reb_simulation_error(sim, msg.c_str());
+        return 0;
+    }
+    std::vector<Entry> entries;
+    Entry e;
+    e.kind = kind; e.scal[0] = sim->G;
+    if (kind == REBX_B200_GR_POTENTIAL) {
+        const double* c = force ? static_cast<const double*>(find_value(force->ap, "c")) : nullptr;
+        if (!c) { rebx_error(rebx, "REBOUNDx Error: Need to set speed of light in gr effect.  See examples in documentation.\n"); return 0; }
+        e.scal[1] = (*c)*(*c); e.body_index = 0;
+        entries.push_back(e);
+    } else {
+        // keyed by the extras address: these potentials take no force argument in the reference API
+        ForceTables& T = tables_for(side, ctx, reinterpret_cast<struct rebx_force*>(rebx), kind, particles, N, ctx->tables);
+        e.T = &T;
+        for (size_t b = 0; b < T.bodies.size(); b++) { e.body_index = T.bodies[b]; e.ob = &T.oblate[b]; entries.push_back(e); }
+    }
+    if (entries.empty()) return 0;
+    const char* fail = nullptr;
+    cudaError_t fail_code = cudaSuccess;
+    const size_t ne = entries.size();
+    const size_t stride = (N + 1) & ~size_t(1);
+    const rebx_b200_aos_layout L = {(int32_t)sizeof(struct reb_particle), (int32_t)offsetof(struct reb_particle, x),
+                                    (int32_t)offsetof(struct reb_particle, vx), (int32_t)offsetof(struct reb_particle, ax),
+                                    (int32_t)offsetof(struct reb_particle, m), (int32_t)offsetof(struct reb_particle, r)};
+    int launches = 0;
+    double total = 0.0;
+    cudaStream_t s = ctx->stream[0];
+    double* base = nullptr;
+    double* out_h = nullptr;
+    rebx_b200_state st;
+    REBXB_CUDA(ctx->aos[0].ensure(N*sizeof(struct reb_particle)), "allocating AoS staging");
+    REBXB_CUDA(ctx->soa[0].ensure(11*stride*sizeof(double)), "allocating SoA state");
+    REBXB_CUDA(ctx->work[0].ensure(rebx_b200_workspace_bytes()), "allocating reduction scratch");
+    REBXB_CUDA(ctx->bodies_h.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating pinned body records");
+    REBXB_CUDA(ctx->bodies.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating body records");
+    REBXB_CUDA(ctx->br_h.ensure(ne*sizeof(double)), "allocating pinned results");
+    REBXB_CUDA(ctx->br.ensure(ne*sizeof(double)), "allocating results");
+    for (size_t k = 0; k < ne; k++) fill_body(static_cast<double*>(ctx->bodies_h.p) + k*REBX_B200_BODY_DOUBLES, entries[k], particles);
+    REBXB_CUDA(cudaMemcpyAsync(ctx->bodies.p, ctx->bodies_h.p, ne*REBX_B200_BODY_DOUBLES*sizeof(double), cudaMemcpyHostToDevice, s), "copying body records");
+    REBXB_CUDA(cudaMemcpyAsync(ctx->aos[0].p, particles, N*sizeof(struct reb_particle), cudaMemcpyHostToDevice, s), "copying particles to the device");
+    ctx->stats.h2d_bytes += N*sizeof(struct reb_particle);
+    base = static_cast<double*>(ctx->soa[0].p);
+    std::memset(&st, 0, sizeof st);
+    st.n = (int64_t)N; st.index_base = 0;
+    st.x = base; st.y = base + stride; st.z = base + 2*stride; st.m = base + 6*stride;
+    st.ax = base + 8*stride; st.ay = base + 9*stride; st.az = base + 10*stride;
+    REBXB_CUDA((cudaError_t)rebx_b200_unpack_aos(ctx->aos[0].p, &L, &st, s, &launches), "unpacking particles");
+    for (size_t k = 0; k < ne; k++) {
+        rebx_b200_effect fx;
+        std::memset(&fx, 0, sizeof fx);
+        fx.kind = kind;
+        fx.body = static_cast<const double*>(ctx->bodies.p) + k*REBX_B200_BODY_DOUBLES;
+        for (int q = 0; q < REBX_B200_MAX_SCALARS; q++) fx.scal[q] = entries[k].scal[q];
+        REBXB_CUDA((cudaError_t)rebx_b200_potential(&st, &fx, static_cast<double*>(ctx->br.p) + k, ctx->work[0].p, s, &launches), "reducing the potential");
+    }
+    out_h = static_cast<double*>(ctx->br_h.p);
+    REBXB_CUDA(cudaMemcpyAsync(out_h, ctx->br.p, ne*sizeof(double), cudaMemcpyDeviceToHost, s), "copying the potential");
+    REBXB_CUDA(cudaStreamSynchronize(s), "waiting for the device");
+    ctx->stats.launches += (std::uint64_t)launches;
+    for (size_t k = 0; k < ne; k++) total += out_h[k];
+    return total;
+failed:
+    {
+        cudaGetLastError();
+        char buf[400];
+        snprintf(buf, sizeof buf, "REBOUNDx-B200 Error: CUDA failure while %s: %s.\n", fail, cudaGetErrorString(fail_code));
+        reb_simulation_error(sim, buf);
+        cudaStreamSynchronize(ctx->stream[0]); cudaGetLastError();
+    }
+    return 0;
+}
+
 }  // namespace rebxh
 
 using namespace rebxh;
 
 extern "C" {
+
+double rebx_gr_potential_potential(struct rebx_extras* const rebx, const struct rebx_force* const gr_potential) {
+    return run_potential(rebx, REBX_B200_GR_POTENTIAL, gr_potential);
+}
+double rebx_gravitational_harmonics_potential(struct rebx_extras* const rebx) {
+    return run_potential(rebx, REBX_B200_HARMONICS, nullptr);
+}
+double rebx_central_force_potential(struct rebx_extras* const rebx) {
+    return run_potential(rebx, REBX_B200_CENTRAL_FORCE, nullptr);
+}
 
 // ---- plug-in entry points: the reference's force signature, one fused sweep each ---------------
 #define REBXB_ENTRY(fn) \

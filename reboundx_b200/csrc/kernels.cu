@@ -704,6 +704,72 @@ __global__ void gather_bodies_kernel(rebx_b200_state st, double* __restrict__ bo
     if (st.m) rec[REBX_B200_BODY_M] = st.m[k];
 }
 
+// ---- diagnostic potentials: one reduction over the shard ---------------------------------------------
+__global__ void __launch_bounds__(kThreads)
+potential_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_effect fx, double* __restrict__ partials) {
+    __shared__ double s_body[REBX_B200_BODY_DOUBLES];
+    __shared__ double s_sum[kThreads];
+    if (threadIdx.x < REBX_B200_BODY_DOUBLES) s_body[threadIdx.x] = fx.body[threadIdx.x];
+    __syncthreads();
+    const long long bi = (long long)s_body[REBX_B200_BODY_INDEX];
+    const double bx = s_body[REBX_B200_BODY_X], by = s_body[REBX_B200_BODY_X+1], bz = s_body[REBX_B200_BODY_X+2], bm = s_body[REBX_B200_BODY_M];
+    const double G = fx.scal[0];
+    double H = 0.0;
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < st.n; k += stride) {
+        if (st.index_base + k == bi) continue;
+        const double dx = st.x[k] - bx, dy = st.y[k] - by, dz = st.z[k] - bz;
+        const double r2 = dx*dx + dy*dy + dz*dz;
+        const double mj = st.m[k];
+        if (fx.kind == REBX_B200_GR_POTENTIAL) {
+            const double mu = G*bm;
+            const double prefac = 3.*mu*mu/fx.scal[1];
+            H -= prefac*mj/r2;
+        } else if (fx.kind == REBX_B200_HARMONICS) {
+            const double r = sqrt(r2);
+            const double dw = s_body[REBX_B200_BODY_W]*dx + s_body[REBX_B200_BODY_W+1]*dy + s_body[REBX_B200_BODY_W+2]*dz;
+            const double costheta = dw/r;
+            const double c2 = costheta*costheta;
+            const double J2 = s_body[REBX_B200_BODY_J2], J4 = s_body[REBX_B200_BODY_J4], R = s_body[REBX_B200_BODY_REQ];
+            {
+                const double f1 = G*bm*mj*J2*R*R/r2/r;
+                const double f2 = 1.0/2.0*(3.0*c2 - 1.0);
+                H += f1*f2;
+            }
+            if (J4 != 0.0) {
+                const double f1 = G*bm*mj*J4*R*R*R*R/r2/r2/r;
+                const double f2 = 1.0/8.0*(35.0*c2*c2 - 30.0*c2 + 3.0);
+                H += f1*f2;
+            }
+        } else {    // CENTRAL_FORCE
+            const double A = s_body[REBX_B200_BODY_J2], gamma = s_body[REBX_B200_BODY_J4];
+            if (fabs(gamma + 1.) < 2.220446049250313e-16) H -= mj*A*log(sqrt(r2));
+            else H -= mj*A*pow(r2, (gamma + 1.)/2.)/(gamma + 1.);
+        }
+    }
+    s_sum[threadIdx.x] = H;
+    __syncthreads();
+    for (int w = kThreads/2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) s_sum[threadIdx.x] += s_sum[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) partials[blockIdx.x] = s_sum[0];
+}
+
+__global__ void __launch_bounds__(kThreads)
+potential_finalize_kernel(const double* __restrict__ partials, int nblocks, double* __restrict__ out) {
+    __shared__ double s_sum[kThreads];
+    double acc = 0.0;
+    for (int b = threadIdx.x; b < nblocks; b += kThreads) acc += partials[b];
+    s_sum[threadIdx.x] = acc;
+    __syncthreads();
+    for (int w = kThreads/2; w > 0; w >>= 1) {
+        if (threadIdx.x < w) s_sum[threadIdx.x] += s_sum[threadIdx.x + w];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) *out = s_sum[0];
+}
+
 // ---- integrate_force schemes: element-wise stage updates --------------------------------------------
 struct V3 { double *x, *y, *z; };
 struct CV3 { const double *x, *y, *z; };
@@ -1108,6 +1174,19 @@ int rebx_b200_gr_sweep(const rebx_b200_state* st, const rebx_b200_gr_args* args,
     gr_sweep_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(*st, *args, not_converged);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+int rebx_b200_potential(const rebx_b200_state* st, const rebx_b200_effect* fx, double* potential, void* workspace, void* stream, int* launches) {
+    if (!st || !fx || !potential || !workspace || !fx->body || !st->x || !st->m) return cudaErrorInvalidValue;
+    if (fx->kind != REBX_B200_GR_POTENTIAL && fx->kind != REBX_B200_HARMONICS && fx->kind != REBX_B200_CENTRAL_FORCE) return cudaErrorInvalidValue;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (st->n == 0) return cudaMemsetAsync(potential, 0, sizeof(double), s);
+    int grid = grid_for(reinterpret_cast<const void*>(potential_kernel), st->n);
+    potential_kernel<<<grid, kThreads, 0, s>>>(*st, *fx, static_cast<double*>(workspace));
+    potential_finalize_kernel<<<1, kThreads, 0, s>>>(static_cast<const double*>(workspace), grid, potential);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) *launches += 2;
     return err;
 }
 

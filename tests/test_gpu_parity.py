@@ -749,3 +749,39 @@ def test_lense_thirring_bit_exact(built):
     for k in range(3):
         assert abs(got[k][0] - exact[k]) <= 1e-12*scale[k]
     assert np.any(np.array(got)[:, 1:] != np.array(acc0)[:, 1:])
+
+
+@pytest.mark.parametrize("which", ["gr_potential", "gravitational_harmonics", "central_force", "central_force_log"])
+def test_device_potentials_match_the_reference(built, which):
+    """rebx_gr_potential_potential / rebx_gravitational_harmonics_potential /
+    rebx_central_force_potential reduced on the device, against the reference's functions in oracle/_ref.
+    The reference sums sequentially; the tolerance is relative to the sum of |terms| (all terms of these
+    potentials have one sign for gr_potential / central_force, so that is |H| itself there)."""
+    import ctypes
+    from oracle import oracle
+    from reboundx_b200 import scenarios, workloads
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    w = workloads.circumplanetary_ring(20001, massive=True, tilted=True)
+    name = "central_force" if which.startswith("central") else which
+    if name == "central_force":
+        w["Acentral"], w["gammacentral"] = 3.0e-9, (-1.0 if which.endswith("log") else -1.7)
+    vals = []
+    for lib in (oracle.ref_lib(), None):
+        sim, rebx, handles = scenarios.build(w, [name], lib=lib)
+        L = rebx._lib
+        for fn in ("rebx_gr_potential_potential", "rebx_gravitational_harmonics_potential", "rebx_central_force_potential"):
+            getattr(L, fn).restype = ctypes.c_double
+        if name == "gr_potential":
+            H = L.rebx_gr_potential_potential(rebx._ptr, handles[name]._ptr)
+        elif name == "gravitational_harmonics":
+            H = L.rebx_gravitational_harmonics_potential(rebx._ptr)
+        else:
+            H = L.rebx_central_force_potential(rebx._ptr)
+        sim.process_messages()
+        vals.append(H)
+        rebx.detach(); sim.free()
+    ref, got = vals
+    assert ref != 0.0
+    # harmonics terms change sign with latitude; their absolute sum is bounded by ~|J2 term| sum ~ a few |H|
+    assert abs(got - ref) <= (1e-13 if name != "gravitational_harmonics" else 1e-11)*abs(ref), (ref, got)
