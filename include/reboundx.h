@@ -159,6 +159,7 @@ void rebx_modify_orbits_with_type_I_migration(struct reb_simulation* const sim, 
 /* Widened per SURVEY.md section 8f rank 3 (same-shape neighbouring forces): */
 void rebx_central_force(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);         /* src/central_force.c:87 */
 void rebx_lense_thirring(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N);        /* src/lense_thirring.c:102 */
+void rebx_gas_dynamical_friction(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N); /* src/gas_dynamical_friction.c:139 */
 void rebx_exponential_migration(struct reb_simulation* const sim, struct rebx_force* const force, struct reb_particle* const particles, const int N); /* src/exponential_migration.c:103 */
 
 /* Diagnostic potentials of the device-backed effects: reference

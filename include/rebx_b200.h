@@ -44,7 +44,8 @@ enum rebx_b200_kind {
     REBX_B200_CENTRAL_FORCE   = 8,  /* src/central_force.c:63-85 (one central body per entry)  [SURVEY 8f rank 3] */
     REBX_B200_EXP_MIGRATION   = 9,  /* src/exponential_migration.c:61-100 under rebx_com_force     [SURVEY 8f rank 3] */
     REBX_B200_LENSE_THIRRING  = 10, /* src/lense_thirring.c:65-100                                 [SURVEY 8f rank 3] */
-    REBX_B200_KIND_COUNT      = 11
+    REBX_B200_GAS_DF          = 11, /* src/gas_dynamical_friction.c:66-137                         [SURVEY 8f rank 3] */
+    REBX_B200_KIND_COUNT      = 12
 };
 
 /* Body record (REBX_B200_BODY_DOUBLES doubles, device memory): the source / primary /
@@ -89,6 +90,8 @@ typedef struct rebx_b200_state {
  *                                                               scal3 tIm_surface_density_1, scal4 tIm_surface_density_exponent,
  *                                                               scal5 ide_position, scal6 ide_width
  *   CENTRAL_FORCE -                                             (Acentral, gammacentral live in the body record)
+ *   GAS_DF        -                                             scal0 G, scal1 gas_df_rhog, scal2 gas_df_alpha_rhog, scal3 gas_df_cs,
+ *                                                               scal4 gas_df_alpha_cs, scal5 gas_df_xmin, scal6 gas_df_hr, scal7 gas_df_Qd
  *   LENSE_THIRRING -                                            scal0 G, scal1 lt_c*lt_c
  *   EXP_MIGRATION tab0 em_tau_a tab1 em_aini tab2 em_afin        scal0 G, scal1 sim->t
  * Tables are indexed like the state arrays (element k <-> global index index_base+k);

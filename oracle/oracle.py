@@ -26,6 +26,7 @@ PORT_PATH = os.path.join(_HERE, "liboracle_forces.so")
 
 YARK_PARAMS = ["ye_body_density", "ye_rotation_period", "ye_thermal_inertia", "ye_albedo", "ye_emissivity",
                "ye_k", "ye_spin_axis_x", "ye_spin_axis_y", "ye_spin_axis_z"]
+GAS_DF_PARAMS = ["gas_df_rhog", "gas_df_alpha_rhog", "gas_df_cs", "gas_df_alpha_cs", "gas_df_xmin", "gas_df_hr", "gas_df_Qd"]
 KIND = {"modify_orbits_forces": 5, "gas_damping_timescale": 6, "type_I_migration": 7, "exponential_migration": 9}
 COORD = {"JACOBI": 0, "BARYCENTRIC": 1, "PARTICLE": 2}
 
@@ -135,6 +136,10 @@ def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE", n_active=-1):
             lib.oracle_central_force(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["m"]), c_int64(0),
                                      c_double(w["Acentral"]), c_double(w["gammacentral"]), _d(acc[0]), _d(acc[1]), _d(acc[2]), out)
             br[name] = np.array([float(v) for v in out])
+        elif name == "gas_dynamical_friction":
+            par = (c_double*7)(*[w[k] for k in GAS_DF_PARAMS])
+            lib.oracle_gas_dynamical_friction(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]),
+                                              _d(S["m"]), _d(S["r"]), c_double(w["G"]), par, _d(acc[0]), _d(acc[1]), _d(acc[2]))
         elif name == "lense_thirring":
             Om = (c_double*3)(*w["Omega"])
             lib.oracle_lense_thirring(c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]), _d(S["m"]),

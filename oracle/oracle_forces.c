@@ -282,6 +282,37 @@ void oracle_lense_thirring(int64_t n, const double* x, const double* y, const do
     if (br) { for (int q = 0; q < 3; q++) { br[q] = bs[q]; br[3 + q] = ba[q]; } }
 }
 
+/* reference src/gas_dynamical_friction.c:66-137 (gaseous disc around particle 0; par = rhog, alpha_rhog,
+ * cs, alpha_cs, xmin, hr, Qd) */
+void oracle_gas_dynamical_friction(int64_t n, const double* x, const double* y, const double* z,
+                                   const double* vx, const double* vy, const double* vz, const double* m, const double* rad,
+                                   double G, const double par[7], double* ax, double* ay, double* az) {
+    const double rhog = par[0], alpha_rhog = par[1], cs = par[2], alpha_cs = par[3], xmin = par[4], hr = par[5], Qd = par[6];
+    for (int64_t i = 1; i < n; i++) {
+        const double dx = x[i] - x[0], dy = y[i] - y[0], dz = z[i] - z[0];
+        const double dvx = vx[i] - vx[0], dvy = vy[i] - vy[0], dvz = vz[i] - vz[0];
+        const double rcyl = sqrt(dx*dx + dy*dy);
+        const double sin_phi = dy/rcyl, cos_phi = dx/rcyl;
+        const double vk = sqrt(G*m[0]/rcyl)*(1.0 - hr*hr);
+        const double v0 = dvx + vk*sin_phi, v1 = dvy - vk*cos_phi, v2 = dvz;
+        const double vrel_norm = sqrt(v0*v0 + v1*v1 + v2*v2);
+        const double mach = vrel_norm/(cs*pow(rcyl, alpha_cs));
+        const double coul = log(1.0/xmin);
+        double integ;
+        if (mach >= 1.0) integ = coul;
+        else {
+            const double sub = (mach < 0.02) ? mach*mach*mach/3. + mach*mach*mach*mach*mach/5. : 0.5*log((1.0 + mach)/(1.0 - mach)) - mach;
+            integ = fmin(coul, sub);
+        }
+        const double h = hr*rcyl;
+        const double vert = (fabs(dz) < (10*h)) ? exp(-dz*dz/(2.0*h*h)) : 0;
+        const double rhog_loc = rhog*pow(rcyl, alpha_rhog)*vert;
+        const double mp = m[i], rstar = rad[i];
+        const double fc = 4.*M_PI*(G*G)*mp*(rhog_loc)/(vrel_norm*vrel_norm*vrel_norm)*integ + M_PI*rhog_loc*rstar*rstar*vrel_norm*Qd/mp;
+        ax[i] -= fc*v0; ay[i] -= fc*v1; az[i] -= fc*v2;
+    }
+}
+
 /* ---- damping trio under rebx_com_force (reference src/rebxtools.c:66-147) ------------------ */
 enum { ORACLE_MODIFY_ORBITS = 5, ORACLE_GAS_DAMPING = 6, ORACLE_TYPE_I = 7, ORACLE_EXP_MIGRATION = 9 };
 enum { ORACLE_JACOBI = 0, ORACLE_BARYCENTRIC = 1, ORACLE_PARTICLE = 2 };

@@ -6,7 +6,6 @@
 #include <stdio.h>
 #include <stdlib.h>
 #define STUB(name) void name(void){ fprintf(stderr, "oracle/_ref: out-of-scope effect '%s' called\n", #name); abort(); }
-STUB(rebx_gas_dynamical_friction)
 STUB(rebx_gr_full) STUB(rebx_stochastic_forces)
 STUB(rebx_tides_constant_time_lag) STUB(rebx_tides_dynamical) STUB(rebx_tides_spin)
 STUB(rebx_modify_mass) STUB(rebx_modify_orbits_direct) STUB(rebx_track_min_distance)

@@ -373,6 +373,7 @@ struct rebx_force* rebx_load_force(struct rebx_extras* const rebx, const char* n
         {"type_I_migration",        REBX_FORCE_VEL, rebx_modify_orbits_with_type_I_migration},
         {"central_force",           REBX_FORCE_POS, rebx_central_force},
         {"lense_thirring",          REBX_FORCE_VEL, rebx_lense_thirring},
+        {"gas_dynamical_friction",  REBX_FORCE_VEL, rebx_gas_dynamical_friction},
         {"exponential_migration",   REBX_FORCE_VEL, rebx_exponential_migration},
     };
     struct rebx_force* force = rebx_create_force(rebx, name);

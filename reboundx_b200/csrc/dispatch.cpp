@@ -143,6 +143,7 @@ static int kind_of(const struct rebx_force* f) {
     if (fn == rebx_central_force) return REBX_B200_CENTRAL_FORCE;
     if (fn == rebx_exponential_migration) return REBX_B200_EXP_MIGRATION;
     if (fn == rebx_lense_thirring) return REBX_B200_LENSE_THIRRING;
+    if (fn == rebx_gas_dynamical_friction) return REBX_B200_GAS_DF;
     return REBX_B200_NONE;
 }
 
@@ -508,6 +509,21 @@ static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceCont
         out.push_back(e);
         return true;
     }
+    case REBX_B200_GAS_DF: {
+        static const char* const names[7] = {"gas_df_rhog", "gas_df_alpha_rhog", "gas_df_cs", "gas_df_alpha_cs", "gas_df_xmin", "gas_df_hr", "gas_df_Qd"};
+        static const char* const msgs[7] = {"Need to specify a gas density\n", "Need to specify a profile for gas density\n", "Need to set a sound speed.\n",
+                                            "Need to specify a profile for the sound speed\n", "Need to set a cutoff.\n", "Need an aspect ratio.\n", "Need to specify Qd"};
+        bool ok = true;
+        for (int q = 0; q < 7; q++) {
+            const double* v = get_d(force, names[q]);
+            if (!v) { reb_simulation_error(sim, msgs[q]); ok = false; }       // the reference reports and then dereferences NULL (gas_dynamical_friction.c:141-173)
+            else e.scal[1 + q] = *v;
+        }
+        if (!ok || N < 2) return false;
+        e.body_index = 0;
+        out.push_back(e);
+        return true;
+    }
     case KIND_GR: {
         const double* c = get_d(force, "c");
         if (!c) { reb_simulation_error(sim, "REBOUNDx Error: Need to set speed of light in gr effect.  See examples in documentation.\n"); return false; }
@@ -640,7 +656,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         switch (e.kind) {
             case REBX_B200_RADIATION: need_vel = true; break;
             case REBX_B200_HARMONICS: case REBX_B200_GR_POTENTIAL: case REBX_B200_CENTRAL_FORCE: need_m = true; break;
-            case REBX_B200_YARKOVSKY: need_vel = need_m = need_r = true; break;
+            case REBX_B200_YARKOVSKY: case REBX_B200_GAS_DF: need_vel = need_m = need_r = true; break;
             default: need_vel = need_m = true; break;     // damping trio, gr, lense_thirring
         }
     }
@@ -933,6 +949,7 @@ REBXB_ENTRY(rebx_gr)
 REBXB_ENTRY(rebx_central_force)
 REBXB_ENTRY(rebx_exponential_migration)
 REBXB_ENTRY(rebx_lense_thirring)
+REBXB_ENTRY(rebx_gas_dynamical_friction)
 REBXB_ENTRY(rebx_yarkovsky_effect)
 REBXB_ENTRY(rebx_modify_orbits_forces)
 REBXB_ENTRY(rebx_gas_damping_timescale)

@@ -519,6 +519,37 @@ __device__ __forceinline__ void lense_thirring(const rebx_b200_effect& fx, const
     red.z -= mratio*2.*(Omega_x*dvy - Omega_y*dvx);
 }
 
+// src/gas_dynamical_friction.c:66-137: Ostriker dynamical friction + geometric drag in a gaseous disc
+// around particle 0 (no back-reaction)
+__device__ __forceinline__ void gas_dynamical_friction(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
+                                                       const Particle& p, Vec3& a) {
+    const double G = fx.scal[0], rhog = fx.scal[1], alpha_rhog = fx.scal[2], cs = fx.scal[3], alpha_cs = fx.scal[4];
+    const double xmin = fx.scal[5], hr = fx.scal[6], Qd = fx.scal[7];
+    const double dx = p.x - org.x, dy = p.y - org.y, dz = p.z - org.z;
+    const double dvx = p.vx - org.vx, dvy = p.vy - org.vy, dvz = p.vz - org.vz;
+    const double rcyl = sqrt(dx*dx + dy*dy);
+    // get_vrel_disk (:90-100): velocity relative to the sub-Keplerian gas
+    const double sin_phi = dy/rcyl, cos_phi = dx/rcyl;
+    const double vk = sqrt(G*org.m/rcyl)*(1.0 - hr*hr);
+    const double v0 = dvx + vk*sin_phi, v1 = dvy - vk*cos_phi, v2 = dvz;
+    const double vrel_norm = sqrt(v0*v0 + v1*v1 + v2*v2);
+    const double mach = vrel_norm/(cs*pow(rcyl, alpha_cs));
+    // calculate_pre_factor (:79-88) with mach_piece_sub (:67-76)
+    const double coul = log(1.0/xmin);
+    double integ;
+    if (mach >= 1.0) integ = coul;
+    else {
+        const double sub = (mach < 0.02) ? mach*mach*mach/3. + mach*mach*mach*mach*mach/5. : 0.5*log((1.0 + mach)/(1.0 - mach)) - mach;
+        integ = fmin(coul, sub);
+    }
+    const double h = hr*rcyl;
+    const double vert = (fabs(dz) < (10*h)) ? exp(-dz*dz/(2.0*h*h)) : 0;
+    const double rhog_loc = rhog*pow(rcyl, alpha_rhog)*vert;
+    const double mp = p.m, rstar = p.r;
+    const double fc = 4.*kPi*(G*G)*mp*(rhog_loc)/(vrel_norm*vrel_norm*vrel_norm)*integ + kPi*rhog_loc*rstar*rstar*vrel_norm*Qd/mp;
+    a.x -= fc*v0;  a.y -= fc*v1;  a.z -= fc*v2;
+}
+
 // src/exponential_migration.c:61-100 (absent parameters: tau = inf, a_ini = 24, a_fin = 30, :65-67)
 __device__ __forceinline__ Vec3 exponential_migration(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
                                                       const Particle& p, double tau_tab, double aini_tab, double afin_tab) {

@@ -48,6 +48,7 @@ template <> struct Traits<REBX_B200_GAS_DAMPING>   { static constexpr bool vel=t
 template <> struct Traits<REBX_B200_TYPE_I>        { static constexpr bool vel=true,  mass=true,  rad=false, red=true;  static constexpr int ntab=0; static constexpr bool itab=false; };
 template <> struct Traits<REBX_B200_CENTRAL_FORCE> { static constexpr bool vel=false, mass=true,  rad=false, red=true;  static constexpr int ntab=0; static constexpr bool itab=false; };
 template <> struct Traits<REBX_B200_LENSE_THIRRING> { static constexpr bool vel=true, mass=true,  rad=false, red=true;  static constexpr int ntab=0; static constexpr bool itab=false; };
+template <> struct Traits<REBX_B200_GAS_DF>        { static constexpr bool vel=true,  mass=true,  rad=true,  red=false; static constexpr int ntab=0; static constexpr bool itab=false; };
 template <> struct Traits<REBX_B200_EXP_MIGRATION> { static constexpr bool vel=true,  mass=true,  rad=false, red=true;  static constexpr int ntab=3; static constexpr bool itab=false; };
 
 // ---- vector loads / stores with streaming hints ------------------------------------------
@@ -127,6 +128,8 @@ __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const Origin& 
         com_force_tail(fx, org, body, p, f, a, red);
     } else if constexpr (K == REBX_B200_LENSE_THIRRING) {
         lense_thirring(fx, org, body, p, a, red);
+    } else if constexpr (K == REBX_B200_GAS_DF) {
+        gas_dynamical_friction(fx, org, body, p, a);
     }
 }
 
@@ -883,7 +886,7 @@ struct Combo { int k[4]; pass_fn fn[2][2]; bool red[4]; pass_fn tma; int tma_sme
 static Combo kCombos[] = {
     // every effect alone (any other stack falls back to consecutive single sweeps, still in list order)
     REBXB_COMBO(1,0,0,0) REBXB_COMBO(2,0,0,0) REBXB_COMBO(3,0,0,0) REBXB_COMBO(4,0,0,0)
-    REBXB_COMBO(5,0,0,0) REBXB_COMBO(6,0,0,0) REBXB_COMBO(7,0,0,0) REBXB_COMBO(8,0,0,0) REBXB_COMBO(9,0,0,0) REBXB_COMBO(10,0,0,0)
+    REBXB_COMBO(5,0,0,0) REBXB_COMBO(6,0,0,0) REBXB_COMBO(7,0,0,0) REBXB_COMBO(8,0,0,0) REBXB_COMBO(9,0,0,0) REBXB_COMBO(10,0,0,0) REBXB_COMBO(11,0,0,0)
     // config 3: J2/J4 (+) gr_potential, either LIFO order
     REBXB_COMBO(2,3,0,0) REBXB_COMBO(3,2,0,0)
     // config 4: yarkovsky (+) gr_potential
@@ -964,7 +967,7 @@ static int check_pass(const rebx_b200_pass& P) {
         bool vel = false, mass = false, rad = false; int ntab = 0; bool itab = false;
         switch (fx.kind) {
 #define REBXB_CASE(K) case K: vel = Traits<K>::vel; mass = Traits<K>::mass; rad = Traits<K>::rad; ntab = Traits<K>::ntab; itab = Traits<K>::itab; break;
-            REBXB_CASE(1) REBXB_CASE(2) REBXB_CASE(3) REBXB_CASE(4) REBXB_CASE(5) REBXB_CASE(6) REBXB_CASE(7) REBXB_CASE(8) REBXB_CASE(9) REBXB_CASE(10)
+            REBXB_CASE(1) REBXB_CASE(2) REBXB_CASE(3) REBXB_CASE(4) REBXB_CASE(5) REBXB_CASE(6) REBXB_CASE(7) REBXB_CASE(8) REBXB_CASE(9) REBXB_CASE(10) REBXB_CASE(11)
 #undef REBXB_CASE
         }
         if (vel && (!P.st.vx || !P.st.vy || !P.st.vz)) return cudaErrorInvalidValue;

@@ -111,6 +111,7 @@ struct reb_orbit reb_orbit_from_particle_err(double G, struct reb_particle p, st
 struct reb_orbit reb_orbit_from_particle(double G, struct reb_particle p, struct reb_particle primary);
 struct reb_particle reb_simulation_com(struct reb_simulation* r);
 struct reb_particle reb_particle_com_of_pair(struct reb_particle p1, struct reb_particle p2);
+void reb_particle_isub(struct reb_particle* p1, struct reb_particle* p2);      /* p1 -= p2 (used by src/gas_dynamical_friction.c:113) */
 
 void reb_transformations_inertial_to_jacobi_posvel(const struct reb_particle* const particles, struct reb_particle* const p_j, const struct reb_particle* const p_mass, const size_t N, const size_t N_active);
 void reb_transformations_inertial_to_jacobi_posvelacc(const struct reb_particle* const particles, struct reb_particle* const p_j, const struct reb_particle* const p_mass, const size_t N, const size_t N_active);

@@ -209,6 +209,13 @@ struct reb_particle reb_particle_com_of_pair(struct reb_particle p1, struct reb_
     return p1;
 }
 
+void reb_particle_isub(struct reb_particle* p1, struct reb_particle* p2){
+    p1->x -= p2->x;   p1->y -= p2->y;   p1->z -= p2->z;
+    p1->vx -= p2->vx; p1->vy -= p2->vy; p1->vz -= p2->vz;
+    p1->ax -= p2->ax; p1->ay -= p2->ay; p1->az -= p2->az;
+    p1->m -= p2->m;
+}
+
 struct reb_particle reb_simulation_com(struct reb_simulation* r){
     struct reb_particle com;
     memset(&com, 0, sizeof(com));

@@ -20,6 +20,7 @@ _FORCE_DOUBLES = {
     "gr_potential": ["c"],
     "gr": ["c"],
     "lense_thirring": ["lt_c"],
+    "gas_dynamical_friction": ["gas_df_rhog", "gas_df_alpha_rhog", "gas_df_cs", "gas_df_alpha_cs", "gas_df_xmin", "gas_df_hr", "gas_df_Qd"],
     "yarkovsky_effect": ["ye_lstar", "ye_c", "ye_stef_boltz"],
     "modify_orbits_forces": ["ide_position", "ide_width"],
     "gas_damping_timescale": ["cs_coeff", "tau_coeff"],

@@ -785,3 +785,19 @@ def test_device_potentials_match_the_reference(built, which):
     assert ref != 0.0
     # harmonics terms change sign with latitude; their absolute sum is bounded by ~|J2 term| sum ~ a few |H|
     assert abs(got - ref) <= (1e-13 if name != "gravitational_harmonics" else 1e-11)*abs(ref), (ref, got)
+
+
+def test_gas_dynamical_friction(built):
+    """reference src/gas_dynamical_friction.c (units of its example: G = 4 pi^2, disc around a central mass)."""
+    from reboundx_b200 import workloads
+    w = workloads.asteroid_ensemble(30001)
+    w["m"][1:] = 10.0**np.random.default_rng(2).uniform(-8, -5, 30001)
+    w["r"][1:] = 1e-5
+    w.update(gas_df_rhog=0.2, gas_df_alpha_rhog=-1.5, gas_df_cs=0.6, gas_df_alpha_cs=-0.5, gas_df_xmin=0.045, gas_df_hr=0.01, gas_df_Qd=5.0)
+    acc0 = acc_variants(w, 15)["gravity"]
+    want, _ = oracle_acc(w, ["gas_dynamical_friction"], acc0)
+    got, _ = device_acc(w, ["gas_dynamical_friction"], acc0)
+    e = errors(got, want)
+    assert e["max_normwise"] <= TOL, e
+    assert e["frac_component_above_tol"] <= 1e-3, e
+    assert np.any(np.array(got)[:, 1:] != np.array(acc0)[:, 1:])
