@@ -368,14 +368,15 @@ __device__ __forceinline__ Rel relative(const Particle& p, const Origin& org, co
 
 // src/modify_orbits_forces.c:77-128
 __device__ __forceinline__ Vec3 modify_orbits(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
-                                              const Particle& p, double tau_a_tab, double tau_e_tab, double tau_inc_tab) {
+                                              const Particle& p, double tau_a_tab, double tau_e_tab, double tau_inc_tab,
+                                              const Orbit* so = nullptr) {
     double invtau_a = 0.0;
     double tau_e = INFINITY, tau_inc = INFINITY;
     const Rel q = relative(p, org, body);
     if (!is_absent(tau_a_tab)) {
         invtau_a = 1.0/tau_a_tab;
         if (fx.flags & REBX_B200_FLAG_TRAP) {
-            const Orbit o = orbit_from_particle<false, false, false>(fx.scal[0], p, org, body);
+            const Orbit o = so ? *so : orbit_from_particle<false, false, false>(fx.scal[0], p, org, body);
             invtau_a *= planet_trap(o.a, fx.scal[1], fx.scal[2]);
         }
     }
@@ -397,11 +398,11 @@ __device__ __forceinline__ Vec3 modify_orbits(const rebx_b200_effect& fx, const 
 
 // src/gas_damping_timescale.c:67-130.  d_factor absent => zero force (the host raises the error).
 __device__ __forceinline__ Vec3 gas_damping(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
-                                            const Particle& p, double d_factor) {
+                                            const Particle& p, double d_factor, const Orbit* so = nullptr) {
     Vec3 f = {0.0, 0.0, 0.0};
     if (is_absent(d_factor)) return f;
     const double G = fx.scal[0], cs_coeff = fx.scal[1], tau_coeff = fx.scal[2];
-    const Orbit o = orbit_from_particle<true, true, false>(G, p, org, body);
+    const Orbit o = so ? *so : orbit_from_particle<true, true, false>(G, p, org, body);
     const Rel q = relative(p, org, body);
     const double a0 = o.a, e0 = o.e, inc0 = o.inc;
     const double starMass = org.m;
@@ -432,10 +433,10 @@ __device__ __forceinline__ Vec3 gas_damping(const rebx_b200_effect& fx, const Or
 
 // src/type_I_migration.c:69-113 (time-scale fits) and :115-203
 __device__ __forceinline__ Vec3 type_I_migration(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
-                                                 const Particle& p) {
+                                                 const Particle& p, const Orbit* so = nullptr) {
     const double G = fx.scal[0], beta = fx.scal[1], h0 = fx.scal[2], sd0 = fx.scal[3], s = fx.scal[4];
     const double dedge = fx.scal[5], hedge = fx.scal[6];
-    const Orbit o = orbit_from_particle<true, true, false>(G, p, org, body);
+    const Orbit o = so ? *so : orbit_from_particle<true, true, false>(G, p, org, body);
     const double a0 = o.a, e0 = o.e, inc0 = o.inc;
     const double mp = p.m, ms = org.m;
     const Rel q = relative(p, org, body);

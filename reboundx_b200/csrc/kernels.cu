@@ -102,7 +102,8 @@ __device__ __forceinline__ void load_params(const rebx_b200_effect& fx, int64_t 
 
 template <int K, int V, class M = IeeeMath>
 __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body, const Pre& pre,
-                                      const Particle& p, const Params<K, V>& q, int v, Vec3& a, Vec3& red, unsigned& bad) {
+                                      const Particle& p, const Params<K, V>& q, int v, Vec3& a, Vec3& red, unsigned& bad,
+                                      const Orbit* so = nullptr) {
     if constexpr (K == REBX_B200_RADIATION) {
         radiation<M>(fx, org, body, pre, p, q.t[0][v], a, bad);
     } else if constexpr (K == REBX_B200_HARMONICS) {
@@ -113,13 +114,13 @@ __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const Origin& 
         YarkParams yp{q.t[0][v], q.t[1][v], q.t[2][v], q.t[3][v], q.t[4][v], q.t[5][v], q.t[6][v], q.t[7][v], q.t[8][v]};
         yarkovsky(fx, org, body, pre, p, yp, q.it[v], a);
     } else if constexpr (K == REBX_B200_MODIFY_ORBITS) {
-        const Vec3 f = modify_orbits(fx, org, body, p, q.t[0][v], q.t[1][v], q.t[2][v]);
+        const Vec3 f = modify_orbits(fx, org, body, p, q.t[0][v], q.t[1][v], q.t[2][v], so);
         com_force_tail(fx, org, body, p, f, a, red);
     } else if constexpr (K == REBX_B200_GAS_DAMPING) {
-        const Vec3 f = gas_damping(fx, org, body, p, q.t[0][v]);
+        const Vec3 f = gas_damping(fx, org, body, p, q.t[0][v], so);
         com_force_tail(fx, org, body, p, f, a, red);
     } else if constexpr (K == REBX_B200_TYPE_I) {
-        const Vec3 f = type_I_migration(fx, org, body, p);
+        const Vec3 f = type_I_migration(fx, org, body, p, so);
         com_force_tail(fx, org, body, p, f, a, red);
     } else if constexpr (K == REBX_B200_CENTRAL_FORCE) {
         central_force(fx, org, body, p, a, red);
@@ -240,10 +241,16 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
                 // one central body: one guard around the whole stack, so the effects sit in one region and
                 // their common sub-expressions (relative coordinates, orbit elements) are computed once
                 if (gi != b0) {
-                    apply<K0, V>(P.fx[0], o0, s_body[0], pre0, p, q0, v, a, red0, unused);
-                    if constexpr (K1 != 0) apply<K1, V>(P.fx[1], o1, s_body[1], pre1, p, q1, v, a, red1, unused);
-                    if constexpr (K2 != 0) apply<K2, V>(P.fx[2], org2, s_body[2], pre2, p, q2, v, a, red2, unused);
-                    if constexpr (K3 != 0) apply<K3, V>(P.fx[3], org3, s_body[3], pre3, p, q3, v, a, red3, unused);
+                    // stacked damping effects evaluate the SAME two-body elements (same particle, same
+                    // central body, same G): computed once here, bit-identical to each effect's own call
+                    constexpr int NDAMP = (K0 >= 5 && K0 <= 7) + (K1 >= 5 && K1 <= 7) + (K2 >= 5 && K2 <= 7) + (K3 >= 5 && K3 <= 7);
+                    Orbit oc;
+                    const Orbit* so = nullptr;
+                    if constexpr (NDAMP >= 2) { oc = orbit_from_particle<true, true, false>(P.fx[0].scal[0], p, o0, s_body[0]); so = &oc; }
+                    apply<K0, V>(P.fx[0], o0, s_body[0], pre0, p, q0, v, a, red0, unused, so);
+                    if constexpr (K1 != 0) apply<K1, V>(P.fx[1], o1, s_body[1], pre1, p, q1, v, a, red1, unused, so);
+                    if constexpr (K2 != 0) apply<K2, V>(P.fx[2], org2, s_body[2], pre2, p, q2, v, a, red2, unused, so);
+                    if constexpr (K3 != 0) apply<K3, V>(P.fx[3], org3, s_body[3], pre3, p, q3, v, a, red3, unused, so);
                 }
             } else {
                 if (gi != b0) apply<K0, V>(P.fx[0], o0, s_body[0], pre0, p, q0, v, a, red0, unused);
