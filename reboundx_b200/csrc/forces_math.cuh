@@ -12,6 +12,10 @@
 #include "rebx_b200.h"
 #include "exact_math.cuh"
 
+#ifndef REBXB_YARK_TRIG_IDENTITY
+#define REBXB_YARK_TRIG_IDENTITY 1
+#endif
+
 namespace rebxb {
 
 constexpr double kPi     = 3.14159265358979323846;
@@ -304,14 +308,32 @@ __device__ __forceinline__ void yarkovsky(const rebx_b200_effect& fx, const Orig
         const double R2h[3][3] = {{hx*hx*inv_hmag_sqrd, hx*hy*inv_hmag_sqrd, hx*hz*inv_hmag_sqrd},
                                   {hx*hy*inv_hmag_sqrd, hy*hy*inv_hmag_sqrd, hy*hz*inv_hmag_sqrd},
                                   {hx*hz*inv_hmag_sqrd, hy*hz*inv_hmag_sqrd, hz*hz*inv_hmag_sqrd}};
+#if REBXB_YARK_TRIG_IDENTITY
+        // x^(1/4) = sqrt(sqrt(x)) and y^(3/4) = sqrt(y) sqrt(sqrt(y)): correctly rounded square roots
+        // (<= 1.5 ulp in all) instead of two libdevice pow calls (1-2 ulp, ~250 FP64 instructions)
+        const double pre  = .5*sqrt(sqrt((stef_boltz*yp.emissivity)/kPi5));
+        const double fsq  = sqrt((lstar*q_yar)/(distance*distance));
+        const double flux = fsq*sqrt(fsq);
+#else
         const double pre  = .5*pow((stef_boltz*yp.emissivity)/kPi5, .25);
         const double flux = pow((lstar*q_yar)/(distance*distance), .75);
+#endif
         const double tanPhi     = 1.0/(1.0 + pre*sqrt(yp.rot_period/(yp.Gamma*yp.Gamma))*flux);
         const double tanEpsilon = 1.0/(1.0 + pre*sqrt(o.P/(yp.Gamma*yp.Gamma))*flux);
+#if REBXB_YARK_TRIG_IDENTITY
+        // cos(atan t) = 1/sqrt(1+t^2), sin(atan t) = t/sqrt(1+t^2): three correctly rounded operations
+        // (<= 1.5 ulp) instead of libdevice atan + sin + cos (each 1-2 ulp, ~150 FP64 instructions together).
+        // The reference composes glibc's atan/cos/sin (yarkovsky_effect.c:160-166); neither form is
+        // bit-reproducible against it, both agree with it to a few ulp.
+        const double inv_phi = 1.0/sqrt(1.0 + tanPhi*tanPhi), inv_eps = 1.0/sqrt(1.0 + tanEpsilon*tanEpsilon);
+        const double cos_phi = inv_phi, sin_phi = tanPhi*inv_phi;
+        const double cos_epsilon = inv_eps, sin_epsilon = tanEpsilon*inv_eps;
+#else
         const double Phi = atan(tanPhi);
         const double Epsilon = atan(tanEpsilon);
         const double cos_phi = cos(Phi), sin_phi = sin(Phi);
         const double cos_epsilon = cos(Epsilon), sin_epsilon = sin(Epsilon);
+#endif
         double Rys[3][3], Ryh[3][3];
 #pragma unroll
         for (int i = 0; i < 3; i++) {
