@@ -22,6 +22,8 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstdlib>
+#include <utility>
+#include <vector>
 #include "rebx_b200.h"
 #include "forces_math.cuh"
 
@@ -934,8 +936,15 @@ static DevInfo device_info() {
 
 static int grid_for(const void* fn, int64_t work_items, int threads = kThreads, int smem = 0, int items_per_block = kThreads) {
     const DevInfo di = device_info();
+    // resident CTAs per SM of this kernel: queried once per (kernel, launch shape) and thread
+    struct Key { const void* fn; int threads, smem; };
+    static thread_local std::vector<std::pair<Key, int>> cache;
     int per_sm = 0;
-    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+    for (const auto& kv : cache) if (kv.first.fn == fn && kv.first.threads == threads && kv.first.smem == smem) { per_sm = kv.second; break; }
+    if (per_sm == 0) {
+        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
+        cache.push_back({Key{fn, threads, smem}, per_sm});
+    }
     int64_t blocks = (work_items + items_per_block - 1)/items_per_block;
     int64_t cap = (int64_t)(di.ok ? di.sms : 148)*per_sm;
     if (cap > kMaxBlocks) cap = kMaxBlocks - (kMaxBlocks % (di.ok ? di.sms : 148));

@@ -1,0 +1,106 @@
+"""Minimal stand-in for the `rebound` Python package (TEST INFRASTRUCTURE ONLY).
+
+The reference's ctypes wrapper (reference reboundx/*.py) imports `rebound` for the Simulation and
+Particle structures.  REBOUND is not installable here, so this module exposes the stand-in host
+(reboundx_b200/rebound_shim) under the names the wrapper uses; only what the wrapper touches on the
+force path is provided.  Used by tests/test_reference_python_wrapper.py.
+"""
+import ctypes
+from ctypes import POINTER, Structure, c_char_p, c_double, c_int, c_size_t, c_void_p
+
+from reboundx_b200 import _lib
+
+_shim = _lib.load_shim()
+
+
+class Vec3dBasic(Structure):
+    _fields_ = [("x", c_double), ("y", c_double), ("z", c_double)]
+
+
+class Vec3d:
+    def __init__(self, *args):
+        v = args[0] if len(args) == 1 else args
+        if isinstance(v, Vec3dBasic):
+            self._vec3d = Vec3dBasic(v.x, v.y, v.z)
+        else:
+            self._vec3d = Vec3dBasic(*[float(c) for c in v])
+
+    def __iter__(self):
+        return iter((self._vec3d.x, self._vec3d.y, self._vec3d.z))
+
+
+class Orbit(Structure):
+    _fields_ = [("d", c_double)]
+
+
+class ODE(Structure):
+    _fields_ = [("length", c_int)]
+
+
+class Rotation(Structure):
+    _fields_ = [("ix", c_double), ("iy", c_double), ("iz", c_double), ("r", c_double)]
+
+
+class Simulation(Structure):
+    pass
+
+
+class Particle(Structure):
+    _fields_ = [("x", c_double), ("y", c_double), ("z", c_double), ("vx", c_double), ("vy", c_double), ("vz", c_double),
+                ("ax", c_double), ("ay", c_double), ("az", c_double), ("m", c_double), ("r", c_double),
+                ("last_collision", c_double), ("c", c_void_p), ("name", c_char_p), ("ap", c_void_p),
+                ("_sim", POINTER(Simulation))]
+
+
+class _Integrator(Structure):
+    _fields_ = [("name", c_char_p), ("state", c_void_p)]
+
+
+Simulation._fields_ = [("t", c_double), ("G", c_double), ("softening", c_double), ("dt", c_double), ("dt_last_done", c_double),
+                       ("N", c_size_t), ("N_var", c_size_t), ("N_active", c_size_t), ("_particles", POINTER(Particle)),
+                       ("force_is_velocity_dependent", c_int), ("_integrator", _Integrator), ("extras", c_void_p),
+                       ("_additional_forces", c_void_p), ("_pre_timestep_modifications", c_void_p),
+                       ("_post_timestep_modifications", c_void_p), ("_free_particle_ap", c_void_p), ("_extras_cleanup", c_void_p)]
+
+
+def _new_simulation():
+    _shim.reb_simulation_create.restype = c_void_p
+    ptr = _shim.reb_simulation_create()
+    return Simulation.from_address(ptr)
+
+
+def _add(self, m=0.0, x=0.0, y=0.0, z=0.0, vx=0.0, vy=0.0, vz=0.0, r=0.0):
+    p = Particle(x=x, y=y, z=z, vx=vx, vy=vy, vz=vz, m=m, r=r)
+    _shim.reb_simulation_add.argtypes = [c_void_p, Particle]
+    _shim.reb_simulation_add(c_void_p(ctypes.addressof(self)), p)
+
+
+def _process_messages(self):
+    _shim.reb_shim_message_count.restype = c_size_t
+    _shim.reb_shim_message.restype = c_char_p
+    _shim.reb_shim_message.argtypes = [c_void_p, c_size_t]
+    n = _shim.reb_shim_message_count(c_void_p(ctypes.addressof(self)))
+    msgs = [_shim.reb_shim_message(c_void_p(ctypes.addressof(self)), i).decode() for i in range(n)]
+    _shim.reb_shim_clear_messages(c_void_p(ctypes.addressof(self)))
+    for m in msgs:
+        if m[0] == "E":
+            raise RuntimeError(m[1:])
+
+
+def _particles(self):
+    return [self._particles[i] for i in range(self.N)]
+
+
+def _call_additional_forces(self):
+    _shim.reb_shim_call_additional_forces(c_void_p(ctypes.addressof(self)))
+
+
+Simulation.add = _add
+Simulation.process_messages = _process_messages
+Simulation.particles = property(_particles)
+Simulation.update_acceleration = _call_additional_forces
+Simulation.__new_sim__ = staticmethod(_new_simulation)
+
+
+class Simulationarchive:
+    pass
