@@ -50,6 +50,8 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    ap.add_argument("--coordinates", default="PARTICLE", choices=["PARTICLE", "JACOBI", "BARYCENTRIC"],
+                    help="reference frame of the rebx_com_force effects (planetesimal_disk only)")
     return ap.parse_args()
 
 
@@ -66,7 +68,11 @@ class ClockSampler:
     Q = "clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
-        self.index, self.proc, self.lines = index, None, []
+        self.index, self.proc, self.lines, self.windows = index, None, [], []
+
+    def window(self, t0, t1):
+        """Marks [t0, t1] (time.time()) as a timed region; the summary prefers samples taken inside one."""
+        self.windows.append((t0, t1))
 
     def __enter__(self):
         try:
@@ -80,7 +86,7 @@ class ClockSampler:
 
     def _read(self):
         for line in self.proc.stdout:
-            self.lines.append(line.strip())
+            self.lines.append((time.time(), line.strip()))
 
     def __exit__(self, *exc):
         if self.proc:
@@ -94,7 +100,10 @@ class ClockSampler:
     def summary(self):
         sm, mx, reasons = [], [], set()
         names = ["hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"]
-        for line in self.lines:
+        # a sample printed at time t describes the ~20 ms before it
+        inside = [ln for t, ln in self.lines if any(t0 <= t <= t1 + 0.05 for t0, t1 in self.windows)]
+        scope = "timed regions" if inside else "whole run (timed regions shorter than the 20 ms sampling period)"
+        for line in (inside or [ln for _, ln in self.lines]):
             parts = [p.strip() for p in line.split(",")]
             if len(parts) < 7:
                 continue
@@ -107,10 +116,10 @@ class ClockSampler:
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm)}
+        return {"sm_mhz": float(np.median(sm)), "sm_max_mhz": float(max(mx)), "reasons": sorted(reasons), "samples": len(sm), "scope": scope}
 
 
-def cpu_reference_leg(workload, add_order, sample_n, reps):
+def cpu_reference_leg(workload, add_order, sample_n, reps, coordinates="PARTICLE"):
     """The reference's own C implementation (oracle/_ref, kind "reference") or, if that library
     was never built, the C restatement (kind "port"), one host thread, bounded sample."""
     from reboundx_b200 import workloads
@@ -119,13 +128,13 @@ def cpu_reference_leg(workload, add_order, sample_n, reps):
     n = w["x"].shape[0]
     nf = len(add_order)
     if oracle.have_ref():
-        _, t = oracle.ref_apply(w, add_order, None, "PARTICLE", reps=reps)
+        _, t = oracle.ref_apply(w, add_order, None, coordinates, reps=reps)
         kind = "reference"
     else:
         best = float("inf")
         for _ in range(reps + 1):
             t0 = time.perf_counter()
-            oracle.port_apply(w, add_order[::-1], None, "PARTICLE")
+            oracle.port_apply(w, add_order[::-1], None, coordinates)
             best = min(best, time.perf_counter() - t0)
         t, kind = best, "port"
     return {"value": (n - 1)*nf/t, "unit": METRIC, "cores": 1, "kind": kind,
@@ -138,9 +147,9 @@ def run_reference(args):
     if rank != 0:
         return
     builder, add_order, n_default = WORKLOADS[args.workload]
-    sample = min(args.cpu_sample, args.n or n_default)
+    sample = min(args.cpu_sample if args.coordinates == "PARTICLE" else 20000, args.n or n_default)   # the COM frames are O(N^2) in the reference
     steps = max(1, args.steps)
-    base = cpu_reference_leg(builder, add_order, sample, steps)
+    base = cpu_reference_leg(builder, add_order, sample, steps, args.coordinates)
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "evals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_dispatch"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
@@ -170,12 +179,17 @@ def run_ours(args):
     n = args.n or n_default
     exec_order = add_order[::-1]
     nf = len(add_order)
+    com = args.coordinates != "PARTICLE"
+    if com and args.workload != "planetesimal_disk":
+        raise SystemExit("--coordinates applies to the rebx_com_force effects of --workload planetesimal_disk")
+    clocks = ClockSampler(local)
+    clocks.__enter__()          # sampled from here to the end of the e2e leg; the timed regions are marked as windows
 
     # Weak scaling: every rank owns n test particles of one global ensemble of world*n; the
     # central body (global index 0) is replicated and broadcast from rank 0 every evaluation.
     w = getattr(workloads, builder)(n, seed=3 + rank)
     lo = 0 if rank == 0 else 1
-    shard = device.Shard(w, exec_order, dev, lo=lo, index_base=(0 if rank == 0 else 1 + rank*n))
+    shard = device.Shard(w, exec_order, dev, lo=lo, index_base=(0 if rank == 0 else 1 + rank*n), coordinates=args.coordinates)
     n_local = shard.n - (1 if rank == 0 else 0)          # the body itself is not an evaluation
 
     def barrier():
@@ -191,23 +205,24 @@ def run_ours(args):
     # ---- resident leg: K evaluations, CUDA events on the launching stream, max over ranks -------
     launches0 = shard.launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    with ClockSampler(local) as clocks:
-        barrier()
-        e0.record()
-        for _ in range(args.steps):
-            shard.evaluate(group)
-        e1.record()
-        barrier()
-        # ---- roofline of the dominant kernel (the fused sweep), timed alone per launch -----------
-        k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        torch.cuda.synchronize()
-        k0.record()
-        for _ in range(args.steps):
-            shard.launch()
-        k1.record()
-        torch.cuda.synchronize()
+    barrier()
+    w0 = time.time()
+    e0.record()
+    for _ in range(args.steps):
+        shard.evaluate(group)
+    e1.record()
+    barrier()
+    gpu_launches = shard.launches - launches0                    # launches of the timed `value` region only
+    # ---- roofline of the dominant kernel (the fused sweep), timed alone per launch -----------
+    k0, k1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    k0.record()
+    for _ in range(args.steps):
+        shard.launch_local()
+    k1.record()
+    torch.cuda.synchronize()
+    clocks.window(w0, time.time())
     ms_total = e0.elapsed_time(e1)
-    gpu_launches = shard.launches - launches0 - args.steps      # launches of the timed `value` region only
     t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -217,17 +232,17 @@ def run_ours(args):
     peak, peak_src = peaks()
     achieved = shard.algorithmic_bytes/(kernel_ms*1e-3)/1e9
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak,
-                "traffic": None, "kernel": "pass_kernel(%s)" % ",".join(exec_order),
-                "algorithmic_bytes_per_particle": device.algorithmic_bytes_per_particle(shard.kinds),
+                "traffic": None, "kernel": ("pass_kernel(%s)" if not com else args.coordinates.lower() + " pipeline: moments, scans, sweep(%s), apply") % ",".join(exec_order),
+                "algorithmic_bytes_per_particle": shard.algorithmic_bytes//shard.n,
                 "kernel_ms": kernel_ms, "peak_source": peak_src}
     prof = os.path.join(ROOT, "profiles", "traffic.json")
-    if os.path.exists(prof) and n == n_default:       # ncu dram__bytes_read+write per launch, captured at the config's size
+    if os.path.exists(prof) and n == n_default and not com:       # ncu dram__bytes_read+write per launch, captured at the config's size
         with open(prof) as f:
             roofline["traffic"] = json.load(f).get(args.workload)
 
     # ---- resident stepping leg: full drift-kick-drift steps, no PCIe --------------
     resident = None
-    if not args.no_e2e:
+    if not args.no_e2e and not com:
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dt_step = 1e-3*2*np.pi*np.sqrt(float(np.hypot(w["x"][1], w["y"][1]))**3/(w["G"]*w["m"][0]))
         # one fused sweep per step on a single GPU; the separate sweeps (with the NCCL body broadcast
@@ -237,11 +252,13 @@ def run_ours(args):
             step()
         barrier()
         l0 = shard.launches
+        w0 = time.time()
         s0.record()
         for _ in range(args.steps):
             step()
         s1.record()
         barrier()
+        clocks.window(w0, time.time())
         tr = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tr, op=dist.ReduceOp.MAX)
@@ -256,19 +273,22 @@ def run_ours(args):
     if not args.no_e2e:
         del shard
         torch.cuda.empty_cache()
-        sim, rebx, _ = scenarios.build(w, add_order)
+        sim, rebx, _ = scenarios.build(w, add_order, coordinates=args.coordinates)
         for _ in range(2):
             sim.additional_forces()
-        sim.process_messages()
+        drain = sim.messages if args.coordinates == "BARYCENTRIC" else sim.process_messages   # BARYCENTRIC evaluates the star too, whose
+        drain()                                                                              # missing d_factor is reported as in the reference
         s0 = rebx.stats()
         steps = args.e2e_steps or min(args.steps, 10)
         barrier()
+        w0 = time.time()
         t0 = time.perf_counter()
         for _ in range(steps):
             sim.additional_forces()            # synchronous: accelerations are valid on return
         dt = time.perf_counter() - t0
+        clocks.window(w0, time.time())
         s1 = rebx.stats()
-        sim.process_messages()
+        drain()
         tt = torch.tensor([dt], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -282,9 +302,10 @@ def run_ours(args):
         rebx.detach()
         sim.free()
 
+    clocks.__exit__(None, None, None)
     cpu = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
-        cpu = cpu_reference_leg(builder, add_order, min(args.cpu_sample, n), 5)
+        cpu = cpu_reference_leg(builder, add_order, min(args.cpu_sample, n) if not com else min(20000, n), 5, args.coordinates)
         cpu["unit"] = "evals/s"
         cpu.pop("ms_per_dispatch")
 
@@ -292,10 +313,11 @@ def run_ours(args):
         line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
                 "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
                 "data": "synthetic",
-                "config": {"workload": f"{args.workload}: {n} test particles per GPU, {'+'.join(add_order)}",
+                "config": {"workload": f"{args.workload}: {n} test particles per GPU, {'+'.join(add_order)}" + (f", REBX_COORDINATES_{args.coordinates}" if com else ""),
                            "particles_per_gpu": n, "forces": add_order,
                            "l2": f"inputs larger than L2 ({shard_bytes(n, exec_order)/1e6:.0f} MB streamed per step)",
-                           "sharding": "index ranges; body state broadcast per step (NCCL) when n_gpus > 1"},
+                           "sharding": ("index ranges; body state broadcast per step (NCCL) when n_gpus > 1" if not com else
+                                        "index ranges; per step an all-gather of 7 mass moments and of 3 back-reaction sums per rank (JACOBI: exclusive prefix / suffix over ranks; BARYCENTRIC: all-reduce)")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "resident_step": resident, "gpu_launches": gpu_launches,
                 "clocks": clocks.summary()}
         print(json.dumps(line), flush=True)

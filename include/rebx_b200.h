@@ -152,6 +152,20 @@ int rebx_b200_com_bodies(const double* totals7, double* bodies, int nbodies, voi
  * (index_base must be 0): prefix scan of the mass moments, sweep, suffix scan of the
  * back-reaction, all on the device in O(n).  fx[].body and fx[].backreaction are ignored. */
 int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* stream, int* launches);
+/* The same pipeline in three stages, for an ensemble SHARDED by index range:
+ * the shards exchange 7 + 3 doubles between the stages, everything else stays local.
+ *   1. jacobi_moments: totals7 (device, may be NULL) = this shard's {sum m, sum m r, sum m v};
+ *      the in-shard prefix stays in `scratch`.
+ *      -> exchange: carry7 of a shard = sum of totals7 over the shards in FRONT of it (lower indices).
+ *   2. jacobi_sweep: a += f against COM_i = (carry7 + in-shard prefix)/mass; tsum3 (device, may be NULL)
+ *      = this shard's sum of t_i = m_i/(M_i+m_i) sum_e f_i^e.  carry7 NULL = the first shard.
+ *      cudaErrorNotSupported for a stack without a fused instantiation (call per effect then).
+ *      -> exchange: carry3 of a shard = sum of tsum3 over the shards BEHIND it (higher indices).
+ *   3. jacobi_apply: a_j -= carry3 + sum_{i >= j in shard} t_i.  carry3 NULL = the last shard.
+ * `scratch` (rebx_b200_scan_scratch_bytes(st.n)) must be the same untouched buffer through 1-3. */
+int rebx_b200_jacobi_moments(const rebx_b200_state* st, void* scratch, double* totals7, void* stream, int* launches);
+int rebx_b200_jacobi_sweep(const rebx_b200_pass* pass, void* scratch, const double* carry7, double* tsum3, void* stream, int* launches);
+int rebx_b200_jacobi_apply(const rebx_b200_state* st, void* scratch, const double* carry3, void* stream, int* launches);
 
 /* ---- 1PN `gr` effect (reference src/gr.c:65-164) for N_active <= REBX_B200_GR_MAX_ACTIVE ---------
  * Passed BY VALUE from host memory.  active[i] = {x, y, z, m} of active body i; com[] = the Jacobi

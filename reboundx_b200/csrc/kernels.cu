@@ -1129,19 +1129,74 @@ int rebx_b200_com_bodies(const double* totals7, double* bodies, int nbodies, voi
     return err;
 }
 
+// Scratch layout shared by the three Jacobi stages (all sized by the shard's own n).
+struct JacobiScratch {
+    double *rows7, *rows3, *totals, *tvec;
+    int64_t ntiles;
+    JacobiScratch(void* scratch, int64_t n) {
+        ntiles = (n + kScanThreads - 1)/kScanThreads;
+        rows7 = static_cast<double*>(scratch);
+        rows3 = rows7 + (size_t)(ntiles + 1)*7;
+        totals = rows3 + (size_t)(ntiles + 1)*3;
+        tvec = totals + 16;
+    }
+};
+
+static const JacobiCombo* find_jacobi_combo(const rebx_b200_pass& P) {
+    for (const JacobiCombo& c : kJacobiCombos) {
+        bool ok = true;
+        for (int j = 0; j < 3; j++) if (c.k[j] != (j < P.n_effects ? P.fx[j].kind : 0)) ok = false;
+        if (ok) return &c;
+    }
+    return nullptr;
+}
+
+int rebx_b200_jacobi_moments(const rebx_b200_state* st, void* scratch, double* totals7, void* stream, int* launches) {
+    if (!st || !scratch || !st->x || !st->vx || !st->m) return cudaErrorInvalidValue;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (st->n == 0) return totals7 ? cudaMemsetAsync(totals7, 0, 7*sizeof(double), s) : cudaSuccess;
+    JacobiScratch J(scratch, st->n);
+    moments_tile_kernel<<<(unsigned)J.ntiles, kScanThreads, 0, s>>>(*st, J.rows7);
+    scan_tiles_kernel<7, false><<<1, 512, 0, s>>>(J.rows7, J.ntiles, totals7 ? totals7 : J.totals);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) *launches += 2;
+    return err;
+}
+
+int rebx_b200_jacobi_sweep(const rebx_b200_pass* pass, void* scratch, const double* carry7, double* tsum3, void* stream, int* launches) {
+    if (!pass || !scratch) return cudaErrorInvalidValue;
+    const rebx_b200_pass& P = *pass;
+    if (P.n_effects < 1 || P.n_effects > 3) return cudaErrorInvalidValue;
+    if (!P.st.x || !P.st.vx || !P.st.m || !P.st.ax) return cudaErrorInvalidValue;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (P.st.n == 0) return tsum3 ? cudaMemsetAsync(tsum3, 0, 3*sizeof(double), s) : cudaSuccess;
+    const JacobiCombo* combo = find_jacobi_combo(P);
+    if (!combo) return cudaErrorNotSupported;
+    JacobiScratch J(scratch, P.st.n);
+    combo->fn<<<(unsigned)J.ntiles, kScanThreads, 0, s>>>(P, J.rows7, J.tvec, J.rows3, carry7);
+    scan_tiles_kernel<3, true><<<1, 512, 0, s>>>(J.rows3, J.ntiles, tsum3 ? tsum3 : J.totals + 8);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) *launches += 2;
+    return err;
+}
+
+int rebx_b200_jacobi_apply(const rebx_b200_state* st, void* scratch, const double* carry3, void* stream, int* launches) {
+    if (!st || !scratch || !st->ax) return cudaErrorInvalidValue;
+    if (st->n == 0) return 0;
+    JacobiScratch J(scratch, st->n);
+    jacobi_apply_kernel<<<(unsigned)J.ntiles, kScanThreads, 0, static_cast<cudaStream_t>(stream)>>>(*st, J.tvec, J.rows3, carry3);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
 int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* stream, int* launches) {
     if (!pass || !scratch) return cudaErrorInvalidValue;
     const rebx_b200_pass& P = *pass;
     if (P.n_effects < 1 || P.n_effects > 3 || P.st.index_base != 0) return cudaErrorInvalidValue;
     if (!P.st.x || !P.st.vx || !P.st.m || !P.st.ax) return cudaErrorInvalidValue;
     if (P.st.n == 0) return 0;
-    const JacobiCombo* combo = nullptr;
-    for (const JacobiCombo& c : kJacobiCombos) {
-        bool ok = true;
-        for (int j = 0; j < 3; j++) if (c.k[j] != (j < P.n_effects ? P.fx[j].kind : 0)) ok = false;
-        if (ok) { combo = &c; break; }
-    }
-    if (!combo) {
+    if (!find_jacobi_combo(P)) {
         // no fused instantiation for this stack: one complete Jacobi pipeline per effect (equivalent,
         // the effects read positions and velocities only)
         if (P.n_effects == 1) return cudaErrorInvalidValue;
@@ -1154,20 +1209,10 @@ int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* str
         }
         return 0;
     }
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    const int64_t n = P.st.n, ntiles = (n + kScanThreads - 1)/kScanThreads;
-    double* rows7 = static_cast<double*>(scratch);
-    double* rows3 = rows7 + (size_t)(ntiles + 1)*7;
-    double* totals = rows3 + (size_t)(ntiles + 1)*3;
-    double* tvec = totals + 16;
-    moments_tile_kernel<<<(unsigned)ntiles, kScanThreads, 0, s>>>(P.st, rows7);
-    scan_tiles_kernel<7, false><<<1, 512, 0, s>>>(rows7, ntiles, totals);
-    combo->fn<<<(unsigned)ntiles, kScanThreads, 0, s>>>(P, rows7, tvec, rows3);
-    scan_tiles_kernel<3, true><<<1, 512, 0, s>>>(rows3, ntiles, totals + 8);
-    jacobi_apply_kernel<<<(unsigned)ntiles, kScanThreads, 0, s>>>(P.st, tvec, rows3);
-    cudaError_t err = cudaGetLastError();
-    if (err == cudaSuccess && launches) *launches += 5;
-    return err;
+    int rc = rebx_b200_jacobi_moments(&P.st, scratch, nullptr, stream, launches);
+    if (rc == 0) rc = rebx_b200_jacobi_sweep(&P, scratch, nullptr, nullptr, stream, launches);
+    if (rc == 0) rc = rebx_b200_jacobi_apply(&P.st, scratch, nullptr, stream, launches);
+    return rc;
 }
 
 int rebx_b200_gr_pull(const rebx_b200_state* st, const rebx_b200_gr_args* args, double* pull, void* workspace, void* stream, int* launches) {

@@ -147,7 +147,7 @@ __device__ __forceinline__ Vec3 damping_force(const rebx_b200_effect& fx, const 
 template <int K0, int K1, int K2>
 __global__ void __launch_bounds__(kScanThreads)
 jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __restrict__ tile_prefix,
-                    double* __restrict__ tvec, double* __restrict__ tile_tsums) {
+                    double* __restrict__ tvec, double* __restrict__ tile_tsums, const double* __restrict__ carry7) {
     __shared__ double s_warp[kScanThreads/32][7];
     const rebx_b200_state& st = P.st;
     const int64_t k = (int64_t)blockIdx.x*kScanThreads + threadIdx.x;
@@ -160,10 +160,13 @@ jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __re
     double total[7];
     block_exclusive_scan<7>(v, total, s_warp);
     double body[REBX_B200_BODY_DOUBLES];
-    const double M = tile_prefix[(size_t)blockIdx.x*7] + v[0];          // mass interior to particle k
+    // carry7: mass moments of the shards in front of this one (index ranges below index_base), or NULL
+    double M = tile_prefix[(size_t)blockIdx.x*7] + v[0];                // mass interior to particle k
+    if (carry7) M = carry7[0] + M;
 #pragma unroll
     for (int j = 0; j < 6; j++) {
-        const double S = tile_prefix[(size_t)blockIdx.x*7 + 1 + j] + v[1 + j];
+        double S = tile_prefix[(size_t)blockIdx.x*7 + 1 + j] + v[1 + j];
+        if (carry7) S = carry7[1 + j] + S;
         body[REBX_B200_BODY_X + j] = (M > 0.) ? S/M : S;
     }
     body[REBX_B200_BODY_INDEX] = -1.0;
@@ -198,7 +201,8 @@ jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __re
 
 // a_j -= sum_{i >= j} t_i : in-tile reverse inclusive scan + exclusive suffix of the tiles behind.
 __global__ void __launch_bounds__(kScanThreads)
-jacobi_apply_kernel(rebx_b200_state st, const double* __restrict__ tvec, const double* __restrict__ tile_suffix) {
+jacobi_apply_kernel(rebx_b200_state st, const double* __restrict__ tvec, const double* __restrict__ tile_suffix,
+                    const double* __restrict__ carry3) {
     __shared__ double s_warp[kScanThreads/32][3];
     const int64_t tile_lo = (int64_t)blockIdx.x*kScanThreads;
     const int64_t tile_hi = (tile_lo + kScanThreads < st.n) ? tile_lo + kScanThreads : st.n;
@@ -209,13 +213,16 @@ jacobi_apply_kernel(rebx_b200_state st, const double* __restrict__ tvec, const d
     double own[3] = {t[0], t[1], t[2]}, tot[3];
     block_exclusive_scan<3>(t, tot, s_warp);
     if (live) {
-        st.ax[k] -= tile_suffix[(size_t)blockIdx.x*3 + 0] + (t[0] + own[0]);
-        st.ay[k] -= tile_suffix[(size_t)blockIdx.x*3 + 1] + (t[1] + own[1]);
-        st.az[k] -= tile_suffix[(size_t)blockIdx.x*3 + 2] + (t[2] + own[2]);
+        // carry3: sum of t over the shards behind this one (higher index ranges), or NULL
+        double s0 = tile_suffix[(size_t)blockIdx.x*3 + 0] + (t[0] + own[0]);
+        double s1 = tile_suffix[(size_t)blockIdx.x*3 + 1] + (t[1] + own[1]);
+        double s2 = tile_suffix[(size_t)blockIdx.x*3 + 2] + (t[2] + own[2]);
+        if (carry3) { s0 = carry3[0] + s0; s1 = carry3[1] + s1; s2 = carry3[2] + s2; }
+        st.ax[k] -= s0; st.ay[k] -= s1; st.az[k] -= s2;
     }
 }
 
-typedef void (*jacobi_fn)(const rebx_b200_pass, const double*, double*, double*);
+typedef void (*jacobi_fn)(const rebx_b200_pass, const double*, double*, double*, const double*);
 struct JacobiCombo { int k[3]; jacobi_fn fn; };
 #define REBXB_JCOMBO(a, b, c) { {a, b, c}, jacobi_sweep_kernel<a, b, c> },
 static const JacobiCombo kJacobiCombos[] = {

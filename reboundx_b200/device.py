@@ -68,8 +68,9 @@ def spin_frame(Omega):
 class Shard:
     """Particles [lo, hi) of a workload, resident on `device`, with `exec_order` effects."""
 
-    def __init__(self, w, exec_order, device, lo=0, hi=None, coordinates="PARTICLE", acc0=None, index_base=None):
+    def __init__(self, w, exec_order, device, lo=0, hi=None, coordinates="PARTICLE", acc0=None, index_base=None, standalone=False):
         import torch
+        self.standalone = standalone        # the whole ensemble is this one shard: evaluate() runs no collective
         self.torch = torch
         self.lib = lib = _lib.load()
         lib.rebx_b200_launch_pass.restype = c_int
@@ -89,6 +90,7 @@ class Shard:
         if not 1 <= len(self.exec_order) <= MAX_EFFECTS:
             raise ValueError("1..4 stacked effects per pass")
         self.kinds = [KIND[name] for name in self.exec_order]
+        self.coordinates = coordinates
 
         def dev(a, dtype=torch.float64):
             return torch.from_numpy(np.ascontiguousarray(a)).to(self.device, dtype=dtype)
@@ -139,8 +141,13 @@ class Shard:
                              0.01 if w.get("tIm_scale_height_1") is None else w["tIm_scale_height_1"],
                              w.get("tIm_surface_density_1") or 0.0, w.get("tIm_surface_density_exponent") or 0.0,
                              w.get("ide_position") or 0.0, w.get("ide_width") or 0.0]
-            if kind in (5, 6, 7) and coordinates != "PARTICLE":
-                raise NotImplementedError("resident shards support PARTICLE coordinates")
+            if coordinates != "PARTICLE":
+                if kind not in (5, 6, 7):
+                    raise ValueError("centre-of-mass coordinates apply to the rebx_com_force effects (damping trio) only")
+                if coordinates == "BARYCENTRIC":
+                    flags |= FLAG_BARYCENTRIC
+                elif coordinates != "JACOBI":
+                    raise ValueError("coordinates must be PARTICLE, BARYCENTRIC or JACOBI")
             self.tables.append(tabs)
             self.itables.append(itab)
             self.scalars.append(scal)
@@ -149,6 +156,13 @@ class Shard:
         self.backreaction = torch.zeros((len(self.kinds), 3), dtype=torch.float64, device=self.device)
         self.workspace = torch.empty(lib.rebx_b200_workspace_bytes(), dtype=torch.uint8, device=self.device)
         self.launches = 0
+        if coordinates != "PARTICLE":
+            if len(self.kinds) > 3:
+                raise ValueError("at most 3 stacked effects in a centre-of-mass frame")
+            lib.rebx_b200_scan_scratch_bytes.restype = ctypes.c_size_t
+            self.scan_scratch = torch.empty(lib.rebx_b200_scan_scratch_bytes(c_int64(self.n)), dtype=torch.uint8, device=self.device)
+            self.moments = torch.zeros(7, dtype=torch.float64, device=self.device)     # sum m, sum m r, sum m v of this shard
+            self.tsum = torch.zeros(3, dtype=torch.float64, device=self.device)        # JACOBI: sum of t_i of this shard
         self._pass = self._make_pass()
 
     # ------------------------------------------------------------------------------------------
@@ -173,8 +187,9 @@ class Shard:
 
     @property
     def algorithmic_bytes(self):
-        """HBM bytes one pass must move for this shard (the roofline numerator)."""
-        return algorithmic_bytes_per_particle(self.kinds)*self.n
+        """HBM bytes one evaluation must move for this shard (the roofline numerator): one pass over the
+        state, plus 16 B/particle of scan scratch in the Jacobi frame."""
+        return (algorithmic_bytes_per_particle(self.kinds) + (16 if self.coordinates == "JACOBI" else 0))*self.n
 
     def _check(self, rc, what):
         if rc != 0:
@@ -205,8 +220,79 @@ class Shard:
         self.launches += n.value
         return n.value
 
+    # ---- centre-of-mass frames of rebx_com_force (reference src/rebxtools.c:66-147), sharded ----------
+    # Three local stages with one small exchange between them; `evaluate` wires them to
+    # torch.distributed, a test may wire several shards on one device by hand.
+    def _libcall(self, name, *args, stream=None):
+        n = c_int(0)
+        fn = getattr(self.lib, name)
+        fn.restype = c_int
+        rc = fn(*args, c_void_p(self._stream(stream).cuda_stream), ctypes.byref(n))
+        self._check(rc, name)
+        self.launches += n.value
+        return n.value
+
+    def com_moments(self, stream=None):
+        """Stage 1: this shard's mass moments -> self.moments (JACOBI also keeps the in-shard prefix)."""
+        st, scr = ctypes.byref(self._pass.st), c_void_p(self.scan_scratch.data_ptr())
+        if self.coordinates == "JACOBI":
+            return self._libcall("rebx_b200_jacobi_moments", st, scr, c_void_p(self.moments.data_ptr()), stream=stream)
+        return self._libcall("rebx_b200_mass_moments", st, c_void_p(self.moments.data_ptr()), scr, stream=stream)
+
+    def com_sweep(self, moments, stream=None):
+        """Stage 2.  BARYCENTRIC: `moments` = the all-reduced totals; the sweep leaves -sum (m_i/M) f_i of this
+        shard in self.backreaction.  JACOBI: `moments` = the carry (sum over the shards in front, or None);
+        leaves this shard's sum of t_i in self.tsum."""
+        if self.coordinates == "JACOBI":
+            carry = c_void_p(moments.data_ptr()) if moments is not None else None
+            return self._libcall("rebx_b200_jacobi_sweep", ctypes.byref(self._pass), c_void_p(self.scan_scratch.data_ptr()), carry,
+                                 c_void_p(self.tsum.data_ptr()), stream=stream)
+        k = self._libcall("rebx_b200_com_bodies", c_void_p(moments.data_ptr()), c_void_p(self.bodies.data_ptr()), c_int(len(self.kinds)), stream=stream)
+        return k + self.launch(stream)
+
+    def com_apply(self, carry, stream=None):
+        """Stage 3.  BARYCENTRIC: `carry` = the all-reduced (n_effects, 3) back-reaction, added to every
+        particle.  JACOBI: `carry` = sum of tsum over the shards behind (or None)."""
+        st = ctypes.byref(self._pass.st)
+        if self.coordinates == "JACOBI":
+            c = c_void_p(carry.data_ptr()) if carry is not None else None
+            return self._libcall("rebx_b200_jacobi_apply", st, c_void_p(self.scan_scratch.data_ptr()), c, stream=stream)
+        k = 0
+        for e in range(len(self.kinds)):
+            k += self._libcall("rebx_b200_add_uniform", st, c_void_p(carry.data_ptr() + e*3*8), stream=stream)
+        return k
+
+    def _evaluate_com(self, group=None):
+        k = self.com_moments()
+        if self.coordinates == "JACOBI":
+            self._carry7 = sharding.exchange_prefix(self.moments, group)        # kept alive until the kernels ran
+            k += self.com_sweep(self._carry7)
+            self._carry3 = sharding.exchange_suffix(self.tsum, group)
+            return k + self.com_apply(self._carry3)
+        sharding.allreduce_sum(self.moments, group)
+        k += self.com_sweep(self.moments)
+        sharding.allreduce_sum(self.backreaction, group)
+        return k + self.com_apply(self.backreaction)
+
+    def launch_local(self, stream=None):
+        """Every kernel of one evaluation of this shard, without the cross-shard exchanges (what a
+        kernel-only timing wants): the sweep in PARTICLE coordinates, the staged pipeline otherwise."""
+        if self.coordinates == "PARTICLE":
+            return self.launch(stream)
+        k = self.com_moments(stream)
+        if self.coordinates == "JACOBI":
+            return k + self.com_sweep(None, stream) + self.com_apply(None, stream)
+        return k + self.com_sweep(self.moments, stream) + self.com_apply(self.backreaction, stream)
+
     def evaluate(self, group=None):
         """Full evaluation incl. the multi-GPU exchange steps; returns kernels launched."""
+        if self.standalone:
+            k = self.launch_local()
+            if self.coordinates == "PARTICLE" and any(kind != 1 and kind != 4 for kind in self.kinds):
+                k += self.apply_backreaction()
+            return k
+        if self.coordinates != "PARTICLE":
+            return self._evaluate_com(group)
         self.sync_bodies(group)
         k = self.launch()
         if any(kind != 1 and kind != 4 for kind in self.kinds):

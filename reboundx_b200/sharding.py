@@ -4,6 +4,11 @@ The force path has no particle-particle coupling beyond the O(1) source / primar
 ranks own contiguous index ranges and exchange only
   * the body records (broadcast from the owner, a few hundred bytes), and
   * the back-reaction sums onto those bodies (all-reduce of 3 doubles per effect).
+The centre-of-mass frames of rebx_com_force add one more exchange each (section 8e rows 3, 4):
+  * BARYCENTRIC: all-reduce of the 7 mass moments before the sweep and of sum (m_i/M) f_i after it;
+  * JACOBI: an exclusive PREFIX over ranks of the 7 mass moments (the centre of mass interior to a
+    shard's first particle) and an exclusive SUFFIX over ranks of the 3-vector sum of t_i (what every
+    particle in front must lose), each an all-gather of one small row per rank.
 These helpers are backend-agnostic torch.distributed calls: NCCL over NVLink on the GPU box,
 gloo in the CPU tests.
 """
@@ -41,3 +46,55 @@ def allreduce_backreaction(backreaction, group=None):
     if dist.is_available() and dist.is_initialized() and dist.get_world_size(group) > 1:
         dist.all_reduce(backreaction, group=group)
     return backreaction
+
+
+def _world(group=None):
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        return dist.get_world_size(group), dist.get_rank(group)
+    return 1, 0
+
+
+def allreduce_sum(t, group=None):
+    """In-place sum over ranks (mass moments, barycentric back-reaction)."""
+    import torch.distributed as dist
+    if _world(group)[0] > 1:
+        dist.all_reduce(t, group=group)
+    return t
+
+
+def gather_rows(row, group=None):
+    """All ranks' copies of a small tensor, in rank order (a list of world_size tensors)."""
+    import torch
+    import torch.distributed as dist
+    world, _ = _world(group)
+    if world == 1:
+        return [row]
+    rows = [torch.empty_like(row) for _ in range(world)]
+    dist.all_gather(rows, row.contiguous(), group=group)
+    return rows
+
+
+def exclusive_prefix(rows, rank):
+    """Sum of rows[0..rank) added front to back (rank 0: zeros).  Fixed order => every rank that
+    recomputes a neighbour's carry gets the same bits."""
+    out = rows[0].new_zeros(rows[0].shape)
+    for q in range(rank):
+        out = out + rows[q]
+    return out
+
+
+def exclusive_suffix(rows, rank):
+    """Sum of rows(rank..world) excluding rank's own, added back to front (last rank: zeros)."""
+    out = rows[0].new_zeros(rows[0].shape)
+    for q in range(len(rows) - 1, rank, -1):
+        out = out + rows[q]
+    return out
+
+
+def exchange_prefix(row, group=None):
+    return exclusive_prefix(gather_rows(row, group), _world(group)[1])
+
+
+def exchange_suffix(row, group=None):
+    return exclusive_suffix(gather_rows(row, group), _world(group)[1])

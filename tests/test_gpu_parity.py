@@ -276,6 +276,80 @@ def test_damping_trio_centre_of_mass_frames(built, coordinates, add_order):
     assert e["frac_component_above_tol"] <= 5e-3, e
 
 
+@pytest.mark.parametrize("coordinates", ["JACOBI", "BARYCENTRIC"])
+@pytest.mark.parametrize("cuts", [(), (1000,), (2, 1537, 2998)])
+def test_sharded_centre_of_mass_frames(built, coordinates, cuts):
+    """the centre-of-mass frames over index-range SHARDS.  Each shard runs the three
+    local stages (rebx_b200_jacobi_moments/_sweep/_apply, or mass_moments / sweep / add_uniform); between
+    them only 7 + 3 doubles per shard are exchanged -- here by hand between shards resident on one
+    device, exactly what Shard.evaluate() does with torch.distributed all-gather / all-reduce."""
+    import torch
+    from reboundx_b200 import device, sharding, workloads
+    w = workloads.planetesimal_disk(3000)
+    acc0 = acc_variants(w, 10)["gravity"]
+    want, _ = oracle_acc(w, TRIO, acc0, coordinates)
+    n = w["x"].shape[0]
+    edges = [0] + list(cuts) + [n]
+    shards = [device.Shard(w, TRIO[::-1], "cuda:0", lo=lo, hi=hi, coordinates=coordinates, acc0=acc0) for lo, hi in zip(edges, edges[1:])]
+    for sh in shards:
+        sh.com_moments()
+    rows = [sh.moments for sh in shards]
+    keep = []
+    if coordinates == "JACOBI":
+        for r, sh in enumerate(shards):
+            keep.append(sharding.exclusive_prefix(rows, r))
+            sh.com_sweep(keep[-1])
+        rows3 = [sh.tsum for sh in shards]
+        for r, sh in enumerate(shards):
+            keep.append(sharding.exclusive_suffix(rows3, r))
+            sh.com_apply(keep[-1])
+    else:
+        total = sum(rows[1:], rows[0].clone())
+        for sh in shards:
+            sh.com_sweep(total)
+        br = sum((sh.backreaction for sh in shards[1:]), shards[0].backreaction.clone())
+        for sh in shards:
+            sh.com_apply(br)
+    torch.cuda.synchronize()
+    got = [np.concatenate([sh.acc()[k] for sh in shards]) for k in range(3)]
+    e = errors(got, want, skip=(0,)) if coordinates == "BARYCENTRIC" else errors(got, want)
+    assert e["max_normwise"] <= TOL, e
+    assert e["frac_component_above_tol"] <= 5e-3, e
+    if not cuts:        # one shard == the host-facing call's resident chunk: same kernels, same bits
+        from reboundx_b200 import scenarios
+        sim, rebx, _ = scenarios.build(w, TRIO, coordinates=coordinates, acc=acc0)
+        sim.additional_forces()
+        sim.messages()              # BARYCENTRIC: the star's missing d_factor is reported, like the reference does
+        host = sim.acc()
+        rebx.detach(); sim.free()
+        assert errors(got, host)["bit_identical"]
+
+
+def test_nccl_sharded_evaluation(built, tmp_path):
+    """World-size-2 NCCL run of the sharded evaluation (tests/nccl_sharded_check.py) when the box has two
+    GPUs: per-particle results bit-identical in PARTICLE coordinates, north-star tolerance in the
+    centre-of-mass frames (the cross-shard carry changes the summation order)."""
+    import json, os, socket, subprocess, sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs two GPUs (gpurun --gpus 2)")
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        port = s.getsockname()[1]
+    out = tmp_path / "report.json"
+    here = os.path.dirname(os.path.abspath(__file__))
+    subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
+                    "--master-port", str(port), os.path.join(here, "nccl_sharded_check.py"), str(out)], check=True, timeout=600)
+    report = json.loads(out.read_text())
+    assert len(report) == 5
+    for r in report:
+        if r["coordinates"] == "PARTICLE":
+            assert r["bit_identical"], r
+            assert r["body_max_normwise"] <= TOL, r
+        else:
+            assert r["max_normwise"] <= TOL, r
+
+
 def test_jacobi_is_the_default_frame(built):
     """No 'coordinates' parameter => REBX_COORDINATES_JACOBI (reference src/modify_orbits_forces.c:131-135)."""
     from reboundx_b200 import workloads

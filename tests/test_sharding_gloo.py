@@ -82,3 +82,44 @@ def test_shard_ranges_cover_and_align():
             assert all(lo % 2 == 0 for lo, hi in edges if lo < n)
             if n:
                 assert sharding.owner_of(n - 1, n, world) == max(r for r, (lo, hi) in enumerate(edges) if hi > lo)
+
+
+def _scan_worker(rank, world, port, out_dir):
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    sys.path.insert(0, root)
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    from reboundx_b200 import sharding
+    moments = torch.arange(7, dtype=torch.float64)*(rank + 1) + 0.1*rank       # this rank's 7 mass moments
+    tsum = torch.tensor([1.0, 10.0, 100.0], dtype=torch.float64)*(rank + 1)      # this rank's sum of t_i
+    pre = sharding.exchange_prefix(moments)
+    suf = sharding.exchange_suffix(tsum)
+    tot = sharding.allreduce_sum(moments.clone())
+    np.savez(os.path.join(out_dir, f"scan{rank}.npz"), pre=pre.numpy(), suf=suf.numpy(), tot=tot.numpy())
+    dist.barrier()
+    dist.destroy_process_group()
+
+
+@pytest.mark.parametrize("world", [2, 3])
+def test_jacobi_prefix_suffix_exchange(world, tmp_path):
+    """The cross-shard scans of the sharded Jacobi frame: exclusive prefix of the
+    mass moments, exclusive suffix of the back-reaction sums, over gloo."""
+    mp.spawn(_scan_worker, args=(world, _free_port(), str(tmp_path)), nprocs=world, join=True)
+    moments = [np.arange(7)*(r + 1) + 0.1*r for r in range(world)]
+    tsum = [np.array([1.0, 10.0, 100.0])*(r + 1) for r in range(world)]
+    for r in range(world):
+        got = np.load(tmp_path / f"scan{r}.npz")
+        assert np.array_equal(got["pre"], sum(moments[:r], np.zeros(7)))
+        assert np.array_equal(got["suf"], sum(tsum[r + 1:][::-1], np.zeros(3)))
+        assert np.allclose(got["tot"], sum(moments), rtol=1e-15)
+
+
+def test_prefix_suffix_pure_functions():
+    from reboundx_b200 import sharding
+    rows = [torch.tensor([float(i), 2.0*i]) for i in range(1, 5)]
+    assert sharding.exclusive_prefix(rows, 0).tolist() == [0.0, 0.0]
+    assert sharding.exclusive_prefix(rows, 3).tolist() == [6.0, 12.0]
+    assert sharding.exclusive_suffix(rows, 3).tolist() == [0.0, 0.0]
+    assert sharding.exclusive_suffix(rows, 0).tolist() == [9.0, 18.0]
