@@ -172,6 +172,11 @@ def run_ours(args):
         raise SystemExit("bench.py: no CUDA device; the force path has no CPU fallback")
     torch.cuda.set_device(local)
     os.environ["REBX_B200_DEVICE"] = str(local)
+    # stdout carries ONE JSON line: anything a library prints to fd 1 meanwhile (NCCL's version banner under
+    # NCCL_DEBUG=VERSION, ...) is sent to stderr, and the line is written to the saved descriptor at the end
+    sys.stdout.flush()
+    json_fd = os.dup(1)
+    os.dup2(2, 1)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
     dev = f"cuda:{local}"
@@ -245,9 +250,9 @@ def run_ours(args):
     if not args.no_e2e and not com:
         s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         dt_step = 1e-3*2*np.pi*np.sqrt(float(np.hypot(w["x"][1], w["y"][1]))**3/(w["G"]*w["m"][0]))
-        # one fused sweep per step on a single GPU; the separate sweeps (with the NCCL body broadcast
-        # and back-reaction all-reduce between them) when sharded
-        step = (lambda: shard.fused_leapfrog_step(dt_step, w["G"])) if world == 1 else (lambda: shard.leapfrog_step(dt_step, w["G"], group))
+        # one fused sweep per step; sharded, every rank advances its replica of the central body itself and
+        # only the back-reaction sums (none for radiation_forces) are all-reduced
+        step = lambda: shard.fused_leapfrog_step(dt_step, w["G"], group=group)
         for _ in range(3):
             step()
         barrier()
@@ -265,8 +270,8 @@ def run_ours(args):
         ms_r = float(tr.item())/args.steps
         resident = {"value": world*n*nf/(ms_r*1e-3), "unit": "evals/s", "ms_per_step": ms_r,
                     "launches_per_step": (shard.launches - l0)//args.steps,
-                    "what": ("device-resident drift-kick-drift step, state never leaves HBM: " +
-                             ("one fused sweep (rebx_b200_leapfrog_step)" if world == 1 else "drift, body refresh + broadcast, central gravity, force sweep, kick, drift"))}
+                    "what": ("device-resident drift-kick-drift step, state never leaves HBM: one fused sweep (rebx_b200_leapfrog_step" +
+                             (")" if world == 1 else "'s two halves with the all-reduce of the back-reaction sums between them; the central body's record is replicated and advanced by every rank)"))}
 
     # ---- end-to-end leg: the REBOUND-facing call on host particle arrays ---------------------------
     e2e = None
@@ -320,7 +325,8 @@ def run_ours(args):
                                         "index ranges; per step an all-gather of 7 mass moments and of 3 back-reaction sums per rank (JACOBI: exclusive prefix / suffix over ranks; BARYCENTRIC: all-reduce)")},
                 "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "resident_step": resident, "gpu_launches": gpu_launches,
                 "clocks": clocks.summary()}
-        print(json.dumps(line), flush=True)
+        sys.stdout.flush()
+        os.write(json_fd, (json.dumps(line) + "\n").encode())
     if world > 1:
         dist.destroy_process_group()
 

@@ -219,6 +219,14 @@ int rebx_b200_gather_bodies(const rebx_b200_state* st, double* bodies, int nbodi
  * apply_backreaction + kick + drift.  Returns cudaErrorNotSupported for a stack without a fused
  * instantiation. */
 int rebx_b200_leapfrog_step(const rebx_b200_pass* pass, double dt, double G, double softening, void* workspace, void* stream, int* launches);
+/* The same step in two halves for an ensemble SHARDED by index range, every shard holding a replica of
+ * the central body's record(s): `_sweep` advances the shard's particles and leaves this shard's
+ * back-reaction sums in fx[].backreaction; the caller all-reduces those (nothing to exchange for a stack
+ * without back-reaction, e.g. radiation_forces); `_body` then advances the central body -- its record(s),
+ * and its state element on the shard that owns it -- identically on every rank.
+ * rebx_b200_leapfrog_step == _sweep followed by _body. */
+int rebx_b200_leapfrog_sweep(const rebx_b200_pass* pass, double dt, double G, double softening, void* workspace, void* stream, int* launches);
+int rebx_b200_leapfrog_body(const rebx_b200_pass* pass, double dt, void* stream, int* launches);
 
 /* Integrates the velocities across `dt` under the stacked effects of `pass` alone, positions fixed --
  * the device form of the reference's integrate_force operator and its schemes

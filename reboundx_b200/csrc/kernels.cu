@@ -1264,17 +1264,37 @@ int rebx_b200_add_uniform(const rebx_b200_state* st, const double* delta, void* 
     return err;
 }
 
-int rebx_b200_leapfrog_step(const rebx_b200_pass* pass, double dt, double G, double softening, void* workspace, void* stream, int* launches) {
-    if (!pass || !workspace) return cudaErrorInvalidValue;
+// The fused step in two halves, so that a SHARDED caller can all-reduce the back-reaction sums between
+// them: (1) the sweep over the shard's particles + the reduction of this shard's back-reaction;
+// (2) the central body's own step from the (summed) back-reaction, run identically by every rank on
+// its replica of the body record.  A stack without back-reaction needs no exchange at all.
+static int leapfrog_combo(const rebx_b200_pass* pass, const Combo** combo_out, unsigned* red_mask, bool* any) {
+    if (!pass) return cudaErrorInvalidValue;
     const int bad = check_pass(*pass);
     if (bad) return bad;
     const rebx_b200_pass& P = *pass;
     if (!P.st.vx || !P.st.vy || !P.st.vz) return cudaErrorInvalidValue;
-    if (P.st.n == 0) return 0;
     const Combo* combo = find_combo(P.fx, P.n_effects);
     if (!combo) return cudaErrorNotSupported;            // stack not instantiated: use the separate sweeps
     for (int e = 1; e < P.n_effects; e++) if (P.fx[e].body == nullptr) return cudaErrorInvalidValue;
+    *combo_out = combo;
+    *red_mask = 0; *any = false;
+    for (int j = 0; j < P.n_effects; j++) if (combo->red[j]) { *red_mask |= 1u << j; if (P.fx[j].backreaction) *any = true; }
+    return 0;
+}
+
+int rebx_b200_leapfrog_sweep(const rebx_b200_pass* pass, double dt, double G, double softening, void* workspace, void* stream, int* launches) {
+    if (!workspace) return cudaErrorInvalidValue;
+    const Combo* combo = nullptr; unsigned red_mask = 0; bool any = false;
+    const int rc = leapfrog_combo(pass, &combo, &red_mask, &any);
+    if (rc) return rc;
+    const rebx_b200_pass& P = *pass;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (P.st.n == 0) {      // an empty shard contributes zero back-reaction
+        for (int j = 0; j < P.n_effects; j++)
+            if (((red_mask >> j) & 1u) && P.fx[j].backreaction) cudaMemsetAsync(P.fx[j].backreaction, 0, 3*sizeof(double), s);
+        return cudaGetLastError();
+    }
     bool heavy = false;
     for (int j = 0; j < P.n_effects; j++) if (P.fx[j].kind >= REBX_B200_YARKOVSKY) heavy = true;
     const int vsel = (pass_is_vectorizable(P) && !heavy) ? 1 : 0;
@@ -1284,15 +1304,28 @@ int rebx_b200_leapfrog_step(const rebx_b200_pass* pass, double dt, double G, dou
     const int grid = grid_for(reinterpret_cast<const void*>(fn), (P.st.n + V - 1)/V);
     fn<<<grid, kThreads, 0, s>>>(P, static_cast<double*>(workspace), S);
     int nl = 1;
-    unsigned red_mask = 0;
-    bool any = false;
-    for (int j = 0; j < P.n_effects; j++) if (combo->red[j]) { red_mask |= 1u << j; if (P.fx[j].backreaction) any = true; }
     if (any) { finalize_kernel<<<1, kThreads, 0, s>>>(P, static_cast<const double*>(workspace), grid, red_mask); nl++; }
-    step_body_kernel<<<1, 32, 0, s>>>(P, S, any ? red_mask : 0u);
-    nl++;
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) *launches += nl;
     return err;
+}
+
+int rebx_b200_leapfrog_body(const rebx_b200_pass* pass, double dt, void* stream, int* launches) {
+    const Combo* combo = nullptr; unsigned red_mask = 0; bool any = false;
+    const int rc = leapfrog_combo(pass, &combo, &red_mask, &any);
+    if (rc) return rc;
+    const StepArgs S = {dt, 0.5*dt, 0.0, 0.0};
+    step_body_kernel<<<1, 32, 0, static_cast<cudaStream_t>(stream)>>>(*pass, S, any ? red_mask : 0u);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+int rebx_b200_leapfrog_step(const rebx_b200_pass* pass, double dt, double G, double softening, void* workspace, void* stream, int* launches) {
+    if (pass && pass->st.n == 0) return check_pass(*pass);
+    int rc = rebx_b200_leapfrog_sweep(pass, dt, G, softening, workspace, stream, launches);
+    if (rc == 0) rc = rebx_b200_leapfrog_body(pass, dt, stream, launches);
+    return rc;
 }
 
 // One force evaluation of the stack on stage arrays (v, a): what the reference's schemes do with

@@ -346,14 +346,28 @@ class Shard:
         k += self.drift(0.5*dt)
         return k
 
-    def fused_leapfrog_step(self, dt, G, softening=0.0, stream=None):
+    def fused_leapfrog_step(self, dt, G, softening=0.0, stream=None, group=None):
         """The same step as `leapfrog_step` in one sweep (rebx_b200_leapfrog_step): the acceleration
-        never touches HBM.  Single shard only."""
+        never touches HBM.  Sharded (a process group with more than one rank): every rank sweeps its own
+        particles, the back-reaction sums are all-reduced -- no exchange at all for a stack without
+        back-reaction such as radiation_forces -- and every rank advances its replica of the central
+        body identically (rebx_b200_leapfrog_sweep / _body)."""
         n = c_int(0)
-        self.lib.rebx_b200_leapfrog_step.restype = c_int
-        rc = self.lib.rebx_b200_leapfrog_step(ctypes.byref(self._pass), c_double(dt), c_double(G), c_double(softening),
-                                              c_void_p(self.workspace.data_ptr()), c_void_p(self._stream(stream).cuda_stream), ctypes.byref(n))
-        self._check(rc, "rebx_b200_leapfrog_step")
+        s = c_void_p(self._stream(stream).cuda_stream)
+        ws = c_void_p(self.workspace.data_ptr())
+        if self.standalone or sharding._world(group)[0] == 1:
+            self.lib.rebx_b200_leapfrog_step.restype = c_int
+            rc = self.lib.rebx_b200_leapfrog_step(ctypes.byref(self._pass), c_double(dt), c_double(G), c_double(softening), ws, s, ctypes.byref(n))
+            self._check(rc, "rebx_b200_leapfrog_step")
+        else:
+            self.lib.rebx_b200_leapfrog_sweep.restype = c_int
+            self.lib.rebx_b200_leapfrog_body.restype = c_int
+            rc = self.lib.rebx_b200_leapfrog_sweep(ctypes.byref(self._pass), c_double(dt), c_double(G), c_double(softening), ws, s, ctypes.byref(n))
+            self._check(rc, "rebx_b200_leapfrog_sweep")
+            if any(kind != 1 and kind != 4 for kind in self.kinds):
+                self.reduce_backreaction(group)
+            rc = self.lib.rebx_b200_leapfrog_body(ctypes.byref(self._pass), c_double(dt), s, ctypes.byref(n))
+            self._check(rc, "rebx_b200_leapfrog_body")
         self.launches += n.value
         return n.value
 
