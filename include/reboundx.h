@@ -8,7 +8,7 @@
  * code and the unmodified Python wrapper bind to this library exactly as they bind to the
  * reference's libreboundx.  Each declaration cites the reference declaration it replaces.
  *
- * Out of scope: operators, splitting integrators, binary I/O,
+ * Out of scope: operators, splitting integrators,
  * interpolation and the other built-in forces.  Their declarations are intentionally
  * absent; a custom force (user function pointer) still runs on the host through the same
  * dispatcher.
@@ -17,6 +17,7 @@
 #define REBOUNDX_B200_REBOUNDX_H
 
 #include <stdint.h>
+#include <stdio.h>
 #include "rebound.h"
 
 #ifdef __cplusplus
@@ -172,6 +173,43 @@ double rebx_central_force_potential(struct rebx_extras* const rebx);
 double rebx_rad_calc_beta(const double G, const double c, const double source_mass, const double source_luminosity, const double radius, const double density, const double Q_pr);
 double rebx_rad_calc_particle_radius(const double G, const double c, const double source_mass, const double source_luminosity, const double beta, const double density, const double Q_pr);
 double rebx_calculate_planet_trap(const double r, const double dedge, const double hedge);
+
+/* ---- binary state files: reference src/reboundx.h:112-165,263-266,
+ * 720-769; written from scratch in reboundx_b200/csrc/binary_io.cpp, byte-compatible with the files of
+ * the reference's src/output.c / src/input.c.  Operators are out of scope: their lists are written empty
+ * and skipped (with the reference's OPERATOR_NOT_LOADED warning) on load. */
+enum rebx_binary_field_type {
+    REBX_BINARY_FIELD_TYPE_NONE = 0, REBX_BINARY_FIELD_TYPE_OPERATOR = 1, REBX_BINARY_FIELD_TYPE_PARTICLE = 2,
+    REBX_BINARY_FIELD_TYPE_REBX_STRUCTURE = 3, REBX_BINARY_FIELD_TYPE_PARAM = 4, REBX_BINARY_FIELD_TYPE_NAME = 5,
+    REBX_BINARY_FIELD_TYPE_PARAM_TYPE = 6, REBX_BINARY_FIELD_TYPE_PARAM_VALUE = 7, REBX_BINARY_FIELD_TYPE_END = 8,
+    REBX_BINARY_FIELD_TYPE_PARTICLE_INDEX = 9, REBX_BINARY_FIELD_TYPE_REBX_INTEGRATOR = 10, REBX_BINARY_FIELD_TYPE_FORCE_TYPE = 11,
+    REBX_BINARY_FIELD_TYPE_OPERATOR_TYPE = 12, REBX_BINARY_FIELD_TYPE_STEP = 13, REBX_BINARY_FIELD_TYPE_STEP_DT_FRACTION = 14,
+    REBX_BINARY_FIELD_TYPE_REGISTERED_PARAM = 15, REBX_BINARY_FIELD_TYPE_ADDITIONAL_FORCE = 16, REBX_BINARY_FIELD_TYPE_PARAM_LIST = 17,
+    REBX_BINARY_FIELD_TYPE_REGISTERED_PARAMETERS = 18, REBX_BINARY_FIELD_TYPE_ALLOCATED_FORCES = 19,
+    REBX_BINARY_FIELD_TYPE_ALLOCATED_OPERATORS = 20, REBX_BINARY_FIELD_TYPE_ADDITIONAL_FORCES = 21,
+    REBX_BINARY_FIELD_TYPE_PRE_TIMESTEP_MODIFICATIONS = 22, REBX_BINARY_FIELD_TYPE_POST_TIMESTEP_MODIFICATIONS = 23,
+    REBX_BINARY_FIELD_TYPE_PARTICLES = 24, REBX_BINARY_FIELD_TYPE_FORCE = 25, REBX_BINARY_FIELD_TYPE_SNAPSHOT = 26
+};
+enum rebx_input_binary_messages {
+    REBX_INPUT_BINARY_WARNING_NONE = 0, REBX_INPUT_BINARY_ERROR_NOFILE = 1, REBX_INPUT_BINARY_ERROR_CORRUPT = 2,
+    REBX_INPUT_BINARY_ERROR_NO_MEMORY = 4, REBX_INPUT_BINARY_ERROR_REBX_NOT_LOADED = 8,
+    REBX_INPUT_BINARY_ERROR_REGISTERED_PARAM_NOT_LOADED = 16, REBX_INPUT_BINARY_WARNING_PARAM_NOT_LOADED = 32,
+    REBX_INPUT_BINARY_WARNING_PARTICLE_PARAMS_NOT_LOADED = 64, REBX_INPUT_BINARY_WARNING_FORCE_NOT_LOADED = 128,
+    REBX_INPUT_BINARY_WARNING_OPERATOR_NOT_LOADED = 256, REBX_INPUT_BINARY_WARNING_STEP_NOT_LOADED = 512,
+    REBX_INPUT_BINARY_WARNING_ADDITIONAL_FORCE_NOT_LOADED = 1024, REBX_INPUT_BINARY_WARNING_FIELD_UNKNOWN = 2048,
+    REBX_INPUT_BINARY_WARNING_LIST_UNKNOWN = 4096, REBX_INPUT_BINARY_WARNING_PARAM_VALUE_NULL = 8192,
+    REBX_INPUT_BINARY_WARNING_VERSION = 16384, REBX_INPUT_BINARY_WARNING_FORCE_PARAM_NOT_LOADED = 32768
+};
+struct rebx_binary_field {
+    enum rebx_binary_field_type type;
+    long size;                          /* bytes that follow this header (children + END for a container) */
+};
+void rebx_output_binary(struct rebx_extras* rebx, char* filename);                                                  /* src/output.c:272 */
+struct rebx_extras* rebx_create_extras_from_binary(struct reb_simulation* sim, const char* const filename);        /* src/input.c:634 */
+void rebx_init_extras_from_binary(struct rebx_extras* rebx, const char* const filename, enum rebx_input_binary_messages* warnings); /* src/input.c:617 */
+FILE* rebx_input_inspect_binary(const char* const filename, enum rebx_input_binary_messages* warnings);            /* src/input.c:692 */
+struct rebx_binary_field rebx_input_read_binary_field(FILE* inf);                                                  /* src/input.c:702 */
+void rebx_input_skip_binary_field(FILE* inf, long field_size);                                                     /* src/input.c:56 */
 
 /* ---- additions of this build (all keep the rebx_ prefix, reference .github/workflows/c.yml:34) */
 /* Tell the SoA parameter tables that a value was changed through a raw pointer obtained

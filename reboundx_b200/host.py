@@ -299,11 +299,35 @@ class Force:
         return Params(self._rebx, ap_field)
 
 
+# reference reboundx/extras.py:13-29 (bit, is it an error) -- messages as in src/input.c:644-689
+REBX_BINARY_WARNINGS = [
+    (True, 1, "REBOUNDx: Cannot open binary file. Check filename."),
+    (True, 2, "REBOUNDx: Binary file is unreadable. Please open an issue on Github mentioning the version of REBOUND and REBOUNDx you are using and include the binary file."),
+    (True, 4, "REBOUNDx: Ran out of system memory."),
+    (True, 8, "REBOUNDx: REBOUNDx structure couldn't be loaded."),
+    (True, 16, "REBOUNDx: At least one registered parameter was not loaded."),
+    (False, 32, "REBOUNDx: At least one force or operator parameter was not loaded from the binary file."),
+    (False, 64, "REBOUNDx: At least one particle's parameters were not loaded from the binary file."),
+    (False, 128, "REBOUNDx: At least one force was not loaded from the binary file."),
+    (False, 256, "REBOUNDx: At least one operator was not loaded from the binary file."),
+    (False, 512, "REBOUNDx: At least one operator step was not loaded from the binary file."),
+    (False, 1024, "REBOUNDx: At least one force was not added to the simulation."),
+    (False, 2048, "REBOUNDx: Unknown field found in binary file. Any unknown fields not loaded."),
+    (False, 4096, "REBOUNDx: Unknown list in the REBOUNDx structure wasn't loaded."),
+    (False, 8192, "REBOUNDx: The value of at least one parameter was not loaded."),
+    (False, 16384, "REBOUNDx: Binary file was saved with a different version of REBOUNDx."),
+    (False, 32768, "REBOUNDx: A force parameter failed to load from the list of REBOUNDx implemented forces."),
+]
+
+
 class Extras:
     """Mirror of reboundx.Extras for the force path, bound to `lib` (default: this package's
     CUDA library)."""
 
-    def __init__(self, sim, lib=None):
+    def __init__(self, sim, filename=None, lib=None):
+        """`filename`: recreate the state saved by `save()` (reference reboundx/extras.py:44-61): registered
+        parameters, forces with their parameters, the additional_forces order and every particle's parameters
+        come from the file; its warning bits become RuntimeError / RuntimeWarning like the reference's."""
         self._lib = lib = lib or _lib.load()
         self._sim = sim
         lib.rebx_attach.restype = POINTER(RebxExtras)
@@ -317,8 +341,27 @@ class Extras:
         lib.rebx_add_force.restype = c_int
         lib.rebx_remove_force.restype = c_int
         lib.rebx_len.restype = c_int
-        self._ptr = lib.rebx_attach(sim.ptr)
+        if filename is None:
+            self._ptr = lib.rebx_attach(sim.ptr)
+        else:
+            import warnings as _warnings
+            # like rebx_create_extras_from_binary: no default registrations, the file brings its own
+            self._owned = RebxExtras()
+            self._ptr = ctypes.pointer(self._owned)
+            lib.rebx_initialize(sim.ptr, self._ptr)
+            w = c_int(0)
+            lib.rebx_init_extras_from_binary(self._ptr, c_char_p(str(filename).encode()), ctypes.byref(w))
+            for major, bit, message in REBX_BINARY_WARNINGS:
+                if w.value & bit:
+                    if major:
+                        raise RuntimeError(message)
+                    _warnings.warn(message, RuntimeWarning)
         sim._extras_ref = self
+        self.process_messages()
+
+    def save(self, filename):
+        """Writes the REBOUNDx state to a binary file (reference reboundx/extras.py:151-156, src/output.c:272)."""
+        self._lib.rebx_output_binary(self._ptr, c_char_p(str(filename).encode()))
         self.process_messages()
 
     @classmethod
@@ -434,8 +477,13 @@ class Extras:
         return out[:n]
 
     def detach(self):
-        if self._ptr is not None:
-            self._lib.rebx_free(self._ptr)
+        if getattr(self, "_ptr", None) is not None:
+            if getattr(self, "_owned", None) is not None:     # Python-owned struct (loaded from a file): reference extras.py:63-66
+                self._lib.rebx_free_pointers(self._ptr)
+                self._lib.rebx_detach(self._ptr)
+                self._owned = None
+            else:
+                self._lib.rebx_free(self._ptr)
             self._ptr = None
             self._sim._extras_ref = None
 
