@@ -1115,7 +1115,7 @@ int rebx_b200_mass_moments(const rebx_b200_state* st, double* totals7, void* scr
     const int64_t ntiles = (st->n + kScanThreads - 1)/kScanThreads;
     double* rows = static_cast<double*>(scratch);
     moments_tile_kernel<<<(unsigned)ntiles, kScanThreads, 0, s>>>(*st, rows);
-    scan_tiles_kernel<7, false><<<1, 512, 0, s>>>(rows, ntiles, totals7);
+    scan_tiles_kernel<7, false><<<7, kTileScanThreads, 0, s>>>(rows, ntiles, totals7);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) *launches += 2;
     return err;
@@ -1157,7 +1157,7 @@ int rebx_b200_jacobi_moments(const rebx_b200_state* st, void* scratch, double* t
     if (st->n == 0) return totals7 ? cudaMemsetAsync(totals7, 0, 7*sizeof(double), s) : cudaSuccess;
     JacobiScratch J(scratch, st->n);
     moments_tile_kernel<<<(unsigned)J.ntiles, kScanThreads, 0, s>>>(*st, J.rows7);
-    scan_tiles_kernel<7, false><<<1, 512, 0, s>>>(J.rows7, J.ntiles, totals7 ? totals7 : J.totals);
+    scan_tiles_kernel<7, false><<<7, kTileScanThreads, 0, s>>>(J.rows7, J.ntiles, totals7 ? totals7 : J.totals);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) *launches += 2;
     return err;
@@ -1174,7 +1174,7 @@ int rebx_b200_jacobi_sweep(const rebx_b200_pass* pass, void* scratch, const doub
     if (!combo) return cudaErrorNotSupported;
     JacobiScratch J(scratch, P.st.n);
     combo->fn<<<(unsigned)J.ntiles, kScanThreads, 0, s>>>(P, J.rows7, J.tvec, J.rows3, carry7);
-    scan_tiles_kernel<3, true><<<1, 512, 0, s>>>(J.rows3, J.ntiles, tsum3 ? tsum3 : J.totals + 8);
+    scan_tiles_kernel<3, true><<<3, kTileScanThreads, 0, s>>>(J.rows3, J.ntiles, tsum3 ? tsum3 : J.totals + 8);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) *launches += 2;
     return err;

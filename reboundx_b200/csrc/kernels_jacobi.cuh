@@ -21,7 +21,7 @@ constexpr int kScanThreads = 256;
 
 // Exclusive scan of NC doubles per thread across a CTA of kScanThreads; returns the CTA total
 // in `total` (valid in every thread).  Fixed evaluation order => deterministic.
-template <int NC>
+template <int NC, int THREADS = kScanThreads>
 __device__ __forceinline__ void block_exclusive_scan(double (&v)[NC], double (&total)[NC], double (*s_warp)[NC]) {
     const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
     double incl[NC], excl[NC];
@@ -47,7 +47,7 @@ __device__ __forceinline__ void block_exclusive_scan(double (&v)[NC], double (&t
     for (int c = 0; c < NC; c++) {
         double before = 0.0, all = 0.0;
 #pragma unroll
-        for (int w = 0; w < kScanThreads/32; w++) {
+        for (int w = 0; w < THREADS/32; w++) {
             const double s = s_warp[w][c];
             if (w < warp) before += s;
             all += s;
@@ -58,7 +58,7 @@ __device__ __forceinline__ void block_exclusive_scan(double (&v)[NC], double (&t
 }
 
 // ---- mass moments: sum m, sum m r, sum m v ------------------------------------------------------
-// tile_sums[tile][7]; one tile = kScanThreads consecutive particles.
+// tile_sums[7][ntiles] (component-major, so the tile scan reads coalesced); one tile = kScanThreads consecutive particles.
 __global__ void __launch_bounds__(kScanThreads)
 moments_tile_kernel(rebx_b200_state st, double* __restrict__ tile_sums) {
     __shared__ double s_warp[kScanThreads/32][7];
@@ -71,45 +71,36 @@ moments_tile_kernel(rebx_b200_state st, double* __restrict__ tile_sums) {
     }
     double total[7];
     block_exclusive_scan<7>(v, total, s_warp);
-    if (threadIdx.x < 7) tile_sums[(size_t)blockIdx.x*7 + threadIdx.x] = total[threadIdx.x];
+#pragma unroll
+    for (int c = 0; c < 7; c++) if (threadIdx.x == c) tile_sums[(size_t)c*gridDim.x + blockIdx.x] = total[c];
 }
 
-// In-place exclusive scan over `ntiles` rows of NC doubles (forward, or backward when REV),
-// single CTA of 512 threads each owning a contiguous span.  totals[NC] gets the grand total.
+// In-place exclusive scan over the `ntiles` tile sums of NC components, stored component-major
+// rows[c*ntiles + tile] (forward over the tiles, or backward when REV).  One CTA walks the tiles in chunks of
+// kTileScanThreads, thread t <-> tile chunk*kTileScanThreads + t, so every access is coalesced (a first
+// version gave each thread a contiguous span of [tile][NC] rows: 86 k uncoalesced line accesses from one SM,
+// 43 us for 3907 tiles); the next chunk is loaded before the current one is scanned.  Fixed order =>
+// deterministic.  totals[NC] gets the grand total.
+// The components are independent: CTA c scans component c (grid = NC), so the CTAs run side by side.
+constexpr int kTileScanThreads = 1024;
 template <int NC, bool REV>
-__global__ void __launch_bounds__(512)
+__global__ void __launch_bounds__(kTileScanThreads)
 scan_tiles_kernel(double* __restrict__ rows, int64_t ntiles, double* __restrict__ totals) {
-    __shared__ double s_part[512][NC];
+    __shared__ double s_warp[kTileScanThreads/32][1];
     const int t = threadIdx.x;
-    const int64_t span = (ntiles + 511)/512;
-    const int64_t lo = (int64_t)t*span, hi = (lo + span < ntiles) ? lo + span : ntiles;
-    auto row = [&](int64_t i) { return REV ? (ntiles - 1 - i) : i; };
-    double acc[NC];
-#pragma unroll
-    for (int c = 0; c < NC; c++) acc[c] = 0.0;
-    for (int64_t i = lo; i < hi; i++)
-#pragma unroll
-        for (int c = 0; c < NC; c++) acc[c] += rows[(size_t)row(i)*NC + c];
-#pragma unroll
-    for (int c = 0; c < NC; c++) s_part[t][c] = acc[c];
-    __syncthreads();
-    if (t < NC) {                         // serial scan of the 512 partials, one component per thread
-        double run = 0.0;
-        for (int i = 0; i < 512; i++) { const double x = s_part[i][t]; s_part[i][t] = run; run += x; }
-        if (totals) totals[t] = run;
+    double* __restrict__ comp = rows + (size_t)blockIdx.x*ntiles;
+    auto at = [&](int64_t i) { return REV ? (ntiles - 1 - i) : i; };
+    double carry = 0.0;
+    double nx = (t < ntiles) ? comp[at(t)] : 0.0;
+    for (int64_t base = 0; base < ntiles; base += kTileScanThreads) {
+        const int64_t i = base + t, inext = i + kTileScanThreads;
+        double x[1] = {nx}, total[1];
+        nx = (inext < ntiles) ? comp[at(inext)] : 0.0;
+        block_exclusive_scan<1, kTileScanThreads>(x, total, s_warp);       // x := sum of the chunk's tiles in front of tile i
+        if (i < ntiles) comp[at(i)] = carry + x[0];
+        carry += total[0];
     }
-    __syncthreads();
-#pragma unroll
-    for (int c = 0; c < NC; c++) acc[c] = s_part[t][c];
-    for (int64_t i = lo; i < hi; i++) {
-#pragma unroll
-        for (int c = 0; c < NC; c++) {
-            const size_t idx = (size_t)row(i)*NC + c;
-            const double x = rows[idx];
-            rows[idx] = acc[c];
-            acc[c] += x;
-        }
-    }
+    if (totals && t == 0) totals[blockIdx.x] = carry;
 }
 
 // Body record of the barycentre from the grand totals (reb_simulation_com restated as a
@@ -128,13 +119,14 @@ __global__ void com_body_kernel(const double* __restrict__ totals, double* __res
 
 // ---- Jacobi sweep --------------------------------------------------------------------------------
 template <int K>
-__device__ __forceinline__ Vec3 damping_force(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body, const Particle& p, int64_t k) {
+__device__ __forceinline__ Vec3 damping_force(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body, const Particle& p, int64_t k,
+                                              const Orbit* so) {
     if constexpr (K == REBX_B200_MODIFY_ORBITS) {
-        return modify_orbits(fx, org, body, p, __ldcs(fx.tab[0] + k), __ldcs(fx.tab[1] + k), __ldcs(fx.tab[2] + k));
+        return modify_orbits(fx, org, body, p, __ldcs(fx.tab[0] + k), __ldcs(fx.tab[1] + k), __ldcs(fx.tab[2] + k), so);
     } else if constexpr (K == REBX_B200_GAS_DAMPING) {
-        return gas_damping(fx, org, body, p, __ldcs(fx.tab[0] + k));
+        return gas_damping(fx, org, body, p, __ldcs(fx.tab[0] + k), so);
     } else if constexpr (K == REBX_B200_TYPE_I) {
-        return type_I_migration(fx, org, body, p);
+        return type_I_migration(fx, org, body, p, so);
     } else if constexpr (K == REBX_B200_EXP_MIGRATION) {
         return exponential_migration(fx, org, body, p, __ldcs(fx.tab[0] + k), __ldcs(fx.tab[1] + k), __ldcs(fx.tab[2] + k));
     } else {
@@ -142,8 +134,8 @@ __device__ __forceinline__ Vec3 damping_force(const rebx_b200_effect& fx, const 
     }
 }
 
-// tile_prefix[tile][7]: exclusive prefix of the mass moments at the tile's first particle.
-// Writes a += f (particle's own force), tvec[3][n] = t_i, tile_tsums[tile][3] = sum of t in the tile.
+// tile_prefix[7][ntiles]: exclusive prefix of the mass moments at the tile's first particle.
+// Writes a += f (particle's own force), tvec[3][n] = t_i, tile_tsums[3][ntiles] = sum of t in the tile.
 template <int K0, int K1, int K2>
 __global__ void __launch_bounds__(kScanThreads)
 jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __restrict__ tile_prefix,
@@ -161,11 +153,11 @@ jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __re
     block_exclusive_scan<7>(v, total, s_warp);
     double body[REBX_B200_BODY_DOUBLES];
     // carry7: mass moments of the shards in front of this one (index ranges below index_base), or NULL
-    double M = tile_prefix[(size_t)blockIdx.x*7] + v[0];                // mass interior to particle k
+    double M = tile_prefix[blockIdx.x] + v[0];                // mass interior to particle k
     if (carry7) M = carry7[0] + M;
 #pragma unroll
     for (int j = 0; j < 6; j++) {
-        double S = tile_prefix[(size_t)blockIdx.x*7 + 1 + j] + v[1 + j];
+        double S = tile_prefix[(size_t)(1 + j)*gridDim.x + blockIdx.x] + v[1 + j];
         if (carry7) S = carry7[1 + j] + S;
         body[REBX_B200_BODY_X + j] = (M > 0.) ? S/M : S;
     }
@@ -179,14 +171,20 @@ jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __re
         const double mr = p.m/(M + p.m);
         Vec3 f;
         const Origin org = load_origin(body);
-        f = damping_force<K0>(P.fx[0], org, body, p, k);
+        // stacked damping effects evaluate the SAME two-body elements (same particle, same interior centre of
+        // mass, same G): computed once, bit-identical to each effect's own call (as in pass_kernel)
+        constexpr int NDAMP = (K0 >= 5 && K0 <= 7) + (K1 >= 5 && K1 <= 7) + (K2 >= 5 && K2 <= 7);
+        Orbit oc;
+        const Orbit* so = nullptr;
+        if constexpr (NDAMP >= 2) { oc = orbit_from_particle<true, true, false>(P.fx[0].scal[0], p, org, body); so = &oc; }
+        f = damping_force<K0>(P.fx[0], org, body, p, k, so);
         a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
         if constexpr (K1 != 0) {
-            f = damping_force<K1>(P.fx[1], org, body, p, k);
+            f = damping_force<K1>(P.fx[1], org, body, p, k, so);
             a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
         }
         if constexpr (K2 != 0) {
-            f = damping_force<K2>(P.fx[2], org, body, p, k);
+            f = damping_force<K2>(P.fx[2], org, body, p, k, so);
             a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
         }
         st.ax[k] = a.x; st.ay[k] = a.y; st.az[k] = a.z;
@@ -196,7 +194,8 @@ jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __re
     double tt[3], tot3[3];
     tt[0] = t[0]; tt[1] = t[1]; tt[2] = t[2];
     block_exclusive_scan<3>(tt, tot3, reinterpret_cast<double (*)[3]>(&s_warp[0][0]));
-    if (threadIdx.x < 3) tile_tsums[(size_t)blockIdx.x*3 + threadIdx.x] = tot3[threadIdx.x];
+#pragma unroll
+    for (int c = 0; c < 3; c++) if (threadIdx.x == c) tile_tsums[(size_t)c*gridDim.x + blockIdx.x] = tot3[c];
 }
 
 // a_j -= sum_{i >= j} t_i : in-tile reverse inclusive scan + exclusive suffix of the tiles behind.
@@ -214,9 +213,9 @@ jacobi_apply_kernel(rebx_b200_state st, const double* __restrict__ tvec, const d
     block_exclusive_scan<3>(t, tot, s_warp);
     if (live) {
         // carry3: sum of t over the shards behind this one (higher index ranges), or NULL
-        double s0 = tile_suffix[(size_t)blockIdx.x*3 + 0] + (t[0] + own[0]);
-        double s1 = tile_suffix[(size_t)blockIdx.x*3 + 1] + (t[1] + own[1]);
-        double s2 = tile_suffix[(size_t)blockIdx.x*3 + 2] + (t[2] + own[2]);
+        double s0 = tile_suffix[(size_t)0*gridDim.x + blockIdx.x] + (t[0] + own[0]);
+        double s1 = tile_suffix[(size_t)1*gridDim.x + blockIdx.x] + (t[1] + own[1]);
+        double s2 = tile_suffix[(size_t)2*gridDim.x + blockIdx.x] + (t[2] + own[2]);
         if (carry3) { s0 = carry3[0] + s0; s1 = carry3[1] + s1; s2 = carry3[2] + s2; }
         st.ax[k] -= s0; st.ay[k] -= s1; st.az[k] -= s2;
     }
