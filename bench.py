@@ -160,14 +160,35 @@ def run_reference(args):
     print(json.dumps(line), flush=True)
 
 
+def bind_to_gpu_numa_node(index):
+    """Pins this rank to the CPUs NVML reports as local to GPU `index` BEFORE the host particle arrays are
+    allocated, so that their pages (first touch) and the DMA of the host-facing leg stay on the GPU's own
+    NUMA node.  Returns a short description for the JSON line (None when NVML has nothing to say)."""
+    try:
+        import pynvml
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(index)
+        ncpu = os.cpu_count() or 1
+        words = pynvml.nvmlDeviceGetCpuAffinity(h, (ncpu + 63)//64)
+        cpus = {64*w + b for w, word in enumerate(words) for b in range(64) if (word >> b) & 1}
+        cpus &= os.sched_getaffinity(0)
+        if cpus and len(cpus) < len(os.sched_getaffinity(0)):
+            os.sched_setaffinity(0, cpus)
+            return f"rank bound to the {len(cpus)} CPUs local to GPU {index}"
+    except Exception:
+        pass
+    return None
+
+
 def run_ours(args):
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    rank = int(os.environ.get("RANK", "0"))
+    local = int(os.environ.get("LOCAL_RANK", "0"))
+    numa = bind_to_gpu_numa_node(local) if world > 1 else None
     import torch
     import torch.distributed as dist
     from reboundx_b200 import device, scenarios, workloads
 
-    world = int(os.environ.get("WORLD_SIZE", "1"))
-    rank = int(os.environ.get("RANK", "0"))
-    local = int(os.environ.get("LOCAL_RANK", "0"))
     if not torch.cuda.is_available():
         raise SystemExit("bench.py: no CUDA device; the force path has no CPU fallback")
     torch.cuda.set_device(local)
@@ -304,6 +325,8 @@ def run_ours(args):
                "ms_per_step": dt/steps*1e3, "steps": steps,
                "launches_per_step": (s1["launches"] - s0["launches"])//steps,
                "call": "sim->additional_forces(sim) == rebx_additional_forces, host AoS particles (cudaHostRegister-pinned)"}
+        if numa:
+            e2e["numa"] = numa
         rebx.detach()
         sim.free()
 

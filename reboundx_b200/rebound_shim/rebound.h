@@ -149,8 +149,11 @@ int reb_shim_call_additional_forces(struct reb_simulation* r);
  * simulation `nsteps` fixed steps of r->dt.  Accelerations = Newtonian gravity of the first N_active
  * bodies (all, when unset) on every particle + r->additional_forces(r).
  *   scheme 0: drift-kick-drift leapfrog, one force evaluation per step  (stands in for WHFast)
- *   scheme 1: classical RK4, four force evaluations per step           (stands in for IAS15's
- *             multi-evaluation high-order stepping)
+ *   scheme 1: classical RK4, four force evaluations per step
+ *   scheme 2: 15th-order Gauss-Radau predictor-corrector, fixed step   (the scheme behind IAS15, epsilon = 0:
+ *             7 force evaluations per sweep over the nodes, sweeps repeated to convergence)
+ *   scheme 3: Wisdom-Holman drift-kick-drift: Kepler drifts about particle 0 + kicks by additional_forces
+ *             only (the splitting behind WHFast, one massive central body, N_active = 1)
  * Used to compare trajectories between two force implementations with everything else equal. */
 void reb_shim_integrate(struct reb_simulation* r, int nsteps, int scheme);
 /* Wall-clock seconds for `reps` calls of r->additional_forces(r) (best single call). */

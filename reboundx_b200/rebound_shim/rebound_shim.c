@@ -443,7 +443,175 @@ static void shim_accelerations(struct reb_simulation* r){
     if (r->additional_forces) r->additional_forces(r);
 }
 
+/* ---- scheme 2: 15th-order Gauss-Radau predictor-corrector with a FIXED step (the scheme behind
+ * REBOUND's IAS15, Everhart 1985 / Rein & Spiegel 2015, without its step-size control, i.e.
+ * epsilon = 0).  Written from the published algorithm: the acceleration along the step is the
+ * polynomial a(s) = a0 + b0 s + ... + b6 s^7 (s in [0,1]) through the 8 Gauss-Radau nodes h_n; its
+ * Newton form a0 + g0 s + g1 s(s-h1) + ... is updated node by node from divided differences, the b's
+ * follow from the g's through the coefficients of prod_{i<=j}(s - h_i), and the sweep over the nodes
+ * is repeated until b6 stops changing.  The coefficient tables are generated from the nodes here. */
+static const double gr_h[8] = {0.0, 0.0562625605369221464656521910318, 0.180240691736892364987579942780,
+                               0.352624717113169637373907769648, 0.547153626330555383001448554766,
+                               0.734210177215410531523210605558, 0.885320946839095768090359771030,
+                               0.977520613561287501891174488626};
+static double gr_rr[28];        /* h_j - h_k, j = 1..7, k = 0..j-1 */
+static double gr_c[7][7];       /* gr_c[j][k] = coefficient of s^k in prod_{i=1..j}(s - h_i) */
+static int gr_ready = 0;
+static void gr_setup(void){
+    if (gr_ready) return;
+    int idx = 0;
+    for (int j = 1; j < 8; j++) for (int k = 0; k < j; k++) gr_rr[idx++] = gr_h[j] - gr_h[k];
+    for (int j = 0; j < 7; j++) for (int k = 0; k < 7; k++) gr_c[j][k] = 0.;
+    gr_c[0][0] = 1.;
+    for (int j = 1; j < 7; j++)
+        for (int k = 0; k <= j; k++)
+            gr_c[j][k] = (k > 0 ? gr_c[j-1][k-1] : 0.) - gr_h[j]*(k < j ? gr_c[j-1][k] : 0.);
+    gr_ready = 1;
+}
+
+static void shim_gauss_radau(struct reb_simulation* r, int nsteps){
+    gr_setup();
+    const size_t N = r->N, M = 3*N;
+    struct reb_particle* p = r->particles;
+    const double dt = r->dt;
+    double* x0 = malloc(M*sizeof(double)); double* v0 = malloc(M*sizeof(double)); double* a0 = malloc(M*sizeof(double));
+    double* b = calloc(7*M, sizeof(double)); double* g = calloc(7*M, sizeof(double));
+    for (int s = 0; s < nsteps; s++){
+        const double t0 = r->t;
+        shim_accelerations(r);
+        for (size_t i = 0; i < N; i++){
+            x0[3*i] = p[i].x; x0[3*i+1] = p[i].y; x0[3*i+2] = p[i].z;
+            v0[3*i] = p[i].vx; v0[3*i+1] = p[i].vy; v0[3*i+2] = p[i].vz;
+            a0[3*i] = p[i].ax; a0[3*i+1] = p[i].ay; a0[3*i+2] = p[i].az;
+        }
+        /* g (and so b) of the previous step are the first guess of this one */
+        for (int it = 0; it < 20; it++){
+            double max_db6 = 0., max_a = 0.;
+            for (int n = 1; n < 8; n++){
+                const double h = gr_h[n];
+                for (size_t q = 0; q < M; q++){
+                    const double* bq = b + q;
+                    const double xs = x0[q] + dt*h*(v0[q] + dt*h*(a0[q]/2. + h*(bq[0]/6. + h*(bq[M]/12. + h*(bq[2*M]/20. + h*(bq[3*M]/30.
+                                      + h*(bq[4*M]/42. + h*(bq[5*M]/56. + h*bq[6*M]/72.))))))));
+                    const double vs = v0[q] + dt*h*(a0[q] + h*(bq[0]/2. + h*(bq[M]/3. + h*(bq[2*M]/4. + h*(bq[3*M]/5.
+                                      + h*(bq[4*M]/6. + h*(bq[5*M]/7. + h*bq[6*M]/8.)))))));
+                    struct reb_particle* pi = &p[q/3];
+                    switch (q % 3){ case 0: pi->x = xs; pi->vx = vs; break; case 1: pi->y = xs; pi->vy = vs; break; default: pi->z = xs; pi->vz = vs; }
+                }
+                r->t = t0 + h*dt;
+                shim_accelerations(r);
+                const double* rr = gr_rr + (n-1)*n/2;
+                for (size_t q = 0; q < M; q++){
+                    const struct reb_particle* pi = &p[q/3];
+                    const double a = (q % 3 == 0) ? pi->ax : ((q % 3 == 1) ? pi->ay : pi->az);
+                    double gk = (a - a0[q])/rr[0];
+                    for (int m = 0; m < n-1; m++) gk = (gk - g[(size_t)m*M + q])/rr[m+1];
+                    const double dg = gk - g[(size_t)(n-1)*M + q];
+                    g[(size_t)(n-1)*M + q] = gk;
+                    for (int k = 0; k < n; k++) b[(size_t)k*M + q] += dg*gr_c[n-1][k];
+                    if (n == 7){
+                        if (fabs(dg) > max_db6) max_db6 = fabs(dg);
+                        if (fabs(a) > max_a) max_a = fabs(a);
+                    }
+                }
+            }
+            if (max_a == 0. || max_db6/max_a < 1e-16) break;
+        }
+        for (size_t q = 0; q < M; q++){
+            const double* bq = b + q;
+            const double xs = x0[q] + dt*v0[q] + dt*dt*(a0[q]/2. + bq[0]/6. + bq[M]/12. + bq[2*M]/20. + bq[3*M]/30. + bq[4*M]/42. + bq[5*M]/56. + bq[6*M]/72.);
+            const double vs = v0[q] + dt*(a0[q] + bq[0]/2. + bq[M]/3. + bq[2*M]/4. + bq[3*M]/5. + bq[4*M]/6. + bq[5*M]/7. + bq[6*M]/8.);
+            struct reb_particle* pi = &p[q/3];
+            switch (q % 3){ case 0: pi->x = xs; pi->vx = vs; break; case 1: pi->y = xs; pi->vy = vs; break; default: pi->z = xs; pi->vz = vs; }
+        }
+        r->t = t0 + dt;
+        r->dt_last_done = dt;
+    }
+    free(x0); free(v0); free(a0); free(b); free(g);
+}
+
+/* ---- scheme 3: Wisdom-Holman drift-kick-drift for ONE massive central body (particle 0) and any
+ * number of light bodies -- the splitting behind REBOUND's WHFast, in heliocentric form: every body
+ * i >= 1 follows its Kepler orbit about particle 0 (mu = G (m_0 + m_i)) for dt/2, receives the kick
+ * dt * (a_i - a_0) of everything that is NOT that two-body attraction -- here only
+ * r->additional_forces -- and drifts another dt/2.  Particle 0 moves inertially and takes its own
+ * kick.  The Kepler drift solves the universal-variable Kepler equation by Newton iteration with
+ * Stumpff functions (Danby's formulation). */
+static void stumpff(double z, double* c0, double* c1, double* c2, double* c3){
+    int n = 0;
+    while (fabs(z) > 0.1){ z *= 0.25; n++; }
+    double C2 = (1. - z*(1. - z*(1. - z*(1. - z*(1. - z*(1. - z/182.)/132.)/90.)/56.)/30.)/12.)/2.;
+    double C3 = (1. - z*(1. - z*(1. - z*(1. - z*(1. - z*(1. - z/210.)/156.)/110.)/72.)/42.)/20.)/6.;
+    double C1 = 1. - z*C3, C0 = 1. - z*C2;
+    for (; n > 0; n--){
+        C3 = (C2 + C0*C3)*0.25;
+        C2 = C1*C1*0.5;
+        C1 = C0*C1;
+        C0 = 2.*C0*C0 - 1.;
+    }
+    *c0 = C0; *c1 = C1; *c2 = C2; *c3 = C3;
+}
+
+static void kepler_drift(double mu, double dt, double* x, double* v){
+    const double r0 = sqrt(x[0]*x[0] + x[1]*x[1] + x[2]*x[2]);
+    const double v2 = v[0]*v[0] + v[1]*v[1] + v[2]*v[2];
+    const double eta = x[0]*v[0] + x[1]*v[1] + x[2]*v[2];
+    const double beta = 2.*mu/r0 - v2;
+    double X = dt/r0, c0 = 1., c1 = 1., c2 = 0.5, c3 = 1./6., G1 = 0., G2 = 0., G3 = 0., rr = r0;
+    for (int it = 0; it < 60; it++){
+        stumpff(beta*X*X, &c0, &c1, &c2, &c3);
+        G1 = c1*X; G2 = c2*X*X; G3 = c3*X*X*X;
+        const double f = r0*G1 + eta*G2 + mu*G3 - dt;
+        rr = r0*c0 + eta*G1 + mu*G2;
+        const double dX = f/rr;
+        X -= dX;
+        if (fabs(dX) <= 1e-16*fabs(X)) break;
+    }
+    stumpff(beta*X*X, &c0, &c1, &c2, &c3);
+    G1 = c1*X; G2 = c2*X*X; G3 = c3*X*X*X;
+    rr = r0*c0 + eta*G1 + mu*G2;
+    const double f = 1. - mu*G2/r0, gg = dt - mu*G3;
+    const double fd = -mu*G1/(r0*rr), gd = 1. - mu*G2/rr;
+    for (int c = 0; c < 3; c++){
+        const double xn = f*x[c] + gg*v[c], vn = fd*x[c] + gd*v[c];
+        x[c] = xn; v[c] = vn;
+    }
+}
+
+static void shim_wh_half_drift(struct reb_simulation* r, double hdt){
+    struct reb_particle* p = r->particles;
+    const size_t N = r->N;
+    const double x0[3] = {p[0].x, p[0].y, p[0].z}, v0[3] = {p[0].vx, p[0].vy, p[0].vz};
+    const double x1[3] = {x0[0] + hdt*v0[0], x0[1] + hdt*v0[1], x0[2] + hdt*v0[2]};
+    for (size_t i = 1; i < N; i++){
+        double x[3] = {p[i].x - x0[0], p[i].y - x0[1], p[i].z - x0[2]};
+        double v[3] = {p[i].vx - v0[0], p[i].vy - v0[1], p[i].vz - v0[2]};
+        kepler_drift(r->G*(p[0].m + p[i].m), hdt, x, v);
+        p[i].x = x1[0] + x[0]; p[i].y = x1[1] + x[1]; p[i].z = x1[2] + x[2];
+        p[i].vx = v0[0] + v[0]; p[i].vy = v0[1] + v[1]; p[i].vz = v0[2] + v[2];
+    }
+    p[0].x = x1[0]; p[0].y = x1[1]; p[0].z = x1[2];
+}
+
+static void shim_wisdom_holman(struct reb_simulation* r, int nsteps){
+    struct reb_particle* p = r->particles;
+    const size_t N = r->N;
+    const double dt = r->dt;
+    for (int s = 0; s < nsteps; s++){
+        shim_wh_half_drift(r, 0.5*dt);
+        r->t += 0.5*dt;
+        for (size_t i = 0; i < N; i++){ p[i].ax = 0.; p[i].ay = 0.; p[i].az = 0.; }
+        if (r->additional_forces) r->additional_forces(r);
+        for (size_t i = 0; i < N; i++){ p[i].vx += dt*p[i].ax; p[i].vy += dt*p[i].ay; p[i].vz += dt*p[i].az; }
+        shim_wh_half_drift(r, 0.5*dt);
+        r->t += 0.5*dt;
+        r->dt_last_done = dt;
+    }
+}
+
 void reb_shim_integrate(struct reb_simulation* r, int nsteps, int scheme){
+    if (scheme == 2){ shim_gauss_radau(r, nsteps); return; }
+    if (scheme == 3){ shim_wisdom_holman(r, nsteps); return; }
     const size_t N = r->N;
     struct reb_particle* p = r->particles;
     const double dt = r->dt;

@@ -389,10 +389,12 @@ def _assert_trajectories_agree(a, b, tol=1e-10):
     assert np.max(dvel[live]/vel_scale[live]) <= tol, np.max(dvel[live]/vel_scale[live])
 
 
-@pytest.mark.parametrize("scheme", ["leapfrog", "rk4"])
+@pytest.mark.parametrize("scheme", ["leapfrog", "rk4", "wisdom_holman", "gauss_radau"])
 def test_trajectory_debris_disk_1000_steps(built, scheme):
     """Config 1a shape (Sun + 1000 dust grains, beta = 0.1, dt = 1e8 s): 10^3 steps with the CUDA force
-    vs the reference-compiled force, everything else identical (host harness, not REBOUND)."""
+    vs the reference-compiled force, everything else identical (host harness, not REBOUND).
+    wisdom_holman = the example's own scheme class (WHFast: Kepler drifts + kicks by the additional
+    force); gauss_radau = the 15th-order scheme behind IAS15 with a fixed step."""
     import os, sys
     sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
     import golden_io
@@ -406,8 +408,25 @@ def test_trajectory_debris_disk_1000_steps(built, scheme):
     assert np.array_equal(ours, ref)          # bit-exact forces => bit-exact trajectories
 
 
+def test_trajectory_circumplanetary_example_gauss_radau(built):
+    """Config 1b shape (reference examples/rad_forces_circumplanetary: Sun + Saturn + 2 grains, IAS15, the Sun
+    flagged as radiation source, N_active = 2): 10^3 fixed Gauss-Radau steps of 1/80 of the grains' orbit."""
+    import os, sys
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import golden_io
+    from oracle import oracle
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    case, _, _ = golden_io.load("rad_circumplanetary_example")
+    ours = _trajectory(case, None, 1000, "gauss_radau", 2.0e3, 2)
+    ref = _trajectory(case, oracle.ref_lib(), 1000, "gauss_radau", 2.0e3, 2)
+    _assert_trajectories_agree(ours, ref)
+    assert np.array_equal(ours, ref)
+
+
 @pytest.mark.parametrize("which", ["ring", "asteroids", "planetesimals_particle", "planetesimals_jacobi"])
-def test_trajectories_other_configs_1000_steps(built, which):
+@pytest.mark.parametrize("scheme", ["rk4", "gauss_radau", "wisdom_holman"])
+def test_trajectories_other_configs_1000_steps(built, which, scheme):
     from oracle import oracle
     from reboundx_b200 import workloads as W
     if not oracle.have_ref():
@@ -420,8 +439,10 @@ def test_trajectories_other_configs_1000_steps(built, which):
         w, add, coords, dt = W.planetesimal_disk(400), TRIO, "PARTICLE", 0.002
     else:
         w, add, coords, dt = W.planetesimal_disk(400), TRIO, "JACOBI", 0.002
-    ours = _trajectory(w, None, 1000, "rk4", dt, 1, add, coords)
-    ref = _trajectory(w, oracle.ref_lib(), 1000, "rk4", dt, 1, add, coords)
+    if scheme != "rk4" and which != "asteroids" and which != "ring":
+        pytest.skip("the planetesimal configurations run under rk4 (their 1000-step runs are the slow ones)")
+    ours = _trajectory(w, None, 1000, scheme, dt, 1, add, coords)
+    ref = _trajectory(w, oracle.ref_lib(), 1000, scheme, dt, 1, add, coords)
     _assert_trajectories_agree(ours, ref)
 
 

@@ -38,6 +38,40 @@ __global__ void zc_write(double* __restrict__ aos, const double* __restrict__ in
     }
 }
 
+// sector-exact variants: read bytes [0,96) of each record (x..last_collision; sector 3 = the pointers is never
+// touched), write bytes [32,96) (vy vz ax ay | az m r lc: the two sectors holding ax..az) as whole 32-byte sectors
+__global__ void zc_read96(const double2* __restrict__ aos, double* __restrict__ out, long n) {
+    long warp = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    long nwarps = ((long)gridDim.x*blockDim.x) >> 5;
+    for (long w = warp; w*32 < n; w += nwarps) {
+        const double2* base = aos + w*32*8;
+        double acc = 0;
+        #pragma unroll
+        for (int it = 0; it < 6; it++) { int j = it*32 + (int)lane; double2 v = base[(j/6)*8 + (j%6)]; acc += v.x + v.y; }
+        out[w*32 + lane] = acc;
+    }
+}
+__global__ void zc_write64(double2* __restrict__ aos, const double* __restrict__ in, long n) {
+    long warp = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    long nwarps = ((long)gridDim.x*blockDim.x) >> 5;
+    for (long w = warp; w*32 < n; w += nwarps) {
+        double2* base = aos + w*32*8;
+        double v = in[w*32 + lane];
+        #pragma unroll
+        for (int it = 0; it < 4; it++) { int j = it*32 + (int)lane; base[(j/4)*8 + 2 + (j%4)] = make_double2(v, v + it); }
+    }
+}
+__global__ void zc_write128(double2* __restrict__ aos, const double* __restrict__ in, long n) {
+    long warp = ((long)blockIdx.x*blockDim.x + threadIdx.x) >> 5, lane = threadIdx.x & 31;
+    long nwarps = ((long)gridDim.x*blockDim.x) >> 5;
+    for (long w = warp; w*32 < n; w += nwarps) {
+        double2* base = aos + w*32*8;
+        double v = in[w*32 + lane];
+        #pragma unroll
+        for (int k = 0; k < 8; k++) base[k*32 + lane] = make_double2(v, v + k);
+    }
+}
+
 static double now() { return std::chrono::duration<double>(std::chrono::steady_clock::now().time_since_epoch()).count(); }
 
 int main(int argc, char** argv) {
@@ -50,7 +84,7 @@ int main(int argc, char** argv) {
     CK(cudaHostRegister(host, bytes, cudaHostRegisterDefault));
     printf("cudaHostRegister %.1f MB: %.1f ms\n", bytes/1e6, (now() - t0)*1e3);
     void* dev; CK(cudaMalloc(&dev, bytes));
-    double* dsmall; CK(cudaMalloc(&dsmall, n*8*9));
+    double* dsmall; CK(cudaMalloc(&dsmall, n*8*9)); CK(cudaMemset(dsmall, 0, n*8*9));
     cudaStream_t s1, s2; CK(cudaStreamCreate(&s1)); CK(cudaStreamCreate(&s2));
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
     auto timeit = [&](const char* name, auto fn, double useful_bytes) {
@@ -120,6 +154,23 @@ int main(int argc, char** argv) {
         timeit("H2D contiguous (s1) + zero-copy write 24 (s2)", [&] {
             CK(cudaMemcpyAsync(dev, host, bytes/2, cudaMemcpyHostToDevice, s1));
             zc_write<<<148*4, 256, 0, s2>>>((double*)hdev + (n/2)*16, dsmall + n/2, n/2); }, (double)(n/2)*152);
+        for (int g : {1, 2, 4, 8, 16}) {
+            char name[128];
+            snprintf(name, sizeof name, "zero-copy read 96 B/p sector-exact, grid 148x%d", g);
+            timeit(name, [&] { zc_read96<<<148*g, 256, 0, s1>>>((const double2*)hdev, dsmall, n); }, (double)n*96);
+            snprintf(name, sizeof name, "zero-copy write 64 B/p sector-exact, grid 148x%d", g);
+            timeit(name, [&] { zc_write64<<<148*g, 256, 0, s1>>>((double2*)hdev, dsmall, n); }, (double)n*64);
+        }
+        timeit("zero-copy write 128 B/p coalesced", [&] { zc_write128<<<148*8, 256, 0, s1>>>((double2*)hdev, dsmall, n); }, (double)n*128);
+        timeit("zero-copy read 96 (s1) + write 64 (s2), all records each", [&] {
+            zc_read96<<<148*4, 256, 0, s1>>>((const double2*)hdev, dsmall, n);
+            zc_write64<<<148*4, 256, 0, s2>>>((double2*)hdev, dsmall + n, n); }, (double)n*160);
+        timeit("H2D contiguous 128 (s1) + zero-copy write 64 (s2), all records each", [&] {
+            CK(cudaMemcpyAsync(dev, host, bytes, cudaMemcpyHostToDevice, s1));
+            zc_write64<<<148*4, 256, 0, s2>>>((double2*)hdev, dsmall + n, n); }, (double)n*192);
+        timeit("zero-copy read 96 (s1) + D2H contiguous 128 (s2), all records each", [&] {
+            zc_read96<<<148*4, 256, 0, s1>>>((const double2*)hdev, dsmall, n);
+            CK(cudaMemcpyAsync(host, dev, bytes, cudaMemcpyDeviceToHost, s2)); }, (double)n*224);
     } else printf("no device pointer for registered memory: %s\n", cudaGetErrorString(e));
     // pageable
     CK(cudaHostUnregister(host));
