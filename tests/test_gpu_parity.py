@@ -439,8 +439,6 @@ def test_trajectories_other_configs_1000_steps(built, which, scheme):
         w, add, coords, dt = W.planetesimal_disk(400), TRIO, "PARTICLE", 0.002
     else:
         w, add, coords, dt = W.planetesimal_disk(400), TRIO, "JACOBI", 0.002
-    if scheme != "rk4" and which != "asteroids" and which != "ring":
-        pytest.skip("the planetesimal configurations run under rk4 (their 1000-step runs are the slow ones)")
     ours = _trajectory(w, None, 1000, scheme, dt, 1, add, coords)
     ref = _trajectory(w, oracle.ref_lib(), 1000, scheme, dt, 1, add, coords)
     _assert_trajectories_agree(ours, ref)
