@@ -294,6 +294,29 @@ def run_ours(args):
                     "what": ("device-resident drift-kick-drift step, state never leaves HBM: one fused sweep (rebx_b200_leapfrog_step" +
                              (")" if world == 1 else "'s two halves with the all-reduce of the back-reaction sums between them; the central body's record is replicated and advanced by every rank)"))}
 
+    # ---- resident Wisdom-Holman leg: BASELINE config 2 is quoted "under WHFast" -- Kepler drift about the star on
+    # the device + kick by the stacked effects (device.Shard.wh_step), state never leaves HBM -----------------------
+    resident_wh = None
+    if not args.no_e2e and not com:
+        for _ in range(3):
+            shard.wh_step(dt_step, w["G"], group)
+        barrier()
+        l0 = shard.launches
+        w0 = time.time()
+        s0.record()
+        for _ in range(args.steps):
+            shard.wh_step(dt_step, w["G"], group)
+        s1.record()
+        barrier()
+        clocks.window(w0, time.time())
+        tr = torch.tensor([s0.elapsed_time(s1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(tr, op=dist.ReduceOp.MAX)
+        ms_w = float(tr.item())/args.steps
+        resident_wh = {"value": world*n*nf/(ms_w*1e-3), "unit": "evals/s", "ms_per_step": ms_w,
+                       "launches_per_step": (shard.launches - l0)//args.steps,
+                       "what": "device-resident Wisdom-Holman step: Kepler drift about the central body (rebx_b200_kepler_drift, universal variables) for dt/2, kick by the stacked effects, Kepler drift for dt/2"}
+
     # ---- end-to-end leg: the REBOUND-facing call on host particle arrays ---------------------------
     e2e = None
     if not args.no_e2e:
@@ -346,7 +369,7 @@ def run_ours(args):
                            "l2": f"inputs larger than L2 ({shard_bytes(n, exec_order)/1e6:.0f} MB streamed per step)",
                            "sharding": ("index ranges; body state broadcast per step (NCCL) when n_gpus > 1" if not com else
                                         "index ranges; per step an all-gather of 7 mass moments and of 3 back-reaction sums per rank (JACOBI: exclusive prefix / suffix over ranks; BARYCENTRIC: all-reduce)")},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "resident_step": resident, "gpu_launches": gpu_launches,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "resident_step": resident, "resident_wh_step": resident_wh, "gpu_launches": gpu_launches,
                 "clocks": clocks.summary()}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())

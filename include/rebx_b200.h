@@ -211,6 +211,15 @@ int rebx_b200_point_mass_gravity(const rebx_b200_state* st, const double* bodies
 /* Refreshes pos/vel/mass of every body record whose particle index lies inside the shard. */
 int rebx_b200_gather_bodies(const rebx_b200_state* st, double* bodies, int nbodies, void* stream, int* launches);
 
+/* Kepler drift: every particle of the shard follows its two-body orbit about `body` (one body record,
+ * device; mu = G (m_body + m_i), m_i = 0 when st->m is NULL) for dt, the body's own element (if the shard
+ * holds it) moves inertially; `body` itself is read, not written -- refresh it with rebx_b200_gather_bodies
+ * afterwards.  The splitting of reference rebx_kepler_step (src/steppers.c:79-87 -> REBOUND's WHFast) for
+ * one massive central body; arithmetic in reboundx_b200/csrc/kepler_core.h (universal variables). */
+int rebx_b200_kepler_drift(const rebx_b200_state* st, const double* body, double G, double dt, void* stream, int* launches);
+/* a = 0 for the shard (the kick of a Wisdom-Holman step sees the additional forces only). */
+int rebx_b200_zero_acc(const rebx_b200_state* st, void* stream, int* launches);
+
 /* One whole drift-kick-drift step (x += dt/2 v; a = pull of the stack's central body + stacked effects;
  * v += dt a; x += dt/2 v) in ONE sweep: accelerations stay in registers, 96 B/particle + tables.
  * All effects of the pass must refer to the same central body, whose record(s) and state the call

@@ -879,6 +879,7 @@ pack_acc_aos_kernel(unsigned char* __restrict__ aos, rebx_b200_aos_layout L,
 }  // namespace rebxb
 #include "kernels_jacobi.cuh"
 #include "kernels_gr.cuh"
+#include "kernels_kepler.cuh"
 namespace rebxb {
 
 // ---- launch plumbing ----------------------------------------------------------------------
@@ -1451,6 +1452,27 @@ int rebx_b200_kick(const rebx_b200_state* st, double dt, void* stream, int* laun
         const_cast<double*>(st->vx), const_cast<double*>(st->vy), const_cast<double*>(st->vz), st->ax, st->ay, st->az, st->n, dt);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+int rebx_b200_kepler_drift(const rebx_b200_state* st, const double* body, double G, double dt, void* stream, int* launches) {
+    if (!st || !body || !st->x || !st->y || !st->z || !st->vx || !st->vy || !st->vz) return cudaErrorInvalidValue;
+    if (st->n == 0) return 0;
+    const int grid = grid_for(reinterpret_cast<const void*>(kepler_drift_kernel), st->n);
+    kepler_drift_kernel<<<grid, kThreads, 0, static_cast<cudaStream_t>(stream)>>>(*st, body, G, dt);
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
+int rebx_b200_zero_acc(const rebx_b200_state* st, void* stream, int* launches) {
+    if (!st || !st->ax || !st->ay || !st->az) return cudaErrorInvalidValue;
+    if (st->n == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    cudaError_t err = cudaMemsetAsync(st->ax, 0, (size_t)st->n*sizeof(double), s);
+    if (err == cudaSuccess) err = cudaMemsetAsync(st->ay, 0, (size_t)st->n*sizeof(double), s);
+    if (err == cudaSuccess) err = cudaMemsetAsync(st->az, 0, (size_t)st->n*sizeof(double), s);
+    (void)launches;
     return err;
 }
 

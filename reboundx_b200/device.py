@@ -346,6 +346,27 @@ class Shard:
         k += self.drift(0.5*dt)
         return k
 
+    def kepler_drift(self, dt, G, stream=None):
+        """Two-body drift of the shard about the central body (rebx_b200_kepler_drift)."""
+        return self._call("rebx_b200_kepler_drift", c_void_p(self.bodies.data_ptr()), c_double(G), c_double(dt), stream=stream)
+
+    def wh_step(self, dt, G, group=None):
+        """One Wisdom-Holman drift-kick-drift step entirely on the device -- Kepler drift about the central
+        body for dt/2, kick by the stacked effects alone, Kepler drift for dt/2: the scheme of the host harness
+        `wisdom_holman` (rebound_shim.c), i.e. the splitting behind WHFast with N_active = 1."""
+        k = self.kepler_drift(0.5*dt, G)
+        k += self.refresh_bodies(group)
+        k += self._call("rebx_b200_zero_acc")
+        k += self.launch()
+        if any(kind != 1 and kind != 4 for kind in self.kinds):
+            self.reduce_backreaction(group)
+            k += self.apply_backreaction()
+        k += self.kick(dt)
+        k += self.refresh_bodies(group)
+        k += self.kepler_drift(0.5*dt, G)
+        k += self.refresh_bodies(group)
+        return k
+
     def fused_leapfrog_step(self, dt, G, softening=0.0, stream=None, group=None):
         """The same step as `leapfrog_step` in one sweep (rebx_b200_leapfrog_step): the acceleration
         never touches HBM.  Sharded (a process group with more than one rank): every rank sweeps its own

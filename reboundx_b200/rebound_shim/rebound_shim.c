@@ -16,6 +16,7 @@
 #include <string.h>
 #include <time.h>
 #include "rebound.h"
+#include "../csrc/kepler_core.h"
 
 #define SHIM_TINY 1.E-308
 
@@ -535,49 +536,9 @@ static void shim_gauss_radau(struct reb_simulation* r, int nsteps){
  * i >= 1 follows its Kepler orbit about particle 0 (mu = G (m_0 + m_i)) for dt/2, receives the kick
  * dt * (a_i - a_0) of everything that is NOT that two-body attraction -- here only
  * r->additional_forces -- and drifts another dt/2.  Particle 0 moves inertially and takes its own
- * kick.  The Kepler drift solves the universal-variable Kepler equation by Newton iteration with
- * Stumpff functions (Danby's formulation). */
-static void stumpff(double z, double* c0, double* c1, double* c2, double* c3){
-    int n = 0;
-    while (fabs(z) > 0.1){ z *= 0.25; n++; }
-    double C2 = (1. - z*(1. - z*(1. - z*(1. - z*(1. - z*(1. - z/182.)/132.)/90.)/56.)/30.)/12.)/2.;
-    double C3 = (1. - z*(1. - z*(1. - z*(1. - z*(1. - z*(1. - z/210.)/156.)/110.)/72.)/42.)/20.)/6.;
-    double C1 = 1. - z*C3, C0 = 1. - z*C2;
-    for (; n > 0; n--){
-        C3 = (C2 + C0*C3)*0.25;
-        C2 = C1*C1*0.5;
-        C1 = C0*C1;
-        C0 = 2.*C0*C0 - 1.;
-    }
-    *c0 = C0; *c1 = C1; *c2 = C2; *c3 = C3;
-}
-
-static void kepler_drift(double mu, double dt, double* x, double* v){
-    const double r0 = sqrt(x[0]*x[0] + x[1]*x[1] + x[2]*x[2]);
-    const double v2 = v[0]*v[0] + v[1]*v[1] + v[2]*v[2];
-    const double eta = x[0]*v[0] + x[1]*v[1] + x[2]*v[2];
-    const double beta = 2.*mu/r0 - v2;
-    double X = dt/r0, c0 = 1., c1 = 1., c2 = 0.5, c3 = 1./6., G1 = 0., G2 = 0., G3 = 0., rr = r0;
-    for (int it = 0; it < 60; it++){
-        stumpff(beta*X*X, &c0, &c1, &c2, &c3);
-        G1 = c1*X; G2 = c2*X*X; G3 = c3*X*X*X;
-        const double f = r0*G1 + eta*G2 + mu*G3 - dt;
-        rr = r0*c0 + eta*G1 + mu*G2;
-        const double dX = f/rr;
-        X -= dX;
-        if (fabs(dX) <= 1e-16*fabs(X)) break;
-    }
-    stumpff(beta*X*X, &c0, &c1, &c2, &c3);
-    G1 = c1*X; G2 = c2*X*X; G3 = c3*X*X*X;
-    rr = r0*c0 + eta*G1 + mu*G2;
-    const double f = 1. - mu*G2/r0, gg = dt - mu*G3;
-    const double fd = -mu*G1/(r0*rr), gd = 1. - mu*G2/rr;
-    for (int c = 0; c < 3; c++){
-        const double xn = f*x[c] + gg*v[c], vn = fd*x[c] + gd*v[c];
-        x[c] = xn; v[c] = vn;
-    }
-}
-
+ * kick.  The Kepler drift (universal variables, Stumpff functions, Newton iteration) lives in
+ * ../csrc/kepler_core.h, shared verbatim with the device kernel so that both execute the same IEEE
+ * operations in the same order. */
 static void shim_wh_half_drift(struct reb_simulation* r, double hdt){
     struct reb_particle* p = r->particles;
     const size_t N = r->N;
@@ -586,7 +547,7 @@ static void shim_wh_half_drift(struct reb_simulation* r, double hdt){
     for (size_t i = 1; i < N; i++){
         double x[3] = {p[i].x - x0[0], p[i].y - x0[1], p[i].z - x0[2]};
         double v[3] = {p[i].vx - v0[0], p[i].vy - v0[1], p[i].vz - v0[2]};
-        kepler_drift(r->G*(p[0].m + p[i].m), hdt, x, v);
+        rebxb_kepler_drift(r->G*(p[0].m + p[i].m), hdt, x, v);
         p[i].x = x1[0] + x[0]; p[i].y = x1[1] + x[1]; p[i].z = x1[2] + x[2];
         p[i].vx = v0[0] + v[0]; p[i].vy = v0[1] + v[1]; p[i].vz = v0[2] + v[2];
     }

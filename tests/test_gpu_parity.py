@@ -515,6 +515,34 @@ def test_resident_leapfrog_matches_host_harness_bitwise(built):
     assert np.array_equal(got, ref)
 
 
+@pytest.mark.parametrize("which", ["debris_disk", "ring_massive"])
+def test_resident_wisdom_holman_matches_host_harness(built, which):
+    """BASELINE config 2 as quoted ("radiation_forces under WHFast"), resident: 1000 Wisdom-Holman steps
+    (Kepler drift about the star on the device, rebx_b200_kepler_drift; kick by the stacked effects) against
+    the host harness `wisdom_holman` stepping the reference-compiled force.  The Kepler arithmetic is the
+    same source on both sides (csrc/kepler_core.h), so radiation is bit for bit; with a massive ring the
+    back-reaction on the planet is summed in another order (tolerance of criterion (ii))."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    if which == "debris_disk":
+        w, add, dt = workloads.debris_disk(1000, seed=3), ["radiation_forces"], 1e8
+    else:
+        w, add, dt = workloads.circumplanetary_ring(1000, massive=True), ["gravitational_harmonics", "gr_potential"], 50.0
+    ref = _trajectory(w, oracle.ref_lib(), 1000, "wisdom_holman", dt, 1, add)
+    sh = device.Shard(w, add[::-1], "cuda:0")
+    for _ in range(1000):
+        sh.wh_step(dt, w["G"])
+    torch.cuda.synchronize()
+    got = np.array(sh.posvel())
+    if which == "debris_disk":
+        assert np.array_equal(got, ref)
+    else:
+        _assert_trajectories_agree(got, ref)
+
+
 @pytest.mark.parametrize("which", ["debris_disk", "ring_massive", "asteroids", "planetesimals"])
 def test_fused_leapfrog_step_equals_separate_sweeps(built, which):
     """rebx_b200_leapfrog_step (one sweep, accelerations in registers) against the five separate
