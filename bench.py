@@ -153,7 +153,10 @@ def run_reference(args):
     line = {"impl": "reference", "metric": METRIC, "value": base["value"], "unit": "evals/s", "n_gpus": args.gpus,
             "steps": args.steps, "warmup": args.warmup, "ms_per_step": base["ms_per_dispatch"], "higher_is_better": True,
             "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic",
-            "config": {"workload": f"{args.workload}: {'+'.join(add_order)}, bounded sample of {sample} test particles on host cores"},
+            # the same workload naming as the GPU arm's line; each step here evaluates a bounded sample of it
+            "config": {"workload": f"{args.workload}: {args.n or n_default} test particles per GPU, {'+'.join(add_order)}" + (f", REBX_COORDINATES_{args.coordinates}" if args.coordinates != "PARTICLE" else ""),
+                       "particles_per_gpu": args.n or n_default, "forces": add_order,
+                       "sample": f"each step = one dispatch of the reference's rebx_additional_forces over a bounded sample of {sample} test particles of this workload, 1 host thread (the reference is single-threaded)"},
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     line["cpu_baseline"]["unit"] = "evals/s"

@@ -453,6 +453,25 @@ __device__ __forceinline__ Vec3 gas_damping(const rebx_b200_effect& fx, const Or
     return f;
 }
 
+// x^p for an exponent that is a FORCE-LEVEL scalar (uniform over the sweep, so the branch never diverges):
+// the exponents disc models actually use are served by correctly rounded operators -- 1/x, sqrt chains
+// (each further sqrt halves the relative error carried in: <= 1 ulp in all), x*sqrt(x) -- instead of
+// libdevice pow (1-2 ulp, ~150 FP64 instructions); any other exponent goes to pow as before.
+__device__ __forceinline__ double pow_uniform(double x, double p) {
+    if (p == 0.0)    return 1.0;
+    if (p == 1.0)    return x;
+    if (p == -1.0)   return 1.0/x;
+    if (p == 0.5)    return sqrt(x);
+    if (p == -0.5)   return 1.0/sqrt(x);
+    if (p == 0.25)   return sqrt(sqrt(x));
+    if (p == 0.125)  return sqrt(sqrt(sqrt(x)));
+    if (p == 1.5)    return x*sqrt(x);
+    if (p == -1.5)   return 1.0/(x*sqrt(x));
+    if (p == 2.0)    return x*x;
+    if (p == -2.0)   return 1.0/(x*x);
+    return pow(x, p);
+}
+
 // src/type_I_migration.c:69-113 (time-scale fits) and :115-203
 __device__ __forceinline__ Vec3 type_I_migration(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body,
                                                  const Particle& p, const Orbit* so = nullptr) {
@@ -463,12 +482,12 @@ __device__ __forceinline__ Vec3 type_I_migration(const rebx_b200_effect& fx, con
     const double mp = p.m, ms = org.m;
     const Rel q = relative(p, org, body);
 
-    const double h  = h0*pow(q.r2, beta/2);
+    const double h  = h0*pow_uniform(q.r2, beta/2);
     const double h2 = h*h;
     const double eh = e0/h;
     const double ih = inc0/h;
 
-    const double sd   = sd0*pow(sqrt(q.r2), -s);
+    const double sd   = sd0*pow_uniform(sqrt(q.r2), -s);
     const double wave = (sqrt(ms*ms*ms)*h2*h2)/(mp*sd*sqrt(a0*G));
 
     const double term  = (eh/2.25);
@@ -504,7 +523,7 @@ __device__ __forceinline__ void central_force(const rebx_b200_effect& fx, const 
     const double dy = p.y - org.y;
     const double dz = p.z - org.z;
     const double r2 = dx*dx + dy*dy + dz*dz;
-    const double prefac = A*pow(r2, (gamma - 1.)/2.);
+    const double prefac = A*pow_uniform(r2, (gamma - 1.)/2.);
     a.x += prefac*dx;  a.y += prefac*dy;  a.z += prefac*dz;
     const double mr = p.m/org.m;
     red.x -= mr*prefac*dx;  red.y -= mr*prefac*dy;  red.z -= mr*prefac*dz;
@@ -556,7 +575,7 @@ __device__ __forceinline__ void gas_dynamical_friction(const rebx_b200_effect& f
     const double vk = sqrt(G*org.m/rcyl)*(1.0 - hr*hr);
     const double v0 = dvx + vk*sin_phi, v1 = dvy - vk*cos_phi, v2 = dvz;
     const double vrel_norm = sqrt(v0*v0 + v1*v1 + v2*v2);
-    const double mach = vrel_norm/(cs*pow(rcyl, alpha_cs));
+    const double mach = vrel_norm/(cs*pow_uniform(rcyl, alpha_cs));
     // calculate_pre_factor (:79-88) with mach_piece_sub (:67-76)
     const double coul = log(1.0/xmin);
     double integ;
@@ -567,7 +586,7 @@ __device__ __forceinline__ void gas_dynamical_friction(const rebx_b200_effect& f
     }
     const double h = hr*rcyl;
     const double vert = (fabs(dz) < (10*h)) ? exp(-dz*dz/(2.0*h*h)) : 0;
-    const double rhog_loc = rhog*pow(rcyl, alpha_rhog)*vert;
+    const double rhog_loc = rhog*pow_uniform(rcyl, alpha_rhog)*vert;
     const double mp = p.m, rstar = p.r;
     const double fc = 4.*kPi*(G*G)*mp*(rhog_loc)/(vrel_norm*vrel_norm*vrel_norm)*integ + kPi*rhog_loc*rstar*rstar*vrel_norm*Qd/mp;
     a.x -= fc*v0;  a.y -= fc*v1;  a.z -= fc*v2;
