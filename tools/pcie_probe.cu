@@ -83,7 +83,7 @@ int main(int argc, char** argv) {
     double t0 = now();
     CK(cudaHostRegister(host, bytes, cudaHostRegisterDefault));
     printf("cudaHostRegister %.1f MB: %.1f ms\n", bytes/1e6, (now() - t0)*1e3);
-    void* dev; CK(cudaMalloc(&dev, bytes));
+    void* dev; CK(cudaMalloc(&dev, bytes + (1 << 20)));
     double* dsmall; CK(cudaMalloc(&dsmall, n*8*9)); CK(cudaMemset(dsmall, 0, n*8*9));
     cudaStream_t s1, s2; CK(cudaStreamCreate(&s1)); CK(cudaStreamCreate(&s2));
     cudaEvent_t a, b; CK(cudaEventCreate(&a)); CK(cudaEventCreate(&b));
@@ -125,6 +125,33 @@ int main(int argc, char** argv) {
                 }
             }, 2.0*bytes);
         }
+    }
+    // same pipeline from a buffer that starts 16 bytes into a page (what glibc hands REBOUND for a large realloc)
+    for (int variant = 0; variant < 4; variant++) {
+        const size_t off0 = variant == 3 ? 2048 : 16;
+        const size_t doff = variant == 1 ? 16 : 0;                         // device address congruent to the host address mod 4096
+        char name[160]; snprintf(name, sizeof name, "pipeline 64 MB x3, host = page + %zu, device = aligned + %zu%s", off0, doff, variant == 2 ? ", head/body split at the page" : "");
+        const size_t chunk = size_t(64) << 20;
+        char* hb = (char*)host + off0;
+        const size_t nb = bytes - 8192;
+        timeit(name, [&] {
+            size_t nchunks = (nb + chunk - 1)/chunk;
+            for (size_t c = 0; c < nchunks; c++) {
+                size_t off = c*chunk, len = (off + chunk <= nb) ? chunk : nb - off;
+                cudaStream_t q = ps[c % 3];
+                char* dbuf = (char*)dev + (c % 3)*(chunk + 4096) + doff;
+                if (variant == 2) {      // copy [hb+off, next page) separately, then the page-aligned remainder
+                    const size_t head = 4096 - off0;
+                    CK(cudaMemcpyAsync(dbuf, hb + off, head, cudaMemcpyHostToDevice, q));
+                    CK(cudaMemcpyAsync(dbuf + head, hb + off + head, len - head, cudaMemcpyHostToDevice, q));
+                    CK(cudaMemcpyAsync(hb + off, dbuf, head, cudaMemcpyDeviceToHost, q));
+                    CK(cudaMemcpyAsync(hb + off + head, dbuf + head, len - head, cudaMemcpyDeviceToHost, q));
+                    continue;
+                }
+                CK(cudaMemcpyAsync(dbuf, hb + off, len, cudaMemcpyHostToDevice, q));
+                CK(cudaMemcpyAsync(hb + off, dbuf, len, cudaMemcpyDeviceToHost, q));
+            }
+        }, 2.0*nb);
     }
     // two independent queues: all H2D on one stream, all D2H on another, D2H(c) gated by an event after H2D(c)
     {
