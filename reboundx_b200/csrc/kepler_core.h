@@ -45,18 +45,32 @@ REBXB_HD void rebxb_kepler_drift(double mu, double dt, double* x, double* v) {
     /* first guess: the Kepler equation to second order in X (dt = r0 X + eta X^2/2 + ...) */
     const double X1 = dt/r0;
     double X = X1*(1. - 0.5*eta*X1/r0), c0 = 1., c1 = 1., c2 = 0.5, c3 = 1./6., G1 = 0., G2 = 0., G3 = 0., rr = r0;
+    double dX = 0.;
+    int converged = 0;
     for (int it = 0; it < 60; it++) {
         rebxb_stumpff(beta*X*X, &c0, &c1, &c2, &c3);
         G1 = c1*X; G2 = c2*X*X; G3 = c3*X*X*X;
         const double f = r0*G1 + eta*G2 + mu*G3 - dt;
         rr = r0*c0 + eta*G1 + mu*G2;
-        const double dX = f/rr;
+        dX = f/rr;
         X -= dX;
         /* Newton converges quadratically: a correction below 1e-9 |X| leaves an error below round-off */
-        if (fabs(dX) <= 1e-9*fabs(X)) break;
+        if (fabs(dX) <= 1e-9*fabs(X)) { converged = 1; break; }
     }
-    rebxb_stumpff(beta*X*X, &c0, &c1, &c2, &c3);
-    G1 = c1*X; G2 = c2*X*X; G3 = c3*X*X*X;
+    /* G-functions at the final X = (X + dX) - dX to first order in the last (tiny) correction, using
+     * dG3/dX = G2, dG2/dX = G1, dG1/dX = G0 = c0, dG0/dX = -beta G1; the neglected terms are O(dX^2) <= 1e-18
+     * relative.  Saves re-evaluating the Stumpff series. */
+    if (!converged) {                  /* not reached for the step sizes an integrator uses; stay exact anyway */
+        rebxb_stumpff(beta*X*X, &c0, &c1, &c2, &c3);
+        G1 = c1*X; G2 = c2*X*X; G3 = c3*X*X*X;
+    } else {
+        const double G0 = c0;
+        G3 = G3 - dX*G2;
+        G2 = G2 - dX*G1;
+        const double G1n = G1 - dX*G0;
+        c0 = G0 + dX*beta*G1;
+        G1 = G1n;
+    }
     rr = r0*c0 + eta*G1 + mu*G2;
     const double f = 1. - mu*G2/r0, g = dt - mu*G3;
     const double fd = -mu*G1/(r0*rr), gd = 1. - mu*G2/rr;
