@@ -444,6 +444,24 @@ def test_trajectories_other_configs_1000_steps(built, which, scheme):
     _assert_trajectories_agree(ours, ref)
 
 
+@pytest.mark.parametrize("full", [True, False])
+def test_yarkovsky_notebook_known_answer_on_the_gpu(built, full):
+    """The reference's published Yarkovsky drift (ipython_examples/YarkovskyEffect.ipynb cells 12 and 20, see
+    tests/yarkovsky_notebook.py) with THIS library's force: the first 10 % of the notebook's run (2*10^5
+    Wisdom-Holman steps through sim->additional_forces) must follow the reference-compiled force to 1e-10
+    (criterion (ii)) and give 10 % of the published drift (the drift is linear in time: measured 2e-5 off)."""
+    import yarkovsky_notebook as nb
+    from oracle import oracle
+    steps = nb.STEPS//10
+    da, pv = nb.drift(full, None, steps)
+    want = np.array([nb.NOTEBOOK_FULL] if full else nb.NOTEBOOK_SIMPLE)/10
+    assert np.all(np.abs(da/want - 1.0) < 1e-3), (da, want)
+    if oracle.have_ref():
+        da_ref, pv_ref = nb.drift(full, oracle.ref_lib(), steps)
+        _assert_trajectories_agree(pv, pv_ref)
+        assert np.all(np.abs(da/da_ref - 1.0) < 1e-6), (da, da_ref)
+
+
 @pytest.mark.parametrize("case", ["one_active_massive_asteroids", "three_active_massless", "stacked_with_yarkovsky"])
 def test_gr_1pn(built, case):
     """`gr` (reference src/gr.c): device reduction + host part for the <= 8 active bodies + device sweep.
