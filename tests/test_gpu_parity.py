@@ -444,6 +444,14 @@ def test_trajectories_other_configs_1000_steps(built, which, scheme):
     _assert_trajectories_agree(ours, ref)
 
 
+def test_gr_notebook_known_answers_with_this_library(built):
+    """The reference's published perihelion advance under `gr` (tests/gr_notebook.py) with THIS library's `gr`:
+    two active bodies, so the work is the from-scratch host part for the actives (dispatch.cpp: gr_host_actives)
+    around the device reduction and sweep."""
+    import gr_notebook as nb
+    nb.check(*nb.run(None))
+
+
 @pytest.mark.parametrize("full", [True, False])
 def test_yarkovsky_notebook_known_answer_on_the_gpu(built, full):
     """The reference's published Yarkovsky drift (ipython_examples/YarkovskyEffect.ipynb cells 12 and 20, see
@@ -926,6 +934,63 @@ def test_device_potentials_match_the_reference(built, which):
     assert ref != 0.0
     # harmonics terms change sign with latitude; their absolute sum is bounded by ~|J2 term| sum ~ a few |H|
     assert abs(got - ref) <= (1e-13 if name != "gravitational_harmonics" else 1e-11)*abs(ref), (ref, got)
+
+
+@pytest.mark.parametrize("name", ["gr_potential", "central_force", "gravitational_harmonics"])
+def test_reference_conservation_tests(built, name):
+    """The reference's own test file for these effects, reboundx/tests/test_conservation.py:44-87, ported to this
+    library: star + two 1e-4 planets (a = 1, e = 0.1; a = 2, e = 0.1, inc = 0.2), the force on the device, and
+    H = Newtonian energy + the effect's potential (reduced on the device) conserved to the reference's bar of
+    1e-12 -- under the fixed-step Gauss-Radau scheme standing in for IAS15, over 10^3 time units (the reference
+    integrates 10^4; one tenth keeps the GPU suite short)."""
+    import ctypes
+    from reboundx_b200 import workloads as W
+    from reboundx_b200.host import Extras, Simulation
+    G = 1.0
+    p1 = [float(v[0]) for v in W.kepler_to_cartesian(G*1.0001, np.array([1.0]), np.array([0.1]), np.array([0.0]), np.array([0.0]), np.array([0.0]), np.array([0.0]))]
+    p2 = [float(v[0]) for v in W.kepler_to_cartesian(G*1.0002, np.array([2.0]), np.array([0.1]), np.array([0.2]), np.array([0.0]), np.array([0.0]), np.array([0.0]))]
+    m = np.array([1.0, 1e-4, 1e-4])
+    st = [np.array([0.0, p1[k], p2[k]]) for k in range(6)]
+    for k in range(6):                              # sim.move_to_com()
+        st[k] = st[k] - (m*st[k]).sum()/m.sum()
+    sim = Simulation(G=G)
+    sim.set_particles(st[0], st[1], st[2], st[3], st[4], st[5], m)
+    rebx = Extras(sim)
+    force = rebx.load_force(name)
+    rebx.add_force(force)
+    L = rebx._lib
+    if name == "gr_potential":
+        force.params["c"] = 1.0e4
+        L.rebx_gr_potential_potential.restype = ctypes.c_double
+        potential = lambda: L.rebx_gr_potential_potential(rebx._ptr, force._ptr)
+    elif name == "central_force":
+        p0 = rebx.particle_params(0)
+        p0["Acentral"] = 1.0e-4; p0["gammacentral"] = -1.0
+        L.rebx_central_force_potential.restype = ctypes.c_double
+        potential = lambda: L.rebx_central_force_potential(rebx._ptr)
+    else:
+        p0 = rebx.particle_params(0)
+        p0["J2"] = 1.0e-3; p0["J4"] = 1.0e-3; p0["R_eq"] = 1.0e-3
+        L.rebx_gravitational_harmonics_potential.restype = ctypes.c_double
+        potential = lambda: L.rebx_gravitational_harmonics_potential(rebx._ptr)
+
+    def energy():                                   # sim.energy(): kinetic + pairwise Newtonian
+        x, y, z, vx, vy, vz = (np.array(a) for a in sim.posvel())
+        E = 0.5*np.sum(m*(vx*vx + vy*vy + vz*vz))
+        for i in range(3):
+            for j in range(i + 1, 3):
+                E -= G*m[i]*m[j]/np.sqrt((x[i] - x[j])**2 + (y[i] - y[j])**2 + (z[i] - z[j])**2)
+        return E
+
+    H0 = energy() + potential()
+    period = 2*np.pi/np.sqrt(G*1.0001)
+    nsteps = int(round(1.0e3/(period/100)))
+    sim.dt = 1.0e3/nsteps
+    sim.integrate(nsteps, "gauss_radau")
+    H = energy() + potential()
+    sim.process_messages()
+    rebx.detach(); sim.free()
+    assert abs((H - H0)/H0) < 1.0e-12, (H0, H)
 
 
 def test_gas_dynamical_friction(built):

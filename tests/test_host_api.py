@@ -267,3 +267,18 @@ def test_rad_calc_helpers(built):
     assert beta == 3.*L*Q/(16.*np.pi*G*M*c*rho*1e-5)
     r = lib.rebx_rad_calc_particle_radius(d(G), d(c), d(M), d(L), d(beta), d(rho), d(Q))
     assert abs(r - 1e-5) < 1e-19
+
+
+def test_rad_calc_beta_published_value(built):
+    """reference ipython_examples/Radiation_Forces_Circumplanetary_Dust.ipynb cell 11 prints
+    "Particle 2's beta parameter = 0.05767021830984005" for rebx.rad_calc_beta(G, c, Msun, L, 1e-5 m, 1000 kg/m^3, 1)."""
+    import ctypes
+    from reboundx_b200 import load
+    lib = load()
+    lib.rebx_rad_calc_beta.restype = ctypes.c_double
+    lib.rebx_rad_calc_beta.argtypes = [ctypes.c_double]*7
+    beta = lib.rebx_rad_calc_beta(6.674e-11, 3.e8, 1.99e30, 3.85e26, 1.e-5, 1000., 1.)
+    assert beta == 0.05767021830984005
+    lib.rebx_rad_calc_particle_radius.restype = ctypes.c_double
+    lib.rebx_rad_calc_particle_radius.argtypes = [ctypes.c_double]*7
+    assert abs(lib.rebx_rad_calc_particle_radius(6.674e-11, 3.e8, 1.99e30, 3.85e26, beta, 1000., 1.)/1.e-5 - 1.0) < 1e-15

@@ -126,3 +126,14 @@ def test_yarkovsky_notebook_known_answers(built):
     da, _ = nb.drift(False, oracle.ref_lib())
     assert abs(da[0]/nb.NOTEBOOK_SIMPLE[0] - 1.0) < 1e-6, da
     assert abs(da[1]/nb.NOTEBOOK_SIMPLE[1] - 1.0) < 1e-6, da
+
+
+def test_gr_notebook_known_answers(built):
+    """Pins the oracle's `gr` -- the reference's gr.c compiled in place on top of the restated REBOUND Jacobi
+    transformations -- to the perihelion advance the reference publishes (GeneralRelativity.ipynb,
+    SavingAndLoadingSimulations.ipynb; real REBOUND + IAS15): see tests/gr_notebook.py."""
+    from oracle import oracle
+    import gr_notebook as nb
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    nb.check(*nb.run(oracle.ref_lib()))
