@@ -993,6 +993,87 @@ def test_reference_conservation_tests(built, name):
     assert abs((H - H0)/H0) < 1.0e-12, (H0, H)
 
 
+def _two_planets():
+    """reference reboundx/tests/test_machine_independent.py:13-19 / test_conservation.py:8-14"""
+    from reboundx_b200 import workloads as W
+    G = 1.0
+    p1 = [float(v[0]) for v in W.kepler_to_cartesian(G*1.0001, np.array([1.0]), np.array([0.1]), np.array([0.0]), np.array([0.0]), np.array([0.0]), np.array([0.0]))]
+    p2 = [float(v[0]) for v in W.kepler_to_cartesian(G*1.0002, np.array([2.0]), np.array([0.1]), np.array([0.2]), np.array([0.0]), np.array([0.0]), np.array([0.0]))]
+    m = np.array([1.0, 1e-4, 1e-4])
+    st = [np.array([0.0, p1[k], p2[k]]) for k in range(6)]
+    return [a - (m*a).sum()/m.sum() for a in st], m
+
+
+@pytest.mark.parametrize("name", ["modify_orbits_forces", "gr", "gr_potential", "radiation_forces", "central_force", "gravitational_harmonics"])
+def test_reference_machine_independent_tests(built, tmp_path, name):
+    """reference reboundx/tests/test_machine_independent.py (one test per effect): set the effect up, save the
+    REBOUNDx state, integrate; then rebuild the extras from the saved file on a fresh copy of the initial
+    simulation, integrate again, and require particles[0].x to be EQUAL.  Here: this library's binary writer and
+    loader, the CUDA force, the Wisdom-Holman stand-in for the reference's WHFast (dt = P/100, 2*10^3 time units)."""
+    from reboundx_b200.host import Extras, Simulation
+    st, m = _two_planets()
+
+    def fresh():
+        sim = Simulation(G=1.0, integrator="whfast")
+        sim.set_particles(st[0], st[1], st[2], st[3], st[4], st[5], m)
+        sim.dt = 2*np.pi/np.sqrt(1.0001)/100
+        return sim
+
+    sim = fresh()
+    rebx = Extras(sim)
+    force = rebx.load_force(name)
+    rebx.add_force(force)
+    ps = [rebx.particle_params(i) for i in range(3)]
+    if name == "modify_orbits_forces":
+        ps[1]["tau_a"] = -1e4; ps[1]["tau_e"] = -1e3; ps[2]["tau_e"] = -1e3; ps[2]["tau_inc"] = -1e3
+    elif name in ("gr", "gr_potential"):
+        force.params["c"] = 1.0e4
+    elif name == "radiation_forces":
+        force.params["c"] = 1.0e4; ps[1]["beta"] = 0.5; ps[2]["beta"] = 0.3
+    elif name == "central_force":
+        ps[0]["Acentral"] = 1.0e-3; ps[0]["gammacentral"] = -1.0
+    else:
+        ps[0]["J2"] = 1.0e-3; ps[0]["J4"] = 1.0e-3; ps[0]["R_eq"] = 1.0e-3
+    path = tmp_path / (name + ".rebx")
+    rebx.save(path)
+    nsteps = int(2.0e3/sim.dt)
+    sim.integrate(nsteps, "wisdom_holman")
+    errs = [msg for k, msg in sim.messages() if k == "error"]
+    assert not errs, errs[:2]
+    first = np.array(sim.posvel())
+    rebx.detach(); sim.free()
+
+    sim2 = fresh()
+    rebx2 = Extras(sim2, str(path))
+    assert rebx2.force_order() == [name]
+    sim2.integrate(nsteps, "wisdom_holman")
+    second = np.array(sim2.posvel())
+    rebx2.detach(); sim2.free()
+    assert second[0][0] == first[0][0]                  # the reference's assertion: particles[0].x
+    assert np.array_equal(first, second)                # and everything else
+    x0 = np.array(st[:3])[:, 1:]
+    assert np.max(np.abs(first[:3, 1:] - x0)) > 1e-3    # the planets did move
+
+
+def test_reference_gr_simple(built):
+    """reference reboundx/tests/test_rebx.py:29-34: gr with c = 100 turns the pericentre by more than 1e-4 in 10 time units."""
+    from reboundx_b200 import workloads as W
+    from reboundx_b200.host import Extras, Simulation
+    p1 = [float(v[0]) for v in W.kepler_to_cartesian(1.0, np.array([1.0]), np.array([0.2]), np.array([0.0]), np.array([0.0]), np.array([0.0]), np.array([0.0]))]
+    sim = Simulation(G=1.0)
+    sim.set_particles(*[np.array([0.0, p1[k]]) for k in range(6)], np.array([1.0, 0.0]))
+    rebx = Extras(sim)
+    gr = rebx.load_force("gr"); rebx.add_force(gr); gr.params["c"] = 1.0e2
+    sim.dt = 2*np.pi/200
+    sim.integrate(int(10.0/sim.dt), "gauss_radau")
+    sim.process_messages()
+    x, y, z, vx, vy, vz = (np.array(a) for a in sim.posvel())
+    d = np.array([x[1] - x[0], y[1] - y[0], z[1] - z[0]]); v = np.array([vx[1] - vx[0], vy[1] - vy[0], vz[1] - vz[0]])
+    ev = (v.dot(v) - 1.0/np.linalg.norm(d))*d - d.dot(v)*v
+    assert np.arctan2(ev[1], ev[0]) > 1.0e-4
+    rebx.detach(); sim.free()
+
+
 def test_gas_dynamical_friction(built):
     """reference src/gas_dynamical_friction.c (units of its example: G = 4 pi^2, disc around a central mass)."""
     from reboundx_b200 import workloads
