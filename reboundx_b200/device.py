@@ -367,6 +367,27 @@ class Shard:
         k += self.refresh_bodies(group)
         return k
 
+    def wh_steps(self, nsteps, dt, G, group=None):
+        """`nsteps` Wisdom-Holman steps with the half drifts between consecutive kicks merged into one Kepler
+        drift of dt (what WHFast does between outputs; host harness scheme `wisdom_holman_merged`):
+        drift(dt/2) [kick drift(dt)]^(n-1) kick drift(dt/2).  One Kepler solve per particle and step."""
+        if nsteps <= 0:
+            return 0
+        reduces = any(kind != 1 and kind != 4 for kind in self.kinds)
+        k = self.kepler_drift(0.5*dt, G)
+        k += self.refresh_bodies(group)
+        for s in range(nsteps):
+            k += self._call("rebx_b200_zero_acc")
+            k += self.launch()
+            if reduces:
+                self.reduce_backreaction(group)
+                k += self.apply_backreaction()
+            k += self.kick(dt)
+            k += self.refresh_bodies(group)
+            k += self.kepler_drift(dt if s + 1 < nsteps else 0.5*dt, G)
+            k += self.refresh_bodies(group)
+        return k
+
     def fused_leapfrog_step(self, dt, G, softening=0.0, stream=None, group=None):
         """The same step as `leapfrog_step` in one sweep (rebx_b200_leapfrog_step): the acceleration
         never touches HBM.  Sharded (a process group with more than one rank): every rank sweeps its own

@@ -203,7 +203,7 @@ class Simulation:
         `dt` with Newtonian gravity from the first N_active bodies + additional_forces.  Schemes: leapfrog,
         rk4, gauss_radau (15th-order, the scheme behind IAS15 without step control), wisdom_holman (Kepler
         drifts about particle 0 + kicks by additional_forces, the splitting behind WHFast)."""
-        self._shim.reb_shim_integrate(self._p, c_int(nsteps), c_int({"leapfrog": 0, "rk4": 1, "gauss_radau": 2, "wisdom_holman": 3}[scheme]))
+        self._shim.reb_shim_integrate(self._p, c_int(nsteps), c_int({"leapfrog": 0, "rk4": 1, "gauss_radau": 2, "wisdom_holman": 3, "wisdom_holman_merged": 4}[scheme]))
 
     def free(self):
         if self._p is not None:

@@ -154,6 +154,8 @@ int reb_shim_call_additional_forces(struct reb_simulation* r);
  *             7 force evaluations per sweep over the nodes, sweeps repeated to convergence)
  *   scheme 3: Wisdom-Holman drift-kick-drift: Kepler drifts about particle 0 + kicks by additional_forces
  *             only (the splitting behind WHFast, one massive central body, N_active = 1)
+ *   scheme 4: the same with the half drifts between consecutive kicks merged into one drift of dt
+ *             (WHFast between outputs); the state is synchronised at the end of the call only
  * Used to compare trajectories between two force implementations with everything else equal. */
 void reb_shim_integrate(struct reb_simulation* r, int nsteps, int scheme);
 /* Wall-clock seconds for `reps` calls of r->additional_forces(r) (best single call). */

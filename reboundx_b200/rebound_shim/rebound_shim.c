@@ -554,25 +554,46 @@ static void shim_wh_half_drift(struct reb_simulation* r, double hdt){
     p[0].x = x1[0]; p[0].y = x1[1]; p[0].z = x1[2];
 }
 
-static void shim_wisdom_holman(struct reb_simulation* r, int nsteps){
+static void shim_wh_kick(struct reb_simulation* r, double dt){
     struct reb_particle* p = r->particles;
     const size_t N = r->N;
+    for (size_t i = 0; i < N; i++){ p[i].ax = 0.; p[i].ay = 0.; p[i].az = 0.; }
+    if (r->additional_forces) r->additional_forces(r);
+    for (size_t i = 0; i < N; i++){ p[i].vx += dt*p[i].ax; p[i].vy += dt*p[i].ay; p[i].vz += dt*p[i].az; }
+}
+
+/* merged = 0: every step is drift(dt/2) kick(dt) drift(dt/2), the state is synchronised after each step.
+ * merged = 1: the two half drifts between consecutive kicks are taken as ONE drift of dt (what WHFast does
+ * between outputs): drift(dt/2) [kick(dt) drift(dt)]^(n-1) kick(dt) drift(dt/2). */
+static void shim_wisdom_holman(struct reb_simulation* r, int nsteps, int merged){
     const double dt = r->dt;
-    for (int s = 0; s < nsteps; s++){
-        shim_wh_half_drift(r, 0.5*dt);
-        r->t += 0.5*dt;
-        for (size_t i = 0; i < N; i++){ p[i].ax = 0.; p[i].ay = 0.; p[i].az = 0.; }
-        if (r->additional_forces) r->additional_forces(r);
-        for (size_t i = 0; i < N; i++){ p[i].vx += dt*p[i].ax; p[i].vy += dt*p[i].ay; p[i].vz += dt*p[i].az; }
-        shim_wh_half_drift(r, 0.5*dt);
-        r->t += 0.5*dt;
-        r->dt_last_done = dt;
+    if (nsteps <= 0) return;
+    if (!merged){
+        for (int s = 0; s < nsteps; s++){
+            shim_wh_half_drift(r, 0.5*dt);
+            r->t += 0.5*dt;
+            shim_wh_kick(r, dt);
+            shim_wh_half_drift(r, 0.5*dt);
+            r->t += 0.5*dt;
+            r->dt_last_done = dt;
+        }
+        return;
     }
+    shim_wh_half_drift(r, 0.5*dt);
+    r->t += 0.5*dt;
+    for (int s = 0; s < nsteps; s++){
+        shim_wh_kick(r, dt);
+        if (s + 1 < nsteps){ shim_wh_half_drift(r, dt); r->t += dt; }
+    }
+    shim_wh_half_drift(r, 0.5*dt);
+    r->t += 0.5*dt;
+    r->dt_last_done = dt;
 }
 
 void reb_shim_integrate(struct reb_simulation* r, int nsteps, int scheme){
     if (scheme == 2){ shim_gauss_radau(r, nsteps); return; }
-    if (scheme == 3){ shim_wisdom_holman(r, nsteps); return; }
+    if (scheme == 3){ shim_wisdom_holman(r, nsteps, 0); return; }
+    if (scheme == 4){ shim_wisdom_holman(r, nsteps, 1); return; }
     const size_t N = r->N;
     struct reb_particle* p = r->particles;
     const double dt = r->dt;
