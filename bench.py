@@ -316,7 +316,7 @@ def run_ours(args):
         ms_w = float(tr.item())/args.steps
         resident_wh = {"value": world*n*nf/(ms_w*1e-3), "unit": "evals/s", "ms_per_step": ms_w,
                        "launches_per_step": (shard.launches - l0)//args.steps,
-                       "what": "device-resident Wisdom-Holman steps (device.Shard.wh_steps): Kepler drift about the central body (rebx_b200_kepler_drift, universal variables), kick by the stacked effects; the half drifts between consecutive kicks merged into one, as WHFast does between outputs"}
+                       "what": "device-resident Wisdom-Holman steps (device.Shard.wh_steps): Kepler drift about the central body (rebx_b200_kepler_drift, universal variables), kick by the stacked effects; the half drifts between consecutive kicks merged into one, as WHFast does between outputs; kick + drift in one fused sweep (rebx_b200_wh_kick_drift) for a single effect without back-reaction"}
 
     # ---- end-to-end leg: the REBOUND-facing call on host particle arrays ---------------------------
     e2e = None

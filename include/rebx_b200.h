@@ -217,6 +217,12 @@ int rebx_b200_gather_bodies(const rebx_b200_state* st, double* bodies, int nbodi
  * afterwards.  The splitting of reference rebx_kepler_step (src/steppers.c:79-87 -> REBOUND's WHFast) for
  * one massive central body; arithmetic in reboundx_b200/csrc/kepler_core.h (universal variables). */
 int rebx_b200_kepler_drift(const rebx_b200_state* st, const double* body, double G, double dt, void* stream, int* launches);
+/* Fused Wisdom-Holman kick + drift for a pass of ONE effect without back-reaction (RADIATION, YARKOVSKY):
+ * a = effect at the current state, v += dt_kick a, Kepler drift about fx[0].body for dt_drift, in one sweep
+ * (104 B/particle for radiation instead of ~390 through zero_acc + launch_pass + kick + kepler_drift; the same
+ * arithmetic per particle).  The body record is read, not written (refresh it with rebx_b200_gather_bodies).
+ * cudaErrorNotSupported for any other pass: use the separate kernels. */
+int rebx_b200_wh_kick_drift(const rebx_b200_pass* pass, double G, double dt_kick, double dt_drift, void* stream, int* launches);
 /* a = 0 for the shard (the kick of a Wisdom-Holman step sees the additional forces only). */
 int rebx_b200_zero_acc(const rebx_b200_state* st, void* stream, int* launches);
 

@@ -1465,6 +1465,29 @@ int rebx_b200_kepler_drift(const rebx_b200_state* st, const double* body, double
     return err;
 }
 
+int rebx_b200_wh_kick_drift(const rebx_b200_pass* pass, double G, double dt_kick, double dt_drift, void* stream, int* launches) {
+    if (!pass) return cudaErrorInvalidValue;
+    const int bad = check_pass(*pass);
+    if (bad) return bad;
+    const rebx_b200_pass& P = *pass;
+    if (!P.st.vx || !P.st.vy || !P.st.vz) return cudaErrorInvalidValue;
+    if (P.n_effects != 1) return cudaErrorNotSupported;
+    if (P.st.n == 0) return 0;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (P.fx[0].kind == REBX_B200_RADIATION) {
+        const int grid = grid_for(reinterpret_cast<const void*>(wh_kick_drift_kernel<REBX_B200_RADIATION>), P.st.n);
+        wh_kick_drift_kernel<REBX_B200_RADIATION><<<grid, kThreads, 0, s>>>(P, G, dt_kick, dt_drift);
+    } else if (P.fx[0].kind == REBX_B200_YARKOVSKY) {
+        const int grid = grid_for(reinterpret_cast<const void*>(wh_kick_drift_kernel<REBX_B200_YARKOVSKY>), P.st.n);
+        wh_kick_drift_kernel<REBX_B200_YARKOVSKY><<<grid, kThreads, 0, s>>>(P, G, dt_kick, dt_drift);
+    } else {
+        return cudaErrorNotSupported;          // an effect with back-reaction: use the separate kernels
+    }
+    cudaError_t err = cudaGetLastError();
+    if (err == cudaSuccess && launches) (*launches)++;
+    return err;
+}
+
 int rebx_b200_zero_acc(const rebx_b200_state* st, void* stream, int* launches) {
     if (!st || !st->ax || !st->ay || !st->az) return cudaErrorInvalidValue;
     if (st->n == 0) return 0;

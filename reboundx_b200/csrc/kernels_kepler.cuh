@@ -34,4 +34,49 @@ kepler_drift_kernel(rebx_b200_state st, const double* __restrict__ body, double 
     }
 }
 
+// Fused Wisdom-Holman "kick + drift" for ONE effect that puts no back-reaction on the central body
+// (radiation_forces, yarkovsky_effect): a = effect at the current state (from zero, like the kick of the
+// splitting sees it), v += dt_kick a, Kepler drift about the body for dt_drift -- one pass over the state,
+// the acceleration never exists in HBM.  Same per-particle arithmetic as rebx_b200_zero_acc +
+// rebx_b200_launch_pass + rebx_b200_kick + rebx_b200_kepler_drift.  Without back-reaction the body keeps its
+// velocity through the kick, so every CTA can advance its own copy of the body record; the caller refreshes
+// the record afterwards (rebx_b200_gather_bodies).
+template <int K>
+__global__ void __launch_bounds__(kThreads)
+wh_kick_drift_kernel(const __grid_constant__ rebx_b200_pass P, double G, double dt_kick, double dt_drift) {
+    static_assert(!Traits<K>::red, "the fused kick+drift needs an effect without back-reaction");
+    __shared__ double s_body[REBX_B200_BODY_DOUBLES];
+    if (threadIdx.x < REBX_B200_BODY_DOUBLES) s_body[threadIdx.x] = P.fx[0].body[threadIdx.x];
+    __syncthreads();
+    const rebx_b200_state& st = P.st;
+    const long long bi = (long long)s_body[REBX_B200_BODY_INDEX];
+    const Origin org = load_origin(s_body);
+    const Pre pre = prepare<K>(P.fx[0], org, s_body);
+    const double nx = org.x + dt_drift*org.vx, ny = org.y + dt_drift*org.vy, nz = org.z + dt_drift*org.vz;
+    double* const X = const_cast<double*>(st.x);  double* const Y = const_cast<double*>(st.y);  double* const Z = const_cast<double*>(st.z);
+    double* const VX = const_cast<double*>(st.vx); double* const VY = const_cast<double*>(st.vy); double* const VZ = const_cast<double*>(st.vz);
+    const int64_t stride = (int64_t)gridDim.x*kThreads;
+    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < st.n; k += stride) {
+        if (st.index_base + k == bi) {          // the body: no force on itself, no back-reaction => inertial
+            X[k] = nx; Y[k] = ny; Z[k] = nz;
+            continue;
+        }
+        Particle p;
+        p.x = __ldcs(X + k); p.y = __ldcs(Y + k); p.z = __ldcs(Z + k);
+        p.vx = __ldcs(VX + k); p.vy = __ldcs(VY + k); p.vz = __ldcs(VZ + k);
+        p.m = st.m ? __ldcs(st.m + k) : 0.0;
+        if constexpr (Traits<K>::rad) { p.r = __ldcs(st.r + k); } else { p.r = 0.0; }
+        Params<K, 1> q;
+        load_params<K, 1>(P.fx[0], k, true, q);
+        Vec3 a = {0.0, 0.0, 0.0}, red = {0.0, 0.0, 0.0};
+        unsigned unused = 0;
+        apply<K, 1>(P.fx[0], org, s_body, pre, p, q, 0, a, red, unused);
+        double v[3] = {(p.vx + dt_kick*a.x) - org.vx, (p.vy + dt_kick*a.y) - org.vy, (p.vz + dt_kick*a.z) - org.vz};
+        double x[3] = {p.x - org.x, p.y - org.y, p.z - org.z};
+        rebxb_kepler_drift(G*(org.m + p.m), dt_drift, x, v);
+        __stcs(X + k, nx + x[0]); __stcs(Y + k, ny + x[1]); __stcs(Z + k, nz + x[2]);
+        __stcs(VX + k, org.vx + v[0]); __stcs(VY + k, org.vy + v[1]); __stcs(VZ + k, org.vz + v[2]);
+    }
+}
+
 }  // namespace rebxb

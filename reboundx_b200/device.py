@@ -367,24 +367,37 @@ class Shard:
         k += self.refresh_bodies(group)
         return k
 
-    def wh_steps(self, nsteps, dt, G, group=None):
+    def wh_steps(self, nsteps, dt, G, group=None, fused=True):
         """`nsteps` Wisdom-Holman steps with the half drifts between consecutive kicks merged into one Kepler
         drift of dt (what WHFast does between outputs; host harness scheme `wisdom_holman_merged`):
-        drift(dt/2) [kick drift(dt)]^(n-1) kick drift(dt/2).  One Kepler solve per particle and step."""
+        drift(dt/2) [kick drift(dt)]^(n-1) kick drift(dt/2).  One Kepler solve per particle and step.  A single
+        effect without back-reaction (radiation_forces, yarkovsky_effect) takes its kick + drift in one fused
+        sweep (rebx_b200_wh_kick_drift) unless `fused` is False; the results are the same bits either way."""
         if nsteps <= 0:
             return 0
         reduces = any(kind != 1 and kind != 4 for kind in self.kinds)
+        fused = fused and len(self.kinds) == 1 and not reduces       # rebx_b200_wh_kick_drift: one effect, no back-reaction
         k = self.kepler_drift(0.5*dt, G)
         k += self.refresh_bodies(group)
         for s in range(nsteps):
-            k += self._call("rebx_b200_zero_acc")
-            k += self.launch()
-            if reduces:
-                self.reduce_backreaction(group)
-                k += self.apply_backreaction()
-            k += self.kick(dt)
-            k += self.refresh_bodies(group)
-            k += self.kepler_drift(dt if s + 1 < nsteps else 0.5*dt, G)
+            drift = dt if s + 1 < nsteps else 0.5*dt
+            if fused:
+                n = c_int(0)
+                self.lib.rebx_b200_wh_kick_drift.restype = c_int
+                rc = self.lib.rebx_b200_wh_kick_drift(ctypes.byref(self._pass), c_double(G), c_double(dt), c_double(drift),
+                                                      c_void_p(self._stream(None).cuda_stream), ctypes.byref(n))
+                self._check(rc, "rebx_b200_wh_kick_drift")
+                self.launches += n.value
+                k += n.value
+            else:
+                k += self._call("rebx_b200_zero_acc")
+                k += self.launch()
+                if reduces:
+                    self.reduce_backreaction(group)
+                    k += self.apply_backreaction()
+                k += self.kick(dt)
+                k += self.refresh_bodies(group)
+                k += self.kepler_drift(drift, G)
             k += self.refresh_bodies(group)
         return k
 

@@ -569,14 +569,15 @@ def test_resident_wisdom_holman_matches_host_harness(built, which):
         _assert_trajectories_agree(got, ref)
     # the merged form (one Kepler drift of dt between consecutive kicks), against the host harness doing the same
     ref = _trajectory(w, oracle.ref_lib(), 1000, "wisdom_holman_merged", dt, 1, add)
-    sh = device.Shard(w, add[::-1], "cuda:0")
-    sh.wh_steps(1000, dt, w["G"])
-    torch.cuda.synchronize()
-    got = np.array(sh.posvel())
-    if which == "debris_disk":
-        assert np.array_equal(got, ref)
-    else:
-        _assert_trajectories_agree(got, ref)
+    for fused in (True, False):      # radiation: kick + drift in one sweep (rebx_b200_wh_kick_drift) or as separate kernels
+        sh = device.Shard(w, add[::-1], "cuda:0")
+        sh.wh_steps(1000, dt, w["G"], fused=fused)
+        torch.cuda.synchronize()
+        got = np.array(sh.posvel())
+        if which == "debris_disk":
+            assert np.array_equal(got, ref)
+        else:
+            _assert_trajectories_agree(got, ref)
 
 
 @pytest.mark.parametrize("which", ["debris_disk", "ring_massive", "asteroids", "planetesimals"])
