@@ -953,7 +953,7 @@ def test_reference_conservation_tests(built, name):
     library: star + two 1e-4 planets (a = 1, e = 0.1; a = 2, e = 0.1, inc = 0.2), the force on the device, and
     H = Newtonian energy + the effect's potential (reduced on the device) conserved to the reference's bar of
     1e-12 -- under the fixed-step Gauss-Radau scheme standing in for IAS15, over 300 time units (48 inner orbits; the
-    reference integrates 10^4, which passes as well and takes 10 minutes of host-facing calls)."""
+    reference integrates 10^4; 10^3 was run once with the same result, 300 keeps the GPU suite short)."""
     import ctypes
     from reboundx_b200 import workloads as W
     from reboundx_b200.host import Extras, Simulation
