@@ -106,6 +106,8 @@ struct DeviceContext {
     std::unordered_map<struct rebx_force*, std::unique_ptr<ForceTables>> tables;
     void* registered_ptr = nullptr;
     size_t registered_bytes = 0;
+    void* registered_dev = nullptr;         // device alias of the registered array (zero-copy path of small ensembles)
+    size_t zero_copy_max = 3072;            // particles (measured crossover with pinned DMA: ~3000); REBX_B200_ZEROCOPY_MAX
     Stats stats;
     size_t chunk = size_t(1) << 19;         // 64 MB of AoS records per pipeline stage
     bool chunk_from_env = false;
@@ -113,7 +115,7 @@ struct DeviceContext {
 
     void unregister_host() {
         if (registered_ptr) { cudaHostUnregister(registered_ptr); cudaGetLastError(); }
-        registered_ptr = nullptr; registered_bytes = 0;
+        registered_ptr = nullptr; registered_bytes = 0; registered_dev = nullptr;
     }
     ~DeviceContext() {
         if (ready) {
@@ -372,6 +374,7 @@ static DeviceContext* ensure_ctx(Side* side, std::string& why) {
     if ((e = cudaEventCreateWithFlags(&ctx->bodies_ready, cudaEventDisableTiming)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
     if (const char* c = std::getenv("REBX_B200_CHUNK")) { long v = std::atol(c); if (v >= 1024) { ctx->chunk = (size_t)v & ~size_t(1); ctx->chunk_from_env = true; } }
     if (const char* p = std::getenv("REBX_B200_PARANOID")) ctx->paranoid = std::atoi(p) != 0;
+    if (const char* z = std::getenv("REBX_B200_ZEROCOPY_MAX")) { long v = std::atol(z); if (v >= 0) ctx->zero_copy_max = (size_t)v; }
     ctx->ready = true;
     side->dev = std::move(ctx);
     return side->dev.get();
@@ -681,6 +684,9 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     int launches = 0;
     double* bodies_h = nullptr;
     double* br_h = nullptr;
+    // a small ensemble is read and written by the staging kernels straight through the host mapping (below)
+    const bool small = nchunks == 1 && !whole && N <= ctx->zero_copy_max;
+    unsigned char* zc = nullptr;
 
     // tables to HBM (no-op unless rebuilt)
     for (Entry& e : entries) if (e.T) REBXB_CUDA(upload_tables(*e.T, ctx->stats), "uploading parameter tables");
@@ -698,18 +704,22 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         REBXB_CUDA(ctx->scan.ensure(rebx_b200_scan_scratch_bytes((int64_t)N)), "allocating scan scratch");
         REBXB_CUDA(ctx->totals.ensure(16*sizeof(double)), "allocating mass moments");
     }
-    // Pin the caller's particle array once so the DMA engines can stream it (only worth it for
-    // the simulation's own long-lived array, not for an integrator's scratch copy).
-    if (particles == sim->particles && N*sizeof(struct reb_particle) >= (size_t(256) << 10)) {
+    // Pin the caller's particle array once so the DMA engines can stream it (only worth it for the
+    // simulation's own long-lived array, not for an integrator's scratch copy).  A small ensemble is
+    // pinned as well: its records are then read and its accelerations written by the staging kernels
+    // straight through the mapping (zero copy) -- no DMA descriptors, one PCIe round trip less each way.
+    if (particles == sim->particles && (small || N*sizeof(struct reb_particle) >= (size_t(256) << 10))) {
         if (ctx->registered_ptr != particles || ctx->registered_bytes != N*sizeof(struct reb_particle)) {
             ctx->unregister_host();
-            if (cudaHostRegister(particles, N*sizeof(struct reb_particle), cudaHostRegisterDefault) == cudaSuccess) {
+            if (cudaHostRegister(particles, N*sizeof(struct reb_particle), cudaHostRegisterMapped) == cudaSuccess) {
                 ctx->registered_ptr = particles; ctx->registered_bytes = N*sizeof(struct reb_particle);
+                if (cudaHostGetDevicePointer(&ctx->registered_dev, particles, 0) != cudaSuccess) { ctx->registered_dev = nullptr; cudaGetLastError(); }
             } else {
                 cudaGetLastError();     // pageable copies still work, just slower
             }
         }
     }
+    if (small && ctx->registered_ptr == particles) zc = static_cast<unsigned char*>(ctx->registered_dev);
 
     bodies_h = static_cast<double*>(ctx->bodies_h.p);
     for (size_t e = 0; e < ne; e++) fill_body(bodies_h + e*REBX_B200_BODY_DOUBLES, entries[e], particles);
@@ -726,7 +736,8 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         cudaStream_t s = ctx->stream[b];
         const size_t c0 = c*CH, n = std::min(CH, N - c0);
         const size_t bytes = n*sizeof(struct reb_particle);
-        REBXB_CUDA(copy_page_split(ctx->aos[b].p, particles + c0, bytes, cudaMemcpyHostToDevice, s), "copying particles to the device");
+        void* const aos_in = zc ? static_cast<void*>(zc) : ctx->aos[b].p;      // zc: nchunks == 1, so c0 == 0
+        if (!zc) REBXB_CUDA(copy_page_split(ctx->aos[b].p, particles + c0, bytes, cudaMemcpyHostToDevice, s), "copying particles to the device");
         ctx->stats.h2d_bytes += bytes;
         double* base = static_cast<double*>(ctx->soa[b].p);
         rebx_b200_state st;
@@ -736,7 +747,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         st.m = need_m ? base + 6*soa_stride : nullptr;
         st.r = need_r ? base + 7*soa_stride : nullptr;
         st.ax = base + 8*soa_stride; st.ay = base + 9*soa_stride; st.az = base + 10*soa_stride;
-        REBXB_CUDA((cudaError_t)rebx_b200_unpack_aos(ctx->aos[b].p, &L, &st, s, &launches), "unpacking particles");
+        REBXB_CUDA((cudaError_t)rebx_b200_unpack_aos(aos_in, &L, &st, s, &launches), "unpacking particles");
         for (size_t e0 = 0; e0 < ne;) {
             // consecutive entries sharing a reference-frame class form one launch group
             const int frame = entries[e0].frame;
@@ -804,9 +815,9 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
             }
             e0 = e1;
         }
-        REBXB_CUDA((cudaError_t)rebx_b200_pack_acc_aos(ctx->aos[b].p, &L, &st, s, &launches), "packing accelerations");
-        REBXB_CUDA(copy_page_split(particles + c0, ctx->aos[b].p, bytes, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
-        ctx->stats.d2h_bytes += bytes;
+        REBXB_CUDA((cudaError_t)rebx_b200_pack_acc_aos(aos_in, &L, &st, s, &launches), "packing accelerations");
+        if (!zc) REBXB_CUDA(copy_page_split(particles + c0, ctx->aos[b].p, bytes, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
+        ctx->stats.d2h_bytes += zc ? n*3*sizeof(double) : bytes;
     }
     if (nchunks > 1) for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamSynchronize(ctx->stream[b]), "waiting for the device");
     br_h = static_cast<double*>(ctx->br_h.p);
