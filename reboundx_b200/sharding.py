@@ -92,9 +92,28 @@ def exclusive_suffix(rows, rank):
     return out
 
 
+def _gathered(row, group=None):
+    """All ranks' rows as ONE (world, ...) tensor with a single collective (NCCL); None on other backends."""
+    import torch.distributed as dist
+    world, _ = _world(group)
+    if world == 1 or dist.get_backend(group) != "nccl":
+        return None
+    buf = row.new_empty((world,) + tuple(row.shape))
+    dist.all_gather_into_tensor(buf, row.contiguous(), group=group)
+    return buf
+
+
 def exchange_prefix(row, group=None):
-    return exclusive_prefix(gather_rows(row, group), _world(group)[1])
+    """Exclusive prefix over ranks of a small row: one all-gather + one reduction kernel on NCCL (the list
+    form, `exclusive_prefix(gather_rows(...))`, elsewhere -- same value up to the order of the additions)."""
+    buf = _gathered(row, group)
+    if buf is None:
+        return exclusive_prefix(gather_rows(row, group), _world(group)[1])
+    return buf[:_world(group)[1]].sum(dim=0)
 
 
 def exchange_suffix(row, group=None):
-    return exclusive_suffix(gather_rows(row, group), _world(group)[1])
+    buf = _gathered(row, group)
+    if buf is None:
+        return exclusive_suffix(gather_rows(row, group), _world(group)[1])
+    return buf[_world(group)[1] + 1:].sum(dim=0)
