@@ -50,6 +50,7 @@ def parse():
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
+    ap.add_argument("--no-parallel-bound", action="store_true", help="skip the all-cores upper bound of the CPU baseline")
     ap.add_argument("--coordinates", default="PARTICLE", choices=["PARTICLE", "JACOBI", "BARYCENTRIC"],
                     help="reference frame of the rebx_com_force effects (planetesimal_disk only)")
     return ap.parse_args()
@@ -142,6 +143,29 @@ def cpu_reference_leg(workload, add_order, sample_n, reps, coordinates="PARTICLE
             "ms_per_dispatch": t*1e3}
 
 
+def cpu_parallel_upper_bound(workload, per_worker):
+    """What the box's host cores could do if the reference's dispatch were run as `nproc` independent shards at
+    once (it is not: REBOUNDx's force path is single-threaded).  Reported next to the 1-core
+    reference figure as an upper bound for a hypothetical embarrassingly-parallel CPU version -- the number the
+    PCIe-bound end-to-end figure has to be read against; the resident figures are three orders above both."""
+    n = len(os.sched_getaffinity(0))
+    cmd = [sys.executable, os.path.abspath(__file__), "--impl", "reference", "--workload", workload, "--steps", "5",
+           "--cpu-sample", str(per_worker), "--no-parallel-bound"]
+    env = dict(os.environ, OMP_NUM_THREADS="1")
+    t0 = time.perf_counter()
+    procs = [subprocess.Popen(cmd, stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True, env=env) for _ in range(n)]
+    vals = []
+    for p in procs:
+        out, _ = p.communicate(timeout=300)
+        for line in out.splitlines():
+            if line.startswith("{"):
+                vals.append(json.loads(line)["value"])
+    if len(vals) != n:
+        return None
+    return {"value": float(sum(vals)), "unit": "evals/s", "cores": n, "kind": "not the reference: %d concurrent single-threaded dispatches, each on its own sample" % n,
+            "sample": f"{per_worker} particles per worker", "seconds": round(time.perf_counter() - t0, 1)}
+
+
 def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
@@ -160,6 +184,8 @@ def run_reference(args):
             "cpu_baseline": {k: base[k] for k in ("value", "unit", "cores", "kind", "sample")},
             "e2e": {"value": base["value"], "unit": "evals/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}
     line["cpu_baseline"]["unit"] = "evals/s"
+    if not args.no_parallel_bound and args.coordinates == "PARTICLE":
+        line["cpu_baseline"]["parallel_upper_bound"] = cpu_parallel_upper_bound(args.workload, min(500_000, sample))
     print(json.dumps(line), flush=True)
 
 
@@ -360,6 +386,8 @@ def run_ours(args):
         cpu = cpu_reference_leg(builder, add_order, min(args.cpu_sample, n) if not com else min(20000, n), 5, args.coordinates)
         cpu["unit"] = "evals/s"
         cpu.pop("ms_per_dispatch")
+        if not args.no_parallel_bound and not com:
+            cpu["parallel_upper_bound"] = cpu_parallel_upper_bound(args.workload, min(500_000, n))
 
     if rank == 0:
         line = {"metric": METRIC, "value": value, "unit": "evals/s", "n_gpus": world, "steps": args.steps, "warmup": max(3, args.warmup),
