@@ -244,6 +244,14 @@ struct Loader {
         param->name = const_cast<char*>(name);
         param->type = static_cast<enum rebx_param_type>(type);
         param->value = nullptr;
+        // a payload must have the size its type says (a FORCE reference: a NUL-terminated name), or later
+        // readers of the value would run past it
+        if (value && vsize > 0) {
+            const size_t want = payload_bytes(param->type);
+            const bool ok = param->type == REBX_TYPE_FORCE ? std::memchr(value, 0, (size_t)vsize) != nullptr
+                                                           : (want == 0 || (size_t)vsize == want);
+            if (!ok) { warn(REBX_INPUT_BINARY_ERROR_CORRUPT); value = nullptr; }
+        }
         if (value && vsize > 0) {
             param->value = malloc((size_t)vsize);
             if (!param->value) { warn(REBX_INPUT_BINARY_ERROR_NO_MEMORY); free(param); return nullptr; }

@@ -177,7 +177,7 @@ class Simulation:
         n = self._shim.reb_shim_message_count(self._p)
         out = []
         for i in range(n):
-            s = self._shim.reb_shim_message(self._p, i).decode()
+            s = self._shim.reb_shim_message(self._p, i).decode(errors="replace")
             out.append(("error" if s[0] == "E" else "warning", s[1:]))
         if clear:
             self._shim.reb_shim_clear_messages(self._p)
