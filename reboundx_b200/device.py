@@ -426,6 +426,32 @@ class Shard:
         self.launches += n.value
         return n.value
 
+    def capture_steps(self, nsteps, dt, G, scheme="leapfrog"):
+        """CUDA graph of `nsteps` resident steps (scheme "leapfrog": fused_leapfrog_step; "whfast": wh_steps with
+        merged drifts) for launch-bound ensembles: at N ~ 10^3 a step is 2-3 kernels of a few microseconds each,
+        so the launches cost more than the work; replaying a captured graph issues them all with one call.
+        Single shard (no collectives inside the capture).  Returns the torch.cuda.CUDAGraph; `.replay()` advances
+        the state by `nsteps` steps -- the same bits as the eager calls."""
+        torch = self.torch
+        if not self.standalone and sharding._world(None)[0] > 1:
+            raise RuntimeError("capture_steps records one shard's kernels; sharded stepping has collectives between them")
+        step = (lambda: self.wh_steps(nsteps, dt, G)) if scheme == "whfast" else (lambda: [self.fused_leapfrog_step(dt, G) for _ in range(nsteps)])
+        # every kernel must have been launched once before a capture (module loading is not capturable): do a
+        # throw-away run on the live state and put the state back
+        keep = {k: v.clone() for k, v in self.state.items()}
+        bodies = self.bodies.clone()
+        step()
+        for k, v in keep.items():
+            self.state[k].copy_(v)
+        self.bodies.copy_(bodies)
+        torch.cuda.synchronize(self.device)
+        graph = torch.cuda.CUDAGraph()
+        side = torch.cuda.Stream(self.device)
+        side.wait_stream(torch.cuda.current_stream(self.device))
+        with torch.cuda.graph(graph, stream=side):
+            step()
+        return graph
+
     def integrate_force(self, dt, scheme="rk4", stream=None):
         """Velocities across `dt` under this shard's stacked effects alone (positions fixed): the
         reference's integrate_force operator (src/integrate_force.c) with its euler / rk2 / rk4 /

@@ -580,6 +580,29 @@ def test_resident_wisdom_holman_matches_host_harness(built, which):
             _assert_trajectories_agree(got, ref)
 
 
+@pytest.mark.parametrize("scheme", ["leapfrog", "whfast"])
+def test_cuda_graph_of_resident_steps(built, scheme):
+    """device.Shard.capture_steps: a CUDA graph of 20 resident steps of the 1000-grain example, replayed 10 times,
+    gives the bits of 200 eager steps (and the launches no longer dominate: timed in tools/latency_probe.py)."""
+    import torch
+    from reboundx_b200 import device, workloads
+    w = workloads.debris_disk(1000, seed=3)
+    eager = device.Shard(w, ["radiation_forces"], "cuda:0")
+    if scheme == "whfast":
+        for _ in range(10):
+            eager.wh_steps(20, 1e8, w["G"])
+    else:
+        for _ in range(200):
+            eager.fused_leapfrog_step(1e8, w["G"])
+    torch.cuda.synchronize()
+    graphed = device.Shard(w, ["radiation_forces"], "cuda:0")
+    g = graphed.capture_steps(20, 1e8, w["G"], scheme)
+    for _ in range(10):
+        g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(np.array(graphed.posvel()), np.array(eager.posvel()))
+
+
 @pytest.mark.parametrize("which", ["debris_disk", "ring_massive", "asteroids", "planetesimals"])
 def test_fused_leapfrog_step_equals_separate_sweeps(built, which):
     """rebx_b200_leapfrog_step (one sweep, accelerations in registers) against the five separate

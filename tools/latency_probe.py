@@ -15,3 +15,20 @@ for n in sizes:
     st = rebx.stats()
     print(f"N = {n:7d}: {t*1e6:8.1f} us per call   (zero-copy max {os.environ.get('REBX_B200_ZEROCOPY_MAX', 'default')})", flush=True)
     rebx.detach(); sim.free()
+
+
+# resident stepping of a small ensemble: eager launches vs a replayed CUDA graph (device.Shard.capture_steps)
+import time
+import torch
+from reboundx_b200 import device
+for n in (1000, 10000):
+    w = workloads.debris_disk(n, seed=3)
+    for scheme, eager in (("leapfrog", lambda sh: [sh.fused_leapfrog_step(1e8, w["G"]) for _ in range(100)]),
+                          ("whfast", lambda sh: sh.wh_steps(100, 1e8, w["G"]))):
+        sh = device.Shard(w, ["radiation_forces"], "cuda:0")
+        eager(sh); torch.cuda.synchronize()
+        t0 = time.perf_counter(); eager(sh); torch.cuda.synchronize(); te = (time.perf_counter() - t0)/100
+        g = sh.capture_steps(100, 1e8, w["G"], scheme)
+        g.replay(); torch.cuda.synchronize()
+        t0 = time.perf_counter(); g.replay(); torch.cuda.synchronize(); tg = (time.perf_counter() - t0)/100
+        print(f"resident {scheme:8s} N = {n:6d}: eager {te*1e6:6.1f} us/step, CUDA graph {tg*1e6:6.1f} us/step", flush=True)
