@@ -1089,6 +1089,45 @@ def test_reference_machine_independent_tests(built, tmp_path, name):
     assert np.max(np.abs(first[:3, 1:] - x0)) > 1e-3    # the planets did move
 
 
+def test_reference_gr_nactive(built):
+    """reference reboundx/tests/test_gr.py:62-92 (test_Nactive): star + 1e-3 planet + two massless bodies under `gr`;
+    with N_active unset every body is "active" (here: the host part of this library's gr), with N_active = 2 the two
+    massless ones are test particles (here: the device sweep); after 100 time units particles[3].x must agree to
+    1e-12.  IAS15 -> the fixed-step Gauss-Radau stand-in, dt = P/100."""
+    import gr_notebook as nb
+    from reboundx_b200 import workloads as W
+    from reboundx_b200.host import Extras, Simulation
+    m = np.array([1.0, 1.0e-3, 0.0, 0.0])
+    cols = [np.zeros(4) for _ in range(6)]
+    msum = 1.0
+    for i, a in ((1, 1.0), (2, 2.0), (3, 3.0)):          # sim.add(a=..., e=0.1): about the centre of mass of what is there
+        el = [float(v[0]) for v in W.kepler_to_cartesian(msum + m[i], np.array([a]), np.array([0.1]), np.array([0.0]), np.array([0.0]), np.array([0.0]), np.array([0.0]))]
+        com = [(m[:i]*cols[k][:i]).sum()/msum for k in range(6)]
+        for k in range(6):
+            cols[k][i] = com[k] + el[k]
+        msum += m[i]
+    for k in range(6):
+        cols[k] = cols[k] - (m*cols[k]).sum()/m.sum()     # move_to_com
+    out = []
+    for n_active in (None, 2):
+        sim = Simulation(G=1.0)
+        sim.set_particles(cols[0], cols[1], cols[2], cols[3], cols[4], cols[5], m)
+        rebx = Extras(sim)
+        gr = rebx.load_force("gr"); rebx.add_force(gr); gr.params["c"] = nb.C
+        if n_active is not None:
+            sim.N_active = n_active
+        period = 2*np.pi/np.sqrt(1.001)
+        nsteps = int(round(100.0/(period/100)))
+        sim.dt = 100.0/nsteps
+        sim.integrate(nsteps, "gauss_radau")
+        sim.process_messages()
+        out.append(np.array(sim.posvel())[0][3])
+        launches = rebx.stats()["launches"]
+        rebx.detach(); sim.free()
+    assert launches > 0
+    assert abs((out[1] - out[0])/out[0]) < 1.0e-12, out
+
+
 def test_reference_gr_simple(built):
     """reference reboundx/tests/test_rebx.py:29-34: gr with c = 100 turns the pericentre by more than 1e-4 in 10 time units."""
     from reboundx_b200 import workloads as W
