@@ -69,7 +69,17 @@ def _new_simulation():
     return Simulation.from_address(ptr)
 
 
-def _add(self, m=0.0, x=0.0, y=0.0, z=0.0, vx=0.0, vy=0.0, vz=0.0, r=0.0):
+def _add(self, m=0.0, x=0.0, y=0.0, z=0.0, vx=0.0, vy=0.0, vz=0.0, r=0.0, a=None, e=0.0):
+    """sim.add(m=...) in Cartesian form, or sim.add(a=..., e=...): a planar orbit at pericentre about the centre of mass
+    of the particles already there (rebound's default primary), mu = G (M + m)."""
+    if a is not None:
+        import math
+        ps = [self._particles[i] for i in range(self.N)]
+        M = sum(q.m for q in ps)
+        com = [sum(q.m*getattr(q, k) for q in ps)/M for k in ("x", "y", "z", "vx", "vy", "vz")]
+        mu = self.G*(M + m)
+        x, y, z = com[0] + a*(1.0 - e), com[1], com[2]
+        vx, vy, vz = com[3], com[4] + math.sqrt(mu*(1.0 + e)/(a*(1.0 - e))), com[5]
     p = Particle(x=x, y=y, z=z, vx=vx, vy=vy, vz=vz, m=m, r=r)
     _shim.reb_simulation_add.argtypes = [c_void_p, Particle]
     _shim.reb_simulation_add(c_void_p(ctypes.addressof(self)), p)
@@ -95,6 +105,45 @@ def _call_additional_forces(self):
     _shim.reb_shim_call_additional_forces(c_void_p(ctypes.addressof(self)))
 
 
+def _integrate(self, tmax):
+    """sim.integrate(t): fixed-step 15th-order Gauss-Radau of the stand-in (the scheme behind IAS15), 100 steps per
+    innermost orbit, gravity of all bodies + additional_forces."""
+    import math
+    span = tmax - self.t
+    if span <= 0 or self.N < 2:
+        return
+    p0, p1 = self._particles[0], self._particles[1]
+    d = math.sqrt((p1.x - p0.x)**2 + (p1.y - p0.y)**2 + (p1.z - p0.z)**2)
+    period = 2*math.pi*math.sqrt(d**3/(self.G*(p0.m + p1.m)))
+    n = max(1, int(math.ceil(span/(period/100))))
+    self.dt = span/n
+    _shim.reb_shim_integrate.argtypes = [c_void_p, c_int, c_int]
+    _shim.reb_shim_integrate(c_void_p(ctypes.addressof(self)), n, 2)
+    self.process_messages()
+
+
+def _pomega(self):
+    """Longitude of pericentre about particles[0] (planar orbits: the angle of the eccentricity vector)."""
+    import math
+    sim = self._sim.contents
+    p0 = sim._particles[0]
+    mu = sim.G*(p0.m + self.m)
+    d = (self.x - p0.x, self.y - p0.y, self.z - p0.z)
+    v = (self.vx - p0.vx, self.vy - p0.vy, self.vz - p0.vz)
+    r = math.sqrt(sum(c*c for c in d)); v2 = sum(c*c for c in v); rv = sum(a*b for a, b in zip(d, v))
+    ex, ey = ((v2 - mu/r)*d[0] - rv*v[0])/mu, ((v2 - mu/r)*d[1] - rv*v[1])/mu
+    return math.atan2(ey, ex)
+
+
+def _sim_new(cls, *args, **kwargs):
+    _shim.reb_simulation_create.restype = c_void_p
+    return cls.from_address(_shim.reb_simulation_create())
+
+
+Simulation.__new__ = staticmethod(lambda cls, *a, **k: _sim_new(cls))
+Simulation.__init__ = lambda self, *a, **k: None
+Simulation.integrate = _integrate
+Particle.pomega = property(_pomega)
 Simulation.add = _add
 Simulation.process_messages = _process_messages
 Simulation.particles = property(_particles)

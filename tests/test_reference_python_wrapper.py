@@ -116,3 +116,24 @@ def test_custom_python_force_is_dispatched(reboundx):
     sim.process_messages()
     assert calls == [3]
     assert sim.particles[1].ax == 0.125
+
+
+def test_the_references_own_force_tests_pass_unmodified(reboundx):
+    """reference reboundx/tests/test_effects.py, class TestForces (12 tests: load / create / get / remove forces, the
+    error cases of add_force, a custom Python force integrated for 10 time units), imported in place and run
+    UNMODIFIED: `import reboundx` resolves to the reference's wrapper bound to this library, `import rebound` to
+    tests/fake_rebound.  (The other classes of that file need operators, the other files a GPU for the built-in
+    forces -- those are ported one by one in tests/test_gpu_parity.py.)"""
+    import importlib.util
+    import unittest
+    path = os.path.join(REF, "reboundx", "tests", "test_effects.py")
+    spec = importlib.util.spec_from_file_location("reference_test_effects", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    suite = unittest.TestLoader().loadTestsFromTestCase(mod.TestForces)
+    assert suite.countTestCases() == 12
+    result = unittest.TestResult()
+    suite.run(result)
+    problems = [(str(t), tb) for t, tb in result.errors + result.failures]
+    assert not problems, problems[0]
+    assert result.testsRun == 12
