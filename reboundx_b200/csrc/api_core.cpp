@@ -529,22 +529,32 @@ static void set_array(struct rebx_extras* rebx, const char* name, const int64_t*
     }
     const char* iname = intern_name(name);
     struct reb_simulation* sim = rebx->sim;
-    for (size_t k = 0; k < n; k++) {
-        const size_t i = index ? static_cast<size_t>(index[k]) : k;
-        if (i >= sim->N) { rebx_error(rebx, "REBOUNDx Error: particle index out of range in array parameter setter.\n"); break; }
-        struct rebx_node** apptr = reinterpret_cast<struct rebx_node**>(&sim->particles[i].ap);
-        struct rebx_param* param = find_param(*apptr, iname);
-        if (!param) {
-            param = rebx_create_param(rebx, iname, type);
-            if (!param) break;
-            struct rebx_node* node = rebx_create_node(rebx);
-            if (!node) { rebx_free_param(param); break; }
-            node->object = param;
-            rebx_add_node(apptr, node);
+    // Distinct particles are independent (each owns its list; malloc is thread-safe), so an index list that is
+    // strictly increasing -- or absent -- is filled by several threads; anything else stays on one.
+    bool increasing = true;
+    for (size_t k = 1; index && k < n && increasing; k++) increasing = index[k] > index[k - 1];
+    std::atomic<int> status{0};         // 1: index out of range, 2: out of memory
+    auto fill = [&](int, size_t lo, size_t hi) {
+        for (size_t k = lo; k < hi; k++) {
+            const size_t i = index ? static_cast<size_t>(index[k]) : k;
+            if (i >= sim->N) { status = 1; return; }
+            struct rebx_node** apptr = reinterpret_cast<struct rebx_node**>(&sim->particles[i].ap);
+            struct rebx_param* param = find_param(*apptr, iname);
+            if (!param) {
+                param = static_cast<struct rebx_param*>(malloc(sizeof *param));
+                struct rebx_node* node = static_cast<struct rebx_node*>(malloc(sizeof *node));
+                if (!param || !node) { free(param); free(node); status = 2; return; }
+                param->name = const_cast<char*>(iname); param->type = type; param->value = nullptr;
+                node->object = param; node->next = *apptr; *apptr = node;
+            }
+            if (param->value == nullptr) param->value = malloc(sizeof(T));
+            if (!param->value) { status = 2; return; }
+            *static_cast<T*>(param->value) = val[k];
         }
-        if (param->value == nullptr) param->value = rebx_malloc(rebx, sizeof(T));
-        if (param->value) *static_cast<T*>(param->value) = val[k];
-    }
+    };
+    if (increasing) parallel_ranges(n, fill); else fill(0, 0, n);
+    if (status == 1) rebx_error(rebx, "REBOUNDx Error: particle index out of range in array parameter setter.\n");
+    if (status == 2) rebx_error(rebx, "REBOUNDx Error: Could not allocate memory.\n");
     mark_dirty(rebx);
 }
 }  // extern "C++"

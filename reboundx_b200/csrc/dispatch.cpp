@@ -161,21 +161,6 @@ static inline bool same_name(const char* a, const char* b) {
     return a == b || (a[0] == b[0] && std::strcmp(a, b) == 0);
 }
 
-template <typename Fn>
-static void parallel_ranges(size_t N, Fn fn) {
-    unsigned hw = std::thread::hardware_concurrency();
-    if (hw == 0) hw = 1;
-    size_t T = std::min<size_t>(std::min<size_t>(hw, 32), N/32768 + 1);
-    if (T <= 1) { fn(0, size_t(0), N); return; }
-    std::vector<std::thread> th;
-    const size_t per = (N + T - 1)/T;
-    for (size_t t = 0; t < T; t++) {
-        const size_t lo = std::min(N, t*per), hi = std::min(N, lo + per);
-        th.emplace_back([=] { fn((int)t, lo, hi); });
-    }
-    for (auto& x : th) x.join();
-}
-
 // uvw(): reference src/gravitational_harmonics.c:104-134 (body-fixed frame from the spin vector)
 static void spin_frame(const struct reb_vec3d Omega, Oblate& o) {
     const double omega2 = Omega.x*Omega.x + Omega.y*Omega.y + Omega.z*Omega.z;

@@ -5,7 +5,9 @@
 #include <cstddef>
 #include <memory>
 #include <mutex>
+#include <algorithm>
 #include <string>
+#include <thread>
 #include <unordered_map>
 #include <vector>
 
@@ -44,6 +46,23 @@ struct rebx_param* find_param(struct rebx_node* ap, const char* name);
 inline void* find_value(struct rebx_node* ap, const char* name) {
     struct rebx_param* p = find_param(ap, name);
     return p ? p->value : nullptr;
+}
+
+// Runs fn(thread, lo, hi) over [0, N) split into contiguous ranges on up to 32 host threads (one range on the
+// calling thread when N is small).  Used by the table builder and the bulk parameter setters.
+template <typename Fn>
+inline void parallel_ranges(size_t N, Fn fn) {
+    unsigned hw = std::thread::hardware_concurrency();
+    if (hw == 0) hw = 1;
+    size_t T = std::min<size_t>(std::min<size_t>(hw, 32), N/32768 + 1);
+    if (T <= 1) { fn(0, size_t(0), N); return; }
+    std::vector<std::thread> th;
+    const size_t per = (N + T - 1)/T;
+    for (size_t t = 0; t < T; t++) {
+        const size_t lo = std::min(N, t*per), hi = std::min(N, lo + per);
+        th.emplace_back([=] { fn((int)t, lo, hi); });
+    }
+    for (auto& x : th) x.join();
 }
 
 }  // namespace rebxh
