@@ -368,6 +368,47 @@ struct Loader {
         }
     }
 
+    // The PARTICLES container: one record per particle, each touching only its own particle's list.  A large file
+    // whose records carry strictly increasing particle indices (every file this library or the reference writes) is
+    // loaded by several threads, each with its own name cache and warning word; anything else goes record by record.
+    bool load_particles(Cursor& c) {
+        struct Item { const unsigned char* p; long size; };
+        std::vector<Item> items;
+        bool increasing = true, well_formed = true;
+        long last_index = -1;
+        {
+            Cursor scan = c;
+            struct rebx_binary_field f;
+            for (;;) {
+                if (!scan.field(f)) { well_formed = false; break; }
+                if (f.type == REBX_BINARY_FIELD_TYPE_END) break;
+                if (f.type != REBX_BINARY_FIELD_TYPE_PARTICLE || !scan.has(f.size)) { well_formed = false; break; }
+                // peek at the record's PARTICLE_INDEX (its first field)
+                struct rebx_binary_field g;
+                int index = -1;
+                if ((size_t)f.size >= kFieldBytes + sizeof(int)) {
+                    std::memcpy(&g, scan.p, kFieldBytes);
+                    if (g.type == REBX_BINARY_FIELD_TYPE_PARTICLE_INDEX && g.size == (long)sizeof(int)) std::memcpy(&index, scan.p + kFieldBytes, sizeof index);
+                }
+                if (index <= last_index) increasing = false;
+                last_index = index;
+                items.push_back({scan.p, f.size});
+                scan.skip(f.size);
+            }
+        }
+        if (!well_formed || !increasing || items.size() < 500000) return load_list(c, REBX_BINARY_FIELD_TYPE_PARTICLE, nullptr);
+        std::vector<int> w(64, 0);
+        parallel_ranges(items.size(), [&](int t, size_t lo, size_t hi) {
+            Loader local{rebx, &w[(size_t)t], {}};
+            for (size_t i = lo; i < hi; i++) {
+                Cursor item = {items[i].p, items[i].p + items[i].size};
+                if (!local.load_particle(item)) local.warn(REBX_INPUT_BINARY_WARNING_PARTICLE_PARAMS_NOT_LOADED);
+            }
+        });
+        for (int bits : w) *warnings |= bits;
+        return true;
+    }
+
     void load_structure(Cursor& c) {
         struct rebx_binary_field f;
         for (;;) {
@@ -399,7 +440,7 @@ struct Loader {
             switch (f.type) {
                 case REBX_BINARY_FIELD_TYPE_REBX_STRUCTURE: load_structure(body); break;
                 case REBX_BINARY_FIELD_TYPE_PARTICLES:
-                    if (!load_list(body, REBX_BINARY_FIELD_TYPE_PARTICLE, nullptr)) warn(REBX_INPUT_BINARY_ERROR_CORRUPT);
+                    if (!load_particles(body)) warn(REBX_INPUT_BINARY_ERROR_CORRUPT);
                     break;
                 default: warn(REBX_INPUT_BINARY_WARNING_LIST_UNKNOWN); break;
             }
