@@ -285,3 +285,31 @@ def test_loader_survives_random_corruption(built, tmp_path):
         s.free()
     assert flagged > 100            # most corruptions are noticed; none may crash
     rebx.detach(); sim.free()
+
+
+def test_threaded_loading_of_a_large_file(built, tmp_path):
+    """From 5*10^5 particle records on the loader works on several threads (records with increasing indices touch
+    disjoint particles): every value of a 6*10^5-particle file comes back, through the SoA table of the force."""
+    from reboundx_b200 import load
+    from reboundx_b200.host import Extras, Simulation
+    lib = load()
+    n = 600_000
+    z = np.zeros(n)
+    beta = np.random.default_rng(2).uniform(0.01, 0.5, n)
+    beta[::7] = np.nan                                                    # marks "not set" below
+    sim = Simulation(G=1.0); sim.set_particles(z, z, z, m=z)
+    rebx = Extras(sim)
+    rad = rebx.load_force("radiation_forces"); rad.params["c"] = 3.0e8; rebx.add_force(rad)
+    have = np.flatnonzero(~np.isnan(beta)).astype(np.int64)
+    vals = beta[have].copy()
+    lib.rebx_set_param_double_array(rebx._ptr, b"beta", have.ctypes.data_as(ctypes.c_void_p), vals.ctypes.data_as(ctypes.c_void_p), ctypes.c_size_t(len(have)))
+    path = tmp_path / "large.rebx"
+    rebx.save(path)
+    sim2 = Simulation(G=1.0); sim2.set_particles(z, z, z, m=z)
+    rebx2 = Extras(sim2, str(path))
+    table = rebx2.host_table(rebx2.get_force("radiation_forces"), 0)      # the SoA beta table built from the loaded lists
+    assert table.shape[0] == n
+    assert np.array_equal(table[have], vals)
+    absent = np.ones(n, dtype=bool); absent[have] = False
+    assert np.all(np.isnan(table[absent]))                                # REBX_B200_ABSENT_BITS is a NaN payload
+    rebx2.detach(); sim2.free(); rebx.detach(); sim.free()
