@@ -692,6 +692,29 @@ def test_full_size_against_oracle_on_a_random_subsample(built, name):
     assert all(np.isfinite(a).all() for a in got)
 
 
+def test_full_size_resident_wisdom_holman_against_the_host_harness_on_a_subsample(built):
+    """BASELINE config 2 at its full size, "radiation_forces under WHFast": 50 resident Wisdom-Holman steps of 10^7
+    grains (fused kick + Kepler drift sweeps), and -- test particles being independent -- the host harness stepping
+    the reference-compiled force on a random subsample of 2000 of them must land on the same bits."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    n, steps, dt = 10_000_000, 50, 1e8
+    w = workloads.debris_disk(n, seed=3)
+    sh = device.Shard(w, ["radiation_forces"], "cuda:0")
+    sh.wh_steps(steps, dt, w["G"])
+    torch.cuda.synchronize()
+    got = np.array(sh.posvel())
+    idx = np.sort(np.random.default_rng(17).choice(np.arange(1, n + 1), size=2000, replace=False))
+    sub = _subsample(w, idx, ["beta"])
+    ref = _trajectory(sub, oracle.ref_lib(), steps, "wisdom_holman_merged", dt, 1, ["radiation_forces"])
+    assert np.array_equal(got[:, np.concatenate([[0], idx])], ref)
+    moved = np.abs(got[0, 1:] - w["x"][1:])
+    assert np.median(moved) > 1e6                     # metres: the grains did move
+
+
 def test_full_size_radiation_is_linear_in_beta_and_shard_independent(built):
     """Config 2 at 10^7: doubling every beta doubles every force exactly (a power-of-two scaling
     commutes with each rounding), and cutting the ensemble into three ragged shards changes no bit."""
