@@ -13,7 +13,11 @@ JSON keys (one line, rank 0): value = evals/s with state resident in HBM (CUDA e
 ranks); e2e = evals/s through the REBOUND-facing call sim->additional_forces(sim) on HOST
 particle arrays, host<->device copies inside the timed region; roofline = the sweep kernel's
 algorithmic HBM bytes / its event-timed duration vs the measured copy bandwidth;
-cpu_baseline = the reference's own C loop (oracle/_ref) on one host core, bounded sample.
+cpu_baseline = the reference's own C loop (oracle/_ref) on one host core, bounded sample (+ parallel_upper_bound:
+all host cores running independent single-threaded dispatches, labelled not-the-reference);
+resident_step / resident_wh_step = whole integrator steps with the state kept in HBM (fused drift-kick-drift
+sweep; Wisdom-Holman with Kepler drifts); --coordinates JACOBI|BARYCENTRIC runs the damping trio in the
+centre-of-mass frames of rebx_com_force (sharded across ranks with prefix / suffix exchanges).
 """
 import argparse
 import json
