@@ -35,7 +35,10 @@ namespace rebxb {
 #ifndef REBXB_HEAVY_MINBLOCKS
 #define REBXB_HEAVY_MINBLOCKS 2
 #endif
-constexpr int kThreads   = 256;
+#ifndef REBXB_THREADS
+#define REBXB_THREADS 256
+#endif
+constexpr int kThreads   = REBXB_THREADS;    // threads per CTA of the sweeps (128 was measured too)
 constexpr int kMaxBlocks = 4096;
 constexpr int kWarps     = kThreads/32;
 
@@ -167,7 +170,7 @@ template <int K0, int K1, int K2, int K3>
 __host__ __device__ constexpr int min_blocks() {
     constexpr bool light = (K0 == REBX_B200_RADIATION || K0 == REBX_B200_GR_POTENTIAL) &&
                            (K1 == 0 || K1 == REBX_B200_RADIATION || K1 == REBX_B200_GR_POTENTIAL) && K2 == 0 && K3 == 0;
-    return light ? 4 : REBXB_HEAVY_MINBLOCKS;
+    return light ? 4*(256/kThreads) : REBXB_HEAVY_MINBLOCKS;
 }
 
 template <int V, bool SHARED, int K0, int K1, int K2, int K3>
