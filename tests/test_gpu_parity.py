@@ -692,6 +692,27 @@ def test_full_size_against_oracle_on_a_random_subsample(built, name):
     assert all(np.isfinite(a).all() for a in got)
 
 
+def test_fused_wisdom_holman_sweep_with_yarkovsky(built):
+    """rebx_b200_wh_kick_drift's second instantiation (yarkovsky_effect alone: all three modes in the ensemble):
+    the fused kick + drift sweep gives the bits of the separate kernels, and follows the host harness stepping the
+    reference-compiled force to the tolerance of criterion (ii)."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    w = workloads.asteroid_ensemble(3000)
+    dt, steps = 0.01, 300
+    out = []
+    for fused in (True, False):
+        sh = device.Shard(w, ["yarkovsky_effect"], "cuda:0")
+        sh.wh_steps(steps, dt, w["G"], fused=fused)
+        torch.cuda.synchronize()
+        out.append(np.array(sh.posvel()))
+    assert np.array_equal(out[0], out[1])
+    if oracle.have_ref():
+        ref = _trajectory(w, oracle.ref_lib(), steps, "wisdom_holman_merged", dt, 1, ["yarkovsky_effect"])
+        _assert_trajectories_agree(out[0], ref)
+
+
 def test_full_size_resident_wisdom_holman_against_the_host_harness_on_a_subsample(built):
     """BASELINE config 2 at its full size, "radiation_forces under WHFast": 50 resident Wisdom-Holman steps of 10^7
     grains (fused kick + Kepler drift sweeps), and -- test particles being independent -- the host harness stepping
