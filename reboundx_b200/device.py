@@ -197,7 +197,8 @@ class Shard:
 
     def sync_bodies(self, group=None, src=0):
         """Active-body state broadcast (NCCL over NVLink when a process group is up)."""
-        sharding.broadcast_bodies(self.bodies, src=src, group=group)
+        if not self.standalone:
+            sharding.broadcast_bodies(self.bodies, src=src, group=group)
 
     def launch(self, stream=None):
         """One force evaluation of the shard: a += sum of the stacked effects (asynchronous)."""
@@ -210,7 +211,8 @@ class Shard:
         return n.value
 
     def reduce_backreaction(self, group=None):
-        sharding.allreduce_backreaction(self.backreaction, group=group)
+        if not self.standalone:
+            sharding.allreduce_backreaction(self.backreaction, group=group)
 
     def apply_backreaction(self, stream=None):
         s = self.torch.cuda.current_stream(self.device) if stream is None else stream

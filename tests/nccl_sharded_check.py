@@ -63,15 +63,20 @@ def main(out_path):
                            "body_max_normwise": float(body["max_normwise"])})
         dist.barrier()
     # sharded fused drift-kick-drift steps (rebx_b200_leapfrog_sweep / all-reduce / _body) vs one shard
-    for name, add_order, n, nsteps in [("debris_disk", ["radiation_forces"], 200_001, 20),
-                                       ("circumplanetary_ring_massive", ["gravitational_harmonics", "gr_potential"], 100_001, 20)]:
+    for name, add_order, n, nsteps, scheme in [("debris_disk", ["radiation_forces"], 200_001, 20, "leapfrog"),
+                                               ("circumplanetary_ring_massive", ["gravitational_harmonics", "gr_potential"], 100_001, 20, "leapfrog"),
+                                               ("debris_disk", ["radiation_forces"], 200_001, 20, "whfast"),
+                                               ("circumplanetary_ring_massive", ["gravitational_harmonics", "gr_potential"], 100_001, 20, "whfast")]:
         w = workloads.circumplanetary_ring(n, massive=True) if name.endswith("_massive") else getattr(workloads, name)(n)
         ntot = w["x"].shape[0]
         dt = 1e-3*2*np.pi*np.sqrt(float(np.hypot(w["x"][1], w["y"][1]))**3/(w["G"]*w["m"][0]))
         lo, hi = sharding.shard_range(ntot, world, rank)
         sh = device.Shard(w, add_order[::-1], dev, lo=lo, hi=hi)
-        for _ in range(nsteps):
-            sh.fused_leapfrog_step(dt, w["G"])
+        if scheme == "leapfrog":
+            for _ in range(nsteps):
+                sh.fused_leapfrog_step(dt, w["G"])
+        else:
+            sh.wh_steps(nsteps, dt, w["G"])
         torch.cuda.synchronize()
         mine = torch.stack([sh.state[k] for k in ("x", "y", "z", "vx", "vy", "vz")])
         per = sharding.shard_range(ntot, world, 0)[1]
@@ -83,12 +88,15 @@ def main(out_path):
             sizes = [sharding.shard_range(ntot, world, r)[1] - sharding.shard_range(ntot, world, r)[0] for r in range(world)]
             got = [np.concatenate([parts[r][k, :sizes[r]].cpu().numpy() for r in range(world)]) for k in range(6)]
             one = device.Shard(w, add_order[::-1], dev, standalone=True)
-            for _ in range(nsteps):
-                one.fused_leapfrog_step(dt, w["G"])
+            if scheme == "leapfrog":
+                for _ in range(nsteps):
+                    one.fused_leapfrog_step(dt, w["G"])
+            else:
+                one.wh_steps(nsteps, dt, w["G"])
             torch.cuda.synchronize()
             want = one.posvel()
             ep, ev = errors(got[:3], want[:3]), errors(got[3:], want[3:])
-            report.append({"case": name + "_fused_leapfrog", "coordinates": "PARTICLE", "n": ntot, "world": world, "steps": nsteps,
+            report.append({"case": name + ("_fused_leapfrog" if scheme == "leapfrog" else "_wisdom_holman"), "coordinates": "PARTICLE", "n": ntot, "world": world, "steps": nsteps,
                            "expect": "bits" if name == "debris_disk" else "traj",
                            "bit_identical": bool(ep["bit_identical"] and ev["bit_identical"]),
                            "max_normwise": float(max(ep["max_normwise"], ev["max_normwise"])), "body_max_normwise": 0.0})

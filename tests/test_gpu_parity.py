@@ -341,7 +341,7 @@ def test_nccl_sharded_evaluation(built, tmp_path):
     subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2", "--master-addr", "127.0.0.1",
                     "--master-port", str(port), os.path.join(here, "nccl_sharded_check.py"), str(out)], check=True, timeout=600)
     report = json.loads(out.read_text())
-    assert len(report) == 7
+    assert len(report) == 9
     for r in report:
         if r["expect"] == "bits":           # no cross-shard arithmetic per particle: identical bits
             assert r["bit_identical"], r
