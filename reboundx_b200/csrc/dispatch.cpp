@@ -708,7 +708,8 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
 
     bodies_h = static_cast<double*>(ctx->bodies_h.p);
     for (size_t e = 0; e < ne; e++) fill_body(bodies_h + e*REBX_B200_BODY_DOUBLES, entries[e], particles);
-    REBXB_CUDA(cudaMemcpyAsync(ctx->bodies.p, bodies_h, ne*REBX_B200_BODY_DOUBLES*sizeof(double), cudaMemcpyHostToDevice, ctx->stream[0]), "copying body records");
+    // zero-copy path: the sweeps read the few body records straight from the pinned host buffer (one copy less)
+    if (!zc) REBXB_CUDA(cudaMemcpyAsync(ctx->bodies.p, bodies_h, ne*REBX_B200_BODY_DOUBLES*sizeof(double), cudaMemcpyHostToDevice, ctx->stream[0]), "copying body records");
     if (any_reduces) REBXB_CUDA(cudaMemsetAsync(ctx->br.p, 0, nchunks*ne*3*sizeof(double), ctx->stream[0]), "clearing back-reaction sums");
     if (nchunks > 1) {      // the other pipeline streams must see the body records
         REBXB_CUDA(cudaEventRecord(ctx->bodies_ready, ctx->stream[0]), "recording event");
@@ -777,7 +778,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 const Entry& en = entries[e0 + j];
                 rebx_b200_effect& fx = P.fx[j];
                 fx.kind = en.kind; fx.flags = en.flags;
-                fx.body = static_cast<const double*>(ctx->bodies.p) + (e0 + j)*REBX_B200_BODY_DOUBLES;
+                fx.body = (zc ? bodies_h : static_cast<const double*>(ctx->bodies.p)) + (e0 + j)*REBX_B200_BODY_DOUBLES;
                 for (int k = 0; k < REBX_B200_MAX_SCALARS; k++) fx.scal[k] = en.scal[k];
                 if (en.T) {
                     for (int k = 0; k < REBX_B200_MAX_TABLES; k++) fx.tab[k] = en.T->d[k].p ? static_cast<const double*>(en.T->d[k].p) + c0 : nullptr;
