@@ -137,11 +137,23 @@ def _pomega(self):
 
 def _sim_new(cls, *args, **kwargs):
     _shim.reb_simulation_create.restype = c_void_p
-    return cls.from_address(_shim.reb_simulation_create())
+    sim = cls.from_address(_shim.reb_simulation_create())
+    sim._owner = True               # views made by ctypes (`pointer.contents`) do not own the C simulation
+    return sim
+
+
+def _sim_del(self):
+    """Like rebound.Simulation.__del__: frees the C simulation, which tells an attached REBOUNDx instance through
+    sim->extras_cleanup that its simulation is gone."""
+    if getattr(self, "_owner", False):
+        self._owner = False
+        _shim.reb_simulation_free.argtypes = [c_void_p]
+        _shim.reb_simulation_free(c_void_p(ctypes.addressof(self)))
 
 
 Simulation.__new__ = staticmethod(lambda cls, *a, **k: _sim_new(cls))
 Simulation.__init__ = lambda self, *a, **k: None
+Simulation.__del__ = _sim_del
 Simulation.integrate = _integrate
 Particle.pomega = property(_pomega)
 Simulation.add = _add

@@ -137,3 +137,48 @@ def test_the_references_own_force_tests_pass_unmodified(reboundx):
     problems = [(str(t), tb) for t, tb in result.errors + result.failures]
     assert not problems, problems[0]
     assert result.testsRun == 12
+
+
+def test_the_references_own_parameter_tests_pass_unmodified(reboundx):
+    """reference reboundx/tests/test_params.py, class TestParams (23 tests of the parameter API through
+    reboundx.params.Params: add / update / copy semantics of doubles and ints, force-valued and custom-struct
+    parameters, unregistered names, re-registration, len / iter / del), imported in place and run UNMODIFIED against
+    this library.  Its setUp also loads an OPERATOR as a third parameter holder; operators are out of this library's
+    scope, so for this test `Extras.load_operator` hands back a force object of that name instead -- the same
+    `.params` interface over the same list API, which is what the tests exercise."""
+    import importlib.util
+    import unittest
+    path = os.path.join(REF, "reboundx", "tests", "test_params.py")
+    spec = importlib.util.spec_from_file_location("reference_test_params", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    saved = reboundx.Extras.load_operator
+    reboundx.Extras.load_operator = lambda self, name: self.create_force(name)
+    try:
+        suite = unittest.TestLoader().loadTestsFromTestCase(mod.TestParams)
+        n = suite.countTestCases()
+        result = unittest.TestResult()
+        suite.run(result)
+    finally:
+        reboundx.Extras.load_operator = saved
+    problems = [(str(t), tb) for t, tb in result.errors + result.failures]
+    assert not problems, (len(problems), problems[0])
+    assert n == 23 and result.testsRun == 23
+
+
+def test_the_references_lifetime_tests_that_need_no_force_evaluation(reboundx):
+    """reference reboundx/tests/test_segfaults.py: test_dropsim (the Simulation is garbage collected while the Extras
+    object lives: the next call must raise AttributeError, not crash -- rebx_extras_cleanup) and
+    test_rebx_not_attached, unmodified.  (The other three integrate with `gr`, i.e. need the GPU.)"""
+    import importlib.util
+    import unittest
+    path = os.path.join(REF, "reboundx", "tests", "test_segfaults.py")
+    spec = importlib.util.spec_from_file_location("reference_test_segfaults", path)
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    suite = unittest.TestSuite([mod.TestSegFaults("test_dropsim"), mod.TestSegFaults("test_rebx_not_attached")])
+    result = unittest.TestResult()
+    suite.run(result)
+    problems = [(str(t), tb) for t, tb in result.errors + result.failures]
+    assert not problems, problems[0]
+    assert result.testsRun == 2
