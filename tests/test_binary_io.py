@@ -313,3 +313,22 @@ def test_threaded_loading_of_a_large_file(built, tmp_path):
     absent = np.ones(n, dtype=bool); absent[have] = False
     assert np.all(np.isnan(table[absent]))                                # REBX_B200_ABSENT_BITS is a NaN payload
     rebx2.detach(); sim2.free(); rebx.detach(); sim.free()
+
+
+def test_golden_file_written_by_the_reference(built, tmp_path):
+    """tests/golden/state_reference_writer.rebx was produced by the reference's src/output.c (make_rebx_golden.py):
+    this library's loader rebuilds the state from it, and its writer turns that state back into the same tree --
+    on any machine, reference tree or not."""
+    from reboundx_b200.host import Extras
+    golden = os.path.join(ROOT, "tests", "golden", "state_reference_writer.rebx")
+    sim, rebx, pos = build_state()                      # what the reference writer was given
+    sim2 = fresh_sim(pos)
+    rebx2 = Extras(sim2, golden)
+    assert_same_state(rebx, rebx2, pos.shape[1])
+    again = tmp_path / "again.rebx"
+    rebx2.save(again)
+    h1, t1 = tree(golden)
+    h2, t2 = tree(str(again))
+    assert t1 == t2
+    assert h1[:36] == h2[:36] == b"REBOUNDx Binary File. Version: 5.1.0"
+    rebx.detach(); sim.free()
