@@ -173,16 +173,34 @@ __host__ __device__ constexpr int min_blocks() {
     return light ? 4*(256/kThreads) : REBXB_HEAVY_MINBLOCKS;
 }
 
+// CTA geometry of the plain sweep per stack.  Occupancy moves in coarse steps with 256-thread CTAs (2 CTAs = 16
+// warps at 128 registers, 3 CTAs need <= 85); 128-thread CTAs add the step in between: 5 CTAs = 20 warps at 96
+// registers.  Measured on all four configurations (profiles/r01_variant_sweep.txt): only the J2/J4 (+) gr_potential
+// pair fits 96 registers without further spills and gains (0.2385 -> 0.2278 ms); the others stay at 256 x 2 / 256 x 4.
+#ifndef REBXB_RING_128
+#define REBXB_RING_128 1
+#endif
+template <int K0, int K1, int K2, int K3>
+__host__ __device__ constexpr bool narrow_cta() {
+    return REBXB_RING_128 && kThreads == 256 && K2 == 0 && K3 == 0 &&
+           ((K0 == REBX_B200_HARMONICS && K1 == REBX_B200_GR_POTENTIAL) || (K0 == REBX_B200_GR_POTENTIAL && K1 == REBX_B200_HARMONICS));
+}
+template <int K0, int K1, int K2, int K3>
+__host__ __device__ constexpr int pass_threads() { return narrow_cta<K0, K1, K2, K3>() ? 128 : kThreads; }
+template <int K0, int K1, int K2, int K3>
+__host__ __device__ constexpr int pass_blocks() { return narrow_cta<K0, K1, K2, K3>() ? 5 : min_blocks<K0, K1, K2, K3>(); }
+
 template <int V, bool SHARED, int K0, int K1, int K2, int K3>
-__global__ void __launch_bounds__(kThreads, min_blocks<K0, K1, K2, K3>())
+__global__ void __launch_bounds__(pass_threads<K0, K1, K2, K3>(), pass_blocks<K0, K1, K2, K3>())
 pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ partials) {
     constexpr bool VEL  = Traits<K0>::vel  || Traits<K1>::vel  || Traits<K2>::vel  || Traits<K3>::vel;
     constexpr bool MASS = Traits<K0>::mass || Traits<K1>::mass || Traits<K2>::mass || Traits<K3>::mass;
     constexpr bool RAD  = Traits<K0>::rad  || Traits<K1>::rad  || Traits<K2>::rad  || Traits<K3>::rad;
+    constexpr int T = pass_threads<K0, K1, K2, K3>(), W = T/32;      // threads / warps per CTA of this stack
 
     __shared__ double s_body[REBX_B200_MAX_EFFECTS][REBX_B200_BODY_DOUBLES];
-    __shared__ double s_red[kWarps][3];
-    for (int idx = threadIdx.x; idx < P.n_effects*REBX_B200_BODY_DOUBLES; idx += kThreads) {
+    __shared__ double s_red[W][3];
+    for (int idx = threadIdx.x; idx < P.n_effects*REBX_B200_BODY_DOUBLES; idx += T) {
         const int e = idx/REBX_B200_BODY_DOUBLES, j = idx - e*REBX_B200_BODY_DOUBLES;
         s_body[e][j] = P.fx[e].body[j];
     }
@@ -207,8 +225,8 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
 
     const int64_t n = P.st.n;
     const int64_t ntiles = (n + V - 1)/V;
-    const int64_t stride = (int64_t)gridDim.x*kThreads;
-    for (int64_t t = (int64_t)blockIdx.x*kThreads + threadIdx.x; t < ntiles; t += stride) {
+    const int64_t stride = (int64_t)gridDim.x*T;
+    for (int64_t t = (int64_t)blockIdx.x*T + threadIdx.x; t < ntiles; t += stride) {
         const int64_t k = t*V;
         const bool full = (k + V <= n);
         double x[V], y[V], z[V], vx[V], vy[V], vz[V], m[V], r[V], ax[V], ay[V], az[V];
@@ -305,10 +323,10 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
         }
         st<V>(P.st.ax, k, full, ax); st<V>(P.st.ay, k, full, ay); st<V>(P.st.az, k, full, az);
     }
-    reduce_effect<K0>(red0, 0, s_red, partials);
-    reduce_effect<K1>(red1, 1, s_red, partials);
-    reduce_effect<K2>(red2, 2, s_red, partials);
-    reduce_effect<K3>(red3, 3, s_red, partials);
+    reduce_effect<K0, W>(red0, 0, s_red, partials);
+    reduce_effect<K1, W>(red1, 1, s_red, partials);
+    reduce_effect<K2, W>(red2, 2, s_red, partials);
+    reduce_effect<K3, W>(red3, 3, s_red, partials);
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -888,14 +906,15 @@ namespace rebxb {
 // ---- launch plumbing ----------------------------------------------------------------------
 typedef void (*pass_fn)(const rebx_b200_pass, double*);
 typedef void (*step_fn)(const rebx_b200_pass, double*, const StepArgs);
-struct Combo { int k[4]; pass_fn fn[2][2]; bool red[4]; pass_fn tma; int tma_smem; step_fn step[2][2]; };   // [shared body][V-1]
+struct Combo { int k[4]; pass_fn fn[2][2]; bool red[4]; pass_fn tma; int tma_smem; step_fn step[2][2]; int threads; };   // [shared body][V-1]
 
 #define REBXB_COMBO(a, b, c, d) { {a, b, c, d}, { { pass_kernel<1, false, a, b, c, d>, pass_kernel<2, false, a, b, c, d> }, \
                                                    { pass_kernel<1, (b) != 0, a, b, c, d>, pass_kernel<2, (b) != 0, a, b, c, d> } }, \
                                   { Traits<a>::red, Traits<b>::red, Traits<c>::red, Traits<d>::red }, \
                                   pass_kernel_tma<a, b, c, d>, TmaCfg<a, b, c, d>::smem_bytes, \
                                   { { step_kernel<1, false, a, b, c, d>, step_kernel<2, false, a, b, c, d> }, \
-                                    { step_kernel<1, (b) != 0, a, b, c, d>, step_kernel<2, (b) != 0, a, b, c, d> } } },
+                                    { step_kernel<1, (b) != 0, a, b, c, d>, step_kernel<2, (b) != 0, a, b, c, d> } }, \
+                                  pass_threads<a, b, c, d>() },
 static Combo kCombos[] = {
     // every effect alone (any other stack falls back to consecutive single sweeps, still in list order)
     REBXB_COMBO(1,0,0,0) REBXB_COMBO(2,0,0,0) REBXB_COMBO(3,0,0,0) REBXB_COMBO(4,0,0,0)
@@ -1076,8 +1095,8 @@ int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* str
             const int V = vsel ? 2 : 1;
             pass_fn fn = combo->fn[(pass->reserved & REBX_B200_PASS_SHARED_BODY) ? 1 : 0][vsel];
             const int64_t tiles = (sub.st.n + V - 1)/V;
-            grid = grid_for(reinterpret_cast<const void*>(fn), tiles);
-            fn<<<grid, kThreads, 0, s>>>(sub, static_cast<double*>(workspace));
+            grid = grid_for(reinterpret_cast<const void*>(fn), tiles, combo->threads, 0, combo->threads);
+            fn<<<grid, combo->threads, 0, s>>>(sub, static_cast<double*>(workspace));
         }
         err = cudaGetLastError();
         if (err != cudaSuccess) return err;
