@@ -10,7 +10,11 @@
 
 namespace rebxb {
 
-__global__ void __launch_bounds__(kThreads)
+#ifndef REBXB_KEPLER_MINBLOCKS
+#define REBXB_KEPLER_MINBLOCKS 1        // resident CTAs per SM asked of the register allocator for the Kepler kernels
+#endif
+
+__global__ void __launch_bounds__(kThreads, REBXB_KEPLER_MINBLOCKS)
 kepler_drift_kernel(rebx_b200_state st, const double* __restrict__ body, double G, double dt) {
     const long long bi = (long long)body[REBX_B200_BODY_INDEX];
     const double bx = body[REBX_B200_BODY_X+0], by = body[REBX_B200_BODY_X+1], bz = body[REBX_B200_BODY_X+2];
@@ -42,7 +46,7 @@ kepler_drift_kernel(rebx_b200_state st, const double* __restrict__ body, double 
 // velocity through the kick, so every CTA can advance its own copy of the body record; the caller refreshes
 // the record afterwards (rebx_b200_gather_bodies).
 template <int K>
-__global__ void __launch_bounds__(kThreads)
+__global__ void __launch_bounds__(kThreads, REBXB_KEPLER_MINBLOCKS)
 wh_kick_drift_kernel(const __grid_constant__ rebx_b200_pass P, double G, double dt_kick, double dt_drift) {
     static_assert(!Traits<K>::red, "the fused kick+drift needs an effect without back-reaction");
     __shared__ double s_body[REBX_B200_BODY_DOUBLES];
