@@ -297,7 +297,11 @@ def run_ours(args):
     prof = os.path.join(ROOT, "profiles", "traffic.json")
     if os.path.exists(prof) and n == n_default and not com:       # ncu dram__bytes_read+write per launch, captured at the config's size
         with open(prof) as f:
-            roofline["traffic"] = json.load(f).get(args.workload)
+            captured = json.load(f)
+        roofline["traffic"] = captured.get(args.workload)
+        # the secondary bound of the FLOP-heavy sweeps: how busy ncu saw the FP64 pipe in that capture (its peak,
+        # measured with tools/fp64_probe.cu: 36.5 TFLOP/s of DFMA)
+        roofline["fp64_pipe_busy_pct"] = captured.get("_fp64_pipe_busy_pct", {}).get(args.workload)
 
     # ---- resident stepping leg: full drift-kick-drift steps, no PCIe --------------
     resident = None
