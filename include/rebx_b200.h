@@ -141,11 +141,23 @@ int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* str
 int rebx_b200_apply_backreaction(const rebx_b200_pass* pass, void* stream, int* launches);
 
 /* ---- centre-of-mass reference frames of rebx_com_force (reference src/rebxtools.c:66-147) ------
- * scratch: device memory of rebx_b200_scan_scratch_bytes(n), reusable between calls. */
+ * scratch: device memory of rebx_b200_scan_scratch_bytes(n), reusable between calls.
+ *
+ * Interior / total MASS (com.m of rebx_com_force) carries the reference's own sequential rounding, exactly:
+ * the masses are scanned on the grid u = ulp of the leading body's mass, on which the reference's forward
+ * fold (reb_simulation_com) and backward peel (rebx_get_com_without_particle, src/rebxtools.c:6-30) are
+ * exact integer arithmetic (kernels_jacobi.cuh has the argument).  `lead_mass`: device pointer to the mass
+ * of GLOBAL particle 0, or NULL for a state that starts at global index 0.  totals8[7] reports whether the
+ * argument held for this shard (0) or not (1: running sum left the binade of the leading mass, an exact
+ * tie, a negative mass, no positive leading mass).  With REBX_B200_COM_WHOLE in `flags` (the state is the
+ * WHOLE ensemble) a launch with status 1 redoes the two recurrences literally -- one thread, O(n)
+ * dependent additions -- so the masses are the reference's bits in every case; a sharded launch keeps the
+ * grid sums (as accurate as the reference's own, no longer bit-identical to them). */
+#define REBX_B200_COM_WHOLE 1
 size_t rebx_b200_scan_scratch_bytes(int64_t n);
-/* totals7 (device) = { sum m, sum m x, sum m y, sum m z, sum m vx, sum m vy, sum m vz } of the shard.
- * A sharded caller all-reduces totals7 before the next call. */
-int rebx_b200_mass_moments(const rebx_b200_state* st, double* totals7, void* scratch, void* stream, int* launches);
+/* totals8 (device) = { sum m (on the grid), sum m x, sum m y, sum m z, sum m vx, sum m vy, sum m vz, status } of
+ * the shard.  A sharded caller all-reduces totals8 before the next call. */
+int rebx_b200_mass_moments(const rebx_b200_state* st, double* totals8, void* scratch, const double* lead_mass, int flags, void* stream, int* launches);
 /* Writes `nbodies` consecutive body records (device) describing the barycentre (index -1). */
 int rebx_b200_com_bodies(const double* totals7, double* bodies, int nbodies, void* stream, int* launches);
 /* REBX_COORDINATES_JACOBI for 1..3 stacked damping effects (kinds 5,6,7) over the WHOLE ensemble
@@ -154,17 +166,18 @@ int rebx_b200_com_bodies(const double* totals7, double* bodies, int nbodies, voi
 int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* stream, int* launches);
 /* The same pipeline in three stages, for an ensemble SHARDED by index range:
  * the shards exchange 7 + 3 doubles between the stages, everything else stays local.
- *   1. jacobi_moments: totals7 (device, may be NULL) = this shard's {sum m, sum m r, sum m v};
+ *   1. jacobi_moments: totals8 (device, may be NULL) = this shard's {sum m, sum m r, sum m v, status};
  *      the in-shard prefix stays in `scratch`.
- *      -> exchange: carry7 of a shard = sum of totals7 over the shards in FRONT of it (lower indices).
+ *      -> exchange: carry7 of a shard = sum of totals over the shards in FRONT of it (lower indices).
  *   2. jacobi_sweep: a += f against COM_i = (carry7 + in-shard prefix)/mass; tsum3 (device, may be NULL)
  *      = this shard's sum of t_i = m_i/(M_i+m_i) sum_e f_i^e.  carry7 NULL = the first shard.
  *      cudaErrorNotSupported for a stack without a fused instantiation (call per effect then).
  *      -> exchange: carry3 of a shard = sum of tsum3 over the shards BEHIND it (higher indices).
  *   3. jacobi_apply: a_j -= carry3 + sum_{i >= j in shard} t_i.  carry3 NULL = the last shard.
- * `scratch` (rebx_b200_scan_scratch_bytes(st.n)) must be the same untouched buffer through 1-3. */
-int rebx_b200_jacobi_moments(const rebx_b200_state* st, void* scratch, double* totals7, void* stream, int* launches);
-int rebx_b200_jacobi_sweep(const rebx_b200_pass* pass, void* scratch, const double* carry7, double* tsum3, void* stream, int* launches);
+ * `scratch` (rebx_b200_scan_scratch_bytes(st.n)) must be the same untouched buffer through 1-3; `flags` the
+ * same in 1 and 2. */
+int rebx_b200_jacobi_moments(const rebx_b200_state* st, void* scratch, double* totals8, const double* lead_mass, int flags, void* stream, int* launches);
+int rebx_b200_jacobi_sweep(const rebx_b200_pass* pass, void* scratch, const double* carry7, double* tsum3, int flags, void* stream, int* launches);
 int rebx_b200_jacobi_apply(const rebx_b200_state* st, void* scratch, const double* carry3, void* stream, int* launches);
 
 /* ---- 1PN `gr` effect (reference src/gr.c:65-164) for N_active <= REBX_B200_GR_MAX_ACTIVE ---------

@@ -104,8 +104,11 @@ def _full(w, name, n):
     return full, mask
 
 
-def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE", n_active=-1):
+def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE", n_active=-1, com="quadratic"):
     """Runs the C restatement on workload `w`; `exec_order` is the EXECUTION order of forces.
+    com: "quadratic" = rebx_com_force's loops as the reference has them (O(n^2) in the centre-of-mass
+    frames); "linear" = oracle_com_force_linear (the reference's COM recurrence, back-reaction summed in
+    long double, O(n)); "linear_exact" = the same with exact prefix sums for COM_i (diagnostics only).
     Returns ((ax, ay, az), {force: [sum_x, sum_y, sum_z, abs_x, abs_y, abs_z]}): the back-reaction
     terms onto the body summed in long double, and the sum of their absolute values."""
     lib = _port()
@@ -188,12 +191,18 @@ def port_apply(w, exec_order, acc0=None, coordinates="PARTICLE", n_active=-1):
             dp.tIm_sd0 = w.get("tIm_surface_density_1") or 0.0
             dp.tIm_s = w.get("tIm_surface_density_exponent") or 0.0
             dp.tIm_dedge, dp.tIm_hedge = w.get("ide_position") or 0.0, w.get("ide_width") or 0.0
-            lib.oracle_com_force.restype = c_int
-            rc = lib.oracle_com_force(c_int(KIND[name]), c_int(COORD[coordinates]), c_int64(0), ctypes.byref(dp), c_double(w["G"]),
-                                      c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]), _d(S["m"]),
-                                      _d(acc[0]), _d(acc[1]), _d(acc[2]), out)
+            if com == "quadratic":
+                lib.oracle_com_force.restype = c_int
+                rc = lib.oracle_com_force(c_int(KIND[name]), c_int(COORD[coordinates]), c_int64(0), ctypes.byref(dp), c_double(w["G"]),
+                                          c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]), _d(S["m"]),
+                                          _d(acc[0]), _d(acc[1]), _d(acc[2]), out)
+                br[name] = np.array([float(v) for v in out])
+            else:
+                lib.oracle_com_force_linear.restype = c_int
+                rc = lib.oracle_com_force_linear(c_int(KIND[name]), c_int(COORD[coordinates]), c_int64(0), ctypes.byref(dp), c_double(w["G"]),
+                                                 c_int64(n), _d(S["x"]), _d(S["y"]), _d(S["z"]), _d(S["vx"]), _d(S["vy"]), _d(S["vz"]), _d(S["m"]),
+                                                 _d(acc[0]), _d(acc[1]), _d(acc[2]), c_int(1 if com == "linear_exact" else 0))
             assert rc == 0
-            br[name] = np.array([float(v) for v in out])
         else:
             raise ValueError(name)
     return acc, br

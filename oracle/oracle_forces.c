@@ -469,6 +469,76 @@ int oracle_com_force(int kind, int coordinates, int64_t primary, const oracle_da
     return 0;
 }
 
+/* O(n) restatement of the same function for ensembles the reference's O(n^2) loops cannot reach
+ * (JACOBI at n = 4*10^4 already takes 4 s per force there; ~40 min at 10^6).
+ *   - The reference frame of particle i is the SAME double-precision recurrence as above (forward fold of
+ *     reb_simulation_com, then the backward peel of rebx_get_com_without_particle, rebxtools.c:6-30,92-99):
+ *     it is O(n) in the reference too, so COM_i is bit-identical to the reference's.
+ *   - Only the back-reaction is restated: the reference subtracts massratio*f_i from every j <= i (JACOBI) or
+ *     from every j (BARYCENTRIC) one i at a time, i.e. n sequential roundings per particle; here the terms
+ *     are accumulated in long double (suffix sums / one total) and applied once.  The two differ by the
+ *     reference's own accumulated rounding, <= sqrt(n)*eps relative to |a_j| (1.6e-14 at n = 2*10^4):
+ *     tests/test_oracle.py pins that against the O(n^2) function and against oracle/_ref.
+ * com_mode 1 replaces the reference's COM recurrence by exact (long double) prefix sums -- used only to
+ * measure how much of a disagreement stems from the reference's own rounding in COM_i. */
+int oracle_com_force_linear(int kind, int coordinates, int64_t primary, const oracle_damping_params* P, double G,
+                            int64_t n, const double* x, const double* y, const double* z,
+                            const double* vx, const double* vy, const double* vz, const double* m,
+                            double* ax, double* ay, double* az, int com_mode) {
+    if (coordinates == ORACLE_PARTICLE)
+        return oracle_com_force(kind, coordinates, primary, P, G, n, x, y, z, vx, vy, vz, m, ax, ay, az, NULL);
+    body_t com = com_all(n, x, y, z, vx, vy, vz, m);
+    long double Sm = 0, S[6] = {0, 0, 0, 0, 0, 0};
+    if (com_mode == 1) {
+        for (int64_t i = 0; i < n; i++) {
+            Sm += m[i];
+            S[0] += (long double)x[i]*m[i]; S[1] += (long double)y[i]*m[i]; S[2] += (long double)z[i]*m[i];
+            S[3] += (long double)vx[i]*m[i]; S[4] += (long double)vy[i]*m[i]; S[5] += (long double)vz[i]*m[i];
+        }
+        if (coordinates == ORACLE_BARYCENTRIC) {
+            com.m = (double)Sm;
+            com.x = (double)(S[0]/Sm); com.y = (double)(S[1]/Sm); com.z = (double)(S[2]/Sm);
+            com.vx = (double)(S[3]/Sm); com.vy = (double)(S[4]/Sm); com.vz = (double)(S[5]/Sm);
+        }
+    }
+    long double tx = 0, ty = 0, tz = 0;      /* running sum of massratio*f over the particles already visited */
+    if (coordinates == ORACLE_BARYCENTRIC) {
+        for (int64_t i = n - 1; i >= 0; i--) {
+            double f[3];
+            damping_calc(kind, P, G, i, x[i], y[i], z[i], vx[i], vy[i], vz[i], m[i], &com, f);
+            const double massratio = m[i]/com.m;
+            tx += (long double)(massratio*f[0]); ty += (long double)(massratio*f[1]); tz += (long double)(massratio*f[2]);
+            ax[i] += f[0]; ay[i] += f[1]; az[i] += f[2];
+        }
+        for (int64_t j = 0; j < n; j++) {
+            ax[j] = (double)((long double)ax[j] - tx); ay[j] = (double)((long double)ay[j] - ty); az[j] = (double)((long double)az[j] - tz);
+        }
+        return 0;
+    }
+    for (int64_t i = n - 1; i >= 1; i--) {
+        if (com_mode == 1) {
+            Sm -= m[i];
+            S[0] -= (long double)x[i]*m[i]; S[1] -= (long double)y[i]*m[i]; S[2] -= (long double)z[i]*m[i];
+            S[3] -= (long double)vx[i]*m[i]; S[4] -= (long double)vy[i]*m[i]; S[5] -= (long double)vz[i]*m[i];
+            com.m = (double)Sm;
+            com.x = (double)(S[0]/Sm); com.y = (double)(S[1]/Sm); com.z = (double)(S[2]/Sm);
+            com.vx = (double)(S[3]/Sm); com.vy = (double)(S[4]/Sm); com.vz = (double)(S[5]/Sm);
+        } else {
+            com.x = com.x*com.m - x[i]*m[i]; com.y = com.y*com.m - y[i]*m[i]; com.z = com.z*com.m - z[i]*m[i];
+            com.vx = com.vx*com.m - vx[i]*m[i]; com.vy = com.vy*com.m - vy[i]*m[i]; com.vz = com.vz*com.m - vz[i]*m[i];
+            com.m -= m[i];
+            if (com.m > 0.) { com.x /= com.m; com.y /= com.m; com.z /= com.m; com.vx /= com.m; com.vy /= com.m; com.vz /= com.m; }
+        }
+        double f[3];
+        damping_calc(kind, P, G, i, x[i], y[i], z[i], vx[i], vy[i], vz[i], m[i], &com, f);
+        const double massratio = m[i]/(com.m + m[i]);
+        tx += (long double)(massratio*f[0]); ty += (long double)(massratio*f[1]); tz += (long double)(massratio*f[2]);
+        ax[i] = (double)((long double)ax[i] + f[0] - tx); ay[i] = (double)((long double)ay[i] + f[1] - ty); az[i] = (double)((long double)az[i] + f[2] - tz);
+    }
+    ax[0] = (double)((long double)ax[0] - tx); ay[0] = (double)((long double)ay[0] - ty); az[0] = (double)((long double)az[0] - tz);
+    return 0;
+}
+
 /* ---- gr (reference src/gr.c:65-181) ----------------------------------------------------------
  * n_active < 0 means "unset" (all particles active).  The Jacobi transforms restate REBOUND's
  * reb_transformations_inertial_to_jacobi_posvelacc / _jacobi_to_inertial_acc (third-party, same

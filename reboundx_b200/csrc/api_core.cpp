@@ -204,7 +204,10 @@ void rebx_free_ap(struct rebx_node** ap) {
 
 // Installed as sim->free_particle_ap (REBOUND calls it when a particle is removed or freed).
 void rebx_free_particle_ap(struct reb_particle* p) {
-    if (p->ap) mark_all_dirty();
+    // Unconditionally: REBOUND calls this whenever a particle is removed and then shifts or swaps the particles
+    // behind it, which moves every per-index table entry and cached body index even if the removed particle
+    // itself carried no parameters.
+    mark_all_dirty();
     rebx_free_ap(reinterpret_cast<struct rebx_node**>(&p->ap));
 }
 

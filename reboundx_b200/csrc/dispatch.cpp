@@ -790,7 +790,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 REBXB_CUDA((cudaError_t)rebx_b200_launch_jacobi(&P, ctx->scan.p, s, &launches), "launching the Jacobi-frame sweep");
             } else {
                 if (frame == 1) {   // barycentre record computed on the device from the resident state
-                    REBXB_CUDA((cudaError_t)rebx_b200_mass_moments(&st, static_cast<double*>(ctx->totals.p), ctx->scan.p, s, &launches), "reducing mass moments");
+                    REBXB_CUDA((cudaError_t)rebx_b200_mass_moments(&st, static_cast<double*>(ctx->totals.p), ctx->scan.p, nullptr, REBX_B200_COM_WHOLE, s, &launches), "reducing mass moments");
                     REBXB_CUDA((cudaError_t)rebx_b200_com_bodies(static_cast<const double*>(ctx->totals.p),
                                                                  static_cast<double*>(ctx->bodies.p) + e0*REBX_B200_BODY_DOUBLES, P.n_effects, s, &launches), "building the barycentre record");
                 }

@@ -1126,22 +1126,53 @@ int rebx_b200_apply_backreaction(const rebx_b200_pass* pass, void* stream, int* 
     return err;
 }
 
+// Scratch layout shared by the centre-of-mass stages (all sized by the shard's own n).
+struct JacobiScratch {
+    double *rows7, *rows3, *totals, *tvec, *mref;
+    MassGrid* grid;
+    unsigned* unsafe;
+    unsigned long long* first;
+    int64_t ntiles;
+    JacobiScratch(void* scratch, int64_t n) {
+        ntiles = (n + kScanThreads - 1)/kScanThreads;
+        rows7 = static_cast<double*>(scratch);
+        rows3 = rows7 + (size_t)(ntiles + 1)*7;
+        totals = rows3 + (size_t)(ntiles + 1)*3;         // [0..7] totals8, [8..10] tsum3, [16..22] MassGrid, [24] unsafe flag, [25] first massive index
+        grid = reinterpret_cast<MassGrid*>(totals + 16);
+        unsafe = reinterpret_cast<unsigned*>(totals + 24);
+        first = reinterpret_cast<unsigned long long*>(totals + 25);
+        tvec = totals + 32;
+        mref = tvec + (size_t)3*(n + 2);
+    }
+};
+static_assert(sizeof(MassGrid) <= 8*sizeof(double), "MassGrid must fit its scratch slot");
+
 size_t rebx_b200_scan_scratch_bytes(int64_t n) {
     const int64_t ntiles = (n + kScanThreads - 1)/kScanThreads + 1;
-    return (size_t)(ntiles*10 + 16 + 3*(n + 2))*sizeof(double);
+    return (size_t)(ntiles*10 + 32 + 4*(n + 2))*sizeof(double);
 }
 
-int rebx_b200_mass_moments(const rebx_b200_state* st, double* totals7, void* scratch, void* stream, int* launches) {
-    if (!st || !totals7 || !scratch || !st->m || !st->vx) return cudaErrorInvalidValue;
-    cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (st->n == 0) return cudaMemsetAsync(totals7, 0, 7*sizeof(double), s);
-    const int64_t ntiles = (st->n + kScanThreads - 1)/kScanThreads;
-    double* rows = static_cast<double*>(scratch);
-    moments_tile_kernel<<<(unsigned)ntiles, kScanThreads, 0, s>>>(*st, rows);
-    scan_tiles_kernel<7, false><<<7, kTileScanThreads, 0, s>>>(rows, ntiles, totals7);
-    cudaError_t err = cudaGetLastError();
-    if (err == cudaSuccess && launches) *launches += 2;
+// Stage 1 of both centre-of-mass frames: quantised mass + moment tile sums, their scan, the status / literal
+// fallback kernel.  `backward`: also provide the interior masses (JACOBI).
+static int com_moments_stage(const rebx_b200_state* st, void* scratch, double* totals8, const double* lead_mass, int flags,
+                             bool backward, cudaStream_t s, int* launches) {
+    JacobiScratch J(scratch, st->n);
+    cudaError_t err = cudaMemsetAsync(J.unsafe, 0, sizeof(double), s);                 // flag = 0
+    if (err == cudaSuccess) err = cudaMemsetAsync(J.first, 0xff, sizeof(unsigned long long), s);   // first massive = none
+    if (err != cudaSuccess) return err;
+    moments_tile_kernel<<<(unsigned)J.ntiles, kScanThreads, 0, s>>>(*st, J.rows7, lead_mass, J.grid, J.unsafe, J.first);
+    scan_tiles_kernel<7, false><<<7, kTileScanThreads, 0, s>>>(J.rows7, J.ntiles, J.totals);
+    mass_status_kernel<<<1, 32, 0, s>>>(*st, J.grid, J.unsafe, J.first, J.totals, (flags & REBX_B200_COM_WHOLE) ? J.mref : nullptr, backward ? 1 : 0, totals8);
+    err = cudaGetLastError();
+    if (err == cudaSuccess && launches) *launches += 3;
     return err;
+}
+
+int rebx_b200_mass_moments(const rebx_b200_state* st, double* totals8, void* scratch, const double* lead_mass, int flags, void* stream, int* launches) {
+    if (!st || !totals8 || !scratch || !st->m || !st->vx) return cudaErrorInvalidValue;
+    cudaStream_t s = static_cast<cudaStream_t>(stream);
+    if (st->n == 0) return cudaMemsetAsync(totals8, 0, 8*sizeof(double), s);
+    return com_moments_stage(st, scratch, totals8, lead_mass, flags, false, s, launches);
 }
 
 int rebx_b200_com_bodies(const double* totals7, double* bodies, int nbodies, void* stream, int* launches) {
@@ -1152,19 +1183,6 @@ int rebx_b200_com_bodies(const double* totals7, double* bodies, int nbodies, voi
     return err;
 }
 
-// Scratch layout shared by the three Jacobi stages (all sized by the shard's own n).
-struct JacobiScratch {
-    double *rows7, *rows3, *totals, *tvec;
-    int64_t ntiles;
-    JacobiScratch(void* scratch, int64_t n) {
-        ntiles = (n + kScanThreads - 1)/kScanThreads;
-        rows7 = static_cast<double*>(scratch);
-        rows3 = rows7 + (size_t)(ntiles + 1)*7;
-        totals = rows3 + (size_t)(ntiles + 1)*3;
-        tvec = totals + 16;
-    }
-};
-
 static const JacobiCombo* find_jacobi_combo(const rebx_b200_pass& P) {
     for (const JacobiCombo& c : kJacobiCombos) {
         bool ok = true;
@@ -1174,19 +1192,14 @@ static const JacobiCombo* find_jacobi_combo(const rebx_b200_pass& P) {
     return nullptr;
 }
 
-int rebx_b200_jacobi_moments(const rebx_b200_state* st, void* scratch, double* totals7, void* stream, int* launches) {
+int rebx_b200_jacobi_moments(const rebx_b200_state* st, void* scratch, double* totals8, const double* lead_mass, int flags, void* stream, int* launches) {
     if (!st || !scratch || !st->x || !st->vx || !st->m) return cudaErrorInvalidValue;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (st->n == 0) return totals7 ? cudaMemsetAsync(totals7, 0, 7*sizeof(double), s) : cudaSuccess;
-    JacobiScratch J(scratch, st->n);
-    moments_tile_kernel<<<(unsigned)J.ntiles, kScanThreads, 0, s>>>(*st, J.rows7);
-    scan_tiles_kernel<7, false><<<7, kTileScanThreads, 0, s>>>(J.rows7, J.ntiles, totals7 ? totals7 : J.totals);
-    cudaError_t err = cudaGetLastError();
-    if (err == cudaSuccess && launches) *launches += 2;
-    return err;
+    if (st->n == 0) return totals8 ? cudaMemsetAsync(totals8, 0, 8*sizeof(double), s) : cudaSuccess;
+    return com_moments_stage(st, scratch, totals8, lead_mass, flags, true, s, launches);
 }
 
-int rebx_b200_jacobi_sweep(const rebx_b200_pass* pass, void* scratch, const double* carry7, double* tsum3, void* stream, int* launches) {
+int rebx_b200_jacobi_sweep(const rebx_b200_pass* pass, void* scratch, const double* carry7, double* tsum3, int flags, void* stream, int* launches) {
     if (!pass || !scratch) return cudaErrorInvalidValue;
     const rebx_b200_pass& P = *pass;
     if (P.n_effects < 1 || P.n_effects > 3) return cudaErrorInvalidValue;
@@ -1196,7 +1209,8 @@ int rebx_b200_jacobi_sweep(const rebx_b200_pass* pass, void* scratch, const doub
     const JacobiCombo* combo = find_jacobi_combo(P);
     if (!combo) return cudaErrorNotSupported;
     JacobiScratch J(scratch, P.st.n);
-    combo->fn<<<(unsigned)J.ntiles, kScanThreads, 0, s>>>(P, J.rows7, J.tvec, J.rows3, carry7);
+    combo->fn<<<(unsigned)J.ntiles, kScanThreads, 0, s>>>(P, J.rows7, J.tvec, J.rows3, carry7, J.grid, J.totals + 7,
+                                                          (flags & REBX_B200_COM_WHOLE) ? J.mref : nullptr);
     scan_tiles_kernel<3, true><<<3, kTileScanThreads, 0, s>>>(J.rows3, J.ntiles, tsum3 ? tsum3 : J.totals + 8);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) *launches += 2;
@@ -1232,8 +1246,8 @@ int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* str
         }
         return 0;
     }
-    int rc = rebx_b200_jacobi_moments(&P.st, scratch, nullptr, stream, launches);
-    if (rc == 0) rc = rebx_b200_jacobi_sweep(&P, scratch, nullptr, nullptr, stream, launches);
+    int rc = rebx_b200_jacobi_moments(&P.st, scratch, nullptr, nullptr, REBX_B200_COM_WHOLE, stream, launches);
+    if (rc == 0) rc = rebx_b200_jacobi_sweep(&P, scratch, nullptr, nullptr, REBX_B200_COM_WHOLE, stream, launches);
     if (rc == 0) rc = rebx_b200_jacobi_apply(&P.st, scratch, nullptr, stream, launches);
     return rc;
 }

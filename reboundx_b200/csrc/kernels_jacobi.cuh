@@ -57,22 +57,150 @@ __device__ __forceinline__ void block_exclusive_scan(double (&v)[NC], double (&t
     }
 }
 
+// ---- the reference's sequentially rounded interior mass, reproduced in parallel -----------------------
+// The reference obtains the mass interior to particle i (com.m in rebx_com_force) from two SEQUENTIAL
+// double-precision recurrences: the forward fold of reb_simulation_com (T_k = fl(T_{k-1} + m_k)) and the
+// backward peel of rebx_get_com_without_particle (B_i = fl(B_{i+1} - m_i), src/rebxtools.c:6-30,92-99).
+// Measured (oracle_com_force_linear, com_mode 1-3): replacing that mass by the EXACT prefix sum changes the
+// damping forces by 2e-12 norm-wise at N = 2e4 (mu = G (m + M_i) enters v^2 - mu/d, a difference of nearly
+// equal numbers on a near-circular orbit), while the position / velocity moments tolerate any summation
+// order (2e-15).  So the mass has to carry the reference's rounding, not a better one.
+// It can, exactly: while the running sum stays inside one binade [2^K, 2^(K+1)) -- a central body at index 0
+// that outweighs everything behind it up to the next power of two -- every T_k is a multiple of
+// u = 2^(K-52), hence fl(T + m) = T + rn_u(m) with rn_u(m) = m rounded to the nearest multiple of u, and
+// likewise fl(B - m) = B - rn_u(m): both recurrences are EXACT integer arithmetic on q_j = rn_u(m_j)/u, so
+// B_i = T_{i-1} = u * sum_{j<i} q_j, and sums of multiples of u below 2^(K+1) are exact in any order.  The
+// scans below therefore run on rn_u(m_j) and reproduce the reference's interior masses bit for bit.
+// One more literal step is needed where the peel reaches the BOTTOM of the binade: for the first particle r >= 1
+// with q_r != 0 the reference computes B_r = fl(T_r - m_r) = fl((m_0 + u q_r) - m_r), which is m_0 unless m_0 is an
+// exact power of two (1.0 solar mass ...): then the difference may round on the finer grid below 2^K (to
+// m_0 - u/2), and the massless particles in front of r inherit that value.  `dip` below is this B_r, evaluated
+// literally; it stands in wherever the prefix equals the leading mass.
+// Not covered by the argument (flagged per launch, see mass_status_kernel): a running sum that leaves the
+// binade, a negative mass, or a tie (m_j/u an exact half-integer: the reference's result then depends on the
+// parity of the running sum).  A single-shard evaluation then recomputes the two recurrences literally, one
+// thread, O(N) dependent additions (mass_sequential path); a sharded one keeps the quantised sums, which are
+// as accurate as the reference's (each within u/2 per term) but no longer bit-identical to them.
+struct MassGrid { double u, inv_u, top, lead, dip; int ok; int pad; };
+
+__device__ __forceinline__ MassGrid make_mass_grid(double m0) {
+    MassGrid g; g.u = 0.0; g.inv_u = 0.0; g.top = 0.0; g.lead = m0; g.dip = m0; g.ok = 0; g.pad = 0;
+    if (!(m0 > 0.0) || isinf(m0)) return g;
+    int e;
+    frexp(m0, &e);                                   // m0 = f 2^e, f in [0.5, 1): binade [2^(e-1), 2^e)
+    if (e - 53 < -1000 || e > 1000) return g;        // keep u, 1/u and the scaled masses far from the exponent limits
+    g.u = ldexp(1.0, e - 53); g.inv_u = ldexp(1.0, 53 - e); g.top = ldexp(1.0, e); g.ok = 1;
+    return g;
+}
+
+// rn_u(m) and whether the reference's rounding of T + m could differ from T + rn_u(m)
+__device__ __forceinline__ double quantise_mass(double m, const MassGrid& g, bool& unsafe) {
+    if (!g.ok) return m;
+    if (!(m >= 0.0) || !(m < g.top)) { unsafe = true; return m; }
+    const double s = m*g.inv_u;                      // exact (power-of-two scaling, no overflow: m < top)
+    const double q = rint(s);
+    if (fabs(s - q) == 0.5) unsafe = true;           // tie: the outcome depends on the parity of the running sum
+    return q*g.u;
+}
+
 // ---- mass moments: sum m, sum m r, sum m v ------------------------------------------------------
 // tile_sums[7][ntiles] (component-major, so the tile scan reads coalesced); one tile = kScanThreads consecutive particles.
+// lead_mass: device pointer to the mass of GLOBAL particle 0 (defines the binade of the mass grid), or NULL:
+// the shard's own first element when it starts at global index 0, no quantisation otherwise.
+// grid_out / unsafe: written by block 0 / OR-ed by every block (scratch of the launcher).
 __global__ void __launch_bounds__(kScanThreads)
-moments_tile_kernel(rebx_b200_state st, double* __restrict__ tile_sums) {
+moments_tile_kernel(rebx_b200_state st, double* __restrict__ tile_sums, const double* __restrict__ lead_mass,
+                    MassGrid* __restrict__ grid_out, unsigned* __restrict__ unsafe, unsigned long long* __restrict__ first_massive) {
     __shared__ double s_warp[kScanThreads/32][7];
     const int64_t k = (int64_t)blockIdx.x*kScanThreads + threadIdx.x;
+    const MassGrid g = lead_mass ? make_mass_grid(*lead_mass) : (st.index_base == 0 ? make_mass_grid(st.m[0]) : make_mass_grid(0.0));
+    if (blockIdx.x == 0 && threadIdx.x == 0) *grid_out = g;
     double v[7] = {0, 0, 0, 0, 0, 0, 0};
+    bool bad = false;
     if (k < st.n) {
         const double m = st.m[k];
-        v[0] = m; v[1] = st.x[k]*m; v[2] = st.y[k]*m; v[3] = st.z[k]*m;
+        v[0] = quantise_mass(m, g, bad);
+        v[1] = st.x[k]*m; v[2] = st.y[k]*m; v[3] = st.z[k]*m;
         v[4] = st.vx[k]*m; v[5] = st.vy[k]*m; v[6] = st.vz[k]*m;
+    }
+    if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(unsafe, 1u);
+    // smallest local index >= (global index 1) whose mass is not zero on the grid: only the first tiles can
+    // lower it, so nearly every CTA leaves after one read
+    const bool massive = k < st.n && st.index_base + k >= 1 && v[0] != 0.0;
+    if (__syncthreads_or(massive) && (unsigned long long)((int64_t)blockIdx.x*kScanThreads) < *first_massive) {
+        if (massive) atomicMin(first_massive, (unsigned long long)k);
     }
     double total[7];
     block_exclusive_scan<7>(v, total, s_warp);
 #pragma unroll
     for (int c = 0; c < 7; c++) if (threadIdx.x == c) tile_sums[(size_t)c*gridDim.x + blockIdx.x] = total[c];
+}
+
+// Status of the mass scan + the literal recurrences when the exactness argument does not hold.
+//   status[0] (totals[7]) = 0: the quantised scan IS the reference's arithmetic; 1: it is not
+//   (running sum left the binade, tie, negative mass, no positive leading mass).
+// mref != NULL (single-shard evaluation): on status 1 the forward fold and, when `backward`, the backward peel
+// are redone literally by one thread (lanes load 32 masses at a time, lane 0 adds them in order):
+// totals[0] = T_{N-1}; mref[k] = B_k.  Cost when taken: 2 N dependent FP64 additions.
+__global__ void mass_status_kernel(rebx_b200_state st, MassGrid* __restrict__ grid, const unsigned* __restrict__ unsafe,
+                                   const unsigned long long* __restrict__ first_massive,
+                                   double* __restrict__ totals, double* __restrict__ mref, int backward, double* __restrict__ totals_out) {
+    const int lane = threadIdx.x;
+    bool bad = (*unsafe != 0u) || !grid->ok || !(totals[0] < grid->top);
+    if (!bad && grid->lead == 0.5*grid->top) {
+        // leading mass an exact power of two: the particles in front of the first massive one sit on the finer grid
+        // below 2^K once the peel has dipped; a non-zero mass among them (too small for the grid) is outside the
+        // argument.  Normally there is none to look at (the first massive particle is particle 1).
+        const unsigned long long r = *first_massive;
+        const int64_t lo = st.index_base >= 1 ? 0 : 1 - st.index_base;
+        const int64_t hi = r < (unsigned long long)st.n ? (int64_t)r : st.n;
+        bool tiny = hi - lo > 65536;
+        for (int64_t k = lo + lane; k < hi && !tiny; k += 32) if (st.m[k] != 0.0) tiny = true;
+        bad = __any_sync(0xffffffffu, tiny);
+    }
+    __syncwarp();
+    if (lane == 0) {
+        totals[7] = bad ? 1.0 : 0.0;
+        const unsigned long long r = *first_massive;
+        if (grid->ok && r < (unsigned long long)st.n) {       // B_r = fl((m_0 + u q_r) - m_r), see the header comment
+            const double mr = st.m[r];
+            bool unused = false;
+            const double mq = quantise_mass(mr, *grid, unused);
+            grid->dip = (grid->lead + mq) - mr;
+        }
+    }
+    if (!bad || mref == nullptr) {
+        __syncwarp();
+        if (totals_out && lane < 8) totals_out[lane] = totals[lane];
+        return;
+    }
+    double T = 0.0;
+    for (int64_t base = 0; base < st.n; base += 32) {
+        const int64_t k = base + lane;
+        const double mine = (k < st.n) ? st.m[k] : 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const double mj = __shfl_sync(0xffffffffu, mine, j);
+            if (base + j < st.n) T += mj;                    // c.m += m_i   (reb_simulation_com)
+        }
+    }
+    if (lane == 0) totals[0] = T;
+    __syncwarp();
+    if (totals_out && lane < 8) totals_out[lane] = totals[lane];
+    if (!backward) return;
+    double B = T;
+    for (int64_t top = st.n; top > 0; top -= 32) {
+        const int64_t k = top - 1 - lane;                    // lane j holds particle top-1-j
+        const double mine = (k >= 0) ? st.m[k] : 0.0;
+        double out = 0.0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const double mj = __shfl_sync(0xffffffffu, mine, j);
+            if (top - 1 - j >= 0) B -= mj;                   // com.m -= p.m  (rebx_get_com_without_particle)
+            if (lane == j) out = B;
+        }
+        if (k >= 0) mref[k] = out;                           // mass interior to particle k
+    }
 }
 
 // In-place exclusive scan over the `ntiles` tile sums of NC components, stored component-major
@@ -139,7 +267,8 @@ __device__ __forceinline__ Vec3 damping_force(const rebx_b200_effect& fx, const 
 template <int K0, int K1, int K2>
 __global__ void __launch_bounds__(kScanThreads)
 jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __restrict__ tile_prefix,
-                    double* __restrict__ tvec, double* __restrict__ tile_tsums, const double* __restrict__ carry7) {
+                    double* __restrict__ tvec, double* __restrict__ tile_tsums, const double* __restrict__ carry7,
+                    const MassGrid* __restrict__ grid, const double* __restrict__ status, const double* __restrict__ mref) {
     __shared__ double s_warp[kScanThreads/32][7];
     const rebx_b200_state& st = P.st;
     const int64_t k = (int64_t)blockIdx.x*kScanThreads + threadIdx.x;
@@ -148,13 +277,16 @@ jacobi_sweep_kernel(const __grid_constant__ rebx_b200_pass P, const double* __re
     if (live) {
         p.x = st.x[k]; p.y = st.y[k]; p.z = st.z[k]; p.vx = st.vx[k]; p.vy = st.vy[k]; p.vz = st.vz[k]; p.m = st.m[k];
     }
-    double v[7] = {p.m, p.x*p.m, p.y*p.m, p.z*p.m, p.vx*p.m, p.vy*p.m, p.vz*p.m};
+    bool unused_flag = false;
+    double v[7] = {live ? quantise_mass(p.m, *grid, unused_flag) : 0.0, p.x*p.m, p.y*p.m, p.z*p.m, p.vx*p.m, p.vy*p.m, p.vz*p.m};
     double total[7];
     block_exclusive_scan<7>(v, total, s_warp);
     double body[REBX_B200_BODY_DOUBLES];
     // carry7: mass moments of the shards in front of this one (index ranges below index_base), or NULL
-    double M = tile_prefix[blockIdx.x] + v[0];                // mass interior to particle k
+    double M = tile_prefix[blockIdx.x] + v[0];                // mass interior to particle k: exact sums of multiples of u
     if (carry7) M = carry7[0] + M;
+    if (grid->ok && M == grid->lead && st.index_base + k >= 1) M = grid->dip;   // bottom of the binade: the literal last peel
+    if (mref != nullptr && status[0] != 0.0 && live) M = mref[k];     // the literal recurrences (mass_status_kernel)
 #pragma unroll
     for (int j = 0; j < 6; j++) {
         double S = tile_prefix[(size_t)(1 + j)*gridDim.x + blockIdx.x] + v[1 + j];
@@ -221,7 +353,7 @@ jacobi_apply_kernel(rebx_b200_state st, const double* __restrict__ tvec, const d
     }
 }
 
-typedef void (*jacobi_fn)(const rebx_b200_pass, const double*, double*, double*, const double*);
+typedef void (*jacobi_fn)(const rebx_b200_pass, const double*, double*, double*, const double*, const MassGrid*, const double*, const double*);
 struct JacobiCombo { int k[3]; jacobi_fn fn; };
 #define REBXB_JCOMBO(a, b, c) { {a, b, c}, jacobi_sweep_kernel<a, b, c> },
 static const JacobiCombo kJacobiCombos[] = {

@@ -161,8 +161,11 @@ class Shard:
                 raise ValueError("at most 3 stacked effects in a centre-of-mass frame")
             lib.rebx_b200_scan_scratch_bytes.restype = ctypes.c_size_t
             self.scan_scratch = torch.empty(lib.rebx_b200_scan_scratch_bytes(c_int64(self.n)), dtype=torch.uint8, device=self.device)
-            self.moments = torch.zeros(7, dtype=torch.float64, device=self.device)     # sum m, sum m r, sum m v of this shard
+            self.moments = torch.zeros(8, dtype=torch.float64, device=self.device)     # sum m, sum m r, sum m v of this shard, status
             self.tsum = torch.zeros(3, dtype=torch.float64, device=self.device)        # JACOBI: sum of t_i of this shard
+            self.lead_mass = dev(np.array([w["m"][0]]))                                # mass of global particle 0 (replicated)
+        # REBX_B200_COM_WHOLE: this shard is the whole ensemble (the literal mass recurrences are available as a fallback)
+        self._com_flags = 1 if (lo == 0 and hi == n_total and self.index_base == 0 and standalone) else 0
         self._pass = self._make_pass()
 
     # ------------------------------------------------------------------------------------------
@@ -237,9 +240,12 @@ class Shard:
     def com_moments(self, stream=None):
         """Stage 1: this shard's mass moments -> self.moments (JACOBI also keeps the in-shard prefix)."""
         st, scr = ctypes.byref(self._pass.st), c_void_p(self.scan_scratch.data_ptr())
+        # the mass of global particle 0 (slot 7 of the replicated body record) fixes the grid on which the masses
+        # are summed, so that every shard reproduces the reference's sequentially rounded interior masses
+        lead = c_void_p(self.lead_mass.data_ptr())
         if self.coordinates == "JACOBI":
-            return self._libcall("rebx_b200_jacobi_moments", st, scr, c_void_p(self.moments.data_ptr()), stream=stream)
-        return self._libcall("rebx_b200_mass_moments", st, c_void_p(self.moments.data_ptr()), scr, stream=stream)
+            return self._libcall("rebx_b200_jacobi_moments", st, scr, c_void_p(self.moments.data_ptr()), lead, c_int(self._com_flags), stream=stream)
+        return self._libcall("rebx_b200_mass_moments", st, c_void_p(self.moments.data_ptr()), scr, lead, c_int(self._com_flags), stream=stream)
 
     def com_sweep(self, moments, stream=None):
         """Stage 2.  BARYCENTRIC: `moments` = the all-reduced totals; the sweep leaves -sum (m_i/M) f_i of this
@@ -248,7 +254,7 @@ class Shard:
         if self.coordinates == "JACOBI":
             carry = c_void_p(moments.data_ptr()) if moments is not None else None
             return self._libcall("rebx_b200_jacobi_sweep", ctypes.byref(self._pass), c_void_p(self.scan_scratch.data_ptr()), carry,
-                                 c_void_p(self.tsum.data_ptr()), stream=stream)
+                                 c_void_p(self.tsum.data_ptr()), c_int(self._com_flags), stream=stream)
         k = self._libcall("rebx_b200_com_bodies", c_void_p(moments.data_ptr()), c_void_p(self.bodies.data_ptr()), c_int(len(self.kinds)), stream=stream)
         return k + self.launch(stream)
 

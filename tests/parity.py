@@ -23,3 +23,39 @@ def errors(got, want, skip=()):
     norm = d/np.maximum(np.max(np.abs(w), axis=0), 1e-300)
     return {"bit_identical": bool(np.array_equal(g, w)), "max_component": float(np.max(comp)),
             "frac_component_above_tol": float(np.mean(comp > TOL)), "max_normwise": float(np.max(norm))}
+
+
+# ---- regression guards on the per-component metric ------------------------------------------------------
+# Where bit identity is impossible (libdevice vs glibc transcendentals, reductions in another order) the
+# tests assert the norm-wise tolerance AND pin the per-component picture: the largest per-component error
+# may not exceed twice the value measured on a B200 when the guard file was recorded
+# (tests/golden/parity_guards.json, written by running the GPU suite with REBX_PARITY_RECORD=1), and the
+# fraction of components above 1e-13 stays <= 1e-5.  A regression on small components (say to 1e-9) that the
+# norm-wise metric cannot see fails here.
+import json
+import os
+
+_GUARD_PATH = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden", "parity_guards.json")
+_RECORD = os.environ.get("REBX_PARITY_RECORD") == "1"
+try:
+    with open(_GUARD_PATH) as _f:
+        GUARDS = json.load(_f)
+except OSError:
+    GUARDS = {}
+
+
+def guard(name, e, normwise=TOL, frac=1e-5):
+    """Asserts the parity bar for a result that is not bit-identical; see the comment above."""
+    if _RECORD:
+        out = os.path.join(os.path.dirname(_GUARD_PATH), "..", "..", "gpurun_out", "parity_guards.jsonl")
+        os.makedirs(os.path.dirname(out), exist_ok=True)
+        with open(out, "a") as f:
+            f.write(json.dumps({"name": name, **e}) + "\n")
+    assert e["max_normwise"] <= normwise, (name, e)
+    assert e["frac_component_above_tol"] <= frac, (name, e)
+    if _RECORD:
+        return
+    g = GUARDS.get(name)
+    assert g is not None, f"no recorded per-component guard for {name!r}: run the GPU suite once with REBX_PARITY_RECORD=1"
+    # floor: a guard recorded as 0 (bit-identical that day) still admits anything inside the tolerance
+    assert e["max_component"] <= max(2.0*g["max_component"], TOL), (name, e, g)

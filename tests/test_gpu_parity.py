@@ -5,7 +5,7 @@ present, else the C restatement (bit-identical to it, tests/test_oracle.py)."""
 import numpy as np
 import pytest
 
-from parity import TOL, errors
+from parity import TOL, errors, guard
 
 pytestmark = pytest.mark.gpu
 
@@ -90,14 +90,14 @@ def test_yarkovsky_gr_potential(built, base):
     """Config 4: all three ye_flag modes, per-particle parameters, fused with gr_potential."""
     from reboundx_b200 import workloads
     order = ["yarkovsky_effect", "gr_potential"]
-    w = workloads.asteroid_ensemble(30001)
+    w = workloads.asteroid_ensemble(200001)
     acc0 = acc_variants(w, 4)[base]
     want, _ = oracle_acc(w, order, acc0)
     got, _ = device_acc(w, order, acc0)
     e = errors(got, want, skip=(0,))
-    # libdevice pow/atan/sin/cos vs glibc: not bit-identical; norm-wise within tolerance always
-    assert e["max_normwise"] <= TOL, e
-    assert e["frac_component_above_tol"] <= 1e-4, e
+    # libdevice pow/atan/sin/cos vs glibc: not bit-identical; norm-wise within tolerance always, the per-component
+    # picture pinned by the recorded guard (tests/parity.py)
+    guard(f"yarkovsky_gr_potential/{base}", e)
     simple = np.concatenate([[False], w["ye_flag"] != 0])
     es = errors([g[simple] for g in got], [x[simple] for x in want])
     assert es["bit_identical"], es          # simple versions use + - * / sqrt only
@@ -112,8 +112,7 @@ def test_damping_trio_particle_coordinates(built, add_order):
     want, br = oracle_acc(w, add_order, acc0)
     got, _ = device_acc(w, add_order, acc0)
     e = errors(got, want, skip=(0,))
-    assert e["max_normwise"] <= TOL, e
-    assert e["frac_component_above_tol"] <= 5e-3, e
+    guard("trio_particle/gravity/" + "+".join(add_order), e, frac=4e-5)       # 30001 x 3 components: at most three outliers
     exact = np.array([acc0[k][0] for k in range(3)]) + sum(br[f][:3] for f in add_order)
     scale = sum(br[f][3:] for f in add_order) + np.abs([acc0[k][0] for k in range(3)])
     for k in range(3):
@@ -272,8 +271,116 @@ def test_damping_trio_centre_of_mass_frames(built, coordinates, add_order):
         assert star["max_normwise"] <= 16*np.finfo(float).eps*cond, (star, cond)
     else:
         e = errors(got, want)
-    assert e["max_normwise"] <= TOL, e
-    assert e["frac_component_above_tol"] <= 5e-3, e
+    guard(f"com_frames_3000/{coordinates}/" + "+".join(add_order), e, frac=1.2e-4 if coordinates == "JACOBI" else 1e-3)
+
+
+def _com_device(w, add_order, coordinates, acc0):
+    from reboundx_b200 import scenarios
+    sim, rebx, _ = scenarios.build(w, add_order, coordinates=coordinates, acc=acc0)
+    sim.additional_forces()
+    sim.messages()
+    got = sim.acc()
+    rebx.detach(); sim.free()
+    return got
+
+
+@pytest.mark.parametrize("coordinates", ["JACOBI", "BARYCENTRIC"])
+@pytest.mark.parametrize("base", ["zero", "gravity"])
+def test_centre_of_mass_frames_20000_against_the_reference(built, coordinates, base):
+    """The harshest view the reference can still produce in seconds: N = 2*10^4, the PURE damping force (zero
+    base) and the gravity base, against the reference's own O(N^2) loops.  Round 1 missed the tolerance here
+    (2e-12 norm-wise): the interior mass of rebx_com_force enters mu = G (m + M_i) and the reference's M_i
+    carries ~sqrt(N) ulps of sequential rounding.  The device now reproduces that rounding exactly
+    (kernels_jacobi.cuh: scan on the mass grid), so the bar is the plain north-star tolerance."""
+    from reboundx_b200 import workloads
+    w = workloads.planetesimal_disk(20000)
+    if coordinates == "BARYCENTRIC":
+        w["d_factor"] = np.full(20000, 5.0)
+    acc0 = acc_variants(w, 21)[base]
+    want, _ = oracle_acc(w, TRIO, acc0, coordinates)
+    got = _com_device(w, TRIO, coordinates, acc0)
+    # BARYCENTRIC: the star's own force is the difference of AU-scale numbers 3e-8 AU apart (see the N = 3000 test)
+    e = errors(got, want, skip=(0,)) if coordinates == "BARYCENTRIC" else errors(got, want)
+    # Per component the reference itself is the noisier side here: it subtracts the back-reaction of every particle
+    # behind j from a_j one at a time (up to N roundings of eps |a_j|), the device once.  The O(N) oracle, which sums
+    # them in long double, differs from the reference's loops by exactly this much (1.1e-12 per component, 1.3e-4 of
+    # the components above 1e-13, 5.2e-15 norm-wise at N = 2*10^4: tests/test_oracle.py) -- so the outlier fraction is
+    # bounded at 5e-4 here and the per-component maximum by the recorded guard.
+    # BARYCENTRIC adds one more ill-conditioned ingredient: the star is evaluated against the barycentre it sits
+    # 3e-8 AU from, and (m_0/M) f_0 ~ f_0 dominates the shift EVERY particle receives (rebxtools.c:108-115).  That
+    # shift agrees to 2.6e-14 relative, i.e. ~1.5e-16 absolute on every component -- 5e-14 norm-wise on the pure
+    # force, and a per-component outlier wherever a component nearly cancels against the shift (0.3 % of them on
+    # the gravity base; the O(N) oracle vs the reference's loops: same picture, tests/test_oracle.py).
+    guard(f"com_frames_20000/{coordinates}/{base}", e, frac=5e-4 if coordinates == "JACOBI" else 1e-2)
+    # Against the reference's own COM recurrence with the back-reaction summed once (the O(N) oracle) the Jacobi
+    # frame meets the tolerance on EVERY component, on the pure force too (measured 2.2e-14):
+    from oracle import oracle
+    lin, _ = oracle.port_apply(w, TRIO[::-1], acc0, coordinates, com="linear")
+    el = errors(got, lin, skip=(0,)) if coordinates == "BARYCENTRIC" else errors(got, lin)
+    if coordinates == "JACOBI":
+        assert el["max_component"] <= TOL, el
+    guard(f"com_frames_20000_vs_linear_oracle/{coordinates}/{base}", el, frac=1e-5 if coordinates == "JACOBI" else 1e-2)
+
+
+@pytest.mark.parametrize("coordinates", ["JACOBI", "BARYCENTRIC"])
+def test_config5_full_size_centre_of_mass_frames(built, coordinates):
+    """BASELINE config 5 at its full 10^6 planetesimals in the reference's default frame (JACOBI) and in
+    BARYCENTRIC: the reference's O(N^2) loops would need ~40 min per force, so the oracle is
+    oracle_com_force_linear -- the reference's own COM recurrence (bit-identical interior masses and
+    centres of mass) with the back-reaction summed in long double, pinned against the O(N^2) loops and
+    oracle/_ref at N <= 2*10^4 by tests/test_oracle.py."""
+    from oracle import oracle
+    from reboundx_b200 import workloads
+    n = 1_000_000
+    w = workloads.planetesimal_disk(n)
+    if coordinates == "BARYCENTRIC":
+        w["d_factor"] = np.full(n, 5.0)
+    acc0 = acc_variants(w, 22)["gravity"]
+    want, _ = oracle.port_apply(w, TRIO[::-1], acc0, coordinates, com="linear")
+    got = _com_device(w, TRIO, coordinates, acc0)
+    e = errors(got, want, skip=(0,)) if coordinates == "BARYCENTRIC" else errors(got, want)
+    # 10^6 sequential steps of the reference's COM fold (reproduced by the oracle) leave ~3e-19 AU of rounding in
+    # COM_i, the device's tree sums ~1e-20: a handful of nearly circular, nearly planar orbits amplify that above
+    # 1e-13 on single small components (JACOBI, zero base: 3e-5 of the components); norm-wise all is <= 6e-14.
+    fr = 1e-4 if coordinates == "JACOBI" else 2e-2
+    guard(f"com_frames_1e6/{coordinates}/gravity", e, frac=fr)
+    want0, _ = oracle.port_apply(w, TRIO[::-1], None, coordinates, com="linear")
+    got0 = _com_device(w, TRIO, coordinates, None)
+    e0 = errors(got0, want0, skip=(0,)) if coordinates == "BARYCENTRIC" else errors(got0, want0)
+    guard(f"com_frames_1e6/{coordinates}/zero", e0, frac=fr)
+
+
+@pytest.mark.parametrize("case", ["lead_0.999_crosses_binade", "exact_ties", "massless_in_front", "tiny_masses_power_of_two_lead",
+                                  "lead_just_below_a_power_of_two"])
+@pytest.mark.parametrize("coordinates", ["JACOBI", "BARYCENTRIC"])
+def test_interior_mass_edge_cases(built, case, coordinates):
+    """Mass distributions on which the exactness argument of the mass-grid scan does NOT hold (running sum
+    leaves the binade of the leading mass, exact ties, peel at the bottom of the binade): the launch must
+    notice and redo the reference's two recurrences literally.  Against the reference's O(N^2) loops."""
+    from reboundx_b200 import workloads
+    n = 3000
+    w = workloads.planetesimal_disk(n)
+    rng = np.random.default_rng(5)
+    if case == "lead_0.999_crosses_binade":
+        w["m"][0] = 0.999
+        w["m"][1:] = 10.0**rng.uniform(-7.0, -5.5, n)         # ~2e-3 in all: the running sum crosses 1.0
+    elif case == "exact_ties":
+        w["m"][1:] = (rng.integers(1, 1000, n) + 0.5)*2.0**-52   # every addition is a tie
+    elif case == "massless_in_front":
+        w["m"][1:40] = 0.0
+    elif case == "tiny_masses_power_of_two_lead":
+        w["m"][0] = 2.0
+        w["m"][1:] = 10.0**rng.uniform(-18.0, -14.0, n)       # many below half a grid unit (2.2e-16)
+    elif case == "lead_just_below_a_power_of_two":
+        w["m"][0] = 1.0 - 2.0**-40                             # the running sum leaves the binade [0.5, 1) within a few particles
+    if coordinates == "BARYCENTRIC":
+        w["d_factor"] = np.full(n, 5.0)
+    acc0 = acc_variants(w, 23)["gravity"]
+    add = ["modify_orbits_forces", "type_I_migration"] if case == "massless_in_front" else TRIO
+    want, _ = oracle_acc(w, add, acc0, coordinates)
+    got = _com_device(w, add, coordinates, acc0)
+    e = errors(got, want, skip=(0,)) if coordinates == "BARYCENTRIC" else errors(got, want)
+    guard(f"interior_mass_edge/{case}/{coordinates}", e, frac=1.2e-4 if coordinates == "JACOBI" else 2e-2)
 
 
 @pytest.mark.parametrize("coordinates", ["JACOBI", "BARYCENTRIC"])
@@ -313,8 +420,7 @@ def test_sharded_centre_of_mass_frames(built, coordinates, cuts):
     torch.cuda.synchronize()
     got = [np.concatenate([sh.acc()[k] for sh in shards]) for k in range(3)]
     e = errors(got, want, skip=(0,)) if coordinates == "BARYCENTRIC" else errors(got, want)
-    assert e["max_normwise"] <= TOL, e
-    assert e["frac_component_above_tol"] <= 5e-3, e
+    guard(f"sharded_com_frames/{coordinates}/{len(cuts)}cuts", e, frac=1.2e-4 if coordinates == "JACOBI" else 1e-3)
     if not cuts:        # one shard == the host-facing call's resident chunk: same kernels, same bits
         from reboundx_b200 import scenarios
         sim, rebx, _ = scenarios.build(w, TRIO, coordinates=coordinates, acc=acc0)
@@ -501,8 +607,7 @@ def test_gr_1pn(built, case):
     if case == "three_active_massless":
         assert e["bit_identical"], e
     else:
-        assert e["max_normwise"] <= TOL, e
-        assert e["frac_component_above_tol"] <= 1e-4, e
+        guard(f"gr_1pn/{case}", e, frac=2e-5)
 
 
 def test_gr_needs_n_active_for_large_ensembles(built):
@@ -687,8 +792,7 @@ def test_full_size_against_oracle_on_a_random_subsample(built, name):
     if name in ("debris_disk", "circumplanetary_ring"):
         assert e["bit_identical"], e
     else:
-        assert e["max_normwise"] <= TOL, e
-        assert e["frac_component_above_tol"] <= 5e-3, e
+        guard(f"full_size_subsample/{name}", e)
     assert all(np.isfinite(a).all() for a in got)
 
 
@@ -938,8 +1042,7 @@ def test_central_force(built, gamma):
     want, br = oracle_acc(w, ["central_force"], acc0)
     got, _ = device_acc(w, ["central_force"], acc0)
     e = errors(got, want, skip=(0,))
-    assert e["max_normwise"] <= TOL, e
-    assert e["frac_component_above_tol"] <= 1e-3, e
+    guard(f"central_force/{gamma}", e, frac=4e-5)
     exact = np.array([acc0[k][0] for k in range(3)]) + br["central_force"][:3]
     scale = br["central_force"][3:] + np.abs([acc0[k][0] for k in range(3)])
     for k in range(3):
@@ -1202,6 +1305,5 @@ def test_gas_dynamical_friction(built):
     want, _ = oracle_acc(w, ["gas_dynamical_friction"], acc0)
     got, _ = device_acc(w, ["gas_dynamical_friction"], acc0)
     e = errors(got, want)
-    assert e["max_normwise"] <= TOL, e
-    assert e["frac_component_above_tol"] <= 1e-3, e
+    guard("gas_dynamical_friction", e, frac=4e-5)
     assert np.any(np.array(got)[:, 1:] != np.array(acc0)[:, 1:])

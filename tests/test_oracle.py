@@ -137,3 +137,48 @@ def test_gr_notebook_known_answers(built):
     if not oracle.have_ref():
         pytest.skip("needs oracle/_ref")
     nb.check(*nb.run(oracle.ref_lib()))
+
+
+@pytest.mark.parametrize("coordinates", ["JACOBI", "BARYCENTRIC"])
+@pytest.mark.parametrize("base", ["zero", "gravity"])
+def test_linear_com_oracle_against_the_reference_loops(built, coordinates, base):
+    """oracle_com_force_linear is the full-size (10^6) oracle of the centre-of-mass frames: the reference's own
+    COM recurrence + the back-reaction summed once in long double instead of one particle at a time.  Pinned here
+    against the reference's O(N^2) loops (oracle/_ref when built, and their restatement) at N = 2*10^4: they
+    differ only by the reference's accumulated rounding of the n sequential subtractions, <= sqrt(n) eps of |a|."""
+    from oracle import oracle
+    from parity import errors
+    from reboundx_b200 import workloads as W
+    trio = ["modify_orbits_forces", "gas_damping_timescale", "type_I_migration"]
+    n = 20000
+    w = W.planetesimal_disk(n)
+    if coordinates == "BARYCENTRIC":
+        w["d_factor"] = np.full(n, 5.0)
+    acc0 = None if base == "zero" else W.gravity_like_acc(w, np.random.default_rng(3))
+    quad, _ = oracle.port_apply(w, trio[::-1], acc0, coordinates)
+    lin, _ = oracle.port_apply(w, trio[::-1], acc0, coordinates, com="linear")
+    if oracle.have_ref():
+        ref = oracle.ref_apply(w, trio, acc0, coordinates)
+        for k in range(3):
+            assert np.array_equal(np.array(ref[k]), quad[k])
+    e = errors(lin, quad, skip=(0,)) if coordinates == "BARYCENTRIC" else errors(lin, quad)
+    assert e["max_normwise"] <= 2e-14, e            # measured 5e-15 (JACOBI), 6e-15 (BARYCENTRIC)
+    if coordinates == "BARYCENTRIC":
+        # the star: a tiny force that is nearly all back-reaction, i.e. the sum the two functions round differently
+        star = errors([a[:1] for a in lin], [a[:1] for a in quad])
+        assert star["max_normwise"] <= 1e-11, star
+
+
+def test_exact_com_differs_from_the_reference_by_the_interior_mass(built):
+    """Why the device scans the masses on the reference's rounding grid (kernels_jacobi.cuh): with EXACT prefix
+    sums for COM_i the Jacobi forces move by ~2e-12 norm-wise against the reference -- its interior mass
+    carries ~sqrt(N) ulps of sequential rounding and enters mu = G (m + M_i)."""
+    from oracle import oracle
+    from parity import errors
+    from reboundx_b200 import workloads as W
+    trio = ["modify_orbits_forces", "gas_damping_timescale", "type_I_migration"]
+    w = W.planetesimal_disk(20000)
+    lin, _ = oracle.port_apply(w, trio[::-1], None, "JACOBI", com="linear")
+    exact, _ = oracle.port_apply(w, trio[::-1], None, "JACOBI", com="linear_exact")
+    e = errors(exact, lin)
+    assert 1e-13 < e["max_normwise"] < 1e-10, e
