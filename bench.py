@@ -55,6 +55,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--cpu-sample", type=int, default=2_000_000)
     ap.add_argument("--no-parallel-bound", action="store_true", help="skip the all-cores upper bound of the CPU baseline")
+    ap.add_argument("--math", default="exact", choices=["exact", "tolerance"],
+                    help="exact: bit-identical to the reference where + - * / sqrt (default); tolerance: kernels_tol.cu (FMA, shared reciprocals)")
     ap.add_argument("--coordinates", default="PARTICLE", choices=["PARTICLE", "JACOBI", "BARYCENTRIC"],
                     help="reference frame of the rebx_com_force effects (planetesimal_disk only)")
     return ap.parse_args()
@@ -248,7 +250,9 @@ def run_ours(args):
     # central body (global index 0) is replicated and broadcast from rank 0 every evaluation.
     w = getattr(workloads, builder)(n, seed=3 + rank)
     lo = 0 if rank == 0 else 1
-    shard = device.Shard(w, exec_order, dev, lo=lo, index_base=(0 if rank == 0 else 1 + rank*n), coordinates=args.coordinates)
+    shard = device.Shard(w, exec_order, dev, lo=lo, index_base=(0 if rank == 0 else 1 + rank*n), coordinates=args.coordinates, math=args.math)
+    if args.math == "tolerance":
+        os.environ["REBX_B200_MATH"] = "tolerance"          # the host-facing leg reads it when its device context is created
     n_local = shard.n - (1 if rank == 0 else 0)          # the body itself is not an evaluation
 
     def barrier():

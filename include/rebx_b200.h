@@ -111,6 +111,12 @@ typedef struct rebx_b200_effect {
  * velocity and mass in all body records).  Lets the fused sweep share the relative coordinates and the
  * orbit elements between stacked effects; results are unchanged. */
 #define REBX_B200_PASS_SHARED_BODY 1
+/* pass.reserved bit: TOLERANCE-MODE arithmetic for this pass (reboundx_b200/csrc/kernels_tol.cu): FMA contraction, one
+ * reciprocal square root per particle shared by every power of the distance, Newton reciprocals instead of IEEE
+ * divisions -- a few ulp per operation, ~1e-15 on a force vector, against the default build's bit identity with the
+ * reference.  Honoured for stacks of up to three effects that all refer to one central body in PARTICLE
+ * coordinates (REBX_B200_PASS_SHARED_BODY must be set as well); any other pass runs the exact kernels. */
+#define REBX_B200_PASS_TOLERANCE 2
 
 typedef struct rebx_b200_pass {
     rebx_b200_state st;

@@ -112,6 +112,7 @@ struct DeviceContext {
     size_t chunk = size_t(1) << 19;         // 64 MB of AoS records per pipeline stage
     bool chunk_from_env = false;
     bool paranoid = false;
+    bool tolerance = false;                 // REBX_B200_MATH=tolerance: kernels_tol.cu for the stacks it covers
 
     void unregister_host() {
         if (registered_ptr) { cudaHostUnregister(registered_ptr); cudaGetLastError(); }
@@ -359,6 +360,7 @@ static DeviceContext* ensure_ctx(Side* side, std::string& why) {
     if ((e = cudaEventCreateWithFlags(&ctx->bodies_ready, cudaEventDisableTiming)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
     if (const char* c = std::getenv("REBX_B200_CHUNK")) { long v = std::atol(c); if (v >= 1024) { ctx->chunk = (size_t)v & ~size_t(1); ctx->chunk_from_env = true; } }
     if (const char* p = std::getenv("REBX_B200_PARANOID")) ctx->paranoid = std::atoi(p) != 0;
+    if (const char* m = std::getenv("REBX_B200_MATH")) ctx->tolerance = (m[0] == 't' || m[0] == 'T');
     if (const char* z = std::getenv("REBX_B200_ZEROCOPY_MAX")) { long v = std::atol(z); if (v >= 0) ctx->zero_copy_max = (size_t)v; }
     ctx->ready = true;
     side->dev = std::move(ctx);
@@ -773,6 +775,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 bool same = true;
                 for (size_t j = e0 + 1; j < e1; j++) if (entries[j].body_index != entries[e0].body_index) same = false;
                 if (same) P.reserved |= REBX_B200_PASS_SHARED_BODY;
+                if (ctx->tolerance) P.reserved |= REBX_B200_PASS_TOLERANCE;
             }
             for (int j = 0; j < P.n_effects; j++) {
                 const Entry& en = entries[e0 + j];

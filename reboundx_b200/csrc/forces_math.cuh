@@ -10,6 +10,7 @@
 #include <cstdint>
 #include <cmath>
 #include "rebx_b200.h"
+#include "pass_common.cuh"
 #include "exact_math.cuh"
 
 #ifndef REBXB_YARK_TRIG_IDENTITY
@@ -22,21 +23,6 @@ constexpr double kPi     = 3.14159265358979323846;
 constexpr double kTwoPi  = 2*kPi;
 constexpr double kPi5    = kPi*kPi*kPi*kPi*kPi;          // M_PI*M_PI*M_PI*M_PI*M_PI, left-assoc (yarkovsky_effect.c:156)
 constexpr double kTiny   = 1.E-308;
-
-struct Particle { double x, y, z, vx, vy, vz, m, r; };
-// Position, velocity and mass of the body an effect refers to, held in REGISTERS: stacked effects that
-// share one central body then share one Origin, and the compiler can merge their common sub-expressions
-// (values re-read from shared memory after every libdevice / division slow-path call could not be).
-struct Origin { double x, y, z, vx, vy, vz, m; };
-__device__ __forceinline__ Origin load_origin(const double* __restrict__ rec) {
-    return Origin{rec[REBX_B200_BODY_X+0], rec[REBX_B200_BODY_X+1], rec[REBX_B200_BODY_X+2],
-                  rec[REBX_B200_BODY_VX+0], rec[REBX_B200_BODY_VX+1], rec[REBX_B200_BODY_VX+2], rec[REBX_B200_BODY_M]};
-}
-struct Vec3     { double x, y, z; };
-
-__device__ __forceinline__ bool is_absent(double v) {
-    return (unsigned long long)__double_as_longlong(v) == REBX_B200_ABSENT_BITS;
-}
 
 // ---------------------------------------------------------------------------------------
 // Arithmetic policies.  The light effects (radiation, J2/J4, gr_potential) are written once against

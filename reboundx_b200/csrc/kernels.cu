@@ -25,85 +25,14 @@
 #include <utility>
 #include <vector>
 #include "rebx_b200.h"
+#include "pass_common.cuh"
 #include "forces_math.cuh"
-
-namespace rebxb {
 
 #ifndef REBXB_FASTMATH
 #define REBXB_FASTMATH 0
 #endif
-#ifndef REBXB_HEAVY_MINBLOCKS
-#define REBXB_HEAVY_MINBLOCKS 2
-#endif
-#ifndef REBXB_THREADS
-#define REBXB_THREADS 256
-#endif
-constexpr int kThreads   = REBXB_THREADS;    // threads per CTA of the sweeps (128 was measured too)
-constexpr int kMaxBlocks = 4096;
-constexpr int kWarps     = kThreads/32;
 
-template <int K> struct Traits;
-template <> struct Traits<REBX_B200_NONE>          { static constexpr bool vel=false, mass=false, rad=false, red=false; static constexpr int ntab=0; static constexpr bool itab=false; };
-template <> struct Traits<REBX_B200_RADIATION>     { static constexpr bool vel=true,  mass=false, rad=false, red=false; static constexpr int ntab=1; static constexpr bool itab=false; };
-template <> struct Traits<REBX_B200_HARMONICS>     { static constexpr bool vel=false, mass=true,  rad=false, red=true;  static constexpr int ntab=0; static constexpr bool itab=false; };
-template <> struct Traits<REBX_B200_GR_POTENTIAL>  { static constexpr bool vel=false, mass=true,  rad=false, red=true;  static constexpr int ntab=0; static constexpr bool itab=false; };
-template <> struct Traits<REBX_B200_YARKOVSKY>     { static constexpr bool vel=true,  mass=true,  rad=true,  red=false; static constexpr int ntab=9; static constexpr bool itab=true;  };
-template <> struct Traits<REBX_B200_MODIFY_ORBITS> { static constexpr bool vel=true,  mass=true,  rad=false, red=true;  static constexpr int ntab=3; static constexpr bool itab=false; };
-template <> struct Traits<REBX_B200_GAS_DAMPING>   { static constexpr bool vel=true,  mass=true,  rad=false, red=true;  static constexpr int ntab=1; static constexpr bool itab=false; };
-template <> struct Traits<REBX_B200_TYPE_I>        { static constexpr bool vel=true,  mass=true,  rad=false, red=true;  static constexpr int ntab=0; static constexpr bool itab=false; };
-template <> struct Traits<REBX_B200_CENTRAL_FORCE> { static constexpr bool vel=false, mass=true,  rad=false, red=true;  static constexpr int ntab=0; static constexpr bool itab=false; };
-template <> struct Traits<REBX_B200_LENSE_THIRRING> { static constexpr bool vel=true, mass=true,  rad=false, red=true;  static constexpr int ntab=0; static constexpr bool itab=false; };
-template <> struct Traits<REBX_B200_GAS_DF>        { static constexpr bool vel=true,  mass=true,  rad=true,  red=false; static constexpr int ntab=0; static constexpr bool itab=false; };
-template <> struct Traits<REBX_B200_EXP_MIGRATION> { static constexpr bool vel=true,  mass=true,  rad=false, red=true;  static constexpr int ntab=3; static constexpr bool itab=false; };
-
-// ---- vector loads / stores with streaming hints ------------------------------------------
-template <int V>
-__device__ __forceinline__ void ld(const double* __restrict__ p, int64_t k, bool full, double (&out)[V]) {
-    if constexpr (V == 2) {
-        if (full) {
-            const double2 t = __ldcs(reinterpret_cast<const double2*>(p + k));
-            out[0] = t.x; out[1] = t.y;
-        } else {
-            out[0] = __ldcs(p + k); out[1] = 0.0;
-        }
-    } else {
-        out[0] = __ldcs(p + k);
-    }
-}
-template <int V>
-__device__ __forceinline__ void ldi(const int32_t* __restrict__ p, int64_t k, bool full, int (&out)[V]) {
-    if constexpr (V == 2) {
-        if (full) {
-            const int2 t = __ldcs(reinterpret_cast<const int2*>(p + k));
-            out[0] = t.x; out[1] = t.y;
-        } else {
-            out[0] = __ldcs(p + k); out[1] = 2;
-        }
-    } else {
-        out[0] = __ldcs(p + k);
-    }
-}
-template <int V>
-__device__ __forceinline__ void st(double* __restrict__ p, int64_t k, bool full, const double (&v)[V]) {
-    if constexpr (V == 2) {
-        if (full) __stcs(reinterpret_cast<double2*>(p + k), make_double2(v[0], v[1]));
-        else      __stcs(p + k, v[0]);
-    } else {
-        __stcs(p + k, v[0]);
-    }
-}
-
-template <int K, int V> struct Params {
-    double t[Traits<K>::ntab > 0 ? Traits<K>::ntab : 1][V];
-    int    it[V];
-};
-
-template <int K, int V>
-__device__ __forceinline__ void load_params(const rebx_b200_effect& fx, int64_t k, bool full, Params<K, V>& q) {
-#pragma unroll
-    for (int j = 0; j < Traits<K>::ntab; j++) ld<V>(fx.tab[j], k, full, q.t[j]);
-    if constexpr (Traits<K>::itab) ldi<V>(fx.itab, k, full, q.it);
-}
+namespace rebxb {
 
 template <int K, int V, class M = IeeeMath>
 __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const Origin& org, const double* __restrict__ body, const Pre& pre,
@@ -136,28 +65,6 @@ __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const Origin& 
         lense_thirring(fx, org, body, p, a, red);
     } else if constexpr (K == REBX_B200_GAS_DF) {
         gas_dynamical_friction(fx, org, body, p, a);
-    }
-}
-
-template <int K, int NWARPS = kWarps>
-__device__ __forceinline__ void reduce_effect(Vec3 red, int e, double (*s_red)[3], double* __restrict__ partials) {
-    if constexpr (Traits<K>::red) {
-#pragma unroll
-        for (int off = 16; off > 0; off >>= 1) {
-            red.x += __shfl_down_sync(0xffffffffu, red.x, off);
-            red.y += __shfl_down_sync(0xffffffffu, red.y, off);
-            red.z += __shfl_down_sync(0xffffffffu, red.z, off);
-        }
-        const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        __syncthreads();
-        if (lane == 0) { s_red[warp][0] = red.x; s_red[warp][1] = red.y; s_red[warp][2] = red.z; }
-        __syncthreads();
-        if (threadIdx.x < 3) {
-            double s = 0.0;
-#pragma unroll
-            for (int w = 0; w < NWARPS; w++) s += s_red[w][threadIdx.x];
-            partials[((size_t)blockIdx.x*REBX_B200_MAX_EFFECTS + e)*3 + threadIdx.x] = s;
-        }
     }
 }
 
@@ -942,58 +849,14 @@ static const Combo* find_combo(const rebx_b200_effect* fx, int count) {
     return nullptr;
 }
 
-struct DevInfo { int sms; bool ok; };
-static DevInfo device_info() {
-    static thread_local int cached_dev = -1;
-    static thread_local DevInfo info = {0, false};
-    int dev = -1;
-    if (cudaGetDevice(&dev) != cudaSuccess) return {0, false};
-    if (dev != cached_dev) {
-        int sms = 0;
-        if (cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return {0, false};
-        info = {sms, true};
-        cached_dev = dev;
-    }
-    return info;
-}
-
-static int grid_for(const void* fn, int64_t work_items, int threads = kThreads, int smem = 0, int items_per_block = kThreads) {
-    const DevInfo di = device_info();
-    // resident CTAs per SM of this kernel: queried once per (kernel, launch shape) and thread
-    struct Key { const void* fn; int threads, smem; };
-    static thread_local std::vector<std::pair<Key, int>> cache;
-    int per_sm = 0;
-    for (const auto& kv : cache) if (kv.first.fn == fn && kv.first.threads == threads && kv.first.smem == smem) { per_sm = kv.second; break; }
-    if (per_sm == 0) {
-        if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, fn, threads, smem) != cudaSuccess || per_sm < 1) per_sm = 1;
-        cache.push_back({Key{fn, threads, smem}, per_sm});
-    }
-    int64_t blocks = (work_items + items_per_block - 1)/items_per_block;
-    int64_t cap = (int64_t)(di.ok ? di.sms : 148)*per_sm;
-    if (cap > kMaxBlocks) cap = kMaxBlocks - (kMaxBlocks % (di.ok ? di.sms : 148));
-    if (blocks > cap) blocks = cap;
-    if (blocks < 1) blocks = 1;
-    return (int)blocks;
-}
+// kernels_tol.cu
+bool tol_launch(const rebx_b200_pass& sub, int take, double* workspace, cudaStream_t s, int* grid_out);
 
 static bool use_tma() {
     // opt-in (REBX_B200_KERNEL=tma): measured slower than the occupancy-tuned plain sweep on B200
     // (radiation 10^7: 0.179 ms vs 0.171 ms; FP64-heavy sweeps 5-30 % slower), see DESIGN.md
     static const int mode = [] { const char* e = getenv("REBX_B200_KERNEL"); return (e && e[0] == 't') ? 1 : 0; }();
     return mode != 0;
-}
-
-static bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
-
-static bool pass_is_vectorizable(const rebx_b200_pass& P) {
-    const rebx_b200_state& s = P.st;
-    const void* ptrs[] = {s.x, s.y, s.z, s.vx, s.vy, s.vz, s.m, s.r, s.ax, s.ay, s.az};
-    for (const void* p : ptrs) if (p && !aligned16(p)) return false;
-    for (int e = 0; e < P.n_effects; e++) {
-        for (int j = 0; j < REBX_B200_MAX_TABLES; j++) if (P.fx[e].tab[j] && !aligned16(P.fx[e].tab[j])) return false;
-        if (P.fx[e].itab && (reinterpret_cast<uintptr_t>(P.fx[e].itab) & 7u)) return false;
-    }
-    return true;
 }
 
 static int check_pass(const rebx_b200_pass& P) {
@@ -1084,7 +947,10 @@ int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* str
         bool heavy = false;
         for (int j = 0; j < take; j++) if (sub.fx[j].kind >= REBX_B200_YARKOVSKY) heavy = true;
         const int vsel = (aligned && !heavy) ? 1 : 0;
-        if (aligned && use_tma() && sub.st.n >= 4*kTile) {
+        const bool want_tol = (pass->reserved & REBX_B200_PASS_TOLERANCE) && (pass->reserved & REBX_B200_PASS_SHARED_BODY);
+        if (want_tol && tol_launch(sub, take, static_cast<double*>(workspace), s, &grid)) {
+            // tolerance-mode sweep launched (kernels_tol.cu)
+        } else if (aligned && use_tma() && sub.st.n >= 4*kTile) {
             // TMA-fed ring (needs 16-byte aligned arrays)
             pass_fn fn = combo->tma;
             err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, combo->tma_smem);

@@ -1,0 +1,554 @@
+// kernels_tol.cu -- TOLERANCE-MODE sweeps: the same effects as kernels.cu, evaluated for speed instead of for
+// bit identity with the reference.  Selected per pass with REBX_B200_PASS_TOLERANCE (dispatcher:
+// REBX_B200_MATH=tolerance; device.Shard(math="tolerance")); the default stays the bit-exact build.
+//
+// What changes against forces_math.cuh (reference src/radiation_forces.c:69-98, gravitational_harmonics.c:72-224,
+// gr_potential.c:60-78, yarkovsky_effect.c:76-216, modify_orbits_forces.c:77-128, gas_damping_timescale.c:67-130,
+// type_I_migration.c:69-203, rebxtools.c:131-141):
+//   * this translation unit is compiled WITH FMA contraction (the exact build: -fmad=false);
+//   * one reciprocal square root of r^2 per particle (MUFU seed + two coupled Newton steps, <= 2 ulp) serves every
+//     power of the distance -- r^-1, r^-2, r^-4, r^-5, r^-7 by multiplication -- where the reference divides
+//     12 times and takes a square root (the exact build repeats those IEEE divisions one for one);
+//   * every other quotient is a product with a Newton reciprocal (MUFU seed + two steps, <= 1 ulp), particle-
+//     independent quotients are hoisted into per-CTA constants in shared memory;
+//   * stacked effects that refer to the same central body share the geometry and the two-body elements;
+//   * the two Rodrigues matrices of the full Yarkovsky version are applied as two rotations of the vector instead
+//     of being built and multiplied out; pow(x, 1.2) of type_I_migration is exp(1.2 log x).
+// Accuracy: a few ulp per operation instead of 0.5, i.e. ~1e-15 relative on a force vector -- two orders inside the
+// north-star tolerance (per-component relative error <= 1e-13 on the accelerations REBOUND integrates); measured
+// against the reference-compiled oracle in tests/test_gpu_parity.py::test_tolerance_mode_* and reported by
+// bench.py next to the bit-exact numbers.
+//
+// Only stacks whose effects all refer to ONE central body in PARTICLE coordinates have an instantiation here
+// (every BASELINE configuration); anything else falls back to the exact kernels.
+#include <cuda_runtime.h>
+#include <cmath>
+#include <cstdint>
+#include <cstdlib>
+#include "rebx_b200.h"
+#include "pass_common.cuh"
+#include "exact_math.cuh"       // rcp_seed / rsqrt_seed (MUFU.RCP64H / MUFU.RSQ64H)
+
+namespace rebxb {
+namespace tol {
+
+constexpr double kPi    = 3.14159265358979323846;
+constexpr double kTwoPi = 2*kPi;
+constexpr double kPi5   = kPi*kPi*kPi*kPi*kPi;
+
+// 1/b, <= 1 ulp for finite non-zero b away from the exponent limits (seed ~2^-20, two Newton steps)
+__device__ __forceinline__ double frcp(double b) {
+    double y = rcp_seed(b);
+    double e = fma(-b, y, 1.0);  y = fma(y, e, y);
+    e = fma(-b, y, 1.0);         y = fma(y, e, y);
+    return y;
+}
+// s = sqrt(x), rs = 1/sqrt(x), <= 2 ulp each (Goldschmidt: two coupled steps on g ~ sqrt x, h ~ 1/(2 sqrt x))
+__device__ __forceinline__ void fsqrt2(double x, double& s, double& rs) {
+    const double y = rsqrt_seed(x);
+    double g = x*y, h = 0.5*y;
+    double r = fma(-g, h, 0.5);  g = fma(g, r, g);  h = fma(h, r, h);
+    r = fma(-g, h, 0.5);         g = fma(g, r, g);  h = fma(h, r, h);
+    s = (x == 0.0) ? 0.0 : g;
+    rs = h + h;
+}
+__device__ __forceinline__ double fsqrt(double x) { double s, rs; fsqrt2(x, s, rs); return s; }
+__device__ __forceinline__ double frsqrt(double x) { double s, rs; fsqrt2(x, s, rs); return rs; }
+
+// x^p for a force-level (uniform) exponent, through the cheap roots where disc models put it; s1 = sqrt(x), rs1 = 1/sqrt(x)
+// are passed in when the caller has them (x = r: the distance).  Returns x^p and, in `inv`, x^-p.
+__device__ __forceinline__ double pow_uniform2(double x, double xinv, double p, double& inv) {
+    if (p == 0.0) { inv = 1.0; return 1.0; }
+    if (p == 1.0) { inv = xinv; return x; }
+    if (p == -1.0) { inv = x; return xinv; }
+    if (p == 2.0) { inv = frcp(x*x); return x*x; }
+    if (p == -2.0) { inv = x*x; return frcp(x*x); }
+    double s, rs;
+    if (p == 0.5 || p == -0.5 || p == 0.25 || p == -0.25 || p == 1.5 || p == -1.5 || p == 0.125 || p == -0.125) {
+        fsqrt2(x, s, rs);
+        if (p == 0.5) { inv = rs; return s; }
+        if (p == -0.5) { inv = s; return rs; }
+        if (p == 1.5) { inv = rs*rs*rs; return x*s; }
+        if (p == -1.5) { inv = x*s; return rs*rs*rs; }
+        double s2, rs2;
+        fsqrt2(s, s2, rs2);
+        if (p == 0.25) { inv = rs2; return s2; }
+        if (p == -0.25) { inv = s2; return rs2; }
+        double s3, rs3;
+        fsqrt2(s2, s3, rs3);
+        if (p == 0.125) { inv = rs3; return s3; }
+        inv = s3; return rs3;
+    }
+    const double v = pow(x, p);
+    inv = frcp(v);
+    return v;
+}
+
+// ---- per-CTA constants of one effect entry (shared memory; particle-independent sub-expressions) ------------
+constexpr int kC = 24;
+// common: c[0] = G, c[1] = body mass, c[2] = 1/body mass, c[kC-1] = 1/G
+// RADIATION     c[3] = G m_s (mu), c[4] = 1/c
+// HARMONICS     c[3] = 3/2 G m J2 R^2, c[4] = 5/8 G m J4 R^4 (0 without J4), c[5..13] = u, v, w
+// GR_POTENTIAL  c[3] = 6 (G m)^2/c^2
+// YARKOVSKY     c[3] = 1/c, c[4] = 3 L/(64 pi c), c[5] = 3 L/(16 pi c), c[6] = 0.5 (sb/pi^5)^(1/4) [times emissivity^(1/4) per particle], c[7] = L
+// MODIFY_ORBITS c[3] = ide_position, c[4] = ide_width
+// GAS_DAMPING   c[3] = sqrt(G M), c[4] = 1/sqrt(G M), c[5] = cs_coeff, c[6] = 1/cs_coeff, c[7] = -tau_coeff M
+// TYPE_I        c[3] = beta, c[4] = h0, c[5] = 1/h0, c[6] = sd0, c[7] = s, c[8] = dedge, c[9] = hedge,
+//               c[10] = sqrt(M^3), c[11] = sqrt(G), c[12] = (2.7 + 1.1 s)/2
+__device__ void fill_constants(const rebx_b200_effect& fx, const double* __restrict__ body, double* __restrict__ c) {
+    const double G = fx.scal[0], bm = body[REBX_B200_BODY_M];
+    c[0] = G; c[1] = bm; c[2] = 1.0/bm; c[kC - 1] = 1.0/G;
+    switch (fx.kind) {
+    case REBX_B200_RADIATION: c[3] = G*bm; c[4] = 1.0/fx.scal[1]; break;
+    case REBX_B200_HARMONICS: {
+        const double J2 = body[REBX_B200_BODY_J2], J4 = body[REBX_B200_BODY_J4], R = body[REBX_B200_BODY_REQ];
+        c[3] = 1.5*G*bm*J2*R*R; c[4] = 0.625*G*bm*J4*R*R*R*R;
+        for (int j = 0; j < 9; j++) c[5 + j] = body[REBX_B200_BODY_U + j];
+        break;
+    }
+    case REBX_B200_GR_POTENTIAL: c[3] = 6.*(G*bm)*(G*bm)/fx.scal[1]; break;
+    case REBX_B200_YARKOVSKY: {
+        const double L = fx.scal[1], cc = fx.scal[2], sb = fx.scal[3];
+        c[3] = 1.0/cc; c[4] = 3.0*L/(64.0*kPi*cc); c[5] = 3.0*L/(16.0*kPi*cc); c[6] = 0.5*sqrt(sqrt(sb/kPi5)); c[7] = L;
+        break;
+    }
+    case REBX_B200_MODIFY_ORBITS: c[3] = fx.scal[1]; c[4] = fx.scal[2]; break;
+    case REBX_B200_GAS_DAMPING: c[3] = sqrt(G*bm); c[4] = 1.0/sqrt(G*bm); c[5] = fx.scal[1]; c[6] = 1.0/fx.scal[1]; c[7] = -fx.scal[2]*bm; break;
+    case REBX_B200_TYPE_I:
+        c[3] = fx.scal[1]; c[4] = fx.scal[2]; c[5] = 1.0/fx.scal[2]; c[6] = fx.scal[3]; c[7] = fx.scal[4]; c[8] = fx.scal[5]; c[9] = fx.scal[6];
+        c[10] = sqrt(bm*bm*bm); c[11] = sqrt(G); c[12] = 0.5*(2.7 + 1.1*fx.scal[4]);
+        break;
+    default: break;
+    }
+}
+
+// Geometry of one particle relative to the central body, shared by the whole stack.
+struct Geo { double dx, dy, dz, r2, r, rinv, rinv2, dvx, dvy, dvz, rv; };
+struct Elements { double a, e, inc, sa, rsa; };       // sa = sqrt(a), rsa = 1/sqrt(a)
+
+__device__ __forceinline__ double planet_trap(double r, double dedge, double hedge) {      // src/inner_disk_edge.c:61-77
+    if (r > dedge*(1.0 + hedge)) return 1.0;
+    if (dedge*(1.0 - hedge) < r) return 5.5*cos(((dedge*(1.0 + hedge) - r)*2*kPi)/(4*hedge*dedge)) - 4.5;
+    return -10.0;
+}
+
+// Two-body elements a, e, inc relative to the central body (REBOUND's reb_orbit_from_particle_err as restated in
+// forces_math.cuh).  Two of their uses are ill conditioned on the nearly planar, nearly circular orbits of a
+// planetesimal disc: the inclination is acos(h_z/h), and the planet trap is a cosine of ~80 (a - a_edge)/a_edge --
+// both amplify the rounding of their argument by 10^2..10^3 (measured with fast reciprocals throughout: 2e-12
+// norm-wise on the pure damping force).  Those two arguments therefore follow the reference's own operation
+// sequence with IEEE operators that the compiler may not contract (__dmul_rn & co.), which makes them bit-identical
+// to the exact build's: h_z/h always, the semi-major axis only for a particle inside the trap's transition band
+// (trap_factor).  Everything else -- a elsewhere, the eccentricity, all the forces -- is well conditioned and uses the
+// tolerance arithmetic.
+__device__ __forceinline__ double xmul(double a, double b) { return __dmul_rn(a, b); }
+__device__ __forceinline__ double xadd(double a, double b) { return __dadd_rn(a, b); }
+__device__ __forceinline__ double xsub(double a, double b) { return __dadd_rn(a, -b); }
+__device__ __forceinline__ double xdot(double ax, double ay, double az, double bx, double by, double bz) {
+    return xadd(xadd(xmul(ax, bx), xmul(ay, by)), xmul(az, bz));
+}
+
+__device__ __noinline__ double exact_semimajor_axis(double G, double bm, double m, double dx, double dy, double dz, double dvx, double dvy, double dvz) {
+    const double mu = xmul(G, xadd(m, bm));
+    const double d = __dsqrt_rn(xdot(dx, dy, dz, dx, dy, dz));
+    const double v2 = xdot(dvx, dvy, dvz, dvx, dvy, dvz);
+    const double vc2 = __ddiv_rn(mu, d);
+    return __ddiv_rn(-mu, xsub(v2, xmul(2., vc2)));
+}
+
+// acos(c) for the rounded cosine c of the inclination.  Disc models live at c -> 1, where acos(c) = 2 asin(s) with
+// s = sqrt((1 - c)/2) (1 - c is exact there, Sterbenz) and the Maclaurin series of asin converges in a few terms:
+// for 1 - c < 5e-3 (inc < 0.1 rad) eight terms leave < 2e-21 s.  Anything else goes to libdevice.
+__device__ __forceinline__ double acos_near_one(double c) {
+    const double t = 1.0 - c;
+    if (!(t < 5e-3) || !(t > 0.0)) return acos(c);
+    const double s2 = 0.5*t, s = fsqrt(s2);
+    // (2k)!/(4^k (k!)^2 (2k+1)), k = 1..8
+    double p = 6435.0/557056.0;
+    p = fma(p, s2, 143.0/10240.0);
+    p = fma(p, s2, 231.0/13312.0);
+    p = fma(p, s2, 63.0/2816.0);
+    p = fma(p, s2, 35.0/1152.0);
+    p = fma(p, s2, 5.0/112.0);
+    p = fma(p, s2, 3.0/40.0);
+    p = fma(p, s2, 1.0/6.0);
+    const double as = fma(s*s2, p, s);
+    return as + as;
+}
+
+template <bool WANT_E_INC>
+__device__ __forceinline__ Elements elements(double G, double inv_G, double bm, double m, double inv_mb, const Geo& g) {
+    Elements o;
+    const double mu = G*(m + bm);
+    const double v2 = g.dvx*g.dvx + g.dvy*g.dvy + g.dvz*g.dvz;
+    const double vc2 = mu*g.rinv;
+    o.a = -mu*frcp(v2 - 2.*vc2);
+    o.e = 0.0; o.inc = 0.0; o.sa = 0.0; o.rsa = 0.0;
+    if (WANT_E_INC) {
+        const double inv_mu = inv_mb*inv_G, vd2 = v2 - vc2;        // 1/(G (m + M))
+        const double ex = inv_mu*(vd2*g.dx - g.rv*g.dvx), ey = inv_mu*(vd2*g.dy - g.rv*g.dvy), ez = inv_mu*(vd2*g.dz - g.rv*g.dvz);
+        o.e = fsqrt(ex*ex + ey*ey + ez*ez);
+        const double hx = xsub(xmul(g.dy, g.dvz), xmul(g.dz, g.dvy));
+        const double hy = xsub(xmul(g.dz, g.dvx), xmul(g.dx, g.dvz));
+        const double hz = xsub(xmul(g.dx, g.dvy), xmul(g.dy, g.dvx));
+        const double cosine = __ddiv_rn(hz, __dsqrt_rn(xdot(hx, hy, hz, hx, hy, hz)));
+        o.inc = (cosine > -1. && cosine < 1.) ? acos_near_one(cosine) : ((cosine <= -1.) ? kPi : 0.);
+        fsqrt2(o.a, o.sa, o.rsa);
+    }
+    return o;
+}
+
+// planet trap of src/inner_disk_edge.c:61-77 evaluated at the particle's semi-major axis: outside the transition band
+// it is a constant, inside it the axis is recomputed with the reference's exact operation sequence first
+__device__ __forceinline__ double trap_factor(double a, double dedge, double hedge, double G, double bm, double m, const Geo& g) {
+    const double hi = dedge*(1.0 + hedge), lo = dedge*(1.0 - hedge);
+    if (a > hi*(1.0 + 1e-12)) return 1.0;
+    if (!(a > lo*(1.0 - 1e-12))) return -10.0;
+    return planet_trap(exact_semimajor_axis(G, bm, m, g.dx, g.dy, g.dz, g.dvx, g.dvy, g.dvz), dedge, hedge);
+}
+
+// x^1.2 = (x z^2)^2 with z = x^(-1/5): single-precision seed (MUFU lg2 / ex2), two division-free Newton steps
+// z <- z (6 - x z^5)/5 in FP64 (quadratic: 1e-6 -> 3e-12 -> below eps), ~16 FP64 operations against ~150 for pow().
+__device__ __forceinline__ double pow_1p2(double x) {
+    if (!(x > 0.0)) return 0.0;
+    if (x < 1e-30) return pow(x, 1.2);                   // below the seed's comfortable single-precision range
+    double z = (double)__powf((float)x, -0.2f);
+#pragma unroll
+    for (int it = 0; it < 2; it++) {
+        const double z2 = z*z;
+        z = z*fma(-x*z2, z2*z, 6.0)*0.2;
+    }
+    const double t = x*z*z;
+    return t*t;
+}
+
+// ---- effects (each adds to `a`; `red` = signed back-reaction sum onto the body) ------------------------------
+__device__ __forceinline__ void radiation(const double* __restrict__ c, const Geo& g, double beta, Vec3& a) {
+    if (is_absent(beta)) return;
+    const double rdot = g.rv*g.rinv;
+    const double a_rad = beta*c[3]*g.rinv2;
+    const double k1 = (1. - rdot*c[4])*g.rinv;
+    a.x += a_rad*(k1*g.dx - g.dvx*c[4]);
+    a.y += a_rad*(k1*g.dy - g.dvy*c[4]);
+    a.z += a_rad*(k1*g.dz - g.dvz*c[4]);
+}
+
+__device__ __forceinline__ void harmonics(const double* __restrict__ c, const Geo& g, double m, Vec3& a, Vec3& red) {
+    const double du = c[5]*g.dx + c[6]*g.dy + c[7]*g.dz;
+    const double dv = c[8]*g.dx + c[9]*g.dy + c[10]*g.dz;
+    const double dw = c[11]*g.dx + c[12]*g.dy + c[13]*g.dz;
+    const double ct = dw*g.rinv, c2 = ct*ct;
+    const double r5 = g.rinv2*g.rinv2*g.rinv;
+    const double f1 = c[3]*r5, f2 = 5.0*c2 - 1.0;
+    double au = f1*f2*du, av = f1*f2*dv, aw = f1*(f2 - 2.0)*dw;
+    if (c[4] != 0.0) {
+        const double g1 = c[4]*r5*g.rinv2, g2 = 63.0*c2*c2 - 42.0*c2 + 3.0;
+        au += g1*g2*du; av += g1*g2*dv; aw += g1*(g2 - 28.0*c2 + 12.0)*dw;
+    }
+    const double ax = c[5]*au + c[8]*av + c[11]*aw;
+    const double ay = c[6]*au + c[9]*av + c[12]*aw;
+    const double az = c[7]*au + c[10]*av + c[13]*aw;
+    a.x += ax; a.y += ay; a.z += az;
+    const double fac = m*c[2];
+    red.x -= fac*ax; red.y -= fac*ay; red.z -= fac*az;
+}
+
+__device__ __forceinline__ void gr_potential(const double* __restrict__ c, const Geo& g, double m, Vec3& a, Vec3& red) {
+    const double prefac = c[3]*g.rinv2*g.rinv2;
+    a.x -= prefac*g.dx; a.y -= prefac*g.dy; a.z -= prefac*g.dz;
+    const double mr = m*c[2]*prefac;
+    red.x += mr*g.dx; red.y += mr*g.dy; red.z += mr*g.dz;
+}
+
+struct YarkParams { double density, rot_period, Gamma, albedo, emissivity, k, sx, sy, sz; };
+
+// v' = cos v + sin (k x v) + (1 - cos)(k.v) k : rotation of v about the UNIT vector k (sin < 0 rotates the other way)
+__device__ __forceinline__ void rotate(double kx, double ky, double kz, double cs, double sn, double& vx, double& vy, double& vz) {
+    const double cx = ky*vz - kz*vy, cy = kz*vx - kx*vz, cz = kx*vy - ky*vx;
+    const double kd = (1.0 - cs)*(kx*vx + ky*vy + kz*vz);
+    const double nx = cs*vx + sn*cx + kd*kx, ny = cs*vy + sn*cy + kd*ky, nz = cs*vz + sn*cz + kd*kz;
+    vx = nx; vy = ny; vz = nz;
+}
+
+__device__ __forceinline__ void yarkovsky(const double* __restrict__ c, const Geo& g, double m, double radius, const YarkParams& yp, int code, Vec3& a) {
+    if (code == 2 || radius == 0) return;
+    const double q = 1.0 - yp.albedo, inv_c = c[3];
+    const double k1 = (1.0 - g.rv*inv_c*g.rinv)*g.rinv;
+    double i0 = k1*g.dx - g.dvx*inv_c, i1 = k1*g.dy - g.dvy*inv_c, i2 = k1*g.dz - g.dvz*inv_c;
+    const double geom = q*frcp(radius*yp.density*g.r2);          // (1 - A)/(R rho r^2)
+    if (code != 0) {
+        const double mag = c[4]*geom;
+        if (code == 1) a.y += mag*i0; else a.x += mag*i1;        // Y[1][0] = 1 resp. Y[0][1] = 1 (yarkovsky_effect.c:109-121)
+        return;
+    }
+    const double mag = c[5]*yp.k*geom;
+    // orbital period: n = sign(a) sqrt(|mu/a^3|), P = 2 pi/n; only sqrt(P) enters (NaN for an unbound orbit, like the reference)
+    const double mu = c[0]*(m + c[1]);
+    const double v2 = g.dvx*g.dvx + g.dvy*g.dvy + g.dvz*g.dvz;
+    const double inv_a = -(v2 - 2.*mu*g.rinv)*frcp(mu);
+    const double n = copysign(fsqrt(fabs(mu*inv_a*inv_a*inv_a)), inv_a);
+    const double sqrtP = frsqrt(n*(1.0/kTwoPi));
+    const double inv_gamma = fabs(frcp(yp.Gamma));
+    // X = 0.5 (sb eps/pi^5)^(1/4) sqrt(P_x/Gamma^2) ((1-A) L/r^2)^(3/4)
+    const double fsq = fsqrt(c[7]*q)*g.rinv;
+    const double flux = fsq*fsqrt(fsq);
+    const double pre = c[6]*fsqrt(fsqrt(yp.emissivity))*inv_gamma*flux;
+    const double tanPhi = frcp(1.0 + pre*fsqrt(yp.rot_period));
+    const double tanEps = frcp(1.0 + pre*sqrtP);
+    const double cphi = frsqrt(1.0 + tanPhi*tanPhi), sphi = tanPhi*cphi;
+    const double ceps = frsqrt(1.0 + tanEps*tanEps), seps = tanEps*ceps;
+    const double inv_s = frsqrt(yp.sx*yp.sx + yp.sy*yp.sy + yp.sz*yp.sz);
+    const double hx = g.dy*g.dvz - g.dz*g.dvy, hy = g.dz*g.dvx - g.dx*g.dvz, hz = g.dx*g.dvy - g.dy*g.dvx;
+    const double inv_h = frsqrt(hx*hx + hy*hy + hz*hz);
+    rotate(hx*inv_h, hy*inv_h, hz*inv_h, ceps, -seps, i0, i1, i2);       // Ryh = cos I - sin [h]x + (1 - cos) h h^T   (:176-182)
+    rotate(yp.sx*inv_s, yp.sy*inv_s, yp.sz*inv_s, cphi, sphi, i0, i1, i2);   // Rys = cos I + sin [s]x + (1 - cos) s s^T   (:170-175)
+    a.x += mag*i0; a.y += mag*i1; a.z += mag*i2;
+}
+
+__device__ __forceinline__ Vec3 modify_orbits(const double* __restrict__ c, int flags, const Geo& g, const Elements& o, double m,
+                                              double tau_a, double tau_e, double tau_inc) {
+    double invtau_a = 0.0;
+    if (!is_absent(tau_a)) {
+        invtau_a = frcp(tau_a);
+        if (flags & REBX_B200_FLAG_TRAP) invtau_a *= trap_factor(o.a, c[3], c[4], c[0], c[1], m, g);
+    }
+    const double ite = is_absent(tau_e) ? 0.0 : frcp(tau_e), iti = is_absent(tau_inc) ? 0.0 : frcp(tau_inc);
+    const double prefac = 2.*g.rv*g.rinv2*ite;
+    Vec3 f;
+    f.x = 0.5*g.dvx*invtau_a + prefac*g.dx;
+    f.y = 0.5*g.dvy*invtau_a + prefac*g.dy;
+    f.z = 0.5*g.dvz*invtau_a + prefac*g.dz + 2.*g.dvz*iti;
+    return f;
+}
+
+__device__ __forceinline__ Vec3 gas_damping(const double* __restrict__ c, const Geo& g, const Elements& o, double m, double d_factor) {
+    Vec3 f = {0.0, 0.0, 0.0};
+    if (is_absent(d_factor)) return f;
+    const double vk = c[3]*o.rsa;                         // sqrt(G M/a)
+    const double v = fsqrt(o.e*o.e + o.inc*o.inc)*vk;
+    double s4, rs4;
+    fsqrt2(o.sa, s4, rs4);                                // a^(1/4)
+    const double cs = c[5]*rs4;
+    const double voc = v*s4*c[6];                         // v/cs
+    double coeff = 1.;
+    if (!(v <= cs)) coeff = (o.inc < cs*o.sa*c[4]) ? voc*voc*voc : voc*voc*voc*voc;
+    // tau_e = -tau_coeff d a^2 (M/m) coeff ; tau_inc = 2 tau_e
+    const double ite = m*frcp(c[7]*d_factor*o.a*o.a*coeff);
+    const double prefac = 2.*g.rv*g.rinv2*ite;
+    f.x = prefac*g.dx; f.y = prefac*g.dy; f.z = prefac*g.dz + g.dvz*ite;
+    return f;
+}
+
+__device__ __forceinline__ Vec3 type_I_migration(const double* __restrict__ c, const Geo& g, const Elements& o, double m) {
+    double inv_hr, inv_sd;
+    const double hr = pow_uniform2(g.r, g.rinv, c[3], inv_hr);              // r^beta   (h = h0 r2^(beta/2))
+    const double h = c[4]*hr, inv_h = c[5]*inv_hr, h2 = h*h;
+    const double eh = o.e*inv_h, ih = o.inc*inv_h;
+    const double rs = pow_uniform2(g.r, g.rinv, c[7], inv_sd);              // r^s ; sd = sd0 r^-s
+    (void)rs;
+    const double sd = c[6]*inv_sd;
+    // 1/wave = m sd sqrt(a G)/(sqrt(M^3) h^4)
+    const double inv_wave = m*sd*c[11]*o.sa*frcp(c[10]*h2*h2);
+    const double x1 = eh*(1.0/2.25), x2 = eh*(1.0/2.84), x3 = eh*(1.0/2.02);
+    const double x22 = x2*x2, x32 = x3*x3;
+    const double p12 = pow_1p2(x1);
+    const double Pe = (1. + p12 + x22*x22*x22)*frcp(1. - x32*x32);
+    const double ih2 = ih*ih;
+    const double corr = 0.070*ih + 0.085*ih2*ih2 - 0.080*eh*ih2;
+    const double invtau_mig = trap_factor(o.a, c[8], c[9], c[0], c[1], m, g)*inv_wave*c[12]*h2*frcp(Pe + (Pe < 0.0 ? -corr : corr));
+    const double ite = 0.780*inv_wave*frcp(1. - 0.14*eh*eh + 0.06*eh*eh*eh + 0.18*eh*ih2);
+    const double iti = 0.544*inv_wave*frcp(1. - 0.30*ih2 + 0.24*ih2*ih + 0.14*eh*eh*ih);
+    const double prefac = -2.*g.rv*g.rinv2*ite;
+    Vec3 f;
+    f.x = -g.dvx*invtau_mig + prefac*g.dx;
+    f.y = -g.dvy*invtau_mig + prefac*g.dy;
+    f.z = -g.dvz*invtau_mig + prefac*g.dz - 2.*g.dvz*iti;
+    return f;
+}
+
+template <int K> __host__ __device__ constexpr bool is_damping() { return K == REBX_B200_MODIFY_ORBITS || K == REBX_B200_GAS_DAMPING || K == REBX_B200_TYPE_I; }
+
+template <int K, int V>
+__device__ __forceinline__ void apply(const rebx_b200_effect& fx, const double* __restrict__ c, const Geo& g, const Elements& o, double mr,
+                                      double m, double rad, const Params<K, V>& q, int v, Vec3& a, Vec3& red) {
+    if constexpr (K == REBX_B200_RADIATION) radiation(c, g, q.t[0][v], a);
+    else if constexpr (K == REBX_B200_HARMONICS) harmonics(c, g, m, a, red);
+    else if constexpr (K == REBX_B200_GR_POTENTIAL) gr_potential(c, g, m, a, red);
+    else if constexpr (K == REBX_B200_YARKOVSKY) {
+        const YarkParams yp{q.t[0][v], q.t[1][v], q.t[2][v], q.t[3][v], q.t[4][v], q.t[5][v], q.t[6][v], q.t[7][v], q.t[8][v]};
+        yarkovsky(c, g, m, rad, yp, q.it[v], a);
+    } else if constexpr (is_damping<K>()) {
+        // the damping effects of a stack share one rebx_com_force tail (pass_kernel_tol): their forces are summed in `a`
+        // here, which the caller hands in as a separate accumulator
+        Vec3 f;
+        if constexpr (K == REBX_B200_MODIFY_ORBITS) f = modify_orbits(c, fx.flags, g, o, m, q.t[0][v], q.t[1][v], q.t[2][v]);
+        else if constexpr (K == REBX_B200_GAS_DAMPING) f = gas_damping(c, g, o, m, q.t[0][v]);
+        else f = type_I_migration(c, g, o, m);
+        a.x += f.x; a.y += f.y; a.z += f.z;
+        (void)mr; (void)red;
+    }
+}
+
+// CTA geometry per stack class (tools/tol_variants.sh sweeps them on the GPU): threads per CTA and resident CTAs per
+// SM asked of the register allocator.  "light" = the streaming stacks (radiation, gr_potential, J2/J4), "heavy" =
+// the ones with transcendentals (yarkovsky, damping trio).
+#ifndef REBXB_TOL_LIGHT_THREADS
+#define REBXB_TOL_LIGHT_THREADS 256
+#endif
+#ifndef REBXB_TOL_LIGHT_BLOCKS
+#define REBXB_TOL_LIGHT_BLOCKS 2
+#endif
+#ifndef REBXB_TOL_YARK_THREADS
+#define REBXB_TOL_YARK_THREADS 256
+#endif
+#ifndef REBXB_TOL_YARK_BLOCKS
+#define REBXB_TOL_YARK_BLOCKS 3
+#endif
+#ifndef REBXB_TOL_TRIO_THREADS
+#define REBXB_TOL_TRIO_THREADS 256
+#endif
+#ifndef REBXB_TOL_TRIO_BLOCKS
+#define REBXB_TOL_TRIO_BLOCKS 2
+#endif
+template <int K0, int K1, int K2>
+__host__ __device__ constexpr bool trio_stack() { return K0 >= REBX_B200_MODIFY_ORBITS || K1 >= REBX_B200_MODIFY_ORBITS || K2 >= REBX_B200_MODIFY_ORBITS; }
+template <int K0, int K1, int K2>
+__host__ __device__ constexpr bool yark_stack() { return !trio_stack<K0, K1, K2>() && (K0 == REBX_B200_YARKOVSKY || K1 == REBX_B200_YARKOVSKY || K2 == REBX_B200_YARKOVSKY); }
+template <int K0, int K1, int K2>
+__host__ __device__ constexpr int tol_blocks() {
+    return trio_stack<K0, K1, K2>() ? REBXB_TOL_TRIO_BLOCKS : (yark_stack<K0, K1, K2>() ? REBXB_TOL_YARK_BLOCKS : REBXB_TOL_LIGHT_BLOCKS);
+}
+template <int K0, int K1, int K2>
+__host__ __device__ constexpr int tol_threads() {
+    return trio_stack<K0, K1, K2>() ? REBXB_TOL_TRIO_THREADS : (yark_stack<K0, K1, K2>() ? REBXB_TOL_YARK_THREADS : REBXB_TOL_LIGHT_THREADS);
+}
+
+template <int V, int K0, int K1, int K2>
+__global__ void __launch_bounds__(tol_threads<K0, K1, K2>(), tol_blocks<K0, K1, K2>())
+pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ partials) {
+    constexpr bool VEL  = Traits<K0>::vel  || Traits<K1>::vel  || Traits<K2>::vel;
+    constexpr bool MASS = Traits<K0>::mass || Traits<K1>::mass || Traits<K2>::mass;
+    constexpr bool RAD  = Traits<K0>::rad  || Traits<K1>::rad  || Traits<K2>::rad;
+    constexpr bool DAMP = is_damping<K0>() || is_damping<K1>() || is_damping<K2>();
+    constexpr bool EINC = K0 == REBX_B200_GAS_DAMPING || K1 == REBX_B200_GAS_DAMPING || K2 == REBX_B200_GAS_DAMPING ||
+                          K0 == REBX_B200_TYPE_I || K1 == REBX_B200_TYPE_I || K2 == REBX_B200_TYPE_I;
+    constexpr int T = tol_threads<K0, K1, K2>(), W = T/32;
+    __shared__ double s_c[3][kC];
+    __shared__ double s_org[8];
+    __shared__ double s_red[W][3];
+    if (threadIdx.x < P.n_effects) fill_constants(P.fx[threadIdx.x], P.fx[threadIdx.x].body, s_c[threadIdx.x]);
+    if (threadIdx.x < 8) s_org[threadIdx.x] = P.fx[0].body[threadIdx.x];
+    __syncthreads();
+    const long long b0 = (long long)s_org[0];
+    const double ox = s_org[REBX_B200_BODY_X], oy = s_org[REBX_B200_BODY_X+1], oz = s_org[REBX_B200_BODY_X+2];
+    Vec3 red0 = {0., 0., 0.}, red1 = {0., 0., 0.}, red2 = {0., 0., 0.};
+
+    const int64_t n = P.st.n;
+    const int64_t ntiles = (n + V - 1)/V;
+    const int64_t stride = (int64_t)gridDim.x*T;
+    for (int64_t t = (int64_t)blockIdx.x*T + threadIdx.x; t < ntiles; t += stride) {
+        const int64_t k = t*V;
+        const bool full = (k + V <= n);
+        double x[V], y[V], z[V], vx[V], vy[V], vz[V], m[V], r[V], ax[V], ay[V], az[V];
+        ld<V>(P.st.x, k, full, x); ld<V>(P.st.y, k, full, y); ld<V>(P.st.z, k, full, z);
+        if constexpr (VEL)  { ld<V>(P.st.vx, k, full, vx); ld<V>(P.st.vy, k, full, vy); ld<V>(P.st.vz, k, full, vz); }
+        if constexpr (MASS) { ld<V>(P.st.m, k, full, m); }
+        if constexpr (RAD)  { ld<V>(P.st.r, k, full, r); }
+        ld<V>(P.st.ax, k, full, ax); ld<V>(P.st.ay, k, full, ay); ld<V>(P.st.az, k, full, az);
+        Params<K0, V> q0; Params<K1, V> q1; Params<K2, V> q2;
+        load_params<K0, V>(P.fx[0], k, full, q0);
+        if constexpr (K1 != 0) load_params<K1, V>(P.fx[1], k, full, q1);
+        if constexpr (K2 != 0) load_params<K2, V>(P.fx[2], k, full, q2);
+#pragma unroll
+        for (int v = 0; v < V; v++) {
+            if (v > 0 && !full) break;
+            if (P.st.index_base + k + v == b0) continue;            // the central body itself
+            Geo g;
+            g.dx = x[v] - ox; g.dy = y[v] - oy; g.dz = z[v] - oz;
+            g.r2 = g.dx*g.dx + g.dy*g.dy + g.dz*g.dz;
+            fsqrt2(g.r2, g.r, g.rinv);
+            g.rinv2 = g.rinv*g.rinv;
+            if constexpr (VEL) {
+                g.dvx = vx[v] - s_org[REBX_B200_BODY_VX]; g.dvy = vy[v] - s_org[REBX_B200_BODY_VX+1]; g.dvz = vz[v] - s_org[REBX_B200_BODY_VX+2];
+                g.rv = g.dx*g.dvx + g.dy*g.dvy + g.dz*g.dvz;
+            } else { g.dvx = g.dvy = g.dvz = g.rv = 0.0; }
+            const double mp = MASS ? m[v] : 0.0, rp = RAD ? r[v] : 0.0;
+            Elements o = {0., 0., 0., 0., 0.};
+            double mr = 0.0;
+            if constexpr (DAMP) {
+                const double inv_mb = frcp(s_c[0][1] + mp);         // 1/(M + m): serves mu^-1 and the mass ratio
+                o = elements<EINC>(s_c[0][0], s_c[0][kC - 1], s_c[0][1], mp, inv_mb, g);
+                mr = mp*inv_mb;
+            }
+            Vec3 a = {ax[v], ay[v], az[v]};
+            Vec3 fd = {0., 0., 0.};                                 // sum of the damping forces of the stack
+            apply<K0, V>(P.fx[0], s_c[0], g, o, mr, mp, rp, q0, v, is_damping<K0>() ? fd : a, red0);
+            if constexpr (K1 != 0) apply<K1, V>(P.fx[1], s_c[1], g, o, mr, mp, rp, q1, v, is_damping<K1>() ? fd : a, red1);
+            if constexpr (K2 != 0) apply<K2, V>(P.fx[2], s_c[2], g, o, mr, mp, rp, q2, v, is_damping<K2>() ? fd : a, red2);
+            if constexpr (DAMP) {
+                // rebx_com_force, PARTICLE coordinates (src/rebxtools.c:131-141), once for the summed force:
+                // p.a += f - mr f ; body.a -= mr f with mr = m/(M + m).  The back-reaction of the whole stack is
+                // carried by its first damping effect's sum (the host adds the effects' sums to the body anyway).
+                const double kx = mr*fd.x, ky = mr*fd.y, kz = mr*fd.z;
+                a.x += fd.x - kx; a.y += fd.y - ky; a.z += fd.z - kz;
+                Vec3& red = is_damping<K0>() ? red0 : (is_damping<K1>() ? red1 : red2);
+                red.x -= kx; red.y -= ky; red.z -= kz;
+            }
+            ax[v] = a.x; ay[v] = a.y; az[v] = a.z;
+        }
+        st<V>(P.st.ax, k, full, ax); st<V>(P.st.ay, k, full, ay); st<V>(P.st.az, k, full, az);
+    }
+    reduce_effect<K0, W>(red0, 0, s_red, partials);
+    reduce_effect<K1, W>(red1, 1, s_red, partials);
+    reduce_effect<K2, W>(red2, 2, s_red, partials);
+}
+
+typedef void (*tol_fn)(const rebx_b200_pass, double*);
+struct TolCombo { int k[3]; tol_fn fn[2]; int threads; };
+#define REBXB_TCOMBO(a, b, c) { {a, b, c}, { pass_kernel_tol<1, a, b, c>, pass_kernel_tol<2, a, b, c> }, tol_threads<a, b, c>() },
+static const TolCombo kTolCombos[] = {
+    REBXB_TCOMBO(1,0,0) REBXB_TCOMBO(2,0,0) REBXB_TCOMBO(3,0,0) REBXB_TCOMBO(4,0,0) REBXB_TCOMBO(5,0,0) REBXB_TCOMBO(6,0,0) REBXB_TCOMBO(7,0,0)
+    REBXB_TCOMBO(2,3,0) REBXB_TCOMBO(3,2,0) REBXB_TCOMBO(4,3,0) REBXB_TCOMBO(3,4,0) REBXB_TCOMBO(1,3,0) REBXB_TCOMBO(3,1,0)
+    REBXB_TCOMBO(7,6,5) REBXB_TCOMBO(5,6,7)
+};
+
+}  // namespace tol
+
+// Launches the tolerance-mode sweep of `sub` (effects 0..take-1, all referring to the same central body in PARTICLE
+// coordinates).  Returns false when the stack has no tolerance instantiation (the caller then uses the exact
+// kernels); on true *grid_out is the grid (the back-reaction partials are laid out as by pass_kernel).
+bool tol_launch(const rebx_b200_pass& sub, int take, double* workspace, cudaStream_t s, int* grid_out) {
+    if (take < 1 || take > 3) return false;
+    for (int j = 0; j < take; j++) if (sub.fx[j].flags & REBX_B200_FLAG_BARYCENTRIC) return false;
+    const tol::TolCombo* combo = nullptr;
+    for (const tol::TolCombo& c : tol::kTolCombos) {
+        bool ok = true;
+        for (int j = 0; j < 3; j++) if (c.k[j] != (j < take ? sub.fx[j].kind : 0)) ok = false;
+        if (ok) { combo = &c; break; }
+    }
+    if (!combo) return false;
+    bool heavy = false;
+    for (int j = 0; j < take; j++) if (sub.fx[j].kind >= REBX_B200_YARKOVSKY) heavy = true;
+    // two particles per thread (double2 access) for the streaming stacks, one for the register-heavy ones;
+    // REBX_B200_TOL_V=1|2 overrides (tuning)
+    static const int forced = [] { const char* e = getenv("REBX_B200_TOL_V"); return e ? atoi(e) : 0; }();
+    // REBX_B200_TOL_GRID=full: one tile per thread (as many CTAs as it takes, up to the partials' capacity) instead of
+    // a resident grid with a grid-stride loop: the hardware scheduler then balances the tail of a short heavy sweep
+    static const int full_grid = [] { const char* e = getenv("REBX_B200_TOL_GRID"); return (e && e[0] == 'f') ? 1 : 0; }();
+    // Measured (tools/tol_sweep.sh, profiles/r02_tol_variants.txt): the streaming stacks want two particles per thread
+    // (double2 access) and all 128 registers -- 256 x 2 CTAs: J2/J4 (+) gr_potential 0.134 ms against 0.165 with one
+    // particle per thread at 80 registers; the stacks with transcendentals want one particle per thread.
+    int vsel = (pass_is_vectorizable(sub) && !heavy) ? 1 : 0;
+    if (forced == 1) vsel = 0;
+    if (forced == 2 && pass_is_vectorizable(sub)) vsel = 1;
+    const int V = vsel ? 2 : 1;
+    tol::tol_fn fn = combo->fn[vsel];
+    const int64_t tiles = (sub.st.n + V - 1)/V;
+    int grid = grid_for(reinterpret_cast<const void*>(fn), tiles, combo->threads, 0, combo->threads);
+    if (full_grid) { const int64_t want = (tiles + combo->threads - 1)/combo->threads; grid = (int)(want < kMaxBlocks ? want : kMaxBlocks); }
+    fn<<<grid, combo->threads, 0, s>>>(sub, workspace);
+    *grid_out = grid;
+    return true;
+}
+
+}  // namespace rebxb

@@ -68,9 +68,13 @@ def spin_frame(Omega):
 class Shard:
     """Particles [lo, hi) of a workload, resident on `device`, with `exec_order` effects."""
 
-    def __init__(self, w, exec_order, device, lo=0, hi=None, coordinates="PARTICLE", acc0=None, index_base=None, standalone=False):
+    def __init__(self, w, exec_order, device, lo=0, hi=None, coordinates="PARTICLE", acc0=None, index_base=None, standalone=False,
+                 math="exact"):
         import torch
         self.standalone = standalone        # the whole ensemble is this one shard: evaluate() runs no collective
+        if math not in ("exact", "tolerance"):
+            raise ValueError("math must be 'exact' (bit-identical to the reference where + - * / sqrt) or 'tolerance' (kernels_tol.cu)")
+        self.math = math
         self.torch = torch
         self.lib = lib = _lib.load()
         lib.rebx_b200_launch_pass.restype = c_int
@@ -175,7 +179,8 @@ class Shard:
         for k in ("x", "y", "z", "vx", "vy", "vz", "m", "r", "ax", "ay", "az"):
             setattr(P.st, k, self.state[k].data_ptr())
         P.n_effects = len(self.kinds)
-        P.reserved = 1          # REBX_B200_PASS_SHARED_BODY: every effect of a Shard refers to the central body (index 0)
+        P.reserved = 1 | (2 if self.math == "tolerance" else 0)   # REBX_B200_PASS_SHARED_BODY (every effect of a Shard refers to the
+                                                                  # central body, index 0) | REBX_B200_PASS_TOLERANCE
         for e, kind in enumerate(self.kinds):
             fx = P.fx[e]
             fx.kind, fx.flags = kind, self.flags[e]

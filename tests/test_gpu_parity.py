@@ -347,7 +347,20 @@ def test_config5_full_size_centre_of_mass_frames(built, coordinates):
     want0, _ = oracle.port_apply(w, TRIO[::-1], None, coordinates, com="linear")
     got0 = _com_device(w, TRIO, coordinates, None)
     e0 = errors(got0, want0, skip=(0,)) if coordinates == "BARYCENTRIC" else errors(got0, want0)
-    guard(f"com_frames_1e6/{coordinates}/zero", e0, frac=fr)
+    if coordinates == "JACOBI":
+        guard(f"com_frames_1e6/{coordinates}/zero", e0, frac=fr)
+    else:
+        # BARYCENTRIC, pure force: every particle receives the SAME shift -sum_i (m_i/M) f_i, which the star's own term
+        # dominates -- the star sits 3e-8 AU from the barycentre, so its force carries the 10^6 roundings of the
+        # reference's sequential centre-of-mass fold (reproduced by the oracle, not by the device's tree sum).  The
+        # disagreement is therefore ONE 3-vector, the same on every particle (~9e-14 of |a|): norm-wise inside the
+        # tolerance, per component meaningless (2/3 of all components sit above 1e-13 because of it).  Asserted as
+        # such: norm-wise <= 1e-13, and with the common shift removed every particle agrees to 1e-15 of |a|.
+        guard(f"com_frames_1e6/{coordinates}/zero", e0, frac=1.0)
+        d = np.array(got0)[:, 1:] - np.array(want0)[:, 1:]
+        common = np.median(d, axis=1, keepdims=True)
+        scale = np.max(np.abs(np.array(want0)[:, 1:]), axis=0)
+        assert np.max(np.abs(d - common)/scale) <= 1e-15, float(np.max(np.abs(d - common)/scale))
 
 
 @pytest.mark.parametrize("case", ["lead_0.999_crosses_binade", "exact_ties", "massless_in_front", "tiny_masses_power_of_two_lead",
@@ -737,6 +750,63 @@ def test_fused_leapfrog_step_equals_separate_sweeps(built, which):
         # follow the grid, and the two kernels run different grids -> last-bit differences in the
         # body's kick.  Everything else is the same arithmetic.
         _assert_trajectories_agree(pa, pb, tol=1e-11)
+
+
+# ---- tolerance-mode arithmetic (kernels_tol.cu): FMA, shared reciprocals; default stays bit-exact -------------
+TOL_CASES = {
+    "debris_disk": (["radiation_forces"], {}),
+    "circumplanetary_ring": (["gravitational_harmonics", "gr_potential"], {"tilted": True, "massive": True}),
+    "asteroid_ensemble": (["yarkovsky_effect", "gr_potential"], {}),
+    "planetesimal_disk": (TRIO, {}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(TOL_CASES))
+@pytest.mark.parametrize("base", ["zero", "gravity"])
+def test_tolerance_mode_against_the_reference(built, monkeypatch, name, base):
+    """REBX_B200_MATH=tolerance through the drop-in call, against the reference's own loops: the north-star bar
+    (<= 1e-13) norm-wise on the pure force AND on the gravity base, the per-component picture pinned by the
+    recorded guards.  The kernels must really be the tolerance ones (results differ from the exact build's)."""
+    from reboundx_b200 import workloads
+    add, kw = TOL_CASES[name]
+    w = getattr(workloads, name)(200001, **kw)
+    acc0 = acc_variants(w, 31)[base]
+    want, br = oracle_acc(w, add, acc0)
+    exact, _ = device_acc(w, add, acc0)
+    monkeypatch.setenv("REBX_B200_MATH", "tolerance")
+    got, _ = device_acc(w, add, acc0)
+    assert not errors(got, exact)["bit_identical"], "REBX_B200_MATH=tolerance did not select the tolerance kernels"
+    e = errors(got, want, skip=(0,))
+    guard(f"tolerance_mode/{name}/{base}", e, frac=2e-5)
+    # the central body: back-reaction sums against the long-double sum of the oracle's terms
+    reducing = [f for f in add if f in br]
+    if reducing:
+        a0 = [0.0, 0.0, 0.0] if acc0 is None else [acc0[k][0] for k in range(3)]
+        exact0 = np.array(a0) + sum(br[f][:3] for f in reducing)
+        scale = sum(br[f][3:] for f in reducing) + np.abs(a0)
+        for k in range(3):
+            assert abs(got[k][0] - exact0[k]) <= 1e-12*scale[k] + 1e-300, (k, got[k][0], exact0[k], scale[k])
+
+
+def test_tolerance_mode_resident_full_size(built):
+    """device.Shard(math="tolerance") at the configurations' full sizes: finite everywhere, and within the tolerance of
+    the bit-exact sweep on every particle (norm-wise; the exact sweep itself is pinned to the oracle above)."""
+    import torch
+    from reboundx_b200 import device, workloads
+    for name, (n, add, _) in FULL.items():
+        w = getattr(workloads, name)(n)
+        acc0 = workloads.gravity_like_acc(w, np.random.default_rng(98))
+        res = {}
+        for math in ("exact", "tolerance"):
+            sh = device.Shard(w, add[::-1], "cuda:0", acc0=acc0, math=math, standalone=True)
+            sh.evaluate()
+            torch.cuda.synchronize()
+            res[math] = sh.acc()
+            del sh
+        e = errors(res["tolerance"], res["exact"])
+        assert all(np.isfinite(a).all() for a in res["tolerance"])
+        assert e["max_normwise"] <= TOL, (name, e)
+        assert not e["bit_identical"], name
 
 
 # ---- BASELINE.json full sizes: size-independent properties ---------------------------------------------
