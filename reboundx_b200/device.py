@@ -160,6 +160,11 @@ class Shard:
         self.backreaction = torch.zeros((len(self.kinds), 3), dtype=torch.float64, device=self.device)
         self.workspace = torch.empty(lib.rebx_b200_workspace_bytes(), dtype=torch.uint8, device=self.device)
         self.launches = 0
+        # The replicated body records are re-broadcast from their owner only when they may have changed (construction,
+        # a stepping call that moves the body on its owner only, mark_bodies_stale()): a loop of force evaluations over a
+        # fixed state runs NO collective for a stack without back-reaction.  Every rank makes the same sequence of calls,
+        # so the flag agrees across ranks.
+        self._bodies_stale = True
         if coordinates != "PARTICLE":
             if len(self.kinds) > 3:
                 raise ValueError("at most 3 stacked effects in a centre-of-mass frame")
@@ -207,6 +212,11 @@ class Shard:
         """Active-body state broadcast (NCCL over NVLink when a process group is up)."""
         if not self.standalone:
             sharding.broadcast_bodies(self.bodies, src=src, group=group)
+        self._bodies_stale = False
+
+    def mark_bodies_stale(self):
+        """The owner's copy of a body record was changed from outside (every rank must call this at the same point)."""
+        self._bodies_stale = True
 
     def launch(self, stream=None):
         """One force evaluation of the shard: a += sum of the stacked effects (asynchronous)."""
@@ -306,7 +316,8 @@ class Shard:
             return k
         if self.coordinates != "PARTICLE":
             return self._evaluate_com(group)
-        self.sync_bodies(group)
+        if self._bodies_stale:
+            self.sync_bodies(group)
         k = self.launch()
         if any(kind != 1 and kind != 4 for kind in self.kinds):
             self.reduce_backreaction(group)
