@@ -280,6 +280,23 @@ int rebx_b200_unpack_aos(const void* aos, const rebx_b200_aos_layout* layout, co
 int rebx_b200_pack_acc_aos(void* aos, const rebx_b200_aos_layout* layout, const rebx_b200_state* st,
                            void* stream, int* launches);
 
+/* ---- the host dispatcher's knobs and counters (reboundx_b200/csrc/dispatch.cpp) ------------------------------------
+ * Environment, read when an extras' device context is created (first force evaluation):
+ *   REBX_B200_DEVICE=<ordinal>           primary device (default 0)
+ *   REBX_B200_DEVICES=all|<count>|<list> devices a large PARTICLE-frame segment is split over by index range: one
+ *                                        process, one host thread, per-device streams; parameter tables sharded the
+ *                                        same way; back-reaction sums added on the host in index order
+ *   REBX_B200_MULTI_MIN=<particles>      smallest ensemble worth splitting (default 2^20)
+ *   REBX_B200_MATH=tolerance             REBX_B200_PASS_TOLERANCE for every pass
+ *   REBX_B200_CHUNK, REBX_B200_ZEROCOPY_MAX, REBX_B200_PARANOID   pipeline chunk, zero-copy threshold, rebuild tables every call */
+struct rebx_extras;
+struct rebx_force;
+/* Counters of the host-facing path: {calls, kernel launches, H2D bytes, D2H bytes, table builds}. */
+int rebx_b200_get_stats(struct rebx_extras* rebx, uint64_t out[5]);
+/* Builds (on the host, without touching a device) SoA table `index` of `force` into out[0..cap); index -1 = the int
+ * table, -2 = the body index list.  Returns the number of elements, or -1. */
+int64_t rebx_b200_host_table(struct rebx_extras* rebx, struct rebx_force* force, int index, double* out, int64_t cap);
+
 #ifdef __cplusplus
 }
 #endif

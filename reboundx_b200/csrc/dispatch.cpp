@@ -81,11 +81,13 @@ struct ForceTables {
     int kind = 0;
     std::uint64_t gen = 0, epoch = 0;
     size_t N = 0;
-    bool valid = false, uploaded = false;
+    bool valid = false;
     std::vector<double> h[REBX_B200_MAX_TABLES];
     std::vector<int32_t> hi;
-    DevBuf d[REBX_B200_MAX_TABLES];
-    DevBuf di;
+    // device copies: one slice [lo, hi) of every table per device the segment is spread over (index = slot in
+    // DeviceContext::devs; a single-device run holds the whole range in slot 0)
+    struct Slice { DevBuf d[REBX_B200_MAX_TABLES]; DevBuf di; size_t lo = 0, hi = 0; bool uploaded = false; };
+    std::vector<std::unique_ptr<Slice>> dev;
     std::vector<int64_t> bodies;     // RADIATION: sources; HARMONICS: oblate bodies; damping trio: first "primary"
     std::vector<Oblate> oblate;
     int64_t n_incomplete = 0;        // particles whose parameter set the reference would report as incomplete
@@ -95,19 +97,44 @@ struct Stats {
     std::uint64_t calls = 0, launches = 0, h2d_bytes = 0, d2h_bytes = 0, table_builds = 0;
 };
 
-struct DeviceContext {
-    int device = 0;
-    bool ready = false;
+// What one device needs to run its share of a segment: pipeline streams and staging buffers.
+struct DevSlot {
     static constexpr int kBuffers = 3;      // chunks in flight: H2D of c+1 and D2H of c-1 overlap the sweep of c
+    int device = 0;
     cudaStream_t stream[kBuffers] = {nullptr, nullptr, nullptr};
     cudaEvent_t bodies_ready = nullptr;
-    DevBuf aos[kBuffers], soa[kBuffers], work[kBuffers], bodies, br, scan, totals, grbuf;
-    PinnedBuf bodies_h, br_h, gr_h;
+    DevBuf aos[kBuffers], soa[kBuffers], work[kBuffers], bodies, br;
+    PinnedBuf br_h;
+    cudaError_t init(int dev) {
+        device = dev;
+        cudaError_t e = cudaSetDevice(dev);
+        if (e != cudaSuccess) return e;
+        for (auto& s : stream) if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) return e;
+        return cudaEventCreateWithFlags(&bodies_ready, cudaEventDisableTiming);
+    }
+    ~DevSlot() {
+        cudaSetDevice(device);
+        for (auto& s : stream) if (s) { cudaStreamSynchronize(s); cudaStreamDestroy(s); }
+        if (bodies_ready) cudaEventDestroy(bodies_ready);
+        cudaGetLastError();
+    }
+};
+
+struct DeviceContext {
+    static constexpr int kBuffers = DevSlot::kBuffers;
+    int device = 0;                         // primary device (devs[0]): zero-copy path, centre-of-mass frames, gr, potentials
+    bool ready = false;
+    // devs[0] is the primary; REBX_B200_DEVICES=all|<count>|<list> adds the others: a large PARTICLE-frame segment is
+    // then split by index range over all of them (one process, one host thread issuing asynchronous work per device)
+    std::vector<std::unique_ptr<DevSlot>> devs;
+    DevBuf scan, totals, grbuf;
+    PinnedBuf bodies_h, gr_h;
     std::unordered_map<struct rebx_force*, std::unique_ptr<ForceTables>> tables;
     void* registered_ptr = nullptr;
     size_t registered_bytes = 0;
     void* registered_dev = nullptr;         // device alias of the registered array (zero-copy path of small ensembles)
     size_t zero_copy_max = 3072;            // particles (measured crossover with pinned DMA: ~3000); REBX_B200_ZEROCOPY_MAX
+    size_t multi_min = size_t(1) << 20;     // smallest ensemble worth spreading over several devices; REBX_B200_MULTI_MIN
     Stats stats;
     size_t chunk = size_t(1) << 19;         // 64 MB of AoS records per pipeline stage
     bool chunk_from_env = false;
@@ -119,14 +146,10 @@ struct DeviceContext {
         registered_ptr = nullptr; registered_bytes = 0; registered_dev = nullptr;
     }
     ~DeviceContext() {
-        if (ready) {
-            cudaSetDevice(device);
-            for (auto& s : stream) if (s) { cudaStreamSynchronize(s); }
-        }
         unregister_host();
+        if (ready) cudaSetDevice(device);
         tables.clear();
-        if (bodies_ready) cudaEventDestroy(bodies_ready);
-        for (auto& s : stream) if (s) cudaStreamDestroy(s);
+        devs.clear();
     }
 };
 
@@ -182,7 +205,7 @@ static void build_tables(ForceTables& T, int kind, struct rebx_force* force, con
     T.bodies.clear();
     T.oblate.clear();
     T.n_incomplete = 0;
-    T.uploaded = false;
+    for (auto& sl : T.dev) if (sl) sl->uploaded = false;
     const double ABSENT = absent_value();
 
     std::vector<const char*> dnames;     // double tables in tab[] order
@@ -304,24 +327,29 @@ static void build_tables(ForceTables& T, int kind, struct rebx_force* force, con
     T.valid = true;
 }
 
-static cudaError_t upload_tables(ForceTables& T, Stats& st) {
-    if (T.uploaded) return cudaSuccess;
+// Uploads rows [lo, hi) of every table of T to the CURRENT device as slice `slot` (no-op when that slice is up to date).
+static cudaError_t upload_tables(ForceTables& T, Stats& st, size_t slot, size_t lo, size_t hi) {
+    if (T.dev.size() <= slot) T.dev.resize(slot + 1);
+    if (!T.dev[slot]) T.dev[slot] = std::make_unique<ForceTables::Slice>();
+    ForceTables::Slice& S = *T.dev[slot];
+    if (S.uploaded && S.lo == lo && S.hi == hi) return cudaSuccess;
+    const size_t n = hi - lo;
     for (size_t j = 0; j < REBX_B200_MAX_TABLES; j++) {
-        if (T.h[j].empty()) continue;
-        cudaError_t e = T.d[j].ensure(T.h[j].size()*sizeof(double));
+        if (T.h[j].empty() || n == 0) continue;
+        cudaError_t e = S.d[j].ensure(n*sizeof(double));
         if (e != cudaSuccess) return e;
-        e = cudaMemcpy(T.d[j].p, T.h[j].data(), T.h[j].size()*sizeof(double), cudaMemcpyHostToDevice);
+        e = cudaMemcpy(S.d[j].p, T.h[j].data() + lo, n*sizeof(double), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return e;
-        st.h2d_bytes += T.h[j].size()*sizeof(double);
+        st.h2d_bytes += n*sizeof(double);
     }
-    if (!T.hi.empty()) {
-        cudaError_t e = T.di.ensure(T.hi.size()*sizeof(int32_t));
+    if (!T.hi.empty() && n > 0) {
+        cudaError_t e = S.di.ensure(n*sizeof(int32_t));
         if (e != cudaSuccess) return e;
-        e = cudaMemcpy(T.di.p, T.hi.data(), T.hi.size()*sizeof(int32_t), cudaMemcpyHostToDevice);
+        e = cudaMemcpy(S.di.p, T.hi.data() + lo, n*sizeof(int32_t), cudaMemcpyHostToDevice);
         if (e != cudaSuccess) return e;
-        st.h2d_bytes += T.hi.size()*sizeof(int32_t);
+        st.h2d_bytes += n*sizeof(int32_t);
     }
-    T.uploaded = true;
+    S.lo = lo; S.hi = hi; S.uploaded = true;
     return cudaSuccess;
 }
 
@@ -355,13 +383,27 @@ static DeviceContext* ensure_ctx(Side* side, std::string& why) {
     const char* env = std::getenv("REBX_B200_DEVICE");
     ctx->device = env ? std::atoi(env) : 0;
     if (ctx->device < 0 || ctx->device >= count) ctx->device = 0;
+    // REBX_B200_DEVICES = all | <count> | <comma-separated ordinals>: the devices a large segment is spread over.
+    // The primary device (REBX_B200_DEVICE, default 0) always comes first.
+    std::vector<int> ordinals = {ctx->device};
+    if (const char* list = std::getenv("REBX_B200_DEVICES")) {
+        std::vector<int> want;
+        if (std::strcmp(list, "all") == 0) { for (int d = 0; d < count; d++) want.push_back(d); }
+        else if (std::strchr(list, ',')) { for (const char* q = list; *q;) { char* end; long v = std::strtol(q, &end, 10); if (end == q) break; want.push_back((int)v); q = (*end == ',') ? end + 1 : end; } }
+        else { const long k = std::atol(list); for (int d = 0; d < k && d < count; d++) want.push_back((ctx->device + d) % count); }
+        for (int d : want) if (d >= 0 && d < count && std::find(ordinals.begin(), ordinals.end(), d) == ordinals.end()) ordinals.push_back(d);
+    }
+    for (int d : ordinals) {
+        auto slot = std::make_unique<DevSlot>();
+        if ((e = slot->init(d)) != cudaSuccess) { why = std::string("device ") + std::to_string(d) + ": " + cudaGetErrorString(e); return nullptr; }
+        ctx->devs.push_back(std::move(slot));
+    }
     if ((e = cudaSetDevice(ctx->device)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
-    for (auto& s : ctx->stream) if ((e = cudaStreamCreateWithFlags(&s, cudaStreamNonBlocking)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
-    if ((e = cudaEventCreateWithFlags(&ctx->bodies_ready, cudaEventDisableTiming)) != cudaSuccess) { why = cudaGetErrorString(e); return nullptr; }
     if (const char* c = std::getenv("REBX_B200_CHUNK")) { long v = std::atol(c); if (v >= 1024) { ctx->chunk = (size_t)v & ~size_t(1); ctx->chunk_from_env = true; } }
     if (const char* p = std::getenv("REBX_B200_PARANOID")) ctx->paranoid = std::atoi(p) != 0;
     if (const char* m = std::getenv("REBX_B200_MATH")) ctx->tolerance = (m[0] == 't' || m[0] == 'T');
     if (const char* z = std::getenv("REBX_B200_ZEROCOPY_MAX")) { long v = std::atol(z); if (v >= 0) ctx->zero_copy_max = (size_t)v; }
+    if (const char* z = std::getenv("REBX_B200_MULTI_MIN")) { long v = std::atol(z); if (v >= 2) ctx->multi_min = (size_t)v; }
     ctx->ready = true;
     side->dev = std::move(ctx);
     return side->dev.get();
@@ -647,12 +689,20 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     // all particles precedes the sweep), so such a segment runs as one resident chunk.
     bool whole = false;
     for (const Entry& e : entries) if (e.frame != 0) whole = true;
+    // Devices of this segment: every configured device for a large segment in PARTICLE frames, split by index range
+    // [lo_d, hi_d) with even boundaries (each device streams its range through its own three-stage pipeline; tables
+    // are sharded the same way; the per-device, per-chunk back-reaction sums are added on the host in index order);
+    // the primary device alone otherwise.
+    const size_t ndev = (!whole && ctx->devs.size() > 1 && N >= ctx->multi_min) ? ctx->devs.size() : 1;
+    size_t per_dev = (N + ndev - 1)/ndev;
+    per_dev += per_dev & 1;
     // Pipeline granularity: the configured chunk for large ensembles; mid-size ones are cut into ~6
     // pieces (>= 32768 particles) so that H2D, sweep and D2H of different pieces overlap.
     size_t CH = ctx->chunk;
-    if (!ctx->chunk_from_env && N < 6*ctx->chunk) CH = std::max<size_t>(32768, ((N/6) + 1) & ~size_t(1));
+    if (!ctx->chunk_from_env && per_dev < 6*ctx->chunk) CH = std::max<size_t>(32768, ((per_dev/6) + 1) & ~size_t(1));
     if (whole) CH = (N + 1) & ~size_t(1);
-    const size_t nchunks = (N + CH - 1)/CH;
+    const size_t chunks_per_dev = (std::min(per_dev, N) + CH - 1)/CH;
+    const size_t nchunks = chunks_per_dev*ndev;                 // slots (a trailing device may use fewer)
     const size_t chunk_cap = std::min(N, CH);
     bool need_vel = false, need_m = false, need_r = false, any_reduces = false;
     for (const Entry& e : entries) if (e.reduces) any_reduces = true;
@@ -670,23 +720,28 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     const size_t soa_stride = (chunk_cap + 1) & ~size_t(1);      // keep every array 16-byte aligned
     int launches = 0;
     double* bodies_h = nullptr;
-    double* br_h = nullptr;
+    DevSlot& D0 = *ctx->devs[0];
     // a small ensemble is read and written by the staging kernels straight through the host mapping (below)
     const bool small = nchunks == 1 && !whole && N <= ctx->zero_copy_max;
     unsigned char* zc = nullptr;
 
-    // tables to HBM (no-op unless rebuilt)
-    for (Entry& e : entries) if (e.T) REBXB_CUDA(upload_tables(*e.T, ctx->stats), "uploading parameter tables");
-
     REBXB_CUDA(ctx->bodies_h.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating pinned body records");
-    REBXB_CUDA(ctx->bodies.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating body records");
-    REBXB_CUDA(ctx->br_h.ensure(nchunks*ne*3*sizeof(double)), "allocating pinned back-reaction sums");
-    REBXB_CUDA(ctx->br.ensure(nchunks*ne*3*sizeof(double)), "allocating back-reaction sums");
-    for (int b = 0; b < DeviceContext::kBuffers && (size_t)b < nchunks; b++) {
-        REBXB_CUDA(ctx->aos[b].ensure(chunk_cap*sizeof(struct reb_particle)), "allocating AoS staging");
-        REBXB_CUDA(ctx->soa[b].ensure(11*soa_stride*sizeof(double)), "allocating SoA state");
-        REBXB_CUDA(ctx->work[b].ensure(rebx_b200_workspace_bytes()), "allocating reduction scratch");
+    for (size_t d = 0; d < ndev; d++) {
+        DevSlot& D = *ctx->devs[d];
+        const size_t lo = std::min(N, d*per_dev), hi = std::min(N, lo + per_dev);
+        REBXB_CUDA(cudaSetDevice(D.device), "selecting a device");
+        // tables to HBM (no-op unless rebuilt or re-partitioned)
+        for (Entry& e : entries) if (e.T) REBXB_CUDA(upload_tables(*e.T, ctx->stats, d, ndev == 1 ? 0 : lo, ndev == 1 ? N : hi), "uploading parameter tables");
+        REBXB_CUDA(D.bodies.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating body records");
+        REBXB_CUDA(D.br_h.ensure(chunks_per_dev*ne*3*sizeof(double)), "allocating pinned back-reaction sums");
+        REBXB_CUDA(D.br.ensure(chunks_per_dev*ne*3*sizeof(double)), "allocating back-reaction sums");
+        for (int b = 0; b < DeviceContext::kBuffers && (size_t)b < chunks_per_dev; b++) {
+            REBXB_CUDA(D.aos[b].ensure(chunk_cap*sizeof(struct reb_particle)), "allocating AoS staging");
+            REBXB_CUDA(D.soa[b].ensure(11*soa_stride*sizeof(double)), "allocating SoA state");
+            REBXB_CUDA(D.work[b].ensure(rebx_b200_workspace_bytes()), "allocating reduction scratch");
+        }
     }
+    REBXB_CUDA(cudaSetDevice(D0.device), "selecting a device");
     if (whole) {
         REBXB_CUDA(ctx->scan.ensure(rebx_b200_scan_scratch_bytes((int64_t)N)), "allocating scan scratch");
         REBXB_CUDA(ctx->totals.ensure(16*sizeof(double)), "allocating mass moments");
@@ -696,9 +751,17 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
     // pinned as well: its records are then read and its accelerations written by the staging kernels
     // straight through the mapping (zero copy) -- no DMA descriptors, one PCIe round trip less each way.
     if (particles == sim->particles && (small || N*sizeof(struct reb_particle) >= (size_t(256) << 10))) {
+        // REBOUND reallocs or frees its array without telling us: a cached registration is trusted only while the
+        // runtime still reports the first and the last byte of the range as registered host memory
+        if (ctx->registered_ptr == particles && ctx->registered_bytes == N*sizeof(struct reb_particle)) {
+            cudaPointerAttributes a0, a1;
+            const char* last = reinterpret_cast<const char*>(particles) + N*sizeof(struct reb_particle) - 1;
+            if (cudaPointerGetAttributes(&a0, particles) != cudaSuccess || cudaPointerGetAttributes(&a1, last) != cudaSuccess ||
+                a0.type != cudaMemoryTypeHost || a1.type != cudaMemoryTypeHost) { cudaGetLastError(); ctx->unregister_host(); }
+        }
         if (ctx->registered_ptr != particles || ctx->registered_bytes != N*sizeof(struct reb_particle)) {
             ctx->unregister_host();
-            if (cudaHostRegister(particles, N*sizeof(struct reb_particle), cudaHostRegisterMapped) == cudaSuccess) {
+            if (cudaHostRegister(particles, N*sizeof(struct reb_particle), cudaHostRegisterMapped | cudaHostRegisterPortable) == cudaSuccess) {
                 ctx->registered_ptr = particles; ctx->registered_bytes = N*sizeof(struct reb_particle);
                 if (cudaHostGetDevicePointer(&ctx->registered_dev, particles, 0) != cudaSuccess) { ctx->registered_dev = nullptr; cudaGetLastError(); }
             } else {
@@ -710,24 +773,35 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
 
     bodies_h = static_cast<double*>(ctx->bodies_h.p);
     for (size_t e = 0; e < ne; e++) fill_body(bodies_h + e*REBX_B200_BODY_DOUBLES, entries[e], particles);
-    // zero-copy path: the sweeps read the few body records straight from the pinned host buffer (one copy less)
-    if (!zc) REBXB_CUDA(cudaMemcpyAsync(ctx->bodies.p, bodies_h, ne*REBX_B200_BODY_DOUBLES*sizeof(double), cudaMemcpyHostToDevice, ctx->stream[0]), "copying body records");
-    if (any_reduces) REBXB_CUDA(cudaMemsetAsync(ctx->br.p, 0, nchunks*ne*3*sizeof(double), ctx->stream[0]), "clearing back-reaction sums");
-    if (nchunks > 1) {      // the other pipeline streams must see the body records
-        REBXB_CUDA(cudaEventRecord(ctx->bodies_ready, ctx->stream[0]), "recording event");
-        for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamWaitEvent(ctx->stream[b], ctx->bodies_ready, 0), "waiting on event");
+    for (size_t d = 0; d < ndev; d++) {
+        DevSlot& D = *ctx->devs[d];
+        if (ndev > 1) REBXB_CUDA(cudaSetDevice(D.device), "selecting a device");
+        // zero-copy path: the sweeps read the few body records straight from the pinned host buffer (one copy less)
+        if (!zc) REBXB_CUDA(cudaMemcpyAsync(D.bodies.p, bodies_h, ne*REBX_B200_BODY_DOUBLES*sizeof(double), cudaMemcpyHostToDevice, D.stream[0]), "copying body records");
+        if (any_reduces) REBXB_CUDA(cudaMemsetAsync(D.br.p, 0, chunks_per_dev*ne*3*sizeof(double), D.stream[0]), "clearing back-reaction sums");
+        if (chunks_per_dev > 1) {      // the other pipeline streams must see the body records
+            REBXB_CUDA(cudaEventRecord(D.bodies_ready, D.stream[0]), "recording event");
+            for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamWaitEvent(D.stream[b], D.bodies_ready, 0), "waiting on event");
+        }
+        ctx->stats.h2d_bytes += ne*REBX_B200_BODY_DOUBLES*sizeof(double);
     }
-    ctx->stats.h2d_bytes += ne*REBX_B200_BODY_DOUBLES*sizeof(double);
 
-    for (size_t c = 0; c < nchunks; c++) {
-        const int b = (int)(c % DeviceContext::kBuffers);
-        cudaStream_t s = ctx->stream[b];
-        const size_t c0 = c*CH, n = std::min(CH, N - c0);
+    // chunk ci of every device is issued before chunk ci + 1 of any, so that all devices start streaming at once
+    for (size_t ci = 0; ci < chunks_per_dev; ci++) for (size_t d = 0; d < ndev; d++) {
+        DevSlot& D = *ctx->devs[d];
+        const size_t lo = std::min(N, d*per_dev), hi = std::min(N, lo + per_dev);
+        const size_t c0 = lo + ci*CH;
+        if (c0 >= hi) continue;
+        if (ndev > 1) REBXB_CUDA(cudaSetDevice(D.device), "selecting a device");
+        const int b = (int)(ci % DeviceContext::kBuffers);
+        cudaStream_t s = D.stream[b];
+        const size_t n = std::min(CH, hi - c0);
         const size_t bytes = n*sizeof(struct reb_particle);
-        void* const aos_in = zc ? static_cast<void*>(zc) : ctx->aos[b].p;      // zc: nchunks == 1, so c0 == 0
-        if (!zc) REBXB_CUDA(copy_page_split(ctx->aos[b].p, particles + c0, bytes, cudaMemcpyHostToDevice, s), "copying particles to the device");
+        const size_t tab0 = c0 - (ndev == 1 ? 0 : lo);                              // offset inside this device's table slice
+        void* const aos_in = zc ? static_cast<void*>(zc) : D.aos[b].p;      // zc: one chunk on one device, so c0 == 0
+        if (!zc) REBXB_CUDA(copy_page_split(D.aos[b].p, particles + c0, bytes, cudaMemcpyHostToDevice, s), "copying particles to the device");
         ctx->stats.h2d_bytes += bytes;
-        double* base = static_cast<double*>(ctx->soa[b].p);
+        double* base = static_cast<double*>(D.soa[b].p);
         rebx_b200_state st;
         st.n = (int64_t)n; st.index_base = (int64_t)c0;
         st.x = base + 0*soa_stride; st.y = base + 1*soa_stride; st.z = base + 2*soa_stride;
@@ -756,7 +830,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 int* flag_d = reinterpret_cast<int*>(pull_d + 32);
                 double* pull_h = static_cast<double*>(ctx->gr_h.p);
                 REBXB_CUDA(cudaMemsetAsync(flag_d, 0, sizeof(int), s), "clearing the convergence flag");
-                REBXB_CUDA((cudaError_t)rebx_b200_gr_pull(&st, &ga, pull_d, ctx->work[b].p, s, &launches), "reducing the test particles' pull");
+                REBXB_CUDA((cudaError_t)rebx_b200_gr_pull(&st, &ga, pull_d, D.work[b].p, s, &launches), "reducing the test particles' pull");
                 REBXB_CUDA(cudaMemcpyAsync(pull_h, pull_d, (size_t)en.n_active*3*sizeof(double), cudaMemcpyDeviceToHost, s), "copying the pull");
                 REBXB_CUDA(cudaStreamSynchronize(s), "waiting for the device");
                 bool host_nc = false;
@@ -781,13 +855,14 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 const Entry& en = entries[e0 + j];
                 rebx_b200_effect& fx = P.fx[j];
                 fx.kind = en.kind; fx.flags = en.flags;
-                fx.body = (zc ? bodies_h : static_cast<const double*>(ctx->bodies.p)) + (e0 + j)*REBX_B200_BODY_DOUBLES;
+                fx.body = (zc ? bodies_h : static_cast<const double*>(D.bodies.p)) + (e0 + j)*REBX_B200_BODY_DOUBLES;
                 for (int k = 0; k < REBX_B200_MAX_SCALARS; k++) fx.scal[k] = en.scal[k];
                 if (en.T) {
-                    for (int k = 0; k < REBX_B200_MAX_TABLES; k++) fx.tab[k] = en.T->d[k].p ? static_cast<const double*>(en.T->d[k].p) + c0 : nullptr;
-                    fx.itab = en.T->di.p ? static_cast<const int32_t*>(en.T->di.p) + c0 : nullptr;
+                    const ForceTables::Slice& S = *en.T->dev[d];
+                    for (int k = 0; k < REBX_B200_MAX_TABLES; k++) fx.tab[k] = S.d[k].p ? static_cast<const double*>(S.d[k].p) + tab0 : nullptr;
+                    fx.itab = S.di.p ? static_cast<const int32_t*>(S.di.p) + tab0 : nullptr;
                 }
-                fx.backreaction = en.reduces ? static_cast<double*>(ctx->br.p) + (c*ne + e0 + j)*3 : nullptr;
+                fx.backreaction = en.reduces ? static_cast<double*>(D.br.p) + (ci*ne + e0 + j)*3 : nullptr;
             }
             if (frame == 2) {
                 REBXB_CUDA((cudaError_t)rebx_b200_launch_jacobi(&P, ctx->scan.p, s, &launches), "launching the Jacobi-frame sweep");
@@ -795,9 +870,9 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 if (frame == 1) {   // barycentre record computed on the device from the resident state
                     REBXB_CUDA((cudaError_t)rebx_b200_mass_moments(&st, static_cast<double*>(ctx->totals.p), ctx->scan.p, nullptr, REBX_B200_COM_WHOLE, s, &launches), "reducing mass moments");
                     REBXB_CUDA((cudaError_t)rebx_b200_com_bodies(static_cast<const double*>(ctx->totals.p),
-                                                                 static_cast<double*>(ctx->bodies.p) + e0*REBX_B200_BODY_DOUBLES, P.n_effects, s, &launches), "building the barycentre record");
+                                                                 static_cast<double*>(D.bodies.p) + e0*REBX_B200_BODY_DOUBLES, P.n_effects, s, &launches), "building the barycentre record");
                 }
-                REBXB_CUDA((cudaError_t)rebx_b200_launch_pass(&P, ctx->work[b].p, s, &launches), "launching the force sweep");
+                REBXB_CUDA((cudaError_t)rebx_b200_launch_pass(&P, D.work[b].p, s, &launches), "launching the force sweep");
                 if (frame == 1)     // every particle loses sum_i (m_i/M) f_i  (rebxtools.c:108-115)
                     for (int j = 0; j < P.n_effects; j++)
                         REBXB_CUDA((cudaError_t)rebx_b200_add_uniform(&st, P.fx[j].backreaction, s, &launches), "applying the barycentric back-reaction");
@@ -805,16 +880,20 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
             e0 = e1;
         }
         REBXB_CUDA((cudaError_t)rebx_b200_pack_acc_aos(aos_in, &L, &st, s, &launches), "packing accelerations");
-        if (!zc) REBXB_CUDA(copy_page_split(particles + c0, ctx->aos[b].p, bytes, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
+        if (!zc) REBXB_CUDA(copy_page_split(particles + c0, D.aos[b].p, bytes, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
         ctx->stats.d2h_bytes += zc ? n*3*sizeof(double) : bytes;
     }
-    if (nchunks > 1) for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamSynchronize(ctx->stream[b]), "waiting for the device");
-    br_h = static_cast<double*>(ctx->br_h.p);
-    if (any_reduces) {
-        REBXB_CUDA(cudaMemcpyAsync(br_h, ctx->br.p, nchunks*ne*3*sizeof(double), cudaMemcpyDeviceToHost, ctx->stream[0]), "copying back-reaction sums");
-        ctx->stats.d2h_bytes += nchunks*ne*3*sizeof(double);
+    for (size_t d = 0; d < ndev; d++) {
+        DevSlot& D = *ctx->devs[d];
+        if (ndev > 1) REBXB_CUDA(cudaSetDevice(D.device), "selecting a device");
+        if (chunks_per_dev > 1) for (int b = 1; b < DeviceContext::kBuffers; b++) REBXB_CUDA(cudaStreamSynchronize(D.stream[b]), "waiting for the device");
+        if (any_reduces) {
+            REBXB_CUDA(cudaMemcpyAsync(D.br_h.p, D.br.p, chunks_per_dev*ne*3*sizeof(double), cudaMemcpyDeviceToHost, D.stream[0]), "copying back-reaction sums");
+            ctx->stats.d2h_bytes += chunks_per_dev*ne*3*sizeof(double);
+        }
+        REBXB_CUDA(cudaStreamSynchronize(D.stream[0]), "waiting for the device");
     }
-    REBXB_CUDA(cudaStreamSynchronize(ctx->stream[0]), "waiting for the device");
+    if (ndev > 1) REBXB_CUDA(cudaSetDevice(D0.device), "selecting a device");
     ctx->stats.launches += (std::uint64_t)launches;
 
     // Back-reaction onto the source / primary / oblate bodies (gr_potential.c:74-76,
@@ -832,8 +911,11 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
             continue;
         }
         if (!entries[e].reduces || entries[e].frame != 0) continue;    // COM frames were applied on the device
-        double sx = 0.0, sy = 0.0, sz = 0.0;
-        for (size_t c = 0; c < nchunks; c++) { sx += br_h[(c*ne + e)*3 + 0]; sy += br_h[(c*ne + e)*3 + 1]; sz += br_h[(c*ne + e)*3 + 2]; }
+        double sx = 0.0, sy = 0.0, sz = 0.0;          // device by device, chunk by chunk: ascending particle index
+        for (size_t d = 0; d < ndev; d++) {
+            const double* br_h = static_cast<const double*>(ctx->devs[d]->br_h.p);
+            for (size_t c = 0; c < chunks_per_dev; c++) { sx += br_h[(c*ne + e)*3 + 0]; sy += br_h[(c*ne + e)*3 + 1]; sz += br_h[(c*ne + e)*3 + 2]; }
+        }
         struct reb_particle& b = particles[entries[e].body_index];
         b.ax += sx; b.ay += sy; b.az += sz;
     }
@@ -845,7 +927,8 @@ failed:
         char buf[400];
         snprintf(buf, sizeof buf, "REBOUNDx-B200 Error: CUDA failure while %s: %s. Accelerations are NOT valid for this call.\n", fail, cudaGetErrorString(fail_code));
         reb_simulation_error(sim, buf);
-        for (auto& st : ctx->stream) cudaStreamSynchronize(st);
+        for (auto& D : ctx->devs) { cudaSetDevice(D->device); for (auto& st : D->stream) cudaStreamSynchronize(st); }
+        cudaSetDevice(ctx->device);
         cudaGetLastError();
     }
 }
@@ -866,6 +949,7 @@ static double run_potential(struct rebx_extras* rebx, int kind, const struct reb
         reb_simulation_error(sim, msg.c_str());
         return 0;
     }
+    DevSlot& P0 = *ctx->devs[0];
     std::vector<Entry> entries;
     Entry e;
     e.kind = kind; e.scal[0] = sim->G;
@@ -890,37 +974,37 @@ static double run_potential(struct rebx_extras* rebx, int kind, const struct reb
                                     (int32_t)offsetof(struct reb_particle, m), (int32_t)offsetof(struct reb_particle, r)};
     int launches = 0;
     double total = 0.0;
-    cudaStream_t s = ctx->stream[0];
+    cudaStream_t s = P0.stream[0];
     double* base = nullptr;
     double* out_h = nullptr;
     rebx_b200_state st;
-    REBXB_CUDA(ctx->aos[0].ensure(N*sizeof(struct reb_particle)), "allocating AoS staging");
-    REBXB_CUDA(ctx->soa[0].ensure(11*stride*sizeof(double)), "allocating SoA state");
-    REBXB_CUDA(ctx->work[0].ensure(rebx_b200_workspace_bytes()), "allocating reduction scratch");
+    REBXB_CUDA(P0.aos[0].ensure(N*sizeof(struct reb_particle)), "allocating AoS staging");
+    REBXB_CUDA(P0.soa[0].ensure(11*stride*sizeof(double)), "allocating SoA state");
+    REBXB_CUDA(P0.work[0].ensure(rebx_b200_workspace_bytes()), "allocating reduction scratch");
     REBXB_CUDA(ctx->bodies_h.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating pinned body records");
-    REBXB_CUDA(ctx->bodies.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating body records");
-    REBXB_CUDA(ctx->br_h.ensure(ne*sizeof(double)), "allocating pinned results");
-    REBXB_CUDA(ctx->br.ensure(ne*sizeof(double)), "allocating results");
+    REBXB_CUDA(P0.bodies.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating body records");
+    REBXB_CUDA(P0.br_h.ensure(ne*sizeof(double)), "allocating pinned results");
+    REBXB_CUDA(P0.br.ensure(ne*sizeof(double)), "allocating results");
     for (size_t k = 0; k < ne; k++) fill_body(static_cast<double*>(ctx->bodies_h.p) + k*REBX_B200_BODY_DOUBLES, entries[k], particles);
-    REBXB_CUDA(cudaMemcpyAsync(ctx->bodies.p, ctx->bodies_h.p, ne*REBX_B200_BODY_DOUBLES*sizeof(double), cudaMemcpyHostToDevice, s), "copying body records");
-    REBXB_CUDA(copy_page_split(ctx->aos[0].p, particles, N*sizeof(struct reb_particle), cudaMemcpyHostToDevice, s), "copying particles to the device");
+    REBXB_CUDA(cudaMemcpyAsync(P0.bodies.p, ctx->bodies_h.p, ne*REBX_B200_BODY_DOUBLES*sizeof(double), cudaMemcpyHostToDevice, s), "copying body records");
+    REBXB_CUDA(copy_page_split(P0.aos[0].p, particles, N*sizeof(struct reb_particle), cudaMemcpyHostToDevice, s), "copying particles to the device");
     ctx->stats.h2d_bytes += N*sizeof(struct reb_particle);
-    base = static_cast<double*>(ctx->soa[0].p);
+    base = static_cast<double*>(P0.soa[0].p);
     std::memset(&st, 0, sizeof st);
     st.n = (int64_t)N; st.index_base = 0;
     st.x = base; st.y = base + stride; st.z = base + 2*stride; st.m = base + 6*stride;
     st.ax = base + 8*stride; st.ay = base + 9*stride; st.az = base + 10*stride;
-    REBXB_CUDA((cudaError_t)rebx_b200_unpack_aos(ctx->aos[0].p, &L, &st, s, &launches), "unpacking particles");
+    REBXB_CUDA((cudaError_t)rebx_b200_unpack_aos(P0.aos[0].p, &L, &st, s, &launches), "unpacking particles");
     for (size_t k = 0; k < ne; k++) {
         rebx_b200_effect fx;
         std::memset(&fx, 0, sizeof fx);
         fx.kind = kind;
-        fx.body = static_cast<const double*>(ctx->bodies.p) + k*REBX_B200_BODY_DOUBLES;
+        fx.body = static_cast<const double*>(P0.bodies.p) + k*REBX_B200_BODY_DOUBLES;
         for (int q = 0; q < REBX_B200_MAX_SCALARS; q++) fx.scal[q] = entries[k].scal[q];
-        REBXB_CUDA((cudaError_t)rebx_b200_potential(&st, &fx, static_cast<double*>(ctx->br.p) + k, ctx->work[0].p, s, &launches), "reducing the potential");
+        REBXB_CUDA((cudaError_t)rebx_b200_potential(&st, &fx, static_cast<double*>(P0.br.p) + k, P0.work[0].p, s, &launches), "reducing the potential");
     }
-    out_h = static_cast<double*>(ctx->br_h.p);
-    REBXB_CUDA(cudaMemcpyAsync(out_h, ctx->br.p, ne*sizeof(double), cudaMemcpyDeviceToHost, s), "copying the potential");
+    out_h = static_cast<double*>(P0.br_h.p);
+    REBXB_CUDA(cudaMemcpyAsync(out_h, P0.br.p, ne*sizeof(double), cudaMemcpyDeviceToHost, s), "copying the potential");
     REBXB_CUDA(cudaStreamSynchronize(s), "waiting for the device");
     ctx->stats.launches += (std::uint64_t)launches;
     for (size_t k = 0; k < ne; k++) total += out_h[k];
@@ -931,7 +1015,7 @@ failed:
         char buf[400];
         snprintf(buf, sizeof buf, "REBOUNDx-B200 Error: CUDA failure while %s: %s.\n", fail, cudaGetErrorString(fail_code));
         reb_simulation_error(sim, buf);
-        cudaStreamSynchronize(ctx->stream[0]); cudaGetLastError();
+        cudaStreamSynchronize(P0.stream[0]); cudaGetLastError();
     }
     return 0;
 }

@@ -126,9 +126,19 @@ moments_tile_kernel(rebx_b200_state st, double* __restrict__ tile_sums, const do
     if (__syncthreads_or(bad) && threadIdx.x == 0) atomicOr(unsafe, 1u);
     // smallest local index >= (global index 1) whose mass is not zero on the grid: only the first tiles can
     // lower it, so nearly every CTA leaves after one read
-    const bool massive = k < st.n && st.index_base + k >= 1 && v[0] != 0.0;
-    if (__syncthreads_or(massive) && (unsigned long long)((int64_t)blockIdx.x*kScanThreads) < *first_massive) {
-        if (massive) atomicMin(first_massive, (unsigned long long)k);
+    // (a candidate only while it could still lower the current minimum, so nearly every CTA leaves after one read;
+    // __syncthreads_or makes the branch uniform although the threads may read different values of the global word)
+    const bool massive = k < st.n && st.index_base + k >= 1 && v[0] != 0.0 && (unsigned long long)k < *first_massive;
+    if (__syncthreads_or(massive)) {
+        // one global atomic per CTA: the lowest massive lane of each warp competes in shared memory first (every
+        // thread hitting the one global word cost 110 us at 10^6 particles)
+        __shared__ unsigned s_first;
+        if (threadIdx.x == 0) s_first = 0xffffffffu;
+        __syncthreads();
+        const unsigned ballot = __ballot_sync(0xffffffffu, massive);
+        if (ballot != 0u && (threadIdx.x & 31) == (unsigned)(__ffs(ballot) - 1)) atomicMin(&s_first, threadIdx.x);
+        __syncthreads();
+        if (threadIdx.x == 0 && s_first != 0xffffffffu) atomicMin(first_massive, (unsigned long long)((int64_t)blockIdx.x*kScanThreads + s_first));
     }
     double total[7];
     block_exclusive_scan<7>(v, total, s_warp);
