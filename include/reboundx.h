@@ -97,6 +97,27 @@ struct rebx_force {
     void (*free_memory)(struct rebx_extras* rebx, struct rebx_force* const force);
 };
 
+/* ---- operators (the callers either side of the force path) -------------------------
+ * reference src/reboundx.h:86-89,103-107,170-176,241-258 */
+enum rebx_timing { REBX_TIMING_PRE = -1, REBX_TIMING_POST = 1 };
+enum rebx_operator_type { REBX_OPERATOR_NONE = 0, REBX_OPERATOR_UPDATER = 1, REBX_OPERATOR_RECORDER = 2 };
+enum rebx_integrator {
+    REBX_INTEGRATOR_NONE = -1, REBX_INTEGRATOR_IMPLICIT_MIDPOINT = 0, REBX_INTEGRATOR_RK4 = 1,
+    REBX_INTEGRATOR_EULER = 2, REBX_INTEGRATOR_RK2 = 3
+};
+struct rebx_operator {
+    char* name;
+    struct rebx_node* ap;
+    struct reb_simulation* sim;
+    enum rebx_operator_type operator_type;
+    void (*step_function)(struct reb_simulation* sim, struct rebx_operator* operator_, const double dt);
+    void (*free_memory)(struct rebx_extras* rebx, struct rebx_operator* const operator_);
+};
+struct rebx_step {
+    struct rebx_operator* operator_;    /* `operator` in the reference (a C++ keyword; same layout) */
+    double dt_fraction;
+};
+
 /* ---- attach / free: reference src/reboundx.h:294-304, src/core.h:37-38 ---------------- */
 struct rebx_extras* rebx_attach(struct reb_simulation* sim);
 void rebx_initialize(struct reb_simulation* sim, struct rebx_extras* rebx);
@@ -141,6 +162,24 @@ void rebx_free_force(struct rebx_extras* rebx, struct rebx_force* force);
 void rebx_free_param(struct rebx_param* param);
 void rebx_error(struct rebx_extras* rebx, const char* const msg);
 void rebx_reset_accelerations(struct reb_particle* const ps, const int N);
+
+/* ---- operators: reference src/reboundx.h:307,353-358,393,684,691, src/core.h:77-80; src/core.c:362-453,500-602,
+ * 1041-1089.  Built-in names of this build: "integrate_force" (the force path's own operator: velocities advanced
+ * across dt under ONE force, src/integrate_force.c:34-78, on the device when that force is device-backed), "drift" and
+ * "kick" (src/steppers.c:109-130).  Every other built-in operator name reports "not found"; custom operators
+ * (rebx_create_operator + step_function) run on the host unchanged. */
+struct rebx_operator* rebx_create_operator(struct rebx_extras* const rebx, const char* name);
+struct rebx_operator* rebx_load_operator(struct rebx_extras* const rebx, const char* name);
+int rebx_add_operator(struct rebx_extras* rebx, struct rebx_operator* operator_);
+int rebx_add_operator_step(struct rebx_extras* rebx, struct rebx_operator* operator_, const double dt_fraction, enum rebx_timing timing);
+int rebx_remove_operator(struct rebx_extras* rebx, struct rebx_operator* operator_);
+struct rebx_operator* rebx_get_operator(struct rebx_extras* const rebx, const char* const name);
+void rebx_free_operator(struct rebx_operator* operator_);
+void rebx_pre_timestep_modifications(struct reb_simulation* sim);
+void rebx_post_timestep_modifications(struct reb_simulation* sim);
+void rebx_integrate_force(struct reb_simulation* const sim, struct rebx_operator* const operator_, const double dt);   /* src/integrate_force.c:34 */
+void rebx_drift_step(struct reb_simulation* const sim, struct rebx_operator* const operator_, const double dt);        /* src/steppers.c:109 */
+void rebx_kick_step(struct reb_simulation* const sim, struct rebx_operator* const operator_, const double dt);         /* src/steppers.c:120 */
 
 /* ---- the hot path --------------------------------------------------------------------- */
 /* Dispatcher installed as sim->additional_forces: reference src/core.c:1026-1041. */

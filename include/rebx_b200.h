@@ -280,6 +280,35 @@ int rebx_b200_unpack_aos(const void* aos, const rebx_b200_aos_layout* layout, co
 int rebx_b200_pack_acc_aos(void* aos, const rebx_b200_aos_layout* layout, const rebx_b200_state* st,
                            void* stream, int* launches);
 
+/* ---- resident session: a simulation's particles kept in HBM between force evaluations, driven from C -------------
+ * (the PCIe round trip of the host-facing call is the end-to-end bottleneck by ~100x.)
+ * A session uploads sim->particles once, keeps SoA state + the parameter tables of every force on
+ * rebx->additional_forces resident on the primary device, and advances / evaluates there; nothing crosses PCIe
+ * until rebx_b200_session_sync_to_host.  Requirements: every added force is device-backed and refers to ONE central
+ * body (particle 0) in PARTICLE coordinates, at most REBX_B200_MAX_EFFECTS effect entries; the steppers integrate
+ * test-particle-like ensembles about particle 0 (N_active = 1 semantics, as the host harness reb_shim_integrate with
+ * N_active = 1).  All calls return 0 or a cudaError_t value / -1 (a REBOUND error is queued on the simulation). */
+struct reb_simulation;
+typedef struct rebx_b200_session rebx_b200_session;
+rebx_b200_session* rebx_b200_session_create(struct reb_simulation* sim, struct rebx_extras* rebx);
+/* a += stacked effects at the resident state (what sim->additional_forces(sim) adds). */
+int rebx_b200_session_evaluate(rebx_b200_session* s);
+/* `nsteps` drift-kick-drift steps of dt: central gravity of particle 0 (sim->G, sim->softening) + the stacked effects;
+ * one fused sweep per step where the stack has one (rebx_b200_leapfrog_step).  Same bits as reb_shim_integrate
+ * scheme "leapfrog" with N_active = 1 calling this library's (or the reference's) force. */
+int rebx_b200_session_step_leapfrog(rebx_b200_session* s, int nsteps, double dt);
+/* `nsteps` Wisdom-Holman steps of dt: Kepler drift about particle 0 (universal variables), kick by the stacked effects
+ * alone; the half drifts between consecutive kicks merged into one (scheme "wisdom_holman_merged" of the harness). */
+int rebx_b200_session_step_wh(rebx_b200_session* s, int nsteps, double dt);
+/* Velocities advanced across dt under the stacked effects alone, positions fixed: the integrate_force operator
+ * (reference src/integrate_force.c:34-78); scheme = enum rebx_integrator value. */
+int rebx_b200_session_integrate_force(rebx_b200_session* s, double dt, int scheme);
+/* Writes positions, velocities and accelerations back into sim->particles and advances sim->t by the time stepped. */
+int rebx_b200_session_sync_to_host(rebx_b200_session* s);
+/* Kernel launches issued by the session so far. */
+uint64_t rebx_b200_session_launches(const rebx_b200_session* s);
+void rebx_b200_session_free(rebx_b200_session* s);
+
 /* ---- the host dispatcher's knobs and counters (reboundx_b200/csrc/dispatch.cpp) ------------------------------------
  * Environment, read when an extras' device context is created (first force evaluation):
  *   REBX_B200_DEVICE=<ordinal>           primary device (default 0)

@@ -308,14 +308,15 @@ def port_case(case):
 INTEGRATORS = {"implicit_midpoint": 0, "rk4": 1, "euler": 2, "rk2": 3}       # reference reboundx.h enum rebx_integrator
 
 
-def ref_integrate_force(w, force_name, dt, scheme, nsteps=1):
+def ref_integrate_force(w, force_name, dt, scheme, nsteps=1, lib=None, coordinates="PARTICLE"):
     """Velocities after `nsteps` applications of the reference's rebx_integrate_force(sim, operator, dt)
-    with the reference's own force loop, all compiled in oracle/_ref.  Returns (vx, vy, vz)."""
+    with the reference's own force loop, all compiled in oracle/_ref.  Returns (vx, vy, vz).
+    `lib`: another library with the same operator API (the tests drive the product through the same calls)."""
     from ctypes import c_char_p
     from reboundx_b200 import scenarios
     from reboundx_b200.host import RebxForce
-    lib = ref_lib()
-    sim, rebx, handles = scenarios.build(w, [force_name], lib=lib)
+    lib = lib or ref_lib()
+    sim, rebx, handles = scenarios.build(w, [force_name], lib=lib, coordinates=coordinates)
     lib.rebx_load_operator.restype = POINTER(RebxForce)          # rebx_operator has the same leading layout
     op = lib.rebx_load_operator(rebx._ptr, c_char_p(b"integrate_force"))
     ap = ctypes.cast(ctypes.addressof(op.contents) + RebxForce.ap.offset, c_void_p)

@@ -295,6 +295,8 @@ void rebx_detach(struct rebx_extras* rebx) {
     if (sim == nullptr) return;
     if (sim->extras == rebx) {
         if (sim->additional_forces == rebx_additional_forces) sim->additional_forces = nullptr;
+        if (sim->pre_timestep_modifications == rebx_pre_timestep_modifications) sim->pre_timestep_modifications = nullptr;
+        if (sim->post_timestep_modifications == rebx_post_timestep_modifications) sim->post_timestep_modifications = nullptr;
         if (sim->extras_cleanup == rebx_extras_cleanup) sim->extras_cleanup = nullptr;
         if (sim->free_particle_ap == rebx_free_particle_ap) sim->free_particle_ap = nullptr;
         sim->extras = nullptr;
@@ -319,11 +321,15 @@ void rebx_free_pointers(struct rebx_extras* rebx) {
     free_node_list(rebx->allocated_forces,
                    [](struct rebx_extras* r, void* f) { rebx_free_force(r, static_cast<struct rebx_force*>(f)); }, rebx);
     free_node_list(rebx->additional_forces, nullptr, rebx);
-    // operator / step lists are never populated by this library (operators are out of scope);
-    // free the nodes only, should a foreign caller have pushed some.
-    free_node_list(rebx->allocated_operators, nullptr, rebx);
-    free_node_list(rebx->pre_timestep_modifications, nullptr, rebx);
-    free_node_list(rebx->post_timestep_modifications, nullptr, rebx);
+    // operators (reference src/core.c:273-287): the steps own nothing but themselves
+    free_node_list(rebx->allocated_operators,
+                   [](struct rebx_extras* r, void* o) {
+                       struct rebx_operator* op = static_cast<struct rebx_operator*>(o);
+                       if (op->free_memory) { op->free_memory(r, op); }
+                       rebx_free_operator(op);
+                   }, rebx);
+    free_node_list(rebx->pre_timestep_modifications, [](struct rebx_extras*, void* st) { free(st); }, rebx);
+    free_node_list(rebx->post_timestep_modifications, [](struct rebx_extras*, void* st) { free(st); }, rebx);
     free_node_list(rebx->registered_params,
                    [](struct rebx_extras*, void* p) { free(p); }, rebx);   // registry entries carry no value
     rebx->allocated_forces = rebx->additional_forces = rebx->allocated_operators = nullptr;

@@ -1120,3 +1120,5 @@ int rebx_b200_get_stats(struct rebx_extras* rebx, uint64_t out[5]) {
 }
 
 }  // extern "C"
+
+#include "session.inl"

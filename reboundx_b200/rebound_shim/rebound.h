@@ -104,6 +104,7 @@ void reb_simulation_remove_particle(struct reb_simulation* r, size_t index, int 
 /* --- messages ------------------------------------------------------------------------ */
 void reb_simulation_error(struct reb_simulation* r, const char* msg);
 void reb_simulation_warning(struct reb_simulation* r, const char* msg);
+void reb_simulation_update_acceleration(struct reb_simulation* r);
 const char* reb_simulation_register_name(struct reb_simulation* r, const char* name);
 
 /* --- celestial mechanics helpers used on the hot path --------------------------------- */

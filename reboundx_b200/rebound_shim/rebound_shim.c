@@ -444,6 +444,9 @@ static void shim_accelerations(struct reb_simulation* r){
     if (r->additional_forces) r->additional_forces(r);
 }
 
+/* REBOUND's public name for "gravity + additional forces" (called by rebx_kick_step, reference src/steppers.c:121). */
+void reb_simulation_update_acceleration(struct reb_simulation* r){ shim_accelerations(r); }
+
 /* ---- scheme 2: 15th-order Gauss-Radau predictor-corrector with a FIXED step (the scheme behind
  * REBOUND's IAS15, Everhart 1985 / Rein & Spiegel 2015, without its step-size control, i.e.
  * epsilon = 0).  Written from the published algorithm: the acceleration along the step is the
@@ -599,6 +602,7 @@ void reb_shim_integrate(struct reb_simulation* r, int nsteps, int scheme){
     const double dt = r->dt;
     if (scheme == 0){
         for (int s = 0; s < nsteps; s++){
+            if (r->pre_timestep_modifications) r->pre_timestep_modifications(r);     /* REBOUNDx operators, as REBOUND's step does */
             for (size_t i = 0; i < N; i++){ p[i].x += 0.5*dt*p[i].vx; p[i].y += 0.5*dt*p[i].vy; p[i].z += 0.5*dt*p[i].vz; }
             r->t += 0.5*dt;
             shim_accelerations(r);
@@ -606,6 +610,7 @@ void reb_shim_integrate(struct reb_simulation* r, int nsteps, int scheme){
             for (size_t i = 0; i < N; i++){ p[i].x += 0.5*dt*p[i].vx; p[i].y += 0.5*dt*p[i].vy; p[i].z += 0.5*dt*p[i].vz; }
             r->t += 0.5*dt;
             r->dt_last_done = dt;
+            if (r->post_timestep_modifications) r->post_timestep_modifications(r);
         }
         return;
     }

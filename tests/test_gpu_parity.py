@@ -1406,3 +1406,52 @@ def test_c_program_multi_device_dispatch(built, tmp_path):
     assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
     rep = json.loads(run.stdout.strip().splitlines()[-1])
     assert rep["ok"] and rep["debris_disk"]["differing_components"] == 0 and rep["ring_massive"]["differing_components"] == 0, rep
+
+
+def test_c_program_resident_session(built, tmp_path):
+    """tests/c_resident_session.c: BASELINE config 1a integrated for 10^3 steps by a resident session driven from C
+    (rebx_b200_session_step_wh / _step_leapfrog: one upload, one download) -- bit for bit the trajectory of the host
+    harness that calls sim->additional_forces every step; the session's evaluation against the dispatcher's; and the
+    reference's operator entry rebx_load_operator("integrate_force") + rebx_add_operator against the same scheme by hand."""
+    import json
+    import subprocess
+    exe = _compile_c(tmp_path, "c_resident_session.c", "c_resident_session")
+    run = subprocess.run([exe, "1000", "1000"], stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, timeout=600)
+    assert run.returncode == 0, (run.returncode, run.stdout, run.stderr)
+    rep = json.loads(run.stdout.strip().splitlines()[-1])
+    assert rep["ok"], rep
+    assert rep["wisdom_holman_merged"]["differing_coordinates"] == 0 and rep["leapfrog"]["differing_coordinates"] == 0, rep
+    assert rep["evaluate"]["differing"] == 0 and rep["operator_integrate_force_rk4"]["differing_coordinates"] == 0, rep
+
+
+@pytest.mark.parametrize("scheme", ["euler", "rk2", "rk4", "implicit_midpoint"])
+@pytest.mark.parametrize("force,coordinates", [("radiation_forces", "PARTICLE"), ("modify_orbits_forces", "JACOBI")])
+def test_operator_api_integrate_force_against_the_reference_operator(built, scheme, force, coordinates):
+    """The reference's operator entry points, driven identically on both libraries: rebx_load_operator("integrate_force"),
+    "force" / "integrator" parameters on the operator, rebx_integrate_force(sim, operator, dt) -- the product's runs
+    the scheme on the device for a device-backed force about particle 0 (radiation_forces) and the host schemes
+    around device sweeps otherwise (modify_orbits_forces in the Jacobi frame)."""
+    from oracle import oracle
+    from reboundx_b200 import _lib, workloads
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    if force == "radiation_forces":
+        w = workloads.debris_disk(20001)
+        w["beta"] = w["beta"]*50.0
+        dt = 3.0e8
+    else:
+        w = workloads.planetesimal_disk(2000)
+        w["tau_a"] = np.full(2000, -1e3); w["tau_e"] = np.full(2000, -1e2); w["tau_inc"] = np.full(2000, -1e2)
+        dt = 0.05
+    want, msgs = oracle.ref_integrate_force(w, force, dt, scheme, nsteps=3, coordinates=coordinates)
+    assert not [m for k, m in msgs if k == "error"]
+    got, msgs2 = oracle.ref_integrate_force(w, force, dt, scheme, nsteps=3, lib=_lib.load(), coordinates=coordinates)
+    assert not [m for k, m in msgs2 if k == "error"], msgs2
+    want, got = np.array(want), np.array(got)
+    assert np.any(want != np.array([w["vx"], w["vy"], w["vz"]]))
+    if force == "radiation_forces" and scheme != "implicit_midpoint":
+        assert np.array_equal(got, want)
+    else:
+        # implicit midpoint: the convergence sums run in another order on the device; Jacobi frame: O(N) scans vs the
+        # reference's O(N^2) loops -- tolerance relative to the largest velocity component
+        assert np.max(np.abs(got - want)/np.max(np.abs(want))) <= 1e-14
