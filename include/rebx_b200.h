@@ -187,17 +187,17 @@ int rebx_b200_jacobi_sweep(const rebx_b200_pass* pass, void* scratch, const doub
 int rebx_b200_jacobi_apply(const rebx_b200_state* st, void* scratch, const double* carry3, void* stream, int* launches);
 
 /* ---- 1PN `gr` effect (reference src/gr.c:65-164) for N_active <= REBX_B200_GR_MAX_ACTIVE ---------
- * Passed BY VALUE from host memory.  active[i] = {x, y, z, m} of active body i; com[] = the Jacobi
- * origin of a test particle: position, velocity and Newtonian acceleration of the actives' centre of
- * mass; mu = G*m_0.  Particles with global index < n_active are skipped by both kernels (the
+ * Passed BY VALUE from host memory.  active (DEVICE pointer) = n_active x {x, y, z, m} of the active bodies;
+ * com[] = the Jacobi origin of a test particle: position, velocity and Newtonian acceleration of the actives'
+ * centre of mass; mu = G*m_0.  Particles with global index < n_active are skipped by both kernels (the
  * O(n_active^2) part is the caller's). */
-#define REBX_B200_GR_MAX_ACTIVE 8
+#define REBX_B200_GR_MAX_ACTIVE 4096
 typedef struct rebx_b200_gr_args {
     int32_t n_active;
     int32_t max_iterations;
     double G, C2, mu;
     double com[9];
-    double active[REBX_B200_GR_MAX_ACTIVE][4];
+    const double* active;
 } rebx_b200_gr_args;
 /* pull[i*3+c] (device) = sum over the shard's test particles j of G m_j (x_i - x_j)_c / r^3. */
 int rebx_b200_gr_pull(const rebx_b200_state* st, const rebx_b200_gr_args* args, double* pull, void* workspace, void* stream, int* launches);

@@ -36,6 +36,8 @@ static std::unordered_map<struct rebx_extras*, std::unique_ptr<Side>>& sides() {
 }
 static std::atomic<std::uint64_t> g_epoch{1};
 
+static void forget_side(Side* side);
+
 Side* side_of(struct rebx_extras* rebx) {
     std::lock_guard<std::mutex> lk(g_mu);
     auto& m = sides();
@@ -46,6 +48,11 @@ Side* side_of(struct rebx_extras* rebx) {
 
 void side_drop(struct rebx_extras* rebx) {
     std::unique_ptr<Side> victim;
+    {
+        std::lock_guard<std::mutex> lk(g_mu);
+        auto it = sides().find(rebx);
+        if (it != sides().end()) forget_side(it->second.get());
+    }
     {
         std::lock_guard<std::mutex> lk(g_mu);
         auto& m = sides();
@@ -59,6 +66,76 @@ void side_drop(struct rebx_extras* rebx) {
 
 void mark_dirty(struct rebx_extras* rebx) {
     if (rebx) side_of(rebx)->generation++;
+}
+
+// ---- escaped value pointers -----------------------------------------------------------------
+static std::mutex g_esc_mu;
+static std::unordered_map<const struct rebx_param*, std::pair<Side*, size_t>>& escaped_index() {
+    static auto* m = new std::unordered_map<const struct rebx_param*, std::pair<Side*, size_t>>();
+    return *m;
+}
+static std::atomic<size_t> g_escaped_count{0};
+
+static bool value_bits(const struct rebx_param* p, std::uint64_t& out) {
+    if (!p || !p->value) return false;
+    switch (p->type) {
+        case REBX_TYPE_DOUBLE: std::memcpy(&out, p->value, 8); return true;
+        case REBX_TYPE_INT: case REBX_TYPE_UINT32: { std::uint32_t v; std::memcpy(&v, p->value, 4); out = v; return true; }
+        case REBX_TYPE_VEC3D: {
+            std::uint64_t w[3];
+            std::memcpy(w, p->value, 24);
+            out = w[0]*0x9e3779b97f4a7c15ULL ^ (w[1] + 0x7f4a7c15ULL)*0xbf58476d1ce4e5b9ULL ^ (w[2] + 0x1ce4e5b9ULL)*0x94d049bb133111ebULL;
+            return true;
+        }
+        default: return false;          // pointers, strings, forces: nothing a parameter table is built from
+    }
+}
+
+static void note_escape(struct rebx_extras* rebx, struct rebx_param* p) {
+    std::uint64_t bits;
+    if (!rebx || !value_bits(p, bits)) return;
+    Side* side = side_of(rebx);
+    std::lock_guard<std::mutex> lk(g_esc_mu);
+    auto& idx = escaped_index();
+    if (idx.find(p) != idx.end()) return;
+    idx.emplace(p, std::make_pair(side, side->escaped.size()));
+    side->escaped.push_back(Escaped{p, bits});
+    g_escaped_count.fetch_add(1, std::memory_order_relaxed);
+}
+
+static void forget_escape(const struct rebx_param* p) {          // the parameter is being freed
+    if (g_escaped_count.load(std::memory_order_relaxed) == 0) return;
+    std::lock_guard<std::mutex> lk(g_esc_mu);
+    auto& idx = escaped_index();
+    auto it = idx.find(p);
+    if (it == idx.end()) return;
+    it->second.first->escaped[it->second.second].param = nullptr;
+    idx.erase(it);
+    g_escaped_count.fetch_sub(1, std::memory_order_relaxed);
+}
+
+static void forget_side(Side* side) {
+    if (side->escaped.empty()) return;
+    std::lock_guard<std::mutex> lk(g_esc_mu);
+    auto& idx = escaped_index();
+    for (const Escaped& e : side->escaped) if (e.param && idx.erase(e.param)) g_escaped_count.fetch_sub(1, std::memory_order_relaxed);
+    side->escaped.clear();
+}
+
+void refresh_escaped(Side* side) {
+    if (side->escaped.empty()) return;
+    bool changed = false;
+    auto scan = [&](int, size_t lo, size_t hi) {
+        bool any = false;
+        for (size_t k = lo; k < hi; k++) {
+            Escaped& e = side->escaped[k];
+            std::uint64_t bits;
+            if (e.param && value_bits(e.param, bits) && bits != e.bits) { e.bits = bits; any = true; }
+        }
+        if (any) changed = true;        // benign race: every writer stores `true`
+    };
+    parallel_ranges(side->escaped.size(), scan);
+    if (changed) side->generation++;
 }
 void mark_all_dirty() { g_epoch.fetch_add(1, std::memory_order_relaxed); }
 std::uint64_t global_epoch() { return g_epoch.load(std::memory_order_relaxed); }
@@ -186,6 +263,7 @@ int rebx_add_param(struct rebx_extras* const rebx, struct rebx_node** apptr, str
 // reference src/core.c:864-875: only INT and DOUBLE payloads are owned by the list
 void rebx_free_param(struct rebx_param* param) {
     if (!param) return;
+    forget_escape(param);
     // param->name is interned (rebx_create_param) and shared: never freed here
     if ((param->type == REBX_TYPE_INT || param->type == REBX_TYPE_DOUBLE) && param->value) free(param->value);
     free(param);
@@ -449,7 +527,7 @@ struct rebx_force* rebx_get_force(struct rebx_extras* const rebx, const char* co
 // dirty; the library's own effects use rebxh::find_param instead.
 struct rebx_param* rebx_get_param_struct(struct rebx_extras* const rebx, struct rebx_node* ap, const char* const param_name) {
     struct rebx_param* p = find_param(ap, param_name);
-    if (p && rebx) mark_dirty(rebx);
+    if (p && rebx) { mark_dirty(rebx); note_escape(rebx, p); }      // the caller may write now AND keep the pointer for later
     return p;
 }
 
@@ -458,7 +536,16 @@ void* rebx_get_param(struct rebx_extras* const rebx, struct rebx_node* ap, const
     return p ? p->value : nullptr;
 }
 
+extern "C++" { static struct rebx_param* get_or_add_param_impl(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name); }
+
 struct rebx_param* rebx_get_or_add_param(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name) {
+    struct rebx_param* p = get_or_add_param_impl(rebx, apptr, param_name);
+    if (p && rebx) note_escape(rebx, p);       // exported: a foreign caller holds the struct (and its value pointer) from here on
+    return p;
+}
+
+extern "C++" {
+static struct rebx_param* get_or_add_param_impl(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name) {
     if (apptr == nullptr) {
         rebx_error(rebx, "REBOUNDx Error: Passed NULL apptr to rebx_add_param. See examples.\n");
         return nullptr;
@@ -478,11 +565,12 @@ struct rebx_param* rebx_get_or_add_param(struct rebx_extras* const rebx, struct 
     if (!rebx_add_param(rebx, apptr, param)) { rebx_free_param(param); return nullptr; }
     return param;
 }
+}  // extern "C++"
 
 extern "C++" {
 template <typename T>
 static void set_scalar(struct rebx_extras* rebx, struct rebx_node** apptr, const char* name, T val) {
-    struct rebx_param* param = rebx_get_or_add_param(rebx, apptr, name);
+    struct rebx_param* param = get_or_add_param_impl(rebx, apptr, name);
     if (!param) return;
     if (param->value == nullptr) param->value = rebx_malloc(rebx, sizeof(T));
     if (param->value) *static_cast<T*>(param->value) = val;
@@ -495,12 +583,12 @@ void rebx_set_param_uint32(struct rebx_extras* const rebx, struct rebx_node** ap
 void rebx_set_param_vec3d(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name, struct reb_vec3d val) { set_scalar<struct reb_vec3d>(rebx, apptr, param_name, val); }
 
 void rebx_set_param_pointer(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name, void* val) {
-    struct rebx_param* param = rebx_get_or_add_param(rebx, apptr, param_name);
+    struct rebx_param* param = get_or_add_param_impl(rebx, apptr, param_name);
     if (param) param->value = val;
 }
 
 void rebx_set_param_string(struct rebx_extras* const rebx, struct rebx_node** apptr, const char* const param_name, const char* const val) {
-    struct rebx_param* param = rebx_get_or_add_param(rebx, apptr, param_name);
+    struct rebx_param* param = get_or_add_param_impl(rebx, apptr, param_name);
     if (!param) return;
     if (param->value == nullptr) param->value = rebx_malloc(rebx, sizeof(char*));
     if (param->value) *static_cast<const char**>(param->value) = reb_simulation_register_name(rebx->sim, val);

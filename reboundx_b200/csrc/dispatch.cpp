@@ -562,7 +562,7 @@ static bool entries_for_force(struct reb_simulation* sim, Side* side, DeviceCont
         const size_t A = (sim->N_active == SIZE_MAX || sim->N_active > N) ? N : sim->N_active;
         if (A < 1 || N < 2) return false;
         if (A > REBX_B200_GR_MAX_ACTIVE) {
-            reb_simulation_error(sim, "REBOUNDx-B200 Error: the device implementation of 'gr' handles up to 8 active (massive) bodies plus any number of test particles; set sim->N_active. (With N_active unset the reference recomputes O(N^2) Newtonian gravity.)\n");
+            reb_simulation_error(sim, "REBOUNDx-B200 Error: 'gr' handles up to 4096 active (massive) bodies -- their mutual terms are O(N_active^2) on the host -- plus any number of test particles; set sim->N_active. (With N_active unset the reference recomputes O(N^2) Newtonian gravity among ALL particles.)\n");
             return false;
         }
         const int* it = static_cast<const int*>(find_value(force->ap, "max_iterations"));
@@ -677,6 +677,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         return;
     }
     ctx->stats.calls++;
+    refresh_escaped(side);          // values written through pointers the getters handed out (no API call announces them)
 
     std::vector<Entry> entries;
     for (int f = 0; f < nf; f++) entries_for_force(sim, side, ctx, forces[f], kind_of(forces[f]), particles, N, entries, ctx->tables);
@@ -823,12 +824,18 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 std::memset(&ga, 0, sizeof ga);
                 ga.n_active = en.n_active; ga.max_iterations = (int)en.scal[2];
                 ga.G = sim->G; ga.C2 = en.scal[1]; ga.mu = sim->G*particles[0].m;
-                for (int i = 0; i < en.n_active; i++) { ga.active[i][0] = particles[i].x; ga.active[i][1] = particles[i].y; ga.active[i][2] = particles[i].z; ga.active[i][3] = particles[i].m; }
-                REBXB_CUDA(ctx->grbuf.ensure(64*sizeof(double)), "allocating gr scratch");
-                REBXB_CUDA(ctx->gr_h.ensure(64*sizeof(double)), "allocating pinned gr scratch");
+                // device scratch: pull [3A] | convergence flag | actives {x, y, z, m} [4A]; pinned mirror of the first two + staging of the third
+                const size_t Aq = (size_t)en.n_active;
+                REBXB_CUDA(ctx->grbuf.ensure((7*Aq + 16)*sizeof(double)), "allocating gr scratch");
+                REBXB_CUDA(ctx->gr_h.ensure((7*Aq + 16)*sizeof(double)), "allocating pinned gr scratch");
                 double* pull_d = static_cast<double*>(ctx->grbuf.p);
-                int* flag_d = reinterpret_cast<int*>(pull_d + 32);
+                int* flag_d = reinterpret_cast<int*>(pull_d + 3*Aq);
+                double* act_d = pull_d + 3*Aq + 8;
                 double* pull_h = static_cast<double*>(ctx->gr_h.p);
+                double* act_h = pull_h + 3*Aq + 8;
+                for (size_t i = 0; i < Aq; i++) { act_h[4*i] = particles[i].x; act_h[4*i + 1] = particles[i].y; act_h[4*i + 2] = particles[i].z; act_h[4*i + 3] = particles[i].m; }
+                REBXB_CUDA(cudaMemcpyAsync(act_d, act_h, 4*Aq*sizeof(double), cudaMemcpyHostToDevice, s), "copying the active bodies");
+                ga.active = act_d;
                 REBXB_CUDA(cudaMemsetAsync(flag_d, 0, sizeof(int), s), "clearing the convergence flag");
                 REBXB_CUDA((cudaError_t)rebx_b200_gr_pull(&st, &ga, pull_d, D.work[b].p, s, &launches), "reducing the test particles' pull");
                 REBXB_CUDA(cudaMemcpyAsync(pull_h, pull_d, (size_t)en.n_active*3*sizeof(double), cudaMemcpyDeviceToHost, s), "copying the pull");
@@ -836,8 +843,8 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 bool host_nc = false;
                 gr_host_actives(particles, en.n_active, sim->G, ga.C2, ga.max_iterations, pull_h, ga, en.gr_active, host_nc);
                 REBXB_CUDA((cudaError_t)rebx_b200_gr_sweep(&st, &ga, flag_d, s, &launches), "launching the gr sweep");
-                REBXB_CUDA(cudaMemcpyAsync(pull_h + 32, flag_d, sizeof(int), cudaMemcpyDeviceToHost, s), "copying the convergence flag");
-                if (host_nc) *reinterpret_cast<int*>(pull_h + 40) = 1; else *reinterpret_cast<int*>(pull_h + 40) = 0;
+                REBXB_CUDA(cudaMemcpyAsync(pull_h + 3*Aq, flag_d, sizeof(int), cudaMemcpyDeviceToHost, s), "copying the convergence flag");
+                *reinterpret_cast<int*>(pull_h + 3*Aq + 4) = host_nc ? 1 : 0;
                 e0 = e1;
                 continue;
             }
@@ -905,8 +912,8 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 particles[i].ay += entries[e].gr_active[(size_t)i].ay;
                 particles[i].az += entries[e].gr_active[(size_t)i].az;
             }
-            const double* gh = static_cast<const double*>(ctx->gr_h.p);
-            if (*reinterpret_cast<const int*>(gh + 32) || *reinterpret_cast<const int*>(gh + 40))
+            const double* gh = static_cast<const double*>(ctx->gr_h.p) + 3*(size_t)entries[e].n_active;
+            if (*reinterpret_cast<const int*>(gh) || *reinterpret_cast<const int*>(gh + 4))
                 reb_simulation_warning(sim, "REBOUNDx Warning: 10 iterations in gr.c failed to converge. This is typically because the perturbation is too strong for the current implementation.");
             continue;
         }
@@ -950,6 +957,7 @@ static double run_potential(struct rebx_extras* rebx, int kind, const struct reb
         return 0;
     }
     DevSlot& P0 = *ctx->devs[0];
+    refresh_escaped(side);
     std::vector<Entry> entries;
     Entry e;
     e.kind = kind; e.scal[0] = sim->G;

@@ -20,8 +20,15 @@ struct DeviceContext;   // dispatch.cpp
 
 // Per-rebx_extras state that cannot live in the struct itself (Python allocates exactly
 // seven pointers, reference reboundx/extras.py:327-333).
+// A parameter whose interior value pointer was handed to the caller (rebx_get_param & co.): the reference's documented C
+// idiom keeps such a pointer and writes through it between force evaluations (doc/c_quickstart.rst:49-54), which no API
+// call announces.  The value's bits at the last check are remembered; every dispatch re-reads the (few) escaped values
+// and rebuilds the tables when one moved.
+struct Escaped { struct rebx_param* param; std::uint64_t bits; };
+
 struct Side {
     std::uint64_t generation = 1;          // bumped whenever any parameter list may have changed
+    std::vector<Escaped> escaped;          // see above; entries of freed parameters are nulled
     std::unordered_map<std::string, int> types;   // mirror of registered_params for O(1) rebx_get_type
     std::unique_ptr<DeviceContext, void (*)(DeviceContext*)> dev{nullptr, nullptr};
 };
@@ -34,6 +41,9 @@ void side_drop(struct rebx_extras* rebx);
 void mark_dirty(struct rebx_extras* rebx);
 // Some list head was freed without a rebx pointer at hand (sim->free_particle_ap hook).
 void mark_all_dirty();
+// Re-reads the values whose pointers escaped through the getters; bumps the generation (tables rebuilt) if one changed.
+// Called at the start of every dispatch / session call.  Cost: one 8-byte read per escaped parameter.
+void refresh_escaped(Side* side);
 std::uint64_t global_epoch();
 
 // Interned parameter-name storage: every rebx_param created by this library points at one

@@ -1119,22 +1119,27 @@ int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* str
 }
 
 int rebx_b200_gr_pull(const rebx_b200_state* st, const rebx_b200_gr_args* args, double* pull, void* workspace, void* stream, int* launches) {
-    if (!st || !args || !pull || !workspace || !st->m) return cudaErrorInvalidValue;
+    if (!st || !args || !pull || !workspace || !st->m || !args->active) return cudaErrorInvalidValue;
     if (args->n_active < 1 || args->n_active > REBX_B200_GR_MAX_ACTIVE) return cudaErrorInvalidValue;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
     if (st->n == 0) return cudaMemsetAsync(pull, 0, (size_t)args->n_active*3*sizeof(double), s);
     int grid = grid_for(reinterpret_cast<const void*>(gr_pull_kernel), st->n);
-    const int cap = kMaxBlocks*REBX_B200_MAX_EFFECTS/REBX_B200_GR_MAX_ACTIVE;      // workspace rows available
+    const int cap = kMaxBlocks*REBX_B200_MAX_EFFECTS/kGrChunk;      // workspace rows available
     if (grid > cap) grid = cap;
-    gr_pull_kernel<<<grid, kThreads, 0, s>>>(*st, *args, static_cast<double*>(workspace));
-    gr_pull_finalize_kernel<<<1, kThreads, 0, s>>>(static_cast<const double*>(workspace), grid, args->n_active, pull);
+    int nl = 0;
+    for (int first = 0; first < args->n_active; first += kGrChunk) {        // kGrChunk actives per sweep over the test particles
+        const int count = args->n_active - first < kGrChunk ? args->n_active - first : kGrChunk;
+        gr_pull_kernel<<<grid, kThreads, 0, s>>>(*st, *args, first, static_cast<double*>(workspace));
+        gr_pull_finalize_kernel<<<1, kThreads, 0, s>>>(static_cast<const double*>(workspace), grid, count, pull + (size_t)first*3);
+        nl += 2;
+    }
     cudaError_t err = cudaGetLastError();
-    if (err == cudaSuccess && launches) *launches += 2;
+    if (err == cudaSuccess && launches) *launches += nl;
     return err;
 }
 
 int rebx_b200_gr_sweep(const rebx_b200_state* st, const rebx_b200_gr_args* args, int* not_converged, void* stream, int* launches) {
-    if (!st || !args || !not_converged || !st->vx || !st->ax) return cudaErrorInvalidValue;
+    if (!st || !args || !not_converged || !st->vx || !st->ax || !args->active) return cudaErrorInvalidValue;
     if (args->n_active < 1 || args->n_active > REBX_B200_GR_MAX_ACTIVE) return cudaErrorInvalidValue;
     if (st->n == 0) return 0;
     const int grid = grid_for(reinterpret_cast<const void*>(gr_sweep_kernel), st->n);

@@ -3,7 +3,9 @@
 // moves to Jacobi coordinates, solves a per-particle fixed point for the Jacobi velocity
 // (:114-129), evaluates the post-Newtonian acceleration (:135-148) and transforms back.
 //
-// Split used here (N_active <= REBX_B200_GR_MAX_ACTIVE, the regime of a test-particle ensemble):
+// Split used here (N_active <= REBX_B200_GR_MAX_ACTIVE = 4096 active bodies -- the host part is O(N_active^2) -- plus any
+// number of test particles).  The actives {x, y, z, m} live in a device array; the sweep stages them through shared
+// memory in tiles, the pull reduction takes them kGrChunk at a time (one launch per chunk, per-thread accumulators):
 //   gr_pull_kernel   sum over test particles j of G m_j (x_i - x_j)/r^3 for each active body i --
 //                    what the test particles contribute to the actives' Newtonian acceleration
 //                    (gr.c:79-96 with j >= N_active); exact zeros for massless test particles.
@@ -16,12 +18,19 @@
 
 namespace rebxb {
 
+constexpr int kGrChunk = 8;         // actives per launch of the pull reduction (per-thread accumulators in registers)
+
+// partials[block][kGrChunk][3] for the actives first .. first + kGrChunk - 1
 __global__ void __launch_bounds__(kThreads)
-gr_pull_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_gr_args A, double* __restrict__ partials) {
+gr_pull_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_gr_args A, int first, double* __restrict__ partials) {
     __shared__ double s_red[kWarps][3];
-    double acc[REBX_B200_GR_MAX_ACTIVE][3];
+    __shared__ double s_act[kGrChunk][4];
+    const int count = (A.n_active - first < kGrChunk) ? A.n_active - first : kGrChunk;
+    if (threadIdx.x < count*4) s_act[threadIdx.x/4][threadIdx.x%4] = A.active[(size_t)(first + threadIdx.x/4)*4 + threadIdx.x%4];
+    __syncthreads();
+    double acc[kGrChunk][3];
 #pragma unroll
-    for (int i = 0; i < REBX_B200_GR_MAX_ACTIVE; i++) acc[i][0] = acc[i][1] = acc[i][2] = 0.0;
+    for (int i = 0; i < kGrChunk; i++) acc[i][0] = acc[i][1] = acc[i][2] = 0.0;
     const int64_t stride = (int64_t)gridDim.x*kThreads;
     for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < st.n; k += stride) {
         if (st.index_base + k < A.n_active) continue;
@@ -29,9 +38,9 @@ gr_pull_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_gr_args A, 
         if (mj == 0.0) continue;                    // contributes exact zeros
         const double xj = st.x[k], yj = st.y[k], zj = st.z[k];
 #pragma unroll
-        for (int i = 0; i < REBX_B200_GR_MAX_ACTIVE; i++) {
-            if (i < A.n_active) {
-                const double dx = A.active[i][0] - xj, dy = A.active[i][1] - yj, dz = A.active[i][2] - zj;
+        for (int i = 0; i < kGrChunk; i++) {
+            if (i < count) {
+                const double dx = s_act[i][0] - xj, dy = s_act[i][1] - yj, dz = s_act[i][2] - zj;
                 const double r2 = dx*dx + dy*dy + dz*dz;
                 const double r = sqrt(r2);
                 const double prefac = A.G/(r2*r);
@@ -39,7 +48,7 @@ gr_pull_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_gr_args A, 
             }
         }
     }
-    for (int i = 0; i < A.n_active; i++) {
+    for (int i = 0; i < count; i++) {
         double v[3] = {acc[i][0], acc[i][1], acc[i][2]};
 #pragma unroll
         for (int c = 0; c < 3; c++)
@@ -52,17 +61,17 @@ gr_pull_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_gr_args A, 
             double s = 0.0;
 #pragma unroll
             for (int w = 0; w < kWarps; w++) s += s_red[w][threadIdx.x];
-            partials[((size_t)blockIdx.x*REBX_B200_GR_MAX_ACTIVE + i)*3 + threadIdx.x] = s;
+            partials[((size_t)blockIdx.x*kGrChunk + i)*3 + threadIdx.x] = s;
         }
     }
 }
 
 __global__ void __launch_bounds__(kThreads)
-gr_pull_finalize_kernel(const double* __restrict__ partials, int nblocks, int n_active, double* __restrict__ pull) {
+gr_pull_finalize_kernel(const double* __restrict__ partials, int nblocks, int count, double* __restrict__ pull) {
     __shared__ double s[kThreads];
-    for (int q = 0; q < n_active*3; q++) {
+    for (int q = 0; q < count*3; q++) {
         double acc = 0.0;
-        for (int b = threadIdx.x; b < nblocks; b += kThreads) acc += partials[(size_t)b*REBX_B200_GR_MAX_ACTIVE*3 + q];
+        for (int b = threadIdx.x; b < nblocks; b += kThreads) acc += partials[(size_t)b*kGrChunk*3 + q];
         s[threadIdx.x] = acc;
         __syncthreads();
         for (int w = kThreads/2; w > 0; w >>= 1) {
@@ -76,20 +85,34 @@ gr_pull_finalize_kernel(const double* __restrict__ partials, int nblocks, int n_
 
 __global__ void __launch_bounds__(kThreads)
 gr_sweep_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_gr_args A, int* __restrict__ not_converged) {
+    constexpr int kTileActives = 256;
+    __shared__ double s_act[kTileActives][4];
     const double C2 = A.C2, mu = A.mu;
     const int64_t stride = (int64_t)gridDim.x*kThreads;
-    for (int64_t k = (int64_t)blockIdx.x*kThreads + threadIdx.x; k < st.n; k += stride) {
-        if (st.index_base + k < A.n_active) continue;           // actives are finished on the host
-        const double x = st.x[k], y = st.y[k], z = st.z[k];
-        // Newtonian acceleration from the active bodies (gr.c:79-96, role "j")
+    // every thread of the CTA runs the same number of rounds (the tile loads below are CTA-wide barriers)
+    const int64_t rounds = (st.n + stride - 1)/stride;
+    for (int64_t round = 0; round < rounds; round++) {
+        const int64_t k = round*stride + (int64_t)blockIdx.x*kThreads + threadIdx.x;
+        const bool live = k < st.n && st.index_base + k >= A.n_active;       // actives are finished on the host
+        const double x = live ? st.x[k] : 0.0, y = live ? st.y[k] : 0.0, z = live ? st.z[k] : 0.0;
+        // Newtonian acceleration from the active bodies (gr.c:79-96, role "j"), ascending i like the reference
         double nx = 0.0, ny = 0.0, nz = 0.0;
-        for (int i = 0; i < A.n_active; i++) {
-            const double dx = A.active[i][0] - x, dy = A.active[i][1] - y, dz = A.active[i][2] - z;
-            const double r2 = dx*dx + dy*dy + dz*dz;
-            const double r = sqrt(r2);
-            const double prefac = A.G/(r2*r);
-            nx += prefac*A.active[i][3]*dx; ny += prefac*A.active[i][3]*dy; nz += prefac*A.active[i][3]*dz;
+        for (int base = 0; base < A.n_active; base += kTileActives) {
+            const int cnt = (A.n_active - base < kTileActives) ? A.n_active - base : kTileActives;
+            if (A.n_active > kTileActives || round == 0) {        // a single tile stays valid for all rounds
+                __syncthreads();
+                for (int q = threadIdx.x; q < cnt*4; q += kThreads) s_act[q/4][q%4] = A.active[(size_t)base*4 + q];
+                __syncthreads();
+            }
+            if (live) for (int i = 0; i < cnt; i++) {
+                const double dx = s_act[i][0] - x, dy = s_act[i][1] - y, dz = s_act[i][2] - z;
+                const double r2 = dx*dx + dy*dy + dz*dz;
+                const double r = sqrt(r2);
+                const double prefac = A.G/(r2*r);
+                nx += prefac*s_act[i][3]*dx; ny += prefac*s_act[i][3]*dy; nz += prefac*s_act[i][3]*dz;
+            }
         }
+        if (!live) continue;
         // Jacobi coordinates of a test particle: relative to the centre of mass of the actives
         const double px = x - A.com[0], py = y - A.com[1], pz = z - A.com[2];
         const double pvx = st.vx[k] - A.com[3], pvy = st.vy[k] - A.com[4], pvz = st.vz[k] - A.com[5];

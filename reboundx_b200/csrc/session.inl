@@ -95,6 +95,7 @@ static int session_bind(rebx_b200_session* s, struct rebx_force** only, int n_on
 
 // Parameters changed through the API since the tables were built: rebuild (cheap check per call).
 static int session_refresh(rebx_b200_session* s) {
+    refresh_escaped(s->side);
     if (s->generation == s->side->generation && s->epoch == global_epoch()) return 0;
     return session_bind(s, nullptr, 0);
 }

@@ -169,6 +169,11 @@ class Simulation:
     def particle_ap(self, i):
         return self._shim.reb_shim_particle_ap(self._p, c_size_t(i))
 
+    def add_particle(self, **fields):
+        """reb_simulation_add of one particle (x, y, z, vx, vy, vz, m, r)."""
+        self._shim.reb_simulation_add.argtypes = [c_void_p, RebParticle]
+        self._shim.reb_simulation_add(self._p, RebParticle(**{k: float(v) for k, v in fields.items()}))
+
     def remove_particle(self, i, keep_sorted=True):
         self._shim.reb_simulation_remove_particle(self._p, c_size_t(i), c_int(1 if keep_sorted else 0))
 
