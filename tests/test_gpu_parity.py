@@ -667,6 +667,510 @@ def test_gr_refuses_an_unbounded_number_of_active_bodies(built):
     rebx.detach(); sim.free()
 
 
+def test_resident_leapfrog_matches_host_harness_bitwise(built):
+    """drift/kick/gravity kept on the device around the force sweep.  1000
+    drift-kick-drift steps of a resident shard (no PCIe traffic) reproduce, bit for bit, the host
+    harness stepping the reference-compiled radiation force through sim->additional_forces."""
+    import os, sys
+    import torch
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden"))
+    import golden_io
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    w = workloads.debris_disk(1000, seed=3)
+    w["beta"] = np.full(1000, 0.1)
+    case = {"G": w["G"], "integrator": "whfast", "state": {k: w[k] for k in ("x", "y", "z", "vx", "vy", "vz", "m", "r")}, "acc0": None,
+            "forces": [{"name": "radiation_forces", "params": {"c": w["c"]}}],
+            "particle_params": {"beta": (np.arange(1, 1001, dtype=np.int64), w["beta"])}}
+    ref = _trajectory(case, oracle.ref_lib(), 1000, "leapfrog", 1e8, 1)
+    sh = device.Shard(w, ["radiation_forces"], "cuda:0")
+    for _ in range(1000):
+        sh.leapfrog_step(1e8, w["G"])
+    torch.cuda.synchronize()
+    got = np.array(sh.posvel())
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("which", ["debris_disk", "ring_massive"])
+def test_resident_wisdom_holman_matches_host_harness(built, which):
+    """BASELINE config 2 as quoted ("radiation_forces under WHFast"), resident: 1000 Wisdom-Holman steps
+    (Kepler drift about the star on the device, rebx_b200_kepler_drift; kick by the stacked effects) against
+    the host harness `wisdom_holman` stepping the reference-compiled force.  The Kepler arithmetic is the
+    same source on both sides (csrc/kepler_core.h), so radiation is bit for bit; with a massive ring the
+    back-reaction on the planet is summed in another order (tolerance of criterion (ii))."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    if which == "debris_disk":
+        w, add, dt = workloads.debris_disk(1000, seed=3), ["radiation_forces"], 1e8
+    else:
+        w, add, dt = workloads.circumplanetary_ring(1000, massive=True), ["gravitational_harmonics", "gr_potential"], 50.0
+    ref = _trajectory(w, oracle.ref_lib(), 1000, "wisdom_holman", dt, 1, add)
+    sh = device.Shard(w, add[::-1], "cuda:0")
+    for _ in range(1000):
+        sh.wh_step(dt, w["G"])
+    torch.cuda.synchronize()
+    got = np.array(sh.posvel())
+    if which == "debris_disk":
+        assert np.array_equal(got, ref)
+    else:
+        _assert_trajectories_agree(got, ref)
+    # the merged form (one Kepler drift of dt between consecutive kicks), against the host harness doing the same
+    ref = _trajectory(w, oracle.ref_lib(), 1000, "wisdom_holman_merged", dt, 1, add)
+    for fused in (True, False):      # radiation: kick + drift in one sweep (rebx_b200_wh_kick_drift) or as separate kernels
+        sh = device.Shard(w, add[::-1], "cuda:0")
+        sh.wh_steps(1000, dt, w["G"], fused=fused)
+        torch.cuda.synchronize()
+        got = np.array(sh.posvel())
+        if which == "debris_disk":
+            assert np.array_equal(got, ref)
+        else:
+            _assert_trajectories_agree(got, ref)
+
+
+@pytest.mark.parametrize("scheme", ["leapfrog", "whfast"])
+def test_cuda_graph_of_resident_steps(built, scheme):
+    """device.Shard.capture_steps: a CUDA graph of 20 resident steps of the 1000-grain example, replayed 10 times,
+    gives the bits of 200 eager steps (and the launches no longer dominate: timed in tools/latency_probe.py)."""
+    import torch
+    from reboundx_b200 import device, workloads
+    w = workloads.debris_disk(1000, seed=3)
+    eager = device.Shard(w, ["radiation_forces"], "cuda:0")
+    if scheme == "whfast":
+        for _ in range(10):
+            eager.wh_steps(20, 1e8, w["G"])
+    else:
+        for _ in range(200):
+            eager.fused_leapfrog_step(1e8, w["G"])
+    torch.cuda.synchronize()
+    graphed = device.Shard(w, ["radiation_forces"], "cuda:0")
+    g = graphed.capture_steps(20, 1e8, w["G"], scheme)
+    for _ in range(10):
+        g.replay()
+    torch.cuda.synchronize()
+    assert np.array_equal(np.array(graphed.posvel()), np.array(eager.posvel()))
+
+
+@pytest.mark.parametrize("which", ["debris_disk", "ring_massive", "asteroids", "planetesimals"])
+def test_fused_leapfrog_step_equals_separate_sweeps(built, which):
+    """rebx_b200_leapfrog_step (one sweep, accelerations in registers) against the five separate
+    sweeps of Shard.leapfrog_step: bit-identical state after 100 steps, central body included."""
+    import torch
+    from reboundx_b200 import device, workloads as W
+    if which == "debris_disk":
+        w, order, dt = W.debris_disk(20001), ["radiation_forces"], 1e8
+    elif which == "ring_massive":
+        w, order, dt = W.circumplanetary_ring(20001, massive=True, tilted=True), ["gr_potential", "gravitational_harmonics"], 50.0
+    elif which == "asteroids":
+        w, order, dt = W.asteroid_ensemble(20001), ["gr_potential", "yarkovsky_effect"], 0.01
+    else:
+        w, order, dt = W.planetesimal_disk(20001), ["type_I_migration", "gas_damping_timescale", "modify_orbits_forces"], 0.002
+    a = device.Shard(w, order, "cuda:0")
+    b = device.Shard(w, order, "cuda:0")
+    for _ in range(100):
+        a.leapfrog_step(dt, w["G"])
+        b.fused_leapfrog_step(dt, w["G"])
+    torch.cuda.synchronize()
+    pa, pb = np.array(a.posvel()), np.array(b.posvel())
+    if which == "debris_disk":
+        assert np.array_equal(pa, pb)
+        assert torch.equal(a.bodies[:, :8], b.bodies[:, :8])
+    else:
+        # massive particles: the back-reaction onto the central body is a reduction whose partial sums
+        # follow the grid, and the two kernels run different grids -> last-bit differences in the
+        # body's kick.  Everything else is the same arithmetic.
+        _assert_trajectories_agree(pa, pb, tol=1e-11)
+
+
+# ---- tolerance-mode arithmetic (kernels_tol.cu): FMA, shared reciprocals; default stays bit-exact -------------
+TOL_CASES = {
+    "debris_disk": (["radiation_forces"], {}),
+    "circumplanetary_ring": (["gravitational_harmonics", "gr_potential"], {"tilted": True, "massive": True}),
+    "asteroid_ensemble": (["yarkovsky_effect", "gr_potential"], {}),
+    "planetesimal_disk": (TRIO, {}),
+}
+
+
+@pytest.mark.parametrize("name", sorted(TOL_CASES))
+@pytest.mark.parametrize("base", ["zero", "gravity"])
+def test_tolerance_mode_against_the_reference(built, monkeypatch, name, base):
+    """REBX_B200_MATH=tolerance through the drop-in call, against the reference's own loops: the north-star bar
+    (<= 1e-13) norm-wise on the pure force AND on the gravity base, the per-component picture pinned by the
+    recorded guards.  The kernels must really be the tolerance ones (results differ from the exact build's)."""
+    from reboundx_b200 import workloads
+    add, kw = TOL_CASES[name]
+    w = getattr(workloads, name)(200001, **kw)
+    acc0 = acc_variants(w, 31)[base]
+    want, br = oracle_acc(w, add, acc0)
+    exact, _ = device_acc(w, add, acc0)
+    monkeypatch.setenv("REBX_B200_MATH", "tolerance")
+    got, _ = device_acc(w, add, acc0)
+    assert not errors(got, exact)["bit_identical"], "REBX_B200_MATH=tolerance did not select the tolerance kernels"
+    e = errors(got, want, skip=(0,))
+    guard(f"tolerance_mode/{name}/{base}", e, frac=2e-5)
+    # the central body: back-reaction sums against the long-double sum of the oracle's terms
+    reducing = [f for f in add if f in br]
+    if reducing:
+        a0 = [0.0, 0.0, 0.0] if acc0 is None else [acc0[k][0] for k in range(3)]
+        exact0 = np.array(a0) + sum(br[f][:3] for f in reducing)
+        scale = sum(br[f][3:] for f in reducing) + np.abs(a0)
+        for k in range(3):
+            assert abs(got[k][0] - exact0[k]) <= 1e-12*scale[k] + 1e-300, (k, got[k][0], exact0[k], scale[k])
+
+
+def test_tolerance_mode_resident_full_size(built):
+    """device.Shard(math="tolerance") at the configurations' full sizes: finite everywhere, and within the tolerance of
+    the bit-exact sweep on every particle (norm-wise; the exact sweep itself is pinned to the oracle above)."""
+    import torch
+    from reboundx_b200 import device, workloads
+    for name, (n, add, _) in FULL.items():
+        w = getattr(workloads, name)(n)
+        acc0 = workloads.gravity_like_acc(w, np.random.default_rng(98))
+        res = {}
+        for math in ("exact", "tolerance"):
+            sh = device.Shard(w, add[::-1], "cuda:0", acc0=acc0, math=math, standalone=True)
+            sh.evaluate()
+            torch.cuda.synchronize()
+            res[math] = sh.acc()
+            del sh
+        e = errors(res["tolerance"], res["exact"])
+        assert all(np.isfinite(a).all() for a in res["tolerance"])
+        assert e["max_normwise"] <= TOL, (name, e)
+        assert not e["bit_identical"], name
+
+
+# ---- BASELINE.json full sizes: size-independent properties ---------------------------------------------
+def _subsample(w, idx, per_particle):
+    """Workload restricted to the central body + the particles `idx` (global indices >= 1)."""
+    sub = {}
+    for k, v in w.items():
+        if isinstance(v, np.ndarray) and v.shape[0] == w["x"].shape[0]:
+            sub[k] = np.concatenate([v[:1], v[idx]])
+        elif isinstance(v, np.ndarray) and k in per_particle:
+            sub[k] = v[idx - 1]
+        else:
+            sub[k] = v
+    return sub
+
+
+FULL = {
+    "debris_disk": (10_000_000, ["radiation_forces"], ["beta"]),
+    "circumplanetary_ring": (10_000_000, ["gravitational_harmonics", "gr_potential"], []),
+    "asteroid_ensemble": (1_000_000, ["yarkovsky_effect", "gr_potential"],
+                          ["ye_body_density", "ye_rotation_period", "ye_thermal_inertia", "ye_albedo", "ye_emissivity", "ye_k",
+                           "ye_spin_axis_x", "ye_spin_axis_y", "ye_spin_axis_z", "ye_flag"]),
+    "planetesimal_disk": (1_000_000, TRIO, ["tau_a", "tau_e", "tau_inc", "d_factor"]),
+}
+
+
+@pytest.mark.parametrize("name", sorted(FULL))
+def test_full_size_against_oracle_on_a_random_subsample(built, name):
+    """At the configuration's full size the oracle cannot be run on everything in seconds, but every
+    particle's force depends only on itself and the central body: the oracle evaluated on
+    (body + 50 000 random particles) must reproduce the full device result at those indices --
+    bit for bit where the arithmetic is + - * / sqrt, to the tolerance otherwise.  Massless
+    ensembles only (a massive ensemble couples through the back-reaction sum, tested at small N)."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    n, add, per_particle = FULL[name]
+    w = getattr(workloads, name)(n)
+    w["m"][1:] = 0.0 if name in ("debris_disk", "circumplanetary_ring") else w["m"][1:]
+    rng = np.random.default_rng(99)
+    acc0 = workloads.gravity_like_acc(w, rng)
+    sh = device.Shard(w, add[::-1], "cuda:0", acc0=acc0)
+    sh.launch()
+    torch.cuda.synchronize()
+    got = sh.acc()
+    idx = np.sort(rng.choice(np.arange(1, n + 1), size=50_000, replace=False))
+    sub = _subsample(w, idx, per_particle)
+    sub_acc0 = [np.concatenate([a[:1], a[idx]]) for a in acc0]
+    want, _ = oracle.port_apply(sub, add[::-1], sub_acc0)
+    g = [a[idx] for a in got]
+    ww = [a[1:] for a in want]
+    e = errors(g, ww)
+    if name in ("debris_disk", "circumplanetary_ring"):
+        assert e["bit_identical"], e
+    else:
+        guard(f"full_size_subsample/{name}", e)
+    assert all(np.isfinite(a).all() for a in got)
+
+
+def test_fused_wisdom_holman_sweep_with_yarkovsky(built):
+    """rebx_b200_wh_kick_drift's second instantiation (yarkovsky_effect alone: all three modes in the ensemble):
+    the fused kick + drift sweep gives the bits of the separate kernels, and follows the host harness stepping the
+    reference-compiled force to the tolerance of criterion (ii)."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    w = workloads.asteroid_ensemble(3000)
+    dt, steps = 0.01, 300
+    out = []
+    for fused in (True, False):
+        sh = device.Shard(w, ["yarkovsky_effect"], "cuda:0")
+        sh.wh_steps(steps, dt, w["G"], fused=fused)
+        torch.cuda.synchronize()
+        out.append(np.array(sh.posvel()))
+    assert np.array_equal(out[0], out[1])
+    if oracle.have_ref():
+        ref = _trajectory(w, oracle.ref_lib(), steps, "wisdom_holman_merged", dt, 1, ["yarkovsky_effect"])
+        _assert_trajectories_agree(out[0], ref)
+
+
+def test_full_size_resident_wisdom_holman_against_the_host_harness_on_a_subsample(built):
+    """BASELINE config 2 at its full size, "radiation_forces under WHFast": 50 resident Wisdom-Holman steps of 10^7
+    grains (fused kick + Kepler drift sweeps), and -- test particles being independent -- the host harness stepping
+    the reference-compiled force on a random subsample of 2000 of them must land on the same bits."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    n, steps, dt = 10_000_000, 50, 1e8
+    w = workloads.debris_disk(n, seed=3)
+    sh = device.Shard(w, ["radiation_forces"], "cuda:0")
+    sh.wh_steps(steps, dt, w["G"])
+    torch.cuda.synchronize()
+    got = np.array(sh.posvel())
+    idx = np.sort(np.random.default_rng(17).choice(np.arange(1, n + 1), size=2000, replace=False))
+    sub = _subsample(w, idx, ["beta"])
+    ref = _trajectory(sub, oracle.ref_lib(), steps, "wisdom_holman_merged", dt, 1, ["radiation_forces"])
+    assert np.array_equal(got[:, np.concatenate([[0], idx])], ref)
+    moved = np.abs(got[0, 1:] - w["x"][1:])
+    assert np.median(moved) > 1e6                     # metres: the grains did move
+
+
+def test_full_size_radiation_is_linear_in_beta_and_shard_independent(built):
+    """Config 2 at 10^7: doubling every beta doubles every force exactly (a power-of-two scaling
+    commutes with each rounding), and cutting the ensemble into three ragged shards changes no bit."""
+    import torch
+    from reboundx_b200 import device, workloads
+    n = 10_000_000
+    w = workloads.debris_disk(n)
+    one = device.Shard(w, ["radiation_forces"], "cuda:0")
+    one.launch()
+    w2 = dict(w); w2["beta"] = 2.0*w["beta"]
+    two = device.Shard(w2, ["radiation_forces"], "cuda:0")
+    two.launch()
+    torch.cuda.synchronize()
+    for k in ("ax", "ay", "az"):
+        assert torch.equal(two.state[k], 2.0*one.state[k])
+        assert bool(torch.any(one.state[k] != 0))
+    del two
+    cuts = [0, 3_333_333, 6_000_001, n + 1]
+    parts = []
+    for lo, hi in zip(cuts, cuts[1:]):
+        sh = device.Shard(w, ["radiation_forces"], "cuda:0", lo=lo, hi=hi)
+        sh.launch()
+        parts.append(sh)
+    torch.cuda.synchronize()
+    for k in ("ax", "ay", "az"):
+        assert torch.equal(torch.cat([p.state[k] for p in parts]), one.state[k])
+
+
+def test_full_size_host_facing_call(built):
+    """The exact call bench.py's e2e leg times -- sim->additional_forces(sim) on 10^7 host AoS particles,
+    chunked three-buffer pipeline -- checked against the oracle on a random subsample, bit for bit."""
+    from oracle import oracle
+    from reboundx_b200 import scenarios, workloads
+    n = 10_000_000
+    w = workloads.debris_disk(n)
+    rng = np.random.default_rng(5)
+    acc0 = workloads.gravity_like_acc(w, rng)
+    sim, rebx, _ = scenarios.build(w, ["radiation_forces"], acc=acc0)
+    sim.additional_forces()
+    sim.process_messages()
+    got = sim.acc()
+    stats = rebx.stats()
+    rebx.detach(); sim.free()
+    assert stats["h2d_bytes"] >= n*128 and stats["d2h_bytes"] >= n*128 and stats["launches"] >= 3*(n >> 19)
+    idx = np.sort(rng.choice(np.arange(1, n + 1), size=50_000, replace=False))
+    sub = _subsample(w, idx, ["beta"])
+    want, _ = oracle.port_apply(sub, ["radiation_forces"], [np.concatenate([a[:1], a[idx]]) for a in acc0])
+    assert errors([a[idx] for a in got], [a[1:] for a in want])["bit_identical"]
+    assert all(got[k][0] == acc0[k][0] for k in range(3))          # the source itself feels nothing
+
+
+def test_raw_pointer_writes_are_seen(built):
+    """The reference's documented C idiom (doc/c_quickstart.rst:49-54): keep the pointer rebx_get_param returned and
+    write through it between evaluations -- no API call announces the write.  The library remembers which values'
+    pointers it handed out and re-reads those (only those) at every dispatch: the new value is used at once, without
+    rebx_mark_params_dirty; an untouched pointer costs no rebuild."""
+    import ctypes
+    from reboundx_b200 import scenarios, workloads
+    w = workloads.debris_disk(3000)
+    sim, rebx, handles = scenarios.build(w, ["radiation_forces"])
+    lib = rebx._lib
+    lib.rebx_get_param.restype = ctypes.POINTER(ctypes.c_double)
+    lib.rebx_get_param.argtypes = [ctypes.c_void_p, ctypes.c_void_p, ctypes.c_char_p]
+    ptr = lib.rebx_get_param(rebx._ptr, sim.particle(9).ap, b"beta")
+    cptr = lib.rebx_get_param(rebx._ptr, handles["radiation_forces"]._ptr.contents.ap, b"c")
+    sim.additional_forces(); sim.process_messages()
+    a1 = sim.acc()[0][9]
+    builds = rebx.stats()["table_builds"]
+    sim.set_acc(); sim.additional_forces(); sim.process_messages()
+    assert rebx.stats()["table_builds"] == builds              # nothing written: nothing rebuilt
+    ptr[0] = 2.0*ptr[0]                                          # raw write through the kept pointer, no API call
+    sim.set_acc(); sim.additional_forces(); sim.process_messages()
+    assert sim.acc()[0][9] == 2.0*a1
+    assert rebx.stats()["table_builds"] == builds + 1
+    a2 = sim.acc()[0][11]
+    cptr[0] = 0.5*cptr[0]                                        # a force-level parameter, same idiom
+    sim.set_acc(); sim.additional_forces(); sim.process_messages()
+    assert sim.acc()[0][11] != a2
+    rebx.detach(); sim.free()
+
+
+def test_particle_removal_invalidates_the_tables(built):
+    """REBOUND calls sim->free_particle_ap for a removed particle and then moves the particles behind it, even when the
+    removed one carried no parameters: every per-index table entry and cached body index shifts.  Remove a parameter-less
+    particle, add one at the end (N unchanged), and compare with the oracle on the new ordering."""
+    from oracle import oracle
+    from reboundx_b200 import scenarios, workloads
+    w = workloads.debris_disk(3000)
+    sim, rebx, _ = scenarios.build(w, ["radiation_forces"])
+    sim.additional_forces(); sim.process_messages()             # tables built for the original ordering
+    k = 5
+    # strip particle k's parameters first (then the removal hook sees a parameter-less particle: the case the
+    # advisor flagged), remove it the way REBOUND does (hook, then the particles behind it shift down) ...
+    lib = rebx._lib
+    lib.rebx_free_ap(sim.particle_ap(k))
+    sim.remove_particle(k, keep_sorted=True)
+    # ... and add a particle at the end, so that N is what it was
+    last = {q: w[q][-1] for q in ("x", "y", "z", "vx", "vy", "vz", "m", "r")}
+    sim.add_particle(**{q: float(v)*1.01 for q, v in last.items()})
+    rebx.particle_params(sim.N - 1)["beta"] = 0.3
+    idx = np.r_[0:k, k + 1:w["x"].shape[0]]
+    w2 = {q: (np.append(v[idx], v[-1]*1.01) if isinstance(v, np.ndarray) and v.shape[0] == w["x"].shape[0] else v) for q, v in w.items()}
+    w2["beta"] = np.append(np.delete(w["beta"], k - 1), 0.3)
+    sim.set_acc(); sim.additional_forces(); sim.process_messages()
+    got = sim.acc()
+    want, _ = oracle.port_apply(w2, ["radiation_forces"], None)
+    for c in range(3):
+        assert np.array_equal(got[c], want[c])
+    rebx.detach(); sim.free()
+
+
+def test_missing_parameters_report_like_the_reference(built):
+    """Error paths of the effects (reference tests/test_gr.py:17-21 and the effects' own checks)."""
+    from reboundx_b200 import scenarios, workloads
+    from reboundx_b200.host import Extras, Simulation
+    w = workloads.debris_disk(100)
+    for name, pattern in (("radiation_forces", "speed of light"), ("gr_potential", "speed of light"), ("gr", "speed of light")):
+        sim = Simulation(G=w["G"])
+        sim.set_particles(w["x"], w["y"], w["z"], w["vx"], w["vy"], w["vz"], w["m"], w["r"])
+        sim.N_active = 1
+        rebx = Extras(sim)
+        rebx.add_force(rebx.load_force(name))
+        before = sim.acc()
+        sim.additional_forces()
+        with pytest.raises(RuntimeError, match=pattern):
+            sim.process_messages()
+        assert all(np.array_equal(a, b) for a, b in zip(before, sim.acc()))
+        rebx.detach(); sim.free()
+    w5 = workloads.planetesimal_disk(100)
+    sim, rebx, _ = scenarios.build(w5, ["modify_orbits_forces"], coordinates=None)
+    rebx.get_force("modify_orbits_forces").params["coordinates"] = 2          # PARTICLE, but nobody is 'primary'
+    sim.additional_forces()
+    with pytest.raises(RuntimeError, match="primary param was not found"):
+        sim.process_messages()
+    rebx.detach(); sim.free()
+
+
+@pytest.mark.parametrize("effect", ["gr_potential", "gravitational_harmonics"])
+def test_force_is_minus_gradient_of_the_reference_potential(built, effect):
+    """The reference's conservation tests (reboundx/tests/test_conservation.py:44-56,73-87) pin these two
+    effects through their potentials.  Independent of the force oracle: m_i a_i computed on the device
+    must equal -dU/dx_i, with U the REFERENCE's own potential function (compiled in oracle/_ref)
+    differentiated by 4th-order central differences.  Same 3-body set-up as the reference's test."""
+    import ctypes
+    from oracle import oracle
+    from reboundx_b200 import workloads as W
+    from reboundx_b200.host import Extras, Simulation
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    G = 1.0
+    x1, y1, z1, vx1, vy1, vz1 = (float(v[0]) for v in W.kepler_to_cartesian(G*1.0001, np.array([1.0]), np.array([0.1]), np.array([0.0]), np.array([0.3]), np.array([0.7]), np.array([1.1])))
+    x2, y2, z2, vx2, vy2, vz2 = (float(v[0]) for v in W.kepler_to_cartesian(G*1.0002, np.array([2.0]), np.array([0.1]), np.array([0.2]), np.array([1.3]), np.array([0.2]), np.array([2.5])))
+    state = {"x": np.array([0.0, x1, x2]), "y": np.array([0.0, y1, y2]), "z": np.array([0.0, z1, z2]),
+             "vx": np.array([0.0, vx1, vx2]), "vy": np.array([0.0, vy1, vy2]), "vz": np.array([0.0, vz1, vz2]),
+             "m": np.array([1.0, 1e-4, 1e-4])}
+
+    def build(lib, pos):
+        sim = Simulation(G=G)
+        sim.set_particles(pos["x"], pos["y"], pos["z"], state["vx"], state["vy"], state["vz"], state["m"])
+        rebx = Extras(sim, lib=lib)
+        f = rebx.load_force(effect)
+        if effect == "gr_potential":
+            f.params["c"] = 1.0e2
+        else:
+            p0 = rebx.particle_params(0)
+            p0["J2"] = 1e-3; p0["J4"] = 1e-3; p0["R_eq"] = 1e-1; p0["Omega"] = (0.2, -0.1, 1.0)
+        rebx.add_force(f)
+        return sim, rebx, f
+
+    ref = oracle.ref_lib()
+    ref.rebx_gr_potential_potential.restype = ctypes.c_double
+    ref.rebx_gravitational_harmonics_potential.restype = ctypes.c_double
+
+    def potential(pos):
+        sim, rebx, f = build(ref, pos)
+        U = ref.rebx_gr_potential_potential(rebx._ptr, f._ptr) if effect == "gr_potential" else ref.rebx_gravitational_harmonics_potential(rebx._ptr)
+        rebx.detach(); sim.free()
+        return U
+
+    sim, rebx, _ = build(None, state)
+    sim.additional_forces(); sim.process_messages()
+    acc = sim.acc()
+    rebx.detach(); sim.free()
+    h = 1e-4
+    for i in range(3):
+        for c, key in enumerate(("x", "y", "z")):
+            def U(delta):
+                pos = {k: state[k].copy() for k in ("x", "y", "z")}
+                pos[key][i] += delta
+                return potential(pos)
+            dU = (-U(2*h) + 8*U(h) - 8*U(-h) + U(-2*h))/(12*h)
+            force = state["m"][i]*acc[c][i]
+            scale = max(abs(state["m"][i]*a[i]) for a in acc)
+            assert abs(force + dU) <= 2e-7*scale + 1e-18, (i, key, force, -dU)
+
+
+@pytest.mark.parametrize("scheme", ["euler", "rk2", "rk4", "implicit_midpoint"])
+def test_device_integrate_force_against_the_reference_operator(built, scheme):
+    """the reference's integrate_force operator and its four schemes
+    (src/integrate_force.c, src/integrator_*.c, compiled unmodified into oracle/_ref together with the
+    reference's radiation loop) against rebx_b200_integrate_force on a resident shard."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    w = workloads.debris_disk(20001)
+    w["beta"] = w["beta"]*50.0                  # a strong force, so every stage matters
+    dt = 3.0e8
+    (vx, vy, vz), msgs = oracle.ref_integrate_force(w, "radiation_forces", dt, scheme, nsteps=3)
+    assert not [m for k, m in msgs if k == "error"]
+    sh = device.Shard(w, ["radiation_forces"], "cuda:0")
+    for _ in range(3):
+        sh.integrate_force(dt, scheme)
+    torch.cuda.synchronize()
+    got = sh.posvel()
+    assert np.array_equal(np.array(got[:3]), np.array([w["x"], w["y"], w["z"]]))       # positions untouched
+    want = np.array([vx, vy, vz])
+    if scheme == "implicit_midpoint":
+        # the convergence test sums over all particles; the device sums in another order, so the
+        # iteration may stop one step apart in the last bit
+        assert np.max(np.abs(np.array(got[3:]) - want)/np.max(np.abs(want))) <= 1e-15
+    else:
+        assert np.array_equal(np.array(got[3:]), want)
+    assert np.any(want != np.array([w["vx"], w["vy"], w["vz"]]))
+
+
 # ---- SURVEY section 8f rank 3: same-shape neighbouring forces --------------------------------------------
 @pytest.mark.parametrize("gamma", [-1.0, -1.7, 2.0])
 def test_central_force(built, gamma):
