@@ -583,6 +583,22 @@ def run_ours(args):
         if numa:
             e2e["numa"] = numa
 
+    # ---- ONE simulation of the headline size spread over all N GPUs by the C dispatcher itself (REBX_B200_DEVICES): the
+    # unchanged drop-in call of a single-process C host; rank 0 alone runs it, the other ranks wait ----------------------
+    e2e_one = None
+    if world > 1 and not args.no_e2e and not com and not args.no_extras:
+        cx.barrier()
+        if rank == 0:
+            os.environ["REBX_B200_DEVICES"] = ",".join(str(d) for d in range(world))
+            solo = Ctx(args)
+            solo.world, solo.clocks = 1, clocks          # no collectives inside: one process drives every device
+            e2e_one = e2e_leg(solo, w, add_order, args.coordinates, args.e2e_steps or min(steps, 10), nf, n)
+            e2e_one["devices"] = world
+            e2e_one["what"] = ("ONE simulation of %d test particles, one process, one host thread: sim->additional_forces(sim) with REBX_B200_DEVICES "
+                               "naming all %d GPUs -- the dispatcher splits the particle array by index range over per-device copy/compute pipelines" % (n, world))
+            del os.environ["REBX_B200_DEVICES"]
+        cx.barrier()
+
     # ---- the other BASELINE configurations (one GPU, default invocation) -----------------------------------------
     extras = None
     if world == 1 and args.workload == "debris_disk" and not com and not args.no_extras and args.n == 0:
@@ -610,7 +626,7 @@ def run_ours(args):
                            "l2": l2_note,
                            "sharding": ("index ranges; the central body's record is replicated and re-broadcast (NCCL) only when its owner changed it" if not com else
                                         "index ranges; per step an all-gather of 7 mass moments and of 3 back-reaction sums per rank (JACOBI: exclusive prefix / suffix over ranks; BARYCENTRIC: all-reduce)")},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "strong": strong, "sharded_parity": parity,
+                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_one_simulation_all_gpus": e2e_one, "strong": strong, "sharded_parity": parity,
                 "workloads": extras, "resident_step": resident, "resident_wh_step": resident_wh, "gpu_launches": gpu_launches,
                 "clocks": clocks.summary()}
         sys.stdout.flush()
