@@ -118,6 +118,12 @@ typedef struct rebx_b200_effect {
  * coordinates (REBX_B200_PASS_SHARED_BODY must be set as well); any other pass runs the exact kernels. */
 #define REBX_B200_PASS_TOLERANCE 2
 
+/* pass.reserved bit: the sweep itself adds each effect's back-reaction sum to the acceleration of the body it acts on
+ * (when that body lies inside the shard), as rebx_b200_apply_backreaction would afterwards -- for a single-shard
+ * caller, whose sums are final when the sweep ends.  A sharded caller leaves it clear, all-reduces the sums and
+ * calls rebx_b200_apply_backreaction. */
+#define REBX_B200_PASS_APPLY_BACKREACTION 4
+
 typedef struct rebx_b200_pass {
     rebx_b200_state st;
     int32_t n_effects;
@@ -134,13 +140,17 @@ typedef struct rebx_b200_aos_layout {
 /* ---- device management --------------------------------------------------------------- */
 int  rebx_b200_device_count(void);                       /* 0 when no usable CUDA device */
 const char* rebx_b200_error_string(int code);            /* text for a non-zero return code */
-size_t rebx_b200_workspace_bytes(void);                  /* scratch a pass launch needs */
+size_t rebx_b200_workspace_bytes(void);                  /* scratch a pass launch needs; ZERO it once after allocating it
+                                                            (cudaMemset): it holds the ticket counter by which the last CTA
+                                                            of a sweep knows to sum the back-reaction partials, which every
+                                                            launch leaves at zero again.  One workspace per stream. */
 int  rebx_b200_sm_count(int device);
 
 /* ---- kernels (all asynchronous on `stream`, a cudaStream_t passed as void*) ------------ */
 /* Streams the shard once and applies pass->fx[0..n_effects) in order.  `workspace` is
  * device scratch of rebx_b200_workspace_bytes().  Returns 0 or a cudaError_t value.
- * `launches` (host, may be NULL) is incremented by the number of kernels launched. */
+ * `launches` (host, may be NULL) is incremented by the number of kernels launched.  fx[].backreaction is
+ * final when the launch completes (summed by the sweep's last CTA, no separate reduction launch). */
 int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* stream, int* launches);
 
 /* a[index - index_base] += backreaction for each effect whose body lies inside the shard. */

@@ -39,6 +39,12 @@ struct DevBuf {
         if (e == cudaSuccess) cap = want; else p = nullptr;
         return e;
     }
+    // zero-filled when (re)allocated: what rebx_b200_launch_pass asks of its workspace (ticket counter)
+    cudaError_t ensure_zeroed(size_t bytes) {
+        if (bytes <= cap) return cudaSuccess;
+        cudaError_t e = ensure(bytes);
+        return e == cudaSuccess ? cudaMemset(p, 0, cap) : e;
+    }
     ~DevBuf() { if (p) cudaFree(p); }
     DevBuf() = default;
     DevBuf(const DevBuf&) = delete;
@@ -739,7 +745,7 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
         for (int b = 0; b < DeviceContext::kBuffers && (size_t)b < chunks_per_dev; b++) {
             REBXB_CUDA(D.aos[b].ensure(chunk_cap*sizeof(struct reb_particle)), "allocating AoS staging");
             REBXB_CUDA(D.soa[b].ensure(11*soa_stride*sizeof(double)), "allocating SoA state");
-            REBXB_CUDA(D.work[b].ensure(rebx_b200_workspace_bytes()), "allocating reduction scratch");
+            REBXB_CUDA(D.work[b].ensure_zeroed(rebx_b200_workspace_bytes()), "allocating reduction scratch");
         }
     }
     REBXB_CUDA(cudaSetDevice(D0.device), "selecting a device");
@@ -988,7 +994,7 @@ static double run_potential(struct rebx_extras* rebx, int kind, const struct reb
     rebx_b200_state st;
     REBXB_CUDA(P0.aos[0].ensure(N*sizeof(struct reb_particle)), "allocating AoS staging");
     REBXB_CUDA(P0.soa[0].ensure(11*stride*sizeof(double)), "allocating SoA state");
-    REBXB_CUDA(P0.work[0].ensure(rebx_b200_workspace_bytes()), "allocating reduction scratch");
+    REBXB_CUDA(P0.work[0].ensure_zeroed(rebx_b200_workspace_bytes()), "allocating reduction scratch");
     REBXB_CUDA(ctx->bodies_h.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating pinned body records");
     REBXB_CUDA(P0.bodies.ensure(ne*REBX_B200_BODY_DOUBLES*sizeof(double)), "allocating body records");
     REBXB_CUDA(P0.br_h.ensure(ne*sizeof(double)), "allocating pinned results");

@@ -84,6 +84,9 @@ __host__ __device__ constexpr int min_blocks() {
 // warps at 128 registers, 3 CTAs need <= 85); 128-thread CTAs add the step in between: 5 CTAs = 20 warps at 96
 // registers.  Measured on all four configurations (profiles/r01_variant_sweep.txt): only the J2/J4 (+) gr_potential
 // pair fits 96 registers without further spills and gains (0.2385 -> 0.2278 ms); the others stay at 256 x 2 / 256 x 4.
+#ifndef REBXB_PASS_PREFETCH_ALL
+#define REBXB_PASS_PREFETCH_ALL 0
+#endif
 #ifndef REBXB_RING_128
 #define REBXB_RING_128 1
 #endif
@@ -136,6 +139,22 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
     for (int64_t t = (int64_t)blockIdx.x*T + threadIdx.x; t < ntiles; t += stride) {
         const int64_t k = t*V;
         const bool full = (k + V <= n);
+        // the register-heavy sweeps (2 CTAs of 256 or 5 of 128 per SM) prefetch the next iteration's operands
+        constexpr bool PREFETCH = REBXB_PASS_PREFETCH_ALL || min_blocks<K0, K1, K2, K3>() != 4;
+        if constexpr (PREFETCH) {
+            if (t + stride < ntiles) {
+                const int64_t kn = (t + stride)*V;
+                prefetch_next(P.st.x + kn); prefetch_next(P.st.y + kn); prefetch_next(P.st.z + kn);
+                if constexpr (VEL)  { prefetch_next(P.st.vx + kn); prefetch_next(P.st.vy + kn); prefetch_next(P.st.vz + kn); }
+                if constexpr (MASS) prefetch_next(P.st.m + kn);
+                if constexpr (RAD)  prefetch_next(P.st.r + kn);
+                prefetch_next(P.st.ax + kn); prefetch_next(P.st.ay + kn); prefetch_next(P.st.az + kn);
+                prefetch_params<K0>(P.fx[0], kn);
+                if constexpr (K1 != 0) prefetch_params<K1>(P.fx[1], kn);
+                if constexpr (K2 != 0) prefetch_params<K2>(P.fx[2], kn);
+                if constexpr (K3 != 0) prefetch_params<K3>(P.fx[3], kn);
+            }
+        }
         double x[V], y[V], z[V], vx[V], vy[V], vz[V], m[V], r[V], ax[V], ay[V], az[V];
         ld<V>(P.st.x, k, full, x); ld<V>(P.st.y, k, full, y); ld<V>(P.st.z, k, full, z);
         if constexpr (VEL)  { ld<V>(P.st.vx, k, full, vx); ld<V>(P.st.vy, k, full, vy); ld<V>(P.st.vz, k, full, vz); }
@@ -234,6 +253,7 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
     reduce_effect<K1, W>(red1, 1, s_red, partials);
     reduce_effect<K2, W>(red2, 2, s_red, partials);
     reduce_effect<K3, W>(red3, 3, s_red, partials);
+    finalize_by_last_cta<T, K0, K1, K2, K3>(P, partials, ApplyTail{});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -246,6 +266,43 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
 // here and advanced by step_body_kernel once the back-reaction sums are final.
 // ---------------------------------------------------------------------------------------------
 struct StepArgs { double dt, hdt, G, soft2; };
+
+static __device__ __noinline__ void step_body(const rebx_b200_pass& P, const StepArgs& S, unsigned red_mask) {
+    double* rec0 = const_cast<double*>(P.fx[0].body);
+    const long long bi = (long long)rec0[REBX_B200_BODY_INDEX];
+    const long long k = bi - P.st.index_base;
+    double pos[3] = {rec0[REBX_B200_BODY_X+0], rec0[REBX_B200_BODY_X+1], rec0[REBX_B200_BODY_X+2]};
+    double vel[3] = {rec0[REBX_B200_BODY_VX+0], rec0[REBX_B200_BODY_VX+1], rec0[REBX_B200_BODY_VX+2]};
+    double a[3] = {0.0, 0.0, 0.0};
+    for (int e = 0; e < P.n_effects; e++)
+        if (((red_mask >> e) & 1u) && P.fx[e].backreaction)
+            for (int c = 0; c < 3; c++) a[c] += P.fx[e].backreaction[c];
+    for (int c = 0; c < 3; c++) {
+        pos[c] += S.hdt*vel[c];
+        vel[c] += S.dt*a[c];
+        pos[c] += S.hdt*vel[c];
+    }
+    for (int e = 0; e < P.n_effects; e++) {
+        double* rec = const_cast<double*>(P.fx[e].body);
+        for (int c = 0; c < 3; c++) { rec[REBX_B200_BODY_X + c] = pos[c]; rec[REBX_B200_BODY_VX + c] = vel[c]; }
+    }
+    if (k >= 0 && k < P.st.n) {
+        const_cast<double*>(P.st.x)[k] = pos[0]; const_cast<double*>(P.st.y)[k] = pos[1]; const_cast<double*>(P.st.z)[k] = pos[2];
+        const_cast<double*>(P.st.vx)[k] = vel[0]; const_cast<double*>(P.st.vy)[k] = vel[1]; const_cast<double*>(P.st.vz)[k] = vel[2];
+    }
+}
+__global__ void step_body_kernel(const __grid_constant__ rebx_b200_pass P, const StepArgs S, unsigned red_mask) {
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    step_body(P, S, red_mask);
+}
+// step_kernel's tail in the last CTA of a single-shard step (REBX_B200_PASS_APPLY_BACKREACTION): every other CTA read
+// the body record when it started and stored its particles before it took its ticket, so the body may move now.
+struct StepBodyTail {
+    StepArgs S; unsigned red_mask;
+    __device__ __forceinline__ void operator()(const rebx_b200_pass& P) const {
+        if (P.reserved & REBX_B200_PASS_APPLY_BACKREACTION) step_body(P, S, red_mask);
+    }
+};
 
 template <int V, bool SHARED, int K0, int K1, int K2, int K3>
 __global__ void __launch_bounds__(kThreads, min_blocks<K0, K1, K2, K3>())
@@ -330,36 +387,12 @@ step_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
     reduce_effect<K1>(red1, 1, s_red, partials);
     reduce_effect<K2>(red2, 2, s_red, partials);
     reduce_effect<K3>(red3, 3, s_red, partials);
+    constexpr unsigned RED_MASK = (Traits<K0>::red ? 1u : 0u) | (Traits<K1>::red ? 2u : 0u) | (Traits<K2>::red ? 4u : 0u) | (Traits<K3>::red ? 8u : 0u);
+    finalize_by_last_cta<kThreads, K0, K1, K2, K3>(P, partials, StepBodyTail{S, RED_MASK}, (P.reserved & REBX_B200_PASS_APPLY_BACKREACTION) != 0);
 }
 
 // The central body's own step (one thread): half drift, kick by the back-reaction sums of the stack
 // (in stack order, like apply_backreaction), half drift; then every body record is refreshed.
-__global__ void step_body_kernel(const __grid_constant__ rebx_b200_pass P, const StepArgs S, unsigned red_mask) {
-    if (threadIdx.x != 0 || blockIdx.x != 0) return;
-    double* rec0 = const_cast<double*>(P.fx[0].body);
-    const long long bi = (long long)rec0[REBX_B200_BODY_INDEX];
-    const long long k = bi - P.st.index_base;
-    double pos[3] = {rec0[REBX_B200_BODY_X+0], rec0[REBX_B200_BODY_X+1], rec0[REBX_B200_BODY_X+2]};
-    double vel[3] = {rec0[REBX_B200_BODY_VX+0], rec0[REBX_B200_BODY_VX+1], rec0[REBX_B200_BODY_VX+2]};
-    double a[3] = {0.0, 0.0, 0.0};
-    for (int e = 0; e < P.n_effects; e++)
-        if (((red_mask >> e) & 1u) && P.fx[e].backreaction)
-            for (int c = 0; c < 3; c++) a[c] += P.fx[e].backreaction[c];
-    for (int c = 0; c < 3; c++) {
-        pos[c] += S.hdt*vel[c];
-        vel[c] += S.dt*a[c];
-        pos[c] += S.hdt*vel[c];
-    }
-    for (int e = 0; e < P.n_effects; e++) {
-        double* rec = const_cast<double*>(P.fx[e].body);
-        for (int c = 0; c < 3; c++) { rec[REBX_B200_BODY_X + c] = pos[c]; rec[REBX_B200_BODY_VX + c] = vel[c]; }
-    }
-    if (k >= 0 && k < P.st.n) {
-        const_cast<double*>(P.st.x)[k] = pos[0]; const_cast<double*>(P.st.y)[k] = pos[1]; const_cast<double*>(P.st.z)[k] = pos[2];
-        const_cast<double*>(P.st.vx)[k] = vel[0]; const_cast<double*>(P.st.vy)[k] = vel[1]; const_cast<double*>(P.st.vz)[k] = vel[2];
-    }
-}
-
 // ---------------------------------------------------------------------------------------------
 // pass_kernel_tma<K0..K3>: same sweep, but the particle state and parameter tables are moved
 // HBM -> shared memory by the TMA engine (cp.async.bulk, 1-D bulk copies completing on an
@@ -898,7 +931,7 @@ const char* rebx_b200_error_string(int code) {
 }
 
 size_t rebx_b200_workspace_bytes(void) {
-    return ((size_t)kMaxBlocks*REBX_B200_MAX_EFFECTS*3 + 8)*sizeof(double);     // CTA partials + a few scalars
+    return (kTicketOffset + 8)*sizeof(double);     // CTA partials + a few scalars + the CTA ticket counter (pass_common.cuh)
 }
 
 int rebx_b200_sm_count(int device) {
@@ -948,9 +981,11 @@ int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* str
         for (int j = 0; j < take; j++) if (sub.fx[j].kind >= REBX_B200_YARKOVSKY) heavy = true;
         const int vsel = (aligned && !heavy) ? 1 : 0;
         const bool want_tol = (pass->reserved & REBX_B200_PASS_TOLERANCE) && (pass->reserved & REBX_B200_PASS_SHARED_BODY);
+        bool separate_finalize = false;      // the plain and the tolerance sweeps finish their own sums (finalize_by_last_cta)
         if (want_tol && tol_launch(sub, take, static_cast<double*>(workspace), s, &grid)) {
             // tolerance-mode sweep launched (kernels_tol.cu)
         } else if (aligned && use_tma() && sub.st.n >= 4*kTile) {
+            separate_finalize = true;
             // TMA-fed ring (needs 16-byte aligned arrays)
             pass_fn fn = combo->tma;
             err = cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, combo->tma_smem);
@@ -970,11 +1005,15 @@ int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* str
         unsigned red_mask = 0;
         bool any = false;
         for (int j = 0; j < take; j++) if (combo->red[j]) { red_mask |= 1u << j; if (sub.fx[j].backreaction) any = true; }
-        if (any) {
+        if (any && separate_finalize) {
             finalize_kernel<<<1, kThreads, 0, s>>>(sub, static_cast<const double*>(workspace), grid, red_mask);
             err = cudaGetLastError();
             if (err != cudaSuccess) return err;
             if (launches) (*launches)++;
+            if (pass->reserved & REBX_B200_PASS_APPLY_BACKREACTION) {
+                apply_backreaction_kernel<<<1, 32, 0, s>>>(sub);
+                if (launches) (*launches)++;
+            }
         }
         done += take;
     }
@@ -983,6 +1022,7 @@ int rebx_b200_launch_pass(const rebx_b200_pass* pass, void* workspace, void* str
 
 int rebx_b200_apply_backreaction(const rebx_b200_pass* pass, void* stream, int* launches) {
     if (!pass) return cudaErrorInvalidValue;
+    if (pass->reserved & REBX_B200_PASS_APPLY_BACKREACTION) return 0;       // the sweep applied the sums itself
     bool any = false;
     for (int e = 0; e < pass->n_effects; e++) if (pass->fx[e].backreaction) any = true;
     if (!any) return 0;
@@ -1210,11 +1250,10 @@ int rebx_b200_leapfrog_sweep(const rebx_b200_pass* pass, double dt, double G, do
     const StepArgs S = {dt, 0.5*dt, G, softening*softening};
     step_fn fn = combo->step[1][vsel];        // the fused step requires one central body for the whole stack
     const int grid = grid_for(reinterpret_cast<const void*>(fn), (P.st.n + V - 1)/V);
-    fn<<<grid, kThreads, 0, s>>>(P, static_cast<double*>(workspace), S);
-    int nl = 1;
-    if (any) { finalize_kernel<<<1, kThreads, 0, s>>>(P, static_cast<const double*>(workspace), grid, red_mask); nl++; }
+    fn<<<grid, kThreads, 0, s>>>(P, static_cast<double*>(workspace), S);       // its last CTA finishes the sums (and the body, see _step)
+    (void)any;
     cudaError_t err = cudaGetLastError();
-    if (err == cudaSuccess && launches) *launches += nl;
+    if (err == cudaSuccess && launches) *launches += 1;
     return err;
 }
 
@@ -1231,8 +1270,21 @@ int rebx_b200_leapfrog_body(const rebx_b200_pass* pass, double dt, void* stream,
 
 int rebx_b200_leapfrog_step(const rebx_b200_pass* pass, double dt, double G, double softening, void* workspace, void* stream, int* launches) {
     if (pass && pass->st.n == 0) return check_pass(*pass);
-    int rc = rebx_b200_leapfrog_sweep(pass, dt, G, softening, workspace, stream, launches);
-    if (rc == 0) rc = rebx_b200_leapfrog_body(pass, dt, stream, launches);
+    if (!pass) return cudaErrorInvalidValue;
+    const Combo* combo = nullptr; unsigned red_mask = 0; bool any = false;
+    int rc = leapfrog_combo(pass, &combo, &red_mask, &any);
+    if (rc) return rc;
+    if (red_mask != 0) {
+        // a stack with back-reaction sums, single shard: the sweep's last CTA finishes the sums AND advances the body
+        rebx_b200_pass Q = *pass;
+        Q.reserved |= REBX_B200_PASS_APPLY_BACKREACTION;
+        return rebx_b200_leapfrog_sweep(&Q, dt, G, softening, workspace, stream, launches);
+    }
+    // no sums (radiation_forces, yarkovsky_effect): those sweeps take no ticket (pass_common.cuh), the body follows in its own launch
+    rebx_b200_pass Q = *pass;
+    Q.reserved &= ~REBX_B200_PASS_APPLY_BACKREACTION;
+    rc = rebx_b200_leapfrog_sweep(&Q, dt, G, softening, workspace, stream, launches);
+    if (rc == 0) rc = rebx_b200_leapfrog_body(&Q, dt, stream, launches);
     return rc;
 }
 

@@ -392,6 +392,9 @@ __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const double* 
 // CTA geometry per stack class (tools/tol_variants.sh sweeps them on the GPU): threads per CTA and resident CTAs per
 // SM asked of the register allocator.  "light" = the streaming stacks (radiation, gr_potential, J2/J4), "heavy" =
 // the ones with transcendentals (yarkovsky, damping trio).
+#ifndef REBXB_TOL_PREFETCH_ALL
+#define REBXB_TOL_PREFETCH_ALL 0
+#endif
 #ifndef REBXB_TOL_LIGHT_THREADS
 #define REBXB_TOL_LIGHT_THREADS 256
 #endif
@@ -433,6 +436,8 @@ pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
     constexpr bool EINC = K0 == REBX_B200_GAS_DAMPING || K1 == REBX_B200_GAS_DAMPING || K2 == REBX_B200_GAS_DAMPING ||
                           K0 == REBX_B200_TYPE_I || K1 == REBX_B200_TYPE_I || K2 == REBX_B200_TYPE_I;
     constexpr int T = tol_threads<K0, K1, K2>(), W = T/32;
+    // prefetch the next iteration's operands in the sweeps with transcendentals (few warps, long chains per particle)
+    constexpr bool PREFETCH = REBXB_TOL_PREFETCH_ALL || trio_stack<K0, K1, K2>() || yark_stack<K0, K1, K2>();
     __shared__ double s_c[3][kC];
     __shared__ double s_org[8];
     __shared__ double s_red[W][3];
@@ -449,6 +454,19 @@ pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
     for (int64_t t = (int64_t)blockIdx.x*T + threadIdx.x; t < ntiles; t += stride) {
         const int64_t k = t*V;
         const bool full = (k + V <= n);
+        if constexpr (PREFETCH) {
+            if (t + stride < ntiles) {
+                const int64_t kn = (t + stride)*V;
+                prefetch_next(P.st.x + kn); prefetch_next(P.st.y + kn); prefetch_next(P.st.z + kn);
+                if constexpr (VEL)  { prefetch_next(P.st.vx + kn); prefetch_next(P.st.vy + kn); prefetch_next(P.st.vz + kn); }
+                if constexpr (MASS) prefetch_next(P.st.m + kn);
+                if constexpr (RAD)  prefetch_next(P.st.r + kn);
+                prefetch_next(P.st.ax + kn); prefetch_next(P.st.ay + kn); prefetch_next(P.st.az + kn);
+                prefetch_params<K0>(P.fx[0], kn);
+                if constexpr (K1 != 0) prefetch_params<K1>(P.fx[1], kn);
+                if constexpr (K2 != 0) prefetch_params<K2>(P.fx[2], kn);
+            }
+        }
         double x[V], y[V], z[V], vx[V], vy[V], vz[V], m[V], r[V], ax[V], ay[V], az[V];
         ld<V>(P.st.x, k, full, x); ld<V>(P.st.y, k, full, y); ld<V>(P.st.z, k, full, z);
         if constexpr (VEL)  { ld<V>(P.st.vx, k, full, vx); ld<V>(P.st.vy, k, full, vy); ld<V>(P.st.vz, k, full, vz); }
@@ -501,6 +519,7 @@ pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
     reduce_effect<K0, W>(red0, 0, s_red, partials);
     reduce_effect<K1, W>(red1, 1, s_red, partials);
     reduce_effect<K2, W>(red2, 2, s_red, partials);
+    finalize_by_last_cta<T, K0, K1, K2, 0>(P, partials, ApplyTail{});
 }
 
 typedef void (*tol_fn)(const rebx_b200_pass, double*);

@@ -88,6 +88,29 @@ __device__ __forceinline__ void st(double* __restrict__ p, int64_t k, bool full,
     }
 }
 
+// ---- software prefetch of the NEXT grid-stride iteration's operands (an option that did NOT pay) ---------------------
+// The FP64-heavy sweeps hold 4-5 warps per scheduler (96-128 registers), each a dependent chain of several hundred
+// FP64 instructions per particle, and ncu puts 18-22 % of the trio sweep's stall samples on the first use of the ~14
+// operands loaded at the top of an iteration.  Register double-buffering would cost ~28 registers the kernels do not
+// have; a prefetch into L2 / L1 (CCTL.E.PF2 / PF1 in the SASS) costs none.  MEASURED on a B200
+// (tools/prefetch_variants.sh + prefetch_sweep.sh, profiles/r02_prefetch_sweep.txt): no gain anywhere -- ring exact
+// 0.2306 / 0.2292 / 0.2290 ms (off / L1 / L2), asteroids exact 0.0709 / 0.0709 / 0.0707, trio exact 0.1031 / 0.1033 /
+// 0.1027, trio tolerance 0.0584 / 0.0598 / 0.0599 (slower: 14 more address computations per iteration).  The exposed
+// load is one of many serial waits of a warp, and with 4 warps per scheduler the others fill the gap either way.
+// REBXB_PREFETCH: 0 off (default), 1 = prefetch.global.L1, 2 = prefetch.global.L2.
+#ifndef REBXB_PREFETCH
+#define REBXB_PREFETCH 0
+#endif
+__device__ __forceinline__ void prefetch_next(const void* p) {
+#if REBXB_PREFETCH == 1
+    asm volatile("prefetch.global.L1 [%0];" :: "l"(p));
+#elif REBXB_PREFETCH == 2
+    asm volatile("prefetch.global.L2 [%0];" :: "l"(p));
+#else
+    (void)p;
+#endif
+}
+
 template <int K, int V> struct Params {
     double t[Traits<K>::ntab > 0 ? Traits<K>::ntab : 1][V];
     int    it[V];
@@ -98,6 +121,13 @@ __device__ __forceinline__ void load_params(const rebx_b200_effect& fx, int64_t 
 #pragma unroll
     for (int j = 0; j < Traits<K>::ntab; j++) ld<V>(fx.tab[j], k, full, q.t[j]);
     if constexpr (Traits<K>::itab) ldi<V>(fx.itab, k, full, q.it);
+}
+
+template <int K>
+__device__ __forceinline__ void prefetch_params(const rebx_b200_effect& fx, int64_t k) {
+#pragma unroll
+    for (int j = 0; j < Traits<K>::ntab; j++) prefetch_next(fx.tab[j] + k);
+    if constexpr (Traits<K>::itab) prefetch_next(fx.itab + k);
 }
 
 template <int K, int NWARPS = kWarps>
@@ -118,9 +148,114 @@ __device__ __forceinline__ void reduce_effect(Vec3 red, int e, double (*s_red)[3
 #pragma unroll
             for (int w = 0; w < NWARPS; w++) s += s_red[w][threadIdx.x];
             partials[((size_t)blockIdx.x*REBX_B200_MAX_EFFECTS + e)*3 + threadIdx.x] = s;
+            __threadfence();            // visible device-wide before this CTA takes its ticket (finalize_by_last_cta)
         }
     }
 }
+
+// ---- back-reaction sums finished inside the sweep -----------------------------------------------------------------
+// The sweeps used to be followed by a one-CTA finalize launch (sum of the CTA partials) and, for a resident caller, a
+// one-thread launch adding the sums to the body: 2 x ~4 us of launch + drain behind sweeps that take 40-230 us.  Now
+// every CTA takes a ticket when its partials are out (threadfence + atomicInc on a counter in the workspace); the CTA
+// that draws the last ticket sums the partials -- in the ORDER finalize_kernel uses (256 virtual lanes striding over the
+// CTAs, then a binary tree), so the sums keep their bits for a given grid whatever the CTA size -- writes
+// fx[e].backreaction and, when the pass asks for it (REBX_B200_PASS_APPLY_BACKREACTION), adds the sums to the body's
+// acceleration like apply_backreaction_kernel.  atomicInc wraps the counter back to 0 on the last ticket, so a
+// workspace that was zeroed once after allocation stays ready for every later launch.
+constexpr int kFinalLanes = 256;
+constexpr size_t kTicketOffset = (size_t)kMaxBlocks*REBX_B200_MAX_EFFECTS*3 + 8;      // in doubles, behind the scalar tail
+
+template <int K, int T>
+__device__ __forceinline__ void finalize_effect(const rebx_b200_pass& P, int e, const double* partials, double* s_sum) {
+    if constexpr (Traits<K>::red) {
+        double* out = P.fx[e].backreaction;
+        if (out == nullptr) return;
+        const int nblocks = gridDim.x;
+        for (int c = 0; c < 3; c++) {
+            for (int lane = threadIdx.x; lane < kFinalLanes; lane += T) {
+                double acc = 0.0;
+                for (int b = lane; b < nblocks; b += kFinalLanes)
+                    acc += __ldcg(partials + ((size_t)b*REBX_B200_MAX_EFFECTS + e)*3 + c);
+                s_sum[lane] = acc;
+            }
+            __syncthreads();
+            for (int w = kFinalLanes/2; w > 0; w >>= 1) {
+                for (int lane = threadIdx.x; lane < w; lane += T) s_sum[lane] += s_sum[lane + w];
+                __syncthreads();
+            }
+            if (threadIdx.x == 0) out[c] = s_sum[0];
+            __syncthreads();
+        }
+    }
+}
+
+// CTA-uniform: true in the CTA that finishes last.  Called by ALL threads of every CTA of the grid, after the CTA's
+// last global store.
+__device__ __forceinline__ bool last_cta_ticket(double* partials) {
+    __shared__ unsigned s_last;
+    __syncthreads();                                    // this CTA's stores (partials, accelerations) are issued
+    if (threadIdx.x == 0) {
+        unsigned* ticket = reinterpret_cast<unsigned*>(partials + kTicketOffset);
+        __threadfence();                                // cumulative: covers what the CTA's other threads stored before the barrier
+        s_last = (atomicInc(ticket, gridDim.x - 1) == gridDim.x - 1) ? 1u : 0u;
+    }
+    __syncthreads();
+    if (!s_last) return false;
+    __threadfence();
+    return true;
+}
+
+// apply_backreaction_kernel's loop, by ONE thread: effects in stack order, only bodies inside this shard.
+static __device__ __noinline__ void apply_backreaction_inline(const rebx_b200_pass& P) {
+    for (int e = 0; e < P.n_effects; e++) {
+        const rebx_b200_effect& fx = P.fx[e];
+        if (fx.backreaction == nullptr) continue;
+        const long long bi = (long long)fx.body[REBX_B200_BODY_INDEX];
+        const long long k = bi - P.st.index_base;
+        if (bi < 0 || k < 0 || k >= P.st.n) continue;
+        P.st.ax[k] = __ldcg(P.st.ax + k) + fx.backreaction[0];
+        P.st.ay[k] = __ldcg(P.st.ay + k) + fx.backreaction[1];
+        P.st.az[k] = __ldcg(P.st.az + k) + fx.backreaction[2];
+    }
+}
+
+// out of line: runs in one CTA per launch, and must not weigh on the register allocation of the sweep's loop
+template <int T, int K0, int K1, int K2, int K3>
+__device__ __noinline__ void finalize_sums(const rebx_b200_pass& P, const double* partials, double* s_sum) {
+    finalize_effect<K0, T>(P, 0, partials, s_sum);
+    finalize_effect<K1, T>(P, 1, partials, s_sum);
+    finalize_effect<K2, T>(P, 2, partials, s_sum);
+    finalize_effect<K3, T>(P, 3, partials, s_sum);
+}
+
+// Call at the end of a sweep, after reduce_effect for every effect, by ALL threads of the CTA.  `tail(P)` runs in
+// thread 0 of the last CTA once the sums are written; `always` (uniform over the grid) = take the ticket even when
+// no effect of the stack wants its sum (all fx[].backreaction NULL), because the tail has other work.
+template <int T, int K0, int K1, int K2, int K3, class Tail>
+__device__ __forceinline__ void finalize_by_last_cta(const rebx_b200_pass& P, double* partials, Tail tail, bool always = false) {
+    constexpr bool RED = Traits<K0>::red || Traits<K1>::red || Traits<K2>::red || Traits<K3>::red;
+    // A stack without sums (radiation_forces, yarkovsky_effect) takes no ticket at all: those sweeps run at the
+    // 64-register cap and the tail's presence alone cost them 3.5x the spill traffic (ptxas -v), 0.195 -> 0.251 ms
+    // on the fused leapfrog step.  Their callers keep the separate one-thread launch for the body.
+    if constexpr (!RED) return;
+    __shared__ double s_sum[RED ? kFinalLanes : 1];
+    bool any = always;
+    if constexpr (Traits<K0>::red) any |= P.fx[0].backreaction != nullptr;
+    if constexpr (Traits<K1>::red) any |= P.fx[1].backreaction != nullptr;
+    if constexpr (Traits<K2>::red) any |= P.fx[2].backreaction != nullptr;
+    if constexpr (Traits<K3>::red) any |= P.fx[3].backreaction != nullptr;
+    if (!any) return;                                   // uniform over the grid: nobody takes a ticket
+    if (!last_cta_ticket(partials)) return;
+    finalize_sums<T, K0, K1, K2, K3>(P, partials, s_sum);
+    if (threadIdx.x == 0) tail(P);
+}
+// the force sweeps' tail: add the sums to the body when the pass asks for it.  Every other CTA stored its
+// accelerations before taking its ticket, the body's own element included (unchanged).
+struct ApplyTail {
+    __device__ __forceinline__ void operator()(const rebx_b200_pass& P) const {
+        if (P.reserved & REBX_B200_PASS_APPLY_BACKREACTION) apply_backreaction_inline(P);
+    }
+};
 
 // ---- launch plumbing ----------------------------------------------------------------------
 struct DevInfo { int sms; bool ok; };

@@ -118,7 +118,7 @@ static rebx_b200_session* session_open(struct reb_simulation* sim, struct rebx_e
     s->stream = ctx->devs[0]->stream[0];
     cudaError_t err;
     if ((err = s->aos.ensure(s->N*sizeof(struct reb_particle))) != cudaSuccess || (err = s->soa.ensure(11*s->stride*sizeof(double))) != cudaSuccess ||
-        (err = s->work.ensure(rebx_b200_workspace_bytes())) != cudaSuccess) { session_fail(s.get(), "allocating device state", err); return nullptr; }
+        (err = s->work.ensure_zeroed(rebx_b200_workspace_bytes())) != cudaSuccess) { session_fail(s.get(), "allocating device state", err); return nullptr; }
     if ((err = copy_page_split(s->aos.p, sim->particles, s->N*sizeof(struct reb_particle), cudaMemcpyHostToDevice, s->stream)) != cudaSuccess) { session_fail(s.get(), "copying particles to the device", err); return nullptr; }
     ctx->stats.h2d_bytes += s->N*sizeof(struct reb_particle);
     if (session_bind(s.get(), only, n_only) != 0) return nullptr;
@@ -131,8 +131,9 @@ static int session_gather(rebx_b200_session* s) {
 }
 
 static int session_force(rebx_b200_session* s) {        // a += stacked effects (+ back-reaction onto particle 0)
-    REBXS(rebx_b200_launch_pass(&s->P, s->work.p, s->stream, &s->launches_i), "launching the force sweep");
-    if (s->reduces) REBXS(rebx_b200_apply_backreaction(&s->P, s->stream, &s->launches_i), "applying the back-reaction");
+    rebx_b200_pass Q = s->P;                             // one shard holds everything: the sweep's last CTA applies the sums
+    Q.reserved |= REBX_B200_PASS_APPLY_BACKREACTION;
+    REBXS(rebx_b200_launch_pass(&Q, s->work.p, s->stream, &s->launches_i), "launching the force sweep");
     return 0;
 }
 

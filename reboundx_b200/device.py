@@ -158,7 +158,7 @@ class Shard:
             self.flags.append(flags)
         self.bodies = dev(self.bodies_host)
         self.backreaction = torch.zeros((len(self.kinds), 3), dtype=torch.float64, device=self.device)
-        self.workspace = torch.empty(lib.rebx_b200_workspace_bytes(), dtype=torch.uint8, device=self.device)
+        self.workspace = torch.zeros(lib.rebx_b200_workspace_bytes(), dtype=torch.uint8, device=self.device)   # zeroed once: CTA ticket counter
         self.launches = 0
         # The replicated body records are re-broadcast from their owner only when they may have changed (construction,
         # a stepping call that moves the body on its owner only, mark_bodies_stale()): a loop of force evaluations over a
@@ -176,6 +176,10 @@ class Shard:
         # REBX_B200_COM_WHOLE: this shard is the whole ensemble (the literal mass recurrences are available as a fallback)
         self._com_flags = 1 if (lo == 0 and hi == n_total and self.index_base == 0 and standalone) else 0
         self._pass = self._make_pass()
+        # the same pass with REBX_B200_PASS_APPLY_BACKREACTION: a standalone shard's sums are final when its sweep ends,
+        # so the sweep's last CTA adds them to the body itself (one launch per evaluation instead of three)
+        self._pass_apply = self._make_pass()
+        self._pass_apply.reserved |= 4
 
     # ------------------------------------------------------------------------------------------
     def _make_pass(self):
@@ -218,11 +222,12 @@ class Shard:
         """The owner's copy of a body record was changed from outside (every rank must call this at the same point)."""
         self._bodies_stale = True
 
-    def launch(self, stream=None):
-        """One force evaluation of the shard: a += sum of the stacked effects (asynchronous)."""
+    def launch(self, stream=None, apply=False):
+        """One force evaluation of the shard: a += sum of the stacked effects (asynchronous); the back-reaction sums are
+        left in self.backreaction, and with apply=True also added to the body's acceleration by the same launch."""
         s = self.torch.cuda.current_stream(self.device) if stream is None else stream
         n = c_int(0)
-        rc = self.lib.rebx_b200_launch_pass(ctypes.byref(self._pass), c_void_p(self.workspace.data_ptr()),
+        rc = self.lib.rebx_b200_launch_pass(ctypes.byref(self._pass_apply if apply else self._pass), c_void_p(self.workspace.data_ptr()),
                                             c_void_p(s.cuda_stream), ctypes.byref(n))
         self._check(rc, "rebx_b200_launch_pass")
         self.launches += n.value
@@ -310,10 +315,9 @@ class Shard:
     def evaluate(self, group=None):
         """Full evaluation incl. the multi-GPU exchange steps; returns kernels launched."""
         if self.standalone:
-            k = self.launch_local()
-            if self.coordinates == "PARTICLE" and any(kind != 1 and kind != 4 for kind in self.kinds):
-                k += self.apply_backreaction()
-            return k
+            if self.coordinates == "PARTICLE":
+                return self.launch(apply=True)
+            return self.launch_local()
         if self.coordinates != "PARTICLE":
             return self._evaluate_com(group)
         if self._bodies_stale:
