@@ -106,10 +106,9 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
     constexpr bool VEL  = Traits<K0>::vel  || Traits<K1>::vel  || Traits<K2>::vel  || Traits<K3>::vel;
     constexpr bool MASS = Traits<K0>::mass || Traits<K1>::mass || Traits<K2>::mass || Traits<K3>::mass;
     constexpr bool RAD  = Traits<K0>::rad  || Traits<K1>::rad  || Traits<K2>::rad  || Traits<K3>::rad;
-    constexpr int T = pass_threads<K0, K1, K2, K3>(), W = T/32;      // threads / warps per CTA of this stack
+    constexpr int T = pass_threads<K0, K1, K2, K3>();      // threads per CTA of this stack
 
     __shared__ double s_body[REBX_B200_MAX_EFFECTS][REBX_B200_BODY_DOUBLES];
-    __shared__ double s_red[W][3];
     for (int idx = threadIdx.x; idx < P.n_effects*REBX_B200_BODY_DOUBLES; idx += T) {
         const int e = idx/REBX_B200_BODY_DOUBLES, j = idx - e*REBX_B200_BODY_DOUBLES;
         s_body[e][j] = P.fx[e].body[j];
@@ -249,11 +248,7 @@ pass_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
         }
         st<V>(P.st.ax, k, full, ax); st<V>(P.st.ay, k, full, ay); st<V>(P.st.az, k, full, az);
     }
-    reduce_effect<K0, W>(red0, 0, s_red, partials);
-    reduce_effect<K1, W>(red1, 1, s_red, partials);
-    reduce_effect<K2, W>(red2, 2, s_red, partials);
-    reduce_effect<K3, W>(red3, 3, s_red, partials);
-    finalize_by_last_cta<T, K0, K1, K2, K3>(P, partials, ApplyTail{});
+    finish_sums<T, K0, K1, K2, K3>(red0, red1, red2, red3, P, partials, ApplyTail{});
 }
 
 // ---------------------------------------------------------------------------------------------
@@ -311,7 +306,6 @@ step_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
     constexpr bool RAD  = Traits<K0>::rad  || Traits<K1>::rad  || Traits<K2>::rad  || Traits<K3>::rad;
 
     __shared__ double s_body[REBX_B200_MAX_EFFECTS][REBX_B200_BODY_DOUBLES];
-    __shared__ double s_red[kWarps][3];
     for (int idx = threadIdx.x; idx < P.n_effects*REBX_B200_BODY_DOUBLES; idx += kThreads) {
         const int e = idx/REBX_B200_BODY_DOUBLES, j = idx - e*REBX_B200_BODY_DOUBLES;
         s_body[e][j] = P.fx[e].body[j];
@@ -383,12 +377,8 @@ step_kernel(const __grid_constant__ rebx_b200_pass P, double* __restrict__ parti
         st<V>(X, k, full, x); st<V>(Y, k, full, y); st<V>(Z, k, full, z);
         st<V>(VX, k, full, vx); st<V>(VY, k, full, vy); st<V>(VZ, k, full, vz);
     }
-    reduce_effect<K0>(red0, 0, s_red, partials);
-    reduce_effect<K1>(red1, 1, s_red, partials);
-    reduce_effect<K2>(red2, 2, s_red, partials);
-    reduce_effect<K3>(red3, 3, s_red, partials);
     constexpr unsigned RED_MASK = (Traits<K0>::red ? 1u : 0u) | (Traits<K1>::red ? 2u : 0u) | (Traits<K2>::red ? 4u : 0u) | (Traits<K3>::red ? 8u : 0u);
-    finalize_by_last_cta<kThreads, K0, K1, K2, K3>(P, partials, StepBodyTail{S, RED_MASK}, (P.reserved & REBX_B200_PASS_APPLY_BACKREACTION) != 0);
+    finish_sums<kThreads, K0, K1, K2, K3>(red0, red1, red2, red3, P, partials, StepBodyTail{S, RED_MASK}, (P.reserved & REBX_B200_PASS_APPLY_BACKREACTION) != 0);
 }
 
 // The central body's own step (one thread): half drift, kick by the back-reaction sums of the stack

@@ -25,6 +25,7 @@
 #include <cmath>
 #include <cstdint>
 #include <cstdlib>
+#include <type_traits>
 #include "rebx_b200.h"
 #include "pass_common.cuh"
 #include "exact_math.cuh"       // rcp_seed / rsqrt_seed (MUFU.RCP64H / MUFU.RSQ64H)
@@ -95,9 +96,15 @@ constexpr int kC = 24;
 // GAS_DAMPING   c[3] = sqrt(G M), c[4] = 1/sqrt(G M), c[5] = cs_coeff, c[6] = 1/cs_coeff, c[7] = -tau_coeff M
 // TYPE_I        c[3] = beta, c[4] = h0, c[5] = 1/h0, c[6] = sd0, c[7] = s, c[8] = dedge, c[9] = hedge,
 //               c[10] = sqrt(M^3), c[11] = sqrt(G), c[12] = (2.7 + 1.1 s)/2
+// Exponent p of a uniform power law as an integer number of quarters, |p| <= 2.75, or 99: not on that grid.
+__device__ __forceinline__ double quarter_code(double p) {
+    const double k = 4.0*p;
+    return (k == rint(k) && fabs(k) <= 11.0) ? k : 99.0;
+}
+
 __device__ void fill_constants(const rebx_b200_effect& fx, const double* __restrict__ body, double* __restrict__ c) {
     const double G = fx.scal[0], bm = body[REBX_B200_BODY_M];
-    c[0] = G; c[1] = bm; c[2] = 1.0/bm; c[kC - 1] = 1.0/G;
+    c[0] = G; c[1] = bm; c[2] = frcp(bm); c[kC - 1] = frcp(G);
     switch (fx.kind) {
     case REBX_B200_RADIATION: c[3] = G*bm; c[4] = 1.0/fx.scal[1]; break;
     case REBX_B200_HARMONICS: {
@@ -112,11 +119,17 @@ __device__ void fill_constants(const rebx_b200_effect& fx, const double* __restr
         c[3] = 1.0/cc; c[4] = 3.0*L/(64.0*kPi*cc); c[5] = 3.0*L/(16.0*kPi*cc); c[6] = 0.5*sqrt(sqrt(sb/kPi5)); c[7] = L;
         break;
     }
-    case REBX_B200_MODIFY_ORBITS: c[3] = fx.scal[1]; c[4] = fx.scal[2]; break;
-    case REBX_B200_GAS_DAMPING: c[3] = sqrt(G*bm); c[4] = 1.0/sqrt(G*bm); c[5] = fx.scal[1]; c[6] = 1.0/fx.scal[1]; c[7] = -fx.scal[2]*bm; break;
+    case REBX_B200_MODIFY_ORBITS:
+        c[3] = fx.scal[1]; c[4] = fx.scal[2];
+        c[13] = fx.scal[1]*(1.0 + fx.scal[2])*(1.0 + 1e-12); c[14] = fx.scal[1]*(1.0 - fx.scal[2])*(1.0 - 1e-12);    // trap band (trap_factor)
+        break;
+    case REBX_B200_GAS_DAMPING: { double sq, rsq; fsqrt2(G*bm, sq, rsq); c[3] = sq; c[4] = rsq; c[5] = fx.scal[1]; c[6] = frcp(fx.scal[1]); c[7] = -fx.scal[2]*bm; break; }
     case REBX_B200_TYPE_I:
-        c[3] = fx.scal[1]; c[4] = fx.scal[2]; c[5] = 1.0/fx.scal[2]; c[6] = fx.scal[3]; c[7] = fx.scal[4]; c[8] = fx.scal[5]; c[9] = fx.scal[6];
-        c[10] = sqrt(bm*bm*bm); c[11] = sqrt(G); c[12] = 0.5*(2.7 + 1.1*fx.scal[4]);
+        c[3] = fx.scal[1]; c[4] = fx.scal[2]; c[5] = frcp(fx.scal[2]); c[6] = fx.scal[3]; c[7] = fx.scal[4]; c[8] = fx.scal[5]; c[9] = fx.scal[6];
+        { double rq; fsqrt2(bm*bm*bm, c[10], rq); c[17] = rq; }
+        c[11] = fsqrt(G); c[12] = 0.5*(2.7 + 1.1*fx.scal[4]);
+        c[13] = fx.scal[5]*(1.0 + fx.scal[6])*(1.0 + 1e-12); c[14] = fx.scal[5]*(1.0 - fx.scal[6])*(1.0 - 1e-12);    // trap band (trap_factor)
+        c[15] = quarter_code(fx.scal[1]); c[16] = quarter_code(fx.scal[4]);          // exponents in quarters (pow_quarters)
         break;
     default: break;
     }
@@ -366,7 +379,162 @@ __device__ __forceinline__ Vec3 type_I_migration(const double* __restrict__ c, c
     return f;
 }
 
+// ---- the damping effects in ONE basic block ---------------------------------------------------------------------
+// ncu on the functions above (profiles/r02_kernel_tolerance_planetesimal_disk.txt): 820 warp instructions per particle,
+// 30 of them branches, 4 warps per scheduler issuing 46 % of the cycles with `stall_wait` on top -- every warp a serial
+// FP64 chain, because each quotient's Newton steps, each root and each effect sits in its own basic block (IEEE
+// division / sqrt slow-path calls, acos and pow fall-backs, is_absent and trap tests) and the scheduler cannot
+// interleave across them.  damping_fast evaluates the same formulas without a single branch: rare cases are not
+// handled inline but FLAGGED in `bad`, and the caller redoes such a particle with the functions above
+// (damping_generic); the planet trap's transition band, the one rare case that is not THAT rare (0.2 % of a disc),
+// only marks its particle, and the caller recomputes the two trap factors -- the forces are linear in them.
+//   flagged: inclination outside acos_near_one's series, e/h below pow_1p2's single-precision seed, an exponent that
+//   is not a multiple of 1/4 (uniform: then every particle takes the generic path), operands outside exact_math's domain.
+struct DampCoef { double cv_mo, cv_ti, cr, cz; };     // fd = dv (cv_mo T_mo + cv_ti T_ti) + d cr ; fd.z += dvz cz
+
+// x^(k/4) and x^(-k/4) from x, 1/x and the two roots, k = c (an integer in [-11, 11], uniform): selects and products only
+__device__ __forceinline__ double pow_quarters(double kq, double x, double xinv, double s1, double rs1, double s2, double rs2, double& inv) {
+    const int k = (int)kq, ka = k < 0 ? -k : k, q = ka >> 2;
+    double P = (q == 0) ? 1.0 : ((q == 1) ? x : x*x);
+    double N = (q == 0) ? 1.0 : ((q == 1) ? xinv : xinv*xinv);
+    const double P1 = P*s1, N1 = N*rs1;
+    P = (ka & 2) ? P1 : P;  N = (ka & 2) ? N1 : N;
+    const double P2 = P*s2, N2 = N*rs2;
+    P = (ka & 1) ? P2 : P;  N = (ka & 1) ? N2 : N;
+    inv = (k < 0) ? P : N;
+    return (k < 0) ? N : P;
+}
+
+template <bool MO, bool GD, bool TI>
+__device__ __forceinline__ DampCoef damping_fast(const double* __restrict__ cmo, const double* __restrict__ cgd, const double* __restrict__ cti,
+                                                 int mo_flags, const Geo& g, double m, double inv_mb,
+                                                 double tau_a, double tau_e, double tau_inc, double d_factor,
+                                                 double& a_out, unsigned& bad, unsigned& band) {
+    const double* c0 = MO ? cmo : (GD ? cgd : cti);            // G, M, 1/G are the same in every effect of the stack
+    const double G = c0[0], bm = c0[1], inv_G = c0[kC - 1];
+    // -- two-body elements (elements<> above), straight-line
+    const double mu = G*(m + bm);
+    const double v2 = g.dvx*g.dvx + g.dvy*g.dvy + g.dvz*g.dvz;
+    const double vc2 = mu*g.rinv;
+    const double a = -mu*frcp(v2 - 2.*vc2);
+    a_out = a;
+    double e = 0.0, inc = 0.0, sa = 0.0, rsa = 0.0;
+    if constexpr (GD || TI) {
+        const double inv_mu = inv_mb*inv_G, vd2 = v2 - vc2;
+        const double ex = inv_mu*(vd2*g.dx - g.rv*g.dvx), ey = inv_mu*(vd2*g.dy - g.rv*g.dvy), ez = inv_mu*(vd2*g.dz - g.rv*g.dvz);
+        e = fsqrt(ex*ex + ey*ey + ez*ez);
+        // cos(inc) = h_z/h with the reference's own operation sequence, correctly rounded (exact_math.cuh: same bits as / and sqrt)
+        const double hx = xsub(xmul(g.dy, g.dvz), xmul(g.dz, g.dvy));
+        const double hy = xsub(xmul(g.dz, g.dvx), xmul(g.dx, g.dvz));
+        const double hz = xsub(xmul(g.dx, g.dvy), xmul(g.dy, g.dvx));
+        const double hh = exact_sqrt(xdot(hx, hy, hz, hx, hy, hz), bad);
+        const double cosine = exact_div(hz, exact_rcp(hh, bad), bad);
+        // acos_near_one's series; anything else is flagged
+        const double t = 1.0 - cosine;
+        const bool inside = (cosine > -1. && cosine < 1.);
+        bad |= (inside && !(t < 5e-3)) ? 1u : 0u;
+        const double s2h = 0.5*t, sh = fsqrt(s2h);
+        // Estrin on the 8 coefficients (2k)!/(4^k (k!)^2 (2k+1)), k = 1..8: depth 3 instead of 8
+        const double z2 = s2h*s2h, z4 = z2*z2;
+        const double p01 = fma(3.0/40.0, s2h, 1.0/6.0), p23 = fma(35.0/1152.0, s2h, 5.0/112.0);
+        const double p45 = fma(231.0/13312.0, s2h, 63.0/2816.0), p67 = fma(6435.0/557056.0, s2h, 143.0/10240.0);
+        const double pl = fma(p23, z2, p01), ph = fma(p67, z2, p45);
+        const double poly = fma(ph, z4, pl);
+        const double as = fma(sh*s2h, poly, sh);
+        inc = inside ? (as + as) : ((cosine <= -1.) ? kPi : 0.);
+        fsqrt2(a, sa, rsa);
+    }
+    DampCoef o = {0.0, 0.0, 0.0, 0.0};
+    const double two_rv_r2 = 2.*g.rv*g.rinv2;
+    double ite_sum = 0.0;
+    if constexpr (MO) {
+        const double ita = is_absent(tau_a) ? 0.0 : frcp(tau_a);
+        const double ite = is_absent(tau_e) ? 0.0 : frcp(tau_e), iti = is_absent(tau_inc) ? 0.0 : frcp(tau_inc);
+        o.cv_mo = 0.5*ita;
+        ite_sum += ite;
+        o.cz += 2.*iti;
+        if (mo_flags & REBX_B200_FLAG_TRAP) band |= (!(a > cmo[13]) && (a > cmo[14]) && !is_absent(tau_a)) ? 1u : 0u;
+    }
+    if constexpr (GD) {
+        const double vk = cgd[3]*rsa;
+        const double v = fsqrt(e*e + inc*inc)*vk;
+        double s4, rs4;
+        fsqrt2(sa, s4, rs4);
+        const double cs = cgd[5]*rs4;
+        const double voc = v*s4*cgd[6];
+        const double voc3 = voc*voc*voc;
+        const double coeff = (v <= cs) ? 1. : ((inc < cs*sa*cgd[4]) ? voc3 : voc3*voc);
+        const double ite = m*frcp(cgd[7]*d_factor*a*a*coeff);
+        const bool on = !is_absent(d_factor);
+        ite_sum += on ? ite : 0.0;
+        o.cz += on ? ite : 0.0;
+    }
+    if constexpr (TI) {
+        double s1, rs1, s2, rs2, inv_hr, inv_sd;
+        fsqrt2(g.r, s1, rs1);
+        fsqrt2(s1, s2, rs2);
+        bad |= (cti[15] == 99.0 || cti[16] == 99.0) ? 1u : 0u;
+        const double hr = pow_quarters(cti[15], g.r, g.rinv, s1, rs1, s2, rs2, inv_hr);
+        (void)pow_quarters(cti[16], g.r, g.rinv, s1, rs1, s2, rs2, inv_sd);
+        const double h = cti[4]*hr, inv_h = cti[5]*inv_hr, h2 = h*h;
+        const double eh = e*inv_h, ih = inc*inv_h;
+        const double sd = cti[6]*inv_sd;
+        const double ih4 = inv_h*inv_h;                                  // 1/h^4 from the inverse power, no quotient
+        const double inv_wave = m*sd*cti[11]*sa*cti[17]*(ih4*ih4);
+        const double x1 = eh*(1.0/2.25), x2 = eh*(1.0/2.84), x3 = eh*(1.0/2.02);
+        const double x22 = x2*x2, x32 = x3*x3;
+        // pow_1p2, straight-line: x = 0 gives 0 by the select, a positive x below the seed's range is flagged
+        bad |= (x1 > 0.0 && x1 < 1e-30) ? 1u : 0u;
+        double z = (double)__powf((float)x1, -0.2f);
+#pragma unroll
+        for (int it = 0; it < 2; it++) {
+            const double zz = z*z;
+            z = z*fma(-x1*zz, zz*z, 6.0)*0.2;
+        }
+        const double t12 = x1*z*z;
+        const double p12 = (x1 > 0.0) ? t12*t12 : 0.0;
+        const double Pe = (1. + p12 + x22*x22*x22)*frcp(1. - x32*x32);
+        const double ih2 = ih*ih;
+        const double corr = 0.070*ih + 0.085*ih2*ih2 - 0.080*eh*ih2;
+        o.cv_ti = -inv_wave*cti[12]*h2*frcp(Pe + (Pe < 0.0 ? -corr : corr));
+        const double ite = 0.780*inv_wave*frcp(1. - 0.14*eh*eh + 0.06*eh*eh*eh + 0.18*eh*ih2);
+        const double iti = 0.544*inv_wave*frcp(1. - 0.30*ih2 + 0.24*ih2*ih + 0.14*eh*eh*ih);
+        ite_sum -= ite;
+        o.cz -= 2.*iti;
+        band |= (!(a > cti[13]) && (a > cti[14])) ? 2u : 0u;
+    }
+    o.cr = two_rv_r2*ite_sum;
+    return o;
+}
+
 template <int K> __host__ __device__ constexpr bool is_damping() { return K == REBX_B200_MODIFY_ORBITS || K == REBX_B200_GAS_DAMPING || K == REBX_B200_TYPE_I; }
+
+template <int K, int K0, int K1, int K2> __host__ __device__ constexpr int slot_of() { return K0 == K ? 0 : (K1 == K ? 1 : (K2 == K ? 2 : -1)); }
+template <int K0, int K1, int K2> __host__ __device__ constexpr bool all_damping() {
+    return is_damping<K0>() && (K1 == 0 || is_damping<K1>()) && (K2 == 0 || is_damping<K2>());
+}
+
+// The flagged particles of damping_fast: the branching functions above, effects in stack order.  Out of line (rare).
+template <int K0, int K1, int K2>
+__device__ __noinline__ void damping_generic(const rebx_b200_pass* P, const double (*s_c)[kC], const Geo* gp, double m, double inv_mb,
+                                             double tau_a, double tau_e, double tau_inc, double d_factor, Vec3* out) {
+    constexpr bool EINC = slot_of<REBX_B200_GAS_DAMPING, K0, K1, K2>() >= 0 || slot_of<REBX_B200_TYPE_I, K0, K1, K2>() >= 0;
+    const Geo g = *gp;
+    const Elements o = elements<EINC>(s_c[0][0], s_c[0][kC - 1], s_c[0][1], m, inv_mb, g);
+    Vec3 fd = {0., 0., 0.};
+    auto one = [&](auto kc, int j) {
+        constexpr int K = decltype(kc)::value;
+        Vec3 f = {0., 0., 0.};
+        if constexpr (K == REBX_B200_MODIFY_ORBITS) f = modify_orbits(s_c[j], P->fx[j].flags, g, o, m, tau_a, tau_e, tau_inc);
+        else if constexpr (K == REBX_B200_GAS_DAMPING) f = gas_damping(s_c[j], g, o, m, d_factor);
+        else if constexpr (K == REBX_B200_TYPE_I) f = type_I_migration(s_c[j], g, o, m);
+        fd.x += f.x; fd.y += f.y; fd.z += f.z;
+    };
+    one(std::integral_constant<int, K0>{}, 0);
+    if constexpr (K1 != 0) one(std::integral_constant<int, K1>{}, 1);
+    if constexpr (K2 != 0) one(std::integral_constant<int, K2>{}, 2);
+    *out = fd;
+}
 
 template <int K, int V>
 __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const double* __restrict__ c, const Geo& g, const Elements& o, double mr,
@@ -392,6 +560,9 @@ __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const double* 
 // CTA geometry per stack class (tools/tol_variants.sh sweeps them on the GPU): threads per CTA and resident CTAs per
 // SM asked of the register allocator.  "light" = the streaming stacks (radiation, gr_potential, J2/J4), "heavy" =
 // the ones with transcendentals (yarkovsky, damping trio).
+#ifndef REBXB_TOL_FAST_DAMP
+#define REBXB_TOL_FAST_DAMP 1
+#endif
 #ifndef REBXB_TOL_PREFETCH_ALL
 #define REBXB_TOL_PREFETCH_ALL 0
 #endif
@@ -426,6 +597,55 @@ __host__ __device__ constexpr int tol_threads() {
     return trio_stack<K0, K1, K2>() ? REBXB_TOL_TRIO_THREADS : (yark_stack<K0, K1, K2>() ? REBXB_TOL_YARK_THREADS : REBXB_TOL_LIGHT_THREADS);
 }
 
+// ---- operands of the NEXT iteration staged through shared memory (cp.async) ------------------------------------------
+// ncu on the trio sweep (profiles/r02_kernel_tolerance_planetesimal_disk.txt and the source page): 22 % of all stall
+// samples sit on the first use of the ~14 operands loaded at the top of an iteration (4 warps per scheduler, 128
+// registers: nobody to hide an HBM round trip behind, and no registers for a second set of operands); an L2 / L1
+// prefetch one iteration ahead only took 30 % off that wait (pass_common.cuh).  Here every thread copies ITS OWN next
+// operands global -> shared with cp.async (8 bytes each, no registers, no barrier: a thread only ever reads what it
+// copied itself, after cp.async.wait_group), one full iteration (~8000 cycles) ahead, and the top of the loop reads
+// them back with LDS (29 cycles).  Two stages of (operand arrays) x (CTA threads) doubles of dynamic shared memory.
+#ifndef REBXB_TOL_LOCKSTEP
+#define REBXB_TOL_LOCKSTEP 0
+#endif
+#ifndef REBXB_TOL_STAGED
+#define REBXB_TOL_STAGED 1
+#endif
+template <int K0, int K1, int K2>
+__host__ __device__ constexpr int staged_doubles() {        // per thread and stage; 0 = this stack is not staged
+    constexpr bool VEL  = Traits<K0>::vel  || Traits<K1>::vel  || Traits<K2>::vel;
+    constexpr bool MASS = Traits<K0>::mass || Traits<K1>::mass || Traits<K2>::mass;
+    constexpr bool RAD  = Traits<K0>::rad  || Traits<K1>::rad  || Traits<K2>::rad;
+    return 6 + (VEL ? 3 : 0) + (MASS ? 1 : 0) + (RAD ? 1 : 0) + Traits<K0>::ntab + Traits<K1>::ntab + Traits<K2>::ntab +
+           ((Traits<K0>::itab || Traits<K1>::itab || Traits<K2>::itab) ? 1 : 0);      // an int table takes a double's slot
+}
+template <int V, int K0, int K1, int K2>
+__host__ __device__ constexpr bool staged_stack() { return REBXB_TOL_STAGED && V == 1 && trio_stack<K0, K1, K2>(); }
+template <int V, int K0, int K1, int K2>
+__host__ __device__ constexpr int staged_bytes() { return staged_stack<V, K0, K1, K2>() ? 2*staged_doubles<K0, K1, K2>()*tol_threads<K0, K1, K2>()*8 : 0; }
+
+__device__ __forceinline__ void cp_async8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async4(int* smem_dst, const int* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
+
+template <int K, int T>
+__device__ __forceinline__ void stage_params(const rebx_b200_effect& fx, int64_t k, double* base, int& slot) {
+#pragma unroll
+    for (int j = 0; j < Traits<K>::ntab; j++) cp_async8(base + (slot++)*T, fx.tab[j] + k);
+    if constexpr (Traits<K>::itab) cp_async4(reinterpret_cast<int*>(base + (slot++)*T), fx.itab + k);
+}
+template <int K, int T>
+__device__ __forceinline__ void unstage_params(const double* base, int& slot, Params<K, 1>& q) {
+#pragma unroll
+    for (int j = 0; j < Traits<K>::ntab; j++) q.t[j][0] = base[(slot++)*T];
+    if constexpr (Traits<K>::itab) q.it[0] = *reinterpret_cast<const int*>(base + (slot++)*T);
+}
+
 template <int V, int K0, int K1, int K2>
 __global__ void __launch_bounds__(tol_threads<K0, K1, K2>(), tol_blocks<K0, K1, K2>())
 pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ partials) {
@@ -435,12 +655,35 @@ pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
     constexpr bool DAMP = is_damping<K0>() || is_damping<K1>() || is_damping<K2>();
     constexpr bool EINC = K0 == REBX_B200_GAS_DAMPING || K1 == REBX_B200_GAS_DAMPING || K2 == REBX_B200_GAS_DAMPING ||
                           K0 == REBX_B200_TYPE_I || K1 == REBX_B200_TYPE_I || K2 == REBX_B200_TYPE_I;
-    constexpr int T = tol_threads<K0, K1, K2>(), W = T/32;
+    constexpr bool FAST_DAMP = REBXB_TOL_FAST_DAMP && all_damping<K0, K1, K2>();
+    constexpr int T = tol_threads<K0, K1, K2>();
     // prefetch the next iteration's operands in the sweeps with transcendentals (few warps, long chains per particle)
     constexpr bool PREFETCH = REBXB_TOL_PREFETCH_ALL || trio_stack<K0, K1, K2>() || yark_stack<K0, K1, K2>();
     __shared__ double s_c[3][kC];
     __shared__ double s_org[8];
-    __shared__ double s_red[W][3];
+    const int64_t n = P.st.n;
+    const int64_t ntiles = (n + V - 1)/V;
+    const int64_t stride = (int64_t)gridDim.x*T;
+    constexpr bool STAGED = staged_stack<V, K0, K1, K2>();
+    constexpr bool LOCKSTEP = REBXB_TOL_LOCKSTEP && (trio_stack<K0, K1, K2>() || yark_stack<K0, K1, K2>());
+    constexpr int ND = staged_doubles<K0, K1, K2>();
+    extern __shared__ __align__(16) double s_stage[];                    // [2][ND][T] when STAGED
+    auto stage = [&](int buf, int64_t k) {                               // this thread's operands of particle k -> stage `buf`
+        double* base = s_stage + (size_t)buf*ND*T + threadIdx.x;
+        int slot = 0;
+        cp_async8(base + (slot++)*T, P.st.x + k); cp_async8(base + (slot++)*T, P.st.y + k); cp_async8(base + (slot++)*T, P.st.z + k);
+        if constexpr (VEL)  { cp_async8(base + (slot++)*T, P.st.vx + k); cp_async8(base + (slot++)*T, P.st.vy + k); cp_async8(base + (slot++)*T, P.st.vz + k); }
+        if constexpr (MASS) cp_async8(base + (slot++)*T, P.st.m + k);
+        if constexpr (RAD)  cp_async8(base + (slot++)*T, P.st.r + k);
+        cp_async8(base + (slot++)*T, P.st.ax + k); cp_async8(base + (slot++)*T, P.st.ay + k); cp_async8(base + (slot++)*T, P.st.az + k);
+        stage_params<K0, T>(P.fx[0], k, base, slot);
+        if constexpr (K1 != 0) stage_params<K1, T>(P.fx[1], k, base, slot);
+        if constexpr (K2 != 0) stage_params<K2, T>(P.fx[2], k, base, slot);
+        cp_async_commit();
+    };
+    int buf = 0;
+    // the first particle's operands travel while the CTA's constants are worked out
+    if constexpr (STAGED) { if ((int64_t)blockIdx.x*T + threadIdx.x < ntiles) stage(0, (int64_t)blockIdx.x*T + threadIdx.x); }
     if (threadIdx.x < P.n_effects) fill_constants(P.fx[threadIdx.x], P.fx[threadIdx.x].body, s_c[threadIdx.x]);
     if (threadIdx.x < 8) s_org[threadIdx.x] = P.fx[0].body[threadIdx.x];
     __syncthreads();
@@ -448,13 +691,20 @@ pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
     const double ox = s_org[REBX_B200_BODY_X], oy = s_org[REBX_B200_BODY_X+1], oz = s_org[REBX_B200_BODY_X+2];
     Vec3 red0 = {0., 0., 0.}, red1 = {0., 0., 0.}, red2 = {0., 0., 0.};
 
-    const int64_t n = P.st.n;
-    const int64_t ntiles = (n + V - 1)/V;
-    const int64_t stride = (int64_t)gridDim.x*T;
-    for (int64_t t = (int64_t)blockIdx.x*T + threadIdx.x; t < ntiles; t += stride) {
+    // LOCKSTEP (an option that did NOT pay, off): the warps of a CTA start every iteration together, one barrier per
+    // ~8000-cycle iteration, in case the schedulers let the warps of an SM drift iterations apart and the sweep ended
+    // in a tail of a few warps finishing alone (ncu: 14 % of all warp time waits at the final barrier).  Measured
+    // (profiles/r02_tol_ab.txt): trio 0.0575 -> 0.0640 ms, asteroids 0.0396 -> 0.0415 -- warps in phase hide each
+    // other's latencies worse than warps out of phase.  The trip count stays uniform over the CTA for it.
+    const int64_t t_cta = (int64_t)blockIdx.x*T;
+    const int64_t iters = t_cta < ntiles ? (ntiles - t_cta + stride - 1)/stride : 0;        // uniform over the CTA
+    for (int64_t it = 0; it < iters; it++) {
+        const int64_t t = t_cta + threadIdx.x + it*stride;
+        if constexpr (LOCKSTEP) __syncthreads();
+        if (t >= ntiles) continue;
         const int64_t k = t*V;
         const bool full = (k + V <= n);
-        if constexpr (PREFETCH) {
+        if constexpr (PREFETCH && !STAGED) {
             if (t + stride < ntiles) {
                 const int64_t kn = (t + stride)*V;
                 prefetch_next(P.st.x + kn); prefetch_next(P.st.y + kn); prefetch_next(P.st.z + kn);
@@ -468,15 +718,31 @@ pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
             }
         }
         double x[V], y[V], z[V], vx[V], vy[V], vz[V], m[V], r[V], ax[V], ay[V], az[V];
+        Params<K0, V> q0; Params<K1, V> q1; Params<K2, V> q2;
+        if constexpr (STAGED) {
+            // start the copies of the next particle, then wait for this one's (issued one iteration ago)
+            if (t + stride < ntiles) { stage(buf ^ 1, t + stride); cp_async_wait<1>(); } else cp_async_wait<0>();
+            const double* base = s_stage + (size_t)buf*ND*T + threadIdx.x;
+            int slot = 0;
+            x[0] = base[(slot++)*T]; y[0] = base[(slot++)*T]; z[0] = base[(slot++)*T];
+            if constexpr (VEL)  { vx[0] = base[(slot++)*T]; vy[0] = base[(slot++)*T]; vz[0] = base[(slot++)*T]; }
+            if constexpr (MASS) m[0] = base[(slot++)*T];
+            if constexpr (RAD)  r[0] = base[(slot++)*T];
+            ax[0] = base[(slot++)*T]; ay[0] = base[(slot++)*T]; az[0] = base[(slot++)*T];
+            unstage_params<K0, T>(base, slot, q0);
+            if constexpr (K1 != 0) unstage_params<K1, T>(base, slot, q1);
+            if constexpr (K2 != 0) unstage_params<K2, T>(base, slot, q2);
+            buf ^= 1;
+        } else {
         ld<V>(P.st.x, k, full, x); ld<V>(P.st.y, k, full, y); ld<V>(P.st.z, k, full, z);
         if constexpr (VEL)  { ld<V>(P.st.vx, k, full, vx); ld<V>(P.st.vy, k, full, vy); ld<V>(P.st.vz, k, full, vz); }
         if constexpr (MASS) { ld<V>(P.st.m, k, full, m); }
         if constexpr (RAD)  { ld<V>(P.st.r, k, full, r); }
         ld<V>(P.st.ax, k, full, ax); ld<V>(P.st.ay, k, full, ay); ld<V>(P.st.az, k, full, az);
-        Params<K0, V> q0; Params<K1, V> q1; Params<K2, V> q2;
         load_params<K0, V>(P.fx[0], k, full, q0);
         if constexpr (K1 != 0) load_params<K1, V>(P.fx[1], k, full, q1);
         if constexpr (K2 != 0) load_params<K2, V>(P.fx[2], k, full, q2);
+        }
 #pragma unroll
         for (int v = 0; v < V; v++) {
             if (v > 0 && !full) break;
@@ -492,17 +758,46 @@ pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
             } else { g.dvx = g.dvy = g.dvz = g.rv = 0.0; }
             const double mp = MASS ? m[v] : 0.0, rp = RAD ? r[v] : 0.0;
             Elements o = {0., 0., 0., 0., 0.};
-            double mr = 0.0;
+            double mr = 0.0, inv_mb = 0.0;
             if constexpr (DAMP) {
-                const double inv_mb = frcp(s_c[0][1] + mp);         // 1/(M + m): serves mu^-1 and the mass ratio
-                o = elements<EINC>(s_c[0][0], s_c[0][kC - 1], s_c[0][1], mp, inv_mb, g);
+                inv_mb = frcp(s_c[0][1] + mp);                      // 1/(M + m): serves mu^-1 and the mass ratio
+                if constexpr (!FAST_DAMP) o = elements<EINC>(s_c[0][0], s_c[0][kC - 1], s_c[0][1], mp, inv_mb, g);
                 mr = mp*inv_mb;
             }
             Vec3 a = {ax[v], ay[v], az[v]};
             Vec3 fd = {0., 0., 0.};                                 // sum of the damping forces of the stack
+            if constexpr (FAST_DAMP) {
+                // the whole stack in one basic block (damping_fast), flagged particles redone by the branching functions
+                constexpr int SMO = slot_of<REBX_B200_MODIFY_ORBITS, K0, K1, K2>(), SGD = slot_of<REBX_B200_GAS_DAMPING, K0, K1, K2>(),
+                              STI = slot_of<REBX_B200_TYPE_I, K0, K1, K2>();
+                auto tabv = [&](int slot, int j) -> double {
+                    return slot == 0 ? q0.t[j < Traits<K0>::ntab ? j : 0][v] : (slot == 1 ? q1.t[j < Traits<K1>::ntab ? j : 0][v] : q2.t[j < Traits<K2>::ntab ? j : 0][v]);
+                };
+                const double tau_a = SMO >= 0 ? tabv(SMO, 0) : 0.0, tau_e = SMO >= 0 ? tabv(SMO, 1) : 0.0, tau_inc = SMO >= 0 ? tabv(SMO, 2) : 0.0;
+                const double d_factor = SGD >= 0 ? tabv(SGD, 0) : 0.0;
+                const int mo_flags = SMO >= 0 ? P.fx[SMO >= 0 ? SMO : 0].flags : 0;
+                const double* cmo = s_c[SMO >= 0 ? SMO : 0]; const double* cgd = s_c[SGD >= 0 ? SGD : 0]; const double* cti = s_c[STI >= 0 ? STI : 0];
+                unsigned bad = 0, band = 0;
+                double a_el;
+                const DampCoef dc = damping_fast<(SMO >= 0), (SGD >= 0), (STI >= 0)>(cmo, cgd, cti, mo_flags, g, mp, inv_mb, tau_a, tau_e, tau_inc, d_factor, a_el, bad, band);
+                double T_mo = 1.0, T_ti = 1.0;
+                if constexpr (SMO >= 0) { if (mo_flags & REBX_B200_FLAG_TRAP) T_mo = (a_el > cmo[13]) ? 1.0 : -10.0; }
+                if constexpr (STI >= 0) T_ti = (a_el > cti[13]) ? 1.0 : -10.0;
+                if (band) {             // inside a trap's transition band: the axis with the reference's exact operation sequence
+                    const double ax_exact = exact_semimajor_axis(s_c[0][0], s_c[0][1], mp, g.dx, g.dy, g.dz, g.dvx, g.dvy, g.dvz);
+                    if (band & 1u) T_mo = planet_trap(ax_exact, cmo[3], cmo[4]);
+                    if (band & 2u) T_ti = planet_trap(ax_exact, cti[8], cti[9]);
+                }
+                const double cv = dc.cv_mo*T_mo + dc.cv_ti*T_ti;
+                fd.x = g.dvx*cv + g.dx*dc.cr;
+                fd.y = g.dvy*cv + g.dy*dc.cr;
+                fd.z = g.dvz*(cv + dc.cz) + g.dz*dc.cr;
+                if (bad) damping_generic<K0, K1, K2>(&P, s_c, &g, mp, inv_mb, tau_a, tau_e, tau_inc, d_factor, &fd);
+            } else {
             apply<K0, V>(P.fx[0], s_c[0], g, o, mr, mp, rp, q0, v, is_damping<K0>() ? fd : a, red0);
             if constexpr (K1 != 0) apply<K1, V>(P.fx[1], s_c[1], g, o, mr, mp, rp, q1, v, is_damping<K1>() ? fd : a, red1);
             if constexpr (K2 != 0) apply<K2, V>(P.fx[2], s_c[2], g, o, mr, mp, rp, q2, v, is_damping<K2>() ? fd : a, red2);
+            }
             if constexpr (DAMP) {
                 // rebx_com_force, PARTICLE coordinates (src/rebxtools.c:131-141), once for the summed force:
                 // p.a += f - mr f ; body.a -= mr f with mr = m/(M + m).  The back-reaction of the whole stack is
@@ -516,15 +811,13 @@ pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
         }
         st<V>(P.st.ax, k, full, ax); st<V>(P.st.ay, k, full, ay); st<V>(P.st.az, k, full, az);
     }
-    reduce_effect<K0, W>(red0, 0, s_red, partials);
-    reduce_effect<K1, W>(red1, 1, s_red, partials);
-    reduce_effect<K2, W>(red2, 2, s_red, partials);
-    finalize_by_last_cta<T, K0, K1, K2, 0>(P, partials, ApplyTail{});
+    finish_sums<T, K0, K1, K2, 0>(red0, red1, red2, Vec3{0., 0., 0.}, P, partials, ApplyTail{});
 }
 
 typedef void (*tol_fn)(const rebx_b200_pass, double*);
-struct TolCombo { int k[3]; tol_fn fn[2]; int threads; };
-#define REBXB_TCOMBO(a, b, c) { {a, b, c}, { pass_kernel_tol<1, a, b, c>, pass_kernel_tol<2, a, b, c> }, tol_threads<a, b, c>() },
+struct TolCombo { int k[3]; tol_fn fn[2]; int threads; int smem[2]; };
+#define REBXB_TCOMBO(a, b, c) { {a, b, c}, { pass_kernel_tol<1, a, b, c>, pass_kernel_tol<2, a, b, c> }, tol_threads<a, b, c>(), \
+                                { staged_bytes<1, a, b, c>(), staged_bytes<2, a, b, c>() } },
 static const TolCombo kTolCombos[] = {
     REBXB_TCOMBO(1,0,0) REBXB_TCOMBO(2,0,0) REBXB_TCOMBO(3,0,0) REBXB_TCOMBO(4,0,0) REBXB_TCOMBO(5,0,0) REBXB_TCOMBO(6,0,0) REBXB_TCOMBO(7,0,0)
     REBXB_TCOMBO(2,3,0) REBXB_TCOMBO(3,2,0) REBXB_TCOMBO(4,3,0) REBXB_TCOMBO(3,4,0) REBXB_TCOMBO(1,3,0) REBXB_TCOMBO(3,1,0)
@@ -563,9 +856,21 @@ bool tol_launch(const rebx_b200_pass& sub, int take, double* workspace, cudaStre
     const int V = vsel ? 2 : 1;
     tol::tol_fn fn = combo->fn[vsel];
     const int64_t tiles = (sub.st.n + V - 1)/V;
-    int grid = grid_for(reinterpret_cast<const void*>(fn), tiles, combo->threads, 0, combo->threads);
+    const int smem = combo->smem[vsel];
+    if (smem > 48*1024) {
+        // opt in to more than 48 KB of dynamic shared memory: once per kernel and device
+        static thread_local std::vector<std::pair<const void*, int>> done;
+        int dev = -1; cudaGetDevice(&dev);
+        bool seen = false;
+        for (const auto& d : done) if (d.first == reinterpret_cast<const void*>(fn) && d.second == dev) seen = true;
+        if (!seen) {
+            if (cudaFuncSetAttribute(reinterpret_cast<const void*>(fn), cudaFuncAttributeMaxDynamicSharedMemorySize, smem) != cudaSuccess) { cudaGetLastError(); return false; }
+            done.push_back({reinterpret_cast<const void*>(fn), dev});
+        }
+    }
+    int grid = grid_for(reinterpret_cast<const void*>(fn), tiles, combo->threads, smem, combo->threads);
     if (full_grid) { const int64_t want = (tiles + combo->threads - 1)/combo->threads; grid = (int)(want < kMaxBlocks ? want : kMaxBlocks); }
-    fn<<<grid, combo->threads, 0, s>>>(sub, workspace);
+    fn<<<grid, combo->threads, smem, s>>>(sub, workspace);
     *grid_out = grid;
     return true;
 }

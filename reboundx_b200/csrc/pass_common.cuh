@@ -148,7 +148,6 @@ __device__ __forceinline__ void reduce_effect(Vec3 red, int e, double (*s_red)[3
 #pragma unroll
             for (int w = 0; w < NWARPS; w++) s += s_red[w][threadIdx.x];
             partials[((size_t)blockIdx.x*REBX_B200_MAX_EFFECTS + e)*3 + threadIdx.x] = s;
-            __threadfence();            // visible device-wide before this CTA takes its ticket (finalize_by_last_cta)
         }
     }
 }
@@ -162,32 +161,14 @@ __device__ __forceinline__ void reduce_effect(Vec3 red, int e, double (*s_red)[3
 // fx[e].backreaction and, when the pass asks for it (REBX_B200_PASS_APPLY_BACKREACTION), adds the sums to the body's
 // acceleration like apply_backreaction_kernel.  atomicInc wraps the counter back to 0 on the last ticket, so a
 // workspace that was zeroed once after allocation stays ready for every later launch.
+//
+// The whole epilogue is ONE pass for all effects and components (ncu at one iteration per thread: the epilogue of
+// three reduce_effect calls, four fences and nine serial 256-lane reductions was 40 % of a 24 us launch, and
+// tools/size_scaling.py put the fixed cost of a trio sweep at 25 us of its 56): one shuffle tree + one barrier for the
+// CTA's partials, one fence, and the last CTA reduces all (effect, component) pairs side by side -- every pair in
+// finalize_kernel's own order, so the bits do not change.
 constexpr int kFinalLanes = 256;
 constexpr size_t kTicketOffset = (size_t)kMaxBlocks*REBX_B200_MAX_EFFECTS*3 + 8;      // in doubles, behind the scalar tail
-
-template <int K, int T>
-__device__ __forceinline__ void finalize_effect(const rebx_b200_pass& P, int e, const double* partials, double* s_sum) {
-    if constexpr (Traits<K>::red) {
-        double* out = P.fx[e].backreaction;
-        if (out == nullptr) return;
-        const int nblocks = gridDim.x;
-        for (int c = 0; c < 3; c++) {
-            for (int lane = threadIdx.x; lane < kFinalLanes; lane += T) {
-                double acc = 0.0;
-                for (int b = lane; b < nblocks; b += kFinalLanes)
-                    acc += __ldcg(partials + ((size_t)b*REBX_B200_MAX_EFFECTS + e)*3 + c);
-                s_sum[lane] = acc;
-            }
-            __syncthreads();
-            for (int w = kFinalLanes/2; w > 0; w >>= 1) {
-                for (int lane = threadIdx.x; lane < w; lane += T) s_sum[lane] += s_sum[lane + w];
-                __syncthreads();
-            }
-            if (threadIdx.x == 0) out[c] = s_sum[0];
-            __syncthreads();
-        }
-    }
-}
 
 // CTA-uniform: true in the CTA that finishes last.  Called by ALL threads of every CTA of the grid, after the CTA's
 // last global store.
@@ -219,34 +200,94 @@ static __device__ __noinline__ void apply_backreaction_inline(const rebx_b200_pa
     }
 }
 
-// out of line: runs in one CTA per launch, and must not weigh on the register allocation of the sweep's loop
+// All (effect, component) pairs of the stack at once, by the last CTA; out of line (one CTA per launch runs it, and it
+// must not weigh on the register allocation of the sweep's loop).  s_fin: [12][kFinalLanes] doubles.
 template <int T, int K0, int K1, int K2, int K3>
-__device__ __noinline__ void finalize_sums(const rebx_b200_pass& P, const double* partials, double* s_sum) {
-    finalize_effect<K0, T>(P, 0, partials, s_sum);
-    finalize_effect<K1, T>(P, 1, partials, s_sum);
-    finalize_effect<K2, T>(P, 2, partials, s_sum);
-    finalize_effect<K3, T>(P, 3, partials, s_sum);
+__device__ __noinline__ void finalize_sums(const rebx_b200_pass& P, const double* partials, double* s_fin) {
+    constexpr bool R[4] = {Traits<K0>::red, Traits<K1>::red, Traits<K2>::red, Traits<K3>::red};
+    const int nblocks = gridDim.x;
+    bool want[4];
+#pragma unroll
+    for (int e = 0; e < 4; e++) want[e] = R[e] && P.fx[e].backreaction != nullptr;
+    for (int lane = threadIdx.x; lane < kFinalLanes; lane += T) {
+        double acc[12];
+#pragma unroll
+        for (int q = 0; q < 12; q++) acc[q] = 0.0;
+        for (int b = lane; b < nblocks; b += kFinalLanes) {
+            const double* row = partials + (size_t)b*REBX_B200_MAX_EFFECTS*3;
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (!R[e]) continue;
+                if (want[e]) { acc[e*3 + 0] += __ldcg(row + e*3 + 0); acc[e*3 + 1] += __ldcg(row + e*3 + 1); acc[e*3 + 2] += __ldcg(row + e*3 + 2); }
+            }
+        }
+#pragma unroll
+        for (int e = 0; e < 4; e++) {
+            if (!R[e]) continue;
+#pragma unroll
+            for (int c = 0; c < 3; c++) s_fin[(e*3 + c)*kFinalLanes + lane] = acc[e*3 + c];
+        }
+    }
+    __syncthreads();
+    for (int w = kFinalLanes/2; w > 0; w >>= 1) {
+        for (int lane = threadIdx.x; lane < w; lane += T) {
+#pragma unroll
+            for (int e = 0; e < 4; e++) {
+                if (!R[e]) continue;
+#pragma unroll
+                for (int c = 0; c < 3; c++) s_fin[(e*3 + c)*kFinalLanes + lane] += s_fin[(e*3 + c)*kFinalLanes + lane + w];
+            }
+        }
+        __syncthreads();
+    }
+    if (threadIdx.x < 12) {
+        const int e = threadIdx.x/3, c = threadIdx.x - e*3;
+        if (want[e]) P.fx[e].backreaction[c] = s_fin[threadIdx.x*kFinalLanes];
+    }
+    __syncthreads();
 }
 
-// Call at the end of a sweep, after reduce_effect for every effect, by ALL threads of the CTA.  `tail(P)` runs in
-// thread 0 of the last CTA once the sums are written; `always` (uniform over the grid) = take the ticket even when
-// no effect of the stack wants its sum (all fx[].backreaction NULL), because the tail has other work.
+// The end of a sweep, called by ALL threads of the CTA with the thread's running sums: CTA partials, ticket, and in
+// the last CTA the sums and `tail(P)` (thread 0).  `always` (uniform over the grid) = take the ticket even when no
+// effect of the stack wants its sum (all fx[].backreaction NULL), because the tail has other work.  s_red: [W][12].
 template <int T, int K0, int K1, int K2, int K3, class Tail>
-__device__ __forceinline__ void finalize_by_last_cta(const rebx_b200_pass& P, double* partials, Tail tail, bool always = false) {
-    constexpr bool RED = Traits<K0>::red || Traits<K1>::red || Traits<K2>::red || Traits<K3>::red;
+__device__ __forceinline__ void finish_sums(const Vec3& red0, const Vec3& red1, const Vec3& red2, const Vec3& red3,
+                                            const rebx_b200_pass& P, double* partials, Tail tail, bool always = false) {
+    constexpr bool R[4] = {Traits<K0>::red, Traits<K1>::red, Traits<K2>::red, Traits<K3>::red};
+    constexpr bool RED = R[0] || R[1] || R[2] || R[3];
     // A stack without sums (radiation_forces, yarkovsky_effect) takes no ticket at all: those sweeps run at the
     // 64-register cap and the tail's presence alone cost them 3.5x the spill traffic (ptxas -v), 0.195 -> 0.251 ms
     // on the fused leapfrog step.  Their callers keep the separate one-thread launch for the body.
     if constexpr (!RED) return;
-    __shared__ double s_sum[RED ? kFinalLanes : 1];
+    constexpr int W = T/32;
+    __shared__ double s_red[W][12];
+    __shared__ double s_fin[RED ? 12*kFinalLanes : 1];
+    double v[12] = {red0.x, red0.y, red0.z, red1.x, red1.y, red1.z, red2.x, red2.y, red2.z, red3.x, red3.y, red3.z};
+    const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+#pragma unroll
+    for (int e = 0; e < 4; e++) {
+        if (!R[e]) continue;
+#pragma unroll
+        for (int c = 0; c < 3; c++) {
+            double x = v[e*3 + c];
+#pragma unroll
+            for (int off = 16; off > 0; off >>= 1) x += __shfl_down_sync(0xffffffffu, x, off);
+            if (lane == 0) s_red[warp][e*3 + c] = x;
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x < 12 && R[threadIdx.x/3]) {
+        double s = 0.0;
+#pragma unroll
+        for (int w = 0; w < W; w++) s += s_red[w][threadIdx.x];
+        partials[(size_t)blockIdx.x*REBX_B200_MAX_EFFECTS*3 + threadIdx.x] = s;
+    }
     bool any = always;
-    if constexpr (Traits<K0>::red) any |= P.fx[0].backreaction != nullptr;
-    if constexpr (Traits<K1>::red) any |= P.fx[1].backreaction != nullptr;
-    if constexpr (Traits<K2>::red) any |= P.fx[2].backreaction != nullptr;
-    if constexpr (Traits<K3>::red) any |= P.fx[3].backreaction != nullptr;
+#pragma unroll
+    for (int e = 0; e < 4; e++) if (R[e]) any |= P.fx[e].backreaction != nullptr;
     if (!any) return;                                   // uniform over the grid: nobody takes a ticket
     if (!last_cta_ticket(partials)) return;
-    finalize_sums<T, K0, K1, K2, K3>(P, partials, s_sum);
+    finalize_sums<T, K0, K1, K2, K3>(P, partials, s_fin);
     if (threadIdx.x == 0) tail(P);
 }
 // the force sweeps' tail: add the sums to the body when the pass asks for it.  Every other CTA stored its
