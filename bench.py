@@ -365,7 +365,7 @@ def extra_workload(cx, name, coordinates, steps):
     exec_order, nf = add_order[::-1], len(add_order)
     w = getattr(workloads, builder)(n)
     out = {"config": workload_label(name, n, add_order, coordinates), "evals_per_step": n*nf}
-    for math in (("exact", "tolerance") if coordinates == "PARTICLE" else ("exact",)):
+    for math in (("exact", "tolerance") if coordinates in ("PARTICLE", "JACOBI") else ("exact",)):
         shard = device.Shard(w, exec_order, cx.dev, coordinates=coordinates, math=math, standalone=True)
         l0 = shard.launches
         ms = cx.timed(shard.evaluate, steps)

@@ -874,6 +874,8 @@ static const Combo* find_combo(const rebx_b200_effect* fx, int count) {
 
 // kernels_tol.cu
 bool tol_launch(const rebx_b200_pass& sub, int take, double* workspace, cudaStream_t s, int* grid_out);
+bool tol_jacobi_launch(const rebx_b200_pass& P, unsigned ntiles, const double* tile_prefix, double* tvec, double* tile_tsums, const double* carry7,
+                       const void* grid, const double* status, const double* mref, cudaStream_t s);
 
 static bool use_tma() {
     // opt-in (REBX_B200_KERNEL=tma): measured slower than the occupancy-tuned plain sweep on B200
@@ -1105,8 +1107,11 @@ int rebx_b200_jacobi_sweep(const rebx_b200_pass* pass, void* scratch, const doub
     const JacobiCombo* combo = find_jacobi_combo(P);
     if (!combo) return cudaErrorNotSupported;
     JacobiScratch J(scratch, P.st.n);
-    combo->fn<<<(unsigned)J.ntiles, kScanThreads, 0, s>>>(P, J.rows7, J.tvec, J.rows3, carry7, J.grid, J.totals + 7,
-                                                          (flags & REBX_B200_COM_WHOLE) ? J.mref : nullptr);
+    const double* mref = (flags & REBX_B200_COM_WHOLE) ? J.mref : nullptr;
+    // REBX_B200_PASS_TOLERANCE: the sweep in tolerance arithmetic where kernels_tol.cu has the stack (the scans are the same)
+    if (!((P.reserved & REBX_B200_PASS_TOLERANCE) &&
+          tol_jacobi_launch(P, (unsigned)J.ntiles, J.rows7, J.tvec, J.rows3, carry7, J.grid, J.totals + 7, mref, s)))
+        combo->fn<<<(unsigned)J.ntiles, kScanThreads, 0, s>>>(P, J.rows7, J.tvec, J.rows3, carry7, J.grid, J.totals + 7, mref);
     scan_tiles_kernel<3, true><<<3, kTileScanThreads, 0, s>>>(J.rows3, J.ntiles, tsum3 ? tsum3 : J.totals + 8);
     cudaError_t err = cudaGetLastError();
     if (err == cudaSuccess && launches) *launches += 2;

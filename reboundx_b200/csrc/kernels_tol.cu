@@ -29,6 +29,7 @@
 #include "rebx_b200.h"
 #include "pass_common.cuh"
 #include "exact_math.cuh"       // rcp_seed / rsqrt_seed (MUFU.RCP64H / MUFU.RSQ64H)
+#include "jacobi_common.cuh"    // CTA-wide scan + mass grid of the centre-of-mass pipeline
 
 namespace rebxb {
 namespace tol {
@@ -87,15 +88,16 @@ __device__ __forceinline__ double pow_uniform2(double x, double xinv, double p, 
 
 // ---- per-CTA constants of one effect entry (shared memory; particle-independent sub-expressions) ------------
 constexpr int kC = 24;
-// common: c[0] = G, c[1] = body mass, c[2] = 1/body mass, c[kC-1] = 1/G
+// common: c[0] = G, c[1] = body mass, c[2] = 1/body mass, c[kC-1] = 1/G, c[kC-2] = sqrt(G)
 // RADIATION     c[3] = G m_s (mu), c[4] = 1/c
 // HARMONICS     c[3] = 3/2 G m J2 R^2, c[4] = 5/8 G m J4 R^4 (0 without J4), c[5..13] = u, v, w
 // GR_POTENTIAL  c[3] = 6 (G m)^2/c^2
 // YARKOVSKY     c[3] = 1/c, c[4] = 3 L/(64 pi c), c[5] = 3 L/(16 pi c), c[6] = 0.5 (sb/pi^5)^(1/4) [times emissivity^(1/4) per particle], c[7] = L
 // MODIFY_ORBITS c[3] = ide_position, c[4] = ide_width
-// GAS_DAMPING   c[3] = sqrt(G M), c[4] = 1/sqrt(G M), c[5] = cs_coeff, c[6] = 1/cs_coeff, c[7] = -tau_coeff M
+// GAS_DAMPING   c[3] = sqrt(G M), c[4] = 1/sqrt(G M), c[5] = cs_coeff, c[6] = 1/cs_coeff, c[7] = -tau_coeff M, c[8] = -tau_coeff
 // TYPE_I        c[3] = beta, c[4] = h0, c[5] = 1/h0, c[6] = sd0, c[7] = s, c[8] = dedge, c[9] = hedge,
-//               c[10] = sqrt(M^3), c[11] = sqrt(G), c[12] = (2.7 + 1.1 s)/2
+//               c[10] = sqrt(M^3), c[11] = sqrt(G), c[12] = (2.7 + 1.1 s)/2, c[13], c[14] = trap band, c[15], c[16] = beta, s in
+//               quarters (or 99), c[17] = 1/sqrt(M^3)
 // Exponent p of a uniform power law as an integer number of quarters, |p| <= 2.75, or 99: not on that grid.
 __device__ __forceinline__ double quarter_code(double p) {
     const double k = 4.0*p;
@@ -104,7 +106,7 @@ __device__ __forceinline__ double quarter_code(double p) {
 
 __device__ void fill_constants(const rebx_b200_effect& fx, const double* __restrict__ body, double* __restrict__ c) {
     const double G = fx.scal[0], bm = body[REBX_B200_BODY_M];
-    c[0] = G; c[1] = bm; c[2] = frcp(bm); c[kC - 1] = frcp(G);
+    c[0] = G; c[1] = bm; c[2] = frcp(bm); c[kC - 1] = frcp(G); c[kC - 2] = fsqrt(G);
     switch (fx.kind) {
     case REBX_B200_RADIATION: c[3] = G*bm; c[4] = 1.0/fx.scal[1]; break;
     case REBX_B200_HARMONICS: {
@@ -123,7 +125,7 @@ __device__ void fill_constants(const rebx_b200_effect& fx, const double* __restr
         c[3] = fx.scal[1]; c[4] = fx.scal[2];
         c[13] = fx.scal[1]*(1.0 + fx.scal[2])*(1.0 + 1e-12); c[14] = fx.scal[1]*(1.0 - fx.scal[2])*(1.0 - 1e-12);    // trap band (trap_factor)
         break;
-    case REBX_B200_GAS_DAMPING: { double sq, rsq; fsqrt2(G*bm, sq, rsq); c[3] = sq; c[4] = rsq; c[5] = fx.scal[1]; c[6] = frcp(fx.scal[1]); c[7] = -fx.scal[2]*bm; break; }
+    case REBX_B200_GAS_DAMPING: { double sq, rsq; fsqrt2(G*bm, sq, rsq); c[3] = sq; c[4] = rsq; c[5] = fx.scal[1]; c[6] = frcp(fx.scal[1]); c[7] = -fx.scal[2]*bm; c[8] = -fx.scal[2]; break; }
     case REBX_B200_TYPE_I:
         c[3] = fx.scal[1]; c[4] = fx.scal[2]; c[5] = frcp(fx.scal[2]); c[6] = fx.scal[3]; c[7] = fx.scal[4]; c[8] = fx.scal[5]; c[9] = fx.scal[6];
         { double rq; fsqrt2(bm*bm*bm, c[10], rq); c[17] = rq; }
@@ -391,6 +393,9 @@ __device__ __forceinline__ Vec3 type_I_migration(const double* __restrict__ c, c
 //   flagged: inclination outside acos_near_one's series, e/h below pow_1p2's single-precision seed, an exponent that
 //   is not a multiple of 1/4 (uniform: then every particle takes the generic path), operands outside exact_math's domain.
 struct DampCoef { double cv_mo, cv_ti, cr, cz; };     // fd = dv (cv_mo T_mo + cv_ti T_ti) + d cr ; fd.z += dvz cz
+// What the formulas need of the reference body's MASS: per CTA in PARTICLE coordinates (the central body, from the
+// constants in shared memory), per particle in JACOBI coordinates (the mass interior to the particle).
+struct BodyK { double bm, sqrtGM, rsqrtGM, rsqrtM3; };
 
 // x^(k/4) and x^(-k/4) from x, 1/x and the two roots, k = c (an integer in [-11, 11], uniform): selects and products only
 __device__ __forceinline__ double pow_quarters(double kq, double x, double xinv, double s1, double rs1, double s2, double rs2, double& inv) {
@@ -407,11 +412,11 @@ __device__ __forceinline__ double pow_quarters(double kq, double x, double xinv,
 
 template <bool MO, bool GD, bool TI>
 __device__ __forceinline__ DampCoef damping_fast(const double* __restrict__ cmo, const double* __restrict__ cgd, const double* __restrict__ cti,
-                                                 int mo_flags, const Geo& g, double m, double inv_mb,
+                                                 int mo_flags, const BodyK& bk, const Geo& g, double m, double inv_mb,
                                                  double tau_a, double tau_e, double tau_inc, double d_factor,
                                                  double& a_out, unsigned& bad, unsigned& band) {
-    const double* c0 = MO ? cmo : (GD ? cgd : cti);            // G, M, 1/G are the same in every effect of the stack
-    const double G = c0[0], bm = c0[1], inv_G = c0[kC - 1];
+    const double* c0 = MO ? cmo : (GD ? cgd : cti);            // G and 1/G are the same in every effect of the stack
+    const double G = c0[0], bm = bk.bm, inv_G = c0[kC - 1];
     // -- two-body elements (elements<> above), straight-line
     const double mu = G*(m + bm);
     const double v2 = g.dvx*g.dvx + g.dvy*g.dvy + g.dvz*g.dvz;
@@ -456,15 +461,15 @@ __device__ __forceinline__ DampCoef damping_fast(const double* __restrict__ cmo,
         if (mo_flags & REBX_B200_FLAG_TRAP) band |= (!(a > cmo[13]) && (a > cmo[14]) && !is_absent(tau_a)) ? 1u : 0u;
     }
     if constexpr (GD) {
-        const double vk = cgd[3]*rsa;
+        const double vk = bk.sqrtGM*rsa;
         const double v = fsqrt(e*e + inc*inc)*vk;
         double s4, rs4;
         fsqrt2(sa, s4, rs4);
         const double cs = cgd[5]*rs4;
         const double voc = v*s4*cgd[6];
         const double voc3 = voc*voc*voc;
-        const double coeff = (v <= cs) ? 1. : ((inc < cs*sa*cgd[4]) ? voc3 : voc3*voc);
-        const double ite = m*frcp(cgd[7]*d_factor*a*a*coeff);
+        const double coeff = (v <= cs) ? 1. : ((inc < cs*sa*bk.rsqrtGM) ? voc3 : voc3*voc);
+        const double ite = m*frcp(cgd[8]*bk.bm*d_factor*a*a*coeff);
         const bool on = !is_absent(d_factor);
         ite_sum += on ? ite : 0.0;
         o.cz += on ? ite : 0.0;
@@ -480,7 +485,7 @@ __device__ __forceinline__ DampCoef damping_fast(const double* __restrict__ cmo,
         const double eh = e*inv_h, ih = inc*inv_h;
         const double sd = cti[6]*inv_sd;
         const double ih4 = inv_h*inv_h;                                  // 1/h^4 from the inverse power, no quotient
-        const double inv_wave = m*sd*cti[11]*sa*cti[17]*(ih4*ih4);
+        const double inv_wave = m*sd*cti[11]*sa*bk.rsqrtM3*(ih4*ih4);
         const double x1 = eh*(1.0/2.25), x2 = eh*(1.0/2.84), x3 = eh*(1.0/2.02);
         const double x22 = x2*x2, x32 = x3*x3;
         // pow_1p2, straight-line: x = 0 gives 0 by the select, a positive x below the seed's range is flagged
@@ -779,7 +784,8 @@ pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
                 const double* cmo = s_c[SMO >= 0 ? SMO : 0]; const double* cgd = s_c[SGD >= 0 ? SGD : 0]; const double* cti = s_c[STI >= 0 ? STI : 0];
                 unsigned bad = 0, band = 0;
                 double a_el;
-                const DampCoef dc = damping_fast<(SMO >= 0), (SGD >= 0), (STI >= 0)>(cmo, cgd, cti, mo_flags, g, mp, inv_mb, tau_a, tau_e, tau_inc, d_factor, a_el, bad, band);
+                const BodyK bk = {s_c[0][1], cgd[3], cgd[4], cti[17]};      // entries of an absent effect are never read
+                const DampCoef dc = damping_fast<(SMO >= 0), (SGD >= 0), (STI >= 0)>(cmo, cgd, cti, mo_flags, bk, g, mp, inv_mb, tau_a, tau_e, tau_inc, d_factor, a_el, bad, band);
                 double T_mo = 1.0, T_ti = 1.0;
                 if constexpr (SMO >= 0) { if (mo_flags & REBX_B200_FLAG_TRAP) T_mo = (a_el > cmo[13]) ? 1.0 : -10.0; }
                 if constexpr (STI >= 0) T_ti = (a_el > cti[13]) ? 1.0 : -10.0;
@@ -813,6 +819,122 @@ pass_kernel_tol(const __grid_constant__ rebx_b200_pass P, double* __restrict__ p
     }
     finish_sums<T, K0, K1, K2, 0>(red0, red1, red2, Vec3{0., 0., 0.}, P, partials, ApplyTail{});
 }
+
+// ---- JACOBI coordinates: the sweep of the centre-of-mass pipeline in tolerance arithmetic ----------------------------
+// Same interface and the same scans as jacobi_sweep_kernel (kernels_jacobi.cuh; reference src/rebxtools.c:92-128 as two
+// O(N) scans): the interior MASS of particle k still carries the reference's own rounding, bit for bit (mass grid,
+// dip, literal recurrences) -- mu = G (m + M_k) enters v^2 - mu/d, a difference of nearly equal numbers.  What
+// changes is everything behind it: COM_k = S_k * (1/M_k) by a Newton reciprocal instead of six IEEE divisions, and the
+// stacked damping forces by damping_fast with the body-mass constants (BodyK) worked out per particle.
+template <int K0, int K1, int K2>
+__global__ void __launch_bounds__(kScanThreads, 2)
+jacobi_sweep_tol_kernel(const __grid_constant__ rebx_b200_pass P, const double* __restrict__ tile_prefix,
+                        double* __restrict__ tvec, double* __restrict__ tile_tsums, const double* __restrict__ carry7,
+                        const MassGrid* __restrict__ grid, const double* __restrict__ status, const double* __restrict__ mref, int ntiles) {
+    constexpr int SMO = slot_of<REBX_B200_MODIFY_ORBITS, K0, K1, K2>(), SGD = slot_of<REBX_B200_GAS_DAMPING, K0, K1, K2>(),
+                  STI = slot_of<REBX_B200_TYPE_I, K0, K1, K2>();
+    __shared__ double s_warp[kScanThreads/32][7];
+    __shared__ double s_c[3][kC];
+    __shared__ double s_unit[REBX_B200_BODY_DOUBLES];        // a unit-mass body at rest: the body-independent constants only
+    if (threadIdx.x < REBX_B200_BODY_DOUBLES) s_unit[threadIdx.x] = (threadIdx.x == REBX_B200_BODY_M) ? 1.0 : 0.0;
+    __syncthreads();
+    if (threadIdx.x < P.n_effects) fill_constants(P.fx[threadIdx.x], s_unit, s_c[threadIdx.x]);
+    __syncthreads();
+    const rebx_b200_state& st = P.st;
+    const MassGrid mg = *grid;
+    const bool literal = mref != nullptr && status[0] != 0.0;
+    const double G = s_c[0][0];
+    // Resident grid, a CTA walks the tiles (one tile = kScanThreads consecutive particles, as in the scans around this
+    // kernel): the constants are worked out once per CTA, not once per tile (measured with one CTA per tile: 107 us at
+    // 10^6 particles against 48 us for the same forces in PARTICLE coordinates).
+    for (int tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const int64_t k = (int64_t)tile*kScanThreads + threadIdx.x;
+        const bool live = k < st.n;
+        double px = 0, py = 0, pz = 0, pvx = 0, pvy = 0, pvz = 0, pm = 0;
+        double tau_a = 0.0, tau_e = 0.0, tau_inc = 0.0, d_factor = 0.0, a0 = 0.0, a1 = 0.0, a2 = 0.0;
+        if (live) {
+            px = __ldcs(st.x + k); py = __ldcs(st.y + k); pz = __ldcs(st.z + k); pvx = __ldcs(st.vx + k); pvy = __ldcs(st.vy + k); pvz = __ldcs(st.vz + k); pm = __ldcs(st.m + k);
+            if constexpr (SMO >= 0) { tau_a = __ldcs(P.fx[SMO >= 0 ? SMO : 0].tab[0] + k); tau_e = __ldcs(P.fx[SMO >= 0 ? SMO : 0].tab[1] + k); tau_inc = __ldcs(P.fx[SMO >= 0 ? SMO : 0].tab[2] + k); }
+            if constexpr (SGD >= 0) d_factor = __ldcs(P.fx[SGD >= 0 ? SGD : 0].tab[0] + k);
+            a0 = __ldcs(st.ax + k); a1 = __ldcs(st.ay + k); a2 = __ldcs(st.az + k);
+        }
+        bool unused_flag = false;
+        double v[7] = {live ? quantise_mass(pm, mg, unused_flag) : 0.0, px*pm, py*pm, pz*pm, pvx*pm, pvy*pm, pvz*pm};
+        double total[7];
+        block_exclusive_scan<7>(v, total, s_warp);
+        double M = tile_prefix[tile] + v[0];
+        if (carry7) M = carry7[0] + M;
+        if (mg.ok && M == mg.lead && st.index_base + k >= 1) M = mg.dip;
+        if (literal && live) M = mref[k];
+        double S[6];
+#pragma unroll
+        for (int j = 0; j < 6; j++) {
+            S[j] = tile_prefix[(size_t)(1 + j)*ntiles + tile] + v[1 + j];
+            if (carry7) S[j] = carry7[1 + j] + S[j];
+        }
+        double t[3] = {0.0, 0.0, 0.0};
+        const long long gi = st.index_base + k;
+        if (live && gi != 0) {
+            const double inv_M = (M > 0.) ? frcp(M) : 1.0;
+            Geo g;
+            g.dx = px - S[0]*inv_M; g.dy = py - S[1]*inv_M; g.dz = pz - S[2]*inv_M;
+            g.r2 = g.dx*g.dx + g.dy*g.dy + g.dz*g.dz;
+            fsqrt2(g.r2, g.r, g.rinv);
+            g.rinv2 = g.rinv*g.rinv;
+            g.dvx = pvx - S[3]*inv_M; g.dvy = pvy - S[4]*inv_M; g.dvz = pvz - S[5]*inv_M;
+            g.rv = g.dx*g.dvx + g.dy*g.dvy + g.dz*g.dvz;
+            const double inv_mb = frcp(M + pm), mr = pm*inv_mb;
+            BodyK bk;
+            bk.bm = M;
+            fsqrt2(G*M, bk.sqrtGM, bk.rsqrtGM);
+            const double rsm = bk.rsqrtGM*s_c[0][kC - 2];           // 1/sqrt(M) = sqrt(G)/sqrt(G M)
+            bk.rsqrtM3 = rsm*rsm*rsm;
+            const int mo_flags = SMO >= 0 ? P.fx[SMO >= 0 ? SMO : 0].flags : 0;
+            const double* cmo = s_c[SMO >= 0 ? SMO : 0]; const double* cgd = s_c[SGD >= 0 ? SGD : 0]; const double* cti = s_c[STI >= 0 ? STI : 0];
+            unsigned bad = 0, band = 0;
+            double a_el;
+            const DampCoef dc = damping_fast<(SMO >= 0), (SGD >= 0), (STI >= 0)>(cmo, cgd, cti, mo_flags, bk, g, pm, inv_mb, tau_a, tau_e, tau_inc, d_factor, a_el, bad, band);
+            double T_mo = 1.0, T_ti = 1.0;
+            if constexpr (SMO >= 0) { if (mo_flags & REBX_B200_FLAG_TRAP) T_mo = (a_el > cmo[13]) ? 1.0 : -10.0; }
+            if constexpr (STI >= 0) T_ti = (a_el > cti[13]) ? 1.0 : -10.0;
+            if (band) {
+                const double ax_exact = exact_semimajor_axis(G, M, pm, g.dx, g.dy, g.dz, g.dvx, g.dvy, g.dvz);
+                if (band & 1u) T_mo = planet_trap(ax_exact, cmo[3], cmo[4]);
+                if (band & 2u) T_ti = planet_trap(ax_exact, cti[8], cti[9]);
+            }
+            const double cv = dc.cv_mo*T_mo + dc.cv_ti*T_ti;
+            Vec3 fd;
+            fd.x = g.dvx*cv + g.dx*dc.cr;
+            fd.y = g.dvy*cv + g.dy*dc.cr;
+            fd.z = g.dvz*(cv + dc.cz) + g.dz*dc.cr;
+            if (bad) {
+                // flagged: the branching functions, with this particle's own body-mass constants
+                double body[REBX_B200_BODY_DOUBLES];
+                for (int j = 0; j < REBX_B200_BODY_DOUBLES; j++) body[j] = 0.0;
+                body[REBX_B200_BODY_M] = M;
+                double c_loc[3][kC];
+                for (int j = 0; j < P.n_effects; j++) fill_constants(P.fx[j], body, c_loc[j]);
+                damping_generic<K0, K1, K2>(&P, c_loc, &g, pm, inv_mb, tau_a, tau_e, tau_inc, d_factor, &fd);
+            }
+            __stcs(st.ax + k, a0 + fd.x); __stcs(st.ay + k, a1 + fd.y); __stcs(st.az + k, a2 + fd.z);
+            t[0] = mr*fd.x; t[1] = mr*fd.y; t[2] = mr*fd.z;
+        }
+        if (live) { __stcs(tvec + k, t[0]); __stcs(tvec + st.n + k, t[1]); __stcs(tvec + 2*st.n + k, t[2]); }
+        double tt[3], tot3[3];
+        tt[0] = t[0]; tt[1] = t[1]; tt[2] = t[2];
+        block_exclusive_scan<3>(tt, tot3, reinterpret_cast<double (*)[3]>(&s_warp[0][0]));
+#pragma unroll
+        for (int c = 0; c < 3; c++) if (threadIdx.x == c) tile_tsums[(size_t)c*ntiles + tile] = tot3[c];
+    }
+}
+
+typedef void (*jacobi_tol_fn)(const rebx_b200_pass, const double*, double*, double*, const double*, const MassGrid*, const double*, const double*, int);
+struct JacobiTolCombo { int k[3]; jacobi_tol_fn fn; };
+#define REBXB_JTCOMBO(a, b, c) { {a, b, c}, jacobi_sweep_tol_kernel<a, b, c> },
+static const JacobiTolCombo kJacobiTolCombos[] = {
+    REBXB_JTCOMBO(5,0,0) REBXB_JTCOMBO(6,0,0) REBXB_JTCOMBO(7,0,0)
+    REBXB_JTCOMBO(5,6,7) REBXB_JTCOMBO(7,6,5)
+};
 
 typedef void (*tol_fn)(const rebx_b200_pass, double*);
 struct TolCombo { int k[3]; tol_fn fn[2]; int threads; int smem[2]; };
@@ -873,6 +995,21 @@ bool tol_launch(const rebx_b200_pass& sub, int take, double* workspace, cudaStre
     fn<<<grid, combo->threads, smem, s>>>(sub, workspace);
     *grid_out = grid;
     return true;
+}
+
+// The tolerance-mode Jacobi sweep for the stack of `P` (kinds 5, 6, 7), or false when it has no instantiation here (the
+// caller then launches the exact jacobi_sweep_kernel).  Arguments as for that kernel.
+bool tol_jacobi_launch(const rebx_b200_pass& P, unsigned ntiles, const double* tile_prefix, double* tvec, double* tile_tsums, const double* carry7,
+                       const void* grid, const double* status, const double* mref, cudaStream_t s) {
+    for (const tol::JacobiTolCombo& c : tol::kJacobiTolCombos) {
+        bool ok = true;
+        for (int j = 0; j < 3; j++) if (c.k[j] != (j < P.n_effects ? P.fx[j].kind : 0)) ok = false;
+        if (!ok) continue;
+        const int grid_ctas = grid_for(reinterpret_cast<const void*>(c.fn), (int64_t)ntiles*kScanThreads, kScanThreads, 0, kScanThreads);
+        c.fn<<<grid_ctas, kScanThreads, 0, s>>>(P, tile_prefix, tvec, tile_tsums, carry7, static_cast<const MassGrid*>(grid), status, mref, (int)ntiles);
+        return true;
+    }
+    return false;
 }
 
 }  // namespace rebxb

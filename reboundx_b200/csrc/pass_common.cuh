@@ -186,18 +186,37 @@ __device__ __forceinline__ bool last_cta_ticket(double* partials) {
     return true;
 }
 
-// apply_backreaction_kernel's loop, by ONE thread: effects in stack order, only bodies inside this shard.
+// apply_backreaction_kernel's loop, by ONE thread: effects in stack order, only bodies inside this shard.  The whole
+// grid is waiting for this thread, so every load it needs is issued before the first one is used (body indices and
+// sums side by side), and consecutive effects on the same body -- the usual case: one central body -- share one
+// read-modify-write of its acceleration.  The additions happen in stack order, as in the kernel.
 static __device__ __noinline__ void apply_backreaction_inline(const rebx_b200_pass& P) {
-    for (int e = 0; e < P.n_effects; e++) {
-        const rebx_b200_effect& fx = P.fx[e];
-        if (fx.backreaction == nullptr) continue;
-        const long long bi = (long long)fx.body[REBX_B200_BODY_INDEX];
-        const long long k = bi - P.st.index_base;
-        if (bi < 0 || k < 0 || k >= P.st.n) continue;
-        P.st.ax[k] = __ldcg(P.st.ax + k) + fx.backreaction[0];
-        P.st.ay[k] = __ldcg(P.st.ay + k) + fx.backreaction[1];
-        P.st.az[k] = __ldcg(P.st.az + k) + fx.backreaction[2];
+    long long kk[REBX_B200_MAX_EFFECTS];
+    double br[REBX_B200_MAX_EFFECTS][3];
+#pragma unroll
+    for (int e = 0; e < REBX_B200_MAX_EFFECTS; e++) {
+        kk[e] = -1;
+        br[e][0] = br[e][1] = br[e][2] = 0.0;
+        if (e < P.n_effects && P.fx[e].backreaction != nullptr) {
+            const long long bi = (long long)__ldcg(P.fx[e].body + REBX_B200_BODY_INDEX);
+            const long long k = bi - P.st.index_base;
+            if (bi >= 0 && k >= 0 && k < P.st.n) kk[e] = k;
+            br[e][0] = __ldcg(P.fx[e].backreaction + 0); br[e][1] = __ldcg(P.fx[e].backreaction + 1); br[e][2] = __ldcg(P.fx[e].backreaction + 2);
+        }
     }
+    long long cur = -1;
+    double a0 = 0.0, a1 = 0.0, a2 = 0.0;
+#pragma unroll
+    for (int e = 0; e < REBX_B200_MAX_EFFECTS; e++) {
+        if (kk[e] < 0) continue;
+        if (kk[e] != cur) {
+            if (cur >= 0) { P.st.ax[cur] = a0; P.st.ay[cur] = a1; P.st.az[cur] = a2; }
+            cur = kk[e];
+            a0 = __ldcg(P.st.ax + cur); a1 = __ldcg(P.st.ay + cur); a2 = __ldcg(P.st.az + cur);
+        }
+        a0 += br[e][0]; a1 += br[e][1]; a2 += br[e][2];
+    }
+    if (cur >= 0) { P.st.ax[cur] = a0; P.st.ay[cur] = a1; P.st.az[cur] = a2; }
 }
 
 // All (effect, component) pairs of the stack at once, by the last CTA; out of line (one CTA per launch runs it, and it

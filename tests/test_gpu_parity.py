@@ -826,6 +826,36 @@ def test_tolerance_mode_against_the_reference(built, monkeypatch, name, base):
             assert abs(got[k][0] - exact0[k]) <= 1e-12*scale[k] + 1e-300, (k, got[k][0], exact0[k], scale[k])
 
 
+@pytest.mark.parametrize("n", [20000, 300001])
+@pytest.mark.parametrize("base", ["zero", "gravity"])
+def test_tolerance_mode_jacobi_frame(built, monkeypatch, n, base):
+    """REBX_B200_MATH=tolerance in the reference's default frame of the damping forces (JACOBI): the centre-of-mass
+    pipeline with jacobi_sweep_tol_kernel (kernels_tol.cu) -- the interior masses still carry the reference's own
+    rounding (mass grid), the forces are damping_fast with per-particle body-mass constants.  Norm-wise inside the
+    north-star tolerance against the O(N) oracle (the reference's own COM recurrence, pinned against its O(N^2) loops
+    at N <= 2*10^4 by tests/test_oracle.py), and against the reference's loops themselves at N = 2*10^4."""
+    from oracle import oracle
+    from reboundx_b200 import workloads
+    w = workloads.planetesimal_disk(n)
+    acc0 = acc_variants(w, 41)[base]
+    exact = _com_device(w, TRIO, "JACOBI", acc0)
+    monkeypatch.setenv("REBX_B200_MATH", "tolerance")
+    got = _com_device(w, TRIO, "JACOBI", acc0)
+    assert not errors(got, exact)["bit_identical"], "REBX_B200_MATH=tolerance did not select the tolerance Jacobi sweep"
+    lin, _ = oracle.port_apply(w, TRIO[::-1], acc0, "JACOBI", com="linear")
+    e = errors(got, lin)
+    assert e["max_normwise"] <= TOL, e
+    assert all(np.isfinite(a).all() for a in got)
+    # the per-component outliers are those of the PARTICLE-frame tolerance sweep (components far below |a|)
+    assert e["frac_component_above_tol"] <= 1e-2, e
+    if n <= 20000:
+        want, _ = oracle_acc(w, TRIO, acc0, "JACOBI")
+        er = errors(got, want)
+        assert er["max_normwise"] <= TOL, er
+    ee = errors(got, exact)
+    assert ee["max_normwise"] <= TOL, ee
+
+
 def test_tolerance_mode_resident_full_size(built):
     """device.Shard(math="tolerance") at the configurations' full sizes: finite everywhere, and within the tolerance of
     the bit-exact sweep on every particle (norm-wise; the exact sweep itself is pinned to the oracle above)."""
