@@ -8,10 +8,13 @@
  * code and the unmodified Python wrapper bind to this library exactly as they bind to the
  * reference's libreboundx.  Each declaration cites the reference declaration it replaces.
  *
- * Out of scope: operators, splitting integrators,
+ * The callers either side of the force path are declared too: the operator API with the
+ * built-in operators "integrate_force", "drift" and "kick", and the binary state format.
+ *
+ * Out of scope: every other built-in operator, the splitting integrators,
  * interpolation and the other built-in forces.  Their declarations are intentionally
- * absent; a custom force (user function pointer) still runs on the host through the same
- * dispatcher.
+ * absent; a custom force or operator (user function pointer) still runs on the host through the
+ * same dispatcher.
  */
 #ifndef REBOUNDX_B200_REBOUNDX_H
 #define REBOUNDX_B200_REBOUNDX_H
@@ -251,8 +254,10 @@ struct rebx_binary_field rebx_input_read_binary_field(FILE* inf);               
 void rebx_input_skip_binary_field(FILE* inf, long field_size);                                                     /* src/input.c:56 */
 
 /* ---- additions of this build (all keep the rebx_ prefix, reference .github/workflows/c.yml:34) */
-/* Tell the SoA parameter tables that a value was changed through a raw pointer obtained
- * from rebx_get_param (the API setters mark the tables dirty themselves). */
+/* Forces a rebuild of the SoA parameter tables at the next force evaluation.  NOT needed for the reference's C
+ * idiom of keeping a pointer from rebx_get_param and writing through it later: parameters whose pointer was handed
+ * out are tracked and compared with the tables' copy at every call (api_core.cpp / dispatch.cpp, "escaped" params).
+ * Kept for callers that change values behind the API in other ways. */
 void rebx_mark_params_dirty(struct rebx_extras* rebx);
 /* Bulk ingest: sets `param_name` on particles[index[k]] (index==NULL => k) for k<n. */
 void rebx_set_param_double_array(struct rebx_extras* const rebx, const char* const param_name, const int64_t* index, const double* val, size_t n);
