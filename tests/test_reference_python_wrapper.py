@@ -143,8 +143,8 @@ def test_the_references_own_parameter_tests_pass_unmodified(reboundx):
     """reference reboundx/tests/test_params.py, class TestParams (23 tests of the parameter API through
     reboundx.params.Params: add / update / copy semantics of doubles and ints, force-valued and custom-struct
     parameters, unregistered names, re-registration, len / iter / del), imported in place and run UNMODIFIED against
-    this library.  Its setUp also loads an OPERATOR as a third parameter holder; operators are out of this library's
-    scope, so for this test `Extras.load_operator` hands back a force object of that name instead -- the same
+    this library.  Its setUp also loads the OPERATOR "modify_mass" as a third parameter holder; that built-in operator is out of this
+    library's scope (only integrate_force / drift / kick are built in), so for this test `Extras.load_operator` hands back a force object of that name instead -- the same
     `.params` interface over the same list API, which is what the tests exercise."""
     import importlib.util
     import unittest
