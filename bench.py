@@ -18,6 +18,7 @@ Further keys:
   strong          the SAME 10^7 particles split over the N GPUs (strong scaling), with the 1-GPU time of the same
                   ensemble measured in the same run -> efficiency_vs_1gpu
   sharded_parity  (N > 1) a subsample of every rank's shard re-evaluated as ONE shard on rank 0 and compared bit for bit
+  other_math      (N = 1) the headline sweep in the other arithmetic build (tolerance when the run is exact)
   workloads       (N = 1, headline workload) the other BASELINE configurations -- ring, asteroids, planetesimals in
                   PARTICLE and JACOBI coordinates -- each with ms_per_step, roofline (bit-exact and tolerance-mode
                   arithmetic) and e2e
@@ -323,10 +324,12 @@ def roofline_for(workload, math, coordinates, shard, kernel_ms, exec_order):
     return hbm
 
 
-def e2e_leg(cx, w, add_order, coordinates, steps, nf, n):
+def e2e_leg(cx, w, add_order, coordinates, steps, nf, n, n_active=None):
     """The REBOUND-facing call on host particle arrays, copies inside the timed region."""
     from reboundx_b200 import scenarios
     sim, rebx, _ = scenarios.build(w, add_order, coordinates=coordinates)
+    if n_active is not None:
+        sim.N_active = n_active
     t_first = time.perf_counter()
     sim.additional_forces()                # first call: pins the caller's array (cudaHostRegister), builds and uploads the tables
     first_ms = (time.perf_counter() - t_first)*1e3
@@ -381,6 +384,13 @@ def extra_workload(cx, name, coordinates, steps):
         torch.cuda.empty_cache()
     if not cx.args.no_e2e:
         out["e2e"] = e2e_leg(cx, w, add_order, coordinates, 5, nf, n)
+        if name == "asteroid_ensemble" and coordinates == "PARTICLE":
+            # BASELINE config 4 names `gr` (the 1PN effect of src/gr.c:65-164, N_active = 1: the star is active, the
+            # asteroids are test particles) next to gr_potential: it exists in the host-facing dispatcher only
+            # (device reduction of the test particles' pull -> the active bodies on the host -> device sweep)
+            gr = e2e_leg(cx, w, ["yarkovsky_effect", "gr"], coordinates, 5, 2, n, n_active=1)
+            gr["config"] = workload_label(name, n, ["yarkovsky_effect", "gr"], coordinates) + ", N_active = 1"
+            out["gr_variant_e2e"] = gr
     return out
 
 
@@ -514,6 +524,18 @@ def run_ours(args):
     if world > 1 and not com and not args.no_extras:
         parity = sharded_parity(cx, shard, w, exec_order)
 
+    # ---- the same sweep in the other arithmetic build (the headline stays the default, bit-exact one) ---------------
+    other_math = None
+    if world == 1 and not com and not args.no_extras:
+        om = "tolerance" if args.math == "exact" else "exact"
+        osh = device.Shard(w, exec_order, dev, math=om, standalone=True)
+        oms = cx.timed(osh.evaluate, steps)
+        okm = cx.timed(osh.launch_local, steps)
+        other_math = {"math": om, "ms_per_step": oms, "value": n*nf/(oms*1e-3), "unit": "evals/s",
+                      "roofline": roofline_for(args.workload, om, args.coordinates, osh, okm, exec_order)}
+        del osh
+        torch.cuda.empty_cache()
+
     # ---- resident stepping leg: full drift-kick-drift steps, no PCIe --------------
     resident = resident_wh = None
     if not args.no_e2e and not com:
@@ -626,7 +648,7 @@ def run_ours(args):
                            "l2": l2_note,
                            "sharding": ("index ranges; the central body's record is replicated and re-broadcast (NCCL) only when its owner changed it" if not com else
                                         "index ranges; per step an all-gather of 7 mass moments and of 3 back-reaction sums per rank (JACOBI: exclusive prefix / suffix over ranks; BARYCENTRIC: all-reduce)")},
-                "roofline": roofline, "cpu_baseline": cpu, "e2e": e2e, "e2e_one_simulation_all_gpus": e2e_one, "strong": strong, "sharded_parity": parity,
+                "roofline": roofline, "other_math": other_math, "cpu_baseline": cpu, "e2e": e2e, "e2e_one_simulation_all_gpus": e2e_one, "strong": strong, "sharded_parity": parity,
                 "workloads": extras, "resident_step": resident, "resident_wh_step": resident_wh, "gpu_launches": gpu_launches,
                 "clocks": clocks.summary()}
         sys.stdout.flush()

@@ -10,9 +10,14 @@
 
 namespace rebxb {
 
+// Resident CTAs per SM asked of the register allocator for the Kepler kernels.  3 (80 registers, 24 warps per SM) is what
+// the allocator chose by itself in round 1; since then it drifted to 94-96 registers (2 CTAs, 16 warps) and the fused
+// radiation sweep went 0.390 -> 0.450 ms at 10^7, so the bound is stated.  4 CTAs (64 registers) spill and are slower
+// (0.399 ms, measured round 1); the Yarkovsky variant needs 140 registers and keeps the allocator's choice.
 #ifndef REBXB_KEPLER_MINBLOCKS
-#define REBXB_KEPLER_MINBLOCKS 1        // resident CTAs per SM asked of the register allocator for the Kepler kernels
+#define REBXB_KEPLER_MINBLOCKS 3
 #endif
+template <int K> constexpr int kepler_minblocks() { return K == REBX_B200_RADIATION ? REBXB_KEPLER_MINBLOCKS : 1; }
 
 __global__ void __launch_bounds__(kThreads, REBXB_KEPLER_MINBLOCKS)
 kepler_drift_kernel(rebx_b200_state st, const double* __restrict__ body, double G, double dt) {
@@ -46,7 +51,7 @@ kepler_drift_kernel(rebx_b200_state st, const double* __restrict__ body, double 
 // velocity through the kick, so every CTA can advance its own copy of the body record; the caller refreshes
 // the record afterwards (rebx_b200_gather_bodies).
 template <int K>
-__global__ void __launch_bounds__(kThreads, REBXB_KEPLER_MINBLOCKS)
+__global__ void __launch_bounds__(kThreads, kepler_minblocks<K>())
 wh_kick_drift_kernel(const __grid_constant__ rebx_b200_pass P, double G, double dt_kick, double dt_drift) {
     static_assert(!Traits<K>::red, "the fused kick+drift needs an effect without back-reaction");
     __shared__ double s_body[REBX_B200_BODY_DOUBLES];
