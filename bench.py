@@ -304,7 +304,9 @@ def roofline_for(workload, math, coordinates, shard, kernel_ms, exec_order):
     achieved = shard.algorithmic_bytes/(kernel_ms*1e-3)/1e9
     kname = ("pass_kernel_tol(%s)" if math == "tolerance" else "pass_kernel(%s)") % ",".join(exec_order)
     if com:
-        kname = coordinates.lower() + " pipeline: moments, scans, sweep(%s), apply" % ",".join(exec_order)
+        kname = (("jacobi_fused_tol_kernel(%s)" if math == "tolerance" else "jacobi_fused_kernel(%s)") % ",".join(exec_order) + ": moments, forces, back-reaction suffix in one cooperative launch"
+                 if coordinates == "JACOBI" and shard.standalone else
+                 coordinates.lower() + " pipeline: moments, scans, sweep(%s), apply" % ",".join(exec_order))
     hbm = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": None,
            "kernel": kname, "algorithmic_bytes_per_particle": shard.algorithmic_bytes//shard.n, "kernel_ms": kernel_ms,
            "peak_source": peak_src, "math": math}
@@ -497,7 +499,8 @@ def run_ours(args):
     # index 0) is replicated; its record is broadcast from rank 0 when the owner changed it.
     w = getattr(workloads, builder)(n, seed=3 + rank)
     lo = 0 if rank == 0 else 1
-    shard = device.Shard(w, exec_order, dev, lo=lo, index_base=(0 if rank == 0 else 1 + rank*n), coordinates=args.coordinates, math=args.math)
+    shard = device.Shard(w, exec_order, dev, lo=lo, index_base=(0 if rank == 0 else 1 + rank*n), coordinates=args.coordinates, math=args.math,
+                         standalone=(world == 1))
 
     group = None
     for _ in range(max(3, args.warmup)):

@@ -73,11 +73,14 @@ __device__ __forceinline__ void apply(const rebx_b200_effect& fx, const Origin& 
 // registers, 16 warps/SM, 0.49 eligible warps/cycle, 80 % of HBM); capping them at 64
 // registers (4 CTAs, 32 warps/SM) costs a few spilled doubles but lifts the radiation sweep
 // to 93 % of the measured copy bandwidth.  The FP64-heavy sweeps keep their registers.
+#ifndef REBXB_LIGHT_MINBLOCKS
+#define REBXB_LIGHT_MINBLOCKS 4
+#endif
 template <int K0, int K1, int K2, int K3>
 __host__ __device__ constexpr int min_blocks() {
     constexpr bool light = (K0 == REBX_B200_RADIATION || K0 == REBX_B200_GR_POTENTIAL) &&
                            (K1 == 0 || K1 == REBX_B200_RADIATION || K1 == REBX_B200_GR_POTENTIAL) && K2 == 0 && K3 == 0;
-    return light ? 4*(256/kThreads) : REBXB_HEAVY_MINBLOCKS;
+    return light ? REBXB_LIGHT_MINBLOCKS*(256/kThreads) : REBXB_HEAVY_MINBLOCKS;
 }
 
 // CTA geometry of the plain sweep per stack.  Occupancy moves in coarse steps with 256-thread CTAs (2 CTAs = 16
@@ -876,6 +879,7 @@ static const Combo* find_combo(const rebx_b200_effect* fx, int count) {
 bool tol_launch(const rebx_b200_pass& sub, int take, double* workspace, cudaStream_t s, int* grid_out);
 bool tol_jacobi_launch(const rebx_b200_pass& P, unsigned ntiles, const double* tile_prefix, double* tvec, double* tile_tsums, const double* carry7,
                        const void* grid, const double* status, const double* mref, cudaStream_t s);
+const void* tol_jacobi_fused_kernel(const rebx_b200_pass& P);
 
 static bool use_tma() {
     // opt-in (REBX_B200_KERNEL=tma): measured slower than the occupancy-tuned plain sweep on B200
@@ -1047,7 +1051,7 @@ static_assert(sizeof(MassGrid) <= 8*sizeof(double), "MassGrid must fit its scrat
 
 size_t rebx_b200_scan_scratch_bytes(int64_t n) {
     const int64_t ntiles = (n + kScanThreads - 1)/kScanThreads + 1;
-    return (size_t)(ntiles*10 + 32 + 4*(n + 2))*sizeof(double);
+    return (size_t)(ntiles*10 + 32 + 4*(n + 2) + 2*ntiles)*sizeof(double);     // the last 2*ntiles: per-warp flags of the fused pipeline
 }
 
 // Stage 1 of both centre-of-mass frames: quantised mass + moment tile sums, their scan, the status / literal
@@ -1128,6 +1132,39 @@ int rebx_b200_jacobi_apply(const rebx_b200_state* st, void* scratch, const doubl
     return err;
 }
 
+// The fused pipeline: cudaErrorNotSupported when the device cannot launch cooperatively (the caller falls back).
+static int launch_jacobi_fused(const rebx_b200_pass& P, const JacobiCombo* combo, void* scratch, cudaStream_t s) {
+    static thread_local std::vector<std::pair<int, int>> coop;            // (device, cooperative launch supported)
+    int dev = -1;
+    if (cudaGetDevice(&dev) != cudaSuccess) return cudaErrorNotSupported;
+    int ok = -1;
+    for (const auto& c : coop) if (c.first == dev) ok = c.second;
+    if (ok < 0) {
+        int v = 0;
+        if (cudaDeviceGetAttribute(&v, cudaDevAttrCooperativeLaunch, dev) != cudaSuccess) { cudaGetLastError(); v = 0; }
+        coop.push_back({dev, v});
+        ok = v;
+    }
+    if (!ok || !combo) return cudaErrorNotSupported;
+    const void* fn = nullptr;
+    if (P.reserved & REBX_B200_PASS_TOLERANCE) fn = tol_jacobi_fused_kernel(P);
+    if (!fn) fn = reinterpret_cast<const void*>(combo->fused);
+    JacobiScratch J(scratch, P.st.n);
+    // resident grid: every CTA must be co-resident (cooperative launch); the per-warp aggregates live in the tile rows of
+    // the staged pipeline's scratch, so not more warps than 256-particle tiles
+    int grid = grid_for(fn, (J.ntiles/kFusedWarps)*kScanThreads, kScanThreads, 0, kScanThreads);
+    FusedScratch F;
+    F.agg7 = J.rows7; F.tagg3 = J.rows3; F.tvec = J.tvec; F.mref = J.mref;
+    double* extra = J.mref + (P.st.n + 2);
+    F.first = reinterpret_cast<unsigned long long*>(extra);
+    F.unsafe = reinterpret_cast<unsigned*>(extra + (J.ntiles + 1));
+    int wtiles = (int)((P.st.n + 31)/32);                                  // 32-particle tiles, a contiguous range per warp
+    void* args[] = { const_cast<rebx_b200_pass*>(&P), &F, &wtiles };
+    const cudaError_t err = cudaLaunchCooperativeKernel(fn, dim3((unsigned)grid), dim3(kScanThreads), args, 0, s);
+    if (err == cudaErrorCooperativeLaunchTooLarge || err == cudaErrorNotSupported) { cudaGetLastError(); return cudaErrorNotSupported; }
+    return err;
+}
+
 int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* stream, int* launches) {
     if (!pass || !scratch) return cudaErrorInvalidValue;
     const rebx_b200_pass& P = *pass;
@@ -1146,6 +1183,14 @@ int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* str
             if (rc) return rc;
         }
         return 0;
+    }
+    // One cooperative launch for the whole pipeline (jacobi_fused.cuh) where the device supports it; REBX_B200_JACOBI=staged
+    // keeps the six-launch pipeline below (which is also what a sharded caller drives stage by stage).
+    static const bool staged = [] { const char* e = getenv("REBX_B200_JACOBI"); return e && e[0] == 's'; }();
+    if (!staged) {
+        const int frc = launch_jacobi_fused(P, find_jacobi_combo(P), scratch, static_cast<cudaStream_t>(stream));
+        if (frc == 0) { if (launches) (*launches)++; return 0; }
+        if (frc != cudaErrorNotSupported) return frc;
     }
     int rc = rebx_b200_jacobi_moments(&P.st, scratch, nullptr, nullptr, REBX_B200_COM_WHOLE, stream, launches);
     if (rc == 0) rc = rebx_b200_jacobi_sweep(&P, scratch, nullptr, nullptr, REBX_B200_COM_WHOLE, stream, launches);

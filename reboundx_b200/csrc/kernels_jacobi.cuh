@@ -16,6 +16,7 @@
 #pragma once
 
 #include "jacobi_common.cuh"
+#include "jacobi_fused.cuh"
 
 namespace rebxb {
 
@@ -279,9 +280,52 @@ jacobi_apply_kernel(rebx_b200_state st, const double* __restrict__ tvec, const d
     }
 }
 
+// ---- the whole pipeline in one cooperative launch (jacobi_fused.cuh), reference-exact arithmetic ----------------------
+// The force of the stack on particle k against the centre of mass of the particles in front of it: the body of
+// jacobi_sweep_kernel, operation for operation (IEEE divisions for COM_k = S/M, the effects' own functions).
+template <int K0, int K1, int K2>
+struct JacobiExactForce {
+    struct Ops { int unused; };
+    __device__ __forceinline__ void init(const rebx_b200_pass&) {}
+    __device__ __forceinline__ Ops load(const rebx_b200_pass&, int64_t) { return Ops{0}; }
+    // a += f_e and t += m/(M + m) f_e, effect by effect (the association order of jacobi_sweep_kernel)
+    __device__ __forceinline__ void eval(const rebx_b200_pass& P, const Ops&, int64_t k, double px, double py, double pz, double pvx, double pvy, double pvz,
+                                         double pm, double M, const double (&S)[6], Vec3& a, double (&t)[3]) {
+        double body[REBX_B200_BODY_DOUBLES];
+#pragma unroll
+        for (int j = 0; j < 6; j++) body[REBX_B200_BODY_X + j] = (M > 0.) ? S[j]/M : S[j];
+        body[REBX_B200_BODY_INDEX] = -1.0;
+        body[REBX_B200_BODY_M] = M;
+        const Particle p = {px, py, pz, pvx, pvy, pvz, pm, 0.0};
+        const double mr = pm/(M + pm);
+        const Origin org = load_origin(body);
+        constexpr int NDAMP = (K0 >= 5 && K0 <= 7) + (K1 >= 5 && K1 <= 7) + (K2 >= 5 && K2 <= 7);
+        Orbit oc;
+        const Orbit* so = nullptr;
+        if constexpr (NDAMP >= 2) { oc = orbit_from_particle<true, true, false>(P.fx[0].scal[0], p, org, body); so = &oc; }
+        Vec3 f = damping_force<K0>(P.fx[0], org, body, p, k, so);
+        a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
+        if constexpr (K1 != 0) {
+            f = damping_force<K1>(P.fx[1], org, body, p, k, so);
+            a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
+        }
+        if constexpr (K2 != 0) {
+            f = damping_force<K2>(P.fx[2], org, body, p, k, so);
+            a.x += f.x; a.y += f.y; a.z += f.z;  t[0] += mr*f.x; t[1] += mr*f.y; t[2] += mr*f.z;
+        }
+    }
+};
+
+template <int K0, int K1, int K2>
+__global__ void __launch_bounds__(kScanThreads, 2)
+jacobi_fused_kernel(const __grid_constant__ rebx_b200_pass P, const FusedScratch F, const int wtiles) {
+    jacobi_fused_body<JacobiExactForce<K0, K1, K2>>(P, F, wtiles);
+}
+
+typedef void (*jacobi_fused_fn)(const rebx_b200_pass, const FusedScratch, const int);
 typedef void (*jacobi_fn)(const rebx_b200_pass, const double*, double*, double*, const double*, const MassGrid*, const double*, const double*);
-struct JacobiCombo { int k[3]; jacobi_fn fn; };
-#define REBXB_JCOMBO(a, b, c) { {a, b, c}, jacobi_sweep_kernel<a, b, c> },
+struct JacobiCombo { int k[3]; jacobi_fn fn; jacobi_fused_fn fused; };
+#define REBXB_JCOMBO(a, b, c) { {a, b, c}, jacobi_sweep_kernel<a, b, c>, jacobi_fused_kernel<a, b, c> },
 static const JacobiCombo kJacobiCombos[] = {
     REBXB_JCOMBO(5,0,0) REBXB_JCOMBO(6,0,0) REBXB_JCOMBO(7,0,0) REBXB_JCOMBO(9,0,0)
     REBXB_JCOMBO(5,6,0) REBXB_JCOMBO(6,5,0) REBXB_JCOMBO(5,7,0) REBXB_JCOMBO(7,5,0) REBXB_JCOMBO(6,7,0) REBXB_JCOMBO(7,6,0)

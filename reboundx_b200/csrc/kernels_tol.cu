@@ -30,6 +30,7 @@
 #include "pass_common.cuh"
 #include "exact_math.cuh"       // rcp_seed / rsqrt_seed (MUFU.RCP64H / MUFU.RSQ64H)
 #include "jacobi_common.cuh"    // CTA-wide scan + mass grid of the centre-of-mass pipeline
+#include "jacobi_fused.cuh"     // the whole Jacobi pipeline in one cooperative launch
 
 namespace rebxb {
 namespace tol {
@@ -928,9 +929,87 @@ jacobi_sweep_tol_kernel(const __grid_constant__ rebx_b200_pass P, const double* 
     }
 }
 
+// ---- the whole Jacobi pipeline in one cooperative launch (jacobi_fused.cuh), tolerance arithmetic --------------------
+// The per-particle part of jacobi_sweep_tol_kernel as the Force functor of jacobi_fused_body.
+template <int K0, int K1, int K2>
+struct JacobiTolForce {
+    static constexpr int SMO = slot_of<REBX_B200_MODIFY_ORBITS, K0, K1, K2>(), SGD = slot_of<REBX_B200_GAS_DAMPING, K0, K1, K2>(),
+                         STI = slot_of<REBX_B200_TYPE_I, K0, K1, K2>();
+    struct Ops { double tau_a, tau_e, tau_inc, d_factor; };
+    double (*s_c)[kC];
+    __device__ __forceinline__ void init(const rebx_b200_pass& P) {
+        __shared__ double sh_c[3][kC];
+        __shared__ double sh_unit[REBX_B200_BODY_DOUBLES];      // a unit-mass body at rest: the body-independent constants only
+        if (threadIdx.x < REBX_B200_BODY_DOUBLES) sh_unit[threadIdx.x] = (threadIdx.x == REBX_B200_BODY_M) ? 1.0 : 0.0;
+        __syncthreads();
+        if (threadIdx.x < P.n_effects) fill_constants(P.fx[threadIdx.x], sh_unit, sh_c[threadIdx.x]);
+        s_c = sh_c;
+    }
+    __device__ __forceinline__ Ops load(const rebx_b200_pass& P, int64_t k) {
+        Ops o = {0.0, 0.0, 0.0, 0.0};
+        if constexpr (SMO >= 0) { o.tau_a = __ldcs(P.fx[SMO >= 0 ? SMO : 0].tab[0] + k); o.tau_e = __ldcs(P.fx[SMO >= 0 ? SMO : 0].tab[1] + k); o.tau_inc = __ldcs(P.fx[SMO >= 0 ? SMO : 0].tab[2] + k); }
+        if constexpr (SGD >= 0) o.d_factor = __ldcs(P.fx[SGD >= 0 ? SGD : 0].tab[0] + k);
+        return o;
+    }
+    __device__ __forceinline__ void eval(const rebx_b200_pass& P, const Ops& o, int64_t, double px, double py, double pz, double pvx, double pvy, double pvz,
+                                         double pm, double M, const double (&S)[6], Vec3& a, double (&t)[3]) {
+        const double G = s_c[0][0];
+        const double inv_M = (M > 0.) ? frcp(M) : 1.0;
+        Geo g;
+        g.dx = px - S[0]*inv_M; g.dy = py - S[1]*inv_M; g.dz = pz - S[2]*inv_M;
+        g.r2 = g.dx*g.dx + g.dy*g.dy + g.dz*g.dz;
+        fsqrt2(g.r2, g.r, g.rinv);
+        g.rinv2 = g.rinv*g.rinv;
+        g.dvx = pvx - S[3]*inv_M; g.dvy = pvy - S[4]*inv_M; g.dvz = pvz - S[5]*inv_M;
+        g.rv = g.dx*g.dvx + g.dy*g.dvy + g.dz*g.dvz;
+        const double inv_mb = frcp(M + pm), mr = pm*inv_mb;
+        BodyK bk;
+        bk.bm = M;
+        fsqrt2(G*M, bk.sqrtGM, bk.rsqrtGM);
+        const double rsm = bk.rsqrtGM*s_c[0][kC - 2];           // 1/sqrt(M) = sqrt(G)/sqrt(G M)
+        bk.rsqrtM3 = rsm*rsm*rsm;
+        const int mo_flags = SMO >= 0 ? P.fx[SMO >= 0 ? SMO : 0].flags : 0;
+        const double* cmo = s_c[SMO >= 0 ? SMO : 0]; const double* cgd = s_c[SGD >= 0 ? SGD : 0]; const double* cti = s_c[STI >= 0 ? STI : 0];
+        unsigned bad = 0, band = 0;
+        double a_el;
+        const DampCoef dc = damping_fast<(SMO >= 0), (SGD >= 0), (STI >= 0)>(cmo, cgd, cti, mo_flags, bk, g, pm, inv_mb, o.tau_a, o.tau_e, o.tau_inc, o.d_factor, a_el, bad, band);
+        double T_mo = 1.0, T_ti = 1.0;
+        if constexpr (SMO >= 0) { if (mo_flags & REBX_B200_FLAG_TRAP) T_mo = (a_el > cmo[13]) ? 1.0 : -10.0; }
+        if constexpr (STI >= 0) T_ti = (a_el > cti[13]) ? 1.0 : -10.0;
+        if (band) {
+            const double ax_exact = exact_semimajor_axis(G, M, pm, g.dx, g.dy, g.dz, g.dvx, g.dvy, g.dvz);
+            if (band & 1u) T_mo = planet_trap(ax_exact, cmo[3], cmo[4]);
+            if (band & 2u) T_ti = planet_trap(ax_exact, cti[8], cti[9]);
+        }
+        const double cv = dc.cv_mo*T_mo + dc.cv_ti*T_ti;
+        Vec3 fd;
+        fd.x = g.dvx*cv + g.dx*dc.cr;
+        fd.y = g.dvy*cv + g.dy*dc.cr;
+        fd.z = g.dvz*(cv + dc.cz) + g.dz*dc.cr;
+        if (bad) {
+            // flagged: the branching functions, with this particle's own body-mass constants
+            double body[REBX_B200_BODY_DOUBLES];
+            for (int j = 0; j < REBX_B200_BODY_DOUBLES; j++) body[j] = 0.0;
+            body[REBX_B200_BODY_M] = M;
+            double c_loc[3][kC];
+            for (int j = 0; j < P.n_effects; j++) fill_constants(P.fx[j], body, c_loc[j]);
+            damping_generic<K0, K1, K2>(&P, c_loc, &g, pm, inv_mb, o.tau_a, o.tau_e, o.tau_inc, o.d_factor, &fd);
+        }
+        a.x += fd.x; a.y += fd.y; a.z += fd.z;
+        t[0] = mr*fd.x; t[1] = mr*fd.y; t[2] = mr*fd.z;
+    }
+};
+
+template <int K0, int K1, int K2>
+__global__ void __launch_bounds__(kScanThreads, 2)
+jacobi_fused_tol_kernel(const __grid_constant__ rebx_b200_pass P, const FusedScratch F, const int wtiles) {
+    jacobi_fused_body<JacobiTolForce<K0, K1, K2>>(P, F, wtiles);
+}
+
 typedef void (*jacobi_tol_fn)(const rebx_b200_pass, const double*, double*, double*, const double*, const MassGrid*, const double*, const double*, int);
-struct JacobiTolCombo { int k[3]; jacobi_tol_fn fn; };
-#define REBXB_JTCOMBO(a, b, c) { {a, b, c}, jacobi_sweep_tol_kernel<a, b, c> },
+typedef void (*jacobi_fused_tol_fn)(const rebx_b200_pass, const FusedScratch, const int);
+struct JacobiTolCombo { int k[3]; jacobi_tol_fn fn; jacobi_fused_tol_fn fused; };
+#define REBXB_JTCOMBO(a, b, c) { {a, b, c}, jacobi_sweep_tol_kernel<a, b, c>, jacobi_fused_tol_kernel<a, b, c> },
 static const JacobiTolCombo kJacobiTolCombos[] = {
     REBXB_JTCOMBO(5,0,0) REBXB_JTCOMBO(6,0,0) REBXB_JTCOMBO(7,0,0)
     REBXB_JTCOMBO(5,6,7) REBXB_JTCOMBO(7,6,5)
@@ -1010,6 +1089,16 @@ bool tol_jacobi_launch(const rebx_b200_pass& P, unsigned ntiles, const double* t
         return true;
     }
     return false;
+}
+
+// The kernel of the fused Jacobi pipeline in tolerance arithmetic for the stack of `P`, or nullptr.
+const void* tol_jacobi_fused_kernel(const rebx_b200_pass& P) {
+    for (const tol::JacobiTolCombo& c : tol::kJacobiTolCombos) {
+        bool ok = true;
+        for (int j = 0; j < 3; j++) if (c.k[j] != (j < P.n_effects ? P.fx[j].kind : 0)) ok = false;
+        if (ok) return reinterpret_cast<const void*>(c.fused);
+    }
+    return nullptr;
 }
 
 }  // namespace rebxb

@@ -302,11 +302,16 @@ class Shard:
         sharding.allreduce_sum(self.backreaction, group)
         return k + self.com_apply(self.backreaction)
 
-    def launch_local(self, stream=None):
+    def launch_local(self, stream=None, staged=False):
         """Every kernel of one evaluation of this shard, without the cross-shard exchanges (what a
-        kernel-only timing wants): the sweep in PARTICLE coordinates, the staged pipeline otherwise."""
+        kernel-only timing wants): the sweep in PARTICLE coordinates; in the centre-of-mass frames the staged
+        pipeline (moments -> sweep -> apply), or -- JACOBI, the whole ensemble on this device, `staged` False -- the
+        fused one (rebx_b200_launch_jacobi)."""
         if self.coordinates == "PARTICLE":
             return self.launch(stream)
+        if self.coordinates == "JACOBI" and self.standalone and self._com_flags == 1 and not staged:
+            # the whole ensemble on this device: the fused pipeline (one cooperative launch, jacobi_fused.cuh)
+            return self._libcall("rebx_b200_launch_jacobi", ctypes.byref(self._pass), c_void_p(self.scan_scratch.data_ptr()), stream=stream)
         k = self.com_moments(stream)
         if self.coordinates == "JACOBI":
             return k + self.com_sweep(None, stream) + self.com_apply(None, stream)
