@@ -5,12 +5,13 @@
 // guaranteed by the cooperative launch) gives every WARP a contiguous range of 32-particle tiles and runs the three phases
 // with two grid-wide barriers between them; inside a phase a warp never meets a CTA barrier (warp scans by shuffles, the
 // running carry in a per-warp shared-memory slot), so the warps of an SM drift apart and hide each other's latencies:
-//   A  mass moments (sum rn_u(m), sum m r, sum m v) of the warp's range                 -> agg7[7][W], unsafe[W], first[W]
+//   A  mass moments (sum rn_u(m), sum m r, sum m v) of the warp's range (kept in shared memory), summed over the CTA
+//                                                                                       -> agg7[7][G], unsafe[G], first[G]
 //      ---- grid barrier ----   every CTA: sum over the warps in front of it, grand totals, status of the mass-grid
 //                               argument (jacobi_common.cuh), the literal last peel `dip`; every warp: its own prefix
 //   B  tiles in ascending order, running carry: COM_k from the prefix, the stacked damping forces (Force functor:
 //      reference-exact arithmetic in kernels.cu, tolerance arithmetic in kernels_tol.cu),
-//      a += f, t_k = m_k/(M_k + m_k) f -> tvec, sum of t over the range                -> tagg3[3][W]
+//      a += f, t_k = m_k/(M_k + m_k) f -> tvec, sum of t over the range, summed over the CTA   -> tagg3[3][G]
 //      ---- grid barrier ----   every warp: the sum over the warps behind it
 //   C  tiles in descending order: a_j -= sum_{i >= j} t_i
 // (a first version walked 256-particle tiles per CTA with CTA-wide scans, five barriers per tile: 0.128 ms at 10^6 in
@@ -25,14 +26,26 @@
 namespace rebxb {
 
 struct FusedScratch {
-    double* agg7;                   // [7][W]  mass moments of each warp's tile range (component-major), W = warps of the grid
-    double* tagg3;                  // [3][W]  sum of t over each warp's tile range
+    double* agg7;                   // [7][G]  mass moments of each CTA's tile range (component-major), G = CTAs of the grid
+    double* tagg3;                  // [3][G]  sum of t over each CTA's tile range
     double* tvec;                   // [3][n]  t_k
     double* mref;                   // [n]     interior masses by the literal recurrences (status 1 only)
-    unsigned long long* first;      // [W]     smallest index >= 1 in the range whose mass is not zero on the grid (~0: none)
-    unsigned* unsafe;               // [W]     the range holds a mass outside the mass-grid argument
+    unsigned long long* first;      // [G]     smallest index >= 1 in the range whose mass is not zero on the grid (~0: none)
+    unsigned* unsafe;               // [G]     the range holds a mass outside the mass-grid argument
 };
 constexpr int kFusedWarps = kScanThreads/32;
+
+// Phase B's state of the NEXT tile travels global -> shared by cp.async while the current tile's forces are evaluated
+// (every thread copies its own ten operands and reads only those back after cp.async.wait_group: no barrier, no
+// registers); without it the top of every iteration waits a full L2 / HBM round trip (ncu: 6 % of the kernel).
+#ifndef REBXB_JF_STAGED
+#define REBXB_JF_STAGED 1
+#endif
+__device__ __forceinline__ void jf_cp_async8(double* smem_dst, const double* gsrc) {
+    asm volatile("cp.async.ca.shared.global [%0], [%1], 8;" :: "r"((unsigned)__cvta_generic_to_shared(smem_dst)), "l"(gsrc) : "memory");
+}
+__device__ __forceinline__ void jf_cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void jf_cp_async_wait() { asm volatile("cp.async.wait_group %0;" :: "n"(N) : "memory"); }
 
 // Sum over the entries i < lo (forward) or i >= hi (REV) and over all `W` entries of NC component-major rows, by the
 // whole CTA in a fixed order.  part[c], all[c] valid in every thread.
@@ -122,10 +135,14 @@ __device__ __forceinline__ void jacobi_fused_body(const rebx_b200_pass& P, const
     cg::grid_group grid = cg::this_grid();
     __shared__ double s_warp[kFusedWarps][7];
     __shared__ double s_carry[kFusedWarps][7];
+    __shared__ double s_agg[kFusedWarps][7];                            // the warps' mass moments (phase A), later their sums of t (phase B)
+    __shared__ unsigned long long s_wfirst[kFusedWarps];
+    __shared__ unsigned s_wunsafe[kFusedWarps];
     __shared__ unsigned long long s_first;
     const rebx_b200_state& st = P.st;
     const int lane = threadIdx.x & 31, w = threadIdx.x >> 5;
-    const int W = (int)gridDim.x*kFusedWarps, gw = (int)blockIdx.x*kFusedWarps + w;
+    const int G = (int)gridDim.x, b = (int)blockIdx.x;
+    const int W = G*kFusedWarps, gw = b*kFusedWarps + w;
     const int t0 = (int)((int64_t)wtiles*gw/W), t1 = (int)((int64_t)wtiles*(gw + 1)/W);     // this warp's tiles [t0, t1)
     const MassGrid mg0 = make_mass_grid(st.m[0]);
 
@@ -155,9 +172,21 @@ __device__ __forceinline__ void jacobi_fused_body(const rebx_b200_pass& P, const
         }
         if (lane == 0) {
 #pragma unroll
-            for (int c = 0; c < 7; c++) F.agg7[(size_t)c*W + gw] = acc[c];
-            F.unsafe[gw] = any_bad ? 1u : 0u;
-            F.first[gw] = first;
+            for (int c = 0; c < 7; c++) s_agg[w][c] = acc[c];
+            s_wunsafe[w] = any_bad ? 1u : 0u;
+            s_wfirst[w] = first;
+        }
+        __syncthreads();
+        if (threadIdx.x < 7) {                                          // the CTA's moments: its warps in order
+            double sum = 0.0;
+            for (int j = 0; j < kFusedWarps; j++) sum += s_agg[j][threadIdx.x];
+            F.agg7[(size_t)threadIdx.x*G + b] = sum;
+        } else if (threadIdx.x == 32) {
+            unsigned u = 0u;
+            unsigned long long f = ~0ull;
+            for (int j = 0; j < kFusedWarps; j++) { u |= s_wunsafe[j]; f = s_wfirst[j] < f ? s_wfirst[j] : f; }
+            F.unsafe[b] = u;
+            F.first[b] = f;
         }
     }
     __threadfence();
@@ -165,13 +194,13 @@ __device__ __forceinline__ void jacobi_fused_body(const rebx_b200_pass& P, const
 
     // ---- every CTA: the sum in front of it, the totals, the status of the mass-grid argument ---------------------------
     double before[7], all[7];
-    cta_sum_of_aggregates<7, false>(F.agg7, W, (int)blockIdx.x*kFusedWarps, 0, before, all, s_warp);
+    cta_sum_of_aggregates<7, false>(F.agg7, G, b, 0, before, all, s_warp);
     MassGrid mg = mg0;
     bool literal;
     {
         bool u = false;
         unsigned long long fm = ~0ull;
-        for (int i = threadIdx.x; i < W; i += kScanThreads) {
+        for (int i = threadIdx.x; i < G; i += kScanThreads) {
             u = u || F.unsafe[i] != 0u;
             const unsigned long long f = F.first[i];
             fm = f < fm ? f : fm;
@@ -212,22 +241,49 @@ __device__ __forceinline__ void jacobi_fused_body(const rebx_b200_pass& P, const
 #pragma unroll
         for (int c = 0; c < 7; c++) {
             double sum = before[c];
-            for (int j = 0; j < w; j++) sum += F.agg7[(size_t)c*W + (gw - w + j)];
+            for (int j = 0; j < w; j++) sum += s_agg[j][c];
             s_carry[w][c] = sum;
         }
     }
     __syncthreads();
     double tsum[3] = {0.0, 0.0, 0.0};
+#if REBXB_JF_STAGED
+    __shared__ double s_stage[2][10][kScanThreads];
+    auto stage = [&](int buf, int64_t k) {
+        if (k < st.n) {
+            double* base = &s_stage[buf][0][threadIdx.x];
+            jf_cp_async8(base + 0*kScanThreads, st.x + k);  jf_cp_async8(base + 1*kScanThreads, st.y + k);  jf_cp_async8(base + 2*kScanThreads, st.z + k);
+            jf_cp_async8(base + 3*kScanThreads, st.vx + k); jf_cp_async8(base + 4*kScanThreads, st.vy + k); jf_cp_async8(base + 5*kScanThreads, st.vz + k);
+            jf_cp_async8(base + 6*kScanThreads, st.m + k);
+            jf_cp_async8(base + 7*kScanThreads, st.ax + k); jf_cp_async8(base + 8*kScanThreads, st.ay + k); jf_cp_async8(base + 9*kScanThreads, st.az + k);
+        }
+        jf_cp_async_commit();
+    };
+    int buf = 0;
+    if (t0 < t1) stage(0, (int64_t)t0*32 + lane);
+#endif
     for (int tile = t0; tile < t1; tile++) {
         const int64_t k = (int64_t)tile*32 + lane;
         const bool live = k < st.n;
         double px = 0, py = 0, pz = 0, pvx = 0, pvy = 0, pvz = 0, pm = 0, a0 = 0, a1 = 0, a2 = 0;
         typename Force::Ops ops = {};
+#if REBXB_JF_STAGED
+        if (live) ops = force.load(P, k);
+        if (tile + 1 < t1) { stage(buf ^ 1, k + 32); jf_cp_async_wait<1>(); } else jf_cp_async_wait<0>();
+        if (live) {
+            const double* base = &s_stage[buf][0][threadIdx.x];
+            px = base[0*kScanThreads]; py = base[1*kScanThreads]; pz = base[2*kScanThreads];
+            pvx = base[3*kScanThreads]; pvy = base[4*kScanThreads]; pvz = base[5*kScanThreads]; pm = base[6*kScanThreads];
+            a0 = base[7*kScanThreads]; a1 = base[8*kScanThreads]; a2 = base[9*kScanThreads];
+        }
+        buf ^= 1;
+#else
         if (live) {
             px = st.x[k]; py = st.y[k]; pz = st.z[k]; pvx = st.vx[k]; pvy = st.vy[k]; pvz = st.vz[k]; pm = st.m[k];
             ops = force.load(P, k);
             a0 = st.ax[k]; a1 = st.ay[k]; a2 = st.az[k];
         }
+#endif
         bool unused_flag = false;
         double v[7] = {live ? quantise_mass(pm, mg, unused_flag) : 0.0, px*pm, py*pm, pz*pm, pvx*pm, pvy*pm, pvz*pm};
         double total[7];
@@ -260,21 +316,28 @@ __device__ __forceinline__ void jacobi_fused_body(const rebx_b200_pass& P, const
         }
     }
     warp_sum<3>(tsum);
+    __syncthreads();                                                    // every warp has taken its prefix from s_agg
     if (lane == 0) {
 #pragma unroll
-        for (int c = 0; c < 3; c++) F.tagg3[(size_t)c*W + gw] = tsum[c];
+        for (int c = 0; c < 3; c++) s_agg[w][c] = tsum[c];
+    }
+    __syncthreads();
+    if (threadIdx.x < 3) {
+        double sum = 0.0;
+        for (int j = 0; j < kFusedWarps; j++) sum += s_agg[j][threadIdx.x];
+        F.tagg3[(size_t)threadIdx.x*G + b] = sum;
     }
     __threadfence();
     grid.sync();
 
     // ---- phase C: a_j -= sum_{i >= j} t_i, tiles in descending order -----------------------------------------------------
     double behind[3], all3[3];
-    cta_sum_of_aggregates<3, true>(F.tagg3, W, 0, ((int)blockIdx.x + 1)*kFusedWarps, behind, all3, reinterpret_cast<double (*)[3]>(&s_warp[0][0]));
+    cta_sum_of_aggregates<3, true>(F.tagg3, G, 0, b + 1, behind, all3, reinterpret_cast<double (*)[3]>(&s_warp[0][0]));
     double carry[3];
 #pragma unroll
     for (int c = 0; c < 3; c++) {
         double sum = behind[c];
-        for (int j = kFusedWarps - 1; j > w; j--) sum += F.tagg3[(size_t)c*W + (gw - w + j)];     // the warps of this CTA behind this one
+        for (int j = kFusedWarps - 1; j > w; j--) sum += s_agg[j][c];     // the warps of this CTA behind this one
         carry[c] = sum;
     }
     for (int tile = t1 - 1; tile >= t0; tile--) {

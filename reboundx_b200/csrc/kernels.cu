@@ -1150,9 +1150,9 @@ static int launch_jacobi_fused(const rebx_b200_pass& P, const JacobiCombo* combo
     if (P.reserved & REBX_B200_PASS_TOLERANCE) fn = tol_jacobi_fused_kernel(P);
     if (!fn) fn = reinterpret_cast<const void*>(combo->fused);
     JacobiScratch J(scratch, P.st.n);
-    // resident grid: every CTA must be co-resident (cooperative launch); the per-warp aggregates live in the tile rows of
-    // the staged pipeline's scratch, so not more warps than 256-particle tiles
-    int grid = grid_for(fn, (J.ntiles/kFusedWarps)*kScanThreads, kScanThreads, 0, kScanThreads);
+    // resident grid: every CTA must be co-resident (cooperative launch); the per-CTA aggregates live in the tile rows of
+    // the staged pipeline's scratch, so not more CTAs than 256-particle tiles
+    int grid = grid_for(fn, J.ntiles*kScanThreads, kScanThreads, 0, kScanThreads);
     FusedScratch F;
     F.agg7 = J.rows7; F.tagg3 = J.rows3; F.tvec = J.tvec; F.mref = J.mref;
     double* extra = J.mref + (P.st.n + 2);
