@@ -310,7 +310,7 @@ def roofline_for(workload, math, coordinates, shard, kernel_ms, exec_order):
     hbm = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": None,
            "kernel": kname, "algorithmic_bytes_per_particle": shard.algorithmic_bytes//shard.n, "kernel_ms": kernel_ms,
            "peak_source": peak_src, "math": math}
-    cap = captured().get(f"{workload}/{math}") if not com else None
+    cap = captured().get(f"{workload}/{math}") if not com else (captured().get(f"{workload}_{coordinates}/{math}") if coordinates == "JACOBI" and shard.standalone else None)
     if cap and shard.n - 1 == WORKLOADS[workload][2]:
         hbm["traffic"] = cap.get("dram_bytes")
         hbm["traffic_from"] = cap.get("from")

@@ -17,11 +17,20 @@ def num(s):
 
 
 def main(src_dir, commit):
-    out = {"_what": "ncu --set full --clock-control none captures of the sweep kernels at the bench's sizes (tools/prof_round2.sh); "
+    out = {"_what": "ncu --set full --clock-control none captures of the sweep kernels at the bench's sizes (tools/prof_round2.sh, tools/prof_final.sh); "
                     "fp64_slots_per_particle = sm__pipe_fp64_cycles_active (share of elapsed cycles) x cycles x SMs x 64 lanes / particles"}
-    for math in ("exact", "tolerance"):
-        for wl, n in N.items():
-            path = os.path.join(src_dir, f"r02_{math}_{wl}_raw.csv")
+    dst = os.path.join(ROOT, "profiles", "traffic.json")
+    if os.path.exists(dst):                 # entries whose raw pages are not in src_dir keep their recorded values
+        with open(dst) as f:
+            old = json.load(f)
+        old.update(out)
+        out = old
+    cases = [(wl, n, math, f"r02_{math}_{wl}_raw.csv", f"{wl}/{math}", f"profiles/r02_kernel_{math}_{wl}.txt") for math in ("exact", "tolerance") for wl, n in N.items()]
+    cases += [("planetesimal_disk", 1_000_000, math, f"r02_jacobi_fused_{math}_raw.csv", f"planetesimal_disk_JACOBI/{math}", f"profiles/r02_kernel_jacobi_fused_{math}.txt")
+              for math in ("exact", "tolerance")]
+    for wl, n, math, fname, key, prof in cases:
+        if True:
+            path = os.path.join(src_dir, fname)
             if not os.path.exists(path):
                 continue
             rows = list(csv.reader(open(path)))
@@ -37,10 +46,10 @@ def main(src_dir, commit):
             slots = busy_elapsed*cycles*sms*64/(n + 1)
             t = num(g("gpu__time_duration.sum"))
             t_us = t if u("gpu__time_duration.sum") == "us" else (t*1e3 if u("gpu__time_duration.sum") == "ms" else t/1e3)
-            out[f"{wl}/{math}"] = {"dram_bytes": dram, "fp64_pipe_busy_pct": busy_active, "fp64_slots_per_particle": round(slots, 1),
-                                   "ncu_duration_us": t_us, "kernel": g("Kernel Name"), "registers": int(num(g("launch__registers_per_thread"))),
-                                   "from": f"profiles/r02_kernel_{math}_{wl}.txt, captured at commit {commit}"}
-    with open(os.path.join(ROOT, "profiles", "traffic.json"), "w") as f:
+            out[key] = {"dram_bytes": dram, "fp64_pipe_busy_pct": busy_active, "fp64_slots_per_particle": round(slots, 1),
+                        "ncu_duration_us": t_us, "kernel": g("Kernel Name"), "registers": int(num(g("launch__registers_per_thread"))),
+                        "from": f"{prof}, captured at commit {commit}"}
+    with open(dst, "w") as f:
         json.dump(out, f, indent=1)
     print(json.dumps(out, indent=1))
 
