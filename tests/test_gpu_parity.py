@@ -2,6 +2,8 @@
 would call it (sim->additional_forces on host AoS particles), against the oracle on the same
 seeded inputs.  Oracle = the reference's own sources compiled in place (oracle/_ref) when
 present, else the C restatement (bit-identical to it, tests/test_oracle.py)."""
+import os
+
 import numpy as np
 import pytest
 
@@ -282,6 +284,48 @@ def _com_device(w, add_order, coordinates, acc0):
     got = sim.acc()
     rebx.detach(); sim.free()
     return got
+
+
+_STAGED_SNIPPET = """
+import sys, numpy as np
+sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
+from reboundx_b200 import scenarios, workloads
+w = workloads.planetesimal_disk(50001)
+acc0 = workloads.gravity_like_acc(w, np.random.default_rng(77))
+trio = ["modify_orbits_forces", "gas_damping_timescale", "type_I_migration"]
+sim, rebx, _ = scenarios.build(w, trio, coordinates="JACOBI", acc=acc0)
+sim.additional_forces(); sim.messages()
+np.save({out!r}, np.array(sim.acc()))
+print(rebx.stats()["launches"])
+"""
+
+
+@pytest.mark.parametrize("math", ["exact", "tolerance"])
+def test_jacobi_fused_pipeline_against_the_staged_one(built, tmp_path, math):
+    """rebx_b200_launch_jacobi runs ONE cooperative launch (jacobi_fused.cuh); REBX_B200_JACOBI=staged (read once per
+    process, hence the subprocesses) keeps the six-launch pipeline a sharded caller drives.  Same interior masses, the
+    position / velocity moments summed in another order: the two agree far inside the tolerance, and the launch
+    counters tell which one ran."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = {}
+    for mode in ("fused", "staged"):
+        out = str(tmp_path / f"{mode}.npy")
+        env = dict(os.environ)
+        env.pop("REBX_B200_JACOBI", None)
+        if mode == "staged":
+            env["REBX_B200_JACOBI"] = "staged"
+        if math == "tolerance":
+            env["REBX_B200_MATH"] = "tolerance"
+        run = subprocess.run([sys.executable, "-c", _STAGED_SNIPPET.format(root=root, tests=os.path.join(root, "tests"), out=out)],
+                             stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env, timeout=600)
+        assert run.returncode == 0, run.stderr[-2000:]
+        res[mode] = (np.load(out), int(run.stdout.strip().splitlines()[-1]))
+    assert res["fused"][1] < res["staged"][1], (res["fused"][1], res["staged"][1])      # unpack + 1 + pack against unpack + 6 + pack
+    e = errors(list(res["fused"][0]), list(res["staged"][0]))
+    assert e["max_normwise"] <= 1e-14, e
+    assert not np.array_equal(res["fused"][0], np.zeros_like(res["fused"][0]))
 
 
 @pytest.mark.parametrize("coordinates", ["JACOBI", "BARYCENTRIC"])
