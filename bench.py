@@ -536,6 +536,19 @@ def run_ours(args):
         okm = cx.timed(osh.launch_local, steps)
         other_math = {"math": om, "ms_per_step": oms, "value": n*nf/(oms*1e-3), "unit": "evals/s",
                       "roofline": roofline_for(args.workload, om, args.coordinates, osh, okm, exec_order)}
+        if not args.no_e2e and nf == 1:
+            # resident Wisdom-Holman steps in that build as well (fused kick + Kepler drift sweep)
+            dt_o = 1e-3*2*np.pi*np.sqrt(float(np.hypot(w["x"][1], w["y"][1]))**3/(w["G"]*w["m"][0]))
+            osh.wh_steps(3, dt_o, w["G"], None)
+            o0, o1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            torch.cuda.synchronize()
+            wo = time.time()
+            o0.record()
+            osh.wh_steps(steps, dt_o, w["G"], None)
+            o1.record()
+            torch.cuda.synchronize()
+            clocks.window(wo, time.time())
+            other_math["resident_wh_step_ms"] = o0.elapsed_time(o1)/steps
         del osh
         torch.cuda.empty_cache()
 

@@ -250,7 +250,9 @@ int rebx_b200_kepler_drift(const rebx_b200_state* st, const double* body, double
  * a = effect at the current state, v += dt_kick a, Kepler drift about fx[0].body for dt_drift, in one sweep
  * (104 B/particle for radiation instead of ~390 through zero_acc + launch_pass + kick + kepler_drift; the same
  * arithmetic per particle).  The body record is read, not written (refresh it with rebx_b200_gather_bodies).
- * cudaErrorNotSupported for any other pass: use the separate kernels. */
+ * cudaErrorNotSupported for any other pass: use the separate kernels.  With REBX_B200_PASS_TOLERANCE in pass->reserved
+ * the sweep runs in tolerance arithmetic (kernels_tol.cu: FMA, Newton reciprocals, the force's reciprocal distance reused
+ * by the drift): 0.39 -> 0.23 ms per step of 10^7 grains, trajectories within 1e-10 of the bit-exact sweep after 10^3 steps. */
 int rebx_b200_wh_kick_drift(const rebx_b200_pass* pass, double G, double dt_kick, double dt_drift, void* stream, int* launches);
 /* a = 0 for the shard (the kick of a Wisdom-Holman step sees the additional forces only). */
 int rebx_b200_zero_acc(const rebx_b200_state* st, void* stream, int* launches);

@@ -880,6 +880,7 @@ bool tol_launch(const rebx_b200_pass& sub, int take, double* workspace, cudaStre
 bool tol_jacobi_launch(const rebx_b200_pass& P, unsigned ntiles, const double* tile_prefix, double* tvec, double* tile_tsums, const double* carry7,
                        const void* grid, const double* status, const double* mref, cudaStream_t s);
 const void* tol_jacobi_fused_kernel(const rebx_b200_pass& P);
+bool tol_wh_kick_drift_launch(const rebx_b200_pass& P, double G, double dt_kick, double dt_drift, cudaStream_t s);
 
 static bool use_tma() {
     // opt-in (REBX_B200_KERNEL=tma): measured slower than the occupancy-tuned plain sweep on B200
@@ -1473,7 +1474,10 @@ int rebx_b200_wh_kick_drift(const rebx_b200_pass* pass, double G, double dt_kick
     if (P.n_effects != 1) return cudaErrorNotSupported;
     if (P.st.n == 0) return 0;
     cudaStream_t s = static_cast<cudaStream_t>(stream);
-    if (P.fx[0].kind == REBX_B200_RADIATION) {
+    if ((P.reserved & REBX_B200_PASS_TOLERANCE) && (P.fx[0].kind == REBX_B200_RADIATION || P.fx[0].kind == REBX_B200_YARKOVSKY) &&
+        tol_wh_kick_drift_launch(P, G, dt_kick, dt_drift, s)) {
+        // tolerance arithmetic (kernels_tol.cu): FMA, Newton reciprocals, the force's own reciprocal distance reused by the drift
+    } else if (P.fx[0].kind == REBX_B200_RADIATION) {
         const int grid = grid_for(reinterpret_cast<const void*>(wh_kick_drift_kernel<REBX_B200_RADIATION>), P.st.n);
         wh_kick_drift_kernel<REBX_B200_RADIATION><<<grid, kThreads, 0, s>>>(P, G, dt_kick, dt_drift);
     } else if (P.fx[0].kind == REBX_B200_YARKOVSKY) {

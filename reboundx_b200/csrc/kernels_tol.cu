@@ -929,6 +929,117 @@ jacobi_sweep_tol_kernel(const __grid_constant__ rebx_b200_pass P, const double* 
     }
 }
 
+// ---- fused Wisdom-Holman kick + Kepler drift in tolerance arithmetic ---------------------------------------------------
+// The tolerance counterpart of wh_kick_drift_kernel (kernels_kepler.cuh; the work reference src/steppers.c:79-87 hands to
+// REBOUND's WHFast): a = ONE effect without back-reaction at the current state, v += dt_kick a, Kepler drift about the body
+// for dt_drift.  Same algorithm as kepler_core.h -- universal variables, Newton on r0 G1 + eta G2 + mu G3 = dt, Stumpff
+// functions by quartering + series + duplication -- evaluated with FMA contraction, Newton reciprocals instead of IEEE
+// divisions, and the distance / reciprocal distance the force already has (one reciprocal square root per particle and step).
+__device__ __forceinline__ void stumpff_tol(double z, double& c0, double& c1, double& c2, double& c3) {
+    int n = 0;
+    while (fabs(z) > 0.1) { z *= 0.25; n++; }
+    double C2 = (1. - z*(1. - z*(1. - z*(1. - z*(1. - z*(1. - z*(1./182.))*(1./132.))*(1./90.))*(1./56.))*(1./30.))*(1./12.))*0.5;
+    double C3 = (1. - z*(1. - z*(1. - z*(1. - z*(1. - z*(1. - z*(1./210.))*(1./156.))*(1./110.))*(1./72.))*(1./42.))*(1./20.))*(1./6.);
+    double C1 = 1. - z*C3, C0 = 1. - z*C2;
+    for (; n > 0; n--) {
+        C3 = (C2 + C0*C3)*0.25;
+        C2 = C1*C1*0.5;
+        C1 = C0*C1;
+        C0 = 2.*C0*C0 - 1.;
+    }
+    c0 = C0; c1 = C1; c2 = C2; c3 = C3;
+}
+
+__device__ __forceinline__ void kepler_drift_tol(double mu, double dt, double r0, double inv_r0, double (&x)[3], double (&v)[3]) {
+    const double v2 = v[0]*v[0] + v[1]*v[1] + v[2]*v[2];
+    const double eta = x[0]*v[0] + x[1]*v[1] + x[2]*v[2];
+    const double beta = 2.*mu*inv_r0 - v2;
+    const double X1 = dt*inv_r0;
+    double X = X1*(1. - 0.5*eta*X1*inv_r0), c0 = 1., c1 = 1., c2 = 0.5, c3 = 1./6., G1 = 0., G2 = 0., G3 = 0., rr = r0;
+    double dX = 0.;
+    bool converged = false;
+    for (int it = 0; it < 60; it++) {
+        stumpff_tol(beta*X*X, c0, c1, c2, c3);
+        G1 = c1*X; G2 = c2*X*X; G3 = c3*X*X*X;
+        const double f = r0*G1 + eta*G2 + mu*G3 - dt;
+        rr = r0*c0 + eta*G1 + mu*G2;
+        dX = f*frcp(rr);
+        X -= dX;
+        if (fabs(dX) <= 1e-9*fabs(X)) { converged = true; break; }
+    }
+    if (!converged) {
+        stumpff_tol(beta*X*X, c0, c1, c2, c3);
+        G1 = c1*X; G2 = c2*X*X; G3 = c3*X*X*X;
+    } else {                                   // first order in the last (tiny) correction, as in kepler_core.h
+        const double G0 = c0;
+        G3 = G3 - dX*G2;
+        G2 = G2 - dX*G1;
+        const double G1n = G1 - dX*G0;
+        c0 = G0 + dX*beta*G1;
+        G1 = G1n;
+    }
+    rr = r0*c0 + eta*G1 + mu*G2;
+    const double inv_rr = frcp(rr);
+    const double f = 1. - mu*G2*inv_r0, g = dt - mu*G3;
+    const double fd = -mu*G1*inv_r0*inv_rr, gd = 1. - mu*G2*inv_rr;
+#pragma unroll
+    for (int c = 0; c < 3; c++) {
+        const double xn = f*x[c] + g*v[c], vn = fd*x[c] + gd*v[c];
+        x[c] = xn; v[c] = vn;
+    }
+}
+
+#ifndef REBXB_TOL_WH_BLOCKS
+#define REBXB_TOL_WH_BLOCKS 3
+#endif
+template <int K>
+__global__ void __launch_bounds__(256, K == REBX_B200_RADIATION ? REBXB_TOL_WH_BLOCKS : 1)
+wh_kick_drift_tol_kernel(const __grid_constant__ rebx_b200_pass P, double G, double dt_kick, double dt_drift) {
+    static_assert(!Traits<K>::red, "the fused kick+drift needs an effect without back-reaction");
+    __shared__ double s_c[kC];
+    __shared__ double s_org[8];
+    if (threadIdx.x == 0) fill_constants(P.fx[0], P.fx[0].body, s_c);
+    if (threadIdx.x < 8) s_org[threadIdx.x] = P.fx[0].body[threadIdx.x];
+    __syncthreads();
+    const rebx_b200_state& st = P.st;
+    const long long bi = (long long)s_org[REBX_B200_BODY_INDEX];
+    const double ox = s_org[REBX_B200_BODY_X], oy = s_org[REBX_B200_BODY_X+1], oz = s_org[REBX_B200_BODY_X+2];
+    const double ovx = s_org[REBX_B200_BODY_VX], ovy = s_org[REBX_B200_BODY_VX+1], ovz = s_org[REBX_B200_BODY_VX+2];
+    const double om = s_org[REBX_B200_BODY_M];
+    const double nx = ox + dt_drift*ovx, ny = oy + dt_drift*ovy, nz = oz + dt_drift*ovz;      // the body after its inertial drift
+    double* const X = const_cast<double*>(st.x);  double* const Y = const_cast<double*>(st.y);  double* const Z = const_cast<double*>(st.z);
+    double* const VX = const_cast<double*>(st.vx); double* const VY = const_cast<double*>(st.vy); double* const VZ = const_cast<double*>(st.vz);
+    const int64_t stride = (int64_t)gridDim.x*256;
+    for (int64_t k = (int64_t)blockIdx.x*256 + threadIdx.x; k < st.n; k += stride) {
+        if (st.index_base + k == bi) {          // the body: no force on itself, no back-reaction => inertial
+            X[k] = nx; Y[k] = ny; Z[k] = nz;
+            continue;
+        }
+        const double px = __ldcs(X + k), py = __ldcs(Y + k), pz = __ldcs(Z + k);
+        const double pvx = __ldcs(VX + k), pvy = __ldcs(VY + k), pvz = __ldcs(VZ + k);
+        const double pm = st.m ? __ldcs(st.m + k) : 0.0;
+        double pr = 0.0;
+        if constexpr (Traits<K>::rad) pr = __ldcs(st.r + k);
+        Params<K, 1> q;
+        load_params<K, 1>(P.fx[0], k, true, q);
+        Geo g;
+        g.dx = px - ox; g.dy = py - oy; g.dz = pz - oz;
+        g.r2 = g.dx*g.dx + g.dy*g.dy + g.dz*g.dz;
+        fsqrt2(g.r2, g.r, g.rinv);
+        g.rinv2 = g.rinv*g.rinv;
+        g.dvx = pvx - ovx; g.dvy = pvy - ovy; g.dvz = pvz - ovz;
+        g.rv = g.dx*g.dvx + g.dy*g.dvy + g.dz*g.dvz;
+        Vec3 a = {0.0, 0.0, 0.0}, red = {0.0, 0.0, 0.0};
+        const Elements o = {0., 0., 0., 0., 0.};
+        apply<K, 1>(P.fx[0], s_c, g, o, 0.0, pm, pr, q, 0, a, red);
+        double v[3] = {g.dvx + dt_kick*a.x, g.dvy + dt_kick*a.y, g.dvz + dt_kick*a.z};
+        double x[3] = {g.dx, g.dy, g.dz};
+        kepler_drift_tol(G*(om + pm), dt_drift, g.r, g.rinv, x, v);
+        __stcs(X + k, nx + x[0]); __stcs(Y + k, ny + x[1]); __stcs(Z + k, nz + x[2]);
+        __stcs(VX + k, ovx + v[0]); __stcs(VY + k, ovy + v[1]); __stcs(VZ + k, ovz + v[2]);
+    }
+}
+
 // ---- the whole Jacobi pipeline in one cooperative launch (jacobi_fused.cuh), tolerance arithmetic --------------------
 // The per-particle part of jacobi_sweep_tol_kernel as the Force functor of jacobi_fused_body.
 template <int K0, int K1, int K2>
@@ -1086,6 +1197,22 @@ bool tol_jacobi_launch(const rebx_b200_pass& P, unsigned ntiles, const double* t
         if (!ok) continue;
         const int grid_ctas = grid_for(reinterpret_cast<const void*>(c.fn), (int64_t)ntiles*kScanThreads, kScanThreads, 0, kScanThreads);
         c.fn<<<grid_ctas, kScanThreads, 0, s>>>(P, tile_prefix, tvec, tile_tsums, carry7, static_cast<const MassGrid*>(grid), status, mref, (int)ntiles);
+        return true;
+    }
+    return false;
+}
+
+// The fused Wisdom-Holman kick + Kepler drift in tolerance arithmetic; false when the effect has no instantiation here.
+bool tol_wh_kick_drift_launch(const rebx_b200_pass& P, double G, double dt_kick, double dt_drift, cudaStream_t s) {
+    if (P.n_effects != 1 || (P.fx[0].flags & REBX_B200_FLAG_BARYCENTRIC)) return false;
+    if (P.fx[0].kind == REBX_B200_RADIATION) {
+        const int grid = grid_for(reinterpret_cast<const void*>(tol::wh_kick_drift_tol_kernel<REBX_B200_RADIATION>), P.st.n, 256, 0, 256);
+        tol::wh_kick_drift_tol_kernel<REBX_B200_RADIATION><<<grid, 256, 0, s>>>(P, G, dt_kick, dt_drift);
+        return true;
+    }
+    if (P.fx[0].kind == REBX_B200_YARKOVSKY) {
+        const int grid = grid_for(reinterpret_cast<const void*>(tol::wh_kick_drift_tol_kernel<REBX_B200_YARKOVSKY>), P.st.n, 256, 0, 256);
+        tol::wh_kick_drift_tol_kernel<REBX_B200_YARKOVSKY><<<grid, 256, 0, s>>>(P, G, dt_kick, dt_drift);
         return true;
     }
     return false;

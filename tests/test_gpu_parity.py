@@ -1010,6 +1010,34 @@ def test_fused_wisdom_holman_sweep_with_yarkovsky(built):
         _assert_trajectories_agree(out[0], ref)
 
 
+@pytest.mark.parametrize("which", ["debris_disk", "asteroid_ensemble"])
+def test_tolerance_mode_fused_wisdom_holman_sweep(built, which):
+    """device.Shard(math="tolerance").wh_steps: the fused kick + Kepler drift sweep in tolerance arithmetic
+    (wh_kick_drift_tol_kernel: FMA, Newton reciprocals, the force's reciprocal distance reused by the drift) follows the
+    bit-exact sweep -- which IS the host harness + reference force for radiation -- to criterion (ii) after 10^3 steps,
+    and really is another kernel (results differ in the last bits)."""
+    import torch
+    from oracle import oracle
+    from reboundx_b200 import device, workloads
+    if which == "debris_disk":
+        w, add, dt, steps = workloads.debris_disk(20000, seed=3), ["radiation_forces"], 1e8, 1000
+    else:
+        w, add, dt, steps = workloads.asteroid_ensemble(3000), ["yarkovsky_effect"], 0.01, 300
+    out = {}
+    for math in ("exact", "tolerance"):
+        sh = device.Shard(w, add, "cuda:0", math=math)
+        sh.wh_steps(steps, dt, w["G"])
+        torch.cuda.synchronize()
+        out[math] = np.array(sh.posvel())
+        del sh
+    assert np.isfinite(out["tolerance"]).all()
+    assert not np.array_equal(out["tolerance"], out["exact"]), "math='tolerance' did not select the tolerance sweep"
+    _assert_trajectories_agree(out["tolerance"], out["exact"])
+    if oracle.have_ref():
+        ref = _trajectory(w, oracle.ref_lib(), steps, "wisdom_holman_merged", dt, 1, add)
+        _assert_trajectories_agree(out["tolerance"], ref)
+
+
 def test_full_size_resident_wisdom_holman_against_the_host_harness_on_a_subsample(built):
     """BASELINE config 2 at its full size, "radiation_forces under WHFast": 50 resident Wisdom-Holman steps of 10^7
     grains (fused kick + Kepler drift sweeps), and -- test particles being independent -- the host harness stepping
