@@ -23,6 +23,7 @@ Further keys:
                   PARTICLE and JACOBI coordinates -- each with ms_per_step, roofline (bit-exact and tolerance-mode
                   arithmetic) and e2e
   resident_step / resident_wh_step   whole integrator steps with the state kept in HBM
+  resident_session_wh_step           (N = 1) the same Wisdom-Holman steps driven through the C session API (no torch, no Python per step)
 """
 import argparse
 import json
@@ -326,7 +327,46 @@ def roofline_for(workload, math, coordinates, shard, kernel_ms, exec_order):
     return hbm
 
 
-def e2e_leg(cx, w, add_order, coordinates, steps, nf, n, n_active=None):
+def session_leg(cx, sim, rebx, w, steps, nf, n):
+    """Resident stepping driven through the C session API (include/rebx_b200.h: rebx_b200_session_*; no torch, no Python
+    between the steps): sim->particles uploaded once, `steps` Wisdom-Holman steps in ONE C call, timed on the host around
+    that call + a device synchronisation."""
+    import ctypes
+    from reboundx_b200 import _lib
+    lib = _lib.load()
+    lib.rebx_b200_session_create.restype = ctypes.c_void_p
+    lib.rebx_b200_session_create.argtypes = [ctypes.c_void_p, ctypes.c_void_p]
+    lib.rebx_b200_session_step_wh.restype = ctypes.c_int
+    lib.rebx_b200_session_step_wh.argtypes = [ctypes.c_void_p, ctypes.c_int, ctypes.c_double]
+    lib.rebx_b200_session_launches.restype = ctypes.c_uint64
+    lib.rebx_b200_session_launches.argtypes = [ctypes.c_void_p]
+    lib.rebx_b200_session_free.argtypes = [ctypes.c_void_p]
+    s = lib.rebx_b200_session_create(ctypes.cast(sim.ptr, ctypes.c_void_p), ctypes.cast(rebx._ptr, ctypes.c_void_p))
+    if not s:
+        return None
+    dt = 1e-3*2*np.pi*np.sqrt(float(np.hypot(w["x"][1], w["y"][1]))**3/(w["G"]*w["m"][0]))
+    try:
+        if lib.rebx_b200_session_step_wh(s, 3, dt) != 0:
+            return None
+        cx.torch.cuda.synchronize()
+        l0 = lib.rebx_b200_session_launches(s)
+        w0 = time.time()
+        t0 = time.perf_counter()
+        rc = lib.rebx_b200_session_step_wh(s, steps, dt)
+        cx.torch.cuda.synchronize()
+        ms = (time.perf_counter() - t0)*1e3/steps
+        cx.clocks.window(w0, time.time())
+        if rc != 0:
+            return None
+        return {"value": n*nf/(ms*1e-3), "unit": "evals/s", "ms_per_step": ms, "steps": steps,
+                "launches_per_step": (lib.rebx_b200_session_launches(s) - l0)/steps,
+                "what": "resident Wisdom-Holman steps driven from C: rebx_b200_session_create(sim, rebx) uploads sim->particles once, "
+                        "rebx_b200_session_step_wh(session, steps, dt) issues every step (host timer around the one C call + device synchronisation)"}
+    finally:
+        lib.rebx_b200_session_free(s)
+
+
+def e2e_leg(cx, w, add_order, coordinates, steps, nf, n, n_active=None, session_steps=0):
     """The REBOUND-facing call on host particle arrays, copies inside the timed region."""
     from reboundx_b200 import scenarios
     sim, rebx, _ = scenarios.build(w, add_order, coordinates=coordinates)
@@ -357,6 +397,8 @@ def e2e_leg(cx, w, add_order, coordinates, steps, nf, n, n_active=None):
            "first_call_ms": first_ms,
            "first_call_note": "outside the timed region (two warm-up calls): the first call pins the caller's particle array with cudaHostRegister (~1.1 s for 1.28 GB) and builds + uploads the parameter tables",
            "call": "sim->additional_forces(sim) == rebx_additional_forces, host AoS particles (cudaHostRegister-pinned)"}
+    if session_steps > 0:
+        out["_session"] = session_leg(cx, sim, rebx, w, session_steps, nf, n)
     rebx.detach()
     sim.free()
     return out
@@ -615,9 +657,11 @@ def run_ours(args):
                 strong["efficiency_vs_1gpu"] = t1/(world*strong["ms_per_step"])
 
     # ---- end-to-end leg: the REBOUND-facing call on host particle arrays ---------------------------
-    e2e = None
+    e2e = resident_session = None
     if not args.no_e2e:
-        e2e = e2e_leg(cx, w, add_order, args.coordinates, args.e2e_steps or min(steps, 10), nf, n)
+        e2e = e2e_leg(cx, w, add_order, args.coordinates, args.e2e_steps or min(steps, 10), nf, n,
+                      session_steps=(steps if world == 1 and not com and nf == 1 else 0))
+        resident_session = e2e.pop("_session", None)
         if numa:
             e2e["numa"] = numa
 
@@ -665,7 +709,7 @@ def run_ours(args):
                            "sharding": ("index ranges; the central body's record is replicated and re-broadcast (NCCL) only when its owner changed it" if not com else
                                         "index ranges; per step an all-gather of 7 mass moments and of 3 back-reaction sums per rank (JACOBI: exclusive prefix / suffix over ranks; BARYCENTRIC: all-reduce)")},
                 "roofline": roofline, "other_math": other_math, "cpu_baseline": cpu, "e2e": e2e, "e2e_one_simulation_all_gpus": e2e_one, "strong": strong, "sharded_parity": parity,
-                "workloads": extras, "resident_step": resident, "resident_wh_step": resident_wh, "gpu_launches": gpu_launches,
+                "workloads": extras, "resident_step": resident, "resident_wh_step": resident_wh, "resident_session_wh_step": resident_session, "gpu_launches": gpu_launches,
                 "clocks": clocks.summary()}
         sys.stdout.flush()
         os.write(json_fd, (json.dumps(line) + "\n").encode())
