@@ -208,6 +208,10 @@ typedef struct rebx_b200_gr_args {
     double G, C2, mu;
     double com[9];
     const double* active;
+    const double* pull1;        /* n_active == 1 only, may be NULL: DEVICE pointer to the pull on the one active body (what
+                                 * rebx_b200_gr_pull wrote); the sweep then takes the Jacobi origin's acceleration com[6..8] from
+                                 * it -- (m_0 * (0 - pull_c)) * (1/m_0), the host part's operations -- and the caller needs no
+                                 * device-to-host round trip between the reduction and the sweep */
 } rebx_b200_gr_args;
 /* pull[i*3+c] (device) = sum over the shard's test particles j of G m_j (x_i - x_j)_c / r^3. */
 int rebx_b200_gr_pull(const rebx_b200_state* st, const rebx_b200_gr_args* args, double* pull, void* workspace, void* stream, int* launches);

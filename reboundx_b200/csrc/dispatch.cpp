@@ -844,10 +844,20 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
                 ga.active = act_d;
                 REBXB_CUDA(cudaMemsetAsync(flag_d, 0, sizeof(int), s), "clearing the convergence flag");
                 REBXB_CUDA((cudaError_t)rebx_b200_gr_pull(&st, &ga, pull_d, D.work[b].p, s, &launches), "reducing the test particles' pull");
-                REBXB_CUDA(cudaMemcpyAsync(pull_h, pull_d, (size_t)en.n_active*3*sizeof(double), cudaMemcpyDeviceToHost, s), "copying the pull");
-                REBXB_CUDA(cudaStreamSynchronize(s), "waiting for the device");
                 bool host_nc = false;
-                gr_host_actives(particles, en.n_active, sim->G, ga.C2, ga.max_iterations, pull_h, ga, en.gr_active, host_nc);
+                if (en.n_active == 1) {
+                    // ONE active body (a star and its test particles, the common case): the host part needs nothing from the
+                    // device -- the body's own 1PN acceleration is zero, the Jacobi origin is the body, and its acceleration
+                    // (minus the test particles' pull) is taken from the device-resident reduction by the sweep itself.  No
+                    // round trip, no synchronisation inside the pipeline.
+                    pull_h[0] = pull_h[1] = pull_h[2] = 0.0;
+                    gr_host_actives(particles, 1, sim->G, ga.C2, ga.max_iterations, pull_h, ga, en.gr_active, host_nc);
+                    ga.pull1 = pull_d;
+                } else {
+                    REBXB_CUDA(cudaMemcpyAsync(pull_h, pull_d, (size_t)en.n_active*3*sizeof(double), cudaMemcpyDeviceToHost, s), "copying the pull");
+                    REBXB_CUDA(cudaStreamSynchronize(s), "waiting for the device");
+                    gr_host_actives(particles, en.n_active, sim->G, ga.C2, ga.max_iterations, pull_h, ga, en.gr_active, host_nc);
+                }
                 REBXB_CUDA((cudaError_t)rebx_b200_gr_sweep(&st, &ga, flag_d, s, &launches), "launching the gr sweep");
                 REBXB_CUDA(cudaMemcpyAsync(pull_h + 3*Aq, flag_d, sizeof(int), cudaMemcpyDeviceToHost, s), "copying the convergence flag");
                 *reinterpret_cast<int*>(pull_h + 3*Aq + 4) = host_nc ? 1 : 0;

@@ -88,6 +88,13 @@ gr_sweep_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_gr_args A,
     constexpr int kTileActives = 256;
     __shared__ double s_act[kTileActives][4];
     const double C2 = A.C2, mu = A.mu;
+    // acceleration of the Jacobi origin: from the host part, or -- one active body -- from the device-resident pull with the
+    // host part's own operations (act.a = 0 - pull; s_a = m_0 act.a; com.a = s_a (1/m_0): rebound_shim.c shim_to_jacobi)
+    double ca0 = A.com[6], ca1 = A.com[7], ca2 = A.com[8];
+    if (A.pull1 != nullptr) {
+        const double m0 = A.active[3], mi = 1./m0;
+        ca0 = (m0*(0. - A.pull1[0]))*mi; ca1 = (m0*(0. - A.pull1[1]))*mi; ca2 = (m0*(0. - A.pull1[2]))*mi;
+    }
     const int64_t stride = (int64_t)gridDim.x*kThreads;
     // every thread of the CTA runs the same number of rounds (the tile loads below are CTA-wide barriers)
     const int64_t rounds = (st.n + stride - 1)/stride;
@@ -116,7 +123,7 @@ gr_sweep_kernel(rebx_b200_state st, const __grid_constant__ rebx_b200_gr_args A,
         // Jacobi coordinates of a test particle: relative to the centre of mass of the actives
         const double px = x - A.com[0], py = y - A.com[1], pz = z - A.com[2];
         const double pvx = st.vx[k] - A.com[3], pvy = st.vy[k] - A.com[4], pvz = st.vz[k] - A.com[5];
-        const double pax = nx - A.com[6], pay = ny - A.com[7], paz = nz - A.com[8];
+        const double pax = nx - ca0, pay = ny - ca1, paz = nz - ca2;
         // fixed point for the Jacobi velocity (gr.c:105-129)
         double vix = pvx, viy = pvy, viz = pvz;
         double vi2 = vix*vix + viy*viy + viz*viz;
