@@ -286,6 +286,23 @@ def _com_device(w, add_order, coordinates, acc0):
     return got
 
 
+@pytest.mark.parametrize("math", ["exact", "tolerance"])
+def test_jacobi_frame_ragged_sizes(built, monkeypatch, math):
+    """The fused Jacobi pipeline on ensembles around its granularities (32-particle warp tiles, 256-particle CTA rows, more
+    warps than tiles, a single planetesimal): against the reference's own loops, norm-wise at the north-star tolerance."""
+    from reboundx_b200 import workloads
+    if math == "tolerance":
+        monkeypatch.setenv("REBX_B200_MATH", "tolerance")
+    for n in (1, 2, 31, 32, 33, 63, 255, 256, 257, 1023, 2049):
+        w = workloads.planetesimal_disk(n)
+        acc0 = acc_variants(w, 50 + n)["gravity"]
+        want, _ = oracle_acc(w, TRIO, acc0, "JACOBI")
+        got = _com_device(w, TRIO, "JACOBI", acc0)
+        e = errors(got, want)
+        assert all(np.isfinite(a).all() for a in got), n
+        assert e["max_normwise"] <= TOL, (n, e)
+
+
 _STAGED_SNIPPET = """
 import sys, numpy as np
 sys.path.insert(0, {root!r}); sys.path.insert(0, {tests!r})
