@@ -438,6 +438,39 @@ def extra_workload(cx, name, coordinates, steps):
     return out
 
 
+def graph_timed(cx, shard, steps, barrier=True):
+    """`steps` sweeps of `shard` captured once in a CUDA graph and replayed: the launch gaps of a Python / ctypes issue
+    loop (3-4 us per launch, a fifth of a 22 us sweep) are taken out, what remains is the device's own time.  Only for
+    stacks without back-reaction (no collective between the sweeps).  ms per sweep, max over ranks."""
+    torch = cx.torch
+    shard.launch()
+    torch.cuda.synchronize()
+    graph = torch.cuda.CUDAGraph()
+    side = torch.cuda.Stream(shard.device)
+    side.wait_stream(torch.cuda.current_stream(shard.device))
+    with torch.cuda.graph(graph, stream=side):
+        for _ in range(steps):
+            shard.launch()
+    for _ in range(3):
+        graph.replay()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    if barrier:
+        cx.barrier()
+    else:
+        torch.cuda.synchronize()
+    w0 = time.time()
+    e0.record()
+    graph.replay()
+    e1.record()
+    if barrier:
+        cx.barrier()
+    else:
+        torch.cuda.synchronize()
+    cx.clocks.window(w0, time.time())
+    ms = e0.elapsed_time(e1)/steps
+    return cx.max_over_ranks(ms) if barrier else ms
+
+
 def strong_leg(cx, w_rank0, builder, add_order, n_total, steps):
     """Strong scaling: ONE ensemble of n_total test particles (the headline 10^7) split by index range over the ranks,
     every rank holding the replicated central body.  The 1-GPU time of the same ensemble is measured in the same run on
@@ -457,6 +490,8 @@ def strong_leg(cx, w_rank0, builder, add_order, n_total, steps):
     out = {"particles_total": n_total, "particles_per_gpu": hi - lo, "ms_per_step": ms, "value": n_total*nf/(ms*1e-3), "unit": "evals/s",
            "what": "the headline ensemble split by index range over the ranks; per evaluation each rank launches one sweep over its range, "
                    "the body record is re-broadcast only when its owner changed it (never in a force-evaluation loop), back-reaction sums are all-reduced"}
+    if all(k in (1, 4) for k in shard.kinds):
+        out["graph_ms_per_step"] = graph_timed(cx, shard, max(steps, 50))
     del shard
     torch.cuda.empty_cache()
     return out
@@ -649,12 +684,18 @@ def run_ours(args):
                 a1.record()
                 torch.cuda.synchronize()
                 t1 = a0.elapsed_time(a1)/steps
+                t1g = graph_timed(cx, one, max(steps, 50), barrier=False) if "graph_ms_per_step" in strong else None
                 del one
                 torch.cuda.empty_cache()
             cx.barrier()
             if rank == 0:
                 strong["ms_per_step_1gpu_same_run"] = t1
                 strong["efficiency_vs_1gpu"] = t1/(world*strong["ms_per_step"])
+                if t1g is not None:
+                    g = strong.pop("graph_ms_per_step")
+                    strong["cuda_graph"] = {"ms_per_step": g, "value": n_total*nf/(g*1e-3), "ms_per_step_1gpu_same_run": t1g,
+                                            "efficiency_vs_1gpu": t1g/(world*g),
+                                            "what": "the same sweeps captured once in a CUDA graph and replayed (no Python / launch gaps between them), both the sharded and the 1-GPU run"}
 
     # ---- end-to-end leg: the REBOUND-facing call on host particle arrays ---------------------------
     e2e = resident_session = None
