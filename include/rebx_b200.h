@@ -178,7 +178,9 @@ int rebx_b200_mass_moments(const rebx_b200_state* st, double* totals8, void* scr
 int rebx_b200_com_bodies(const double* totals7, double* bodies, int nbodies, void* stream, int* launches);
 /* REBX_COORDINATES_JACOBI for 1..3 stacked damping effects (kinds 5,6,7) over the WHOLE ensemble
  * (index_base must be 0): prefix scan of the mass moments, sweep, suffix scan of the
- * back-reaction, all on the device in O(n).  fx[].body and fx[].backreaction are ignored. */
+ * back-reaction, all on the device in O(n).  fx[].body and fx[].backreaction are ignored.
+ * ONE cooperative launch (reboundx_b200/csrc/jacobi_fused.cuh: a resident grid, contiguous tile ranges per warp, two
+ * grid-wide barriers) where the device supports it, else -- or with REBX_B200_JACOBI=staged -- the three stages below. */
 int rebx_b200_launch_jacobi(const rebx_b200_pass* pass, void* scratch, void* stream, int* launches);
 /* The same pipeline in three stages, for an ensemble SHARDED by index range:
  * the shards exchange 7 + 3 doubles between the stages, everything else stays local.
@@ -333,6 +335,7 @@ void rebx_b200_session_free(rebx_b200_session* s);
  *                                        same way; back-reaction sums added on the host in index order
  *   REBX_B200_MULTI_MIN=<particles>      smallest ensemble worth splitting (default 2^20)
  *   REBX_B200_MATH=tolerance             REBX_B200_PASS_TOLERANCE for every pass
+ *   REBX_B200_JACOBI=staged              rebx_b200_launch_jacobi keeps the staged pipeline (default: one cooperative launch)
  *   REBX_B200_CHUNK, REBX_B200_ZEROCOPY_MAX, REBX_B200_PARANOID   pipeline chunk, zero-copy threshold, rebuild tables every call */
 struct rebx_extras;
 struct rebx_force;
