@@ -626,6 +626,7 @@ def run_ours(args):
             torch.cuda.synchronize()
             clocks.window(wo, time.time())
             other_math["resident_wh_step_ms"] = o0.elapsed_time(o1)/steps
+            other_math["resident_step_ms"] = cx.timed(lambda: osh.fused_leapfrog_step(dt_o, w["G"]), steps)
         del osh
         torch.cuda.empty_cache()
 

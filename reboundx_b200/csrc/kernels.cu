@@ -881,6 +881,7 @@ bool tol_jacobi_launch(const rebx_b200_pass& P, unsigned ntiles, const double* t
                        const void* grid, const double* status, const double* mref, cudaStream_t s);
 const void* tol_jacobi_fused_kernel(const rebx_b200_pass& P);
 bool tol_wh_kick_drift_launch(const rebx_b200_pass& P, double G, double dt_kick, double dt_drift, cudaStream_t s);
+bool tol_leapfrog_sweep_launch(const rebx_b200_pass& P, double dt, double G, double soft2, cudaStream_t s);
 
 static bool use_tma() {
     // opt-in (REBX_B200_KERNEL=tma): measured slower than the occupancy-tuned plain sweep on B200
@@ -1283,6 +1284,12 @@ int rebx_b200_leapfrog_sweep(const rebx_b200_pass* pass, double dt, double G, do
         for (int j = 0; j < P.n_effects; j++)
             if (((red_mask >> j) & 1u) && P.fx[j].backreaction) cudaMemsetAsync(P.fx[j].backreaction, 0, 3*sizeof(double), s);
         return cudaGetLastError();
+    }
+    if ((P.reserved & REBX_B200_PASS_TOLERANCE) && red_mask == 0 && tol_leapfrog_sweep_launch(P, dt, G, softening*softening, s)) {
+        // tolerance arithmetic (kernels_tol.cu: step_tol_kernel), one effect without back-reaction
+        cudaError_t terr = cudaGetLastError();
+        if (terr == cudaSuccess && launches) *launches += 1;
+        return terr;
     }
     bool heavy = false;
     for (int j = 0; j < P.n_effects; j++) if (P.fx[j].kind >= REBX_B200_YARKOVSKY) heavy = true;

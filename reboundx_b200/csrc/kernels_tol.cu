@@ -1040,6 +1040,63 @@ wh_kick_drift_tol_kernel(const __grid_constant__ rebx_b200_pass P, double G, dou
     }
 }
 
+// ---- fused drift-kick-drift step in tolerance arithmetic -----------------------------------------------------------------
+// The tolerance counterpart of step_kernel (kernels.cu) for ONE effect without back-reaction (radiation_forces,
+// yarkovsky_effect): x += dt/2 v; a = pull of the central body + the effect; v += dt a; x += dt/2 v -- one sweep, the
+// acceleration lives in registers.  One reciprocal square root per particle serves the central gravity and the effect.
+// The central body itself is skipped here and advanced by step_body_kernel, exactly as in the bit-exact path.
+template <int K>
+__global__ void __launch_bounds__(256, K == REBX_B200_RADIATION ? 3 : 1)
+step_tol_kernel(const __grid_constant__ rebx_b200_pass P, double dt, double hdt, double G, double soft2) {
+    static_assert(!Traits<K>::red, "the tolerance step needs an effect without back-reaction");
+    __shared__ double s_c[kC];
+    __shared__ double s_org[8];
+    if (threadIdx.x < 8) s_org[threadIdx.x] = P.fx[0].body[threadIdx.x];
+    __syncthreads();
+    if (threadIdx.x < 3) s_org[REBX_B200_BODY_X + threadIdx.x] += hdt*s_org[REBX_B200_BODY_VX + threadIdx.x];     // the body's own first half drift
+    __syncthreads();
+    if (threadIdx.x == 0) fill_constants(P.fx[0], s_org, s_c);
+    __syncthreads();
+    const rebx_b200_state& st = P.st;
+    const long long bi = (long long)s_org[REBX_B200_BODY_INDEX];
+    const double ox = s_org[REBX_B200_BODY_X], oy = s_org[REBX_B200_BODY_X+1], oz = s_org[REBX_B200_BODY_X+2];
+    const double ovx = s_org[REBX_B200_BODY_VX], ovy = s_org[REBX_B200_BODY_VX+1], ovz = s_org[REBX_B200_BODY_VX+2];
+    const double GM = G*s_org[REBX_B200_BODY_M];
+    double* const X = const_cast<double*>(st.x);  double* const Y = const_cast<double*>(st.y);  double* const Z = const_cast<double*>(st.z);
+    double* const VX = const_cast<double*>(st.vx); double* const VY = const_cast<double*>(st.vy); double* const VZ = const_cast<double*>(st.vz);
+    const int64_t stride = (int64_t)gridDim.x*256;
+    for (int64_t k = (int64_t)blockIdx.x*256 + threadIdx.x; k < st.n; k += stride) {
+        if (st.index_base + k == bi) continue;                       // the central body: step_body_kernel
+        const double pvx = __ldcs(VX + k), pvy = __ldcs(VY + k), pvz = __ldcs(VZ + k);
+        const double px = __ldcs(X + k) + hdt*pvx, py = __ldcs(Y + k) + hdt*pvy, pz = __ldcs(Z + k) + hdt*pvz;
+        const double pm = st.m ? __ldcs(st.m + k) : 0.0;
+        double pr = 0.0;
+        if constexpr (Traits<K>::rad) pr = __ldcs(st.r + k);
+        Params<K, 1> q;
+        load_params<K, 1>(P.fx[0], k, true, q);
+        Geo g;
+        g.dx = px - ox; g.dy = py - oy; g.dz = pz - oz;
+        g.r2 = g.dx*g.dx + g.dy*g.dy + g.dz*g.dz;
+        fsqrt2(g.r2, g.r, g.rinv);
+        g.rinv2 = g.rinv*g.rinv;
+        g.dvx = pvx - ovx; g.dvy = pvy - ovy; g.dvz = pvz - ovz;
+        g.rv = g.dx*g.dvx + g.dy*g.dvy + g.dz*g.dvz;
+        Vec3 a = {0.0, 0.0, 0.0}, red = {0.0, 0.0, 0.0};
+        if (GM != 0.0) {                                             // central gravity
+            double ri3;
+            if (soft2 == 0.0) ri3 = g.rinv2*g.rinv;
+            else { const double rs = frsqrt(g.r2 + soft2); ri3 = rs*rs*rs; }
+            const double pref = -GM*ri3;
+            a.x = pref*g.dx; a.y = pref*g.dy; a.z = pref*g.dz;
+        }
+        const Elements o = {0., 0., 0., 0., 0.};
+        apply<K, 1>(P.fx[0], s_c, g, o, 0.0, pm, pr, q, 0, a, red);
+        const double nvx = pvx + dt*a.x, nvy = pvy + dt*a.y, nvz = pvz + dt*a.z;
+        __stcs(VX + k, nvx); __stcs(VY + k, nvy); __stcs(VZ + k, nvz);
+        __stcs(X + k, px + hdt*nvx); __stcs(Y + k, py + hdt*nvy); __stcs(Z + k, pz + hdt*nvz);
+    }
+}
+
 // ---- the whole Jacobi pipeline in one cooperative launch (jacobi_fused.cuh), tolerance arithmetic --------------------
 // The per-particle part of jacobi_sweep_tol_kernel as the Force functor of jacobi_fused_body.
 template <int K0, int K1, int K2>
@@ -1213,6 +1270,23 @@ bool tol_wh_kick_drift_launch(const rebx_b200_pass& P, double G, double dt_kick,
     if (P.fx[0].kind == REBX_B200_YARKOVSKY) {
         const int grid = grid_for(reinterpret_cast<const void*>(tol::wh_kick_drift_tol_kernel<REBX_B200_YARKOVSKY>), P.st.n, 256, 0, 256);
         tol::wh_kick_drift_tol_kernel<REBX_B200_YARKOVSKY><<<grid, 256, 0, s>>>(P, G, dt_kick, dt_drift);
+        return true;
+    }
+    return false;
+}
+
+// The fused drift-kick-drift sweep in tolerance arithmetic (the particles only; the body follows in step_body_kernel);
+// false when the stack has no instantiation here (anything but one effect without back-reaction).
+bool tol_leapfrog_sweep_launch(const rebx_b200_pass& P, double dt, double G, double soft2, cudaStream_t s) {
+    if (P.n_effects != 1 || (P.fx[0].flags & REBX_B200_FLAG_BARYCENTRIC)) return false;
+    if (P.fx[0].kind == REBX_B200_RADIATION) {
+        const int grid = grid_for(reinterpret_cast<const void*>(tol::step_tol_kernel<REBX_B200_RADIATION>), P.st.n, 256, 0, 256);
+        tol::step_tol_kernel<REBX_B200_RADIATION><<<grid, 256, 0, s>>>(P, dt, 0.5*dt, G, soft2);
+        return true;
+    }
+    if (P.fx[0].kind == REBX_B200_YARKOVSKY) {
+        const int grid = grid_for(reinterpret_cast<const void*>(tol::step_tol_kernel<REBX_B200_YARKOVSKY>), P.st.n, 256, 0, 256);
+        tol::step_tol_kernel<REBX_B200_YARKOVSKY><<<grid, 256, 0, s>>>(P, dt, 0.5*dt, G, soft2);
         return true;
     }
     return false;

@@ -1055,6 +1055,31 @@ def test_tolerance_mode_fused_wisdom_holman_sweep(built, which):
         _assert_trajectories_agree(out["tolerance"], ref)
 
 
+@pytest.mark.parametrize("which", ["debris_disk", "asteroid_ensemble"])
+def test_tolerance_mode_fused_leapfrog_step(built, which):
+    """device.Shard(math="tolerance").fused_leapfrog_step: the drift-kick-drift step in one sweep in tolerance arithmetic
+    (step_tol_kernel; one effect without back-reaction) follows the bit-exact fused step to criterion (ii) after 10^3
+    steps, the central body included, and really is another kernel."""
+    import torch
+    from reboundx_b200 import device, workloads
+    if which == "debris_disk":
+        w, add, dt, steps = workloads.debris_disk(20000, seed=3), ["radiation_forces"], 1e8, 1000
+    else:
+        w, add, dt, steps = workloads.asteroid_ensemble(3000), ["yarkovsky_effect"], 0.01, 300
+    out = {}
+    for math in ("exact", "tolerance"):
+        sh = device.Shard(w, add, "cuda:0", math=math)
+        for _ in range(steps):
+            sh.fused_leapfrog_step(dt, w["G"])
+        torch.cuda.synchronize()
+        out[math] = np.array(sh.posvel())
+        del sh
+    assert np.isfinite(out["tolerance"]).all()
+    assert not np.array_equal(out["tolerance"], out["exact"]), "math='tolerance' did not select the tolerance step"
+    assert np.array_equal(out["tolerance"][:, 0], out["exact"][:, 0])       # the central body: same step_body arithmetic
+    _assert_trajectories_agree(out["tolerance"], out["exact"])
+
+
 def test_full_size_resident_wisdom_holman_against_the_host_harness_on_a_subsample(built):
     """BASELINE config 2 at its full size, "radiation_forces under WHFast": 50 resident Wisdom-Holman steps of 10^7
     grains (fused kick + Kepler drift sweeps), and -- test particles being independent -- the host harness stepping
