@@ -283,3 +283,24 @@ def test_rad_calc_beta_published_value(built):
     lib.rebx_rad_calc_particle_radius.restype = ctypes.c_double
     lib.rebx_rad_calc_particle_radius.argtypes = [ctypes.c_double]*7
     assert abs(lib.rebx_rad_calc_particle_radius(6.674e-11, 3.e8, 1.99e30, 3.85e26, beta, 1000., 1.)/1.e-5 - 1.0) < 1e-15
+
+
+def test_scan_scratch_holds_the_staged_and_the_fused_jacobi_layouts(built):
+    """rebx_b200_scan_scratch_bytes (a pure host function): the buffer must hold the staged pipeline's rows, totals, t
+    vector and literal masses AND the fused pipeline's per-CTA flags (one 8-byte and one 4-byte entry per CTA, at most one
+    CTA per 256-particle tile) -- kernels.cu: JacobiScratch / launch_jacobi_fused."""
+    import ctypes
+    from reboundx_b200 import _lib
+    lib = _lib.load()
+    lib.rebx_b200_scan_scratch_bytes.restype = ctypes.c_size_t
+    lib.rebx_b200_scan_scratch_bytes.argtypes = [ctypes.c_int64]
+    last = 0
+    for n in (1, 2, 255, 256, 257, 3001, 20001, 1_000_001, 10_000_001):
+        ntiles = (n + 255)//256
+        got = lib.rebx_b200_scan_scratch_bytes(n)
+        staged = ((ntiles + 1)*10 + 32 + 4*(n + 2))*8
+        fused_flags = (ntiles + 1)*8 + ntiles*4
+        assert got >= staged + fused_flags, (n, got, staged, fused_flags)
+        assert got % 8 == 0 and got > last
+        last = got
+
