@@ -311,6 +311,9 @@ def roofline_for(workload, math, coordinates, shard, kernel_ms, exec_order):
     hbm = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved/peak, "traffic": None,
            "kernel": kname, "algorithmic_bytes_per_particle": shard.algorithmic_bytes//shard.n, "kernel_ms": kernel_ms,
            "peak_source": peak_src, "math": math}
+    if hbm["frac"] > 1.0:
+        hbm["note"] = ("above 1: the denominator is the measured COPY bandwidth (half reads, half writes); this sweep reads more than it writes "
+                       "(radiation_forces: 10 of its 13 doubles per particle are reads) and HBM3e streams reads faster than a copy")
     cap = captured().get(f"{workload}/{math}") if not com else (captured().get(f"{workload}_{coordinates}/{math}") if coordinates == "JACOBI" and shard.standalone else None)
     if cap and shard.n - 1 == WORKLOADS[workload][2]:
         hbm["traffic"] = cap.get("dram_bytes")
