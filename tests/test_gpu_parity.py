@@ -661,6 +661,31 @@ def test_yarkovsky_notebook_known_answer_on_the_gpu(built, full):
         assert np.all(np.abs(da/da_ref - 1.0) < 1e-6), (da, da_ref)
 
 
+def test_damping_notebook_laws_with_this_library(built):
+    """The analytic laws the reference publishes for its damping forces (tests/damping_notebooks.py; the CPU suite pins
+    the oracle to them over the full spans) with the CUDA force through the drop-in call: the first sample of each law,
+    against the law itself and against the oracle's trajectory (criterion (ii))."""
+    from oracle import oracle
+    from reboundx_b200 import _lib
+    import damping_notebooks as nb
+    lib = _lib.load()
+    ref = oracle.ref_lib() if oracle.have_ref() else None
+    _, a, pred = nb.migration(lib, stop_after=1)
+    assert abs(a[0][0]/pred[0][0] - 1.0) < 5e-4 and abs(a[1][0]/pred[1][0] - 1.0) < 1e-2, (a, pred)
+    if ref is not None:
+        _, ar, _ = nb.migration(ref, stop_after=1)
+        assert np.max(np.abs(a/ar - 1.0)) < 1e-10, a/ar - 1.0
+    _, a, pred = nb.inner_disk_edge(lib, stop_after=1)
+    assert abs(a[0]/pred[0] - 1.0) < 1e-6, (a, pred)
+    _, a, pred, edge, width = nb.type_I(lib, stop_after=1)
+    assert abs(a[0] - pred[0]) < 3e-4, (a, pred)
+    _, e, inc, e_law, i_law = nb.gas_damping(lib, stop_after=1)
+    assert abs(e[0]/e_law[0] - 1.0) < 3e-4 and abs(inc[0]/i_law[0] - 1.0) < 3e-4, (e, e_law, inc, i_law)
+    if ref is not None:
+        _, er, incr, _, _ = nb.gas_damping(ref, stop_after=1)
+        assert abs(e[0]/er[0] - 1.0) < 1e-10 and abs(inc[0]/incr[0] - 1.0) < 1e-10, (e, er, inc, incr)
+
+
 @pytest.mark.parametrize("case", ["one_active_massive_asteroids", "three_active_massless", "stacked_with_yarkovsky"])
 def test_gr_1pn(built, case):
     """`gr` (reference src/gr.c): device reduction + host part for the <= 8 active bodies + device sweep.

@@ -139,6 +139,38 @@ def test_gr_notebook_known_answers(built):
     nb.check(*nb.run(oracle.ref_lib()))
 
 
+def test_damping_notebook_laws(built):
+    """Pins the oracle's damping forces -- the reference's modify_orbits_forces.c, gas_damping_timescale.c,
+    type_I_migration.c and inner_disk_edge.c compiled in place, on top of the RESTATED reb_orbit_from_particle elements
+    and rebx_com_force frames (default: JACOBI) -- to the analytic laws the reference publishes for them
+    (ipython_examples/Migration.ipynb, InnerDiskEdge.ipynb, TypeIMigration.ipynb, GasDampingTimescale.ipynb; plotted there
+    against real REBOUND, no printed digits): tests/damping_notebooks.py.  Trajectory-level, at the accuracy of the laws
+    (measured: 7e-8 ... 1e-4), for the effects whose parity is otherwise unpinned at the REBOUND boundary."""
+    from oracle import oracle
+    import damping_notebooks as nb
+    if not oracle.have_ref():
+        pytest.skip("needs oracle/_ref")
+    lib = oracle.ref_lib()
+    # a(t) = a0 e^(t/tau_a), two planets; the outer one is sampled within its 5 orbits (osculating a wobbles by ~e P/tau)
+    _, a, pred = nb.migration(lib)
+    assert np.max(np.abs(a[0]/pred[0] - 1.0)) < 5e-4, a[0]/pred[0] - 1.0                 # measured 1.4e-4
+    assert np.max(np.abs(a[1]/pred[1] - 1.0)) < 1e-2, a[1]/pred[1] - 1.0                 # measured 4.6e-3
+    # modify_orbits_forces + planet trap: e-fold decay, then the planet stops inside the edge's band
+    _, a, pred = nb.inner_disk_edge(lib)
+    moving = pred > 0.1
+    assert np.max(np.abs(a[moving]/pred[moving] - 1.0)) < 1e-6, a/pred - 1.0             # measured 7e-8
+    assert np.all(np.abs(a[~moving] - 0.1) <= 0.1*0.02), a                                # stops at 0.1012
+    # type_I_migration + planet trap: constant da/dt, then the planet stops inside the edge's band
+    _, a, pred, edge, width = nb.type_I(lib)
+    moving = pred > edge
+    assert np.max(np.abs(a[moving] - pred[moving])) < 3e-4, a - pred                     # measured 1.2e-4 AU
+    assert np.all(np.abs(a[~moving] - edge) <= edge*width), a                             # stops at 0.1010
+    # gas_damping_timescale: e'/e = -1/tau, i'/i = -1/(2 tau), tau(e, i) of Dawson et al. 2016 eq. 16
+    _, e, inc, e_law, i_law = nb.gas_damping(lib)
+    assert np.max(np.abs(e/e_law - 1.0)) < 3e-4 and np.max(np.abs(inc/i_law - 1.0)) < 3e-4, (e/e_law - 1.0, inc/i_law - 1.0)   # measured 1e-4
+    assert e[-1] < 0.97*0.05 and inc[-1] < 0.99*5*np.pi/180                               # and it did damp
+
+
 @pytest.mark.parametrize("coordinates", ["JACOBI", "BARYCENTRIC"])
 @pytest.mark.parametrize("base", ["zero", "gravity"])
 def test_linear_com_oracle_against_the_reference_loops(built, coordinates, base):
