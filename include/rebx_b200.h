@@ -336,6 +336,7 @@ void rebx_b200_session_free(rebx_b200_session* s);
  *   REBX_B200_MULTI_MIN=<particles>      smallest ensemble worth splitting (default 2^20)
  *   REBX_B200_MATH=tolerance             REBX_B200_PASS_TOLERANCE for every pass
  *   REBX_B200_JACOBI=staged              rebx_b200_launch_jacobi keeps the staged pipeline (default: one cooperative launch)
+ *   REBX_B200_D2H=acc|accm               device->host as a 2-D copy of the accelerations only (measured slower than whole records; off)
  *   REBX_B200_CHUNK, REBX_B200_ZEROCOPY_MAX, REBX_B200_PARANOID   pipeline chunk, zero-copy threshold, rebuild tables every call */
 struct rebx_extras;
 struct rebx_force;

@@ -146,6 +146,7 @@ struct DeviceContext {
     bool chunk_from_env = false;
     bool paranoid = false;
     bool tolerance = false;                 // REBX_B200_MATH=tolerance: kernels_tol.cu for the stacks it covers
+    int d2h_width = 0;                      // REBX_B200_D2H=acc|accm: device->host as a 2-D copy of 24 (ax ay az) or 32 (+ m) bytes per record; 0 = whole records
 
     void unregister_host() {
         if (registered_ptr) { cudaHostUnregister(registered_ptr); cudaGetLastError(); }
@@ -409,6 +410,12 @@ static DeviceContext* ensure_ctx(Side* side, std::string& why) {
     if (const char* p = std::getenv("REBX_B200_PARANOID")) ctx->paranoid = std::atoi(p) != 0;
     if (const char* m = std::getenv("REBX_B200_MATH")) ctx->tolerance = (m[0] == 't' || m[0] == 'T');
     if (const char* z = std::getenv("REBX_B200_ZEROCOPY_MAX")) { long v = std::atol(z); if (v >= 0) ctx->zero_copy_max = (size_t)v; }
+    if (const char* z = std::getenv("REBX_B200_D2H")) {
+        // option (off by default): only the accelerations travel back -- the copy engine moves rows of 24 or
+        // 32 bytes out of the 128-byte records instead of the whole records, which takes bytes off the link the uploads contend for
+        if (std::strcmp(z, "acc") == 0) ctx->d2h_width = 24;
+        else if (std::strcmp(z, "accm") == 0 && offsetof(struct reb_particle, m) == offsetof(struct reb_particle, ax) + 24) ctx->d2h_width = 32;
+    }
     if (const char* z = std::getenv("REBX_B200_MULTI_MIN")) { long v = std::atol(z); if (v >= 2) ctx->multi_min = (size_t)v; }
     ctx->ready = true;
     side->dev = std::move(ctx);
@@ -903,8 +910,16 @@ static void run_segment(struct reb_simulation* sim, struct rebx_force** forces, 
             e0 = e1;
         }
         REBXB_CUDA((cudaError_t)rebx_b200_pack_acc_aos(aos_in, &L, &st, s, &launches), "packing accelerations");
-        if (!zc) REBXB_CUDA(copy_page_split(particles + c0, D.aos[b].p, bytes, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
-        ctx->stats.d2h_bytes += zc ? n*3*sizeof(double) : bytes;
+        if (!zc && ctx->d2h_width > 0) {
+            const size_t off = offsetof(struct reb_particle, ax);
+            REBXB_CUDA(cudaMemcpy2DAsync(reinterpret_cast<char*>(particles + c0) + off, sizeof(struct reb_particle),
+                                         static_cast<const char*>(D.aos[b].p) + off, sizeof(struct reb_particle),
+                                         (size_t)ctx->d2h_width, n, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
+            ctx->stats.d2h_bytes += n*(size_t)ctx->d2h_width;
+        } else {
+            if (!zc) REBXB_CUDA(copy_page_split(particles + c0, D.aos[b].p, bytes, cudaMemcpyDeviceToHost, s), "copying accelerations to the host");
+            ctx->stats.d2h_bytes += zc ? n*3*sizeof(double) : bytes;
+        }
     }
     for (size_t d = 0; d < ndev; d++) {
         DevSlot& D = *ctx->devs[d];
